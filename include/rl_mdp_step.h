@@ -1,0 +1,375 @@
+/*
+ * rl_mdp_step.h - C-ABI of the B200-native per-step MDP pipeline (observation / reward /
+ * termination / command / joint-position-action terms of robot_lab's velocity-locomotion tasks).
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference; V/ =
+ * source/robot_lab/robot_lab/tasks/manager_based/locomotion/velocity/; [IL] = IsaacLab v2.3.2 code the
+ * reference calls but does not vendor, restated in SURVEY.md Appendix A):
+ *
+ *   rl_process_action   ActionManager.process_action + JointPositionAction.process_actions [IL]
+ *                       (configured at V/velocity_env_cfg.py:124-126, GO2/rough_env_cfg.py:51-53)
+ *   rl_step             TerminationManager.compute + RewardManager.compute + CommandManager.compute +
+ *                       ObservationManager.compute [IL] looping over the term functions of
+ *                       V/mdp/rewards.py:22-687, V/mdp/observations.py:17-35, V/mdp/commands.py:22-85 and the
+ *                       upstream terms wired at V/velocity_env_cfg.py:134-254,379-664, in the order of
+ *                       ManagerBasedRLEnv.step() [IL], plus reset_buf.nonzero()
+ *   rl_reset_envs       the manager part of ManagerBasedRLEnv._reset_idx [IL]: episode-sum / metric logging
+ *                       means, zeroing, command resample (V/mdp/commands.py:43-47), action reset
+ *   rl_term_eval        one reward term function called on its own: func(env, **params) -> Tensor[N]
+ *                       (term protocol, V/mdp/rewards.py:22 ff.)
+ *
+ * Conventions: every function returns 0 on success or a negative RL_E* code; rl_last_error() gives the
+ * message (thread-local). All data pointers are DEVICE pointers borrowed for the duration of the call;
+ * the caller (PyTorch) owns every tensor, the library owns only the opaque context. Launches are
+ * asynchronous on the given cudaStream_t and never synchronise. One context per GPU; a context is not
+ * thread-safe, different contexts are independent. No torch types cross this boundary.
+ */
+#ifndef RL_MDP_STEP_H_
+#define RL_MDP_STEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_ABI_VERSION 3
+
+#define RL_MAX_JOINTS 64
+#define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
+#define RL_MAX_TIME_BODIES 16   /* bodies in the air/contact-time tensors                       */
+#define RL_MAX_ASSET_BODIES 16  /* bodies in the body_pos_w / body_lin_vel_w tensors            */
+#define RL_MAX_REWARD_TERMS 48
+#define RL_MAX_OBS_TERMS 12
+#define RL_MAX_DONE_TERMS 8
+#define RL_MAX_IDX 32
+#define RL_NUM_OBS_GROUPS 2     /* 0 = policy, 1 = critic                                        */
+#define RL_NUM_CMD_UNIFORMS 7   /* time_left, vx, vy, wz, heading, is_heading, is_standing       */
+
+enum RlError {
+  RL_OK = 0,
+  RL_EINVAL = -1,   /* bad argument / inconsistent spec */
+  RL_ECUDA = -2,    /* CUDA runtime error               */
+  RL_ENOMEM = -3,
+  RL_EUNSUPPORTED = -4
+};
+
+/* Reward term kinds. The comment names the reference function each one restates. */
+enum RlRewardType {
+  RL_REW_NONE = 0,
+  RL_REW_IS_TERMINATED = 1,              /* [IL] mdp.is_terminated                               */
+  RL_REW_LIN_VEL_Z_L2 = 2,               /* V/mdp/rewards.py:647                                  */
+  RL_REW_ANG_VEL_XY_L2 = 3,              /* :656                                                  */
+  RL_REW_FLAT_ORIENTATION_L2 = 4,        /* :678                                                  */
+  RL_REW_BASE_HEIGHT_L2 = 5,             /* :616 (sensor_cfg=None branch only)                    */
+  RL_REW_JOINT_TORQUES_L2 = 6,           /* [IL] mdp.joint_torques_l2                             */
+  RL_REW_JOINT_VEL_L2 = 7,               /* [IL] mdp.joint_vel_l2                                 */
+  RL_REW_JOINT_ACC_L2 = 8,               /* [IL] mdp.joint_acc_l2                                 */
+  RL_REW_JOINT_DEVIATION_L1 = 9,         /* [IL] mdp.joint_deviation_l1                           */
+  RL_REW_JOINT_POS_LIMITS = 10,          /* [IL] mdp.joint_pos_limits                             */
+  RL_REW_JOINT_VEL_LIMITS = 11,          /* [IL] mdp.joint_vel_limits                             */
+  RL_REW_JOINT_POWER = 12,               /* :81                                                   */
+  RL_REW_STAND_STILL = 13,               /* :93                                                   */
+  RL_REW_JOINT_POS_PENALTY = 14,         /* :107                                                  */
+  RL_REW_JOINT_MIRROR = 15,              /* :259                                                  */
+  RL_REW_ACTION_MIRROR = 16,             /* :281                                                  */
+  RL_REW_ACTION_SYNC = 17,               /* :306                                                  */
+  RL_REW_ACTION_RATE_L2 = 18,            /* [IL] mdp.action_rate_l2                               */
+  RL_REW_UNDESIRED_CONTACTS = 19,        /* :665                                                  */
+  RL_REW_CONTACT_FORCES = 20,            /* [IL] mdp.contact_forces                               */
+  RL_REW_TRACK_LIN_VEL_XY_EXP = 21,      /* :22                                                   */
+  RL_REW_TRACK_ANG_VEL_Z_EXP = 22,       /* :38                                                   */
+  RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP = 23, /* :51                                              */
+  RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP = 24, /* :69                                                   */
+  RL_REW_FEET_AIR_TIME = 25,             /* :340                                                  */
+  RL_REW_FEET_AIR_TIME_POSITIVE_BIPED = 26, /* :363                                               */
+  RL_REW_FEET_AIR_TIME_VARIANCE = 27,    /* :386                                                  */
+  RL_REW_FEET_GAIT = 28,                 /* :156-256 (GaitReward)                                 */
+  RL_REW_FEET_CONTACT = 29,              /* :400                                                  */
+  RL_REW_FEET_CONTACT_WITHOUT_CMD = 30,  /* :416                                                  */
+  RL_REW_FEET_STUMBLE = 31,              /* :428                                                  */
+  RL_REW_FEET_SLIDE = 32,                /* :557                                                  */
+  RL_REW_FEET_HEIGHT = 33,               /* :507                                                  */
+  RL_REW_FEET_HEIGHT_BODY = 34,          /* :527                                                  */
+  RL_REW_FEET_DISTANCE_Y_EXP = 35,       /* :439                                                  */
+  RL_REW_FEET_DISTANCE_XY_EXP = 36,      /* :464                                                  */
+  RL_REW_UPWARD = 37,                    /* :608                                                  */
+  RL_REW_WHEEL_VEL_PENALTY = 38,         /* :132                                                  */
+  RL_REW_TYPE_COUNT = 39
+};
+
+/*
+ * One reward term: func + weight + params of the reference's RewardTermCfg, with every name/regex
+ * already resolved to indices. Parameter slots p[] per type:
+ *   TRACK_*_EXP                    p0 = std**2
+ *   STAND_STILL                    p0 = command_threshold
+ *   JOINT_POS_PENALTY              p0 = stand_still_scale, p1 = velocity_threshold, p2 = command_threshold
+ *   JOINT_MIRROR / ACTION_MIRROR   idx_a[i] <-> idx_b[i] (n_idx joint pairs), p0 = 1/len(mirror_joints)
+ *   ACTION_SYNC                    idx_a = action columns, grouped: idx_b[g] = group start in idx_a,
+ *                                  idx_c[g] = group size, n_idx = #groups, p0 = 1/len(joint_groups)
+ *   UNDESIRED_CONTACTS             p0 = threshold, body_mask over history bodies
+ *   CONTACT_FORCES                 p0 = threshold, body_mask
+ *   FEET_AIR_TIME                  p0 = threshold, idx_a = feet in time-body space
+ *   FEET_AIR_TIME_POSITIVE_BIPED   p0 = threshold, idx_a
+ *   FEET_AIR_TIME_VARIANCE         idx_a
+ *   FEET_GAIT                      p0 = std, p1 = max_err**2, p2 = velocity_threshold, p3 = command_threshold,
+ *                                  idx_a[0..3] = {pair0[0], pair0[1], pair1[0], pair1[1]} in time-body space
+ *   FEET_CONTACT                   p0 = expect_contact_num, idx_a
+ *   FEET_CONTACT_WITHOUT_CMD       idx_a
+ *   FEET_STUMBLE                   idx_c = feet in history-body space
+ *   FEET_SLIDE                     idx_c = feet (history space, contact), idx_b = feet (asset-body space, velocity)
+ *   FEET_HEIGHT / _BODY            p0 = target_height, p1 = tanh_mult, idx_b
+ *   FEET_DISTANCE_Y_EXP            p0 = stance_width, p1 = std**2, idx_b
+ *   FEET_DISTANCE_XY_EXP           p0 = stance_width, p1 = stance_length, p2 = std**2, idx_b (4 feet)
+ *   BASE_HEIGHT_L2                 p0 = target_height
+ *   JOINT_VEL_LIMITS               p0 = soft_ratio
+ *   WHEEL_VEL_PENALTY              p0 = velocity_threshold, p1 = command_threshold, idx_a = wheel bodies in
+ *                                  time-body space, idx_b = matching wheel joints (native ids)
+ *   joint terms                    joint_mask = native joint ids the term sums over
+ */
+typedef struct RlRewardTerm {
+  int32_t type;
+  float weight;
+  float p[6];
+  uint64_t joint_mask;
+  uint64_t body_mask;
+  int32_t n_idx;
+  int32_t reserved;
+  uint8_t idx_a[RL_MAX_IDX];
+  uint8_t idx_b[RL_MAX_IDX];
+  uint8_t idx_c[RL_MAX_IDX];
+} RlRewardTerm;
+
+enum RlObsType {
+  RL_OBS_NONE = 0,
+  RL_OBS_BASE_LIN_VEL = 1,        /* [IL] root_lin_vel_b                                   */
+  RL_OBS_BASE_ANG_VEL = 2,        /* [IL] root_ang_vel_b                                   */
+  RL_OBS_PROJECTED_GRAVITY = 3,   /* [IL] projected_gravity_b                              */
+  RL_OBS_GENERATED_COMMANDS = 4,  /* [IL] command_manager.get_command                      */
+  RL_OBS_JOINT_POS_REL = 5,       /* [IL] joint_pos - default_joint_pos, ids[] order       */
+  RL_OBS_JOINT_VEL_REL = 6,       /* [IL] joint_vel - default_joint_vel, ids[] order       */
+  RL_OBS_LAST_ACTION = 7,         /* [IL] action_manager.action                            */
+  RL_OBS_HEIGHT_SCAN = 8,         /* [IL] sensor z - ray hit z - offset (p0 = offset)      */
+  RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL = 9, /* V/mdp/observations.py:17, zero_mask = wheel columns */
+  RL_OBS_PHASE = 10,              /* V/mdp/observations.py:30, p0 = cycle_time             */
+  RL_OBS_TYPE_COUNT = 11
+};
+
+/* ObservationTermCfg: func -> clone -> (+noise) -> clip -> scale. */
+typedef struct RlObsTerm {
+  int32_t type;
+  int32_t dim;
+  int32_t has_noise;
+  float noise_lo, noise_hi;
+  int32_t has_clip;
+  float clip_lo, clip_hi;
+  int32_t has_scale;
+  float scale;
+  float p[2];
+  uint64_t zero_mask;             /* columns forced to 0 (JOINT_POS_REL_WITHOUT_WHEEL) */
+  uint8_t ids[RL_MAX_JOINTS];     /* joint terms: column c reads native joint ids[c]   */
+} RlObsTerm;
+
+typedef struct RlObsGroup {
+  int32_t n_terms;
+  int32_t dim;                    /* sum of term dims = row width */
+  int32_t enable_corruption;
+  int32_t reserved;
+  RlObsTerm terms[RL_MAX_OBS_TERMS];
+} RlObsGroup;
+
+enum RlDoneType {
+  RL_DONE_NONE = 0,
+  RL_DONE_TIME_OUT = 1,               /* [IL] episode_length_buf >= max_episode_length        */
+  RL_DONE_TERRAIN_OUT_OF_BOUNDS = 2,  /* [IL] p0 = 0.5*W - buf, p1 = 0.5*H - buf, p2 = is_generator */
+  RL_DONE_ILLEGAL_CONTACT = 3,        /* [IL] p0 = threshold, body_mask                       */
+  RL_DONE_TYPE_COUNT = 4
+};
+
+typedef struct RlDoneTerm {
+  int32_t type;
+  int32_t time_out;                   /* 1 -> truncated, 0 -> terminated */
+  float p[4];
+  uint64_t body_mask;
+} RlDoneTerm;
+
+/* UniformThresholdVelocityCommandCfg (V/velocity_env_cfg.py:106-117, V/mdp/commands.py:22-92). */
+typedef struct RlCommandCfg {
+  float resampling_time_lo, resampling_time_hi;
+  float rel_standing_envs, rel_heading_envs;
+  int32_t heading_command;
+  float heading_control_stiffness;
+  float lin_vel_x_lo, lin_vel_x_hi;
+  float lin_vel_y_lo, lin_vel_y_hi;
+  float ang_vel_z_lo, ang_vel_z_hi;
+  float heading_lo, heading_hi;
+  float small_cmd_threshold;          /* 0.2, V/mdp/commands.py:47 */
+  float max_command_step;             /* resampling_time_hi / step_dt [IL] */
+} RlCommandCfg;
+
+/* JointPositionActionCfg: target = clamp(action * scale + offset, clip) on joints joint_ids[a]. */
+typedef struct RlActionCfg {
+  int32_t n_actions;
+  int32_t has_clip;
+  uint8_t joint_ids[RL_MAX_JOINTS];
+  float scale[RL_MAX_JOINTS];
+  float offset[RL_MAX_JOINTS];
+  float clip_lo[RL_MAX_JOINTS];
+  float clip_hi[RL_MAX_JOINTS];
+} RlActionCfg;
+
+/* The flat, fully resolved description of one task's MDP step (host POD, copied at rl_ctx_create). */
+typedef struct RlStepSpec {
+  int32_t abi_version;                /* must be RL_ABI_VERSION */
+  int32_t num_joints;                 /* J  */
+  int32_t num_hist_bodies;            /* B  : bodies in net_forces_w_history                 */
+  int32_t hist_len;                   /* T  */
+  int32_t num_time_bodies;            /* Bt : bodies in the air/contact-time tensors         */
+  int32_t num_asset_bodies;           /* Ba : bodies in body_pos_w / body_lin_vel_w          */
+  int32_t num_rays;                   /* R  (0 = no height scanner)                          */
+  int32_t num_reward_terms;           /* K  */
+  int32_t num_done_terms;
+  int32_t max_episode_length;         /* ceil(episode_length_s / step_dt)                    */
+  float step_dt;
+  float contact_time_abs_tol;         /* 1e-8, ContactSensor.compute_first_contact [IL]      */
+  float default_joint_pos[RL_MAX_JOINTS];
+  float default_joint_vel[RL_MAX_JOINTS];
+  float soft_pos_limit_lo[RL_MAX_JOINTS];
+  float soft_pos_limit_hi[RL_MAX_JOINTS];
+  float soft_vel_limit[RL_MAX_JOINTS];
+  RlRewardTerm rewards[RL_MAX_REWARD_TERMS];
+  RlDoneTerm dones[RL_MAX_DONE_TERMS];
+  RlObsGroup obs[RL_NUM_OBS_GROUPS];
+  RlCommandCfg command;
+  RlActionCfg action;
+} RlStepSpec;
+
+/*
+ * A strided view of one per-env field: element (env, comp) lives at ptr[env*env_stride + comp*comp_stride]
+ * (strides in ELEMENTS). SoA [C][N] is {1, N}; AoS [N][C] is {C, 1}. Multi-index fields flatten their
+ * trailing dims row-major into comp (history: comp = (t*B + b)*3 + xyz; body vectors: comp = b*3 + xyz).
+ */
+typedef struct RlField {
+  void* ptr;
+  int64_t env_stride;
+  int64_t comp_stride;
+} RlField;
+
+/* Read-only per-step state produced by physics + sensors. fp32 unless noted. */
+typedef struct RlStateView {
+  RlField root_pos_w;            /* 3                                       */
+  RlField root_quat_w;           /* 4  (w, x, y, z)                         */
+  RlField root_lin_vel_w;        /* 3                                       */
+  RlField root_ang_vel_w;        /* 3                                       */
+  RlField joint_pos;             /* J  native joint order                   */
+  RlField joint_vel;             /* J                                       */
+  RlField joint_acc;             /* J                                       */
+  RlField applied_torque;        /* J                                       */
+  RlField net_forces_w_history;  /* T*B*3, index 0 of T = newest            */
+  RlField current_air_time;      /* Bt                                      */
+  RlField last_air_time;         /* Bt                                      */
+  RlField current_contact_time;  /* Bt                                      */
+  RlField last_contact_time;     /* Bt                                      */
+  RlField body_pos_w;            /* Ba*3                                    */
+  RlField body_lin_vel_w;        /* Ba*3                                    */
+  RlField ray_hits_z;            /* R   (z of ray_hits_w)                   */
+  RlField ray_sensor_pos_z;      /* 1   (z of the ray caster's pos_w)       */
+} RlStateView;
+
+/* Manager-owned state that the step reads AND writes. */
+typedef struct RlMdpState {
+  RlField action;                /* A   action_manager.action       (read by rl_step)    */
+  RlField prev_action;           /* A   action_manager.prev_action  (read by rl_step)    */
+  RlField command;               /* 3   vel_command_b                                      */
+  RlField heading_target;        /* 1                                                      */
+  RlField time_left;             /* 1                                                      */
+  RlField is_heading_env;        /* 1   uint8                                              */
+  RlField is_standing_env;       /* 1   uint8                                              */
+  RlField metric_error_vel_xy;   /* 1                                                      */
+  RlField metric_error_vel_yaw;  /* 1                                                      */
+  RlField episode_length;        /* 1   int32 (int64 at the torch boundary)                */
+  RlField episode_sums;          /* K   reward_manager._episode_sums                       */
+} RlMdpState;
+
+/* Outputs of one step. Any pointer may be NULL to skip that output. */
+typedef struct RlStepOut {
+  float* obs[RL_NUM_OBS_GROUPS]; /* [N, obs_pitch[g]] rows                                 */
+  int64_t obs_pitch[RL_NUM_OBS_GROUPS]; /* row pitch in elements (>= group dim)            */
+  float* reward;                 /* [N]                                                    */
+  uint8_t* terminated;           /* [N]                                                    */
+  uint8_t* truncated;            /* [N]                                                    */
+  uint8_t* done_bits;            /* [N] bit i = done term i fired                          */
+  RlField step_reward;           /* K  reward_manager._step_reward (value / dt)            */
+  int32_t* reset_ids;            /* [N] ascending ids with terminated|truncated            */
+  int32_t* n_reset;              /* [1]                                                    */
+} RlStepOut;
+
+/* Which manager phases a launch evaluates (bit flags). */
+enum RlPhase {
+  RL_PHASE_DONES = 1,       /* episode_length += 1, termination terms                       */
+  RL_PHASE_REWARDS = 2,     /* reward terms, episode sums, step reward                      */
+  RL_PHASE_COMMAND = 4,     /* CommandTerm.compute: metrics, timer, resample, heading update*/
+  RL_PHASE_OBS = 8,         /* observation groups                                           */
+  RL_PHASE_COMPACT = 16,    /* reset id compaction (ascending)                              */
+  RL_PHASE_SKIP_DONE_ENVS = 32, /* COMMAND/OBS only for envs that are not done this step
+                                   (they are refreshed after the external reset instead)   */
+  RL_PHASE_ALL = 31
+};
+
+/* Random inputs. NULL pointers select the in-kernel Philox4x32-10 stream (seed, step, env). */
+typedef struct RlRandom {
+  uint64_t seed;
+  uint64_t step;                 /* step counter: part of the Philox counter                */
+  int64_t env_id_offset;         /* global id of env 0 of this shard (multi-GPU)            */
+  const float* cmd_uniforms;     /* [RL_NUM_CMD_UNIFORMS][N] U[0,1) or NULL                 */
+  const float* obs_uniforms[RL_NUM_OBS_GROUPS]; /* [N, group dim] U[0,1) or NULL           */
+} RlRandom;
+
+/* Logging reductions produced at reset (extras["log"] of the reference [IL]). */
+typedef struct RlResetLog {
+  float* episode_sum_mean;       /* [K]  mean over reset ids of episode_sums (caller divides by
+                                         max_episode_length_s as RewardManager.reset does)  */
+  float* done_term_count;        /* [RL_MAX_DONE_TERMS] count over reset ids                 */
+  float* metric_mean;            /* [2]  error_vel_xy, error_vel_yaw means                   */
+} RlResetLog;
+
+typedef struct RlCtx RlCtx;
+
+int rl_abi_version(void);
+const char* rl_last_error(void);
+/* sizeof() of an ABI struct by name ("RlStepSpec", "RlRewardTerm", ...), -1 if unknown: lets a foreign-
+ * language binding verify its mirror of the layouts before the first call. */
+int64_t rl_struct_sizeof(const char* name);
+
+int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
+void rl_ctx_destroy(RlCtx* ctx);
+
+/* Tuning knobs (envs per CTA, lanes per env). 0 = library default. */
+int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env);
+
+/* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */
+int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
+                      const RlField* joint_target /* J, native order; columns not driven are untouched */,
+                      void* stream);
+
+/* The fused step over envs [0, num_envs), or over env_ids[0 .. *n_env_ids) when env_ids != NULL
+ * (n_env_ids is a DEVICE pointer so that no host sync is needed after the reset compaction). */
+int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpState* mdp,
+            const RlStepOut* out, const RlRandom* rnd, uint32_t phases,
+            const int32_t* env_ids, const int32_t* n_env_ids, void* stream);
+
+/* Manager-side reset of env_ids[0 .. *n_env_ids): log means, zero episode sums / metrics / actions /
+ * episode length, resample the command (CommandTerm.reset [IL] -> V/mdp/commands.py:43-47). */
+int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uint8_t* done_bits,
+                  const RlRandom* rnd, const RlResetLog* log, const int32_t* env_ids,
+                  const int32_t* n_env_ids, void* stream);
+
+/* One reward term evaluated alone (raw value, no weight, no dt): the term-function protocol. */
+int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const RlStateView* state,
+                 const RlMdpState* mdp, const uint8_t* terminated /* may be NULL */, float* out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL_MDP_STEP_H_ */

@@ -1,0 +1,274 @@
+"""Robot constants for the MDP step (joint / body tables, default pose, limits, action scales).
+
+Only the *constants* the MDP terms read are kept here - spawning, meshes and actuator models
+belong to the physics side, which is out of scope.
+
+Sources (reference, file:line):
+  * A1   : source/robot_lab/robot_lab/assets/unitree.py:19-65,  a1_description/urdf/a1.urdf:363-895
+  * Go2  : source/robot_lab/robot_lab/assets/unitree.py:71-117, go2_description/urdf/go2_description.urdf:35-757
+  * G1-29: source/robot_lab/robot_lab/assets/unitree.py:447-636, g1_description/urdf/g1_29dof_rev_1_0.urdf:94-1055
+
+Joint / body orders are the articulation's *native* (breadth-first over the kinematic tree)
+orders that IsaacLab exposes as ``asset.joint_names`` / ``asset.body_names``; the task
+configuration uses a different explicit order for observations and actions
+(GO2/rough_env_cfg.py:22-27), so the kernels carry a permutation table.
+"""
+
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+
+
+def _match_first(patterns: dict[str, float], name: str, default: float | None = None) -> float:
+    hits = [v for k, v in patterns.items() if re.fullmatch(k, name)]
+    if not hits:
+        if default is None:
+            raise KeyError(f"no pattern matches '{name}'")
+        return default
+    if len(hits) > 1 and len(set(hits)) > 1:
+        raise ValueError(f"ambiguous patterns for '{name}'")
+    return hits[0]
+
+
+@dataclass(frozen=True)
+class RobotAsset:
+    """Constant tables of one articulation, in native order."""
+
+    name: str
+    joint_names: tuple[str, ...]
+    body_names: tuple[str, ...]
+    joint_limits: dict[str, tuple[float, float]]
+    default_joint_pos_patterns: dict[str, float]
+    joint_vel_limit_patterns: dict[str, float]
+    soft_joint_pos_limit_factor: float = 0.9
+    init_root_height: float = 0.38
+    action_scale_patterns: dict[str, float] = field(default_factory=dict)
+
+    # -- derived tables -------------------------------------------------------------------
+    @property
+    def num_joints(self) -> int:
+        return len(self.joint_names)
+
+    @property
+    def num_bodies(self) -> int:
+        return len(self.body_names)
+
+    def default_joint_pos(self) -> list[float]:
+        return [_match_first(self.default_joint_pos_patterns, n, 0.0) for n in self.joint_names]
+
+    def default_joint_vel(self) -> list[float]:
+        return [0.0] * self.num_joints
+
+    def joint_vel_limits(self) -> list[float]:
+        return [_match_first(self.joint_vel_limit_patterns, n) for n in self.joint_names]
+
+    def soft_joint_pos_limits(self) -> list[tuple[float, float]]:
+        """mid -/+ 0.5 * range * factor (IsaacLab ArticulationData)."""
+        out = []
+        for n in self.joint_names:
+            lo, hi = self.joint_limits[n]
+            mid = (lo + hi) * 0.5
+            rng = hi - lo
+            out.append((mid - 0.5 * rng * self.soft_joint_pos_limit_factor,
+                        mid + 0.5 * rng * self.soft_joint_pos_limit_factor))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Quadrupeds
+# ---------------------------------------------------------------------------------------------
+_LEGS_BFS = ("FL", "FR", "RL", "RR")
+
+_QUAD_JOINTS = tuple(f"{leg}_{part}_joint" for part in ("hip", "thigh", "calf") for leg in _LEGS_BFS)
+
+_QUAD_DEFAULT_POSE = {  # assets/unitree.py:44-50 (A1) and :96-102 (Go2) - identical tables
+    ".*L_hip_joint": 0.0,
+    ".*R_hip_joint": -0.0,
+    "F.*_thigh_joint": 0.8,
+    "R.*_thigh_joint": 0.8,
+    ".*_calf_joint": -1.5,
+}
+
+UNITREE_GO2 = RobotAsset(
+    name="unitree_go2",
+    joint_names=_QUAD_JOINTS,
+    # base + Head_upper/Head_lower (dont_collapse) + 12 leg links + 4 dont_collapse feet = 19
+    body_names=(
+        "base",
+        "FL_hip", "FR_hip", "Head_upper", "RL_hip", "RR_hip",
+        "FL_thigh", "FR_thigh", "Head_lower", "RL_thigh", "RR_thigh",
+        "FL_calf", "FR_calf", "RL_calf", "RR_calf",
+        "FL_foot", "FR_foot", "RL_foot", "RR_foot",
+    ),
+    joint_limits={
+        **{f"{leg}_hip_joint": (-1.0472, 1.0472) for leg in _LEGS_BFS},
+        "FL_thigh_joint": (-1.5708, 3.4907), "FR_thigh_joint": (-1.5708, 3.4907),
+        "RL_thigh_joint": (-0.5236, 4.5379), "RR_thigh_joint": (-0.5236, 4.5379),
+        **{f"{leg}_calf_joint": (-2.7227, -0.83776) for leg in _LEGS_BFS},
+    },
+    default_joint_pos_patterns=_QUAD_DEFAULT_POSE,
+    joint_vel_limit_patterns={".*": 30.0},  # DCMotorCfg.velocity_limit, assets/unitree.py:111
+    init_root_height=0.38,
+)
+
+UNITREE_A1 = RobotAsset(
+    name="unitree_a1",
+    joint_names=_QUAD_JOINTS,
+    # trunk + 12 leg links + 4 dont_collapse feet = 17
+    body_names=(
+        "trunk",
+        "FL_hip", "FR_hip", "RL_hip", "RR_hip",
+        "FL_thigh", "FR_thigh", "RL_thigh", "RR_thigh",
+        "FL_calf", "FR_calf", "RL_calf", "RR_calf",
+        "FL_foot", "FR_foot", "RL_foot", "RR_foot",
+    ),
+    joint_limits={
+        **{f"{leg}_hip_joint": (-0.802851455917, 0.802851455917) for leg in _LEGS_BFS},
+        **{f"{leg}_thigh_joint": (-1.0471975512, 4.18879020479) for leg in _LEGS_BFS},
+        **{f"{leg}_calf_joint": (-2.69653369433, -0.916297857297) for leg in _LEGS_BFS},
+    },
+    default_joint_pos_patterns=_QUAD_DEFAULT_POSE,
+    joint_vel_limit_patterns={".*": 21.0},  # assets/unitree.py:59
+    init_root_height=0.38,
+)
+
+# ---------------------------------------------------------------------------------------------
+# Unitree G1, 29 DoF (the reference's humanoid; BASELINE.json's "37 DoF" label is IsaacLab's own
+# G1 with dexterous hands - a J=37 synthetic variant is provided below to exercise J > 32)
+# ---------------------------------------------------------------------------------------------
+_ARMATURE_5020 = 0.003609725
+_ARMATURE_7520_14 = 0.010177520
+_ARMATURE_7520_22 = 0.025101925
+_ARMATURE_4010 = 0.00425
+_NATURAL_FREQ = 10 * 2.0 * 3.1415926535
+_STIFFNESS_5020 = _ARMATURE_5020 * _NATURAL_FREQ**2
+_STIFFNESS_7520_14 = _ARMATURE_7520_14 * _NATURAL_FREQ**2
+_STIFFNESS_7520_22 = _ARMATURE_7520_22 * _NATURAL_FREQ**2
+_STIFFNESS_4010 = _ARMATURE_4010 * _NATURAL_FREQ**2
+
+# (effort_limit_sim, stiffness) per joint-name pattern, assets/unitree.py:505-621
+_G1_EFFORT_STIFFNESS = {
+    ".*_hip_yaw_joint": (88.0, _STIFFNESS_7520_14),
+    ".*_hip_roll_joint": (139.0, _STIFFNESS_7520_22),
+    ".*_hip_pitch_joint": (88.0, _STIFFNESS_7520_14),
+    ".*_knee_joint": (139.0, _STIFFNESS_7520_22),
+    ".*_ankle_pitch_joint": (50.0, 2.0 * _STIFFNESS_5020),
+    ".*_ankle_roll_joint": (50.0, 2.0 * _STIFFNESS_5020),
+    "waist_roll_joint": (50.0, 2.0 * _STIFFNESS_5020),
+    "waist_pitch_joint": (50.0, 2.0 * _STIFFNESS_5020),
+    "waist_yaw_joint": (88.0, _STIFFNESS_7520_14),
+    ".*_shoulder_pitch_joint": (25.0, _STIFFNESS_5020),
+    ".*_shoulder_roll_joint": (25.0, _STIFFNESS_5020),
+    ".*_shoulder_yaw_joint": (25.0, _STIFFNESS_5020),
+    ".*_elbow_joint": (25.0, _STIFFNESS_5020),
+    ".*_wrist_roll_joint": (25.0, _STIFFNESS_5020),
+    ".*_wrist_pitch_joint": (5.0, _STIFFNESS_4010),
+    ".*_wrist_yaw_joint": (5.0, _STIFFNESS_4010),
+}
+# action scale = 0.25 * effort / stiffness (assets/unitree.py:625-636)
+UNITREE_G1_29DOF_ACTION_SCALE = {k: 0.25 * e / s for k, (e, s) in _G1_EFFORT_STIFFNESS.items()}
+
+_G1_JOINTS = (
+    "left_hip_pitch_joint", "right_hip_pitch_joint", "waist_yaw_joint",
+    "left_hip_roll_joint", "right_hip_roll_joint", "waist_roll_joint",
+    "left_hip_yaw_joint", "right_hip_yaw_joint", "waist_pitch_joint",
+    "left_knee_joint", "right_knee_joint",
+    "left_shoulder_pitch_joint", "right_shoulder_pitch_joint",
+    "left_ankle_pitch_joint", "right_ankle_pitch_joint",
+    "left_shoulder_roll_joint", "right_shoulder_roll_joint",
+    "left_ankle_roll_joint", "right_ankle_roll_joint",
+    "left_shoulder_yaw_joint", "right_shoulder_yaw_joint",
+    "left_elbow_joint", "right_elbow_joint",
+    "left_wrist_roll_joint", "right_wrist_roll_joint",
+    "left_wrist_pitch_joint", "right_wrist_pitch_joint",
+    "left_wrist_yaw_joint", "right_wrist_yaw_joint",
+)
+
+_G1_LIMITS_SIDE = {  # (left lower, left upper); right side mirrors roll/yaw-type limits where the URDF does
+    "hip_pitch": ((-2.5307, 2.8798), (-2.5307, 2.8798)),
+    "hip_roll": ((-0.5236, 2.9671), (-2.9671, 0.5236)),
+    "hip_yaw": ((-2.7576, 2.7576), (-2.7576, 2.7576)),
+    "knee": ((-0.087267, 2.8798), (-0.087267, 2.8798)),
+    "ankle_pitch": ((-0.87267, 0.5236), (-0.87267, 0.5236)),
+    "ankle_roll": ((-0.2618, 0.2618), (-0.2618, 0.2618)),
+    "shoulder_pitch": ((-3.0892, 2.6704), (-3.0892, 2.6704)),
+    "shoulder_roll": ((-1.5882, 2.2515), (-2.2515, 1.5882)),
+    "shoulder_yaw": ((-2.618, 2.618), (-2.618, 2.618)),
+    "elbow": ((-1.0472, 2.0944), (-1.0472, 2.0944)),
+    "wrist_roll": ((-1.972222054, 1.972222054), (-1.972222054, 1.972222054)),
+    "wrist_pitch": ((-1.614429558, 1.614429558), (-1.614429558, 1.614429558)),
+    "wrist_yaw": ((-1.614429558, 1.614429558), (-1.614429558, 1.614429558)),
+}
+_G1_LIMITS = {"waist_yaw_joint": (-2.618, 2.618), "waist_roll_joint": (-0.52, 0.52), "waist_pitch_joint": (-0.52, 0.52)}
+for _part, (_l, _r) in _G1_LIMITS_SIDE.items():
+    _G1_LIMITS[f"left_{_part}_joint"] = _l
+    _G1_LIMITS[f"right_{_part}_joint"] = _r
+
+_G1_BODIES = (
+    "pelvis",
+    "left_hip_pitch_link", "right_hip_pitch_link", "waist_yaw_link",
+    "left_hip_roll_link", "right_hip_roll_link", "waist_roll_link",
+    "left_hip_yaw_link", "right_hip_yaw_link", "torso_link",
+    "left_knee_link", "right_knee_link",
+    "left_shoulder_pitch_link", "right_shoulder_pitch_link",
+    "left_ankle_pitch_link", "right_ankle_pitch_link",
+    "left_shoulder_roll_link", "right_shoulder_roll_link",
+    "left_ankle_roll_link", "right_ankle_roll_link",
+    "left_shoulder_yaw_link", "right_shoulder_yaw_link",
+    "left_elbow_link", "right_elbow_link",
+    "left_wrist_roll_link", "right_wrist_roll_link",
+    "left_wrist_pitch_link", "right_wrist_pitch_link",
+    "left_wrist_yaw_link", "right_wrist_yaw_link",
+    "left_rubber_hand", "right_rubber_hand",
+)
+
+_G1_DEFAULT_POSE = {  # assets/unitree.py:489-498
+    ".*_hip_pitch_joint": -0.312,
+    ".*_knee_joint": 0.669,
+    ".*_ankle_pitch_joint": -0.363,
+    ".*_elbow_joint": 0.6,
+    "left_shoulder_roll_joint": 0.2,
+    "left_shoulder_pitch_joint": 0.2,
+    "right_shoulder_roll_joint": -0.2,
+    "right_shoulder_pitch_joint": 0.2,
+}
+
+_G1_VEL_LIMITS = {  # velocity_limit_sim, assets/unitree.py:518-591
+    ".*_hip_yaw_joint": 32.0, ".*_hip_roll_joint": 20.0, ".*_hip_pitch_joint": 32.0, ".*_knee_joint": 20.0,
+    ".*_ankle_pitch_joint": 37.0, ".*_ankle_roll_joint": 37.0,
+    "waist_roll_joint": 37.0, "waist_pitch_joint": 37.0, "waist_yaw_joint": 32.0,
+    ".*_shoulder_pitch_joint": 37.0, ".*_shoulder_roll_joint": 37.0, ".*_shoulder_yaw_joint": 37.0,
+    ".*_elbow_joint": 37.0, ".*_wrist_roll_joint": 37.0, ".*_wrist_pitch_joint": 22.0, ".*_wrist_yaw_joint": 22.0,
+}
+
+UNITREE_G1_29DOF = RobotAsset(
+    name="unitree_g1_29dof",
+    joint_names=_G1_JOINTS,
+    body_names=_G1_BODIES,
+    joint_limits=_G1_LIMITS,
+    default_joint_pos_patterns=_G1_DEFAULT_POSE,
+    joint_vel_limit_patterns=_G1_VEL_LIMITS,
+    init_root_height=0.76,
+    action_scale_patterns=UNITREE_G1_29DOF_ACTION_SCALE,
+)
+
+# J = 37 synthetic variant: the 29-DoF body plus 8 finger joints (4 per hand). It exists to honour
+# BASELINE.json's "37 DoF" label and to exercise joint loops with J > one warp (SURVEY 8(a) note).
+_G1_FINGERS = tuple(f"{side}_finger_{i}_joint" for i in range(4) for side in ("left", "right"))
+UNITREE_G1_37DOF = RobotAsset(
+    name="unitree_g1_37dof_synthetic",
+    joint_names=_G1_JOINTS + _G1_FINGERS,
+    body_names=_G1_BODIES + tuple(n.replace("_joint", "_link") for n in _G1_FINGERS),
+    joint_limits={**_G1_LIMITS, **{n: (-0.5, 1.6) for n in _G1_FINGERS}},
+    default_joint_pos_patterns=_G1_DEFAULT_POSE,
+    joint_vel_limit_patterns={**_G1_VEL_LIMITS, ".*_finger_.*": 22.0},
+    init_root_height=0.76,
+    action_scale_patterns={**UNITREE_G1_29DOF_ACTION_SCALE, ".*_finger_.*": 0.25},
+)
+
+
+ASSETS = {a.name: a for a in (UNITREE_A1, UNITREE_GO2, UNITREE_G1_29DOF, UNITREE_G1_37DOF)}
+
+PI = math.pi
