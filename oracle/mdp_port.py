@@ -1,0 +1,667 @@
+"""CPU oracle: a restatement of the reference's per-step MDP pipeline in eager fp32 PyTorch.
+
+TEST INFRASTRUCTURE - NOT PRODUCT CODE. Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package; the product path (``robot_lab_b200``) never
+does and fails loudly when its CUDA library is missing.
+
+What is restated, and from where (paths relative to /root/reference; V/ =
+source/robot_lab/robot_lab/tasks/manager_based/locomotion/velocity/):
+
+  * robot_lab-owned reward terms - V/mdp/rewards.py:22-687, one function each below, citing its lines.
+    PINNED: ``tests/test_oracle_vs_reference.py`` runs the *unmodified* reference file through
+    ``oracle/isaaclab_shim.py`` in the build container and compares every term; the committed fixtures under
+    ``tests/golden/`` were produced by the reference functions themselves (``tests/golden/make_golden.py``).
+  * robot_lab-owned observation terms and command logic - V/mdp/observations.py:17-35, V/mdp/commands.py:43-85
+    (the "pits" branch is identically off for the in-scope terrains: V/mdp/utils.py:27-28).
+  * IsaacLab-owned pieces [IL] - upstream reward / observation / termination terms, the manager loops
+    (RewardManager.compute, ObservationManager.compute_group, TerminationManager.compute, CommandTerm.compute,
+    UniformVelocityCommand, JointAction.process_actions), math helpers and ContactSensor.compute_first_contact.
+    Their source (IsaacLab v2.3.2, pinned by the reference at README.md:4,54 and
+    source/robot_lab/config/extension.toml:4) is NOT vendored under /root/reference and not installed here:
+    they are restated from the published upstream algorithm. **PARITY UNPINNED** for
+    these pieces: the reference holds no tests, golden vectors or fixtures for them.
+
+Arithmetic mirrors the reference's op-by-op eager evaluation (each op rounds to fp32), which also makes this
+module the honest CPU baseline ("port") for bench.py.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from robot_lab_b200.spec import DoneTermSpec, ObsGroupSpec, RewardTermSpec, StepSpec
+
+from . import philox
+
+State = dict  # logical [N, ...] tensors, see robot_lab_b200.synthetic.make_state
+
+
+# ------------------------------------------------------------------------------------------------
+# isaaclab.utils.math [IL]
+# ------------------------------------------------------------------------------------------------
+def quat_apply(quat: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    xyz = quat[:, 1:]
+    t = xyz.cross(vec, dim=-1) * 2
+    return vec + quat[:, 0:1] * t + xyz.cross(t, dim=-1)
+
+
+def quat_apply_inverse(quat: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    xyz = quat[:, 1:]
+    t = xyz.cross(vec, dim=-1) * 2
+    return vec - quat[:, 0:1] * t + xyz.cross(t, dim=-1)
+
+
+def yaw_quat(quat: torch.Tensor) -> torch.Tensor:
+    qw, qx, qy, qz = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    yaw = torch.atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz))
+    out = torch.zeros_like(quat)
+    out[:, 3] = torch.sin(yaw / 2)
+    out[:, 0] = torch.cos(yaw / 2)
+    return out / out.norm(p=2, dim=-1, keepdim=True).clamp(min=1e-9)
+
+
+def wrap_to_pi(angles: torch.Tensor) -> torch.Tensor:
+    wrapped = (angles + torch.pi) % (2 * torch.pi)
+    return torch.where((wrapped == 0) & (angles > 0), torch.pi, wrapped - torch.pi)
+
+
+# ------------------------------------------------------------------------------------------------
+# derived articulation / sensor data [IL] (ArticulationData, ContactSensor)
+# ------------------------------------------------------------------------------------------------
+class Derived:
+    """Lazily computed quantities shared by terms (what ArticulationData properties provide upstream)."""
+
+    def __init__(self, st: State, spec: StepSpec):
+        self.st, self.spec = st, spec
+        n = st["root_quat_w"].shape[0]
+        self.N = n
+        q = st["root_quat_w"]
+        self.projected_gravity_b = quat_apply_inverse(q, torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1))
+        self.root_lin_vel_b = quat_apply_inverse(q, st["root_lin_vel_w"])
+        self.root_ang_vel_b = quat_apply_inverse(q, st["root_ang_vel_w"])
+        self.default_joint_pos = torch.tensor(spec.default_joint_pos, dtype=torch.float32).unsqueeze(0).repeat(n, 1)
+        self.default_joint_vel = torch.tensor(spec.default_joint_vel, dtype=torch.float32).unsqueeze(0).repeat(n, 1)
+        lim = torch.tensor(spec.soft_pos_limits, dtype=torch.float32)
+        self.soft_joint_pos_limits = lim.unsqueeze(0).repeat(n, 1, 1)
+        self.soft_joint_vel_limits = torch.tensor(spec.soft_vel_limits, dtype=torch.float32).unsqueeze(0).repeat(n, 1)
+        self.terminated = st.get("terminated", torch.zeros(n, dtype=torch.bool))
+
+    def gate(self) -> torch.Tensor:
+        return torch.clamp(-self.projected_gravity_b[:, 2], 0, 0.7) / 0.7
+
+    def first_contact(self) -> torch.Tensor:  # ContactSensor.compute_first_contact(step_dt) [IL]
+        t = self.st["current_contact_time"]
+        return (t > 0.0) * (t < (self.spec.step_dt + self.spec.contact_time_abs_tol))
+
+    def first_air(self) -> torch.Tensor:
+        t = self.st["current_air_time"]
+        return (t > 0.0) * (t < (self.spec.step_dt + self.spec.contact_time_abs_tol))
+
+    def heading_w(self) -> torch.Tensor:
+        fwd = quat_apply(self.st["root_quat_w"], torch.tensor([[1.0, 0.0, 0.0]]).repeat(self.N, 1))
+        return torch.atan2(fwd[:, 1], fwd[:, 0])
+
+
+# ------------------------------------------------------------------------------------------------
+# reward terms: raw value [N] (no weight, no dt)
+# ------------------------------------------------------------------------------------------------
+def reward_term(t: RewardTermSpec, st: State, spec: StepSpec, d: Derived | None = None) -> torch.Tensor:
+    d = d or Derived(st, spec)
+    fn = _REWARD_FUNCS[t.type_name]
+    return fn(t, st, spec, d)
+
+
+def _cmd(st):
+    return st["command"]
+
+
+def _rw_is_terminated(t, st, spec, d):  # [IL] rewards.is_terminated
+    return d.terminated.float()
+
+
+def _rw_lin_vel_z_l2(t, st, spec, d):  # V/mdp/rewards.py:647-653
+    r = torch.square(d.root_lin_vel_b[:, 2])
+    r *= d.gate()
+    return r
+
+
+def _rw_ang_vel_xy_l2(t, st, spec, d):  # :656-662
+    r = torch.sum(torch.square(d.root_ang_vel_b[:, :2]), dim=1)
+    r *= d.gate()
+    return r
+
+
+def _rw_flat_orientation_l2(t, st, spec, d):  # :678-687
+    r = torch.sum(torch.square(d.projected_gravity_b[:, :2]), dim=1)
+    r *= d.gate()
+    return r
+
+
+def _rw_base_height_l2(t, st, spec, d):  # :616-644, sensor_cfg=None branch
+    r = torch.square(st["root_pos_w"][:, 2] - t.p[0])
+    r *= d.gate()
+    return r
+
+
+def _rw_upward(t, st, spec, d):  # :608-613
+    return torch.square(1 - d.projected_gravity_b[:, 2])
+
+
+def _rw_joint_torques_l2(t, st, spec, d):  # [IL]
+    return torch.sum(torch.square(st["applied_torque"][:, t.joint_ids]), dim=1)
+
+
+def _rw_joint_vel_l2(t, st, spec, d):  # [IL]
+    return torch.sum(torch.square(st["joint_vel"][:, t.joint_ids]), dim=1)
+
+
+def _rw_joint_acc_l2(t, st, spec, d):  # [IL]
+    return torch.sum(torch.square(st["joint_acc"][:, t.joint_ids]), dim=1)
+
+
+def _joint_deviation_l1(ids, st, d):  # [IL] rewards.joint_deviation_l1
+    angle = st["joint_pos"][:, ids] - d.default_joint_pos[:, ids]
+    return torch.sum(torch.abs(angle), dim=1)
+
+
+def _rw_joint_deviation_l1(t, st, spec, d):
+    return _joint_deviation_l1(t.joint_ids, st, d)
+
+
+def _rw_joint_pos_limits(t, st, spec, d):  # [IL]
+    q = st["joint_pos"][:, t.joint_ids]
+    out = -(q - d.soft_joint_pos_limits[:, t.joint_ids, 0]).clip(max=0.0)
+    out += (q - d.soft_joint_pos_limits[:, t.joint_ids, 1]).clip(min=0.0)
+    return torch.sum(out, dim=1)
+
+
+def _rw_joint_vel_limits(t, st, spec, d):  # [IL]
+    out = torch.abs(st["joint_vel"][:, t.joint_ids]) - d.soft_joint_vel_limits[:, t.joint_ids] * t.p[0]
+    out = out.clip_(min=0.0, max=1.0)
+    return torch.sum(out, dim=1)
+
+
+def _rw_joint_power(t, st, spec, d):  # V/mdp/rewards.py:81-90
+    return torch.sum(torch.abs(st["joint_vel"][:, t.joint_ids] * st["applied_torque"][:, t.joint_ids]), dim=1)
+
+
+def _rw_stand_still(t, st, spec, d):  # :93-104
+    r = _joint_deviation_l1(t.joint_ids, st, d)
+    r *= torch.norm(_cmd(st), dim=1) < t.p[0]
+    r *= d.gate()
+    return r
+
+
+def _rw_joint_pos_penalty(t, st, spec, d):  # :107-129
+    cmd = torch.linalg.norm(_cmd(st), dim=1)
+    body_vel = torch.linalg.norm(d.root_lin_vel_b[:, :2], dim=1)
+    running = torch.linalg.norm(st["joint_pos"][:, t.joint_ids] - d.default_joint_pos[:, t.joint_ids], dim=1)
+    r = torch.where(torch.logical_or(cmd > t.p[2], body_vel > t.p[1]), running, t.p[0] * running)
+    r *= d.gate()
+    return r
+
+
+def _pairs_loop(t, values, absval):
+    n = values.shape[0]
+    r = torch.zeros(n)
+    a, b = values[:, t.idx_a], values[:, t.idx_b]
+    if absval:
+        a, b = torch.abs(a), torch.abs(b)
+    r += torch.sum(torch.square(a - b), dim=-1)
+    return r
+
+
+def _rw_joint_mirror(t, st, spec, d):  # :259-278
+    r = _pairs_loop(t, st["joint_pos"], False)
+    r *= t.p[0]
+    r *= d.gate()
+    return r
+
+
+def _rw_action_mirror(t, st, spec, d):  # :281-303
+    r = _pairs_loop(t, st["action"], True)
+    r *= t.p[0]
+    r *= d.gate()
+    return r
+
+
+def _rw_action_sync(t, st, spec, d):  # :306-337
+    n = st["action"].shape[0]
+    r = torch.zeros(n)
+    for g in range(t.n_idx):
+        start, size = t.idx_b[g], t.idx_c[g]
+        if size < 2:
+            continue
+        acts = torch.abs(st["action"][:, t.idx_a[start:start + size]])
+        mean = torch.mean(acts, dim=1, keepdim=True)
+        r += torch.mean(torch.square(acts - mean), dim=1)
+    r *= t.p[0]
+    r *= d.gate()
+    return r
+
+
+def _rw_action_rate_l2(t, st, spec, d):  # [IL]
+    return torch.sum(torch.square(st["action"] - st["prev_action"]), dim=1)
+
+
+def _hist_max_norm(st, ids):
+    return torch.max(torch.norm(st["net_forces_w_history"][:, :, ids], dim=-1), dim=1)[0]
+
+
+def _rw_undesired_contacts(t, st, spec, d):  # :665-675
+    is_contact = _hist_max_norm(st, t.body_ids) > t.p[0]
+    r = torch.sum(is_contact, dim=1).float()
+    r *= d.gate()
+    return r
+
+
+def _rw_contact_forces(t, st, spec, d):  # [IL]
+    violation = _hist_max_norm(st, t.body_ids) - t.p[0]
+    return torch.sum(violation.clip(min=0.0), dim=1)
+
+
+def _rw_track_lin_vel_xy_exp(t, st, spec, d):  # :22-35
+    err = torch.sum(torch.square(_cmd(st)[:, :2] - d.root_lin_vel_b[:, :2]), dim=1)
+    r = torch.exp(-err / t.p[0])
+    r *= d.gate()
+    return r
+
+
+def _rw_track_ang_vel_z_exp(t, st, spec, d):  # :38-48
+    err = torch.square(_cmd(st)[:, 2] - d.root_ang_vel_b[:, 2])
+    r = torch.exp(-err / t.p[0])
+    r *= d.gate()
+    return r
+
+
+def _rw_track_lin_vel_xy_yaw_frame_exp(t, st, spec, d):  # :51-66
+    vel_yaw = quat_apply_inverse(yaw_quat(st["root_quat_w"]), st["root_lin_vel_w"][:, :3])
+    err = torch.sum(torch.square(_cmd(st)[:, :2] - vel_yaw[:, :2]), dim=1)
+    r = torch.exp(-err / t.p[0])
+    r *= d.gate()
+    return r
+
+
+def _rw_track_ang_vel_z_world_exp(t, st, spec, d):  # :69-78
+    err = torch.square(_cmd(st)[:, 2] - st["root_ang_vel_w"][:, 2])
+    r = torch.exp(-err / t.p[0])
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_air_time(t, st, spec, d):  # :340-360
+    first = d.first_contact()[:, t.idx_a]
+    r = torch.sum((st["last_air_time"][:, t.idx_a] - t.p[0]) * first, dim=1)
+    r *= torch.norm(_cmd(st), dim=1) > 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_air_time_positive_biped(t, st, spec, d):  # :363-383
+    air = st["current_air_time"][:, t.idx_a]
+    con = st["current_contact_time"][:, t.idx_a]
+    in_contact = con > 0.0
+    mode = torch.where(in_contact, con, air)
+    single = torch.sum(in_contact.int(), dim=1) == 1
+    r = torch.min(torch.where(single.unsqueeze(-1), mode, 0.0), dim=1)[0]
+    r = torch.clamp(r, max=t.p[0])
+    r *= torch.norm(_cmd(st), dim=1) > 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_air_time_variance(t, st, spec, d):  # :386-397
+    r = torch.var(torch.clip(st["last_air_time"][:, t.idx_a], max=0.5), dim=1) + torch.var(
+        torch.clip(st["last_contact_time"][:, t.idx_a], max=0.5), dim=1)
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_gait(t, st, spec, d):  # :156-256
+    air, con = st["current_air_time"], st["current_contact_time"]
+    std, me2 = t.p[0], t.p[1]
+    f00, f01, f10, f11 = t.idx_a[:4]
+
+    def sync(a, b):
+        se_air = torch.clip(torch.square(air[:, a] - air[:, b]), max=me2)
+        se_con = torch.clip(torch.square(con[:, a] - con[:, b]), max=me2)
+        return torch.exp(-(se_air + se_con) / std)
+
+    def asyn(a, b):
+        se0 = torch.clip(torch.square(air[:, a] - con[:, b]), max=me2)
+        se1 = torch.clip(torch.square(con[:, a] - air[:, b]), max=me2)
+        return torch.exp(-(se0 + se1) / std)
+
+    sync_r = sync(f00, f01) * sync(f10, f11)
+    async_r = asyn(f00, f10) * asyn(f01, f11) * asyn(f00, f11) * asyn(f10, f01)
+    cmd = torch.linalg.norm(_cmd(st), dim=1)
+    body_vel = torch.linalg.norm(d.root_lin_vel_b[:, :2], dim=1)
+    r = torch.where(torch.logical_or(cmd > t.p[3], body_vel > t.p[2]), sync_r * async_r, 0.0)
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_contact(t, st, spec, d):  # :400-413
+    n = torch.sum(d.first_contact()[:, t.idx_a], dim=1)
+    r = (n != t.p[0]).float()
+    r *= torch.linalg.norm(_cmd(st), dim=1) > 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_contact_without_cmd(t, st, spec, d):  # :416-425
+    r = torch.sum(d.first_contact()[:, t.idx_a], dim=-1).float()
+    r *= torch.linalg.norm(_cmd(st), dim=1) < 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_stumble(t, st, spec, d):  # :428-436 (net_forces_w = newest history sample)
+    f = st["net_forces_w_history"][:, 0]
+    fz = torch.abs(f[:, t.idx_c, 2])
+    fxy = torch.linalg.norm(f[:, t.idx_c, :2], dim=2)
+    r = torch.any(fxy > 4 * fz, dim=1).float()
+    r *= d.gate()
+    return r
+
+
+def _feet_in_body_frame(vec_w, root_w, quat, ids):
+    rel = vec_w[:, ids, :] - root_w.unsqueeze(1)
+    out = torch.zeros(rel.shape[0], len(ids), 3)
+    for i in range(len(ids)):
+        out[:, i, :] = quat_apply_inverse(quat, rel[:, i, :])
+    return out
+
+
+def _rw_feet_slide(t, st, spec, d):  # :557-587
+    contacts = st["net_forces_w_history"][:, :, t.idx_c, :].norm(dim=-1).max(dim=1)[0] > 1.0
+    vel_b = _feet_in_body_frame(st["body_lin_vel_w"], st["root_lin_vel_w"], st["root_quat_w"], t.idx_b)
+    lateral = torch.sqrt(torch.sum(torch.square(vel_b[:, :, :2]), dim=2)).view(vel_b.shape[0], -1)
+    r = torch.sum(lateral * contacts, dim=1)
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_height(t, st, spec, d):  # :507-524
+    err = torch.square(st["body_pos_w"][:, t.idx_b, 2] - t.p[0])
+    tanh = torch.tanh(t.p[1] * torch.linalg.norm(st["body_lin_vel_w"][:, t.idx_b, :2], dim=2))
+    r = torch.sum(err * tanh, dim=1)
+    r *= torch.linalg.norm(_cmd(st), dim=1) > 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_height_body(t, st, spec, d):  # :527-554
+    pos_b = _feet_in_body_frame(st["body_pos_w"], st["root_pos_w"], st["root_quat_w"], t.idx_b)
+    vel_b = _feet_in_body_frame(st["body_lin_vel_w"], st["root_lin_vel_w"], st["root_quat_w"], t.idx_b)
+    err = torch.square(pos_b[:, :, 2] - t.p[0]).view(pos_b.shape[0], -1)
+    tanh = torch.tanh(t.p[1] * torch.norm(vel_b[:, :, :2], dim=2))
+    r = torch.sum(err * tanh, dim=1)
+    r *= torch.linalg.norm(_cmd(st), dim=1) > 0.1
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_distance_y_exp(t, st, spec, d):  # :439-461
+    pos_b = _feet_in_body_frame(st["body_pos_w"], st["root_pos_w"], st["root_quat_w"], t.idx_b)
+    n_feet = len(t.idx_b)
+    side = torch.tensor([1.0 if i % 2 == 0 else -1.0 for i in range(n_feet)])
+    desired = (t.p[0] * torch.ones(pos_b.shape[0], 1)) / 2 * side.unsqueeze(0)
+    diff = torch.square(desired - pos_b[:, :, 1])
+    r = torch.exp(-torch.sum(diff, dim=1) / t.p[1])
+    r *= d.gate()
+    return r
+
+
+def _rw_feet_distance_xy_exp(t, st, spec, d):  # :464-504
+    pos_b = _feet_in_body_frame(st["body_pos_w"], st["root_pos_w"], st["root_quat_w"], t.idx_b)
+    n = pos_b.shape[0]
+    w = t.p[0] * torch.ones(n, 1)
+    l = t.p[1] * torch.ones(n, 1)
+    dx = torch.cat([l / 2, l / 2, -l / 2, -l / 2], dim=1)
+    dy = torch.cat([w / 2, -w / 2, w / 2, -w / 2], dim=1)
+    diff = torch.square(dx - pos_b[:, :, 0]) + torch.square(dy - pos_b[:, :, 1])
+    r = torch.exp(-torch.sum(diff, dim=1) / t.p[2])
+    r *= d.gate()
+    return r
+
+
+def _rw_wheel_vel_penalty(t, st, spec, d):  # :132-153
+    cmd = torch.linalg.norm(_cmd(st), dim=1)
+    body_vel = torch.linalg.norm(d.root_lin_vel_b[:, :2], dim=1)
+    jv = torch.abs(st["joint_vel"][:, t.idx_b])
+    in_air = d.first_air()[:, t.idx_a]
+    running = torch.sum(in_air * jv, dim=1)
+    standing = torch.sum(jv, dim=1)
+    return torch.where(torch.logical_or(cmd > t.p[1], body_vel > t.p[0]), running, standing)
+
+
+_REWARD_FUNCS = {k[4:]: v for k, v in list(globals().items()) if k.startswith("_rw_")}
+
+
+# ------------------------------------------------------------------------------------------------
+# managers [IL]
+# ------------------------------------------------------------------------------------------------
+def done_term(t: DoneTermSpec, st: State, spec: StepSpec, episode_length: torch.Tensor) -> torch.Tensor:
+    if t.type_name == "time_out":
+        return episode_length >= spec.max_episode_length
+    if t.type_name == "terrain_out_of_bounds":
+        n = st["root_pos_w"].shape[0]
+        if t.p[2] == 0.0:
+            return torch.zeros(n, dtype=torch.bool)
+        x_out = torch.abs(st["root_pos_w"][:, 0]) > t.p[0]
+        y_out = torch.abs(st["root_pos_w"][:, 1]) > t.p[1]
+        return torch.logical_or(x_out, y_out)
+    if t.type_name == "illegal_contact":
+        return torch.any(_hist_max_norm(st, t.body_ids) > t.p[0], dim=1)
+    raise NotImplementedError(t.type_name)
+
+
+def compute_dones(spec: StepSpec, st: State):
+    """episode_length += 1; TerminationManager.compute [IL]."""
+    ep = st["episode_length"] + 1
+    n = ep.shape[0]
+    terminated = torch.zeros(n, dtype=torch.bool)
+    truncated = torch.zeros(n, dtype=torch.bool)
+    bits = torch.zeros(n, dtype=torch.int32)
+    for i, t in enumerate(spec.dones):
+        v = done_term(t, st, spec, ep)
+        if t.time_out:
+            truncated |= v
+        else:
+            terminated |= v
+        bits |= v.int() << i
+    return ep, terminated, truncated, bits
+
+
+def compute_rewards(spec: StepSpec, st: State, terminated: torch.Tensor):
+    """RewardManager.compute(dt) [IL]: value = func * weight * dt, summed in declared order."""
+    n = st["root_quat_w"].shape[0]
+    st = dict(st)
+    st["terminated"] = terminated
+    d = Derived(st, spec)
+    dt = spec.step_dt
+    total = torch.zeros(n)
+    sums = st["episode_sums"].clone()
+    step_reward = torch.zeros(n, spec.K)
+    for k, t in enumerate(spec.rewards):
+        if t.weight == 0.0:
+            continue
+        value = reward_term(t, st, spec, d) * t.weight * dt
+        total += value
+        sums[:, k] += value
+        step_reward[:, k] = value / dt
+    return total, sums, step_reward
+
+
+def command_uniforms(spec: StepSpec, st: State, rnd: dict, stream: int) -> torch.Tensor:
+    """[7, N] U[0,1): given inputs (noise-as-input mode) or the kernel's Philox stream."""
+    if rnd.get("cmd_uniforms") is not None:
+        return rnd["cmd_uniforms"]
+    n = st["root_quat_w"].shape[0]
+    return philox.command_uniforms(n, rnd["seed"], rnd["step"], rnd.get("env_id_offset", 0), stream)
+
+
+def _resample(spec: StepSpec, ids: torch.Tensor, u: torch.Tensor, out: dict):
+    """CommandTerm._resample [IL] + UniformThresholdVelocityCommand._resample_command (V/mdp/commands.py:43-47)."""
+    c = spec.command
+
+    def uni(row, lo_hi):
+        lo, hi = lo_hi
+        return u[row, ids] * (hi - lo) + lo
+
+    out["time_left"][ids] = uni(0, c.resampling_time)
+    out["command"][ids, 0] = uni(1, c.lin_vel_x)
+    out["command"][ids, 1] = uni(2, c.lin_vel_y)
+    out["command"][ids, 2] = uni(3, c.ang_vel_z)
+    if c.heading_command:
+        out["heading_target"][ids] = uni(4, c.heading)
+        out["is_heading_env"][ids] = u[5, ids] <= c.rel_heading_envs
+    out["is_standing_env"][ids] = u[6, ids] <= c.rel_standing_envs
+    out["command"][ids, :2] *= (torch.norm(out["command"][ids, :2], dim=1) > c.small_cmd_threshold).unsqueeze(1)
+
+
+def compute_command(spec: StepSpec, st: State, rnd: dict, active: torch.Tensor | None = None) -> dict:
+    """CommandTerm.compute(dt) [IL] for the envs in ``active`` (bool mask; None = all)."""
+    c = spec.command
+    n = st["root_quat_w"].shape[0]
+    out = {k: st[k].clone() for k in ("command", "heading_target", "time_left", "is_heading_env", "is_standing_env",
+                                      "metric_error_vel_xy", "metric_error_vel_yaw")}
+    d = Derived(st, spec)
+    act = torch.ones(n, dtype=torch.bool) if active is None else active
+    # _update_metrics
+    exy = torch.norm(st["command"][:, :2] - d.root_lin_vel_b[:, :2], dim=-1) / c.max_command_step
+    eyaw = torch.abs(st["command"][:, 2] - d.root_ang_vel_b[:, 2]) / c.max_command_step
+    out["metric_error_vel_xy"] = torch.where(act, st["metric_error_vel_xy"] + exy, st["metric_error_vel_xy"])
+    out["metric_error_vel_yaw"] = torch.where(act, st["metric_error_vel_yaw"] + eyaw, st["metric_error_vel_yaw"])
+    out["time_left"] = torch.where(act, st["time_left"] - spec.step_dt, st["time_left"])
+    ids = (act & (out["time_left"] <= 0.0)).nonzero(as_tuple=False).flatten()
+    if len(ids) > 0:
+        _resample(spec, ids, command_uniforms(spec, st, rnd, philox.STREAM_COMMAND), out)
+    # _update_command
+    if c.heading_command:
+        hid = (act & out["is_heading_env"]).nonzero(as_tuple=False).flatten()
+        err = wrap_to_pi(out["heading_target"][hid] - d.heading_w()[hid])
+        out["command"][hid, 2] = torch.clip(c.heading_control_stiffness * err, min=c.ang_vel_z[0], max=c.ang_vel_z[1])
+    sid = (act & out["is_standing_env"]).nonzero(as_tuple=False).flatten()
+    out["command"][sid, :] = 0.0
+    return out
+
+
+def obs_uniforms(spec: StepSpec, g: int, st: State, rnd: dict) -> torch.Tensor:
+    key = ("obs_uniforms_policy", "obs_uniforms_critic")[g]
+    if rnd.get(key) is not None:
+        return rnd[key]
+    n = st["root_quat_w"].shape[0]
+    dims = [t.dim for t in spec.obs[g].terms]
+    return philox.obs_uniforms(n, dims, g, rnd["seed"], rnd["step"], rnd.get("env_id_offset", 0))
+
+
+def compute_obs_group(spec: StepSpec, g: int, st: State, rnd: dict) -> torch.Tensor:
+    """ObservationManager.compute_group [IL]: clone -> +noise -> clip -> scale -> cat."""
+    grp: ObsGroupSpec = spec.obs[g]
+    d = Derived(st, spec)
+    n = d.N
+    cols = []
+    u_all = None
+    col0 = 0
+    for t in grp.terms:
+        ty = t.type_name
+        if ty == "base_lin_vel":
+            v = d.root_lin_vel_b
+        elif ty == "base_ang_vel":
+            v = d.root_ang_vel_b
+        elif ty == "projected_gravity":
+            v = d.projected_gravity_b
+        elif ty == "generated_commands":
+            v = st["command"]
+        elif ty == "joint_pos_rel":
+            v = st["joint_pos"][:, t.ids] - d.default_joint_pos[:, t.ids]
+        elif ty == "joint_pos_rel_without_wheel":  # V/mdp/observations.py:17-27
+            v = st["joint_pos"][:, t.ids] - d.default_joint_pos[:, t.ids]
+            v[:, t.zero_cols] = 0
+        elif ty == "joint_vel_rel":
+            v = st["joint_vel"][:, t.ids] - d.default_joint_vel[:, t.ids]
+        elif ty == "last_action":
+            v = st["action"]
+        elif ty == "height_scan":
+            v = st["ray_sensor_pos_z"].unsqueeze(1) - st["ray_hits_z"] - t.p[0]
+        elif ty == "phase":  # V/mdp/observations.py:30-35
+            ph = st["episode_length"][:, None] * spec.step_dt / t.p[0]
+            v = torch.cat([torch.sin(2 * torch.pi * ph), torch.cos(2 * torch.pi * ph)], dim=-1)
+        else:
+            raise NotImplementedError(ty)
+        v = v.clone()
+        if t.noise is not None and grp.enable_corruption:
+            if u_all is None:
+                u_all = obs_uniforms(spec, g, st, rnd)
+            u = u_all[:, col0:col0 + t.dim]
+            v = v + u * (t.noise[1] - t.noise[0]) + t.noise[0]
+        if t.clip is not None:
+            v = v.clip_(min=t.clip[0], max=t.clip[1])
+        if t.scale is not None:
+            v = v.mul_(t.scale)
+        cols.append(v)
+        col0 += t.dim
+    return torch.cat(cols, dim=-1) if cols else torch.zeros(n, 0)
+
+
+def process_action(spec: StepSpec, st: State, new_action: torch.Tensor):
+    """ActionManager.process_action + JointAction.process_actions [IL]."""
+    a = spec.action
+    prev = st["action"].clone()
+    action = new_action.clone()
+    processed = action * torch.tensor(a.scale, dtype=torch.float32) + torch.tensor(a.offset, dtype=torch.float32)
+    if a.clip is not None:
+        clip = torch.tensor(a.clip, dtype=torch.float32)
+        processed = torch.clamp(processed, min=clip[:, 0], max=clip[:, 1])
+    return action, prev, processed
+
+
+def step(spec: StepSpec, st: State, rnd: dict, skip_done_envs: bool = False) -> dict:
+    """ManagerBasedRLEnv.step() [IL] minus physics and the external reset.
+
+    With ``skip_done_envs`` the command update is withheld from envs that are done this step, exactly like the
+    fused kernel's RL_PHASE_SKIP_DONE_ENVS (they are refreshed after the reset by :func:`refresh_after_reset`).
+    """
+    ep, terminated, truncated, bits = compute_dones(spec, st)
+    total, sums, step_reward = compute_rewards(spec, st, terminated)
+    done = terminated | truncated
+    reset_ids = done.nonzero(as_tuple=False).flatten().to(torch.int32)
+    cmd = compute_command(spec, st, rnd, active=(~done) if skip_done_envs else None)
+    st2 = dict(st)
+    st2.update(cmd)
+    st2["episode_length"] = ep
+    return {
+        "episode_length": ep, "terminated": terminated, "truncated": truncated, "done_bits": bits,
+        "reward": total, "episode_sums": sums, "step_reward": step_reward, "reset_ids": reset_ids,
+        **cmd,
+        "obs_policy": compute_obs_group(spec, 0, st2, rnd),
+        "obs_critic": compute_obs_group(spec, 1, st2, rnd),
+    }
+
+
+def reset_envs(spec: StepSpec, st: State, ids: torch.Tensor, done_bits: torch.Tensor, rnd: dict) -> tuple[dict, dict]:
+    """Manager part of ManagerBasedRLEnv._reset_idx [IL]: logging means, zeroing, command resample."""
+    ids = ids.long()
+    out = {k: st[k].clone() for k in ("episode_sums", "action", "prev_action", "command", "heading_target", "time_left",
+                                      "is_heading_env", "is_standing_env", "metric_error_vel_xy",
+                                      "metric_error_vel_yaw", "episode_length")}
+    log = {
+        "episode_sum_mean": torch.stack([torch.mean(st["episode_sums"][ids, k]) for k in range(spec.K)])
+        if len(ids) > 0 else torch.zeros(spec.K),
+        "done_term_count": torch.tensor([float(torch.count_nonzero((done_bits[ids] >> i) & 1)) for i in range(8)]),
+        "metric_mean": torch.stack([torch.mean(st["metric_error_vel_xy"][ids]), torch.mean(st["metric_error_vel_yaw"][ids])])
+        if len(ids) > 0 else torch.zeros(2),
+    }
+    out["episode_sums"][ids] = 0.0
+    out["action"][ids] = 0.0
+    out["prev_action"][ids] = 0.0
+    out["metric_error_vel_xy"][ids] = 0.0
+    out["metric_error_vel_yaw"][ids] = 0.0
+    out["episode_length"][ids] = 0
+    if len(ids) > 0:
+        _resample(spec, ids, command_uniforms(spec, st, rnd, philox.STREAM_RESET_COMMAND), out)
+    return out, log

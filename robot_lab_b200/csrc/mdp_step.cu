@@ -1275,15 +1275,12 @@ template <int MODE>
 int dispatch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   const int key = ctx->E * 100 + ctx->LPE;
   switch (key) {
-    case 804: return launch_step<8, 4, MODE>(ctx, a, n_items, st);
     case 808: return launch_step<8, 8, MODE>(ctx, a, n_items, st);
     case 816: return launch_step<8, 16, MODE>(ctx, a, n_items, st);
     case 1604: return launch_step<16, 4, MODE>(ctx, a, n_items, st);
     case 1608: return launch_step<16, 8, MODE>(ctx, a, n_items, st);
-    case 1616: return launch_step<16, 16, MODE>(ctx, a, n_items, st);
     case 3204: return launch_step<32, 4, MODE>(ctx, a, n_items, st);
     case 3208: return launch_step<32, 8, MODE>(ctx, a, n_items, st);
-    case 432: return launch_step<4, 32, MODE>(ctx, a, n_items, st);
     default: return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", ctx->E, ctx->LPE);
   }
 }
@@ -1383,7 +1380,7 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env) {
   const int E = envs_per_cta > 0 ? envs_per_cta : 16;
   const int LPE = lanes_per_env > 0 ? lanes_per_env : 8;
   const int key = E * 100 + LPE;
-  const int okeys[] = {804, 808, 816, 1604, 1608, 1616, 3204, 3208, 432};
+  const int okeys[] = {808, 816, 1604, 1608, 3204, 3208};
   bool ok = false;
   for (int k : okeys) ok = ok || (k == key);
   if (!ok) return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", E, LPE);

@@ -1,0 +1,82 @@
+"""Thin object wrapper over the C-ABI: one ``MdpStepEngine`` = one ``RlCtx`` on one GPU.
+
+Every method is a single ``extern "C"`` call with raw device pointers taken from the torch tensors in
+``StateBuffers``; launches are asynchronous on torch's current stream (so they compose with CUDA graphs and
+with NCCL work enqueued by ``torch.distributed``). No method synchronises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+from .spec import RewardTermSpec, StepSpec, reward_term_to_ctypes
+from .state import StateBuffers
+
+
+class MdpStepEngine:
+    def __init__(self, spec: StepSpec, device: torch.device | str = "cuda:0"):
+        self.lib = nat.load()  # raises if the CUDA library is missing: there is no CPU fallback
+        self.spec = spec
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.NativeError("the MDP step runs on CUDA devices only")
+        self._cspec = spec.to_ctypes()
+        self._ctx = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        nat.check(self.lib.rl_ctx_create(C.byref(self._cspec), idx, C.byref(self._ctx)))
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.rl_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def set_launch_config(self, envs_per_cta: int = 0, lanes_per_env: int = 0) -> None:
+        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, envs_per_cta, lanes_per_env))
+
+    def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
+        return StateBuffers(self.spec, num_envs, self.device, layout)
+
+    # ---- the five entry points ----------------------------------------------------------------------
+    def process_action(self, b: StateBuffers, with_target: bool = True) -> None:
+        na = b.field("new_action")
+        mdp = b.mdp_state()
+        tgt = b.field("joint_target") if with_target else nat.RlField(None, 0, 0)
+        nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), self._stream()))
+
+    def step(self, b: StateBuffers, phases: int = nat.PHASE_ALL, seed: int = 0, step: int = 0, env_id_offset: int = 0,
+             use_random_inputs: bool = True, env_ids: torch.Tensor | None = None,
+             n_env_ids: torch.Tensor | None = None) -> None:
+        st, mdp, out = b.state_view(), b.mdp_state(), b.step_out()
+        rnd = b.random(seed, step, env_id_offset, use_random_inputs)
+        nat.check(self.lib.rl_step(self._ctx, b.N, C.byref(st), C.byref(mdp), C.byref(out), C.byref(rnd), phases,
+                                   nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), self._stream()))
+
+    def reset_envs(self, b: StateBuffers, env_ids: torch.Tensor, n_env_ids: torch.Tensor, seed: int = 0, step: int = 0,
+                   env_id_offset: int = 0, use_random_inputs: bool = True, with_log: bool = True) -> None:
+        mdp = b.mdp_state()
+        rnd = b.random(seed, step, env_id_offset, use_random_inputs)
+        log = b.reset_log() if with_log else nat.RlResetLog()
+        nat.check(self.lib.rl_reset_envs(self._ctx, b.N, C.byref(mdp), b.done_bits.data_ptr(), C.byref(rnd), C.byref(log),
+                                         nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), self._stream()))
+
+    def term_eval(self, term: RewardTermSpec, b: StateBuffers, out: torch.Tensor | None = None,
+                  terminated: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(b.N, device=self.device)
+        ct = reward_term_to_ctypes(term)
+        st, mdp = b.state_view(), b.mdp_state()
+        nat.check(self.lib.rl_term_eval(self._ctx, b.N, C.byref(ct), C.byref(st), C.byref(mdp), nat.ptr_of(terminated),
+                                        out.data_ptr(), self._stream()))
+        return out

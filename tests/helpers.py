@@ -1,0 +1,96 @@
+"""Shared helpers of the parity tests: build spec / synthetic state / engine, run both sides, compare."""
+
+from __future__ import annotations
+
+import torch
+
+from oracle import mdp_port as port
+from robot_lab_b200 import _native as nat
+from robot_lab_b200.spec import compact_layout, compile_step_spec
+from robot_lab_b200.synthetic import make_state
+from robot_lab_b200.tasks import make_env_cfg
+
+# fp32 parity bar of BASELINE.json's north_star: 1e-5 relative. The absolute floor covers outputs whose true
+# value is ~0 (sums with cancellation, products with a 0/1 mask): 1e-6 times the O(1) scale of the inputs.
+RTOL, ATOL = 1e-5, 1e-6
+
+TASKS = {
+    "a1_flat": "RobotLab-Isaac-Velocity-Flat-Unitree-A1-v0",
+    "go2_flat": "RobotLab-Isaac-Velocity-Flat-Unitree-Go2-v0",
+    "go2_rough": "RobotLab-Isaac-Velocity-Rough-Unitree-Go2-v0",
+    "g1_rough": "RobotLab-Isaac-Velocity-Rough-Unitree-G1-v0",
+    "g1_rough_37": "RobotLab-Isaac-Velocity-Rough-Unitree-G1-37dof-v0",
+    "g1_flat": "RobotLab-Isaac-Velocity-Flat-Unitree-G1-v0",
+    "a1_rough": "RobotLab-Isaac-Velocity-Rough-Unitree-A1-v0",
+}
+
+
+def make_spec(task_key: str, full_layout: bool = False):
+    cfg = make_env_cfg(TASKS[task_key])
+    layout = cfg.scene.make_layout() if full_layout else compact_layout(cfg)
+    return cfg, compile_step_spec(cfg, layout)
+
+
+def rnd_inputs(st: dict) -> dict:
+    return {"cmd_uniforms": st["cmd_uniforms"], "obs_uniforms_policy": st["obs_uniforms_policy"],
+            "obs_uniforms_critic": st["obs_uniforms_critic"]}
+
+
+def oracle_step(spec, st, skip_done_envs=False, rnd=None):
+    return port.step(spec, st, rnd if rnd is not None else rnd_inputs(st), skip_done_envs=skip_done_envs)
+
+
+def gpu_step_outputs(b) -> dict:
+    """Device outputs of one rl_step call, in the oracle's logical shapes (CPU tensors)."""
+    n = int(b.n_reset.item())
+    out = {
+        "episode_length": b.logical("episode_length").cpu(),
+        "terminated": b.terminated.cpu().bool(), "truncated": b.truncated.cpu().bool(),
+        "done_bits": b.done_bits.cpu().to(torch.int32),
+        "reward": b.reward.cpu(), "episode_sums": b.logical("episode_sums").cpu().contiguous(),
+        "step_reward": b.logical("step_reward").cpu().contiguous(), "reset_ids": b.reset_ids[:n].cpu(),
+        "command": b.logical("command").cpu().contiguous(), "heading_target": b.logical("heading_target").cpu(),
+        "time_left": b.logical("time_left").cpu(), "is_heading_env": b.logical("is_heading_env").cpu(),
+        "is_standing_env": b.logical("is_standing_env").cpu(),
+        "metric_error_vel_xy": b.logical("metric_error_vel_xy").cpu(),
+        "metric_error_vel_yaw": b.logical("metric_error_vel_yaw").cpu(),
+    }
+    if b.obs[0] is not None:
+        out["obs_policy"] = b.obs[0].cpu()
+    if b.obs[1] is not None:
+        out["obs_critic"] = b.obs[1].cpu()
+    return out
+
+
+EXACT_KEYS = ("episode_length", "terminated", "truncated", "done_bits", "reset_ids", "is_heading_env", "is_standing_env")
+
+
+def compare_outputs(got: dict, ref: dict, rtol=RTOL, atol=ATOL, keys=None) -> dict:
+    """Returns {key: (max_abs_err, n_bad)}; raises AssertionError listing every failing key."""
+    report, failures = {}, []
+    for k in keys or ref.keys():
+        if k not in got:
+            continue
+        g, r = got[k], ref[k]
+        if k in EXACT_KEYS:
+            ok = g.shape == r.shape and torch.equal(g.to(r.dtype), r)
+            report[k] = (0.0 if ok else float("nan"), 0 if ok else int((g.to(r.dtype) != r).sum()) if g.shape == r.shape else -1)
+            if not ok:
+                failures.append(f"{k}: exact mismatch ({report[k][1]} elements)")
+            continue
+        g, r = g.float(), r.float()
+        if g.shape != r.shape:
+            failures.append(f"{k}: shape {tuple(g.shape)} vs {tuple(r.shape)}")
+            continue
+        both_inf = torch.isinf(g) & torch.isinf(r) & (g == r)
+        err = torch.where(both_inf, torch.zeros_like(g), (g - r).abs())
+        bad = err > (atol + rtol * r.abs())
+        bad |= torch.isnan(g) != torch.isnan(r)
+        report[k] = (float(err[~torch.isnan(err)].max()) if err.numel() else 0.0, int(bad.sum()))
+        if bad.any():
+            i = int(bad.flatten().nonzero()[0])
+            failures.append(f"{k}: {int(bad.sum())} bad, max abs err {report[k][0]:.3e}, first bad flat idx {i}: "
+                            f"got {g.flatten()[i].item():.9g} want {r.flatten()[i].item():.9g}")
+    if failures:
+        raise AssertionError("parity failures:\n  " + "\n  ".join(failures))
+    return report
