@@ -33,12 +33,12 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 3
+#define RL_ABI_VERSION 5
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
-#define RL_MAX_TIME_BODIES 16   /* bodies in the air/contact-time tensors                       */
-#define RL_MAX_ASSET_BODIES 16  /* bodies in the body_pos_w / body_lin_vel_w tensors            */
+#define RL_MAX_TIME_BODIES 64   /* bodies in the air/contact-time tensors                       */
+#define RL_MAX_ASSET_BODIES 64  /* bodies in the body_pos_w / body_lin_vel_w tensors            */
 #define RL_MAX_REWARD_TERMS 48
 #define RL_MAX_OBS_TERMS 12
 #define RL_MAX_DONE_TERMS 8
@@ -291,6 +291,14 @@ typedef struct RlMdpState {
   RlField episode_sums;          /* K   reward_manager._episode_sums                       */
 } RlMdpState;
 
+/* Logging reductions produced at reset (extras["log"] of the reference [IL]). */
+typedef struct RlResetLog {
+  float* episode_sum_mean;       /* [K]  mean over reset ids of episode_sums (caller divides by
+                                         max_episode_length_s as RewardManager.reset does)  */
+  float* done_term_count;        /* [RL_MAX_DONE_TERMS] count over reset ids                 */
+  float* metric_mean;            /* [2]  error_vel_xy, error_vel_yaw means                   */
+} RlResetLog;
+
 /* Outputs of one step. Any pointer may be NULL to skip that output. */
 typedef struct RlStepOut {
   float* obs[RL_NUM_OBS_GROUPS]; /* [N, obs_pitch[g]] rows                                 */
@@ -302,6 +310,7 @@ typedef struct RlStepOut {
   RlField step_reward;           /* K  reward_manager._step_reward (value / dt)            */
   int32_t* reset_ids;            /* [N] ascending ids with terminated|truncated            */
   int32_t* n_reset;              /* [1]                                                    */
+  RlResetLog reset_log;          /* written by RL_PHASE_RESET launches                     */
 } RlStepOut;
 
 /* Which manager phases a launch evaluates (bit flags). */
@@ -313,6 +322,10 @@ enum RlPhase {
   RL_PHASE_COMPACT = 16,    /* reset id compaction (ascending)                              */
   RL_PHASE_SKIP_DONE_ENVS = 32, /* COMMAND/OBS only for envs that are not done this step
                                    (they are refreshed after the external reset instead)   */
+  RL_PHASE_RESET = 64,      /* env_ids launches only: manager reset of those envs BEFORE the other phases -
+                               logging means (RlStepOut.reset_log), zero episode sums / metrics / actions /
+                               episode length, command resample. RESET|COMMAND|OBS is the whole post-reset
+                               part of ManagerBasedRLEnv.step() [IL] in one launch                     */
   RL_PHASE_ALL = 31
 };
 
@@ -320,18 +333,14 @@ enum RlPhase {
 typedef struct RlRandom {
   uint64_t seed;
   uint64_t step;                 /* step counter: part of the Philox counter                */
+  const uint64_t* step_counter;  /* optional DEVICE counter added to `step` (the env's common_step_counter
+                                    [IL]); rl_process_action increments it, so a captured CUDA graph
+                                    draws fresh noise on every replay                          */
   int64_t env_id_offset;         /* global id of env 0 of this shard (multi-GPU)            */
   const float* cmd_uniforms;     /* [RL_NUM_CMD_UNIFORMS][N] U[0,1) or NULL                 */
   const float* obs_uniforms[RL_NUM_OBS_GROUPS]; /* [N, group dim] U[0,1) or NULL           */
 } RlRandom;
 
-/* Logging reductions produced at reset (extras["log"] of the reference [IL]). */
-typedef struct RlResetLog {
-  float* episode_sum_mean;       /* [K]  mean over reset ids of episode_sums (caller divides by
-                                         max_episode_length_s as RewardManager.reset does)  */
-  float* done_term_count;        /* [RL_MAX_DONE_TERMS] count over reset ids                 */
-  float* metric_mean;            /* [2]  error_vel_xy, error_vel_yaw means                   */
-} RlResetLog;
 
 typedef struct RlCtx RlCtx;
 
@@ -346,11 +355,14 @@ void rl_ctx_destroy(RlCtx* ctx);
 
 /* Tuning knobs (envs per CTA, lanes per env). 0 = library default. */
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env);
+/* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
+ * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
+int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
 
 /* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
                       const RlField* joint_target /* J, native order; columns not driven are untouched */,
-                      void* stream);
+                      uint64_t* step_counter /* device, may be NULL: incremented by 1 */, void* stream);
 
 /* The fused step over envs [0, num_envs), or over env_ids[0 .. *n_env_ids) when env_ids != NULL
  * (n_env_ids is a DEVICE pointer so that no host sync is needed after the reset compaction). */

@@ -14,11 +14,11 @@ from pathlib import Path
 
 import torch
 
-RL_ABI_VERSION = 3
+RL_ABI_VERSION = 5
 RL_MAX_JOINTS = 64
 RL_MAX_BODIES = 64
-RL_MAX_TIME_BODIES = 16
-RL_MAX_ASSET_BODIES = 16
+RL_MAX_TIME_BODIES = 64
+RL_MAX_ASSET_BODIES = 64
 RL_MAX_REWARD_TERMS = 48
 RL_MAX_OBS_TERMS = 12
 RL_MAX_DONE_TERMS = 8
@@ -28,6 +28,7 @@ RL_NUM_CMD_UNIFORMS = 7
 
 # enum RlPhase
 PHASE_DONES, PHASE_REWARDS, PHASE_COMMAND, PHASE_OBS, PHASE_COMPACT, PHASE_SKIP_DONE_ENVS = 1, 2, 4, 8, 16, 32
+PHASE_RESET = 64
 PHASE_ALL = 31
 
 # enum RlRewardType (name -> id); checked against the header by tests/test_abi.py
@@ -140,23 +141,23 @@ class RlMdpState(C.Structure):
     _fields_ = [(n, RlField) for n in _MDP_FIELDS]
 
 
+class RlResetLog(C.Structure):
+    _fields_ = [("episode_sum_mean", C.c_void_p), ("done_term_count", C.c_void_p), ("metric_mean", C.c_void_p)]
+
+
 class RlStepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p * RL_NUM_OBS_GROUPS), ("obs_pitch", C.c_int64 * RL_NUM_OBS_GROUPS),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("done_bits", C.c_void_p),
-        ("step_reward", RlField), ("reset_ids", C.c_void_p), ("n_reset", C.c_void_p),
+        ("step_reward", RlField), ("reset_ids", C.c_void_p), ("n_reset", C.c_void_p), ("reset_log", RlResetLog),
     ]
 
 
 class RlRandom(C.Structure):
     _fields_ = [
-        ("seed", C.c_uint64), ("step", C.c_uint64), ("env_id_offset", C.c_int64),
+        ("seed", C.c_uint64), ("step", C.c_uint64), ("step_counter", C.c_void_p), ("env_id_offset", C.c_int64),
         ("cmd_uniforms", C.c_void_p), ("obs_uniforms", C.c_void_p * RL_NUM_OBS_GROUPS),
     ]
-
-
-class RlResetLog(C.Structure):
-    _fields_ = [("episode_sum_mean", C.c_void_p), ("done_term_count", C.c_void_p), ("metric_mean", C.c_void_p)]
 
 
 _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlActionCfg, RlStepSpec, RlField,
@@ -164,7 +165,7 @@ _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlAct
 
 EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
-    "rl_ctx_set_launch_config", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
+    "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -204,8 +205,9 @@ def load() -> C.CDLL:
     lib.rl_ctx_destroy.argtypes = [C.c_void_p]
     lib.rl_ctx_destroy.restype = None
     lib.rl_ctx_set_launch_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.rl_ctx_set_pdl.argtypes = [C.c_void_p, C.c_int]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),
-                                      C.POINTER(RlField), C.c_void_p]
+                                      C.POINTER(RlField), C.c_void_p, C.c_void_p]
     lib.rl_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlStateView), C.POINTER(RlMdpState),
                             C.POINTER(RlStepOut), C.POINTER(RlRandom), C.c_uint32, C.c_void_p, C.c_void_p,
                             C.c_void_p]

@@ -32,6 +32,7 @@
 
 #define RL_SPEC_SLOTS 3
 #define RL_PI_F 3.14159265358979323846f
+#define RL_LOG_STRIDE 64  // >= RL_MAX_REWARD_TERMS + RL_MAX_DONE_TERMS + 2
 
 __constant__ RlStepSpec c_spec[RL_SPEC_SLOTS];
 
@@ -93,6 +94,8 @@ struct KArgs {
   Layout L;
   unsigned int* ticket;
   uint32_t* cta_mask;
+  float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions
+  int use_pdl;
   // single-term evaluation (rl_term_eval)
   const RlRewardTerm* adhoc;
   const uint8_t* ext_terminated;
@@ -164,7 +167,8 @@ enum { RL_STREAM_COMMAND = 1, RL_STREAM_RESET_COMMAND = 2, RL_STREAM_OBS = 16 };
 
 __device__ __forceinline__ uint4 rl_philox(const RlRandom& r, long long env, uint32_t stream, uint32_t block) {
   const unsigned long long genv = (unsigned long long)(env + r.env_id_offset);
-  uint4 ctr = make_uint4((uint32_t)genv, (uint32_t)r.step, (uint32_t)(r.step >> 32) ^ (uint32_t)(genv >> 32),
+  const unsigned long long step = r.step + (r.step_counter ? *r.step_counter : 0ull);
+  uint4 ctr = make_uint4((uint32_t)genv, (uint32_t)step, (uint32_t)(step >> 32) ^ (uint32_t)(genv >> 32),
                          (stream << 16) | block);
   return philox4x32_10(ctr, make_uint2((uint32_t)r.seed, (uint32_t)(r.seed >> 32)));
 }
@@ -770,17 +774,30 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   const Layout& L = a.L;
   constexpr int NT = E * LPE;
   const int tid = threadIdx.x;
+  const uint32_t ph = a.phases;
+  if (a.use_pdl) {
+    // launch-latency overlap only: every read below may depend on the predecessor, so wait first
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
   const int env0 = blockIdx.x * E;
+  if (MODE == 0 && (ph & RL_PHASE_RESET) && a.has_ids && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
+    // nothing to reset: the logged scalars are defined as 0
+    const int K0 = S.num_reward_terms;
+    if (tid < K0) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
+    else if (tid < K0 + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K0] = 0.f; }
+    else if (tid < K0 + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K0 - RL_MAX_DONE_TERMS] = 0.f; }
+  }
   if (env0 >= n_total && !(a.phases & RL_PHASE_COMPACT)) return;
   const int nvalid = max(0, min(E, n_total - env0));
   const int32_t* ids = a.has_ids ? a.env_ids : nullptr;
-  const uint32_t ph = a.phases;
   const int J = S.num_joints, A = S.action.n_actions, K = S.num_reward_terms;
   const int Bt = S.num_time_bodies, Ba = S.num_asset_bodies, R = S.num_rays;
   const int HW = S.hist_len * S.num_hist_bodies * 3;
   const bool need_hist = (MODE == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
   const bool need_rays = (MODE == 0) && (ph & RL_PHASE_OBS) && R > 0;
+  const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
 
   // ---- load phase --------------------------------------------------------------------------------
   const bool full = (nvalid == E) && (ids == nullptr);
@@ -854,6 +871,21 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         load_soa<E, float>(sm, L.cmdu, f, RL_NUM_CMD_UNIFORMS, env0, nvalid, ids, tid, NT);
       }
     }
+    if (do_reset) {
+      load_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
+      load_soa<E, float>(sm, L.mxy, a.mdp.metric_error_vel_xy, 1, env0, nvalid, ids, tid, NT);
+      load_soa<E, float>(sm, L.myaw, a.mdp.metric_error_vel_yaw, 1, env0, nvalid, ids, tid, NT);
+      load_soa<E, float>(sm, L.head, a.mdp.heading_target, 1, env0, nvalid, ids, tid, NT);
+      load_soa<E, uint8_t>(sm, L.ishead, a.mdp.is_heading_env, 1, env0, nvalid, ids, tid, NT);
+      if (a.out.done_bits != nullptr) {
+        RlField f{a.out.done_bits, 1, 0};
+        load_soa<E, uint8_t>(sm, L.flags, f, 1, env0, nvalid, ids, tid, NT);
+      }
+      if (a.rnd.cmd_uniforms != nullptr && !(ph & RL_PHASE_COMMAND)) {
+        RlField f{const_cast<float*>(a.rnd.cmd_uniforms), 1, (int64_t)a.N};
+        load_soa<E, float>(sm, L.cmdu, f, RL_NUM_CMD_UNIFORMS, env0, nvalid, ids, tid, NT);
+      }
+    }
     if (need_rays) {
       load_soa<E, float>(sm, L.raypos, a.st.ray_sensor_pos_z, 1, env0, nvalid, ids, tid, NT);
       if (!rays_bulk)
@@ -878,6 +910,51 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
   uint32_t done_any = 0;
   if (nvalid > 0) {
+    if (do_reset) {
+      // -- logging partials of this CTA (summed in CTA order by the last CTA -> deterministic) --
+      if (tid < K + RL_MAX_DONE_TERMS + 2) {
+        float acc = 0.f;
+        for (int el = 0; el < nvalid; ++el) {
+          if (tid < K) acc += sm[L.sums + tid * E + el];
+          else if (tid < K + RL_MAX_DONE_TERMS)
+            acc += (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + el]) >> (tid - K)) & 1) : 0.f;
+          else acc += sm[(tid == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + el];
+        }
+        a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = acc;
+      }
+      __syncthreads();
+      // -- manager resets: RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0 --
+      for (int i = tid; i < E * K; i += NT) sm[L.sums + i] = 0.f;
+      for (int i = tid; i < E * A; i += NT) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
+      if (tid < E) {
+        const int el = tid;
+        sm[L.mxy + el] = 0.f; sm[L.myaw + el] = 0.f; sm[L.eplen + el] = __int_as_float(0);
+        const RlCommandCfg& cc = S.command;
+        const long long ev = ids ? (long long)ids[env0 + min(el, nvalid - 1)] : (long long)(env0 + el);
+        float u[RL_NUM_CMD_UNIFORMS];
+        if (a.rnd.cmd_uniforms != nullptr) {
+#pragma unroll
+          for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * E + el];
+        } else {
+          const uint4 r0 = rl_philox(a.rnd, ev, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(a.rnd, ev, RL_STREAM_RESET_COMMAND, 1);
+          u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+          u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
+        }
+        float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
+        float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
+        const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
+        const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+        c0 *= keep; c1 *= keep;
+        sm[L.cmd + 0 * E + el] = c0; sm[L.cmd + 1 * E + el] = c1; sm[L.cmd + 2 * E + el] = c2;
+        sm[L.tleft + el] = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
+        if (cc.heading_command) {
+          sm[L.head + el] = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
+          sm[L.ishead + el] = __int_as_float((u[5] <= cc.rel_heading_envs) ? 1 : 0);
+        }
+        sm[L.isstand + el] = __int_as_float((u[6] <= cc.rel_standing_envs) ? 1 : 0);
+      }
+      __syncthreads();
+    }
     EnvCtx c = make_ctx<E>(sm, L, e);
     if (need_hist) {
       body_max_norm<E, LPE>(sm, L, S, e, sub);
@@ -985,7 +1062,13 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       store_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
       store_soa<E, float>(sm, L.stepr, a.out.step_reward, K, env0, nvalid, ids, tid, NT);
     }
-    if (ph & RL_PHASE_COMMAND) {
+    if (do_reset) {
+      store_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
+      store_soa<E, float>(sm, L.act, a.mdp.action, A, env0, nvalid, ids, tid, NT);
+      store_soa<E, float>(sm, L.pact, a.mdp.prev_action, A, env0, nvalid, ids, tid, NT);
+      store_soa<E, int32_t>(sm, L.eplen, a.mdp.episode_length, 1, env0, nvalid, ids, tid, NT);
+    }
+    if ((ph & RL_PHASE_COMMAND) || do_reset) {
       store_soa<E, float>(sm, L.cmd, a.mdp.command, 3, env0, nvalid, ids, tid, NT);
       store_soa<E, float>(sm, L.head, a.mdp.heading_target, 1, env0, nvalid, ids, tid, NT);
       store_soa<E, float>(sm, L.tleft, a.mdp.time_left, 1, env0, nvalid, ids, tid, NT);
@@ -1044,6 +1127,28 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       return;
     }
   }
+  if (do_reset && nvalid > 0) {
+    const int n_cta = (n_total + E - 1) / E;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(a.ticket, 1u);
+      s_last = (prev == (unsigned)(n_cta - 1));
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < K + RL_MAX_DONE_TERMS + 2) {
+        float tot = 0.f;
+        for (int g = 0; g < n_cta; ++g) tot += __ldcg(a.log_partials + (size_t)g * RL_LOG_STRIDE + tid);
+        const RlResetLog& lg = a.out.reset_log;
+        if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / (float)n_total; }
+        else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
+        else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / (float)n_total;
+      }
+      if (tid == 0) *a.ticket = 0u;
+    }
+  }
   if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
 }
 
@@ -1051,7 +1156,12 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
 // process_action: ActionManager.process_action + JointAction.process_actions [IL]
 // ---------------------------------------------------------------------------------------------------
 __global__ void process_action_kernel(int N, int slot, RlField new_action, RlField action, RlField prev_action,
-                                      RlField target) {
+                                      RlField target, unsigned long long* step_counter, int use_pdl) {
+  if (use_pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
   const RlActionCfg& ac = c_spec[slot].action;
   const int A = ac.n_actions;
   const long long total = (long long)N * A;
@@ -1073,93 +1183,6 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Reset path: logging means (deterministic block reductions) + per-env manager resets
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float block_sum(float v, float* s_red) {
-  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) s_red[w] = v;
-  __syncthreads();
-  float r = 0.f;
-  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += s_red[i];
-  return r;  // valid on thread 0
-}
-
-// grid = K + RL_MAX_DONE_TERMS + 2 blocks; block b reduces one logged scalar over the reset ids
-__global__ void reset_log_kernel(int slot, RlMdpState mdp, const uint8_t* done_bits, RlResetLog log,
-                                 const int32_t* ids, const int32_t* n_ids) {
-  __shared__ float s_red[32];
-  const RlStepSpec& S = c_spec[slot];
-  const int K = S.num_reward_terms;
-  const int n = *n_ids;
-  const int b = blockIdx.x;
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long env = ids[i];
-    if (b < K) {
-      acc += static_cast<const float*>(mdp.episode_sums.ptr)[env * mdp.episode_sums.env_stride + (long long)b * mdp.episode_sums.comp_stride];
-    } else if (b < K + RL_MAX_DONE_TERMS) {
-      if (done_bits) acc += (float)((done_bits[env] >> (b - K)) & 1);
-    } else if (b == K + RL_MAX_DONE_TERMS) {
-      acc += static_cast<const float*>(mdp.metric_error_vel_xy.ptr)[env * mdp.metric_error_vel_xy.env_stride];
-    } else {
-      acc += static_cast<const float*>(mdp.metric_error_vel_yaw.ptr)[env * mdp.metric_error_vel_yaw.env_stride];
-    }
-  }
-  const float tot = block_sum(acc, s_red);
-  if (threadIdx.x == 0) {
-    const float inv = n > 0 ? 1.f / (float)n : 0.f;
-    if (b < K) { if (log.episode_sum_mean) log.episode_sum_mean[b] = n > 0 ? tot / (float)n : 0.f; }
-    else if (b < K + RL_MAX_DONE_TERMS) { if (log.done_term_count) log.done_term_count[b - K] = tot; }
-    else if (log.metric_mean) log.metric_mean[b - K - RL_MAX_DONE_TERMS] = n > 0 ? tot / (float)n : 0.f;
-    (void)inv;
-  }
-}
-
-__global__ void reset_apply_kernel(int N, int slot, RlMdpState mdp, RlRandom rnd, const int32_t* ids, const int32_t* n_ids) {
-  const RlStepSpec& S = c_spec[slot];
-  const RlCommandCfg& cc = S.command;
-  const int n = *n_ids;
-  const int K = S.num_reward_terms, A = S.action.n_actions;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const long long env = ids[i];
-    for (int k = 0; k < K; ++k)
-      static_cast<float*>(mdp.episode_sums.ptr)[env * mdp.episode_sums.env_stride + (long long)k * mdp.episode_sums.comp_stride] = 0.f;
-    for (int c = 0; c < A; ++c) {
-      static_cast<float*>(mdp.action.ptr)[env * mdp.action.env_stride + (long long)c * mdp.action.comp_stride] = 0.f;
-      static_cast<float*>(mdp.prev_action.ptr)[env * mdp.prev_action.env_stride + (long long)c * mdp.prev_action.comp_stride] = 0.f;
-    }
-    static_cast<float*>(mdp.metric_error_vel_xy.ptr)[env * mdp.metric_error_vel_xy.env_stride] = 0.f;
-    static_cast<float*>(mdp.metric_error_vel_yaw.ptr)[env * mdp.metric_error_vel_yaw.env_stride] = 0.f;
-    static_cast<int32_t*>(mdp.episode_length.ptr)[env * mdp.episode_length.env_stride] = 0;
-    // CommandTerm.reset -> _resample: time_left + command (V/mdp/commands.py:43-47)
-    float u[RL_NUM_CMD_UNIFORMS];
-    if (rnd.cmd_uniforms != nullptr) {
-      for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = rnd.cmd_uniforms[(long long)q * N + env];
-    } else {
-      const uint4 r0 = rl_philox(rnd, env, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(rnd, env, RL_STREAM_RESET_COMMAND, 1);
-      u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
-      u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
-    }
-    float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
-    float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
-    const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
-    const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
-    c0 *= keep; c1 *= keep;
-    float* cmd = static_cast<float*>(mdp.command.ptr) + env * mdp.command.env_stride;
-    cmd[0] = c0; cmd[mdp.command.comp_stride] = c1; cmd[2 * mdp.command.comp_stride] = c2;
-    static_cast<float*>(mdp.time_left.ptr)[env * mdp.time_left.env_stride] =
-        u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
-    if (cc.heading_command) {
-      static_cast<float*>(mdp.heading_target.ptr)[env * mdp.heading_target.env_stride] =
-          u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
-      static_cast<uint8_t*>(mdp.is_heading_env.ptr)[env * mdp.is_heading_env.env_stride] = (u[5] <= cc.rel_heading_envs) ? 1 : 0;
-    }
-    static_cast<uint8_t*>(mdp.is_standing_env.ptr)[env * mdp.is_standing_env.env_stride] = (u[6] <= cc.rel_standing_envs) ? 1 : 0;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
 }  // namespace
@@ -1172,9 +1195,11 @@ struct RlCtx {
   Layout L;
   unsigned int* ticket;
   uint32_t* cta_mask;
+  float* log_partials;
   int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
   int sm_count;
+  int use_pdl;
 };
 
 namespace {
@@ -1266,8 +1291,14 @@ int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   }
   const int grid = (n_items + E - 1) / E;
   if (grid <= 0) return RL_OK;
-  mdp_step_kernel<E, LPE, MODE><<<grid, E * LPE, smem, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E * LPE); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<E, LPE, MODE>, a));
   return RL_OK;
 }
 
@@ -1288,10 +1319,14 @@ int dispatch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
 int ensure_scratch(RlCtx* ctx, int grid) {
   if (grid <= ctx->cta_mask_cap) return RL_OK;
   if (ctx->cta_mask) CUDA_TRY(cudaFree(ctx->cta_mask));
+  if (ctx->log_partials) CUDA_TRY(cudaFree(ctx->log_partials));
   ctx->cta_mask = nullptr;
+  ctx->log_partials = nullptr;
   const int cap = grid * 2 + 64;
   CUDA_TRY(cudaMalloc(&ctx->cta_mask, sizeof(uint32_t) * cap));
   CUDA_TRY(cudaMemset(ctx->cta_mask, 0, sizeof(uint32_t) * cap));
+  CUDA_TRY(cudaMalloc(&ctx->log_partials, sizeof(float) * (size_t)cap * RL_LOG_STRIDE));
+  CUDA_TRY(cudaMemset(ctx->log_partials, 0, sizeof(float) * (size_t)cap * RL_LOG_STRIDE));
   ctx->cta_mask_cap = cap;
   return RL_OK;
 }
@@ -1370,6 +1405,7 @@ void rl_ctx_destroy(RlCtx* ctx) {
   DeviceGuard guard(ctx->device);
   if (ctx->ticket) cudaFree(ctx->ticket);
   if (ctx->cta_mask) cudaFree(ctx->cta_mask);
+  if (ctx->log_partials) cudaFree(ctx->log_partials);
   if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
@@ -1393,8 +1429,14 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env) {
   return RL_OK;
 }
 
+int rl_ctx_set_pdl(RlCtx* ctx, int enabled) {
+  if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
+  ctx->use_pdl = enabled ? 1 : 0;
+  return RL_OK;
+}
+
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
-                      const RlField* joint_target, void* stream) {
+                      const RlField* joint_target, uint64_t* step_counter, void* stream) {
   if (!ctx || !new_action || !mdp) return fail(RL_EINVAL, "rl_process_action: null argument%s", "");
   if (num_envs <= 0) return RL_OK;
   if (!new_action->ptr || !mdp->action.ptr) return fail(RL_EINVAL, "rl_process_action: action pointers required%s", "");
@@ -1404,9 +1446,15 @@ int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, c
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
   if (blocks <= 0) return RL_OK;
-  process_action_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((int)num_envs, ctx->slot, *new_action, mdp->action,
-                                                                      mdp->prev_action, tgt);
-  CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, process_action_kernel, (int)num_envs, ctx->slot, *new_action, mdp->action,
+                              mdp->prev_action, tgt, (unsigned long long*)step_counter, ctx->use_pdl));
   return RL_OK;
 }
 
@@ -1444,11 +1492,16 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   }
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
     if (out->obs[g] && out->obs_pitch[g] < s.obs[g].dim) return fail(RL_EINVAL, "rl_step: obs_pitch[%s%lld] smaller than the group dim", "", g);
+  if ((phases & RL_PHASE_RESET) && !env_ids) return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET needs env_ids%s", "");
+  if ((phases & RL_PHASE_RESET) && (phases & (RL_PHASE_DONES | RL_PHASE_REWARDS))) return fail(RL_EINVAL, "rl_step: RESET combines with COMMAND/OBS only%s", "");
+  if ((phases & RL_PHASE_RESET) && (!mdp->episode_sums.ptr || !mdp->prev_action.ptr || !mdp->heading_target.ptr || !mdp->time_left.ptr ||
+      !mdp->is_heading_env.ptr || !mdp->is_standing_env.ptr || !mdp->metric_error_vel_xy.ptr || !mdp->metric_error_vel_yaw.ptr))
+    return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET needs every RlMdpState field%s", "");
   if (env_ids && (phases & RL_PHASE_COMPACT)) return fail(RL_EINVAL, "rl_step: compaction is not available on an env_ids subset%s", "");
   if ((phases & RL_PHASE_COMPACT) && !(phases & RL_PHASE_DONES)) return fail(RL_EINVAL, "rl_step: COMPACT needs DONES%s", "");
   DeviceGuard guard(ctx->device);
   const int grid = (int)((num_envs + ctx->E - 1) / ctx->E);
-  if (phases & RL_PHASE_COMPACT) {
+  if (phases & (RL_PHASE_COMPACT | RL_PHASE_RESET)) {
     if (grid > ctx->cta_mask_cap) {
       cudaStreamCaptureStatus cs;
       CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
@@ -1462,7 +1515,7 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   a.N = (int)num_envs; a.slot = ctx->slot; a.phases = phases; a.has_ids = env_ids != nullptr;
   a.st = *state; a.mdp = *mdp; a.out = *out; a.rnd = *rnd;
   a.env_ids = env_ids; a.n_env_ids = n_env_ids; a.L = ctx->L;
-  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask;
+  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
   return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
@@ -1475,17 +1528,22 @@ int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uin
       !mdp->metric_error_vel_yaw.ptr || !mdp->episode_length.ptr)
     return fail(RL_EINVAL, "rl_reset_envs: every RlMdpState field is required%s", "");
   DeviceGuard guard(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (log && (log->episode_sum_mean || log->done_term_count || log->metric_mean)) {
-    const int blocks = ctx->spec.num_reward_terms + RL_MAX_DONE_TERMS + 2;
-    reset_log_kernel<<<blocks, 256, 0, st>>>(ctx->slot, *mdp, done_bits, *log, env_ids, n_env_ids);
-    CUDA_TRY(cudaGetLastError());
+  const int grid = (int)((num_envs + ctx->E - 1) / ctx->E);
+  if (grid > ctx->cta_mask_cap) {
+    cudaStreamCaptureStatus cs;
+    CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) return fail(RL_EINVAL, "rl_reset_envs: first call at this num_envs must happen outside stream capture%s", "");
+    int rc = ensure_scratch(ctx, grid);
+    if (rc != RL_OK) return rc;
   }
-  int blocks = (int)((num_envs + 127) / 128);
-  if (blocks > ctx->sm_count) blocks = ctx->sm_count;
-  reset_apply_kernel<<<blocks, 128, 0, st>>>((int)num_envs, ctx->slot, *mdp, *rnd, env_ids, n_env_ids);
-  CUDA_TRY(cudaGetLastError());
-  return RL_OK;
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.slot = ctx->slot; a.phases = RL_PHASE_RESET; a.has_ids = 1;
+  a.mdp = *mdp; a.rnd = *rnd; a.out.done_bits = const_cast<uint8_t*>(done_bits);
+  if (log) a.out.reset_log = *log;
+  a.env_ids = env_ids; a.n_env_ids = n_env_ids; a.L = ctx->L;
+  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
 int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const RlStateView* state, const RlMdpState* mdp,
@@ -1508,7 +1566,7 @@ int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const R
   memset(&a, 0, sizeof(a));
   a.N = (int)num_envs; a.slot = ctx->slot; a.phases = 0; a.has_ids = 0;
   a.st = *state; a.mdp = *mdp; a.L = ctx->L;
-  a.adhoc = dev; a.ext_terminated = terminated; a.term_out = out;
+  a.adhoc = dev; a.ext_terminated = terminated; a.term_out = out; a.use_pdl = 0;
   return dispatch_step<1>(ctx, a, (int)num_envs, st);
 }
 

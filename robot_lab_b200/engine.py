@@ -45,21 +45,26 @@ class MdpStepEngine:
     def set_launch_config(self, envs_per_cta: int = 0, lanes_per_env: int = 0) -> None:
         nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, envs_per_cta, lanes_per_env))
 
+    def set_pdl(self, enabled: bool) -> None:
+        """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""
+        nat.check(self.lib.rl_ctx_set_pdl(self._ctx, int(enabled)))
+
     def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
         return StateBuffers(self.spec, num_envs, self.device, layout)
 
     # ---- the five entry points ----------------------------------------------------------------------
-    def process_action(self, b: StateBuffers, with_target: bool = True) -> None:
+    def process_action(self, b: StateBuffers, with_target: bool = True, advance_step_counter: bool = True) -> None:
         na = b.field("new_action")
         mdp = b.mdp_state()
         tgt = b.field("joint_target") if with_target else nat.RlField(None, 0, 0)
-        nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), self._stream()))
+        ctr = b.step_counter.data_ptr() if advance_step_counter else None
+        nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), ctr, self._stream()))
 
     def step(self, b: StateBuffers, phases: int = nat.PHASE_ALL, seed: int = 0, step: int = 0, env_id_offset: int = 0,
              use_random_inputs: bool = True, env_ids: torch.Tensor | None = None,
-             n_env_ids: torch.Tensor | None = None) -> None:
+             n_env_ids: torch.Tensor | None = None, use_step_counter: bool = False) -> None:
         st, mdp, out = b.state_view(), b.mdp_state(), b.step_out()
-        rnd = b.random(seed, step, env_id_offset, use_random_inputs)
+        rnd = b.random(seed, step, env_id_offset, use_random_inputs, use_step_counter)
         nat.check(self.lib.rl_step(self._ctx, b.N, C.byref(st), C.byref(mdp), C.byref(out), C.byref(rnd), phases,
                                    nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), self._stream()))
 
@@ -70,6 +75,14 @@ class MdpStepEngine:
         log = b.reset_log() if with_log else nat.RlResetLog()
         nat.check(self.lib.rl_reset_envs(self._ctx, b.N, C.byref(mdp), b.done_bits.data_ptr(), C.byref(rnd), C.byref(log),
                                          nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), self._stream()))
+
+    def post_reset(self, b: StateBuffers, seed: int = 0, step: int = 0, env_id_offset: int = 0,
+                   use_random_inputs: bool = True, use_step_counter: bool = False) -> None:
+        """Everything ManagerBasedRLEnv.step() [IL] does for the reset ids after the external (physics) reset,
+        in one launch: manager reset + logging means, command.compute, both observation groups."""
+        self.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS, seed=seed, step=step,
+                  env_id_offset=env_id_offset, use_random_inputs=use_random_inputs, env_ids=b.reset_ids,
+                  n_env_ids=b.n_reset, use_step_counter=use_step_counter)
 
     def term_eval(self, term: RewardTermSpec, b: StateBuffers, out: torch.Tensor | None = None,
                   terminated: torch.Tensor | None = None) -> torch.Tensor:

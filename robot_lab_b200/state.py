@@ -5,6 +5,10 @@ loads when a CTA gathers its tile), the sensor streams are AoS rows (contact-for
 hits ``[N, R]``) so that a CTA's tile is one contiguous span for a TMA bulk copy, and policy-facing tensors
 (actions, observation rows) are AoS ``[N, D]`` because the policy network consumes rows.
 
+All per-step *inputs* (what physics + sensors + the policy produce) are carved out of one contiguous device
+arena, all per-step *results* (observation rows, reward, done masks) out of another, each field 256-byte
+aligned: a host-side producer / consumer moves a whole step with ONE copy in each direction.
+
 ``layout="aos"`` stores every field IsaacLab-style (``[N, C]``) instead - same kernels through the strided
 ``RlField`` views; used by tests to cover the generic path and by integrations that hand over PhysX tensors.
 """
@@ -16,29 +20,54 @@ import torch
 from . import _native as nat
 from .spec import StepSpec
 
-# name -> (components fn, dtype, group); components as a function of the spec
-_SOA_STATE = {
-    "root_pos_w": (lambda s: 3, torch.float32), "root_quat_w": (lambda s: 4, torch.float32),
-    "root_lin_vel_w": (lambda s: 3, torch.float32), "root_ang_vel_w": (lambda s: 3, torch.float32),
-    "joint_pos": (lambda s: s.J, torch.float32), "joint_vel": (lambda s: s.J, torch.float32),
-    "joint_acc": (lambda s: s.J, torch.float32), "applied_torque": (lambda s: s.J, torch.float32),
-    "current_air_time": (lambda s: s.Bt, torch.float32), "last_air_time": (lambda s: s.Bt, torch.float32),
-    "current_contact_time": (lambda s: s.Bt, torch.float32), "last_contact_time": (lambda s: s.Bt, torch.float32),
-    "body_pos_w": (lambda s: s.Ba * 3, torch.float32), "body_lin_vel_w": (lambda s: s.Ba * 3, torch.float32),
-    "ray_sensor_pos_z": (lambda s: 1, torch.float32),
+_F32, _U8, _I32 = torch.float32, torch.uint8, torch.int32
+
+# name -> (components as a function of the spec, dtype, preferred layout)
+INPUT_FIELDS = {
+    "root_pos_w": (lambda s: 3, _F32, "soa"), "root_quat_w": (lambda s: 4, _F32, "soa"),
+    "root_lin_vel_w": (lambda s: 3, _F32, "soa"), "root_ang_vel_w": (lambda s: 3, _F32, "soa"),
+    "joint_pos": (lambda s: s.J, _F32, "soa"), "joint_vel": (lambda s: s.J, _F32, "soa"),
+    "joint_acc": (lambda s: s.J, _F32, "soa"), "applied_torque": (lambda s: s.J, _F32, "soa"),
+    "current_air_time": (lambda s: s.Bt, _F32, "soa"), "last_air_time": (lambda s: s.Bt, _F32, "soa"),
+    "current_contact_time": (lambda s: s.Bt, _F32, "soa"), "last_contact_time": (lambda s: s.Bt, _F32, "soa"),
+    "body_pos_w": (lambda s: s.Ba * 3, _F32, "soa"), "body_lin_vel_w": (lambda s: s.Ba * 3, _F32, "soa"),
+    "ray_sensor_pos_z": (lambda s: 1, _F32, "soa"),
+    "net_forces_w_history": (lambda s: s.T * s.B * 3, _F32, "aos"),
+    "ray_hits_z": (lambda s: s.R, _F32, "aos"),
+    "new_action": (lambda s: s.A, _F32, "aos"),
 }
-_AOS_STATE = {
-    "net_forces_w_history": (lambda s: s.T * s.B * 3, torch.float32),
-    "ray_hits_z": (lambda s: s.R, torch.float32),
+MDP_FIELDS = {
+    "command": (lambda s: 3, _F32, "soa"), "heading_target": (lambda s: 1, _F32, "soa"),
+    "time_left": (lambda s: 1, _F32, "soa"), "is_heading_env": (lambda s: 1, _U8, "soa"),
+    "is_standing_env": (lambda s: 1, _U8, "soa"), "metric_error_vel_xy": (lambda s: 1, _F32, "soa"),
+    "metric_error_vel_yaw": (lambda s: 1, _F32, "soa"), "episode_length": (lambda s: 1, _I32, "soa"),
+    "episode_sums": (lambda s: s.K, _F32, "soa"),
+    "action": (lambda s: s.A, _F32, "aos"), "prev_action": (lambda s: s.A, _F32, "aos"),
+    "joint_target": (lambda s: s.J, _F32, "soa"), "step_reward": (lambda s: s.K, _F32, "soa"),
 }
-_SOA_MDP = {
-    "command": (lambda s: 3, torch.float32), "heading_target": (lambda s: 1, torch.float32),
-    "time_left": (lambda s: 1, torch.float32), "is_heading_env": (lambda s: 1, torch.uint8),
-    "is_standing_env": (lambda s: 1, torch.uint8), "metric_error_vel_xy": (lambda s: 1, torch.float32),
-    "metric_error_vel_yaw": (lambda s: 1, torch.float32), "episode_length": (lambda s: 1, torch.int32),
-    "episode_sums": (lambda s: s.K, torch.float32),
-}
-_AOS_MDP = {"action": (lambda s: s.A, torch.float32), "prev_action": (lambda s: s.A, torch.float32)}
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class _Arena:
+    """Named typed views into one contiguous uint8 device buffer."""
+
+    def __init__(self, entries: list[tuple[str, tuple[int, ...], torch.dtype]], device: torch.device):
+        offs, total = {}, 0
+        for name, shape, dtype in entries:
+            nbytes = int(torch.tensor([], dtype=dtype).element_size())
+            for d in shape:
+                nbytes *= d
+            offs[name] = (total, shape, dtype, nbytes)
+            total = _align(total + nbytes)
+        self.nbytes = total
+        self.buf = torch.zeros(max(total, 256), dtype=torch.uint8, device=device)
+        self.views: dict[str, torch.Tensor] = {}
+        for name, (off, shape, dtype, nbytes) in offs.items():
+            self.views[name] = self.buf[off:off + nbytes].view(dtype).view(shape)
+        self.layout = offs
 
 
 class StateBuffers:
@@ -51,40 +80,31 @@ class StateBuffers:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise nat.NativeError("StateBuffers live on a CUDA device - the MDP step has no CPU path")
-        N = self.N
-        self.t: dict[str, torch.Tensor] = {}
+        N, dev = self.N, self.device
         self.kind: dict[str, str] = {}
 
-        def alloc(name, comps, dtype, kind):
+        def shape_of(name, comps, pref):
             c = comps(spec)
-            if kind == "soa" and layout == "soa":
-                self.t[name] = torch.zeros((c, N) if c != 1 else (N,), dtype=dtype, device=self.device)
-                self.kind[name] = "soa"
-            else:
-                self.t[name] = torch.zeros((N, c) if c != 1 else (N,), dtype=dtype, device=self.device)
-                self.kind[name] = "aos"
+            kind = pref if layout == "soa" else "aos"
+            self.kind[name] = kind
+            if c == 1:
+                return (N,)
+            return (c, N) if kind == "soa" else (N, c)
 
-        for name, (comps, dt) in _SOA_STATE.items():
-            alloc(name, comps, dt, "soa")
-        for name, (comps, dt) in _AOS_STATE.items():
-            alloc(name, comps, dt, "aos")
-        for name, (comps, dt) in _SOA_MDP.items():
-            alloc(name, comps, dt, "soa")
-        for name, (comps, dt) in _AOS_MDP.items():
-            alloc(name, comps, dt, "aos")
-        alloc("new_action", lambda s: s.A, torch.float32, "aos")
-        alloc("joint_target", lambda s: s.J, torch.float32, "soa")
-        alloc("step_reward", lambda s: s.K, torch.float32, "soa")
-        # outputs
-        dev = self.device
-        self.obs = [torch.zeros(N, max(g.dim, 1), device=dev)[:, : g.dim].contiguous() if g.dim > 0 else None
-                    for g in spec.obs]
-        self.reward = torch.zeros(N, device=dev)
-        self.terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.done_bits = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.reset_ids = torch.zeros(N, dtype=torch.int32, device=dev)
-        self.n_reset = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.inputs = _Arena([(n, shape_of(n, c, k), dt) for n, (c, dt, k) in INPUT_FIELDS.items()], dev)
+        self.mdp = _Arena([(n, shape_of(n, c, k), dt) for n, (c, dt, k) in MDP_FIELDS.items()], dev)
+        out_entries = [(f"obs{g}", (N, grp.dim), _F32) for g, grp in enumerate(spec.obs)]
+        out_entries += [("reward", (N,), _F32), ("terminated", (N,), _U8), ("truncated", (N,), _U8)]
+        self.outputs = _Arena(out_entries, dev)
+        self.t: dict[str, torch.Tensor] = {**self.inputs.views, **self.mdp.views}
+        self.obs = [self.outputs.views[f"obs{g}"] if grp.dim > 0 else None for g, grp in enumerate(spec.obs)]
+        self.reward = self.outputs.views["reward"]
+        self.terminated = self.outputs.views["terminated"]
+        self.truncated = self.outputs.views["truncated"]
+        self.done_bits = torch.zeros(N, dtype=_U8, device=dev)
+        self.reset_ids = torch.zeros(N, dtype=_I32, device=dev)
+        self.n_reset = torch.zeros(1, dtype=_I32, device=dev)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # common_step_counter [IL]
         # optional random inputs (noise-as-input mode)
         self.cmd_uniforms: torch.Tensor | None = None
         self.obs_uniforms: list[torch.Tensor | None] = [None, None]
@@ -100,6 +120,8 @@ class StateBuffers:
         if src.dtype == torch.bool:
             src = src.to(torch.uint8)
         src = src.to(dst.dtype).reshape(self.N, -1)
+        if dst.numel() == 0:
+            return
         if dst.dim() == 1:
             dst.copy_(src[:, 0])
         elif self.kind[name] == "soa":
@@ -119,7 +141,7 @@ class StateBuffers:
                 self.obs_uniforms[g] = st[key].to(self.device, torch.float32).contiguous()
 
     def logical(self, name: str) -> torch.Tensor:
-        """One field back in its logical [N, C] / [N] shape (a device tensor; may be a copy)."""
+        """One field back in its logical [N, C] / [N] shape (a device tensor; may be a view)."""
         x = self.t[name]
         if x.dim() == 2 and self.kind[name] == "soa":
             x = x.t()
@@ -165,11 +187,15 @@ class StateBuffers:
         o.step_reward = self.field("step_reward")
         o.reset_ids = self.reset_ids.data_ptr()
         o.n_reset = self.n_reset.data_ptr()
+        o.reset_log = self.reset_log()
         return o
 
-    def random(self, seed: int = 0, step: int = 0, env_id_offset: int = 0, use_inputs: bool = True) -> nat.RlRandom:
+    def random(self, seed: int = 0, step: int = 0, env_id_offset: int = 0, use_inputs: bool = True,
+               use_step_counter: bool = False) -> nat.RlRandom:
         r = nat.RlRandom()
         r.seed, r.step, r.env_id_offset = seed, step, env_id_offset
+        if use_step_counter:
+            r.step_counter = self.step_counter.data_ptr()
         if use_inputs:
             if self.cmd_uniforms is not None:
                 r.cmd_uniforms = self.cmd_uniforms.data_ptr()
@@ -186,10 +212,8 @@ class StateBuffers:
         return lg
 
     def input_bytes(self) -> int:
-        """Bytes of the per-step inputs (physics/sensor state + new action) - what an e2e step copies H2D."""
-        names = list(nat._STATE_FIELDS) + ["new_action"]
-        return sum(self.t[n].numel() * self.t[n].element_size() for n in names)
+        """Payload bytes of the per-step inputs (arena padding excluded)."""
+        return sum(v.numel() * v.element_size() for v in self.inputs.views.values())
 
     def output_bytes(self) -> int:
-        outs = [o for o in self.obs if o is not None] + [self.reward, self.terminated, self.truncated]
-        return sum(o.numel() * o.element_size() for o in outs)
+        return sum(v.numel() * v.element_size() for v in self.outputs.views.values())
