@@ -19,20 +19,24 @@ HDR = ROOT / "include" / "rl_mdp_step.h"
 OUT = PKG / "_lib" / "libmdpstep.so"
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", f"-I{ROOT / 'include'}",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--split-compile=0", "-lineinfo", "-fmad=false", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}",
 ]
 
 
 def needs_build() -> bool:
+    from . import codegen
+
+    gen = codegen.write()  # rewrites the baked specs only when the task cfgs changed
     if not OUT.exists():
         return True
-    newest = max(SRC.stat().st_mtime, HDR.stat().st_mtime, Path(__file__).stat().st_mtime)
+    newest = max(SRC.stat().st_mtime, HDR.stat().st_mtime, Path(__file__).stat().st_mtime, gen.stat().st_mtime)
     return OUT.stat().st_mtime < newest
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+    stale = needs_build()
+    if not force and not stale:
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     OUT.parent.mkdir(parents=True, exist_ok=True)

@@ -29,6 +29,9 @@
 #include <string.h>
 
 #include <new>
+#include <utility>
+
+#include "generated/baked_specs.cuh"
 
 #define RL_SPEC_SLOTS 3
 #define RL_PI_F 3.14159265358979323846f
@@ -56,37 +59,128 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0, long lo
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------
-// Shared-memory layout of one CTA tile (word offsets). SoA section: word w of local env e at [w*E + e].
+// Per-launch field descriptors and the static row tables
+//
+// A "row" is one component of one 4-byte per-env field. The step kernel stages rows into an SoA shared-memory
+// record (word w of local env e at sm[w*E + e]) with ONE generic loop of non-blocking cp.async copies and writes
+// result rows back with one generic loop - the row tables (field id, component, record word) are static per
+// context and live in global memory; only the ~25 field descriptors (pointer + strides) travel per launch.
+// ---------------------------------------------------------------------------------------------------
+struct FieldD {
+  const void* ptr;
+  int es;    // env stride   (elements)
+  int cs;    // comp stride  (elements)
+};
+
+enum InField {
+  IF_ROOT_POS = 0, IF_QUAT, IF_LIN_VEL, IF_ANG_VEL, IF_JPOS, IF_JVEL, IF_JACC, IF_JTAU,
+  IF_CAIR, IF_LAIR, IF_CCON, IF_LCON, IF_BPOS, IF_BVEL, IF_RAYPOS,
+  IF_CMD, IF_HEAD, IF_TLEFT, IF_MXY, IF_MYAW, IF_EPLEN, IF_SUMS, IF_CMDU, IF_COUNT
+};
+enum OutField { OF_REWARD = 0, OF_EPLEN, OF_SUMS, OF_STEPR, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_COUNT };
+
+// row meta: field (bits 0-5) | comp (6-15) | record word (16-31)
+__host__ __device__ __forceinline__ uint32_t row_pack(int f, int c, int w) { return (uint32_t)f | ((uint32_t)c << 6) | ((uint32_t)w << 16); }
+
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory layout of one CTA tile (word offsets, already multiplied by E for the SoA words).
 // ---------------------------------------------------------------------------------------------------
 struct Layout {
-  int root_pos, quat, lin_vel, ang_vel;          // 3, 4, 3, 3
-  int jpos, jvel, jacc, jtau;                    // J each
-  int act, pact;                                 // A each
-  int cmd, head, tleft, ishead, isstand;         // 3, 1, 1, 1, 1
-  int mxy, myaw, eplen;                          // 1, 1, 1
-  int sums;                                      // K
-  int cair, lair, ccon, lcon;                    // Bt each
-  int bpos, bvel;                                // Ba*3 each
-  int raypos;                                    // 1
-  int cmdu;                                      // RL_NUM_CMD_UNIFORMS
-  int bmax;                                      // B   scratch: max_t |F_b|
-  int rew, flags, stepr;                         // 1, 1, K   outputs
-  int soa_words;                                 // total words of the SoA section (per env)
-  // AoS rows (word offsets from the start of dynamic smem; each is [E][pitch])
+  int A, J;
+  int root_pos, quat, lin_vel, ang_vel;          // SoA offsets (= word * E)
+  int jpos, jvel, jacc, jtau;
+  int cmd, head, tleft, ishead, isstand;
+  int mxy, myaw, eplen;
+  int sums;
+  int cair, lair, ccon, lcon;
+  int bpos, bvel;
+  int raypos;
+  int cmdu;
+  int bmax;                                      // scratch: max_t |F_b|
+  int rew, flags, stepr;                         // outputs
+  int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw;  // record words of the out fields
+  int soa_words;
+  int cj;                                        // per-joint constants [5][J]: q0, qd0, soft lo, soft hi, vel limit
+  // AoS rows: [E][pitch]
+  int act, pact;                                 // pitch A
   int hist, hist_pitch;
   int rays, rays_pitch;
-  int obs[RL_NUM_OBS_GROUPS], obs_pitch[RL_NUM_OBS_GROUPS];
-  int obsu[RL_NUM_OBS_GROUPS];                   // uniforms for noise-as-input (same pitch as obs)
+  int obs0, obs1, obs_pitch0, obs_pitch1;          // selected with LOBS(g) etc.: no runtime-indexed members,
+  int obsu0, obsu1;                                // so the struct never has to live in local memory
   int total_words;
 };
+
+__host__ __device__ constexpr int in_field_ncomp(const RlStepSpec& s, int f) {
+  switch (f) {
+    case IF_ROOT_POS: case IF_LIN_VEL: case IF_ANG_VEL: case IF_CMD: return 3;
+    case IF_QUAT: return 4;
+    case IF_JPOS: case IF_JVEL: case IF_JACC: case IF_JTAU: return s.num_joints;
+    case IF_CAIR: case IF_LAIR: case IF_CCON: case IF_LCON: return s.num_time_bodies;
+    case IF_BPOS: case IF_BVEL: return 3 * s.num_asset_bodies;
+    case IF_SUMS: return s.num_reward_terms;
+    case IF_CMDU: return RL_NUM_CMD_UNIFORMS;
+    default: return 1;
+  }
+}
+
+__host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ constexpr Layout make_layout(const RlStepSpec& s, int E) {
+  Layout L{};
+  int w = 0;
+  auto take = [&w](int n) { int o = w; w += n; return o; };
+  const int J = s.num_joints, A = s.action.n_actions, K = s.num_reward_terms;
+  L.A = A; L.J = J;
+  int in_word[IF_COUNT] = {};
+  for (int f = 0; f < IF_COUNT; ++f) in_word[f] = take(in_field_ncomp(s, f));
+  L.root_pos = in_word[IF_ROOT_POS] * E; L.quat = in_word[IF_QUAT] * E;
+  L.lin_vel = in_word[IF_LIN_VEL] * E; L.ang_vel = in_word[IF_ANG_VEL] * E;
+  L.jpos = in_word[IF_JPOS] * E; L.jvel = in_word[IF_JVEL] * E; L.jacc = in_word[IF_JACC] * E; L.jtau = in_word[IF_JTAU] * E;
+  L.cair = in_word[IF_CAIR] * E; L.lair = in_word[IF_LAIR] * E; L.ccon = in_word[IF_CCON] * E; L.lcon = in_word[IF_LCON] * E;
+  L.bpos = in_word[IF_BPOS] * E; L.bvel = in_word[IF_BVEL] * E; L.raypos = in_word[IF_RAYPOS] * E;
+  L.cmd = in_word[IF_CMD] * E; L.head = in_word[IF_HEAD] * E; L.tleft = in_word[IF_TLEFT] * E;
+  L.mxy = in_word[IF_MXY] * E; L.myaw = in_word[IF_MYAW] * E; L.eplen = in_word[IF_EPLEN] * E;
+  L.sums = in_word[IF_SUMS] * E; L.cmdu = in_word[IF_CMDU] * E;
+  L.w_eplen = in_word[IF_EPLEN]; L.w_sums = in_word[IF_SUMS]; L.w_cmd = in_word[IF_CMD];
+  L.w_head = in_word[IF_HEAD]; L.w_tleft = in_word[IF_TLEFT]; L.w_mxy = in_word[IF_MXY]; L.w_myaw = in_word[IF_MYAW];
+  L.ishead = take(1) * E; L.isstand = take(1) * E;
+  L.bmax = take(s.num_hist_bodies) * E;
+  L.w_rew = take(1); L.rew = L.w_rew * E;
+  L.flags = take(1) * E;
+  L.w_stepr = take(K); L.stepr = L.w_stepr * E;
+  L.soa_words = w;
+  int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
+  L.cj = off; off = align_up(off + 5 * J, 32);
+  L.act = off; off = align_up(off + E * A, 32);
+  L.pact = off; off = align_up(off + E * A, 32);
+  L.hist_pitch = s.hist_len * s.num_hist_bodies * 3;
+  L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
+  L.rays_pitch = s.num_rays;
+  L.rays = off; off = align_up(off + E * L.rays_pitch, 32);
+  L.obs_pitch0 = s.obs[0].dim; L.obs_pitch1 = s.obs[1].dim;
+  L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
+  L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+  L.obsu0 = off; off = align_up(off + E * L.obs_pitch0, 32);
+  L.obsu1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+  L.total_words = off;
+  return L;
+}
+
 
 struct KArgs {
   int N;
   int slot;
   uint32_t phases;
   int has_ids;
-  RlStateView st;
-  RlMdpState mdp;
+  FieldD in[IF_COUNT];
+  FieldD outf[OF_COUNT];
+  uint32_t in_mask, out_mask;
+  uint32_t in_vec4, out_vec4;     // fields whose rows may move 4 envs at a time (SoA, 16-byte aligned)
+  const uint32_t* in_rows;  int n_in_rows;
+  const uint32_t* out_rows; int n_out_rows;
+  // AoS spans (row-contiguous per env) and byte fields
+  FieldD action, prev_action, hist, rays;
+  FieldD is_heading, is_standing;               // uint8
   RlStepOut out;
   RlRandom rnd;
   const int32_t* env_ids;
@@ -101,6 +195,7 @@ struct KArgs {
   const uint8_t* ext_terminated;
   float* term_out;
 };
+
 
 // ---------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copies (TMA engine, SASS UBLKCP)
@@ -144,6 +239,15 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Ampere-style async copies (SASS LDGSTS): global -> shared without a register round trip, fire and forget
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) - counter-based, so noise needs no state and no bytes.
@@ -165,13 +269,17 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0
 
 enum { RL_STREAM_COMMAND = 1, RL_STREAM_RESET_COMMAND = 2, RL_STREAM_OBS = 16 };
 
-__device__ __forceinline__ uint4 rl_philox(const RlRandom& r, long long env, uint32_t stream, uint32_t block) {
+struct RandState {
+  unsigned long long seed, step;   // step already includes the device-side common step counter
+  long long env_id_offset;
+};
+__device__ __noinline__ uint4 rl_philox(const RandState r, long long env, uint32_t stream, uint32_t block) {
   const unsigned long long genv = (unsigned long long)(env + r.env_id_offset);
-  const unsigned long long step = r.step + (r.step_counter ? *r.step_counter : 0ull);
-  uint4 ctr = make_uint4((uint32_t)genv, (uint32_t)step, (uint32_t)(step >> 32) ^ (uint32_t)(genv >> 32),
+  uint4 ctr = make_uint4((uint32_t)genv, (uint32_t)r.step, (uint32_t)(r.step >> 32) ^ (uint32_t)(genv >> 32),
                          (stream << 16) | block);
   return philox4x32_10(ctr, make_uint2((uint32_t)r.seed, (uint32_t)(r.seed >> 32)));
 }
+
 
 // ---------------------------------------------------------------------------------------------------
 // Math (restates isaaclab.utils.math [IL]: quat_apply, quat_apply_inverse, yaw_quat, wrap_to_pi)
@@ -183,19 +291,19 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
   return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 // v - w*t + xyz x t, t = 2*(xyz x v)
-__device__ __forceinline__ V3 quat_apply_inverse(float w, V3 q, V3 v) {
+__device__ __noinline__ V3 quat_apply_inverse(float w, V3 q, V3 v) {
   V3 t = cross3(q, v);
   t.x *= 2.f; t.y *= 2.f; t.z *= 2.f;
   V3 c = cross3(q, t);
   return V3{(v.x - w * t.x) + c.x, (v.y - w * t.y) + c.y, (v.z - w * t.z) + c.z};
 }
-__device__ __forceinline__ V3 quat_apply(float w, V3 q, V3 v) {
+__device__ __noinline__ V3 quat_apply(float w, V3 q, V3 v) {
   V3 t = cross3(q, v);
   t.x *= 2.f; t.y *= 2.f; t.z *= 2.f;
   V3 c = cross3(q, t);
   return V3{(v.x + w * t.x) + c.x, (v.y + w * t.y) + c.y, (v.z + w * t.z) + c.z};
 }
-__device__ __forceinline__ float remainder_pos(float a, float b) {  // torch.remainder, b > 0
+__device__ __noinline__ float remainder_pos(float a, float b) {  // torch.remainder, b > 0
   float m = fmodf(a, b);
   if (m != 0.f && (m < 0.f)) m += b;
   return m;
@@ -207,71 +315,104 @@ __device__ __forceinline__ float wrap_to_pi(float a) {
 }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 // torch.clamp semantics for NaN are irrelevant here; +-inf behave like fminf/fmaxf.
+// transcendental functions behind calls: one code copy each instead of ~100 inlined instructions per use
+__device__ __noinline__ float rl_expf(float x) { return expf(x); }
+__device__ __noinline__ float rl_tanhf(float x) { return tanhf(x); }
+__device__ __noinline__ float rl_atan2f(float y, float x) { return atan2f(y, x); }
+__device__ __noinline__ float rl_sinf(float x) { return sinf(x); }
+__device__ __noinline__ float rl_cosf(float x) { return cosf(x); }
+
 
 // ---------------------------------------------------------------------------------------------------
-// Tile loaders / storers. SoA smem record: sm[off + c*E + e]. Integer fields travel bit-cast in the
-// float record.
+// Spec access policies. DynPolicy interprets the context's spec from __constant__ memory (any task);
+// StaticPolicy<B> reads a spec baked in at build time (generated/baked_specs.cuh): every use below is a constant
+// expression, so term dispatch, parameters, index lists, loop bounds and shared-memory offsets fold away.
 // ---------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ float to_word(T v) { return __int_as_float((int)v); }
-template <> __device__ __forceinline__ float to_word<float>(float v) { return v; }
-template <typename T> __device__ __forceinline__ T from_word(float w) { return (T)__float_as_int(w); }
-template <> __device__ __forceinline__ float from_word<float>(float w) { return w; }
+struct Scalars {
+  int num_joints, num_hist_bodies, hist_len, num_time_bodies, num_asset_bodies, num_rays;
+  int num_reward_terms, num_done_terms, max_episode_length, n_actions;
+  float step_dt, contact_time_abs_tol;
+};
+__host__ __device__ constexpr Scalars scalars_of(const RlStepSpec& s) {
+  return Scalars{s.num_joints, s.num_hist_bodies, s.hist_len, s.num_time_bodies, s.num_asset_bodies, s.num_rays,
+                 s.num_reward_terms, s.num_done_terms, s.max_episode_length, s.action.n_actions,
+                 s.step_dt, s.contact_time_abs_tol};
+}
 
-template <int E, typename T>
-__device__ __forceinline__ void load_soa(float* sm, int off, const RlField& f, int ncomp, int env0, int nvalid,
-                                         const int32_t* ids, int tid, int nthreads) {
-  if (f.ptr == nullptr || ncomp <= 0) return;
-  const T* __restrict__ p = static_cast<const T*>(f.ptr);
-  const int total = ncomp * E;
-  const bool env_major = (f.env_stride == 1) || (ncomp == 1);
-  for (int i = tid; i < total; i += nthreads) {
-    int c, e;
-    if (env_major) { e = i % E; c = i / E; } else { c = i % ncomp; e = i / ncomp; }
-    if (e < nvalid) {
-      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      sm[off + c * E + e] = to_word<T>(p[env * f.env_stride + (long long)c * f.comp_stride]);
-    }
+template <int... Is, class F>
+__device__ __forceinline__ void static_for(std::integer_sequence<int, Is...>, F&& f) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+
+struct DynPolicy {
+  static constexpr bool kStatic = false;
+  template <int E> __device__ __forceinline__ static Layout layout(const KArgs& a) { return a.L; }
+  __device__ __forceinline__ static Scalars scalars(const KArgs& a) { return scalars_of(c_spec[a.slot]); }
+  __device__ __forceinline__ static const RlCommandCfg& command(const KArgs& a) { return c_spec[a.slot].command; }
+  template <class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+#pragma unroll 1
+    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k);
   }
-}
-
-template <int E>
-__device__ __forceinline__ void load_rows(float* sm, int off, int pitch, const float* ptr, long long es,
-                                          long long cs, int ncomp, int env0, int nvalid, const int32_t* ids,
-                                          int tid, int nthreads) {
-  if (ptr == nullptr || ncomp <= 0) return;
-  const int total = ncomp * E;
-  const bool env_major = (es == 1);
-  for (int i = tid; i < total; i += nthreads) {
-    int c, e;
-    if (env_major) { e = i % E; c = i / E; } else { c = i % ncomp; e = i / ncomp; }
-    if (e < nvalid) {
-      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      sm[off + e * pitch + c] = ptr[env * es + (long long)c * cs];
-    }
+  template <class F> __device__ __forceinline__ static void for_dones(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+#pragma unroll 1
+    for (int d = 0; d < S.num_done_terms; ++d) f(S.dones[d], d);
   }
-}
-
-template <int E, typename T>
-__device__ __forceinline__ void store_soa(const float* sm, int off, const RlField& f, int ncomp, int env0,
-                                          int nvalid, const int32_t* ids, int tid, int nthreads) {
-  if (f.ptr == nullptr || ncomp <= 0) return;
-  T* __restrict__ p = static_cast<T*>(f.ptr);
-  const int total = ncomp * E;
-  const bool env_major = (f.env_stride == 1) || (ncomp == 1);
-  for (int i = tid; i < total; i += nthreads) {
-    int c, e;
-    if (env_major) { e = i % E; c = i / E; } else { c = i % ncomp; e = i / ncomp; }
-    if (e < nvalid) {
-      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      p[env * f.env_stride + (long long)c * f.comp_stride] = from_word<T>(sm[off + c * E + e]);
-    }
+  template <class F> __device__ __forceinline__ static void for_obs_groups(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+#pragma unroll 1
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) f(S.obs[g], g);
   }
-}
+  template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+    f(S.default_joint_pos[j], S.default_joint_vel[j], S.soft_pos_limit_lo[j], S.soft_pos_limit_hi[j], S.soft_vel_limit[j]);
+  }
+  __device__ __forceinline__ static int obs_dim(const KArgs& a, int g) { return c_spec[a.slot].obs[g].dim; }
+};
 
-__device__ __forceinline__ bool bulk_ok(const void* base, long long row_elems, int env0, int E) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (uintptr_t)env0 * (uintptr_t)row_elems * 4u;
-  return ((a & 15u) == 0) && ((((long long)E * row_elems * 4) & 15) == 0);
-}
+template <class B>
+struct StaticPolicy {
+  static constexpr bool kStatic = true;
+  template <int E> __device__ __forceinline__ static constexpr Layout layout(const KArgs&) {
+    constexpr Layout L = make_layout(B::spec, E);
+    return L;
+  }
+  __device__ __forceinline__ static constexpr Scalars scalars(const KArgs&) {
+    constexpr Scalars s = scalars_of(B::spec);
+    return s;
+  }
+  __device__ __forceinline__ static constexpr RlCommandCfg command(const KArgs&) {
+    constexpr RlCommandCfg c = B::spec.command;
+    return c;
+  }
+  template <class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      static constexpr RlRewardTerm t = B::spec.rewards[k];  // static: runtime-indexed lists read it in place
+      f(t, k);
+    });
+  }
+  template <class F> __device__ __forceinline__ static void for_dones(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, B::spec.num_done_terms>{}, [&](auto dc) {
+      constexpr int d = decltype(dc)::value;
+      static constexpr RlDoneTerm t = B::spec.dones[d];
+      f(t, d);
+    });
+  }
+  template <class F> __device__ __forceinline__ static void for_obs_groups(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
+      constexpr int g = decltype(gc)::value;
+      static constexpr RlObsGroup G = B::spec.obs[g];
+      f(G, g);
+    });
+  }
+  template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
+    DynPolicy::for_joint_consts(a, j, f);  // lane-varying joint index: staged from __constant__ like the generic path
+  }
+  __device__ __forceinline__ static constexpr int obs_dim(const KArgs&, int g) { return g == 0 ? B::spec.obs[0].dim : B::spec.obs[1].dim; }
+};
+
 
 // ---------------------------------------------------------------------------------------------------
 // Per-env context shared by all terms
@@ -303,10 +444,15 @@ __device__ __forceinline__ int gor(int v) {
   return v;
 }
 
+#define LOBS(g) ((g) == 0 ? L.obs0 : L.obs1)
+#define LOBSP(g) ((g) == 0 ? L.obs_pitch0 : L.obs_pitch1)
+#define LOBSU(g) ((g) == 0 ? L.obsu0 : L.obsu1)
 #define SMF(off, c) sm[(off) + (c) * E + e]
+#define SMA(off, c) sm[(off) + e * L.A + (c)]
+#define CJ(k, j) sm[L.cj + (k) * L.J + (j)]
 
 template <int E>
-__device__ __forceinline__ bool first_contact(const float* sm, const Layout& L, const RlStepSpec& S, int e, int b) {
+__device__ __forceinline__ bool first_contact(const float* sm, const Layout& L, const Scalars& S, int e, int b) {
   const float t = SMF(L.ccon, b);
   return (t > 0.f) && (t < (S.step_dt + S.contact_time_abs_tol));
 }
@@ -317,7 +463,7 @@ __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
 
 // One reward term, raw value (no weight, no dt). All lanes of the env group return the same value.
 template <int E, int LPE>
-__device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const Layout& L, const float* sm,
+__device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalars& S, const Layout& L, const float* sm,
                              const int e, const int sub, const EnvCtx& c) {
   const int J = S.num_joints;
   switch (t.type) {
@@ -345,7 +491,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
       for (int j = sub; j < J; j += LPE)
-        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - S.default_joint_pos[j]);
+        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       return gsum<LPE>(s);
     }
     case RL_REW_JOINT_POS_LIMITS: {
@@ -353,8 +499,8 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
       for (int j = sub; j < J; j += LPE)
         if ((t.joint_mask >> j) & 1ull) {
           const float q = SMF(L.jpos, j);
-          float o = -fminf(q - S.soft_pos_limit_lo[j], 0.f);
-          o += fmaxf(q - S.soft_pos_limit_hi[j], 0.f);
+          float o = -fminf(q - CJ(2, j), 0.f);
+          o += fmaxf(q - CJ(3, j), 0.f);
           s += o;
         }
       return gsum<LPE>(s);
@@ -363,7 +509,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
       float s = 0.f;
       for (int j = sub; j < J; j += LPE)
         if ((t.joint_mask >> j) & 1ull)
-          s += clampf(fabsf(SMF(L.jvel, j)) - S.soft_vel_limit[j] * t.p[0], 0.f, 1.f);
+          s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
       return gsum<LPE>(s);
     }
     case RL_REW_JOINT_POWER: {
@@ -375,7 +521,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
     case RL_REW_STAND_STILL: {
       float s = 0.f;
       for (int j = sub; j < J; j += LPE)
-        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - S.default_joint_pos[j]);
+        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       s = gsum<LPE>(s);
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
       return s * c.gate;
@@ -383,7 +529,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
       for (int j = sub; j < J; j += LPE)
-        if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - S.default_joint_pos[j]; s += d * d; }
+        if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - CJ(0, j); s += d * d; }
       const float running = sqrtf(gsum<LPE>(s));
       const bool moving = (c.cmd_norm > t.p[2]) || (c.vxy_norm > t.p[1]);
       return (moving ? running : t.p[0] * running) * c.gate;
@@ -400,7 +546,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
       for (int i = sub; i < t.n_idx; i += LPE) {
-        const float d = fabsf(SMF(L.act, t.idx_a[i])) - fabsf(SMF(L.act, t.idx_b[i]));
+        const float d = fabsf(SMA(L.act, t.idx_a[i])) - fabsf(SMA(L.act, t.idx_b[i]));
         s += d * d;
       }
       s = gsum<LPE>(s);
@@ -412,18 +558,18 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
         const int start = t.idx_b[g], n = t.idx_c[g];
         if (n < 2) continue;
         float m = 0.f;
-        for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, t.idx_a[start + i]));
+        for (int i = 0; i < n; ++i) m += fabsf(SMA(L.act, t.idx_a[start + i]));
         m = m / (float)n;
         float v = 0.f;
-        for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, t.idx_a[start + i])) - m; v += d * d; }
+        for (int i = 0; i < n; ++i) { const float d = fabsf(SMA(L.act, t.idx_a[start + i])) - m; v += d * d; }
         r += v / (float)n;
       }
       return (r * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_RATE_L2: {
-      const int A = S.action.n_actions;
+      const int A = S.n_actions;
       float s = 0.f;
-      for (int a = sub; a < A; a += LPE) { const float d = SMF(L.act, a) - SMF(L.pact, a); s += d * d; }
+      for (int a = sub; a < A; a += LPE) { const float d = SMA(L.act, a) - SMA(L.pact, a); s += d * d; }
       return gsum<LPE>(s);
     }
     case RL_REW_UNDESIRED_CONTACTS: {
@@ -440,25 +586,25 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
     }
     case RL_REW_TRACK_LIN_VEL_XY_EXP: {
       const float dx = c.c0 - c.vb.x, dy = c.c1 - c.vb.y;
-      return expf(-(dx * dx + dy * dy) / t.p[0]) * c.gate;
+      return rl_expf(-(dx * dx + dy * dy) / t.p[0]) * c.gate;
     }
     case RL_REW_TRACK_ANG_VEL_Z_EXP: {
       const float d = c.c2 - c.wb.z;
-      return expf(-(d * d) / t.p[0]) * c.gate;
+      return rl_expf(-(d * d) / t.p[0]) * c.gate;
     }
     case RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP: {
       // yaw_quat [IL] then quat_apply_inverse on the world velocity (V/mdp/rewards.py:60)
-      const float yaw = atan2f(2.f * (c.qw * c.q.z + c.q.x * c.q.y), 1.f - 2.f * (c.q.y * c.q.y + c.q.z * c.q.z));
-      float yw = cosf(yaw / 2.f), yz = sinf(yaw / 2.f);
+      const float yaw = rl_atan2f(2.f * (c.qw * c.q.z + c.q.x * c.q.y), 1.f - 2.f * (c.q.y * c.q.y + c.q.z * c.q.z));
+      float yw = rl_cosf(yaw / 2.f), yz = rl_sinf(yaw / 2.f);
       const float nrm = fmaxf(sqrtf(yw * yw + yz * yz), 1e-9f);
       yw = yw / nrm; yz = yz / nrm;
       const V3 v = quat_apply_inverse(yw, V3{0.f, 0.f, yz}, c.vw);
       const float dx = c.c0 - v.x, dy = c.c1 - v.y;
-      return expf(-(dx * dx + dy * dy) / t.p[0]) * c.gate;
+      return rl_expf(-(dx * dx + dy * dy) / t.p[0]) * c.gate;
     }
     case RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP: {
       const float d = c.c2 - c.ww.z;
-      return expf(-(d * d) / t.p[0]) * c.gate;
+      return rl_expf(-(d * d) / t.p[0]) * c.gate;
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
@@ -506,12 +652,12 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
       auto sync = [&](int a, int b) {
         const float da = SMF(L.cair, a) - SMF(L.cair, b);
         const float dc = SMF(L.ccon, a) - SMF(L.ccon, b);
-        return expf(-(fminf(da * da, me2) + fminf(dc * dc, me2)) / sd);
+        return rl_expf(-(fminf(da * da, me2) + fminf(dc * dc, me2)) / sd);
       };
       auto async = [&](int a, int b) {
         const float d0 = SMF(L.cair, a) - SMF(L.ccon, b);
         const float d1 = SMF(L.ccon, a) - SMF(L.cair, b);
-        return expf(-(fminf(d0 * d0, me2) + fminf(d1 * d1, me2)) / sd);
+        return rl_expf(-(fminf(d0 * d0, me2) + fminf(d1 * d1, me2)) / sd);
       };
       const float sync_r = sync(f00, f01) * sync(f10, f11);
       const float async_r = ((async(f00, f10) * async(f01, f11)) * async(f00, f11)) * async(f10, f01);
@@ -558,7 +704,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
         const V3 p = body_vec<E>(sm, L.bpos, e, t.idx_b[i]);
         const V3 v = body_vec<E>(sm, L.bvel, e, t.idx_b[i]);
         const float d = p.z - t.p[0];
-        s += (d * d) * tanhf(t.p[1] * sqrtf(v.x * v.x + v.y * v.y));
+        s += (d * d) * rl_tanhf(t.p[1] * sqrtf(v.x * v.x + v.y * v.y));
       }
       s *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return s * c.gate;
@@ -571,7 +717,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float d = pb.z - t.p[0];
-        s += (d * d) * tanhf(t.p[1] * sqrtf(vb.x * vb.x + vb.y * vb.y));
+        s += (d * d) * rl_tanhf(t.p[1] * sqrtf(vb.x * vb.x + vb.y * vb.y));
       }
       s *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return s * c.gate;
@@ -585,7 +731,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
         const float d = want - pb.y;
         s += d * d;
       }
-      return expf(-s / t.p[1]) * c.gate;
+      return rl_expf(-s / t.p[1]) * c.gate;
     }
     case RL_REW_FEET_DISTANCE_XY_EXP: {
       float s = 0.f;
@@ -597,7 +743,7 @@ __device__ float reward_term(const RlRewardTerm& t, const RlStepSpec& S, const L
         const float dx = wx - pb.x, dy = wy - pb.y;
         s += dx * dx + dy * dy;
       }
-      return expf(-s / t.p[2]) * c.gate;
+      return rl_expf(-s / t.p[2]) * c.gate;
     }
     case RL_REW_WHEEL_VEL_PENALTY: {
       float run = 0.f, stand = 0.f;
@@ -636,7 +782,7 @@ __device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int
 
 // max over the history of |F_b| for the lane group's bodies -> smem scratch (shared by 5 terms)
 template <int E, int LPE>
-__device__ __forceinline__ void body_max_norm(float* sm, const Layout& L, const RlStepSpec& S, int e, int sub) {
+__device__ __forceinline__ void body_max_norm(float* sm, const Layout& L, const Scalars& S, int e, int sub) {
   const int B = S.num_hist_bodies, T = S.hist_len;
   const float* h = sm + L.hist + e * L.hist_pitch;
   for (int b = sub; b < B; b += LPE) {
@@ -653,9 +799,9 @@ __device__ __forceinline__ void body_max_norm(float* sm, const Layout& L, const 
 // CommandTerm.compute [IL] + UniformThresholdVelocityCommand (V/mdp/commands.py:43-85; the "pits" branch
 // is identically off for the in-scope terrains, V/mdp/utils.py:27-28). Writes back into the smem record.
 template <int E>
-__device__ __forceinline__ void command_update(float* sm, const Layout& L, const RlStepSpec& S, const KArgs& a,
-                                               int e, long long env, const EnvCtx& c, bool write) {
-  const RlCommandCfg& cc = S.command;
+__device__ __forceinline__ void command_update(float* sm, const Layout& L, const Scalars& S, const RlCommandCfg& cc,
+                                               const KArgs& a, const RandState rs, int e, long long env,
+                                               const EnvCtx& c, bool write) {
   float c0 = c.c0, c1 = c.c1, c2 = c.c2;
   // metrics use the command and state of this step
   {
@@ -674,7 +820,7 @@ __device__ __forceinline__ void command_update(float* sm, const Layout& L, const
 #pragma unroll
       for (int i = 0; i < RL_NUM_CMD_UNIFORMS; ++i) u[i] = SMF(L.cmdu, i);
     } else {
-      const uint4 r0 = rl_philox(a.rnd, env, RL_STREAM_COMMAND, 0), r1 = rl_philox(a.rnd, env, RL_STREAM_COMMAND, 1);
+      const uint4 r0 = rl_philox(rs, env, RL_STREAM_COMMAND, 0), r1 = rl_philox(rs, env, RL_STREAM_COMMAND, 1);
       u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
       u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
     }
@@ -692,7 +838,7 @@ __device__ __forceinline__ void command_update(float* sm, const Layout& L, const
   }
   if (cc.heading_command && ishead) {
     const V3 fwd = quat_apply(c.qw, c.q, V3{1.f, 0.f, 0.f});
-    const float heading = atan2f(fwd.y, fwd.x);
+    const float heading = rl_atan2f(fwd.y, fwd.x);
     const float err = wrap_to_pi(head - heading);
     c2 = clampf(cc.heading_control_stiffness * err, cc.ang_vel_z_lo, cc.ang_vel_z_hi);
   }
@@ -705,21 +851,24 @@ __device__ __forceinline__ void command_update(float* sm, const Layout& L, const
 }
 
 // One observation group for one env: ObservationManager.compute_group [IL] (clone, +noise, clip, scale, cat)
-template <int E, int LPE>
-__device__ __forceinline__ void obs_group(float* sm, const Layout& L, const RlStepSpec& S, const KArgs& a, int g,
-                                          int e, int sub, long long env, const EnvCtx& c) {
-  const RlObsGroup& G = S.obs[g];
-  float* row = sm + L.obs[g] + e * L.obs_pitch[g];
-  const float* urow = sm + L.obsu[g] + e * L.obs_pitch[g];
+template <int E, int LPE, bool STATIC>
+__device__ __forceinline__ void obs_group(float* sm, const Layout& L, const Scalars& S, const RlObsGroup& G,
+                                          const KArgs& a, const RandState rs, int g, int e, int sub, long long env,
+                                          const EnvCtx& c) {
+  float* row = sm + LOBS(g) + e * LOBSP(g);
+  const float* urow = sm + LOBSU(g) + e * LOBSP(g);
   const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
   int col0 = 0;
-  for (int ti = 0; ti < G.n_terms; ++ti) {
+  constexpr int kUnroll = STATIC ? RL_MAX_OBS_TERMS : 1;  // baked spec: every term's type / dim / noise folds
+#pragma unroll kUnroll
+  for (int ti = 0; ti < RL_MAX_OBS_TERMS; ++ti) {
+    if (ti >= G.n_terms) break;
     const RlObsTerm& t = G.terms[ti];
     const bool noisy = t.has_noise && G.enable_corruption;
     for (int qd = sub; qd * 4 < t.dim; qd += LPE) {
       float u4[4] = {0.f, 0.f, 0.f, 0.f};
       if (noisy && !ext_u) {
-        const uint4 r = rl_philox(a.rnd, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
+        const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
         u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
       }
 #pragma unroll
@@ -732,19 +881,19 @@ __device__ __forceinline__ void obs_group(float* sm, const Layout& L, const RlSt
           case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
           case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
           case RL_OBS_GENERATED_COMMANDS: v = SMF(L.cmd, col); break;
-          case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - S.default_joint_pos[t.ids[col]]; break;
+          case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]); break;
           case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
-            v = SMF(L.jpos, t.ids[col]) - S.default_joint_pos[t.ids[col]];
+            v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]);
             if ((t.zero_mask >> col) & 1ull) v = 0.f;
             break;
-          case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - S.default_joint_vel[t.ids[col]]; break;
-          case RL_OBS_LAST_ACTION: v = SMF(L.act, col); break;
+          case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - CJ(1, t.ids[col]); break;
+          case RL_OBS_LAST_ACTION: v = SMA(L.act, col); break;
           case RL_OBS_HEIGHT_SCAN:
             v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0];
             break;
           case RL_OBS_PHASE: {
             const float ph = ((float)__float_as_int(SMF(L.eplen, 0)) * S.step_dt) / t.p[0];
-            v = col == 0 ? sinf((2.f * RL_PI_F) * ph) : cosf((2.f * RL_PI_F) * ph);
+            v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
             break;
           }
           default: v = 0.f;
@@ -763,15 +912,121 @@ __device__ __forceinline__ void obs_group(float* sm, const Layout& L, const RlSt
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Tile movers (one code copy each, `#pragma unroll 1` outer loops keep the kernel small: the first cut of this
+// kernel inlined a strided loop per field and ran at IPC 0.1 stalled on instruction fetch - see profiles/)
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ void load_rows_async(float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                                bool full, int tid, int nthreads) {
+  constexpr int NV = E / 4;
+  const int total = a.n_in_rows * NV;
+#pragma unroll 1
+  for (int i = tid; i < total; i += nthreads) {
+    const uint32_t meta = __ldg(a.in_rows + i / NV);
+    const int f = meta & 63u;
+    if (!((a.in_mask >> f) & 1u)) continue;
+    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
+    const FieldD fd = a.in[f];
+    float* dst = sm + w * E + 4 * v;
+    if (full && ((a.in_vec4 >> f) & 1u)) {
+      cp_async16(dst, static_cast<const float*>(fd.ptr) + (size_t)c * fd.cs + env0 + 4 * v);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = 4 * v + q;
+        if (e < nvalid) {
+          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+          cp_async4(dst + q, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void store_rows(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                           bool full, int tid, int nthreads) {
+  constexpr int NV = E / 4;
+  const int total = a.n_out_rows * NV;
+#pragma unroll 1
+  for (int i = tid; i < total; i += nthreads) {
+    const uint32_t meta = __ldg(a.out_rows + i / NV);
+    const int f = meta & 63u;
+    if (!((a.out_mask >> f) & 1u)) continue;
+    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
+    const FieldD fd = a.outf[f];
+    const float* src = sm + w * E + 4 * v;
+    float* base = static_cast<float*>(const_cast<void*>(fd.ptr));
+    if (full && ((a.out_vec4 >> f) & 1u)) {
+      *reinterpret_cast<float4*>(base + (size_t)c * fd.cs + env0 + 4 * v) = *reinterpret_cast<const float4*>(src);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = 4 * v + q;
+        if (e < nvalid) {
+          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+          base[env * fd.es + (long long)c * fd.cs] = src[q];
+        }
+      }
+    }
+  }
+}
+
+// AoS span [E][ncomp] <-> global rows; element-wise fallback when a span is not one aligned contiguous block
+__device__ __noinline__ void span_load_elems(float* dst, int pitch, FieldD fd, int ncomp, int E, int env0, int nvalid,
+                                             const int32_t* ids, int tid, int nthreads) {
+  const int total = ncomp * E;
+  const bool env_major = (fd.es == 1);
+  for (int i = tid; i < total; i += nthreads) {
+    int c, e;
+    if (env_major) { e = i % E; c = i / E; } else { c = i % ncomp; e = i / ncomp; }
+    if (e < nvalid) {
+      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+      cp_async4(dst + e * pitch + c, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
+    }
+  }
+}
+__device__ __noinline__ void span_store_elems(const float* src, int pitch, float* ptr, long long es, long long cs, int ncomp,
+                                              int E, int env0, int nvalid, const int32_t* ids, int tid, int nthreads) {
+  const int total = ncomp * E;
+  for (int i = tid; i < total; i += nthreads) {
+    const int c = i % ncomp, e = i / ncomp;
+    if (e < nvalid) {
+      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+      ptr[env * es + (long long)c * cs] = src[e * pitch + c];
+    }
+  }
+}
+__device__ __forceinline__ bool span_bulk_ok(const FieldD& fd, int ncomp, int env0, int E) {
+  if (fd.ptr == nullptr || ncomp <= 0 || fd.cs != 1 || fd.es != ncomp) return false;
+  const uintptr_t p = reinterpret_cast<uintptr_t>(fd.ptr) + (uintptr_t)env0 * (uintptr_t)ncomp * 4u;
+  return ((p & 15u) == 0) && ((((long long)E * ncomp * 4) & 15) == 0);
+}
+__device__ __forceinline__ void load_u8(float* sm, int off, const FieldD& fd, int E, int env0, int nvalid,
+                                        const int32_t* ids, int tid) {
+  if (fd.ptr != nullptr && tid < nvalid) {
+    const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+    sm[off + tid] = __int_as_float((int)static_cast<const uint8_t*>(fd.ptr)[env * fd.es]);
+  }
+}
+__device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD& fd, int env0, int nvalid,
+                                         const int32_t* ids, int tid) {
+  if (fd.ptr != nullptr && tid < nvalid) {
+    const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+    static_cast<uint8_t*>(const_cast<void*>(fd.ptr))[env * fd.es] = (uint8_t)__float_as_int(sm[off + tid]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // The fused step kernel. MODE 0 = step, MODE 1 = single-term evaluation.
 // ---------------------------------------------------------------------------------------------------
-template <int E, int LPE, int MODE>
+template <class P, int E, int LPE, int MODE>
 __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_last;
-  const RlStepSpec& S = c_spec[a.slot];
-  const Layout& L = a.L;
+  const Scalars S = P::scalars(a);
+  const Layout L = P::template layout<E>(a);
   constexpr int NT = E * LPE;
   const int tid = threadIdx.x;
   const uint32_t ph = a.phases;
@@ -782,124 +1037,92 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   }
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
   const int env0 = blockIdx.x * E;
-  if (MODE == 0 && (ph & RL_PHASE_RESET) && a.has_ids && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
+  const int K = S.num_reward_terms;
+  const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
+  if (do_reset && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
     // nothing to reset: the logged scalars are defined as 0
-    const int K0 = S.num_reward_terms;
-    if (tid < K0) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
-    else if (tid < K0 + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K0] = 0.f; }
-    else if (tid < K0 + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K0 - RL_MAX_DONE_TERMS] = 0.f; }
+    if (tid < K) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
+    else if (tid < K + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K] = 0.f; }
+    else if (tid < K + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K - RL_MAX_DONE_TERMS] = 0.f; }
   }
-  if (env0 >= n_total && !(a.phases & RL_PHASE_COMPACT)) return;
+  if (env0 >= n_total && !(ph & RL_PHASE_COMPACT)) return;
   const int nvalid = max(0, min(E, n_total - env0));
   const int32_t* ids = a.has_ids ? a.env_ids : nullptr;
-  const int J = S.num_joints, A = S.action.n_actions, K = S.num_reward_terms;
-  const int Bt = S.num_time_bodies, Ba = S.num_asset_bodies, R = S.num_rays;
+  const int J = S.num_joints, A = S.n_actions;
+  const int R = S.num_rays;
   const int HW = S.hist_len * S.num_hist_bodies * 3;
   const bool need_hist = (MODE == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
-  const bool need_rays = (MODE == 0) && (ph & RL_PHASE_OBS) && R > 0;
-  const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
-
-  // ---- load phase --------------------------------------------------------------------------------
+  const bool need_rays = (MODE == 0) && (ph & RL_PHASE_OBS) && R > 0 && a.rays.ptr != nullptr;
   const bool full = (nvalid == E) && (ids == nullptr);
-  const bool hist_bulk = need_hist && full && HW > 0 && a.st.net_forces_w_history.comp_stride == 1 &&
-                         a.st.net_forces_w_history.env_stride == HW &&
-                         bulk_ok(a.st.net_forces_w_history.ptr, HW, env0, E);
-  const bool rays_bulk = need_rays && full && a.st.ray_hits_z.comp_stride == 1 && a.st.ray_hits_z.env_stride == R &&
-                         bulk_ok(a.st.ray_hits_z.ptr, R, env0, E);
-  bool obsu_bulk[RL_NUM_OBS_GROUPS];
-#pragma unroll
-  for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-    obsu_bulk[g] = (MODE == 0) && (ph & RL_PHASE_OBS) && full && a.rnd.obs_uniforms[g] != nullptr &&
-                   S.obs[g].dim > 0 && bulk_ok(a.rnd.obs_uniforms[g], S.obs[g].dim, env0, E);
+  RandState rs;
+  rs.seed = a.rnd.seed;
+  rs.step = a.rnd.step + (a.rnd.step_counter ? *a.rnd.step_counter : 0ull);
+  rs.env_id_offset = a.rnd.env_id_offset;
+
+  // ---- load phase: everything is asynchronous, nothing below waits until the single join point ---------
   if (nvalid > 0) {
+    const bool act_bulk = full && span_bulk_ok(a.action, A, env0, E);
+    const bool pact_bulk = need_hist && full && span_bulk_ok(a.prev_action, A, env0, E);
+    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, env0, E);
+    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, env0, E);
+    bool obsu_bulk[RL_NUM_OBS_GROUPS];
+    FieldD obsu[RL_NUM_OBS_GROUPS];
+#pragma unroll
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+      const int D = P::obs_dim(a, g);
+      const bool want = (MODE == 0) && (ph & RL_PHASE_OBS) && a.rnd.obs_uniforms[g] != nullptr && D > 0;
+      obsu[g] = FieldD{want ? a.rnd.obs_uniforms[g] : nullptr, D, 1};
+      obsu_bulk[g] = want && full && span_bulk_ok(obsu[g], D, env0, E);
+    }
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       uint32_t bytes = 0;
+      if (act_bulk) bytes += (uint32_t)(E * A * 4);
+      if (pact_bulk) bytes += (uint32_t)(E * A * 4);
       if (hist_bulk) bytes += (uint32_t)(E * HW * 4);
       if (rays_bulk) bytes += (uint32_t)(E * R * 4);
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (obsu_bulk[g]) bytes += (uint32_t)(E * S.obs[g].dim * 4);
+        if (obsu_bulk[g]) bytes += (uint32_t)(E * P::obs_dim(a, g) * 4);
       mbar_expect_tx(&s_bar, bytes);
-      if (hist_bulk)
-        bulk_g2s(sm + L.hist, static_cast<const float*>(a.st.net_forces_w_history.ptr) + (size_t)env0 * HW,
-                 (uint32_t)(E * HW * 4), &s_bar);
-      if (rays_bulk)
-        bulk_g2s(sm + L.rays, static_cast<const float*>(a.st.ray_hits_z.ptr) + (size_t)env0 * R,
-                 (uint32_t)(E * R * 4), &s_bar);
+      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(E * HW * 4), &s_bar);
+      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(E * R * 4), &s_bar);
+      if (act_bulk) bulk_g2s(sm + L.act, static_cast<const float*>(a.action.ptr) + (size_t)env0 * A, (uint32_t)(E * A * 4), &s_bar);
+      if (pact_bulk) bulk_g2s(sm + L.pact, static_cast<const float*>(a.prev_action.ptr) + (size_t)env0 * A, (uint32_t)(E * A * 4), &s_bar);
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
         if (obsu_bulk[g])
-          bulk_g2s(sm + L.obsu[g], a.rnd.obs_uniforms[g] + (size_t)env0 * S.obs[g].dim,
-                   (uint32_t)(E * S.obs[g].dim * 4), &s_bar);
+          bulk_g2s(sm + LOBSU(g), static_cast<const float*>(obsu[g].ptr) + (size_t)env0 * P::obs_dim(a, g),
+                   (uint32_t)(E * P::obs_dim(a, g) * 4), &s_bar);
     }
-    load_soa<E, float>(sm, L.root_pos, a.st.root_pos_w, 3, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.quat, a.st.root_quat_w, 4, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.lin_vel, a.st.root_lin_vel_w, 3, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.ang_vel, a.st.root_ang_vel_w, 3, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.jpos, a.st.joint_pos, J, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.jvel, a.st.joint_vel, J, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.act, a.mdp.action, A, env0, nvalid, ids, tid, NT);
-    load_soa<E, float>(sm, L.cmd, a.mdp.command, 3, env0, nvalid, ids, tid, NT);
-    load_soa<E, int32_t>(sm, L.eplen, a.mdp.episode_length, 1, env0, nvalid, ids, tid, NT);
+    load_rows_async<E>(sm, a, env0, nvalid, ids, full, tid, NT);
+    if (!act_bulk && a.action.ptr) span_load_elems(sm + L.act, A, a.action, A, E, env0, nvalid, ids, tid, NT);
     if (need_hist) {
-      load_soa<E, float>(sm, L.jacc, a.st.joint_acc, J, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.jtau, a.st.applied_torque, J, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.pact, a.mdp.prev_action, A, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.cair, a.st.current_air_time, Bt, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.lair, a.st.last_air_time, Bt, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.ccon, a.st.current_contact_time, Bt, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.lcon, a.st.last_contact_time, Bt, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.bpos, a.st.body_pos_w, Ba * 3, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.bvel, a.st.body_lin_vel_w, Ba * 3, env0, nvalid, ids, tid, NT);
-      if (MODE == 0) load_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
-      if (!hist_bulk)
-        load_rows<E>(sm, L.hist, L.hist_pitch, static_cast<const float*>(a.st.net_forces_w_history.ptr),
-                     a.st.net_forces_w_history.env_stride, a.st.net_forces_w_history.comp_stride, HW, env0, nvalid,
-                     ids, tid, NT);
+      if (!pact_bulk && a.prev_action.ptr) span_load_elems(sm + L.pact, A, a.prev_action, A, E, env0, nvalid, ids, tid, NT);
+      if (!hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, E, env0, nvalid, ids, tid, NT);
     }
-    if (MODE == 0 && (ph & RL_PHASE_COMMAND)) {
-      load_soa<E, float>(sm, L.head, a.mdp.heading_target, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.tleft, a.mdp.time_left, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, uint8_t>(sm, L.ishead, a.mdp.is_heading_env, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, uint8_t>(sm, L.isstand, a.mdp.is_standing_env, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.mxy, a.mdp.metric_error_vel_xy, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.myaw, a.mdp.metric_error_vel_yaw, 1, env0, nvalid, ids, tid, NT);
-      if (a.rnd.cmd_uniforms != nullptr) {
-        RlField f{const_cast<float*>(a.rnd.cmd_uniforms), 1, (int64_t)a.N};
-        load_soa<E, float>(sm, L.cmdu, f, RL_NUM_CMD_UNIFORMS, env0, nvalid, ids, tid, NT);
-      }
-    }
-    if (do_reset) {
-      load_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.mxy, a.mdp.metric_error_vel_xy, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.myaw, a.mdp.metric_error_vel_yaw, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, float>(sm, L.head, a.mdp.heading_target, 1, env0, nvalid, ids, tid, NT);
-      load_soa<E, uint8_t>(sm, L.ishead, a.mdp.is_heading_env, 1, env0, nvalid, ids, tid, NT);
-      if (a.out.done_bits != nullptr) {
-        RlField f{a.out.done_bits, 1, 0};
-        load_soa<E, uint8_t>(sm, L.flags, f, 1, env0, nvalid, ids, tid, NT);
-      }
-      if (a.rnd.cmd_uniforms != nullptr && !(ph & RL_PHASE_COMMAND)) {
-        RlField f{const_cast<float*>(a.rnd.cmd_uniforms), 1, (int64_t)a.N};
-        load_soa<E, float>(sm, L.cmdu, f, RL_NUM_CMD_UNIFORMS, env0, nvalid, ids, tid, NT);
-      }
-    }
-    if (need_rays) {
-      load_soa<E, float>(sm, L.raypos, a.st.ray_sensor_pos_z, 1, env0, nvalid, ids, tid, NT);
-      if (!rays_bulk)
-        load_rows<E>(sm, L.rays, L.rays_pitch, static_cast<const float*>(a.st.ray_hits_z.ptr),
-                     a.st.ray_hits_z.env_stride, a.st.ray_hits_z.comp_stride, R, env0, nvalid, ids, tid, NT);
-    }
-    if (MODE == 0 && (ph & RL_PHASE_OBS)) {
+    if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, E, env0, nvalid, ids, tid, NT);
 #pragma unroll
-      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (a.rnd.obs_uniforms[g] != nullptr && !obsu_bulk[g])
-          load_rows<E>(sm, L.obsu[g], L.obs_pitch[g], a.rnd.obs_uniforms[g], S.obs[g].dim, 1, S.obs[g].dim, env0,
-                       nvalid, ids, tid, NT);
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
+      if (obsu[g].ptr && !obsu_bulk[g])
+        span_load_elems(sm + LOBSU(g), LOBSP(g), obsu[g], P::obs_dim(a, g), E, env0, nvalid, ids, tid, NT);
+    if (MODE == 0 && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET))) {
+      load_u8(sm, L.ishead, a.is_heading, E, env0, nvalid, ids, tid);
+      load_u8(sm, L.isstand, a.is_standing, E, env0, nvalid, ids, tid);
     }
-    __syncthreads();            // smem record + mbarrier init visible
+    if (do_reset && a.out.done_bits != nullptr) {
+      FieldD f{a.out.done_bits, 1, 0};
+      load_u8(sm, L.flags, f, E, env0, nvalid, ids, tid);
+    }
+    // per-joint constants: constant bank -> shared (lane-varying joint indices would serialise LDCs)
+    for (int i = tid; i < J; i += NT)
+      P::for_joint_consts(a, i, [&](float q0, float qd0, float lo, float hi, float vl) {
+        sm[L.cj + 0 * J + i] = q0; sm[L.cj + 1 * J + i] = qd0; sm[L.cj + 2 * J + i] = lo;
+        sm[L.cj + 3 * J + i] = hi; sm[L.cj + 4 * J + i] = vl;
+      });
+    cp_async_wait_all();
+    __syncthreads();            // record + mbarrier init visible to everyone
     mbar_wait(&s_bar, 0);       // bulk copies landed
   }
 
@@ -908,7 +1131,6 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   const int sub = tid % LPE;
   const bool valid = e < nvalid;
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
-  uint32_t done_any = 0;
   if (nvalid > 0) {
     if (do_reset) {
       // -- logging partials of this CTA (summed in CTA order by the last CTA -> deterministic) --
@@ -929,14 +1151,14 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       if (tid < E) {
         const int el = tid;
         sm[L.mxy + el] = 0.f; sm[L.myaw + el] = 0.f; sm[L.eplen + el] = __int_as_float(0);
-        const RlCommandCfg& cc = S.command;
+        const auto& cc = P::command(a);
         const long long ev = ids ? (long long)ids[env0 + min(el, nvalid - 1)] : (long long)(env0 + el);
         float u[RL_NUM_CMD_UNIFORMS];
         if (a.rnd.cmd_uniforms != nullptr) {
 #pragma unroll
           for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * E + el];
         } else {
-          const uint4 r0 = rl_philox(a.rnd, ev, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(a.rnd, ev, RL_STREAM_RESET_COMMAND, 1);
+          const uint4 r0 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 1);
           u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
           u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
         }
@@ -969,8 +1191,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
     uint32_t bits = 0, term = 0, trunc = 0;
     if (ph & RL_PHASE_DONES) {
       const int eplen = __float_as_int(SMF(L.eplen, 0)) + 1;
-      for (int d = 0; d < S.num_done_terms; ++d) {
-        const RlDoneTerm& t = S.dones[d];
+      P::for_dones(a, [&](const RlDoneTerm& t, int d) {
         int fired = 0;
         if (t.type == RL_DONE_TIME_OUT) {
           fired = eplen >= S.max_episode_length;
@@ -983,7 +1204,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
           fired = gor<LPE>(hit);
         }
         if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
-      }
+      });
       c.terminated = term != 0;
       __syncwarp();
       if (sub == 0) {
@@ -991,11 +1212,10 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         SMF(L.flags, 0) = __int_as_float((int)(bits | (term << 8) | (trunc << 9)));
       }
     }
-    done_any = term | trunc;
+    const uint32_t done_any = term | trunc;
     if (ph & RL_PHASE_REWARDS) {
       float total = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const RlRewardTerm& t = S.rewards[k];
+      P::for_rewards(a, [&](const RlRewardTerm& t, int k) {
         float val = 0.f, per_dt = 0.f;
         if (t.weight != 0.f) {
           const float raw = reward_term<E, LPE>(t, S, L, sm, e, sub, c);
@@ -1007,19 +1227,19 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
           SMF(L.sums, k) = SMF(L.sums, k) + val;
           SMF(L.stepr, k) = per_dt;
         }
-      }
+      });
       if (sub == 0) SMF(L.rew, 0) = total;
     }
     __syncwarp();
     if (ph & RL_PHASE_COMMAND) {
       const bool skip = (ph & RL_PHASE_SKIP_DONE_ENVS) && done_any;
-      command_update<E>(sm, L, S, a, e, env, c, (sub == 0) && !skip);
+      command_update<E>(sm, L, S, P::command(a), a, rs, e, env, c, (sub == 0) && !skip);
       __syncwarp();
     }
     if (ph & RL_PHASE_OBS) {
-#pragma unroll
-      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (a.out.obs[g] != nullptr && S.obs[g].dim > 0) obs_group<E, LPE>(sm, L, S, a, g, e, sub, env, c);
+      P::for_obs_groups(a, [&](const RlObsGroup& G, int g) {
+        if (a.out.obs[g] != nullptr && G.dim > 0) obs_group<E, LPE, P::kStatic>(sm, L, S, G, a, rs, g, e, sub, env, c);
+      });
     }
     __syncthreads();
 
@@ -1029,25 +1249,19 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       __syncthreads();
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
-        if (a.out.obs[g] == nullptr || S.obs[g].dim <= 0) continue;
-        const int D = S.obs[g].dim;
-        const bool bulk = full && a.out.obs_pitch[g] == D && bulk_ok(a.out.obs[g], D, env0, E);
-        if (bulk) {
-          if (tid == 0) bulk_s2g(a.out.obs[g] + (size_t)env0 * D, sm + L.obs[g], (uint32_t)(E * D * 4));
+        const int D = P::obs_dim(a, g);
+        if (a.out.obs[g] == nullptr || D <= 0) continue;
+        const FieldD od{a.out.obs[g], (int)a.out.obs_pitch[g], 1};
+        if (full && span_bulk_ok(od, D, env0, E)) {
+          if (tid == 0) bulk_s2g(a.out.obs[g] + (size_t)env0 * D, sm + LOBS(g), (uint32_t)(E * D * 4));
         } else {
-          for (int i = tid; i < E * D; i += NT) {
-            const int el = i / D, col = i % D;
-            if (el < nvalid) {
-              const long long ev = ids ? (long long)ids[env0 + el] : (long long)(env0 + el);
-              a.out.obs[g][ev * a.out.obs_pitch[g] + col] = sm[L.obs[g] + el * L.obs_pitch[g] + col];
-            }
-          }
+          span_store_elems(sm + LOBS(g), LOBSP(g), a.out.obs[g], a.out.obs_pitch[g], 1, D, E, env0, nvalid, ids, tid, NT);
         }
       }
       if (tid == 0) bulk_commit();
     }
+    store_rows<E>(sm, a, env0, nvalid, ids, full, tid, NT);
     if (ph & RL_PHASE_DONES) {
-      store_soa<E, int32_t>(sm, L.eplen, a.mdp.episode_length, 1, env0, nvalid, ids, tid, NT);
       if (tid < nvalid) {
         const int fl = __float_as_int(sm[L.flags + tid]);
         const long long ev = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
@@ -1056,33 +1270,20 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         if (a.out.truncated) a.out.truncated[ev] = (uint8_t)((fl >> 9) & 1);
       }
     }
-    if (ph & RL_PHASE_REWARDS) {
-      RlField fr{a.out.reward, 1, 0};
-      store_soa<E, float>(sm, L.rew, fr, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.stepr, a.out.step_reward, K, env0, nvalid, ids, tid, NT);
+    if ((ph & RL_PHASE_COMMAND) || do_reset) {
+      store_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
+      store_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
     }
     if (do_reset) {
-      store_soa<E, float>(sm, L.sums, a.mdp.episode_sums, K, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.act, a.mdp.action, A, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.pact, a.mdp.prev_action, A, env0, nvalid, ids, tid, NT);
-      store_soa<E, int32_t>(sm, L.eplen, a.mdp.episode_length, 1, env0, nvalid, ids, tid, NT);
-    }
-    if ((ph & RL_PHASE_COMMAND) || do_reset) {
-      store_soa<E, float>(sm, L.cmd, a.mdp.command, 3, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.head, a.mdp.heading_target, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.tleft, a.mdp.time_left, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, uint8_t>(sm, L.ishead, a.mdp.is_heading_env, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, uint8_t>(sm, L.isstand, a.mdp.is_standing_env, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.mxy, a.mdp.metric_error_vel_xy, 1, env0, nvalid, ids, tid, NT);
-      store_soa<E, float>(sm, L.myaw, a.mdp.metric_error_vel_yaw, 1, env0, nvalid, ids, tid, NT);
+      span_store_elems(sm + L.act, A, static_cast<float*>(const_cast<void*>(a.action.ptr)), a.action.es, a.action.cs, A, E, env0, nvalid, ids, tid, NT);
+      span_store_elems(sm + L.pact, A, static_cast<float*>(const_cast<void*>(a.prev_action.ptr)), a.prev_action.es, a.prev_action.cs, A, E, env0, nvalid, ids, tid, NT);
     }
   }
 
   // ---- ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]) -----------
   if ((ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids) {
     // per-CTA bit mask of done envs (E <= 32)
-    if (nvalid > 0 && tid < E) {
+    if (tid < E) {
       const int fl = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
       const unsigned m = __ballot_sync(E == 32 ? 0xffffffffu : ((1u << E) - 1u), (fl >> 8) & 3);
       if (tid == 0) a.cta_mask[blockIdx.x] = m;
@@ -1096,10 +1297,10 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
     __syncthreads();
     if (s_last) {
       __threadfence();
-      // gridDim.x masks; thread i owns a contiguous run of CTAs -> ids come out ascending
-      int* s_cnt = reinterpret_cast<int*>(sm);  // tile data is dead for this CTA only after its stores:
-      if (ph & RL_PHASE_OBS) { if (tid == 0) bulk_wait_read0(); }
+      int* s_cnt = reinterpret_cast<int*>(sm);  // this CTA's tile is dead once its own stores have been issued
+      if ((ph & RL_PHASE_OBS) && nvalid > 0) { if (tid == 0) bulk_wait_read0(); }
       __syncthreads();
+      // gridDim.x masks; thread i owns a contiguous run of CTAs -> ids come out ascending
       const int G = gridDim.x;
       const int per = (G + NT - 1) / NT;
       const int g0 = tid * per, g1 = min(G, g0 + per);
@@ -1152,6 +1353,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
 }
 
+
 // ---------------------------------------------------------------------------------------------------
 // process_action: ActionManager.process_action + JointAction.process_actions [IL]
 // ---------------------------------------------------------------------------------------------------
@@ -1198,48 +1400,121 @@ struct RlCtx {
   float* log_partials;
   int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
+  uint32_t* in_rows_dev;
+  uint32_t* out_rows_dev;
+  int n_in_rows, n_out_rows;
   int sm_count;
   int use_pdl;
+  int baked;   // index into RL_BAKED_LIST when the spec equals a build-time specialised one, else -1
 };
 
 namespace {
 
-int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-Layout make_layout(const RlStepSpec& s, int E) {
-  Layout L;
-  memset(&L, 0, sizeof(L));
-  int w = 0;
-  auto take = [&](int n) { int o = w * E; w += n; return o; };
-  const int J = s.num_joints, A = s.action.n_actions, K = s.num_reward_terms;
-  L.root_pos = take(3); L.quat = take(4); L.lin_vel = take(3); L.ang_vel = take(3);
-  L.jpos = take(J); L.jvel = take(J); L.jacc = take(J); L.jtau = take(J);
-  L.act = take(A); L.pact = take(A);
-  L.cmd = take(3); L.head = take(1); L.tleft = take(1); L.ishead = take(1); L.isstand = take(1);
-  L.mxy = take(1); L.myaw = take(1); L.eplen = take(1);
-  L.sums = take(K);
-  L.cair = take(s.num_time_bodies); L.lair = take(s.num_time_bodies);
-  L.ccon = take(s.num_time_bodies); L.lcon = take(s.num_time_bodies);
-  L.bpos = take(s.num_asset_bodies * 3); L.bvel = take(s.num_asset_bodies * 3);
-  L.raypos = take(1);
-  L.cmdu = take(RL_NUM_CMD_UNIFORMS);
-  L.bmax = take(s.num_hist_bodies);
-  L.rew = take(1); L.flags = take(1); L.stepr = take(K);
-  L.soa_words = w;
-  int off = align_up(w * E, 32);  // 128-byte aligned AoS sections (bulk copies need 16 B)
-  L.hist_pitch = s.hist_len * s.num_hist_bodies * 3;
-  L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
-  L.rays_pitch = s.num_rays;
-  L.rays = off; off = align_up(off + E * L.rays_pitch, 32);
-  for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
-    L.obs_pitch[g] = s.obs[g].dim;
-    L.obs[g] = off; off = align_up(off + E * L.obs_pitch[g], 32);
+// static row tables (field, component, record word); E-independent
+int build_row_tables(RlCtx* ctx) {
+  const RlStepSpec& s = ctx->spec;
+  const Layout L = make_layout(s, 8);
+  uint32_t rows[2048];
+  int n = 0, word = 0;
+  for (int f = 0; f < IF_COUNT; ++f) {  // same running word count as make_layout
+    for (int c = 0; c < in_field_ncomp(s, f); ++c) rows[n++] = row_pack(f, c, word + c);
+    word += in_field_ncomp(s, f);
   }
-  for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
-    L.obsu[g] = off; off = align_up(off + E * L.obs_pitch[g], 32);
+  ctx->n_in_rows = n;
+  CUDA_TRY(cudaMalloc(&ctx->in_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
+  CUDA_TRY(cudaMemcpy(ctx->in_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  n = 0;
+  const int K = s.num_reward_terms;
+  const int ow[OF_COUNT] = {L.w_rew, L.w_eplen, L.w_sums, L.w_stepr, L.w_cmd, L.w_head, L.w_tleft, L.w_mxy, L.w_myaw};
+  const int oc[OF_COUNT] = {1, 1, K, K, 3, 1, 1, 1, 1};
+  for (int f = 0; f < OF_COUNT; ++f)
+    for (int c = 0; c < oc[f]; ++c) rows[n++] = row_pack(f, c, ow[f] + c);
+  ctx->n_out_rows = n;
+  CUDA_TRY(cudaMalloc(&ctx->out_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
+  CUDA_TRY(cudaMemcpy(ctx->out_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  return RL_OK;
+}
+
+bool to_fd(const RlField& f, FieldD* out) {
+  if (f.env_stride > 0x7fffffffLL || f.comp_stride > 0x7fffffffLL || f.env_stride < 0 || f.comp_stride < 0) return false;
+  out->ptr = f.ptr; out->es = (int)f.env_stride; out->cs = (int)f.comp_stride;
+  return true;
+}
+bool vec4_ok(const FieldD& d, int ncomp) {
+  return d.ptr != nullptr && d.es == 1 && (ncomp == 1 || (d.cs % 4) == 0) && (reinterpret_cast<uintptr_t>(d.ptr) & 15u) == 0;
+}
+
+// Field descriptors + masks of one launch. `state` may be NULL (reset-only launches).
+int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, const RlMdpState* mdp, const RlStepOut* out,
+              const RlRandom* rnd, uint32_t ph, int mode) {
+  const RlStepSpec& s = ctx->spec;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.slot = ctx->slot; a.phases = ph;
+  a.L = ctx->L;
+  a.in_rows = ctx->in_rows_dev; a.n_in_rows = ctx->n_in_rows;
+  a.out_rows = ctx->out_rows_dev; a.n_out_rows = ctx->n_out_rows;
+  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  if (out) a.out = *out;
+  if (rnd) a.rnd = *rnd;
+  bool ok = true;
+  RlField none{nullptr, 0, 0};
+  auto S = [&](const RlField RlStateView::*m) -> const RlField& { return st ? st->*m : none; };
+  ok &= to_fd(S(&RlStateView::root_pos_w), &a.in[IF_ROOT_POS]); ok &= to_fd(S(&RlStateView::root_quat_w), &a.in[IF_QUAT]);
+  ok &= to_fd(S(&RlStateView::root_lin_vel_w), &a.in[IF_LIN_VEL]); ok &= to_fd(S(&RlStateView::root_ang_vel_w), &a.in[IF_ANG_VEL]);
+  ok &= to_fd(S(&RlStateView::joint_pos), &a.in[IF_JPOS]); ok &= to_fd(S(&RlStateView::joint_vel), &a.in[IF_JVEL]);
+  ok &= to_fd(S(&RlStateView::joint_acc), &a.in[IF_JACC]); ok &= to_fd(S(&RlStateView::applied_torque), &a.in[IF_JTAU]);
+  ok &= to_fd(S(&RlStateView::current_air_time), &a.in[IF_CAIR]); ok &= to_fd(S(&RlStateView::last_air_time), &a.in[IF_LAIR]);
+  ok &= to_fd(S(&RlStateView::current_contact_time), &a.in[IF_CCON]); ok &= to_fd(S(&RlStateView::last_contact_time), &a.in[IF_LCON]);
+  ok &= to_fd(S(&RlStateView::body_pos_w), &a.in[IF_BPOS]); ok &= to_fd(S(&RlStateView::body_lin_vel_w), &a.in[IF_BVEL]);
+  ok &= to_fd(S(&RlStateView::ray_sensor_pos_z), &a.in[IF_RAYPOS]);
+  ok &= to_fd(S(&RlStateView::net_forces_w_history), &a.hist); ok &= to_fd(S(&RlStateView::ray_hits_z), &a.rays);
+  ok &= to_fd(mdp->command, &a.in[IF_CMD]); ok &= to_fd(mdp->heading_target, &a.in[IF_HEAD]);
+  ok &= to_fd(mdp->time_left, &a.in[IF_TLEFT]); ok &= to_fd(mdp->metric_error_vel_xy, &a.in[IF_MXY]);
+  ok &= to_fd(mdp->metric_error_vel_yaw, &a.in[IF_MYAW]); ok &= to_fd(mdp->episode_length, &a.in[IF_EPLEN]);
+  ok &= to_fd(mdp->episode_sums, &a.in[IF_SUMS]);
+  ok &= to_fd(mdp->action, &a.action); ok &= to_fd(mdp->prev_action, &a.prev_action);
+  ok &= to_fd(mdp->is_heading_env, &a.is_heading); ok &= to_fd(mdp->is_standing_env, &a.is_standing);
+  if (!ok) return fail(RL_EINVAL, "field strides must be non-negative and below 2^31 elements%s", "");
+  a.in[IF_CMDU] = FieldD{a.rnd.cmd_uniforms, 1, (int)num_envs};
+  const bool need_hist = (mode == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
+  uint32_t m = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_JPOS) |
+               (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN);
+  if (need_hist)
+    m |= (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) | (1u << IF_LCON) |
+         (1u << IF_BPOS) | (1u << IF_BVEL);
+  if (mode == 0 && (ph & RL_PHASE_REWARDS)) m |= 1u << IF_SUMS;
+  if (mode == 0 && (ph & RL_PHASE_COMMAND)) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
+  if (mode == 0 && (ph & RL_PHASE_RESET)) m |= (1u << IF_SUMS) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_HEAD) | (1u << IF_CMDU);
+  if (mode == 0 && (ph & RL_PHASE_OBS) && s.num_rays > 0) m |= 1u << IF_RAYPOS;
+  uint32_t v4 = 0;
+  for (int f = 0; f < IF_COUNT; ++f) {
+    if (a.in[f].ptr == nullptr) m &= ~(1u << f);
+    else if (vec4_ok(a.in[f], in_field_ncomp(s, f))) v4 |= 1u << f;
   }
-  L.total_words = off;
-  return L;
+  a.in_mask = m; a.in_vec4 = v4;
+  // outputs
+  if (mode == 0) {
+    a.outf[OF_REWARD] = FieldD{a.out.reward, 1, 0};
+    a.outf[OF_EPLEN] = a.in[IF_EPLEN]; a.outf[OF_SUMS] = a.in[IF_SUMS];
+    FieldD sr; if (!to_fd(a.out.step_reward, &sr)) return fail(RL_EINVAL, "bad step_reward strides%s", "");
+    a.outf[OF_STEPR] = sr;
+    a.outf[OF_CMD] = a.in[IF_CMD]; a.outf[OF_HEAD] = a.in[IF_HEAD]; a.outf[OF_TLEFT] = a.in[IF_TLEFT];
+    a.outf[OF_MXY] = a.in[IF_MXY]; a.outf[OF_MYAW] = a.in[IF_MYAW];
+    uint32_t om = 0;
+    if (ph & RL_PHASE_DONES) om |= 1u << OF_EPLEN;
+    if (ph & RL_PHASE_REWARDS) om |= (1u << OF_REWARD) | (1u << OF_SUMS) | (1u << OF_STEPR);
+    if (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) om |= (1u << OF_CMD) | (1u << OF_HEAD) | (1u << OF_TLEFT) | (1u << OF_MXY) | (1u << OF_MYAW);
+    if (ph & RL_PHASE_RESET) om |= (1u << OF_SUMS) | (1u << OF_EPLEN);
+    const int oc[OF_COUNT] = {1, 1, s.num_reward_terms, s.num_reward_terms, 3, 1, 1, 1, 1};
+    uint32_t ov4 = 0;
+    for (int f = 0; f < OF_COUNT; ++f) {
+      if (a.outf[f].ptr == nullptr) om &= ~(1u << f);
+      else if (vec4_ok(a.outf[f], oc[f])) ov4 |= 1u << f;
+    }
+    a.out_mask = om; a.out_vec4 = ov4;
+  }
+  return RL_OK;
 }
 
 int validate_spec(const RlStepSpec* s) {
@@ -1280,13 +1555,13 @@ int validate_spec(const RlStepSpec* s) {
   return RL_OK;
 }
 
-template <int E, int LPE, int MODE>
+template <class P, int E, int LPE, int MODE>
 int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   const size_t smem = (size_t)ctx->L.total_words * 4;
   static thread_local int configured_device = -1;
   static thread_local size_t configured_smem = 0;
   if (configured_device != ctx->device || configured_smem < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<E, LPE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, E, LPE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = ctx->device; configured_smem = smem;
   }
   const int grid = (n_items + E - 1) / E;
@@ -1298,22 +1573,44 @@ int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<E, LPE, MODE>, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, E, LPE, MODE>, a));
+  return RL_OK;
+}
+
+// (envs per CTA, lanes per env) pairs compiled for the generic kernel / for every baked spec
+#define RL_DYN_CONFIGS(X) X(8, 8) X(8, 16) X(16, 4) X(16, 8) X(32, 4) X(32, 8)
+#define RL_STATIC_CONFIGS(X) X(8, 8) X(8, 16) X(16, 8)
+
+template <class P, int MODE>
+int dispatch_config(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st, bool* found) {
+  const int key = ctx->E * 100 + ctx->LPE;
+  *found = true;
+  if constexpr (P::kStatic) {
+#define RL_CASE(E_, L_) if (key == (E_) * 100 + (L_)) return launch_step<P, E_, L_, MODE>(ctx, a, n_items, st);
+    RL_STATIC_CONFIGS(RL_CASE)
+#undef RL_CASE
+  } else {
+#define RL_CASE(E_, L_) if (key == (E_) * 100 + (L_)) return launch_step<P, E_, L_, MODE>(ctx, a, n_items, st);
+    RL_DYN_CONFIGS(RL_CASE)
+#undef RL_CASE
+  }
+  *found = false;
   return RL_OK;
 }
 
 template <int MODE>
 int dispatch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
-  const int key = ctx->E * 100 + ctx->LPE;
-  switch (key) {
-    case 808: return launch_step<8, 8, MODE>(ctx, a, n_items, st);
-    case 816: return launch_step<8, 16, MODE>(ctx, a, n_items, st);
-    case 1604: return launch_step<16, 4, MODE>(ctx, a, n_items, st);
-    case 1608: return launch_step<16, 8, MODE>(ctx, a, n_items, st);
-    case 3204: return launch_step<32, 4, MODE>(ctx, a, n_items, st);
-    case 3208: return launch_step<32, 8, MODE>(ctx, a, n_items, st);
-    default: return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", ctx->E, ctx->LPE);
+  bool found = false;
+  if (MODE == 0 && ctx->baked >= 0) {
+    int idx = 0, rc = RL_OK;
+#define RL_TRY_BAKED(B) if (idx++ == ctx->baked) rc = dispatch_config<StaticPolicy<baked::B>, 0>(ctx, a, n_items, st, &found);
+    RL_BAKED_LIST(RL_TRY_BAKED)
+#undef RL_TRY_BAKED
+    if (found) return rc;
   }
+  int rc = dispatch_config<DynPolicy, MODE>(ctx, a, n_items, st, &found);
+  if (!found) return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", ctx->E, ctx->LPE);
+  return rc;
 }
 
 int ensure_scratch(RlCtx* ctx, int grid) {
@@ -1395,6 +1692,15 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   CUDA_TRY(cudaMalloc(&ctx->adhoc_dev, sizeof(RlRewardTerm) * 64));
   rc = ensure_scratch(ctx, 4096);
   if (rc != RL_OK) return rc;
+  rc = build_row_tables(ctx);
+  if (rc != RL_OK) return rc;
+  ctx->baked = -1;
+  {
+    int idx = 0;
+#define RL_MATCH_BAKED(B) if (ctx->baked < 0 && memcmp(spec, &baked::B::spec, sizeof(RlStepSpec)) == 0) ctx->baked = idx; ++idx;
+    RL_BAKED_LIST(RL_MATCH_BAKED)
+#undef RL_MATCH_BAKED
+  }
   g_slots[device][slot] = true;
   *out = ctx;
   return RL_OK;
@@ -1407,6 +1713,8 @@ void rl_ctx_destroy(RlCtx* ctx) {
   if (ctx->cta_mask) cudaFree(ctx->cta_mask);
   if (ctx->log_partials) cudaFree(ctx->log_partials);
   if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
+  if (ctx->in_rows_dev) cudaFree(ctx->in_rows_dev);
+  if (ctx->out_rows_dev) cudaFree(ctx->out_rows_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
 }
@@ -1416,7 +1724,7 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env) {
   const int E = envs_per_cta > 0 ? envs_per_cta : 16;
   const int LPE = lanes_per_env > 0 ? lanes_per_env : 8;
   const int key = E * 100 + LPE;
-  const int okeys[] = {808, 816, 1604, 1608, 3204, 3208};
+  const int okeys[] = {808, 816, 1604, 1608, 3204, 3208};  // RL_DYN_CONFIGS
   bool ok = false;
   for (int k : okeys) ok = ok || (k == key);
   if (!ok) return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", E, LPE);
@@ -1511,11 +1819,9 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
     }
   }
   KArgs a;
-  memset(&a, 0, sizeof(a));
-  a.N = (int)num_envs; a.slot = ctx->slot; a.phases = phases; a.has_ids = env_ids != nullptr;
-  a.st = *state; a.mdp = *mdp; a.out = *out; a.rnd = *rnd;
-  a.env_ids = env_ids; a.n_env_ids = n_env_ids; a.L = ctx->L;
-  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  int frc = fill_args(ctx, a, num_envs, state, mdp, out, rnd, phases, 0);
+  if (frc != RL_OK) return frc;
+  a.has_ids = env_ids != nullptr; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
   return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
@@ -1537,12 +1843,13 @@ int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uin
     if (rc != RL_OK) return rc;
   }
   KArgs a;
-  memset(&a, 0, sizeof(a));
-  a.N = (int)num_envs; a.slot = ctx->slot; a.phases = RL_PHASE_RESET; a.has_ids = 1;
-  a.mdp = *mdp; a.rnd = *rnd; a.out.done_bits = const_cast<uint8_t*>(done_bits);
-  if (log) a.out.reset_log = *log;
-  a.env_ids = env_ids; a.n_env_ids = n_env_ids; a.L = ctx->L;
-  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  RlStepOut o;
+  memset(&o, 0, sizeof(o));
+  o.done_bits = const_cast<uint8_t*>(done_bits);
+  if (log) o.reset_log = *log;
+  int frc = fill_args(ctx, a, num_envs, nullptr, mdp, &o, rnd, RL_PHASE_RESET, 0);
+  if (frc != RL_OK) return frc;
+  a.has_ids = 1; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
   return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
@@ -1563,9 +1870,8 @@ int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const R
   RlRewardTerm* dev = ctx->adhoc_dev + (ring++ & 63);
   CUDA_TRY(cudaMemcpyAsync(dev, term, sizeof(RlRewardTerm), cudaMemcpyHostToDevice, st));
   KArgs a;
-  memset(&a, 0, sizeof(a));
-  a.N = (int)num_envs; a.slot = ctx->slot; a.phases = 0; a.has_ids = 0;
-  a.st = *state; a.mdp = *mdp; a.L = ctx->L;
+  int frc = fill_args(ctx, a, num_envs, state, mdp, nullptr, nullptr, 0, 1);
+  if (frc != RL_OK) return frc;
   a.adhoc = dev; a.ext_terminated = terminated; a.term_out = out; a.use_pdl = 0;
   return dispatch_step<1>(ctx, a, (int)num_envs, st);
 }

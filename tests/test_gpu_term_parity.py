@@ -86,6 +86,6 @@ def test_whole_catalogue_including_inactive_terms(native_lib):
     feet = tuple(n for n in layout.asset.body_names if n.endswith("_foot"))
     layout = SceneLayout(layout.asset, layout.hist_body_names, feet, feet, layout.terrain, layout.num_rays, layout.hist_len)
     spec = compile_step_spec(cfg, layout)
-    assert spec.K >= 36
+    assert spec.K >= 34
     _check_terms(spec, spec.rewards)
     del base
