@@ -448,7 +448,7 @@ def measure_handoff(spec, N, world, dev, local_rank):
 
     width = rollout_row_width(spec)
     local = torch.randn(ROLLOUT, N, width, device=dev)
-    gathered = torch.empty(world, ROLLOUT, N, width, device=dev)
+    gathered = torch.empty(world * ROLLOUT, N, width, device=dev)
     for _ in range(3):
         dist.all_gather_into_tensor(gathered, local)
     torch.cuda.synchronize(dev)

@@ -66,6 +66,8 @@ class RolloutBuffer:
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return self.data
         world = dist.get_world_size(group)
-        out = torch.empty(world, *self.data.shape, device=self.data.device, dtype=self.data.dtype)
+        # concatenated-along-dim-0 output: the form both NCCL and gloo accept
+        out = torch.empty(world * self.steps, self.N, self.width, device=self.data.device, dtype=self.data.dtype)
         dist.all_gather_into_tensor(out, self.data.contiguous(), group=group)
+        out = out.view(world, self.steps, self.N, self.width)
         return out.permute(1, 0, 2, 3).reshape(self.steps, world * self.N, self.width)

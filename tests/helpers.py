@@ -94,3 +94,46 @@ def compare_outputs(got: dict, ref: dict, rtol=RTOL, atol=ATOL, keys=None) -> di
     if failures:
         raise AssertionError("parity failures:\n  " + "\n  ".join(failures))
     return report
+
+
+def make_catalogue_spec():
+    """Go2 with EVERY reward term of the reference's catalogue switched on (weights 1), incl. the ones the in-scope
+    tasks leave at 0 (V/velocity_env_cfg.py:379-644) and feet_distance_xy_exp (commented out there, :633-642)."""
+    import math
+
+    from robot_lab_b200 import mdp
+    from robot_lab_b200.cfg import RewardTermCfg, SceneEntityCfg
+    from robot_lab_b200.spec import SceneLayout
+    from robot_lab_b200.tasks.locomotion_velocity import _reward_catalogue
+
+    cfg = make_env_cfg(TASKS["go2_rough"])
+    cat = _reward_catalogue()
+    foot = [".*_foot"]
+    for name in ("feet_air_time", "feet_air_time_variance", "feet_contact", "feet_contact_without_cmd", "feet_stumble",
+                 "contact_forces"):
+        getattr(cat, name).params["sensor_cfg"].body_names = foot
+    cat.undesired_contacts.params["sensor_cfg"].body_names = ["^(?!.*_foot).*"]
+    cat.feet_slide.params["sensor_cfg"].body_names = foot
+    for name in ("feet_slide", "feet_height", "feet_height_body", "feet_distance_y_exp"):
+        getattr(cat, name).params["asset_cfg"].body_names = foot
+    cat.feet_distance_y_exp.params["stance_width"] = 0.3
+    cat.feet_gait.params["synced_feet_pair_names"] = (("FL_foot", "RR_foot"), ("FR_foot", "RL_foot"))
+    cat.base_height_l2.params["sensor_cfg"] = None
+    cat.base_height_l2.params["target_height"] = 0.33
+    cat.joint_mirror.params["mirror_joints"] = [["FR_(hip|thigh|calf).*", "RL_(hip|thigh|calf).*"],
+                                                ["FL_(hip|thigh|calf).*", "RR_(hip|thigh|calf).*"]]
+    cat.action_mirror.params["mirror_joints"] = cat.joint_mirror.params["mirror_joints"]
+    cat.wheel_vel_penalty.params["asset_cfg"].joint_names = [".*_calf_joint"]
+    cat.wheel_vel_penalty.params["sensor_cfg"].body_names = foot
+    cat.feet_distance_xy_exp = RewardTermCfg(func=mdp.feet_distance_xy_exp, weight=0.0, params={
+        "std": math.sqrt(0.25), "asset_cfg": SceneEntityCfg("robot", body_names=foot), "stance_length": 0.4,
+        "stance_width": 0.3})
+    cat.joint_deviation_hip = RewardTermCfg(func=mdp.joint_deviation_l1, weight=0.0, params={
+        "asset_cfg": SceneEntityCfg("robot", joint_names=[".*_hip_joint"])})
+    for _, term in cat.items():
+        term.weight = 1.0
+    cfg.rewards = cat
+    full = cfg.scene.make_layout()
+    feet = tuple(n for n in full.asset.body_names if n.endswith("_foot"))
+    layout = SceneLayout(full.asset, full.hist_body_names, feet, feet, full.terrain, full.num_rays, full.hist_len)
+    return cfg, compile_step_spec(cfg, layout)

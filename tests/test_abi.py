@@ -1,0 +1,91 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/rl_mdp_step.h declares, and the
+ctypes mirror agrees with the header (struct sizes, enum values, limits). No compute calls here."""
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "rl_mdp_step.h").read_text()
+
+
+def test_library_loads_and_exports_every_declared_symbol(native_lib):
+    from robot_lab_b200 import _native as nat
+
+    declared = set(re.findall(r"^\s*(?:int64_t|int|void|const char\*)\s+(rl_[a-z_]+)\(", HEADER, re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(nat.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(native_lib, sym), sym
+    assert native_lib.rl_abi_version() == nat.RL_ABI_VERSION == int(re.search(r"#define RL_ABI_VERSION (\d+)", HEADER).group(1))
+
+
+def test_struct_sizes_match(native_lib):
+    from robot_lab_b200 import _native as nat
+
+    for st in nat._STRUCTS:
+        assert native_lib.rl_struct_sizeof(st.__name__.encode()) == C.sizeof(st), st.__name__
+    assert native_lib.rl_struct_sizeof(b"NoSuchStruct") == -1
+
+
+def _enum(name):
+    body = re.search(r"enum %s \{(.*?)\};" % name, HEADER, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return {m.group(1): int(m.group(2)) for m in re.finditer(r"(RL_[A-Z0-9_]+)\s*=\s*(-?\d+)", body)}
+
+
+def test_enums_and_limits_match_header():
+    from robot_lab_b200 import _native as nat
+
+    rew = _enum("RlRewardType")
+    for name, val in nat.REWARD_TYPES.items():
+        assert rew["RL_REW_" + name.upper()] == val, name
+    assert len(nat.REWARD_TYPES) == rew["RL_REW_TYPE_COUNT"] - 1
+    obs = _enum("RlObsType")
+    for name, val in nat.OBS_TYPES.items():
+        assert obs["RL_OBS_" + name.upper()] == val, name
+    done = _enum("RlDoneType")
+    for name, val in nat.DONE_TYPES.items():
+        assert done["RL_DONE_" + name.upper()] == val, name
+    ph = _enum("RlPhase")
+    assert (ph["RL_PHASE_DONES"], ph["RL_PHASE_REWARDS"], ph["RL_PHASE_COMMAND"], ph["RL_PHASE_OBS"],
+            ph["RL_PHASE_COMPACT"], ph["RL_PHASE_SKIP_DONE_ENVS"], ph["RL_PHASE_RESET"], ph["RL_PHASE_ALL"]) == (
+        nat.PHASE_DONES, nat.PHASE_REWARDS, nat.PHASE_COMMAND, nat.PHASE_OBS, nat.PHASE_COMPACT,
+        nat.PHASE_SKIP_DONE_ENVS, nat.PHASE_RESET, nat.PHASE_ALL)
+    for macro in ("RL_MAX_JOINTS", "RL_MAX_BODIES", "RL_MAX_TIME_BODIES", "RL_MAX_ASSET_BODIES", "RL_MAX_REWARD_TERMS",
+                  "RL_MAX_OBS_TERMS", "RL_MAX_DONE_TERMS", "RL_MAX_IDX", "RL_NUM_OBS_GROUPS", "RL_NUM_CMD_UNIFORMS"):
+        assert int(re.search(r"#define %s (\d+)" % macro, HEADER).group(1)) == getattr(nat, macro), macro
+
+
+def test_every_mdp_term_function_has_an_abi_type():
+    from robot_lab_b200 import _native as nat
+    from robot_lab_b200 import mdp
+
+    tables = {"reward": nat.REWARD_TYPES, "obs": nat.OBS_TYPES, "done": nat.DONE_TYPES}
+    seen = {k: set() for k in tables}
+    for name, fn in mdp.all_terms().items():
+        assert tables[fn.rl_kind][fn.rl_type_name] == fn.rl_type_id, name
+        seen[fn.rl_kind].add(fn.rl_type_name)
+    for kind, table in tables.items():
+        assert seen[kind] == set(table), (kind, set(table) - seen[kind])
+
+
+def test_product_path_fails_loudly_without_the_library(monkeypatch, tmp_path):
+    """No CPU fallback: a missing .so is an error, not a silent detour through the oracle."""
+    from robot_lab_b200 import _native as nat
+
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setenv("RL_MDPSTEP_LIB", str(tmp_path / "missing.so"))
+    with pytest.raises(nat.NativeError, match="no CPU fallback"):
+        nat.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = ROOT / "robot_lab_b200"
+    for py in pkg.rglob("*.py"):
+        text = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), py
+    for src in (pkg / "csrc").rglob("*.cu"):
+        assert "oracle" not in src.read_text().lower().replace("// oracle", ""), src
