@@ -137,3 +137,33 @@ def make_catalogue_spec():
     feet = tuple(n for n in full.asset.body_names if n.endswith("_foot"))
     layout = SceneLayout(full.asset, full.hist_body_names, feet, feet, full.terrain, full.num_rays, full.hist_len)
     return cfg, compile_step_spec(cfg, layout)
+
+
+def oracle_env_rollout(spec, mdp0: dict, phys: list[dict], actions: list[torch.Tensor], seed: int, n_envs: int):
+    """CPU replay of ``ManagerBasedRLEnv.step()`` (robot_lab_b200.envs) for a list of physics states / actions, with
+    the production Philox streams: returns per-step (obs_policy, obs_critic, reward, terminated, truncated, mdp)."""
+    mdp = {k: v.clone() for k, v in mdp0.items()}
+    outs = []
+    keys_cmd = ("command", "heading_target", "time_left", "is_heading_env", "is_standing_env",
+                "metric_error_vel_xy", "metric_error_vel_yaw")
+    for t, (ph, act) in enumerate(zip(phys, actions)):
+        rnd = {"seed": seed, "step": t + 1, "env_id_offset": 0}
+        action, prev, _ = port.process_action(spec, mdp, act)
+        mdp["action"], mdp["prev_action"] = action, prev
+        st = {**ph, **mdp}
+        out = port.step(spec, st, rnd, skip_done_envs=True)
+        for k in keys_cmd + ("episode_length", "episode_sums"):
+            mdp[k] = out[k]
+        st = {**ph, **mdp}
+        st2, _log = port.reset_envs(spec, st, out["reset_ids"], out["done_bits"], rnd)
+        mdp.update(st2)
+        mask = torch.zeros(n_envs, dtype=torch.bool)
+        mask[out["reset_ids"].long()] = True
+        st = {**ph, **mdp}
+        mdp.update(port.compute_command(spec, st, rnd, active=mask))
+        st = {**ph, **mdp}
+        obs_p = torch.where(mask[:, None], port.compute_obs_group(spec, 0, st, rnd), out["obs_policy"])
+        obs_c = torch.where(mask[:, None], port.compute_obs_group(spec, 1, st, rnd), out["obs_critic"])
+        outs.append({"obs_policy": obs_p, "obs_critic": obs_c, "reward": out["reward"], "terminated": out["terminated"],
+                     "truncated": out["truncated"], "mdp": {k: v.clone() for k, v in mdp.items()}})
+    return outs
