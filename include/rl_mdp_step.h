@@ -353,8 +353,10 @@ int64_t rl_struct_sizeof(const char* name);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knobs (envs per CTA, lanes per env). 0 = library default. */
-int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env);
+/* Tuning knob: warps per CTA (4, 8, 12 or 16; 0 = default 8). A CTA always owns 32 consecutive envs (one lane per
+ * env); its warps share the reward / observation terms according to a static schedule. envs_per_cta must be 0 or 32.
+ * Synchronous (re-uploads the schedule): call it outside hot loops and outside stream capture. */
+int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);

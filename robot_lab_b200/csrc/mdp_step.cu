@@ -66,6 +66,8 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0, long lo
 // result rows back with one generic loop - the row tables (field id, component, record word) are static per
 // context and live in global memory; only the ~25 field descriptors (pointer + strides) travel per launch.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
+
 struct FieldD {
   const void* ptr;
   int es;    // env stride   (elements)
@@ -75,20 +77,21 @@ struct FieldD {
 enum InField {
   IF_ROOT_POS = 0, IF_QUAT, IF_LIN_VEL, IF_ANG_VEL, IF_JPOS, IF_JVEL, IF_JACC, IF_JTAU,
   IF_CAIR, IF_LAIR, IF_CCON, IF_LCON, IF_BPOS, IF_BVEL, IF_RAYPOS,
-  IF_CMD, IF_HEAD, IF_TLEFT, IF_MXY, IF_MYAW, IF_EPLEN, IF_SUMS, IF_CMDU, IF_COUNT
+  IF_CMD, IF_HEAD, IF_TLEFT, IF_MXY, IF_MYAW, IF_EPLEN, IF_SUMS, IF_CMDU, IF_ACT, IF_PACT, IF_COUNT
 };
-enum OutField { OF_REWARD = 0, OF_EPLEN, OF_SUMS, OF_STEPR, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_COUNT };
+enum OutField { OF_REWARD = 0, OF_EPLEN, OF_SUMS, OF_STEPR, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_ACT, OF_PACT, OF_COUNT };
 
 // row meta: field (bits 0-5) | comp (6-15) | record word (16-31)
-__host__ __device__ __forceinline__ uint32_t row_pack(int f, int c, int w) { return (uint32_t)f | ((uint32_t)c << 6) | ((uint32_t)w << 16); }
+__host__ __device__ constexpr uint32_t row_pack(int f, int c, int w) { return (uint32_t)f | ((uint32_t)c << 6) | ((uint32_t)w << 16); }
 
 // ---------------------------------------------------------------------------------------------------
-// Shared-memory layout of one CTA tile (word offsets, already multiplied by E for the SoA words).
+// Shared-memory layout of one CTA tile (word offsets; SoA words already multiplied by kE).
 // ---------------------------------------------------------------------------------------------------
 struct Layout {
-  int A, J;
-  int root_pos, quat, lin_vel, ang_vel;          // SoA offsets (= word * E)
+  int A, J, K;
+  int root_pos, quat, lin_vel, ang_vel;          // SoA offsets (= word * kE)
   int jpos, jvel, jacc, jtau;
+  int act, pact;
   int cmd, head, tleft, ishead, isstand;
   int mxy, myaw, eplen;
   int sums;
@@ -96,13 +99,12 @@ struct Layout {
   int bpos, bvel;
   int raypos;
   int cmdu;
-  int bmax;                                      // scratch: max_t |F_b|
   int rew, flags, stepr;                         // outputs
-  int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw;  // record words of the out fields
+  int termv;                                     // [K][2] weighted term values (or raw partials of split terms)
+  int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
   int soa_words;
   int cj;                                        // per-joint constants [5][J]: q0, qd0, soft lo, soft hi, vel limit
-  // AoS rows: [E][pitch]
-  int act, pact;                                 // pitch A
+  // AoS rows [kE][pitch]; pitches are forced ODD so that lane e reading row e is bank-conflict free
   int hist, hist_pitch;
   int rays, rays_pitch;
   int obs0, obs1, obs_pitch0, obs_pitch1;          // selected with LOBS(g) etc.: no runtime-indexed members,
@@ -119,18 +121,21 @@ __host__ __device__ constexpr int in_field_ncomp(const RlStepSpec& s, int f) {
     case IF_BPOS: case IF_BVEL: return 3 * s.num_asset_bodies;
     case IF_SUMS: return s.num_reward_terms;
     case IF_CMDU: return RL_NUM_CMD_UNIFORMS;
+    case IF_ACT: case IF_PACT: return s.action.n_actions;
     default: return 1;
   }
 }
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+__host__ __device__ constexpr int odd_pitch(int n) { return n <= 0 ? 1 : (n | 1); }
 
-__host__ __device__ constexpr Layout make_layout(const RlStepSpec& s, int E) {
+__host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   Layout L{};
+  constexpr int E = kE;
   int w = 0;
   auto take = [&w](int n) { int o = w; w += n; return o; };
   const int J = s.num_joints, A = s.action.n_actions, K = s.num_reward_terms;
-  L.A = A; L.J = J;
+  L.A = A; L.J = J; L.K = K;
   int in_word[IF_COUNT] = {};
   for (int f = 0; f < IF_COUNT; ++f) in_word[f] = take(in_field_ncomp(s, f));
   L.root_pos = in_word[IF_ROOT_POS] * E; L.quat = in_word[IF_QUAT] * E;
@@ -141,23 +146,23 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s, int E) {
   L.cmd = in_word[IF_CMD] * E; L.head = in_word[IF_HEAD] * E; L.tleft = in_word[IF_TLEFT] * E;
   L.mxy = in_word[IF_MXY] * E; L.myaw = in_word[IF_MYAW] * E; L.eplen = in_word[IF_EPLEN] * E;
   L.sums = in_word[IF_SUMS] * E; L.cmdu = in_word[IF_CMDU] * E;
+  L.act = in_word[IF_ACT] * E; L.pact = in_word[IF_PACT] * E;
   L.w_eplen = in_word[IF_EPLEN]; L.w_sums = in_word[IF_SUMS]; L.w_cmd = in_word[IF_CMD];
   L.w_head = in_word[IF_HEAD]; L.w_tleft = in_word[IF_TLEFT]; L.w_mxy = in_word[IF_MXY]; L.w_myaw = in_word[IF_MYAW];
+  L.w_act = in_word[IF_ACT]; L.w_pact = in_word[IF_PACT];
   L.ishead = take(1) * E; L.isstand = take(1) * E;
-  L.bmax = take(s.num_hist_bodies) * E;
   L.w_rew = take(1); L.rew = L.w_rew * E;
   L.flags = take(1) * E;
   L.w_stepr = take(K); L.stepr = L.w_stepr * E;
+  L.termv = take(2 * K) * E;
   L.soa_words = w;
   int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
   L.cj = off; off = align_up(off + 5 * J, 32);
-  L.act = off; off = align_up(off + E * A, 32);
-  L.pact = off; off = align_up(off + E * A, 32);
-  L.hist_pitch = s.hist_len * s.num_hist_bodies * 3;
+  L.hist_pitch = odd_pitch(s.hist_len * s.num_hist_bodies * 3);
   L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
-  L.rays_pitch = s.num_rays;
+  L.rays_pitch = odd_pitch(s.num_rays);
   L.rays = off; off = align_up(off + E * L.rays_pitch, 32);
-  L.obs_pitch0 = s.obs[0].dim; L.obs_pitch1 = s.obs[1].dim;
+  L.obs_pitch0 = odd_pitch(s.obs[0].dim); L.obs_pitch1 = odd_pitch(s.obs[1].dim);
   L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
   L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
   L.obsu0 = off; off = align_up(off + E * L.obs_pitch0, 32);
@@ -166,6 +171,109 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s, int E) {
   return L;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Work schedule. The compute phase is thread-per-env (lane e of every warp owns env e, so SIMT lanes never
+// duplicate per-env scalar work); the warps of a CTA differ in WHICH tasks they run: one task per reward term
+// (wide body-mask terms split in two halves) and one per observation term (the height scan in 64-column chunks),
+// balanced over the warps by a longest-processing-time greedy on rough instruction costs. constexpr, so a baked
+// spec gets its schedule at compile time and every warp's code is straight-line.
+// ---------------------------------------------------------------------------------------------------
+#define RL_MAX_TASKS 112
+enum { TK_REWARD = 0, TK_OBS = 1 };
+constexpr int kStage2Owner = 255;  // tasks that need the post-update command run in stage 2 (warp 1)
+
+struct Task {
+  uint8_t kind, a, b, owner;   // REWARD: a = term k, b = half (0/1); OBS: a = group, b = term index
+  uint16_t lo, hi;             // REWARD: body-index range [lo, hi); OBS: column range within the term
+  uint16_t col0, pad;          // OBS: first column of the term inside the group row
+};
+struct Schedule {
+  int n;
+  Task t[RL_MAX_TASKS];
+  uint8_t split[RL_MAX_REWARD_TERMS];   // term evaluated as two partial sums (termv[k][0] + termv[k][1])
+  uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (split terms, is_terminated)
+};
+
+__host__ __device__ constexpr int popc64(uint64_t m) { int n = 0; while (m) { m &= m - 1; ++n; } return n; }
+
+__host__ __device__ constexpr int reward_cost(const RlRewardTerm& t, const RlStepSpec& s, int nbodies) {
+  const int J = popc64(t.joint_mask), F = t.n_idx, T = s.hist_len;
+  switch (t.type) {
+    case RL_REW_JOINT_TORQUES_L2: case RL_REW_JOINT_VEL_L2: case RL_REW_JOINT_ACC_L2: case RL_REW_JOINT_DEVIATION_L1:
+    case RL_REW_JOINT_POWER: case RL_REW_STAND_STILL: return 30 + 5 * J;
+    case RL_REW_JOINT_POS_LIMITS: case RL_REW_JOINT_VEL_LIMITS: case RL_REW_JOINT_POS_PENALTY: return 40 + 8 * J;
+    case RL_REW_JOINT_MIRROR: case RL_REW_ACTION_MIRROR: return 30 + 8 * F;
+    case RL_REW_ACTION_SYNC: return 40 + 30 * F;
+    case RL_REW_ACTION_RATE_L2: return 30 + 5 * s.action.n_actions;
+    case RL_REW_UNDESIRED_CONTACTS: case RL_REW_CONTACT_FORCES: return 30 + nbodies * T * 18;
+    case RL_REW_TRACK_LIN_VEL_XY_EXP: case RL_REW_TRACK_ANG_VEL_Z_EXP: case RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP: return 70;
+    case RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP: return 260;
+    case RL_REW_FEET_AIR_TIME: case RL_REW_FEET_CONTACT: case RL_REW_FEET_CONTACT_WITHOUT_CMD: return 30 + 10 * F;
+    case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: return 40 + 12 * F;
+    case RL_REW_FEET_AIR_TIME_VARIANCE: return 40 + 40 * F;
+    case RL_REW_FEET_GAIT: return 260;
+    case RL_REW_FEET_STUMBLE: return 30 + 20 * F;
+    case RL_REW_FEET_SLIDE: return 30 + F * (60 + T * 18);
+    case RL_REW_FEET_HEIGHT: return 40 + 60 * F;
+    case RL_REW_FEET_HEIGHT_BODY: return 40 + 130 * F;
+    case RL_REW_FEET_DISTANCE_Y_EXP: case RL_REW_FEET_DISTANCE_XY_EXP: return 80 + 60 * F;
+    case RL_REW_WHEEL_VEL_PENALTY: return 40 + 12 * F;
+    default: return 30;
+  }
+}
+
+__host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw) {
+  Schedule sc{};
+  int cost[RL_MAX_TASKS] = {};
+  int n = 0;
+  for (int k = 0; k < s.num_reward_terms; ++k) {
+    const RlRewardTerm& t = s.rewards[k];
+    if (t.weight == 0.f) continue;
+    if (t.type == RL_REW_IS_TERMINATED) { sc.late[k] = 1; continue; }
+    const bool body_sum = (t.type == RL_REW_UNDESIRED_CONTACTS || t.type == RL_REW_CONTACT_FORCES);
+    const int nb = popc64(t.body_mask);
+    if (body_sum && nb > 8) {
+      int seen = 0, mid = 0;  // split after the first nb/2 set bits
+      for (int b = 0; b < 64; ++b) if ((t.body_mask >> b) & 1ull) { if (++seen == nb / 2) { mid = b + 1; break; } }
+      sc.split[k] = 1; sc.late[k] = 1;
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, (uint16_t)mid, 0, 0}; cost[n++] = reward_cost(t, s, nb / 2);
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 1, 0, (uint16_t)mid, 64, 0, 0}; cost[n++] = reward_cost(t, s, nb - nb / 2);
+    } else {
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 0, 0}; cost[n++] = reward_cost(t, s, nb);
+    }
+  }
+  for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+    int col0 = 0;
+    for (int ti = 0; ti < s.obs[g].n_terms; ++ti) {
+      const RlObsTerm& o = s.obs[g].terms[ti];
+      const int per_col = 8 + ((o.has_noise && s.obs[g].enable_corruption) ? 24 : 0);
+      if (o.type == RL_OBS_GENERATED_COMMANDS) {
+        sc.t[n] = Task{TK_OBS, (uint8_t)g, (uint8_t)ti, (uint8_t)kStage2Owner, 0, (uint16_t)o.dim, (uint16_t)col0, 0}; cost[n++] = 0;
+      } else {
+        for (int lo = 0; lo < o.dim; lo += 64) {
+          const int hi = (lo + 64 < o.dim) ? lo + 64 : o.dim;
+          sc.t[n] = Task{TK_OBS, (uint8_t)g, (uint8_t)ti, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)col0, 0};
+          cost[n++] = 20 + per_col * (hi - lo);
+        }
+      }
+      col0 += o.dim;
+    }
+  }
+  sc.n = n;
+  // longest-processing-time greedy; warp 0 starts with the termination terms on its plate
+  int load[32] = {};
+  load[0] = 120;
+  bool done[RL_MAX_TASKS] = {};
+  for (int it = 0; it < n; ++it) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) if (!done[i] && sc.t[i].owner != kStage2Owner && (best < 0 || cost[i] > cost[best])) best = i;
+    if (best < 0) break;
+    int w = 0;
+    for (int j = 1; j < nw; ++j) if (load[j] < load[w]) w = j;
+    sc.t[best].owner = (uint8_t)w; load[w] += cost[best]; done[best] = true;
+  }
+  return sc;
+}
 
 struct KArgs {
   int N;
@@ -179,13 +287,14 @@ struct KArgs {
   const uint32_t* in_rows;  int n_in_rows;
   const uint32_t* out_rows; int n_out_rows;
   // AoS spans (row-contiguous per env) and byte fields
-  FieldD action, prev_action, hist, rays;
+  FieldD hist, rays;
   FieldD is_heading, is_standing;               // uint8
   RlStepOut out;
   RlRandom rnd;
   const int32_t* env_ids;
   const int32_t* n_env_ids;
-  Layout L;
+  Layout L;                // generic kernel only; baked kernels compute theirs at compile time
+  const Schedule* sched;   // device copy (generic kernel); baked kernels carry theirs as constexpr data
   unsigned int* ticket;
   uint32_t* cta_mask;
   float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions
@@ -326,7 +435,8 @@ __device__ __noinline__ float rl_cosf(float x) { return cosf(x); }
 // ---------------------------------------------------------------------------------------------------
 // Spec access policies. DynPolicy interprets the context's spec from __constant__ memory (any task);
 // StaticPolicy<B> reads a spec baked in at build time (generated/baked_specs.cuh): every use below is a constant
-// expression, so term dispatch, parameters, index lists, loop bounds and shared-memory offsets fold away.
+// expression, so term dispatch, parameters, index lists, loop bounds, shared-memory offsets and the warp
+// schedule fold away.
 // ---------------------------------------------------------------------------------------------------
 struct Scalars {
   int num_joints, num_hist_bodies, hist_len, num_time_bodies, num_asset_bodies, num_rays;
@@ -346,23 +456,29 @@ __device__ __forceinline__ void static_for(std::integer_sequence<int, Is...>, F&
 
 struct DynPolicy {
   static constexpr bool kStatic = false;
-  template <int E> __device__ __forceinline__ static Layout layout(const KArgs& a) { return a.L; }
+  __device__ __forceinline__ static Layout layout(const KArgs& a) { return a.L; }
   __device__ __forceinline__ static Scalars scalars(const KArgs& a) { return scalars_of(c_spec[a.slot]); }
   __device__ __forceinline__ static const RlCommandCfg& command(const KArgs& a) { return c_spec[a.slot].command; }
-  template <class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+    const int n = a.sched->n;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const Task tk = a.sched->t[i];
+      if (tk.kind == TK_REWARD) f(tk, S.rewards[tk.a], S.obs[0].terms[0], false);
+      else f(tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0);
+    }
+  }
+  // f(term, k, split, late): split = evaluated as two partial sums; late = finished in stage 2
+  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
 #pragma unroll 1
-    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k);
+    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k, a.sched->split[k] != 0, a.sched->late[k] != 0);
   }
   template <class F> __device__ __forceinline__ static void for_dones(const KArgs& a, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
 #pragma unroll 1
     for (int d = 0; d < S.num_done_terms; ++d) f(S.dones[d], d);
-  }
-  template <class F> __device__ __forceinline__ static void for_obs_groups(const KArgs& a, F&& f) {
-    const RlStepSpec& S = c_spec[a.slot];
-#pragma unroll 1
-    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) f(S.obs[g], g);
   }
   template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
@@ -374,8 +490,8 @@ struct DynPolicy {
 template <class B>
 struct StaticPolicy {
   static constexpr bool kStatic = true;
-  template <int E> __device__ __forceinline__ static constexpr Layout layout(const KArgs&) {
-    constexpr Layout L = make_layout(B::spec, E);
+  __device__ __forceinline__ static constexpr Layout layout(const KArgs&) {
+    constexpr Layout L = make_layout(B::spec);
     return L;
   }
   __device__ __forceinline__ static constexpr Scalars scalars(const KArgs&) {
@@ -386,11 +502,23 @@ struct StaticPolicy {
     constexpr RlCommandCfg c = B::spec.command;
     return c;
   }
-  template <class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
+  template <int NW> struct Sched { static constexpr Schedule value = make_schedule(B::spec, NW); };
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, Sched<NW>::value.n>{}, [&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      constexpr Task tk = Sched<NW>::value.t[i];
+      static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
+      static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
+      constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+      f(tk, rt, ot, corrupt);
+    });
+  }
+  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
     static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
       constexpr int k = decltype(kc)::value;
       static constexpr RlRewardTerm t = B::spec.rewards[k];  // static: runtime-indexed lists read it in place
-      f(t, k);
+      constexpr bool split = Sched<NW>::value.split[k] != 0, late = Sched<NW>::value.late[k] != 0;
+      f(t, k, split, late);
     });
   }
   template <class F> __device__ __forceinline__ static void for_dones(const KArgs&, F&& f) {
@@ -398,13 +526,6 @@ struct StaticPolicy {
       constexpr int d = decltype(dc)::value;
       static constexpr RlDoneTerm t = B::spec.dones[d];
       f(t, d);
-    });
-  }
-  template <class F> __device__ __forceinline__ static void for_obs_groups(const KArgs&, F&& f) {
-    static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
-      constexpr int g = decltype(gc)::value;
-      static constexpr RlObsGroup G = B::spec.obs[g];
-      f(G, g);
     });
   }
   template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
@@ -415,7 +536,7 @@ struct StaticPolicy {
 
 
 // ---------------------------------------------------------------------------------------------------
-// Per-env context shared by all terms
+// Per-env context shared by all terms (thread-per-env: lane e = env e of the tile)
 // ---------------------------------------------------------------------------------------------------
 struct EnvCtx {
   float qw;
@@ -431,41 +552,36 @@ struct EnvCtx {
   bool terminated;
 };
 
-template <int LPE>
-__device__ __forceinline__ float gsum(float v) {
-#pragma unroll
-  for (int m = LPE / 2; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-template <int LPE>
-__device__ __forceinline__ int gor(int v) {
-#pragma unroll
-  for (int m = LPE / 2; m > 0; m >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-
 #define LOBS(g) ((g) == 0 ? L.obs0 : L.obs1)
 #define LOBSP(g) ((g) == 0 ? L.obs_pitch0 : L.obs_pitch1)
 #define LOBSU(g) ((g) == 0 ? L.obsu0 : L.obsu1)
-#define SMF(off, c) sm[(off) + (c) * E + e]
-#define SMA(off, c) sm[(off) + e * L.A + (c)]
+#define SMF(off, c) sm[(off) + (c) * kE + e]
 #define CJ(k, j) sm[L.cj + (k) * L.J + (j)]
 
-template <int E>
 __device__ __forceinline__ bool first_contact(const float* sm, const Layout& L, const Scalars& S, int e, int b) {
   const float t = SMF(L.ccon, b);
   return (t > 0.f) && (t < (S.step_dt + S.contact_time_abs_tol));
 }
-template <int E>
 __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
   return V3{SMF(off, 3 * b + 0), SMF(off, 3 * b + 1), SMF(off, 3 * b + 2)};
 }
+// max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
+__device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int b) {
+  float m = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* f = h + (t * B + b) * 3;
+    const float n = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+    m = (t == 0) ? n : fmaxf(m, n);
+  }
+  return m;
+}
 
-// One reward term, raw value (no weight, no dt). All lanes of the env group return the same value.
-template <int E, int LPE>
+// One reward term for env e: raw value (no weight, no dt). [lo, hi) restricts body-mask terms to a body-index
+// range (the two halves of a split term add up).
 __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalars& S, const Layout& L, const float* sm,
-                             const int e, const int sub, const EnvCtx& c) {
+                                             const int e, const EnvCtx& c, const int lo, const int hi) {
   const int J = S.num_joints;
+  const float* h = sm + L.hist + e * L.hist_pitch;
   switch (t.type) {
     case RL_REW_IS_TERMINATED: return c.terminated ? 1.f : 0.f;
     case RL_REW_LIN_VEL_Z_L2: return (c.vb.z * c.vb.z) * c.gate;
@@ -484,72 +600,68 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_JOINT_ACC_L2: {
       const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? L.jtau : (t.type == RL_REW_JOINT_VEL_L2 ? L.jvel : L.jacc);
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float v = SMF(off, j); s += v * v; }
-      return gsum<LPE>(s);
+      return s;
     }
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
-      return gsum<LPE>(s);
+      return s;
     }
     case RL_REW_JOINT_POS_LIMITS: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) {
           const float q = SMF(L.jpos, j);
           float o = -fminf(q - CJ(2, j), 0.f);
           o += fmaxf(q - CJ(3, j), 0.f);
           s += o;
         }
-      return gsum<LPE>(s);
+      return s;
     }
     case RL_REW_JOINT_VEL_LIMITS: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
-        if ((t.joint_mask >> j) & 1ull)
-          s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
-      return gsum<LPE>(s);
+      for (int j = 0; j < J; ++j)
+        if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
+      return s;
     }
     case RL_REW_JOINT_POWER: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jvel, j) * SMF(L.jtau, j));
-      return gsum<LPE>(s);
+      return s;
     }
     case RL_REW_STAND_STILL: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
-      s = gsum<LPE>(s);
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
       return s * c.gate;
     }
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
-      for (int j = sub; j < J; j += LPE)
+      for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - CJ(0, j); s += d * d; }
-      const float running = sqrtf(gsum<LPE>(s));
+      const float running = sqrtf(s);
       const bool moving = (c.cmd_norm > t.p[2]) || (c.vxy_norm > t.p[1]);
       return (moving ? running : t.p[0] * running) * c.gate;
     }
     case RL_REW_JOINT_MIRROR: {
       float s = 0.f;
-      for (int i = sub; i < t.n_idx; i += LPE) {
+      for (int i = 0; i < t.n_idx; ++i) {
         const float d = SMF(L.jpos, t.idx_a[i]) - SMF(L.jpos, t.idx_b[i]);
         s += d * d;
       }
-      s = gsum<LPE>(s);
       return (s * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
-      for (int i = sub; i < t.n_idx; i += LPE) {
-        const float d = fabsf(SMA(L.act, t.idx_a[i])) - fabsf(SMA(L.act, t.idx_b[i]));
+      for (int i = 0; i < t.n_idx; ++i) {
+        const float d = fabsf(SMF(L.act, t.idx_a[i])) - fabsf(SMF(L.act, t.idx_b[i]));
         s += d * d;
       }
-      s = gsum<LPE>(s);
       return (s * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_SYNC: {
@@ -558,31 +670,30 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
         const int start = t.idx_b[g], n = t.idx_c[g];
         if (n < 2) continue;
         float m = 0.f;
-        for (int i = 0; i < n; ++i) m += fabsf(SMA(L.act, t.idx_a[start + i]));
+        for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, t.idx_a[start + i]));
         m = m / (float)n;
         float v = 0.f;
-        for (int i = 0; i < n; ++i) { const float d = fabsf(SMA(L.act, t.idx_a[start + i])) - m; v += d * d; }
+        for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, t.idx_a[start + i])) - m; v += d * d; }
         r += v / (float)n;
       }
       return (r * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_RATE_L2: {
-      const int A = S.n_actions;
       float s = 0.f;
-      for (int a = sub; a < A; a += LPE) { const float d = SMA(L.act, a) - SMA(L.pact, a); s += d * d; }
-      return gsum<LPE>(s);
+      for (int a = 0; a < S.n_actions; ++a) { const float d = SMF(L.act, a) - SMF(L.pact, a); s += d * d; }
+      return s;
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
-      for (int b = sub; b < S.num_hist_bodies; b += LPE)
-        if (((t.body_mask >> b) & 1ull) && (SMF(L.bmax, b) > t.p[0])) s += 1.f;
-      return gsum<LPE>(s) * c.gate;
+      for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
+        if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
+      return s * c.gate;   // gate distributes over the two halves of a split term
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
-      for (int b = sub; b < S.num_hist_bodies; b += LPE)
-        if ((t.body_mask >> b) & 1ull) s += fmaxf(SMF(L.bmax, b) - t.p[0], 0.f);
-      return gsum<LPE>(s);
+      for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
+        if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
+      return s;
     }
     case RL_REW_TRACK_LIN_VEL_XY_EXP: {
       const float dx = c.c0 - c.vb.x, dy = c.c1 - c.vb.y;
@@ -610,7 +721,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
-        s += (SMF(L.lair, b) - t.p[0]) * (first_contact<E>(sm, L, S, e, b) ? 1.f : 0.f);
+        s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
       }
       s *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return s * c.gate;
@@ -666,21 +777,20 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact<E>(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return r * c.gate;
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact<E>(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
       return r * c.gate;
     }
     case RL_REW_FEET_STUMBLE: {
-      bool any = false;
-      const float* h = sm + L.hist + e * L.hist_pitch;  // t = 0 is the newest sample = net_forces_w
+      bool any = false;   // t = 0 is the newest history sample = net_forces_w
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_c[i];
         const float fx = h[3 * b + 0], fy = h[3 * b + 1], fz = h[3 * b + 2];
@@ -691,18 +801,18 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 vw = body_vec<E>(sm, L.bvel, e, t.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float lat = sqrtf(vb.x * vb.x + vb.y * vb.y);
-        s += lat * ((SMF(L.bmax, t.idx_c[i]) > 1.0f) ? 1.f : 0.f);
+        s += lat * ((hist_max_norm(h, S.hist_len, S.num_hist_bodies, t.idx_c[i]) > 1.0f) ? 1.f : 0.f);
       }
       return s * c.gate;
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 p = body_vec<E>(sm, L.bpos, e, t.idx_b[i]);
-        const V3 v = body_vec<E>(sm, L.bvel, e, t.idx_b[i]);
+        const V3 p = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 v = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const float d = p.z - t.p[0];
         s += (d * d) * rl_tanhf(t.p[1] * sqrtf(v.x * v.x + v.y * v.y));
       }
@@ -712,8 +822,8 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec<E>(sm, L.bpos, e, t.idx_b[i]);
-        const V3 vw = body_vec<E>(sm, L.bvel, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float d = pb.z - t.p[0];
@@ -725,7 +835,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_DISTANCE_Y_EXP: {
       float s = 0.f;
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec<E>(sm, L.bpos, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float want = (t.p[0] / 2.f) * ((i % 2 == 0) ? 1.f : -1.f);
         const float d = want - pb.y;
@@ -736,7 +846,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_DISTANCE_XY_EXP: {
       float s = 0.f;
       for (int i = 0; i < 4; ++i) {
-        const V3 pw = body_vec<E>(sm, L.bpos, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float wx = (i < 2) ? (t.p[1] / 2.f) : (-t.p[1] / 2.f);
         const float wy = (i % 2 == 0) ? (t.p[0] / 2.f) : (-t.p[0] / 2.f);
@@ -761,7 +871,6 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
   }
 }
 
-template <int E>
 __device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int e) {
   EnvCtx c;
   c.qw = SMF(L.quat, 0);
@@ -780,25 +889,8 @@ __device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int
   return c;
 }
 
-// max over the history of |F_b| for the lane group's bodies -> smem scratch (shared by 5 terms)
-template <int E, int LPE>
-__device__ __forceinline__ void body_max_norm(float* sm, const Layout& L, const Scalars& S, int e, int sub) {
-  const int B = S.num_hist_bodies, T = S.hist_len;
-  const float* h = sm + L.hist + e * L.hist_pitch;
-  for (int b = sub; b < B; b += LPE) {
-    float m = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float* f = h + (t * B + b) * 3;
-      const float n = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
-      m = (t == 0) ? n : fmaxf(m, n);
-    }
-    SMF(L.bmax, b) = m;
-  }
-}
-
 // CommandTerm.compute [IL] + UniformThresholdVelocityCommand (V/mdp/commands.py:43-85; the "pits" branch
 // is identically off for the in-scope terrains, V/mdp/utils.py:27-28). Writes back into the smem record.
-template <int E>
 __device__ __forceinline__ void command_update(float* sm, const Layout& L, const Scalars& S, const RlCommandCfg& cc,
                                                const KArgs& a, const RandState rs, int e, long long env,
                                                const EnvCtx& c, bool write) {
@@ -850,84 +942,74 @@ __device__ __forceinline__ void command_update(float* sm, const Layout& L, const
   }
 }
 
-// One observation group for one env: ObservationManager.compute_group [IL] (clone, +noise, clip, scale, cat)
-template <int E, int LPE, bool STATIC>
-__device__ __forceinline__ void obs_group(float* sm, const Layout& L, const Scalars& S, const RlObsGroup& G,
-                                          const KArgs& a, const RandState rs, int g, int e, int sub, long long env,
-                                          const EnvCtx& c) {
+// Columns [lo, hi) of one observation term for env e: ObservationManager.compute_group [IL]
+// (clone -> +noise -> clip -> scale), written into the group's shared-memory row.
+__device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scalars& S, const RlObsTerm& t,
+                                         const bool corrupt, const KArgs& a, const RandState rs, const int g,
+                                         const int ti, const int col0, const int lo, const int hi, const int e,
+                                         const long long env, const EnvCtx& c) {
   float* row = sm + LOBS(g) + e * LOBSP(g);
   const float* urow = sm + LOBSU(g) + e * LOBSP(g);
   const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
-  int col0 = 0;
-  constexpr int kUnroll = STATIC ? RL_MAX_OBS_TERMS : 1;  // baked spec: every term's type / dim / noise folds
-#pragma unroll kUnroll
-  for (int ti = 0; ti < RL_MAX_OBS_TERMS; ++ti) {
-    if (ti >= G.n_terms) break;
-    const RlObsTerm& t = G.terms[ti];
-    const bool noisy = t.has_noise && G.enable_corruption;
-    for (int qd = sub; qd * 4 < t.dim; qd += LPE) {
-      float u4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (noisy && !ext_u) {
-        const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
-        u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
-      }
-#pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        const int col = qd * 4 + r4;
-        if (col >= t.dim) break;
-        float v;
-        switch (t.type) {
-          case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
-          case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
-          case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
-          case RL_OBS_GENERATED_COMMANDS: v = SMF(L.cmd, col); break;
-          case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]); break;
-          case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
-            v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]);
-            if ((t.zero_mask >> col) & 1ull) v = 0.f;
-            break;
-          case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - CJ(1, t.ids[col]); break;
-          case RL_OBS_LAST_ACTION: v = SMA(L.act, col); break;
-          case RL_OBS_HEIGHT_SCAN:
-            v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0];
-            break;
-          case RL_OBS_PHASE: {
-            const float ph = ((float)__float_as_int(SMF(L.eplen, 0)) * S.step_dt) / t.p[0];
-            v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
-            break;
-          }
-          default: v = 0.f;
-        }
-        if (noisy) {
-          const float u = ext_u ? urow[col0 + col] : u4[r4];
-          v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
-        }
-        if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
-        if (t.has_scale) v = v * t.scale;
-        row[col0 + col] = v;
-      }
+  const bool noisy = t.has_noise && corrupt;
+  for (int qd = lo / 4; qd * 4 < hi; ++qd) {
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noisy && !ext_u) {
+      const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
+      u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
     }
-    col0 += t.dim;
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+      const int col = qd * 4 + r4;
+      if (col >= hi) break;
+      float v;
+      switch (t.type) {
+        case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
+        case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
+        case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
+        case RL_OBS_GENERATED_COMMANDS: v = SMF(L.cmd, col); break;
+        case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]); break;
+        case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
+          v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]);
+          if ((t.zero_mask >> col) & 1ull) v = 0.f;
+          break;
+        case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - CJ(1, t.ids[col]); break;
+        case RL_OBS_LAST_ACTION: v = SMF(L.act, col); break;
+        case RL_OBS_HEIGHT_SCAN: v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0]; break;
+        case RL_OBS_PHASE: {
+          const float ph = ((float)__float_as_int(SMF(L.eplen, 0)) * S.step_dt) / t.p[0];
+          v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
+          break;
+        }
+        default: v = 0.f;
+      }
+      if (noisy) {
+        const float u = ext_u ? urow[col0 + col] : u4[r4];
+        v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
+      }
+      if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
+      if (t.has_scale) v = v * t.scale;
+      row[col0 + col] = v;
+    }
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------------
-// Tile movers (one code copy each, `#pragma unroll 1` outer loops keep the kernel small: the first cut of this
-// kernel inlined a strided loop per field and ran at IPC 0.1 stalled on instruction fetch - see profiles/)
+// Tile movers (one code copy each)
 // ---------------------------------------------------------------------------------------------------
-template <int E>
 __device__ __forceinline__ void load_rows_async(float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
                                                 bool full, int tid, int nthreads) {
-  constexpr int NV = E / 4;
+  constexpr int NV = kE / 4;
   const int total = a.n_in_rows * NV;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = tid; i < total; i += nthreads) {
     const uint32_t meta = __ldg(a.in_rows + i / NV);
     const int f = meta & 63u;
     if (!((a.in_mask >> f) & 1u)) continue;
     const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
     const FieldD fd = a.in[f];
-    float* dst = sm + w * E + 4 * v;
+    float* dst = sm + w * kE + 4 * v;
     if (full && ((a.in_vec4 >> f) & 1u)) {
       cp_async16(dst, static_cast<const float*>(fd.ptr) + (size_t)c * fd.cs + env0 + 4 * v);
     } else {
@@ -943,19 +1025,18 @@ __device__ __forceinline__ void load_rows_async(float* sm, const KArgs& a, int e
   }
 }
 
-template <int E>
 __device__ __forceinline__ void store_rows(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
                                            bool full, int tid, int nthreads) {
-  constexpr int NV = E / 4;
+  constexpr int NV = kE / 4;
   const int total = a.n_out_rows * NV;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = tid; i < total; i += nthreads) {
     const uint32_t meta = __ldg(a.out_rows + i / NV);
     const int f = meta & 63u;
     if (!((a.out_mask >> f) & 1u)) continue;
     const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
     const FieldD fd = a.outf[f];
-    const float* src = sm + w * E + 4 * v;
+    const float* src = sm + w * kE + 4 * v;
     float* base = static_cast<float*>(const_cast<void*>(fd.ptr));
     if (full && ((a.out_vec4 >> f) & 1u)) {
       *reinterpret_cast<float4*>(base + (size_t)c * fd.cs + env0 + 4 * v) = *reinterpret_cast<const float4*>(src);
@@ -972,37 +1053,39 @@ __device__ __forceinline__ void store_rows(const float* sm, const KArgs& a, int 
   }
 }
 
-// AoS span [E][ncomp] <-> global rows; element-wise fallback when a span is not one aligned contiguous block
-__device__ __noinline__ void span_load_elems(float* dst, int pitch, FieldD fd, int ncomp, int E, int env0, int nvalid,
+// AoS span [kE][pitch] <-> global rows, element-wise (used when a span is not one aligned contiguous block or the
+// shared-memory pitch is padded)
+__device__ __noinline__ void span_load_elems(float* dst, int pitch, FieldD fd, int ncomp, int env0, int nvalid,
                                              const int32_t* ids, int tid, int nthreads) {
-  const int total = ncomp * E;
+  const int total = ncomp * kE;
   const bool env_major = (fd.es == 1);
   for (int i = tid; i < total; i += nthreads) {
     int c, e;
-    if (env_major) { e = i % E; c = i / E; } else { c = i % ncomp; e = i / ncomp; }
+    if (env_major) { e = i % kE; c = i / kE; } else { c = i % ncomp; e = i / ncomp; }
     if (e < nvalid) {
       const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
       cp_async4(dst + e * pitch + c, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
     }
   }
 }
-__device__ __noinline__ void span_store_elems(const float* src, int pitch, float* ptr, long long es, long long cs, int ncomp,
-                                              int E, int env0, int nvalid, const int32_t* ids, int tid, int nthreads) {
-  const int total = ncomp * E;
+__device__ __noinline__ void span_store_elems(const float* src, int pitch, float* ptr, long long es, int ncomp,
+                                              int env0, int nvalid, const int32_t* ids, int tid, int nthreads) {
+  const int total = ncomp * kE;
   for (int i = tid; i < total; i += nthreads) {
     const int c = i % ncomp, e = i / ncomp;
     if (e < nvalid) {
       const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      ptr[env * es + (long long)c * cs] = src[e * pitch + c];
+      ptr[env * es + c] = src[e * pitch + c];
     }
   }
 }
-__device__ __forceinline__ bool span_bulk_ok(const FieldD& fd, int ncomp, int env0, int E) {
-  if (fd.ptr == nullptr || ncomp <= 0 || fd.cs != 1 || fd.es != ncomp) return false;
+// one aligned contiguous [kE][ncomp] block in global memory AND an unpadded shared-memory pitch
+__device__ __forceinline__ bool span_bulk_ok(const FieldD& fd, int ncomp, int pitch, int env0) {
+  if (fd.ptr == nullptr || ncomp <= 0 || pitch != ncomp || fd.cs != 1 || fd.es != ncomp) return false;
   const uintptr_t p = reinterpret_cast<uintptr_t>(fd.ptr) + (uintptr_t)env0 * (uintptr_t)ncomp * 4u;
-  return ((p & 15u) == 0) && ((((long long)E * ncomp * 4) & 15) == 0);
+  return ((p & 15u) == 0) && ((((long long)kE * ncomp * 4) & 15) == 0);
 }
-__device__ __forceinline__ void load_u8(float* sm, int off, const FieldD& fd, int E, int env0, int nvalid,
+__device__ __forceinline__ void load_u8(float* sm, int off, const FieldD& fd, int env0, int nvalid,
                                         const int32_t* ids, int tid) {
   if (fd.ptr != nullptr && tid < nvalid) {
     const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
@@ -1018,17 +1101,24 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The fused step kernel. MODE 0 = step, MODE 1 = single-term evaluation.
+// The fused step kernel: kE = 32 envs per CTA, NW warps. MODE 0 = step, MODE 1 = single-term evaluation.
+//   load   : everything asynchronous (TMA bulk copies + cp.async), one join
+//   stage 1: every warp runs its share of the schedule, thread-per-env (lane e = env e)
+//   stage 2: warp 0 assembles the reward in manager order, warp 1 updates the command and writes the
+//            command-dependent observation columns
+//   store  : bulk stores for the observation rows, one generic loop for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
-template <class P, int E, int LPE, int MODE>
-__global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
+template <class P, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_last;
   const Scalars S = P::scalars(a);
-  const Layout L = P::template layout<E>(a);
-  constexpr int NT = E * LPE;
+  const Layout L = P::layout(a);
+  constexpr int NT = NW * 32;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int e = tid & 31;       // compute phase: this lane's env inside the tile
   const uint32_t ph = a.phases;
   if (a.use_pdl) {
     // launch-latency overlap only: every read below may depend on the predecessor, so wait first
@@ -1036,7 +1126,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
-  const int env0 = blockIdx.x * E;
+  const int env0 = blockIdx.x * kE;
   const int K = S.num_reward_terms;
   const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
   if (do_reset && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
@@ -1046,14 +1136,14 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
     else if (tid < K + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K - RL_MAX_DONE_TERMS] = 0.f; }
   }
   if (env0 >= n_total && !(ph & RL_PHASE_COMPACT)) return;
-  const int nvalid = max(0, min(E, n_total - env0));
+  const int nvalid = max(0, min(kE, n_total - env0));
   const int32_t* ids = a.has_ids ? a.env_ids : nullptr;
   const int J = S.num_joints, A = S.n_actions;
   const int R = S.num_rays;
   const int HW = S.hist_len * S.num_hist_bodies * 3;
   const bool need_hist = (MODE == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
   const bool need_rays = (MODE == 0) && (ph & RL_PHASE_OBS) && R > 0 && a.rays.ptr != nullptr;
-  const bool full = (nvalid == E) && (ids == nullptr);
+  const bool full = (nvalid == kE) && (ids == nullptr);
   RandState rs;
   rs.seed = a.rnd.seed;
   rs.step = a.rnd.step + (a.rnd.step_counter ? *a.rnd.step_counter : 0ull);
@@ -1061,10 +1151,8 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
 
   // ---- load phase: everything is asynchronous, nothing below waits until the single join point ---------
   if (nvalid > 0) {
-    const bool act_bulk = full && span_bulk_ok(a.action, A, env0, E);
-    const bool pact_bulk = need_hist && full && span_bulk_ok(a.prev_action, A, env0, E);
-    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, env0, E);
-    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, env0, E);
+    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, L.hist_pitch, env0);
+    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, L.rays_pitch, env0);
     bool obsu_bulk[RL_NUM_OBS_GROUPS];
     FieldD obsu[RL_NUM_OBS_GROUPS];
 #pragma unroll
@@ -1072,50 +1160,42 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       const int D = P::obs_dim(a, g);
       const bool want = (MODE == 0) && (ph & RL_PHASE_OBS) && a.rnd.obs_uniforms[g] != nullptr && D > 0;
       obsu[g] = FieldD{want ? a.rnd.obs_uniforms[g] : nullptr, D, 1};
-      obsu_bulk[g] = want && full && span_bulk_ok(obsu[g], D, env0, E);
+      obsu_bulk[g] = want && full && span_bulk_ok(obsu[g], D, LOBSP(g), env0);
     }
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       uint32_t bytes = 0;
-      if (act_bulk) bytes += (uint32_t)(E * A * 4);
-      if (pact_bulk) bytes += (uint32_t)(E * A * 4);
-      if (hist_bulk) bytes += (uint32_t)(E * HW * 4);
-      if (rays_bulk) bytes += (uint32_t)(E * R * 4);
+      if (hist_bulk) bytes += (uint32_t)(kE * HW * 4);
+      if (rays_bulk) bytes += (uint32_t)(kE * R * 4);
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (obsu_bulk[g]) bytes += (uint32_t)(E * P::obs_dim(a, g) * 4);
+        if (obsu_bulk[g]) bytes += (uint32_t)(kE * P::obs_dim(a, g) * 4);
       mbar_expect_tx(&s_bar, bytes);
-      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(E * HW * 4), &s_bar);
-      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(E * R * 4), &s_bar);
-      if (act_bulk) bulk_g2s(sm + L.act, static_cast<const float*>(a.action.ptr) + (size_t)env0 * A, (uint32_t)(E * A * 4), &s_bar);
-      if (pact_bulk) bulk_g2s(sm + L.pact, static_cast<const float*>(a.prev_action.ptr) + (size_t)env0 * A, (uint32_t)(E * A * 4), &s_bar);
+      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(kE * HW * 4), &s_bar);
+      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(kE * R * 4), &s_bar);
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
         if (obsu_bulk[g])
           bulk_g2s(sm + LOBSU(g), static_cast<const float*>(obsu[g].ptr) + (size_t)env0 * P::obs_dim(a, g),
-                   (uint32_t)(E * P::obs_dim(a, g) * 4), &s_bar);
+                   (uint32_t)(kE * P::obs_dim(a, g) * 4), &s_bar);
     }
-    load_rows_async<E>(sm, a, env0, nvalid, ids, full, tid, NT);
-    if (!act_bulk && a.action.ptr) span_load_elems(sm + L.act, A, a.action, A, E, env0, nvalid, ids, tid, NT);
-    if (need_hist) {
-      if (!pact_bulk && a.prev_action.ptr) span_load_elems(sm + L.pact, A, a.prev_action, A, E, env0, nvalid, ids, tid, NT);
-      if (!hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, E, env0, nvalid, ids, tid, NT);
-    }
-    if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, E, env0, nvalid, ids, tid, NT);
+    load_rows_async(sm, a, env0, nvalid, ids, full, tid, NT);
+    if (need_hist && !hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, env0, nvalid, ids, tid, NT);
+    if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, env0, nvalid, ids, tid, NT);
 #pragma unroll
     for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
       if (obsu[g].ptr && !obsu_bulk[g])
-        span_load_elems(sm + LOBSU(g), LOBSP(g), obsu[g], P::obs_dim(a, g), E, env0, nvalid, ids, tid, NT);
+        span_load_elems(sm + LOBSU(g), LOBSP(g), obsu[g], P::obs_dim(a, g), env0, nvalid, ids, tid, NT);
     if (MODE == 0 && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET))) {
-      load_u8(sm, L.ishead, a.is_heading, E, env0, nvalid, ids, tid);
-      load_u8(sm, L.isstand, a.is_standing, E, env0, nvalid, ids, tid);
+      load_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
+      load_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
     }
     if (do_reset && a.out.done_bits != nullptr) {
       FieldD f{a.out.done_bits, 1, 0};
-      load_u8(sm, L.flags, f, E, env0, nvalid, ids, tid);
+      load_u8(sm, L.flags, f, env0, nvalid, ids, tid);
     }
-    // per-joint constants: constant bank -> shared (lane-varying joint indices would serialise LDCs)
+    // per-joint constants: constant bank -> shared
     for (int i = tid; i < J; i += NT)
       P::for_joint_consts(a, i, [&](float q0, float qd0, float lo, float hi, float vl) {
         sm[L.cj + 0 * J + i] = q0; sm[L.cj + 1 * J + i] = qd0; sm[L.cj + 2 * J + i] = lo;
@@ -1126,18 +1206,16 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
     mbar_wait(&s_bar, 0);       // bulk copies landed
   }
 
-  // ---- compute phase ----------------------------------------------------------------------------
-  const int e = tid / LPE;
-  const int sub = tid % LPE;
   const bool valid = e < nvalid;
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
   if (nvalid > 0) {
+    // ---- manager reset of the tile's envs (env_ids launches) ---------------------------------------------
     if (do_reset) {
-      // -- logging partials of this CTA (summed in CTA order by the last CTA -> deterministic) --
+      // logging partials of this CTA (summed in CTA order by the last CTA -> deterministic)
       if (tid < K + RL_MAX_DONE_TERMS + 2) {
         float acc = 0.f;
         for (int el = 0; el < nvalid; ++el) {
-          if (tid < K) acc += sm[L.sums + tid * E + el];
+          if (tid < K) acc += sm[L.sums + tid * kE + el];
           else if (tid < K + RL_MAX_DONE_TERMS)
             acc += (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + el]) >> (tid - K)) & 1) : 0.f;
           else acc += sm[(tid == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + el];
@@ -1145,10 +1223,10 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = acc;
       }
       __syncthreads();
-      // -- manager resets: RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0 --
-      for (int i = tid; i < E * K; i += NT) sm[L.sums + i] = 0.f;
-      for (int i = tid; i < E * A; i += NT) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
-      if (tid < E) {
+      // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
+      for (int i = tid; i < kE * K; i += NT) sm[L.sums + i] = 0.f;
+      for (int i = tid; i < kE * A; i += NT) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
+      if (tid < kE) {
         const int el = tid;
         sm[L.mxy + el] = 0.f; sm[L.myaw + el] = 0.f; sm[L.eplen + el] = __int_as_float(0);
         const auto& cc = P::command(a);
@@ -1156,7 +1234,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         float u[RL_NUM_CMD_UNIFORMS];
         if (a.rnd.cmd_uniforms != nullptr) {
 #pragma unroll
-          for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * E + el];
+          for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * kE + el];
         } else {
           const uint4 r0 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 1);
           u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
@@ -1167,7 +1245,7 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
         const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
         c0 *= keep; c1 *= keep;
-        sm[L.cmd + 0 * E + el] = c0; sm[L.cmd + 1 * E + el] = c1; sm[L.cmd + 2 * E + el] = c2;
+        sm[L.cmd + 0 * kE + el] = c0; sm[L.cmd + 1 * kE + el] = c1; sm[L.cmd + 2 * kE + el] = c2;
         sm[L.tleft + el] = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
         if (cc.heading_command) {
           sm[L.head + el] = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
@@ -1177,20 +1255,21 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
       }
       __syncthreads();
     }
-    EnvCtx c = make_ctx<E>(sm, L, e);
-    if (need_hist) {
-      body_max_norm<E, LPE>(sm, L, S, e, sub);
-      __syncwarp();
-    }
+
+    // ---- stage 1: thread-per-env, warps run different tasks ------------------------------------------------
+    EnvCtx c = make_ctx(sm, L, e);
     if (MODE == 1) {
-      if (a.ext_terminated != nullptr && valid) c.terminated = a.ext_terminated[env] != 0;
-      const float v = reward_term<E, LPE>(*a.adhoc, S, L, sm, e, sub, c);
-      if (valid && sub == 0) a.term_out[env] = v;
+      if (warp == 0) {
+        if (a.ext_terminated != nullptr && valid) c.terminated = a.ext_terminated[env] != 0;
+        const float v = reward_term(*a.adhoc, S, L, sm, e, c, 0, 64);
+        if (valid) a.term_out[env] = v;
+      }
       return;
     }
-    uint32_t bits = 0, term = 0, trunc = 0;
-    if (ph & RL_PHASE_DONES) {
+    if ((ph & RL_PHASE_DONES) && warp == 0) {
+      uint32_t bits = 0, term = 0, trunc = 0;
       const int eplen = __float_as_int(SMF(L.eplen, 0)) + 1;
+      const float* h = sm + L.hist + e * L.hist_pitch;
       P::for_dones(a, [&](const RlDoneTerm& t, int d) {
         int fired = 0;
         if (t.type == RL_DONE_TIME_OUT) {
@@ -1198,48 +1277,64 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
           fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
         } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
-          int hit = 0;
-          for (int b = sub; b < S.num_hist_bodies; b += LPE)
-            if (((t.body_mask >> b) & 1ull) && (SMF(L.bmax, b) > t.p[0])) hit = 1;
-          fired = gor<LPE>(hit);
+          for (int b = 0; b < S.num_hist_bodies; ++b)
+            if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
         }
         if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
       });
-      c.terminated = term != 0;
-      __syncwarp();
-      if (sub == 0) {
-        SMF(L.eplen, 0) = __int_as_float(eplen);
-        SMF(L.flags, 0) = __int_as_float((int)(bits | (term << 8) | (trunc << 9)));
-      }
+      SMF(L.eplen, 0) = __int_as_float(eplen);
+      SMF(L.flags, 0) = __int_as_float((int)(bits | (term << 8) | (trunc << 9)));
     }
-    const uint32_t done_any = term | trunc;
-    if (ph & RL_PHASE_REWARDS) {
+    if (ph & (RL_PHASE_REWARDS | RL_PHASE_OBS)) {
+      P::template for_tasks<NW>(a, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
+        if (tk.owner != warp) return;
+        if (tk.kind == TK_REWARD) {
+          if (!(ph & RL_PHASE_REWARDS)) return;
+          const float raw = reward_term(rt, S, L, sm, e, c, tk.lo, tk.hi);
+          const int k = tk.a;
+          // RewardManager.compute [IL]: value = func * weight * dt; late (split) terms keep the raw partial
+          SMF(L.termv, 2 * k + tk.b) = raw;
+        } else {
+          if (!(ph & RL_PHASE_OBS) || a.out.obs[tk.a] == nullptr) return;
+          obs_task(sm, L, S, ot, corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c);
+        }
+      });
+    }
+    __syncthreads();
+
+    // ---- stage 2 -----------------------------------------------------------------------------------------
+    const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
+    const uint32_t done_any = (fl >> 8) & 3;
+    if ((ph & RL_PHASE_REWARDS) && warp == 0) {
+      c.terminated = ((fl >> 8) & 1) != 0;
       float total = 0.f;
-      P::for_rewards(a, [&](const RlRewardTerm& t, int k) {
+      P::template for_rewards<NW>(a, [&](const RlRewardTerm& t, int k, bool split, bool late) {
         float val = 0.f, per_dt = 0.f;
         if (t.weight != 0.f) {
-          const float raw = reward_term<E, LPE>(t, S, L, sm, e, sub, c);
-          val = (raw * t.weight) * S.step_dt;  // RewardManager.compute [IL]: func * weight * dt
+          float raw;
+          if (t.type == RL_REW_IS_TERMINATED) raw = c.terminated ? 1.f : 0.f;
+          else raw = split ? (SMF(L.termv, 2 * k) + SMF(L.termv, 2 * k + 1)) : SMF(L.termv, 2 * k);
+          (void)late;
+          val = (raw * t.weight) * S.step_dt;
           per_dt = val / S.step_dt;
           total += val;
         }
-        if (sub == (k % LPE)) {
-          SMF(L.sums, k) = SMF(L.sums, k) + val;
-          SMF(L.stepr, k) = per_dt;
-        }
+        SMF(L.sums, k) = SMF(L.sums, k) + val;
+        SMF(L.stepr, k) = per_dt;
       });
-      if (sub == 0) SMF(L.rew, 0) = total;
+      SMF(L.rew, 0) = total;
     }
-    __syncwarp();
-    if (ph & RL_PHASE_COMMAND) {
-      const bool skip = (ph & RL_PHASE_SKIP_DONE_ENVS) && done_any;
-      command_update<E>(sm, L, S, P::command(a), a, rs, e, env, c, (sub == 0) && !skip);
-      __syncwarp();
-    }
-    if (ph & RL_PHASE_OBS) {
-      P::for_obs_groups(a, [&](const RlObsGroup& G, int g) {
-        if (a.out.obs[g] != nullptr && G.dim > 0) obs_group<E, LPE, P::kStatic>(sm, L, S, G, a, rs, g, e, sub, env, c);
-      });
+    if ((ph & (RL_PHASE_COMMAND | RL_PHASE_OBS)) && warp == (NW > 1 ? 1 : 0)) {
+      if (ph & RL_PHASE_COMMAND) {
+        const bool skip = (ph & RL_PHASE_SKIP_DONE_ENVS) && done_any;
+        command_update(sm, L, S, P::command(a), a, rs, e, env, c, !skip);
+      }
+      if (ph & RL_PHASE_OBS) {
+        P::template for_tasks<NW>(a, [&](const Task& tk, const RlRewardTerm&, const RlObsTerm& ot, const bool corrupt) {
+          if (tk.kind != TK_OBS || tk.owner != kStage2Owner || a.out.obs[tk.a] == nullptr) return;
+          obs_task(sm, L, S, ot, corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c);
+        });
+      }
     }
     __syncthreads();
 
@@ -1252,40 +1347,35 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
         const int D = P::obs_dim(a, g);
         if (a.out.obs[g] == nullptr || D <= 0) continue;
         const FieldD od{a.out.obs[g], (int)a.out.obs_pitch[g], 1};
-        if (full && span_bulk_ok(od, D, env0, E)) {
-          if (tid == 0) bulk_s2g(a.out.obs[g] + (size_t)env0 * D, sm + LOBS(g), (uint32_t)(E * D * 4));
+        if (full && span_bulk_ok(od, D, LOBSP(g), env0)) {
+          if (tid == 0) bulk_s2g(a.out.obs[g] + (size_t)env0 * D, sm + LOBS(g), (uint32_t)(kE * D * 4));
         } else {
-          span_store_elems(sm + LOBS(g), LOBSP(g), a.out.obs[g], a.out.obs_pitch[g], 1, D, E, env0, nvalid, ids, tid, NT);
+          span_store_elems(sm + LOBS(g), LOBSP(g), a.out.obs[g], a.out.obs_pitch[g], D, env0, nvalid, ids, tid, NT);
         }
       }
       if (tid == 0) bulk_commit();
     }
-    store_rows<E>(sm, a, env0, nvalid, ids, full, tid, NT);
+    store_rows(sm, a, env0, nvalid, ids, full, tid, NT);
     if (ph & RL_PHASE_DONES) {
       if (tid < nvalid) {
-        const int fl = __float_as_int(sm[L.flags + tid]);
+        const int f2 = __float_as_int(sm[L.flags + tid]);
         const long long ev = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
-        if (a.out.done_bits) a.out.done_bits[ev] = (uint8_t)(fl & 0xff);
-        if (a.out.terminated) a.out.terminated[ev] = (uint8_t)((fl >> 8) & 1);
-        if (a.out.truncated) a.out.truncated[ev] = (uint8_t)((fl >> 9) & 1);
+        if (a.out.done_bits) a.out.done_bits[ev] = (uint8_t)(f2 & 0xff);
+        if (a.out.terminated) a.out.terminated[ev] = (uint8_t)((f2 >> 8) & 1);
+        if (a.out.truncated) a.out.truncated[ev] = (uint8_t)((f2 >> 9) & 1);
       }
     }
     if ((ph & RL_PHASE_COMMAND) || do_reset) {
       store_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
       store_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
     }
-    if (do_reset) {
-      span_store_elems(sm + L.act, A, static_cast<float*>(const_cast<void*>(a.action.ptr)), a.action.es, a.action.cs, A, E, env0, nvalid, ids, tid, NT);
-      span_store_elems(sm + L.pact, A, static_cast<float*>(const_cast<void*>(a.prev_action.ptr)), a.prev_action.es, a.prev_action.cs, A, E, env0, nvalid, ids, tid, NT);
-    }
   }
 
   // ---- ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]) -----------
   if ((ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids) {
-    // per-CTA bit mask of done envs (E <= 32)
-    if (tid < E) {
-      const int fl = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
-      const unsigned m = __ballot_sync(E == 32 ? 0xffffffffu : ((1u << E) - 1u), (fl >> 8) & 3);
+    if (tid < kE) {  // per-CTA bit mask of done envs
+      const int f2 = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, (f2 >> 8) & 3);
       if (tid == 0) a.cta_mask[blockIdx.x] = m;
     }
     __syncthreads();
@@ -1322,14 +1412,14 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
           while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            a.out.reset_ids[pos++] = g * E + b;
+            a.out.reset_ids[pos++] = g * kE + b;
           }
         }
       return;
     }
   }
   if (do_reset && nvalid > 0) {
-    const int n_cta = (n_total + E - 1) / E;
+    const int n_cta = (n_total + kE - 1) / kE;
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -1352,7 +1442,6 @@ __global__ void __launch_bounds__(E* LPE) mdp_step_kernel(const KArgs a) {
   }
   if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // process_action: ActionManager.process_action + JointAction.process_actions [IL]
@@ -1393,8 +1482,9 @@ struct RlCtx {
   int device;
   int slot;
   RlStepSpec spec;
-  int E, LPE;
+  int NW;                 // warps per CTA (kE = 32 envs per CTA is fixed)
   Layout L;
+  Schedule* sched_dev;
   unsigned int* ticket;
   uint32_t* cta_mask;
   float* log_partials;
@@ -1414,7 +1504,7 @@ namespace {
 // static row tables (field, component, record word); E-independent
 int build_row_tables(RlCtx* ctx) {
   const RlStepSpec& s = ctx->spec;
-  const Layout L = make_layout(s, 8);
+  const Layout L = make_layout(s);
   uint32_t rows[2048];
   int n = 0, word = 0;
   for (int f = 0; f < IF_COUNT; ++f) {  // same running word count as make_layout
@@ -1426,8 +1516,9 @@ int build_row_tables(RlCtx* ctx) {
   CUDA_TRY(cudaMemcpy(ctx->in_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
   n = 0;
   const int K = s.num_reward_terms;
-  const int ow[OF_COUNT] = {L.w_rew, L.w_eplen, L.w_sums, L.w_stepr, L.w_cmd, L.w_head, L.w_tleft, L.w_mxy, L.w_myaw};
-  const int oc[OF_COUNT] = {1, 1, K, K, 3, 1, 1, 1, 1};
+  const int A = s.action.n_actions;
+  const int ow[OF_COUNT] = {L.w_rew, L.w_eplen, L.w_sums, L.w_stepr, L.w_cmd, L.w_head, L.w_tleft, L.w_mxy, L.w_myaw, L.w_act, L.w_pact};
+  const int oc[OF_COUNT] = {1, 1, K, K, 3, 1, 1, 1, 1, A, A};
   for (int f = 0; f < OF_COUNT; ++f)
     for (int c = 0; c < oc[f]; ++c) rows[n++] = row_pack(f, c, ow[f] + c);
   ctx->n_out_rows = n;
@@ -1451,7 +1542,7 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
   const RlStepSpec& s = ctx->spec;
   memset(&a, 0, sizeof(a));
   a.N = (int)num_envs; a.slot = ctx->slot; a.phases = ph;
-  a.L = ctx->L;
+  a.L = ctx->L; a.sched = ctx->sched_dev;
   a.in_rows = ctx->in_rows_dev; a.n_in_rows = ctx->n_in_rows;
   a.out_rows = ctx->out_rows_dev; a.n_out_rows = ctx->n_out_rows;
   a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
@@ -1473,15 +1564,15 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
   ok &= to_fd(mdp->time_left, &a.in[IF_TLEFT]); ok &= to_fd(mdp->metric_error_vel_xy, &a.in[IF_MXY]);
   ok &= to_fd(mdp->metric_error_vel_yaw, &a.in[IF_MYAW]); ok &= to_fd(mdp->episode_length, &a.in[IF_EPLEN]);
   ok &= to_fd(mdp->episode_sums, &a.in[IF_SUMS]);
-  ok &= to_fd(mdp->action, &a.action); ok &= to_fd(mdp->prev_action, &a.prev_action);
+  ok &= to_fd(mdp->action, &a.in[IF_ACT]); ok &= to_fd(mdp->prev_action, &a.in[IF_PACT]);
   ok &= to_fd(mdp->is_heading_env, &a.is_heading); ok &= to_fd(mdp->is_standing_env, &a.is_standing);
   if (!ok) return fail(RL_EINVAL, "field strides must be non-negative and below 2^31 elements%s", "");
   a.in[IF_CMDU] = FieldD{a.rnd.cmd_uniforms, 1, (int)num_envs};
   const bool need_hist = (mode == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
   uint32_t m = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_JPOS) |
-               (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN);
+               (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN) | (1u << IF_ACT);
   if (need_hist)
-    m |= (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) | (1u << IF_LCON) |
+    m |= (1u << IF_PACT) | (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) | (1u << IF_LCON) |
          (1u << IF_BPOS) | (1u << IF_BVEL);
   if (mode == 0 && (ph & RL_PHASE_REWARDS)) m |= 1u << IF_SUMS;
   if (mode == 0 && (ph & RL_PHASE_COMMAND)) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
@@ -1501,12 +1592,13 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
     a.outf[OF_STEPR] = sr;
     a.outf[OF_CMD] = a.in[IF_CMD]; a.outf[OF_HEAD] = a.in[IF_HEAD]; a.outf[OF_TLEFT] = a.in[IF_TLEFT];
     a.outf[OF_MXY] = a.in[IF_MXY]; a.outf[OF_MYAW] = a.in[IF_MYAW];
+    a.outf[OF_ACT] = a.in[IF_ACT]; a.outf[OF_PACT] = a.in[IF_PACT];
     uint32_t om = 0;
     if (ph & RL_PHASE_DONES) om |= 1u << OF_EPLEN;
     if (ph & RL_PHASE_REWARDS) om |= (1u << OF_REWARD) | (1u << OF_SUMS) | (1u << OF_STEPR);
     if (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) om |= (1u << OF_CMD) | (1u << OF_HEAD) | (1u << OF_TLEFT) | (1u << OF_MXY) | (1u << OF_MYAW);
-    if (ph & RL_PHASE_RESET) om |= (1u << OF_SUMS) | (1u << OF_EPLEN);
-    const int oc[OF_COUNT] = {1, 1, s.num_reward_terms, s.num_reward_terms, 3, 1, 1, 1, 1};
+    if (ph & RL_PHASE_RESET) om |= (1u << OF_SUMS) | (1u << OF_EPLEN) | (1u << OF_ACT) | (1u << OF_PACT);
+    const int oc[OF_COUNT] = {1, 1, s.num_reward_terms, s.num_reward_terms, 3, 1, 1, 1, 1, s.action.n_actions, s.action.n_actions};
     uint32_t ov4 = 0;
     for (int f = 0; f < OF_COUNT; ++f) {
       if (a.outf[f].ptr == nullptr) om &= ~(1u << f);
@@ -1555,42 +1647,41 @@ int validate_spec(const RlStepSpec* s) {
   return RL_OK;
 }
 
-template <class P, int E, int LPE, int MODE>
+template <class P, int NW, int MODE>
 int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   const size_t smem = (size_t)ctx->L.total_words * 4;
   static thread_local int configured_device = -1;
   static thread_local size_t configured_smem = 0;
   if (configured_device != ctx->device || configured_smem < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, E, LPE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = ctx->device; configured_smem = smem;
   }
-  const int grid = (n_items + E - 1) / E;
+  const int grid = (n_items + kE - 1) / kE;
   if (grid <= 0) return RL_OK;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E * LPE); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, E, LPE, MODE>, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE>, a));
   return RL_OK;
 }
 
-// (envs per CTA, lanes per env) pairs compiled for the generic kernel / for every baked spec
-#define RL_DYN_CONFIGS(X) X(8, 8) X(8, 16) X(16, 4) X(16, 8) X(32, 4) X(32, 8)
-#define RL_STATIC_CONFIGS(X) X(8, 8) X(8, 16) X(16, 8)
+// warps per CTA compiled for the generic kernel / for every baked spec
+#define RL_DYN_CONFIGS(X) X(4) X(8) X(16)
+#define RL_STATIC_CONFIGS(X) X(8) X(12) X(16)
 
 template <class P, int MODE>
 int dispatch_config(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st, bool* found) {
-  const int key = ctx->E * 100 + ctx->LPE;
   *found = true;
   if constexpr (P::kStatic) {
-#define RL_CASE(E_, L_) if (key == (E_) * 100 + (L_)) return launch_step<P, E_, L_, MODE>(ctx, a, n_items, st);
+#define RL_CASE(W_) if (ctx->NW == (W_)) return launch_step<P, W_, MODE>(ctx, a, n_items, st);
     RL_STATIC_CONFIGS(RL_CASE)
 #undef RL_CASE
   } else {
-#define RL_CASE(E_, L_) if (key == (E_) * 100 + (L_)) return launch_step<P, E_, L_, MODE>(ctx, a, n_items, st);
+#define RL_CASE(W_) if (ctx->NW == (W_)) return launch_step<P, W_, MODE>(ctx, a, n_items, st);
     RL_DYN_CONFIGS(RL_CASE)
 #undef RL_CASE
   }
@@ -1608,8 +1699,13 @@ int dispatch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
 #undef RL_TRY_BAKED
     if (found) return rc;
   }
-  int rc = dispatch_config<DynPolicy, MODE>(ctx, a, n_items, st, &found);
-  if (!found) return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", ctx->E, ctx->LPE);
+  // generic kernel: nearest compiled warp count
+  RlCtx tmp = *ctx;
+  if (tmp.NW != 4 && tmp.NW != 8 && tmp.NW != 16) tmp.NW = tmp.NW < 8 ? 4 : (tmp.NW < 16 ? 8 : 16);
+  KArgs a2 = a;
+  if (tmp.NW != ctx->NW) return fail(RL_EINVAL, "generic kernel is compiled for 4, 8 or 16 warps per CTA, not %s%lld", "", ctx->NW);
+  int rc = dispatch_config<DynPolicy, MODE>(&tmp, a2, n_items, st, &found);
+  if (!found) return fail(RL_EINVAL, "unsupported launch config: %s%lld warps per CTA", "", ctx->NW);
   return rc;
 }
 
@@ -1676,15 +1772,19 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   ctx->device = device;
   ctx->slot = slot;
   ctx->spec = *spec;
-  ctx->E = 16;
-  ctx->LPE = 8;
-  ctx->L = make_layout(ctx->spec, ctx->E);
+  ctx->NW = 8;
+  ctx->L = make_layout(ctx->spec);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   if ((size_t)ctx->L.total_words * 4 > (size_t)prop.sharedMemPerBlockOptin) {
-    ctx->E = 8;
-    ctx->L = make_layout(ctx->spec, ctx->E);
+    delete ctx;
+    return fail(RL_EUNSUPPORTED, "the tile of %s%lld envs needs %lld bytes of shared memory", "", kE, (long long)make_layout(*spec).total_words * 4);
+  }
+  CUDA_TRY(cudaMalloc(&ctx->sched_dev, sizeof(Schedule)));
+  {
+    const Schedule sc = make_schedule(ctx->spec, ctx->NW);
+    CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMemcpyToSymbol(c_spec, spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * slot));
   CUDA_TRY(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
@@ -1714,26 +1814,21 @@ void rl_ctx_destroy(RlCtx* ctx) {
   if (ctx->log_partials) cudaFree(ctx->log_partials);
   if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
   if (ctx->in_rows_dev) cudaFree(ctx->in_rows_dev);
+  if (ctx->sched_dev) cudaFree(ctx->sched_dev);
   if (ctx->out_rows_dev) cudaFree(ctx->out_rows_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
 }
 
-int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int lanes_per_env) {
+int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
-  const int E = envs_per_cta > 0 ? envs_per_cta : 16;
-  const int LPE = lanes_per_env > 0 ? lanes_per_env : 8;
-  const int key = E * 100 + LPE;
-  const int okeys[] = {808, 816, 1604, 1608, 3204, 3208};  // RL_DYN_CONFIGS
-  bool ok = false;
-  for (int k : okeys) ok = ok || (k == key);
-  if (!ok) return fail(RL_EINVAL, "unsupported launch config E=%s%lld LPE=%lld", "", E, LPE);
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
-  Layout L = make_layout(ctx->spec, E);
-  if ((size_t)L.total_words * 4 > (size_t)prop.sharedMemPerBlockOptin)
-    return fail(RL_EINVAL, "launch config E=%s%lld needs %lld bytes of shared memory", "", E, (long long)L.total_words * 4);
-  ctx->E = E; ctx->LPE = LPE; ctx->L = L;
+  if (envs_per_cta != 0 && envs_per_cta != kE) return fail(RL_EINVAL, "envs_per_cta is fixed at %s%lld (one lane per env)", "", kE);
+  const int nw = warps_per_cta > 0 ? warps_per_cta : 8;
+  if (nw != 4 && nw != 8 && nw != 12 && nw != 16) return fail(RL_EINVAL, "warps_per_cta must be 4, 8, 12 or 16%s (got %lld)", "", nw);
+  DeviceGuard guard(ctx->device);
+  const Schedule sc = make_schedule(ctx->spec, nw);
+  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
+  ctx->NW = nw;
   return RL_OK;
 }
 
@@ -1808,7 +1903,7 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   if (env_ids && (phases & RL_PHASE_COMPACT)) return fail(RL_EINVAL, "rl_step: compaction is not available on an env_ids subset%s", "");
   if ((phases & RL_PHASE_COMPACT) && !(phases & RL_PHASE_DONES)) return fail(RL_EINVAL, "rl_step: COMPACT needs DONES%s", "");
   DeviceGuard guard(ctx->device);
-  const int grid = (int)((num_envs + ctx->E - 1) / ctx->E);
+  const int grid = (int)((num_envs + kE - 1) / kE);
   if (phases & (RL_PHASE_COMPACT | RL_PHASE_RESET)) {
     if (grid > ctx->cta_mask_cap) {
       cudaStreamCaptureStatus cs;
@@ -1834,7 +1929,7 @@ int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uin
       !mdp->metric_error_vel_yaw.ptr || !mdp->episode_length.ptr)
     return fail(RL_EINVAL, "rl_reset_envs: every RlMdpState field is required%s", "");
   DeviceGuard guard(ctx->device);
-  const int grid = (int)((num_envs + ctx->E - 1) / ctx->E);
+  const int grid = (int)((num_envs + kE - 1) / kE);
   if (grid > ctx->cta_mask_cap) {
     cudaStreamCaptureStatus cs;
     CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
