@@ -360,6 +360,10 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
+/* Profiling aid: when set (device int64[ceil(N/32)][8]), every CTA of rl_step records clock64() at its phase
+ * boundaries: 0 start, 1 loads issued, 2 tile resident, 3 stage 1 done, 4 stage 2 done, 5 stores issued,
+ * 6 compaction done, 7 exit. NULL switches it off. */
+int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer);
 
 /* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,

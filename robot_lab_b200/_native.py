@@ -165,7 +165,7 @@ _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlAct
 
 EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
-    "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
+    "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -206,6 +206,7 @@ def load() -> C.CDLL:
     lib.rl_ctx_destroy.restype = None
     lib.rl_ctx_set_launch_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.rl_ctx_set_pdl.argtypes = [C.c_void_p, C.c_int]
+    lib.rl_ctx_set_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),
                                       C.POINTER(RlField), C.c_void_p, C.c_void_p]
     lib.rl_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlStateView), C.POINTER(RlMdpState),

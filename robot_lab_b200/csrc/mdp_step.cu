@@ -299,6 +299,7 @@ struct KArgs {
   uint32_t* cta_mask;
   float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions
   int use_pdl;
+  long long* dbg;        // optional [grid][8] clock64 stamps of the phase boundaries (rl_ctx_set_debug_buffer)
   // single-term evaluation (rl_term_eval)
   const RlRewardTerm* adhoc;
   const uint8_t* ext_terminated;
@@ -568,6 +569,7 @@ __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
 __device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int b) {
   float m = 0.f;
+  _Pragma("unroll 1")
   for (int t = 0; t < T; ++t) {
     const float* f = h + (t * B + b) * 3;
     const float n = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
@@ -600,18 +602,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_JOINT_ACC_L2: {
       const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? L.jtau : (t.type == RL_REW_JOINT_VEL_L2 ? L.jvel : L.jacc);
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float v = SMF(off, j); s += v * v; }
       return s;
     }
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       return s;
     }
     case RL_REW_JOINT_POS_LIMITS: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) {
           const float q = SMF(L.jpos, j);
@@ -623,18 +628,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_VEL_LIMITS: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
       return s;
     }
     case RL_REW_JOINT_POWER: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jvel, j) * SMF(L.jtau, j));
       return s;
     }
     case RL_REW_STAND_STILL: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
@@ -642,6 +650,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - CJ(0, j); s += d * d; }
       const float running = sqrtf(s);
@@ -650,6 +659,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_MIRROR: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = SMF(L.jpos, t.idx_a[i]) - SMF(L.jpos, t.idx_b[i]);
         s += d * d;
@@ -658,6 +668,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = fabsf(SMF(L.act, t.idx_a[i])) - fabsf(SMF(L.act, t.idx_b[i]));
         s += d * d;
@@ -666,6 +677,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_ACTION_SYNC: {
       float r = 0.f;
+      _Pragma("unroll 1")
       for (int g = 0; g < t.n_idx; ++g) {
         const int start = t.idx_b[g], n = t.idx_c[g];
         if (n < 2) continue;
@@ -680,17 +692,20 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_ACTION_RATE_L2: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int a = 0; a < S.n_actions; ++a) { const float d = SMF(L.act, a) - SMF(L.pact, a); s += d * d; }
       return s;
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
       return s * c.gate;   // gate distributes over the two halves of a split term
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
       return s;
@@ -719,6 +734,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
         s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
@@ -728,9 +744,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, t.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
         const float ct = SMF(L.ccon, b);
@@ -744,9 +762,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_AIR_TIME_VARIANCE: {
       // torch.var (unbiased) is a Welford reduction on CPU; keep the same update order.
       float r = 0.f;
+      _Pragma("unroll 1")
       for (int which = 0; which < 2; ++which) {
         const int off = which == 0 ? L.lair : L.lcon;
         float mean = 0.f, m2 = 0.f;
+        _Pragma("unroll 1")
         for (int i = 0; i < t.n_idx; ++i) {
           const float x = fminf(SMF(off, t.idx_a[i]), 0.5f);
           const float d = x - mean;
@@ -777,6 +797,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
@@ -784,6 +805,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
@@ -791,6 +813,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_STUMBLE: {
       bool any = false;   // t = 0 is the newest history sample = net_forces_w
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_c[i];
         const float fx = h[3 * b + 0], fy = h[3 * b + 1], fz = h[3 * b + 2];
@@ -800,6 +823,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
@@ -810,6 +834,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 p = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 v = body_vec(sm, L.bvel, e, t.idx_b[i]);
@@ -821,6 +846,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
@@ -834,6 +860,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_DISTANCE_Y_EXP: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
@@ -845,6 +872,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_DISTANCE_XY_EXP: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < 4; ++i) {
         const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
@@ -857,6 +885,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_WHEEL_VEL_PENALTY: {
       float run = 0.f, stand = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const float jv = fabsf(SMF(L.jvel, t.idx_b[i]));
         const float ta = SMF(L.cair, t.idx_a[i]);
@@ -952,6 +981,7 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
   const float* urow = sm + LOBSU(g) + e * LOBSP(g);
   const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
   const bool noisy = t.has_noise && corrupt;
+  _Pragma("unroll 1")
   for (int qd = lo / 4; qd * 4 < hi; ++qd) {
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (noisy && !ext_u) {
@@ -1117,6 +1147,8 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const Layout L = P::layout(a);
   constexpr int NT = NW * 32;
   const int tid = threadIdx.x;
+#define RL_STAMP(i) do { if (a.dbg != nullptr && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+  RL_STAMP(0);
   const int warp = tid >> 5;
   const int e = tid & 31;       // compute phase: this lane's env inside the tile
   const uint32_t ph = a.phases;
@@ -1201,9 +1233,11 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         sm[L.cj + 0 * J + i] = q0; sm[L.cj + 1 * J + i] = qd0; sm[L.cj + 2 * J + i] = lo;
         sm[L.cj + 3 * J + i] = hi; sm[L.cj + 4 * J + i] = vl;
       });
+    RL_STAMP(1);                // all loads issued
     cp_async_wait_all();
     __syncthreads();            // record + mbarrier init visible to everyone
     mbar_wait(&s_bar, 0);       // bulk copies landed
+    RL_STAMP(2);                // tile resident
   }
 
   const bool valid = e < nvalid;
@@ -1277,6 +1311,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
           fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
         } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
+          _Pragma("unroll 1")
           for (int b = 0; b < S.num_hist_bodies; ++b)
             if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
         }
@@ -1301,6 +1336,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       });
     }
     __syncthreads();
+    RL_STAMP(3);                // stage 1 done
 
     // ---- stage 2 -----------------------------------------------------------------------------------------
     const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
@@ -1337,6 +1373,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       }
     }
     __syncthreads();
+    RL_STAMP(4);                // stage 2 done
 
     // ---- store phase ----------------------------------------------------------------------------
     if (ph & RL_PHASE_OBS) {
@@ -1371,6 +1408,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     }
   }
 
+  RL_STAMP(5);                  // stores issued
   // ---- ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]) -----------
   if ((ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids) {
     if (tid < kE) {  // per-CTA bit mask of done envs
@@ -1440,7 +1478,9 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       if (tid == 0) *a.ticket = 0u;
     }
   }
+  RL_STAMP(6);
   if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
+  RL_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1495,6 +1535,7 @@ struct RlCtx {
   int n_in_rows, n_out_rows;
   int sm_count;
   int use_pdl;
+  long long* dbg;
   int baked;   // index into RL_BAKED_LIST when the spec equals a build-time specialised one, else -1
 };
 
@@ -1546,6 +1587,7 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
   a.in_rows = ctx->in_rows_dev; a.n_in_rows = ctx->n_in_rows;
   a.out_rows = ctx->out_rows_dev; a.n_out_rows = ctx->n_out_rows;
   a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  a.dbg = ctx->dbg;
   if (out) a.out = *out;
   if (rnd) a.rnd = *rnd;
   bool ok = true;
@@ -1829,6 +1871,12 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta) {
   const Schedule sc = make_schedule(ctx->spec, nw);
   CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
   ctx->NW = nw;
+  return RL_OK;
+}
+
+int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer) {
+  if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
+  ctx->dbg = static_cast<long long*>(device_i64_buffer);
   return RL_OK;
 }
 

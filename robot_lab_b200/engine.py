@@ -50,6 +50,10 @@ class MdpStepEngine:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""
         nat.check(self.lib.rl_ctx_set_pdl(self._ctx, int(enabled)))
 
+    def set_debug_buffer(self, buf: torch.Tensor | None) -> None:
+        """int64 [ceil(N/32), 8] device tensor receiving per-CTA clock64 stamps of the phase boundaries."""
+        nat.check(self.lib.rl_ctx_set_debug_buffer(self._ctx, nat.ptr_of(buf)))
+
     def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
         return StateBuffers(self.spec, num_envs, self.device, layout)
 

@@ -1,0 +1,65 @@
+"""Per-CTA phase timeline of the fused step kernel (clock64 stamps, see rl_ctx_set_debug_buffer).
+
+Usage (GPU box): python tools/phase_timing.py [num_envs] [warps] [task_key]
+"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+
+import torch  # noqa: E402
+
+import helpers as H  # noqa: E402
+from robot_lab_b200 import _native as nat  # noqa: E402
+from robot_lab_b200.engine import MdpStepEngine  # noqa: E402
+from robot_lab_b200.synthetic import make_state  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
+PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DONES, "rewards": nat.PHASE_REWARDS,
+          "obs": nat.PHASE_OBS, "command": nat.PHASE_COMMAND, "dones+compact": nat.PHASE_DONES | nat.PHASE_COMPACT,
+          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS}
+phase_name = sys.argv[4] if len(sys.argv) > 4 else "all"
+cfg, spec = H.make_spec(key)
+eng = MdpStepEngine(spec, "cuda:0")
+eng.set_launch_config(W)
+sets = []
+for i in range(8):
+    b = eng.new_buffers(N)
+    b.load_logical(make_state(spec, N, seed=1234 + i))
+    b.cmd_uniforms, b.obs_uniforms = None, [None, None]
+    sets.append(b)
+grid = (N + 31) // 32
+dbg = torch.zeros(grid, 8, dtype=torch.int64, device="cuda:0")
+PH = PHASES[phase_name]
+for it in range(6):
+    for b in sets:
+        eng.step(b, phases=PH, use_random_inputs=False)
+torch.cuda.synchronize()
+eng.set_debug_buffer(dbg)
+names = ["start->loads issued", "loads issued->tile resident", "tile resident->stage1 done", "stage1->stage2 done",
+         "stage2->stores issued", "stores->compaction", "compaction->exit"]
+acc = torch.zeros(7)
+mx = torch.zeros(7)
+tot = []
+reps = 8
+for it in range(reps):
+    b = sets[it % len(sets)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.step(b, phases=PH, use_random_inputs=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    d = dbg.cpu().double()
+    dur = d[:, 1:] - d[:, :-1]
+    dur[dur.abs() > 1e8] = 0  # stamps a CTA skipped (early return of the compacting CTA)
+    acc += dur.mean(0).float()
+    mx = torch.maximum(mx, dur.max(0).values.float())
+    span = (d[:, 5] - d[:, 0])
+    tot.append((span.mean().item(), span.max().item(), ev0.elapsed_time(ev1) * 1e3))
+print(f"{key} N={N} warps={W} grid={grid} phases={phase_name}")
+for n, a_, m_ in zip(names, acc / reps, mx):
+    print(f"  {n:32s} mean {a_:9.0f} cyc   max {m_:9.0f} cyc")
+print("  per-CTA total cycles (mean, max), event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
