@@ -353,16 +353,16 @@ int64_t rl_struct_sizeof(const char* name);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knob: warps per CTA (4, 8, 12 or 16; 0 = default 8). A CTA always owns 32 consecutive envs (one lane per
- * env); its warps share the reward / observation terms according to a static schedule. envs_per_cta must be 0 or 32.
- * Synchronous (re-uploads the schedule): call it outside hot loops and outside stream capture. */
-int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
+/* Tuning knobs of the task-sliced grid: number of task groups G and warps (= 32-env tiles) per CTA; 0 = default
+ * (16, 16). Only pairs compiled into the library are accepted. Synchronous (re-uploads the schedule): call it
+ * outside hot loops and outside stream capture. */
+int rl_ctx_set_launch_config(RlCtx* ctx, int groups, int warps_per_cta);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
 /* Profiling aid: when set (device int64[ceil(N/32)][8]), every CTA of rl_step records clock64() at its phase
- * boundaries: 0 start, 1 loads issued, 2 tile resident, 3 stage 1 done, 4 stage 2 done, 5 stores issued,
- * 6 compaction done, 7 exit. NULL switches it off. */
+ * boundaries: 0 start, 3 tasks done, 4 finalisation entered (last CTA of a tile block only), 5 global tail
+ * entered (very last CTA only), 6 tail done. NULL switches it off. */
 int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer);
 
 /* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */

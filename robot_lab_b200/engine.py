@@ -42,9 +42,9 @@ class MdpStepEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def set_launch_config(self, warps_per_cta: int = 0) -> None:
-        """Warps per CTA (4, 8, 12 or 16; a CTA always owns 32 envs, one lane per env)."""
-        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, 0, warps_per_cta))
+    def set_launch_config(self, groups: int = 0, warps_per_cta: int = 0) -> None:
+        """Task groups and warps (= 32-env tiles) per CTA of the task-sliced grid; 0 = default (16, 16)."""
+        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, groups, warps_per_cta))
 
     def set_pdl(self, enabled: bool) -> None:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""

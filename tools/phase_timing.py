@@ -16,7 +16,8 @@ from robot_lab_b200.engine import MdpStepEngine  # noqa: E402
 from robot_lab_b200.synthetic import make_state  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-W = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+GW = sys.argv[2] if len(sys.argv) > 2 else "16x16"
+G_, W = (int(x) for x in GW.split("x"))
 key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
 PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DONES, "rewards": nat.PHASE_REWARDS,
           "obs": nat.PHASE_OBS, "command": nat.PHASE_COMMAND, "dones+compact": nat.PHASE_DONES | nat.PHASE_COMPACT,
@@ -24,14 +25,14 @@ PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DO
 phase_name = sys.argv[4] if len(sys.argv) > 4 else "all"
 cfg, spec = H.make_spec(key)
 eng = MdpStepEngine(spec, "cuda:0")
-eng.set_launch_config(W)
+eng.set_launch_config(G_, W)
 sets = []
 for i in range(8):
     b = eng.new_buffers(N)
     b.load_logical(make_state(spec, N, seed=1234 + i))
     b.cmd_uniforms, b.obs_uniforms = None, [None, None]
     sets.append(b)
-grid = (N + 31) // 32
+grid = (((N + 31) // 32 + W - 1) // W) * G_
 dbg = torch.zeros(grid, 8, dtype=torch.int64, device="cuda:0")
 PH = PHASES[phase_name]
 for it in range(6):
@@ -39,10 +40,9 @@ for it in range(6):
         eng.step(b, phases=PH, use_random_inputs=False)
 torch.cuda.synchronize()
 eng.set_debug_buffer(dbg)
-names = ["start->loads issued", "loads issued->tile resident", "tile resident->stage1 done", "stage1->stage2 done",
-         "stage2->stores issued", "stores->compaction", "compaction->exit"]
-acc = torch.zeros(7)
-mx = torch.zeros(7)
+acc = torch.zeros(1)
+mx = torch.zeros(1)
+per_group = torch.zeros(G_)
 tot = []
 reps = 8
 for it in range(reps):
@@ -53,13 +53,10 @@ for it in range(reps):
     ev1.record()
     torch.cuda.synchronize()
     d = dbg.cpu().double()
-    dur = d[:, 1:] - d[:, :-1]
-    dur[dur.abs() > 1e8] = 0  # stamps a CTA skipped (early return of the compacting CTA)
-    acc += dur.mean(0).float()
-    mx = torch.maximum(mx, dur.max(0).values.float())
-    span = (d[:, 5] - d[:, 0])
-    tot.append((span.mean().item(), span.max().item(), ev0.elapsed_time(ev1) * 1e3))
-print(f"{key} N={N} warps={W} grid={grid} phases={phase_name}")
-for n, a_, m_ in zip(names, acc / reps, mx):
-    print(f"  {n:32s} mean {a_:9.0f} cyc   max {m_:9.0f} cyc")
-print("  per-CTA total cycles (mean, max), event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
+    span = (d[:, 3] - d[:, 0])            # start -> this CTA's tasks done
+    per_group += span.view(-1, G_).mean(0).float()
+    t0 = d[:, 0].min()
+    tot.append((span.mean().item(), span.max().item(), (d[:, 3].max() - t0).item(), ev0.elapsed_time(ev1) * 1e3))
+print(f"{key} N={N} groups x warps={G_}x{W} grid={grid} phases={phase_name}")
+print("  task cycles per group (mean over tile blocks):", [int(x) for x in (per_group / reps).tolist()])
+print("  per-CTA task cycles (mean, max), first start -> last tasks done, event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
