@@ -326,12 +326,13 @@ struct DynPolicy {
   static constexpr bool kStatic = false;
   __device__ __forceinline__ static Scalars scalars(const KArgs& a) { return scalars_of(c_spec[a.slot]); }
   __device__ __forceinline__ static const RlCommandCfg& command(const KArgs& a) { return c_spec[a.slot].command; }
-  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, F&& f) {
+  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, int g, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
     const int n = a.sched->n;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       const Task tk = a.sched->t[i];
+      if (tk.owner != g) continue;
       if (tk.kind == TK_REWARD) f(tk, S.rewards[tk.a], S.obs[0].terms[0], false);
       else f(tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0);
     }
@@ -379,15 +380,30 @@ struct StaticPolicy {
     return c;
   }
   template <int G> struct Sched { static constexpr Schedule value = make_schedule(B::spec, G); };
-  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, F&& f) {
+  // all tasks of group GI, in schedule order
+  template <int G, int GI, class F> __device__ __forceinline__ static void group_tasks(F&& f) {
     static_for(std::make_integer_sequence<int, Sched<G>::value.n>{}, [&](auto ic) {
       constexpr int i = decltype(ic)::value;
       constexpr Task tk = Sched<G>::value.t[i];
-      static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
-      static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
-      constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
-      f(tk, rt, ot, corrupt);
+      if constexpr (tk.owner == GI) {
+        static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
+        static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
+        constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+        f(tk, rt, ot, corrupt);
+      }
     });
+  }
+  // binary search on the (runtime) group id: log2(G) branches straight to the group's contiguous code
+  template <int G, int LO, int HI, class F> __device__ __forceinline__ static void dispatch_group(int g, F&& f) {
+    if constexpr (HI - LO == 1) {
+      group_tasks<G, LO>(f);
+    } else {
+      constexpr int MID = (LO + HI) / 2;
+      if (g < MID) dispatch_group<G, LO, MID>(g, f); else dispatch_group<G, MID, HI>(g, f);
+    }
+  }
+  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, int g, F&& f) {
+    dispatch_group<G, 0, G>(g, f);
   }
   template <int G, class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
     static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
@@ -441,7 +457,14 @@ struct EnvCtx {
 __device__ __forceinline__ float ld_field(const FieldD& fd, long long env, int c) {
   return static_cast<const float*>(fd.ptr)[env * fd.es + (long long)c * fd.cs];
 }
-#define LDF(f, c) ld_field(a.in[(f)], env, (c))
+__device__ __forceinline__ float ld_field_ro(const FieldD& fd, long long env, int c) {
+  return __ldg(static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
+}
+// Every task-phase read goes through ld.global.nc: within one launch no address is re-read after it was written
+// (episode sums / metrics are read once by their only writer; the command and the episode length are rewritten
+// at finalisation only, after every reader of the tile block is done), so the compiler may hoist and batch ALL
+// loads of a group above the stores of its earlier tasks - one memory round trip per CTA instead of one per task.
+#define LDF(f, c) ld_field_ro(a.in[(f)], env, (c))
 #define JC(arr, j) CS.arr[(j)]   // per-joint constants: lane-uniform index -> constant-bank broadcast
 
 __device__ __forceinline__ bool first_contact(const KArgs& a, const Scalars& S, long long env, int b) {
@@ -454,7 +477,7 @@ __device__ __forceinline__ V3 body_vec(const KArgs& a, int f, long long env, int
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
 __device__ __forceinline__ float hist_max_norm(const KArgs& a, long long env, int T, int B, int b) {
   float m = 0.f;
-  _Pragma("unroll 1")
+  _Pragma("unroll")
   for (int t = 0; t < T; ++t) {
     const int i = (t * B + b) * 3;
     const float fx = LDF(IF_HIST, i), fy = LDF(IF_HIST, i + 1), fz = LDF(IF_HIST, i + 2);
@@ -487,18 +510,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_JOINT_ACC_L2: {
       const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? IF_JTAU : (t.type == RL_REW_JOINT_VEL_L2 ? IF_JVEL : IF_JACC);
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float v = LDF(off, j); s += v * v; }
       return s;
     }
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JPOS, j) - JC(default_joint_pos, j));
       return s;
     }
     case RL_REW_JOINT_POS_LIMITS: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) {
           const float q = LDF(IF_JPOS, j);
@@ -510,18 +536,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_VEL_LIMITS: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(LDF(IF_JVEL, j)) - JC(soft_vel_limit, j) * t.p[0], 0.f, 1.f);
       return s;
     }
     case RL_REW_JOINT_POWER: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JVEL, j) * LDF(IF_JTAU, j));
       return s;
     }
     case RL_REW_STAND_STILL: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JPOS, j) - JC(default_joint_pos, j));
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
@@ -529,6 +558,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float d = LDF(IF_JPOS, j) - JC(default_joint_pos, j); s += d * d; }
       const float running = sqrtf(s);
@@ -537,6 +567,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_JOINT_MIRROR: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = LDF(IF_JPOS, t.idx_a[i]) - LDF(IF_JPOS, t.idx_b[i]);
         s += d * d;
@@ -545,6 +576,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = fabsf(LDF(IF_ACT, t.idx_a[i])) - fabsf(LDF(IF_ACT, t.idx_b[i]));
         s += d * d;
@@ -567,17 +599,20 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_ACTION_RATE_L2: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int ai = 0; ai < S.n_actions; ++ai) { const float d = LDF(IF_ACT, ai) - LDF(IF_PACT, ai); s += d * d; }
       return s;
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if (((t.body_mask >> b) & 1ull) && (hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
       return s * c.gate;   // gate distributes over the two halves of a split term
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
       return s;
@@ -606,6 +641,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
         s += (LDF(IF_LAIR, b) - t.p[0]) * (first_contact(a, S, env, b) ? 1.f : 0.f);
@@ -615,9 +651,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) n_contact += (LDF(IF_CCON, t.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
         const float ct = LDF(IF_CCON, b);
@@ -634,6 +672,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       for (int which = 0; which < 2; ++which) {
         const int off = which == 0 ? IF_LAIR : IF_LCON;
         float mean = 0.f, m2 = 0.f;
+        _Pragma("unroll")
         for (int i = 0; i < t.n_idx; ++i) {
           const float x = fminf(LDF(off, t.idx_a[i]), 0.5f);
           const float d = x - mean;
@@ -664,6 +703,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(a, S, env, t.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
@@ -671,6 +711,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(a, S, env, t.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
@@ -678,6 +719,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_STUMBLE: {
       bool any = false;   // t = 0 is the newest history sample = net_forces_w
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_c[i];
         const float fx = LDF(IF_HIST, 3 * b + 0), fy = LDF(IF_HIST, 3 * b + 1), fz = LDF(IF_HIST, 3 * b + 2);
@@ -687,6 +729,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 vw = body_vec(a, IF_BVEL, env, t.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
@@ -697,6 +740,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 p = body_vec(a, IF_BPOS, env, t.idx_b[i]);
         const V3 v = body_vec(a, IF_BVEL, env, t.idx_b[i]);
@@ -708,6 +752,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(a, IF_BPOS, env, t.idx_b[i]);
         const V3 vw = body_vec(a, IF_BVEL, env, t.idx_b[i]);
@@ -721,6 +766,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_DISTANCE_Y_EXP: {
       float s = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(a, IF_BPOS, env, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
@@ -744,6 +790,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_WHEEL_VEL_PENALTY: {
       float run = 0.f, stand = 0.f;
+      _Pragma("unroll")
       for (int i = 0; i < t.n_idx; ++i) {
         const float jv = fabsf(LDF(IF_JVEL, t.idx_b[i]));
         const float ta = LDF(IF_CAIR, t.idx_a[i]);
@@ -807,7 +854,7 @@ __device__ __forceinline__ uint32_t eval_dones(const KArgs& a, const Scalars& S,
     } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
       fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
     } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
-      _Pragma("unroll 1")
+      _Pragma("unroll")
       for (int b = 0; b < S.num_hist_bodies; ++b)
         if (((t.body_mask >> b) & 1ull) && (hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
     }
@@ -816,57 +863,75 @@ __device__ __forceinline__ uint32_t eval_dones(const KArgs& a, const Scalars& S,
   return bits | (term << 8) | (trunc << 9);
 }
 
-// Columns [lo, hi) of one observation term for this lane's env: ObservationManager.compute_group [IL]
-// (clone -> +noise -> clip -> scale), written straight into the group's [N, D] row.
+// Columns [lo, hi) of one observation term for the warp's 32 envs: ObservationManager.compute_group [IL]
+// (clone -> +noise -> clip -> scale). Lane e computes its env's values into a [32][33] shared-memory tile
+// (conflict-free both ways), then the warp writes row segments of the [N, D] observation rows: consecutive
+// lanes hit consecutive addresses instead of 32 partial sectors per store.
 __device__ __forceinline__ void obs_task(const KArgs& a, const Scalars& S, const RlStepSpec& CS, const RlObsTerm& t,
                                          const bool corrupt, const RandState rs, const int g, const int ti,
                                          const int col0, const int lo, const int hi, const long long env,
                                          const bool valid, const EnvCtx& c, const float* cmd3, const int eplen_eff,
-                                         const bool zero_action) {
-  float* row = a.out.obs[g] + env * a.out.obs_pitch[g] + col0;
+                                         const bool zero_action, float (*tile)[33]) {
+  const int lane = threadIdx.x & 31;
+  float* const obs = a.out.obs[g];
+  const long long pitch = a.out.obs_pitch[g];
   const int D = g == 0 ? CS.obs[0].dim : CS.obs[1].dim;
   const float* urow = a.rnd.obs_uniforms[g] ? a.rnd.obs_uniforms[g] + env * D + col0 : nullptr;
   const bool noisy = t.has_noise && corrupt;
-  _Pragma("unroll 1")
-  for (int qd = lo / 4; qd * 4 < hi; ++qd) {
-    float u4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (noisy && urow == nullptr) {
-      const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
-      u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
-    }
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int nc = min(32, hi - c0);
+    _Pragma("unroll")
+    for (int q = 0; q < 8; ++q) {
+      if (q * 4 >= nc) break;
+      float u4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (noisy && urow == nullptr) {
+        const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)((c0 >> 2) + q));
+        u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
+      }
 #pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4) {
-      const int col = qd * 4 + r4;
-      if (col >= hi) break;
-      float v;
-      switch (t.type) {
-        case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
-        case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
-        case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
-        case RL_OBS_GENERATED_COMMANDS: v = cmd3[col]; break;
-        case RL_OBS_JOINT_POS_REL: v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]); break;
-        case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
-          v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]);
-          if ((t.zero_mask >> col) & 1ull) v = 0.f;
-          break;
-        case RL_OBS_JOINT_VEL_REL: v = LDF(IF_JVEL, t.ids[col]) - JC(default_joint_vel, t.ids[col]); break;
-        case RL_OBS_LAST_ACTION: v = zero_action ? 0.f : LDF(IF_ACT, col); break;
-        case RL_OBS_HEIGHT_SCAN: v = (LDF(IF_RAYPOS, 0) - LDF(IF_RAYS, col)) - t.p[0]; break;
-        case RL_OBS_PHASE: {
-          const float ph = ((float)eplen_eff * S.step_dt) / t.p[0];
-          v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
-          break;
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int jj = q * 4 + r4;
+        const int col = c0 + jj;
+        if (jj >= nc) break;
+        float v;
+        switch (t.type) {
+          case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
+          case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
+          case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
+          case RL_OBS_GENERATED_COMMANDS: v = cmd3[col]; break;
+          case RL_OBS_JOINT_POS_REL: v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]); break;
+          case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
+            v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]);
+            if ((t.zero_mask >> col) & 1ull) v = 0.f;
+            break;
+          case RL_OBS_JOINT_VEL_REL: v = LDF(IF_JVEL, t.ids[col]) - JC(default_joint_vel, t.ids[col]); break;
+          case RL_OBS_LAST_ACTION: v = zero_action ? 0.f : LDF(IF_ACT, col); break;
+          case RL_OBS_HEIGHT_SCAN: v = (LDF(IF_RAYPOS, 0) - LDF(IF_RAYS, col)) - t.p[0]; break;
+          case RL_OBS_PHASE: {
+            const float ph = ((float)eplen_eff * S.step_dt) / t.p[0];
+            v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
+            break;
+          }
+          default: v = 0.f;
         }
-        default: v = 0.f;
+        if (noisy) {
+          const float u = urow ? urow[col] : u4[r4];
+          v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
+        }
+        if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
+        if (t.has_scale) v = v * t.scale;
+        tile[lane][jj] = v;
       }
-      if (noisy) {
-        const float u = urow ? urow[col] : u4[r4];
-        v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
-      }
-      if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
-      if (t.has_scale) v = v * t.scale;
-      if (valid) row[col] = v;
     }
+    __syncwarp();
+    const int env_lo = (int)env, ok = valid ? 1 : 0;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const long long env_r = (long long)__shfl_sync(0xffffffffu, env_lo, r);
+      const int ok_r = __shfl_sync(0xffffffffu, ok, r);
+      if (ok_r && lane < nc) obs[env_r * pitch + col0 + c0 + lane] = tile[r][lane];
+    }
+    __syncwarp();
   }
 }
 
@@ -886,7 +951,9 @@ __device__ __forceinline__ void cmd_uniforms(const KArgs& a, const RandState rs,
 // qb*WPC + w, lane e its env e. MODE 0 = step, MODE 1 = single-term evaluation (one group, one task).
 // ---------------------------------------------------------------------------------------------------
 template <class P, int G, int WPC, int MODE>
-__global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
+__global__ void __launch_bounds__(WPC * 32, 1) mdp_step_kernel(const KArgs a) {
+  extern __shared__ __align__(16) float s_dyn[];                 // [WPC][32][33] observation transpose tiles
+  float (*xpose)[33] = reinterpret_cast<float (*)[33]>(s_dyn) + (threadIdx.x >> 5) * 32;
   __shared__ float s_red[WPC][RL_LOG_STRIDE];
   __shared__ int s_last, s_final;
   const Scalars S = P::scalars(a);
@@ -934,11 +1001,14 @@ __global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
       if (valid) a.term_out[env] = v;
       return;
     }
+    RL_STAMP(1);                   // index setup done
+    if (ph & 0x8000u) return;      // profiling aid: empty launch
     // ---- this group's tasks, straight-line for a baked spec ---------------------------------------------
-    const EnvCtx c = make_ctx(a, env);
+    const EnvCtx c = a.in[IF_QUAT].ptr != nullptr ? make_ctx(a, env) : EnvCtx{};   // reset-only launches carry no state
+    RL_STAMP(2);                   // context (root state loads + 3 quaternion rotations) done
+    if (ph & 0x4000u) { if (valid && c.gate < -1.f) a.termv[env] = c.gate; return; }   // profiling aid: context only
     const bool with_dones = (ph & RL_PHASE_DONES) != 0;
-    P::template for_tasks<G>(a, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
-      if (tk.owner != g) return;
+    P::template for_tasks<G>(a, g, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
       if (tk.kind == TK_REWARD) {
         if (!(ph & RL_PHASE_REWARDS)) return;
         const int k = tk.a;
@@ -958,7 +1028,7 @@ __global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
       } else if (tk.kind == TK_OBS) {
         if (!(ph & RL_PHASE_OBS) || a.out.obs[tk.a] == nullptr) return;
         const int eplen_eff = do_reset ? 0 : (ld_eplen(a, env) + (with_dones ? 1 : 0));
-        obs_task(a, S, CS, ot, corrupt, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, env, valid, c, nullptr, eplen_eff, do_reset);
+        obs_task(a, S, CS, ot, corrupt, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, env, valid, c, nullptr, eplen_eff, do_reset, xpose);
       } else if (tk.kind == TK_DONES) {
         if (!with_dones) return;
         const uint32_t fl = eval_dones<P>(a, S, env, c);
@@ -981,7 +1051,6 @@ __global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
         if (do_reset) {
           // ---- manager reset [IL]: logging partials first (deterministic: lane tree, warp order, block order) ----
           const int bits = (a.out.done_bits != nullptr) ? (int)a.out.done_bits[env] : 0;
-          _Pragma("unroll 1")
           for (int v = 0; v < K + RL_MAX_DONE_TERMS + 2; ++v) {
             float x = 0.f;
             if (valid) {
@@ -1001,9 +1070,7 @@ __global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
           }
           // RewardManager / ActionManager / CommandTerm .reset, episode_length_buf = 0
           if (valid) {
-            _Pragma("unroll 1")
             for (int k = 0; k < K; ++k) STF(IF_SUMS, k, 0.f);
-            _Pragma("unroll 1")
             for (int i = 0; i < S.n_actions; ++i) { STF(IF_ACT, i, 0.f); STF(IF_PACT, i, 0.f); }
             static_cast<int32_t*>(const_cast<void*>(a.in[IF_EPLEN].ptr))[env * a.in[IF_EPLEN].es] = 0;
           }
@@ -1065,7 +1132,7 @@ __global__ void __launch_bounds__(WPC * 32) mdp_step_kernel(const KArgs a) {
           const float cmd3[3] = {c0, c1, c2};
           P::for_cmd_obs(a, [&](const RlObsTerm& ct, int og, int oti, int ocol0, bool ocorrupt) {
             if (a.out.obs[og] == nullptr) return;
-            obs_task(a, S, CS, ct, ocorrupt, rs, og, oti, ocol0, 0, ct.dim, env, valid, c, cmd3, 0, do_reset);
+            obs_task(a, S, CS, ct, ocorrupt, rs, og, oti, ocol0, 0, ct.dim, env, valid, c, cmd3, 0, do_reset, xpose);
           });
         }
       }
@@ -1331,7 +1398,13 @@ int launch_step(RlCtx* ctx, const KArgs& a, cudaStream_t st) {
   if (grid <= 0) return RL_OK;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WPC * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  constexpr size_t smem = (size_t)WPC * 32 * 33 * sizeof(float);
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, G, WPC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = ctx->device;
+  }
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WPC * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

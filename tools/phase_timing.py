@@ -21,7 +21,7 @@ G_, W = (int(x) for x in GW.split("x"))
 key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
 PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DONES, "rewards": nat.PHASE_REWARDS,
           "obs": nat.PHASE_OBS, "command": nat.PHASE_COMMAND, "dones+compact": nat.PHASE_DONES | nat.PHASE_COMPACT,
-          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS}
+          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS, "empty": 0x8000, "ctx": 0x4000}
 phase_name = sys.argv[4] if len(sys.argv) > 4 else "all"
 cfg, spec = H.make_spec(key)
 eng = MdpStepEngine(spec, "cuda:0")
@@ -53,10 +53,17 @@ for it in range(reps):
     ev1.record()
     torch.cuda.synchronize()
     d = dbg.cpu().double()
+    if phase_name in ("empty", "ctx"):
+        k = 1 if phase_name == "empty" else 2
+        print("   start->stamp%d cycles: mean %.0f max %.0f" % (k, (d[:, k] - d[:, 0]).mean().item(), (d[:, k] - d[:, 0]).max().item()),
+              " stamp1: mean %.0f" % (d[:, 1] - d[:, 0]).mean().item(), " event us %.1f" % (ev0.elapsed_time(ev1) * 1e3))
+        continue
     span = (d[:, 3] - d[:, 0])            # start -> this CTA's tasks done
     per_group += span.view(-1, G_).mean(0).float()
     t0 = d[:, 0].min()
     tot.append((span.mean().item(), span.max().item(), (d[:, 3].max() - t0).item(), ev0.elapsed_time(ev1) * 1e3))
 print(f"{key} N={N} groups x warps={G_}x{W} grid={grid} phases={phase_name}")
+if phase_name in ("empty", "ctx"):
+    sys.exit(0)
 print("  task cycles per group (mean over tile blocks):", [int(x) for x in (per_group / reps).tolist()])
 print("  per-CTA task cycles (mean, max), first start -> last tasks done, event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
