@@ -49,8 +49,7 @@ def parse_args():
     p.add_argument("--task", default=TASK_DEFAULT)
     p.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (weak scaling)")
     p.add_argument("--sets", type=int, default=24, help="independent state sets the step rotates over (L2 defeat)")
-    p.add_argument("--groups", type=int, default=0, help="task groups of the task-sliced grid (0 = default)")
-    p.add_argument("--warps", type=int, default=0, help="warps (= 32-env tiles) per CTA (0 = default)")
+    p.add_argument("--warps", type=int, default=0, help="warps per CTA (4/8/16/24/32; a CTA owns 32 envs)")
     p.add_argument("--no-pdl", action="store_true")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -218,8 +217,8 @@ def main():
 
     N, S, K, W = args.num_envs, max(1, args.sets), args.steps, max(3, args.warmup)
     eng = MdpStepEngine(spec, dev)
-    if args.groups or args.warps:
-        eng.set_launch_config(args.groups, args.warps)
+    if args.warps:
+        eng.set_launch_config(args.warps)
     eng.set_pdl(not args.no_pdl)
     sets = []
     for i in range(S):
@@ -366,7 +365,7 @@ def main():
                 "workload": f"{args.task} (BASELINE.json configs[2]), {N} envs/GPU, J={spec.J} B={spec.B} F={spec.Bt} "
                             f"R={spec.R} K={spec.K}, policy/critic rows {spec.obs[0].dim}/{spec.obs[1].dim}",
                 "num_envs_per_gpu": N, "state_sets": S, "cuda_graph_steps": G if use_graph else 0,
-                "pdl": not args.no_pdl, "launch": {"task_groups": args.groups or 16, "warps_per_cta": args.warps or 16},
+                "pdl": not args.no_pdl, "launch": {"envs_per_cta": 32, "warps_per_cta": args.warps or 8},
                 "l2_policy": f"rotating over {S} independent state sets (inputs+outputs+manager state "
                              f"{S * (sets[0].inputs.nbytes + sets[0].outputs.nbytes + sets[0].mdp.nbytes) / 1e6:.0f} MB > 126 MB L2)",
                 "noise": "in-kernel Philox4x32-10 (0 bytes)", "parallelism": f"dp{world} (env shards, no data-path collective)",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 5
+#define RL_ABI_VERSION 6
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -43,6 +43,8 @@ extern "C" {
 #define RL_MAX_OBS_TERMS 12
 #define RL_MAX_DONE_TERMS 8
 #define RL_MAX_IDX 32
+#define RL_MAX_TASKS 112       /* entries of the static work schedule (debug interface) */
+#define RL_DEBUG_STRIDE 160     /* int64 words per CTA in the debug buffer */
 #define RL_NUM_OBS_GROUPS 2     /* 0 = policy, 1 = critic                                        */
 #define RL_NUM_CMD_UNIFORMS 7   /* time_left, vx, vy, wz, heading, is_heading, is_standing       */
 
@@ -353,17 +355,22 @@ int64_t rl_struct_sizeof(const char* name);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knobs of the task-sliced grid: number of task groups G and warps (= 32-env tiles) per CTA; 0 = default
- * (16, 16). Only pairs compiled into the library are accepted. Synchronous (re-uploads the schedule): call it
- * outside hot loops and outside stream capture. */
-int rl_ctx_set_launch_config(RlCtx* ctx, int groups, int warps_per_cta);
+/* Tuning knob: warps per CTA (4, 8 or 16 for any spec; 8, 16, 24 or 32 for a spec the library was specialised
+ * for at build time; 0 = default). A CTA always owns 32 consecutive envs (one lane per env); its warps share the
+ * termination / reward / command / observation terms according to a static schedule. envs_per_cta must be 0 or 32.
+ * Synchronous (re-uploads the schedule): call it outside hot loops and outside stream capture. */
+int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
-/* Profiling aid: when set (device int64[ceil(N/32)][8]), every CTA of rl_step records clock64() at its phase
- * boundaries: 0 start, 3 tasks done, 4 finalisation entered (last CTA of a tile block only), 5 global tail
- * entered (very last CTA only), 6 tail done. NULL switches it off. */
+/* Profiling aid: when set (device int64[ceil(N/32)][RL_DEBUG_STRIDE]), every CTA of rl_step records clock64():
+ * words 0-7 phase boundaries (0 start, 1 loads issued, 2 tile resident, 3 stage 1 done, 4 stage 2 done, 5 stores
+ * issued, 6 compaction done, 7 exit); words 8 .. 8+RL_MAX_TASKS-1 the duration of each scheduled task (index as in
+ * rl_ctx_get_schedule); then one word per warp: the clock at which it entered stage 1. NULL switches it off. */
 int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer);
+/* The static work schedule of the current launch config: out[i] = {kind (0 reward, 1 observation, 2 terminations,
+ * 3 command), a (reward term / obs group), b (half / obs term), owner warp, lo, hi, first column, late}. */
+int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out /* [RL_MAX_TASKS][8] */, int32_t* n_tasks);
 
 /* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,

@@ -7,16 +7,16 @@
 // V/mdp/observations.py:17-35, V/mdp/commands.py:22-85, V/velocity_env_cfg.py:106-254,379-664 and the
 // IsaacLab manager loops / upstream terms listed in SURVEY.md Appendix A.
 //
-// Execution model (HBM-bound arithmetic intensity, ~0.5 FLOP/B; no tensor cores - nothing here is a contraction):
-//   * thread-per-env: a warp owns a tile of 32 consecutive envs, lane e its env e. All per-env state is read
-//     straight from global memory; with the SoA [C][N] layout every warp load is one coalesced 128-byte line;
-//   * task-sliced grid: the terms are packed into G groups of similar cost and a CTA = (group, block of tiles).
-//     Every warp of a CTA runs the same straight-line code (baked spec: dispatch, weights, index lists are
-//     immediates) on a different tile - instruction fetch is shared, 16-32 independent warps per SM hide the
-//     dependent-instruction latency, and no SIMT lane repeats another lane's scalar work;
-//   * the last CTA to finish a tile block finalises it (ordered reward sum, late terms, command commit,
-//     episode length, done masks) and the last block compacts the reset ids in ascending order.
-// profiles/r1_*.md documents why (three earlier mappings measured with ncu + clock64 stamps).
+// Execution model (HBM-bound, no tensor cores - the arithmetic intensity is ~0.5 FLOP/B):
+//   * a CTA owns E consecutive envs; LPE lanes cooperate on one env (joint / body / obs-column loops are
+//     strided over the lanes, reductions are xor-shuffles inside the lane group);
+//   * load phase: the big AoS sensor rows (contact-force history, height-scan ray hits, noise inputs) are
+//     staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) while the
+//     small per-env fields are gathered with coalesced LDGs into an SoA [word][E] shared-memory record -
+//     all global reads of the tile are in flight before any arithmetic starts;
+//   * compute phase works on shared memory only and assembles the observation rows there;
+//   * store phase: observation rows leave with bulk stores (cp.async.bulk.global.shared::cta), the SoA
+//     outputs with coalesced STGs; the last CTA to finish compacts the reset ids from per-CTA bit masks.
 //
 // Built with -fmad=false on purpose: the reference is eager PyTorch, every op rounds on its own, and not
 // contracting a*b+c keeps threshold decisions (contact > 1 N, |cmd| > 0.1, ...) bit-identical.
@@ -59,10 +59,14 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0, long lo
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------
-// Per-launch field descriptors. Every per-env field is {ptr, env stride, comp stride} in elements; the kernels are
-// thread-per-env, so the SoA layout [C][N] (env stride 1) makes every warp load one coalesced 128-byte line.
+// Per-launch field descriptors and the static row tables
+//
+// A "row" is one component of one 4-byte per-env field. The step kernel stages rows into an SoA shared-memory
+// record (word w of local env e at sm[w*E + e]) with ONE generic loop of non-blocking cp.async copies and writes
+// result rows back with one generic loop - the row tables (field id, component, record word) are static per
+// context and live in global memory; only the ~25 field descriptors (pointer + strides) travel per launch.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kE = 32;  // envs per tile = lanes per warp: lane e of a warp owns env e of the warp's tile
+constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
 
 struct FieldD {
   const void* ptr;
@@ -72,75 +76,178 @@ struct FieldD {
 
 enum InField {
   IF_ROOT_POS = 0, IF_QUAT, IF_LIN_VEL, IF_ANG_VEL, IF_JPOS, IF_JVEL, IF_JACC, IF_JTAU,
-  IF_CAIR, IF_LAIR, IF_CCON, IF_LCON, IF_BPOS, IF_BVEL, IF_RAYPOS, IF_HIST, IF_RAYS,
-  IF_CMD, IF_HEAD, IF_TLEFT, IF_MXY, IF_MYAW, IF_EPLEN, IF_SUMS, IF_ACT, IF_PACT, IF_STEPR, IF_COUNT
+  IF_CAIR, IF_LAIR, IF_CCON, IF_LCON, IF_BPOS, IF_BVEL, IF_RAYPOS,
+  IF_CMD, IF_HEAD, IF_TLEFT, IF_MXY, IF_MYAW, IF_EPLEN, IF_SUMS, IF_CMDU, IF_ACT, IF_PACT, IF_COUNT
 };
+enum OutField { OF_REWARD = 0, OF_EPLEN, OF_SUMS, OF_STEPR, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_ACT, OF_PACT, OF_COUNT };
+
+// row meta: field (bits 0-5) | comp (6-15) | record word (16-31)
+__host__ __device__ constexpr uint32_t row_pack(int f, int c, int w) { return (uint32_t)f | ((uint32_t)c << 6) | ((uint32_t)w << 16); }
 
 // ---------------------------------------------------------------------------------------------------
-// Work schedule ("task-sliced grid"). A task = one reward term (wide body-mask terms in two halves), one
-// observation term (the height scan in 64-column chunks), the termination terms, or the command update (which
-// also owns the command-dependent observation columns and, on env_ids launches, the manager reset). Tasks are
-// packed into G groups of similar cost (longest-processing-time greedy); a CTA = (group, block of tiles) and all
-// of its warps run the SAME straight-line code on different 32-env tiles, one lane per env:
-//   * no SIMT lane ever repeats another lane's scalar work,
-//   * instruction fetch is shared by every warp of the CTA and an SM only ever sees its group's code,
-//   * 16-32 independent warps per SM hide the dependent-instruction latency a lone warp cannot.
-// constexpr: a baked spec gets its schedule (and straight-line per-group code) at compile time.
+// Shared-memory layout of one CTA tile (word offsets; SoA words already multiplied by kE).
 // ---------------------------------------------------------------------------------------------------
-#define RL_MAX_TASKS 112
+struct Layout {
+  int A, J, K;
+  int root_pos, quat, lin_vel, ang_vel;          // SoA offsets (= word * kE)
+  int jpos, jvel, jacc, jtau;
+  int act, pact;
+  int cmd, head, tleft, ishead, isstand;
+  int cmdn, epnew;                                // updated command / episode length (committed by the store phase)
+  int mxy, myaw, eplen;
+  int sums;
+  int cair, lair, ccon, lcon;
+  int bpos, bvel;
+  int raypos;
+  int cmdu;
+  int rew, flags, stepr;                         // outputs
+  int termv;                                     // [K][2] weighted term values (or raw partials of split terms)
+  int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
+  int soa_words;
+  int cj;                                        // per-joint constants [5][J]: q0, qd0, soft lo, soft hi, vel limit
+  // AoS rows [kE][pitch]; pitches are forced ODD so that lane e reading row e is bank-conflict free
+  int hist, hist_pitch;
+  int rays, rays_pitch;
+  int obs0, obs1, obs_pitch0, obs_pitch1;          // selected with LOBS(g) etc.: no runtime-indexed members,
+  int obsu0, obsu1;                                // so the struct never has to live in local memory
+  int total_words;
+};
+
+__host__ __device__ constexpr int in_field_ncomp(const RlStepSpec& s, int f) {
+  switch (f) {
+    case IF_ROOT_POS: case IF_LIN_VEL: case IF_ANG_VEL: case IF_CMD: return 3;
+    case IF_QUAT: return 4;
+    case IF_JPOS: case IF_JVEL: case IF_JACC: case IF_JTAU: return s.num_joints;
+    case IF_CAIR: case IF_LAIR: case IF_CCON: case IF_LCON: return s.num_time_bodies;
+    case IF_BPOS: case IF_BVEL: return 3 * s.num_asset_bodies;
+    case IF_SUMS: return s.num_reward_terms;
+    case IF_CMDU: return RL_NUM_CMD_UNIFORMS;
+    case IF_ACT: case IF_PACT: return s.action.n_actions;
+    default: return 1;
+  }
+}
+
+__host__ __device__ constexpr int in_field_word(const RlStepSpec& s, int f) {  // first record word of an input field
+  int w = 0;
+  for (int i = 0; i < f; ++i) w += in_field_ncomp(s, i);
+  return w;
+}
+__host__ __device__ constexpr int out_field_ncomp(const RlStepSpec& s, int f) {
+  switch (f) {
+    case OF_SUMS: case OF_STEPR: return s.num_reward_terms;
+    case OF_CMD: return 3;
+    case OF_ACT: case OF_PACT: return s.action.n_actions;
+    default: return 1;
+  }
+}
+
+__host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+__host__ __device__ constexpr int odd_pitch(int n) { return n <= 0 ? 1 : (n | 1); }
+
+__host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
+  Layout L{};
+  constexpr int E = kE;
+  int w = 0;
+  auto take = [&w](int n) { int o = w; w += n; return o; };
+  const int J = s.num_joints, A = s.action.n_actions, K = s.num_reward_terms;
+  L.A = A; L.J = J; L.K = K;
+  int in_word[IF_COUNT] = {};
+  for (int f = 0; f < IF_COUNT; ++f) in_word[f] = take(in_field_ncomp(s, f));
+  L.root_pos = in_word[IF_ROOT_POS] * E; L.quat = in_word[IF_QUAT] * E;
+  L.lin_vel = in_word[IF_LIN_VEL] * E; L.ang_vel = in_word[IF_ANG_VEL] * E;
+  L.jpos = in_word[IF_JPOS] * E; L.jvel = in_word[IF_JVEL] * E; L.jacc = in_word[IF_JACC] * E; L.jtau = in_word[IF_JTAU] * E;
+  L.cair = in_word[IF_CAIR] * E; L.lair = in_word[IF_LAIR] * E; L.ccon = in_word[IF_CCON] * E; L.lcon = in_word[IF_LCON] * E;
+  L.bpos = in_word[IF_BPOS] * E; L.bvel = in_word[IF_BVEL] * E; L.raypos = in_word[IF_RAYPOS] * E;
+  L.cmd = in_word[IF_CMD] * E; L.head = in_word[IF_HEAD] * E; L.tleft = in_word[IF_TLEFT] * E;
+  L.mxy = in_word[IF_MXY] * E; L.myaw = in_word[IF_MYAW] * E; L.eplen = in_word[IF_EPLEN] * E;
+  L.sums = in_word[IF_SUMS] * E; L.cmdu = in_word[IF_CMDU] * E;
+  L.act = in_word[IF_ACT] * E; L.pact = in_word[IF_PACT] * E;
+  L.w_sums = in_word[IF_SUMS];
+  L.w_head = in_word[IF_HEAD]; L.w_tleft = in_word[IF_TLEFT]; L.w_mxy = in_word[IF_MXY]; L.w_myaw = in_word[IF_MYAW];
+  L.w_act = in_word[IF_ACT]; L.w_pact = in_word[IF_PACT];
+  L.ishead = take(1) * E; L.isstand = take(1) * E;
+  // results the step commits at the end: tasks of the same stage still read the old command / episode length
+  { const int wn = take(3); L.cmdn = wn * E; L.w_cmd = wn; }
+  { const int wn = take(1); L.epnew = wn * E; L.w_eplen = wn; }
+  L.w_rew = take(1); L.rew = L.w_rew * E;
+  L.flags = take(1) * E;
+  L.w_stepr = take(K); L.stepr = L.w_stepr * E;
+  L.termv = take(2 * K) * E;
+  L.soa_words = w;
+  int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
+  L.cj = off; off = align_up(off + 5 * J, 32);
+  L.hist_pitch = odd_pitch(s.hist_len * s.num_hist_bodies * 3);
+  L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
+  L.rays_pitch = odd_pitch(s.num_rays);
+  L.rays = off; off = align_up(off + E * L.rays_pitch, 32);
+  L.obs_pitch0 = odd_pitch(s.obs[0].dim); L.obs_pitch1 = odd_pitch(s.obs[1].dim);
+  L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
+  L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+  L.obsu0 = off; off = align_up(off + E * L.obs_pitch0, 32);
+  L.obsu1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+  L.total_words = off;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Work schedule. The compute phase is thread-per-env (lane e of every warp owns env e, so SIMT lanes never
+// duplicate per-env scalar work); the warps of a CTA differ in WHICH tasks they run: one task per reward term
+// (wide body-mask terms split in two halves) and one per observation term (the height scan in 64-column chunks),
+// balanced over the warps by a longest-processing-time greedy on rough instruction costs. constexpr, so a baked
+// spec gets its schedule at compile time and every warp's code is straight-line.
+// ---------------------------------------------------------------------------------------------------
 enum { TK_REWARD = 0, TK_OBS = 1, TK_DONES = 2, TK_COMMAND = 3 };
 
 struct Task {
   uint8_t kind, a, b, owner;   // REWARD: a = term k, b = half (0/1); OBS: a = group, b = term index
   uint16_t lo, hi;             // REWARD: body-index range [lo, hi); OBS: column range within the term
-  uint16_t col0, pad;          // OBS: first column of the term inside the group row
+  uint16_t col0, pad;          // OBS: first column of the term inside the group row; REWARD: pad = 1 for a partial (late) term
 };
 struct Schedule {
-  int n, groups;
+  int n;
   Task t[RL_MAX_TASKS];
-  uint8_t split[RL_MAX_REWARD_TERMS];   // term evaluated as two partial sums (termv[2k] + termv[2k+1])
-  uint8_t late[RL_MAX_REWARD_TERMS];    // weight / sums / step reward applied at finalisation (split terms, is_terminated)
+  uint8_t split[RL_MAX_REWARD_TERMS];   // term evaluated as two partial sums (termv[k][0] + termv[k][1])
+  uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (split terms, is_terminated)
 };
 
 __host__ __device__ constexpr int popc64(uint64_t m) { int n = 0; while (m) { m &= m - 1; ++n; } return n; }
 
 __host__ __device__ constexpr int reward_cost(const RlRewardTerm& t, const RlStepSpec& s, int nbodies) {
   const int J = popc64(t.joint_mask), F = t.n_idx, T = s.hist_len;
-  const int base = 90;  // context (3 quaternion rotations, gate) + weight / sums / step-reward epilogue
   switch (t.type) {
     case RL_REW_JOINT_TORQUES_L2: case RL_REW_JOINT_VEL_L2: case RL_REW_JOINT_ACC_L2: case RL_REW_JOINT_DEVIATION_L1:
-    case RL_REW_JOINT_POWER: case RL_REW_STAND_STILL: return base + 5 * J;
-    case RL_REW_JOINT_POS_LIMITS: case RL_REW_JOINT_VEL_LIMITS: case RL_REW_JOINT_POS_PENALTY: return base + 8 * J;
-    case RL_REW_JOINT_MIRROR: case RL_REW_ACTION_MIRROR: return base + 8 * F;
-    case RL_REW_ACTION_SYNC: return base + 30 * F;
-    case RL_REW_ACTION_RATE_L2: return base + 5 * s.action.n_actions;
-    case RL_REW_UNDESIRED_CONTACTS: case RL_REW_CONTACT_FORCES: return base + nbodies * T * 18;
-    case RL_REW_TRACK_LIN_VEL_XY_EXP: case RL_REW_TRACK_ANG_VEL_Z_EXP: case RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP: return base + 40;
-    case RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP: return base + 230;
-    case RL_REW_FEET_AIR_TIME: case RL_REW_FEET_CONTACT: case RL_REW_FEET_CONTACT_WITHOUT_CMD: return base + 10 * F;
-    case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: return base + 12 * F;
-    case RL_REW_FEET_AIR_TIME_VARIANCE: return base + 40 * F;
-    case RL_REW_FEET_GAIT: return base + 230;
-    case RL_REW_FEET_STUMBLE: return base + 20 * F;
-    case RL_REW_FEET_SLIDE: return base + F * (60 + T * 18);
-    case RL_REW_FEET_HEIGHT: return base + 60 * F;
-    case RL_REW_FEET_HEIGHT_BODY: return base + 130 * F;
-    case RL_REW_FEET_DISTANCE_Y_EXP: case RL_REW_FEET_DISTANCE_XY_EXP: return base + 40 + 60 * F;
-    case RL_REW_WHEEL_VEL_PENALTY: return base + 12 * F;
-    default: return base;
+    case RL_REW_JOINT_POWER: case RL_REW_STAND_STILL: return 30 + 5 * J;
+    case RL_REW_JOINT_POS_LIMITS: case RL_REW_JOINT_VEL_LIMITS: case RL_REW_JOINT_POS_PENALTY: return 40 + 8 * J;
+    case RL_REW_JOINT_MIRROR: case RL_REW_ACTION_MIRROR: return 30 + 8 * F;
+    case RL_REW_ACTION_SYNC: return 40 + 30 * F;
+    case RL_REW_ACTION_RATE_L2: return 30 + 5 * s.action.n_actions;
+    case RL_REW_UNDESIRED_CONTACTS: case RL_REW_CONTACT_FORCES: return 30 + nbodies * T * 18;
+    case RL_REW_TRACK_LIN_VEL_XY_EXP: case RL_REW_TRACK_ANG_VEL_Z_EXP: case RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP: return 70;
+    case RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP: return 260;
+    case RL_REW_FEET_AIR_TIME: case RL_REW_FEET_CONTACT: case RL_REW_FEET_CONTACT_WITHOUT_CMD: return 30 + 10 * F;
+    case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: return 40 + 12 * F;
+    case RL_REW_FEET_AIR_TIME_VARIANCE: return 40 + 40 * F;
+    case RL_REW_FEET_GAIT: return 260;
+    case RL_REW_FEET_STUMBLE: return 30 + 20 * F;
+    case RL_REW_FEET_SLIDE: return 30 + F * (60 + T * 18);
+    case RL_REW_FEET_HEIGHT: return 40 + 60 * F;
+    case RL_REW_FEET_HEIGHT_BODY: return 40 + 130 * F;
+    case RL_REW_FEET_DISTANCE_Y_EXP: case RL_REW_FEET_DISTANCE_XY_EXP: return 80 + 60 * F;
+    case RL_REW_WHEEL_VEL_PENALTY: return 40 + 12 * F;
+    default: return 30;
   }
 }
 
-__host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int groups) {
+__host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw) {
   Schedule sc{};
   int cost[RL_MAX_TASKS] = {};
   int n = 0;
-  sc.t[n] = Task{TK_DONES, 0, 0, 0, 0, 0, 0, 0}; cost[n++] = 120;
+  sc.t[n] = Task{TK_DONES, 0, 0, 0, 0, 0, 0, 0}; cost[n++] = 90;
   {
-    int c = 420;  // command update + heading control; plus its observation columns
+    int c = 380;  // command update + heading control (+ the termination terms again when done envs are skipped)
     for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
       for (int ti = 0; ti < s.obs[g].n_terms; ++ti)
-        if (s.obs[g].terms[ti].type == RL_OBS_GENERATED_COMMANDS) c += 30;
+        if (s.obs[g].terms[ti].type == RL_OBS_GENERATED_COMMANDS) c += 40;   // it also owns these columns
     sc.t[n] = Task{TK_COMMAND, 0, 0, 0, 0, 0, 0, 0}; cost[n++] = c;
   }
   for (int k = 0; k < s.num_reward_terms; ++k) {
@@ -153,38 +260,36 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int gr
       int seen = 0, mid = 0;  // split after the first nb/2 set bits
       for (int b = 0; b < 64; ++b) if ((t.body_mask >> b) & 1ull) { if (++seen == nb / 2) { mid = b + 1; break; } }
       sc.split[k] = 1; sc.late[k] = 1;
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, (uint16_t)mid, 0, 0}; cost[n++] = reward_cost(t, s, nb / 2);
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 1, 0, (uint16_t)mid, 64, 0, 0}; cost[n++] = reward_cost(t, s, nb - nb / 2);
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, (uint16_t)mid, 0, 1}; cost[n++] = reward_cost(t, s, nb / 2);
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 1, 0, (uint16_t)mid, 64, 0, 1}; cost[n++] = reward_cost(t, s, nb - nb / 2);
     } else {
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 0, 0}; cost[n++] = reward_cost(t, s, nb);
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 0, 0}; cost[n++] = 30 + reward_cost(t, s, nb);
     }
   }
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
     int col0 = 0;
     for (int ti = 0; ti < s.obs[g].n_terms; ++ti) {
       const RlObsTerm& o = s.obs[g].terms[ti];
-      const int per_col = 10 + ((o.has_noise && s.obs[g].enable_corruption) ? 24 : 0);
-      const bool needs_ctx = (o.type == RL_OBS_BASE_LIN_VEL || o.type == RL_OBS_BASE_ANG_VEL || o.type == RL_OBS_PROJECTED_GRAVITY);
-      if (o.type != RL_OBS_GENERATED_COMMANDS) {  // those columns belong to the command task
+      const int per_col = 8 + ((o.has_noise && s.obs[g].enable_corruption) ? 24 : 0);
+      if (o.type != RL_OBS_GENERATED_COMMANDS) {
         for (int lo = 0; lo < o.dim; lo += 64) {
           const int hi = (lo + 64 < o.dim) ? lo + 64 : o.dim;
           sc.t[n] = Task{TK_OBS, (uint8_t)g, (uint8_t)ti, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)col0, 0};
-          cost[n++] = 20 + (needs_ctx ? 60 : 0) + per_col * (hi - lo);
+          cost[n++] = 20 + per_col * (hi - lo);
         }
       }
       col0 += o.dim;
     }
   }
   sc.n = n;
-  sc.groups = groups;
-  // longest-processing-time greedy over the groups
-  int load[64] = {};
+  // longest-processing-time greedy over the warps
+  int load[32] = {};
   bool done[RL_MAX_TASKS] = {};
   for (int it = 0; it < n; ++it) {
     int best = -1;
     for (int i = 0; i < n; ++i) if (!done[i] && (best < 0 || cost[i] > cost[best])) best = i;
     int w = 0;
-    for (int j = 1; j < groups; ++j) if (load[j] < load[w]) w = j;
+    for (int j = 1; j < nw; ++j) if (load[j] < load[w]) w = j;
     sc.t[best].owner = (uint8_t)w; load[w] += cost[best]; done[best] = true;
   }
   return sc;
@@ -195,29 +300,83 @@ struct KArgs {
   int slot;
   uint32_t phases;
   int has_ids;
-  int groups, tiles_per_cta, n_blocks;   // grid = n_blocks * groups; CTA = (block qb, group g), warp w -> tile qb*tiles_per_cta + w
   FieldD in[IF_COUNT];
-  FieldD is_heading, is_standing;        // uint8
+  FieldD outf[OF_COUNT];
+  uint32_t in_mask, out_mask;
+  uint32_t in_vec4, out_vec4;     // fields whose rows may move 4 envs at a time (SoA, 16-byte aligned)
+  const uint32_t* in_rows;  int n_in_rows;
+  const uint32_t* out_rows; int n_out_rows;
+  // AoS spans (row-contiguous per env) and byte fields
+  FieldD hist, rays;
+  FieldD is_heading, is_standing;               // uint8
   RlStepOut out;
   RlRandom rnd;
   const int32_t* env_ids;
   const int32_t* n_env_ids;
+  Layout L;                // generic kernel only; baked kernels compute theirs at compile time
   const Schedule* sched;   // device copy (generic kernel); baked kernels carry theirs as constexpr data
-  // scratch owned by the context
-  float* termv;            // [2K][Ncap] weighted term values (raw partial sums for late terms)
-  float* cmd_new;          // [3][Ncap]  updated command, committed at finalisation (rewards read the old one)
-  int Ncap;
-  unsigned int* block_ticket;   // [n_blocks] CTAs of a tile block that have finished
-  unsigned int* final_ticket;   // [1] tile blocks that have been finalised
-  uint32_t* tile_mask;          // [tiles] done bits of each tile, for the ordered compaction
-  float* log_partials;          // [n_blocks][RL_LOG_STRIDE]
+  unsigned int* ticket;
+  uint32_t* cta_mask;
+  float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions
   int use_pdl;
-  long long* dbg;
+  long long* dbg;        // optional [grid][RL_DEBUG_STRIDE] clock64 stamps (rl_ctx_set_debug_buffer)
   // single-term evaluation (rl_term_eval)
   const RlRewardTerm* adhoc;
   const uint8_t* ext_terminated;
   float* term_out;
 };
+
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copies (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Ampere-style async copies (SASS LDGSTS): global -> shared without a register round trip, fire and forget
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -324,29 +483,18 @@ __device__ __forceinline__ void static_for(std::integer_sequence<int, Is...>, F&
 
 struct DynPolicy {
   static constexpr bool kStatic = false;
+  __device__ __forceinline__ static Layout layout(const KArgs& a) { return a.L; }
   __device__ __forceinline__ static Scalars scalars(const KArgs& a) { return scalars_of(c_spec[a.slot]); }
   __device__ __forceinline__ static const RlCommandCfg& command(const KArgs& a) { return c_spec[a.slot].command; }
-  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, int g, F&& f) {
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
     const int n = a.sched->n;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       const Task tk = a.sched->t[i];
-      if (tk.owner != g) continue;
-      if (tk.kind == TK_REWARD) f(tk, S.rewards[tk.a], S.obs[0].terms[0], false);
-      else f(tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0);
+      if (tk.kind == TK_OBS) f(tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0);
+      else f(tk, S.rewards[tk.a], S.obs[0].terms[0], false);
     }
-  }
-  // f(term, k, split, late): split = evaluated as two partial sums; late = finished in stage 2
-  template <int G, class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
-    const RlStepSpec& S = c_spec[a.slot];
-#pragma unroll 1
-    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k, a.sched->split[k] != 0, a.sched->late[k] != 0);
-  }
-  template <class F> __device__ __forceinline__ static void for_dones(const KArgs& a, F&& f) {
-    const RlStepSpec& S = c_spec[a.slot];
-#pragma unroll 1
-    for (int d = 0; d < S.num_done_terms; ++d) f(S.dones[d], d);
   }
   // the command-dependent observation terms: f(term, group, term index, first column, corruption on)
   template <class F> __device__ __forceinline__ static void for_cmd_obs(const KArgs& a, F&& f) {
@@ -361,6 +509,17 @@ struct DynPolicy {
       }
     }
   }
+  // f(term, k, split, late): split = evaluated as two partial sums; late = finished in stage 2
+  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+#pragma unroll 1
+    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k, a.sched->split[k] != 0, a.sched->late[k] != 0);
+  }
+  template <class F> __device__ __forceinline__ static void for_dones(const KArgs& a, F&& f) {
+    const RlStepSpec& S = c_spec[a.slot];
+#pragma unroll 1
+    for (int d = 0; d < S.num_done_terms; ++d) f(S.dones[d], d);
+  }
   template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
     f(S.default_joint_pos[j], S.default_joint_vel[j], S.soft_pos_limit_lo[j], S.soft_pos_limit_hi[j], S.soft_vel_limit[j]);
@@ -371,6 +530,11 @@ struct DynPolicy {
 template <class B>
 struct StaticPolicy {
   static constexpr bool kStatic = true;
+  using Baked = B;
+  __device__ __forceinline__ static constexpr Layout layout(const KArgs&) {
+    constexpr Layout L = make_layout(B::spec);
+    return L;
+  }
   __device__ __forceinline__ static constexpr Scalars scalars(const KArgs&) {
     constexpr Scalars s = scalars_of(B::spec);
     return s;
@@ -379,45 +543,15 @@ struct StaticPolicy {
     constexpr RlCommandCfg c = B::spec.command;
     return c;
   }
-  template <int G> struct Sched { static constexpr Schedule value = make_schedule(B::spec, G); };
-  // all tasks of group GI, in schedule order
-  template <int G, int GI, class F> __device__ __forceinline__ static void group_tasks(F&& f) {
-    static_for(std::make_integer_sequence<int, Sched<G>::value.n>{}, [&](auto ic) {
+  template <int NW> struct Sched { static constexpr Schedule value = make_schedule(B::spec, NW); };
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, Sched<NW>::value.n>{}, [&](auto ic) {
       constexpr int i = decltype(ic)::value;
-      constexpr Task tk = Sched<G>::value.t[i];
-      if constexpr (tk.owner == GI) {
-        static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
-        static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
-        constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
-        f(tk, rt, ot, corrupt);
-      }
-    });
-  }
-  // binary search on the (runtime) group id: log2(G) branches straight to the group's contiguous code
-  template <int G, int LO, int HI, class F> __device__ __forceinline__ static void dispatch_group(int g, F&& f) {
-    if constexpr (HI - LO == 1) {
-      group_tasks<G, LO>(f);
-    } else {
-      constexpr int MID = (LO + HI) / 2;
-      if (g < MID) dispatch_group<G, LO, MID>(g, f); else dispatch_group<G, MID, HI>(g, f);
-    }
-  }
-  template <int G, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, int g, F&& f) {
-    dispatch_group<G, 0, G>(g, f);
-  }
-  template <int G, class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
-    static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      static constexpr RlRewardTerm t = B::spec.rewards[k];  // static: runtime-indexed lists read it in place
-      constexpr bool split = Sched<G>::value.split[k] != 0, late = Sched<G>::value.late[k] != 0;
-      f(t, k, split, late);
-    });
-  }
-  template <class F> __device__ __forceinline__ static void for_dones(const KArgs&, F&& f) {
-    static_for(std::make_integer_sequence<int, B::spec.num_done_terms>{}, [&](auto dc) {
-      constexpr int d = decltype(dc)::value;
-      static constexpr RlDoneTerm t = B::spec.dones[d];
-      f(t, d);
+      constexpr Task tk = Sched<NW>::value.t[i];
+      static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
+      static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
+      constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+      f(tk, rt, ot, corrupt);
     });
   }
   template <class F> __device__ __forceinline__ static void for_cmd_obs(const KArgs&, F&& f) {
@@ -429,6 +563,24 @@ struct StaticPolicy {
         f(t, g, ti, col0, B::spec.obs[g].enable_corruption != 0);
       }
     });
+  }
+  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      static constexpr RlRewardTerm t = B::spec.rewards[k];  // static: runtime-indexed lists read it in place
+      constexpr bool split = Sched<NW>::value.split[k] != 0, late = Sched<NW>::value.late[k] != 0;
+      f(t, k, split, late);
+    });
+  }
+  template <class F> __device__ __forceinline__ static void for_dones(const KArgs&, F&& f) {
+    static_for(std::make_integer_sequence<int, B::spec.num_done_terms>{}, [&](auto dc) {
+      constexpr int d = decltype(dc)::value;
+      static constexpr RlDoneTerm t = B::spec.dones[d];
+      f(t, d);
+    });
+  }
+  template <class F> __device__ __forceinline__ static void for_joint_consts(const KArgs& a, int j, F&& f) {
+    DynPolicy::for_joint_consts(a, j, f);  // lane-varying joint index: staged from __constant__ like the generic path
   }
   __device__ __forceinline__ static constexpr int obs_dim(const KArgs&, int g) { return g == 0 ? B::spec.obs[0].dim : B::spec.obs[1].dim; }
 };
@@ -451,37 +603,26 @@ struct EnvCtx {
   bool terminated;
 };
 
-// Thread-per-env operand access: field f, component c of this lane's env, straight from global memory. For the
-// SoA [C][N] layout consecutive lanes read consecutive addresses (one 128-byte line per warp instruction); any
-// other strides work too, slower.
-__device__ __forceinline__ float ld_field(const FieldD& fd, long long env, int c) {
-  return static_cast<const float*>(fd.ptr)[env * fd.es + (long long)c * fd.cs];
-}
-__device__ __forceinline__ float ld_field_ro(const FieldD& fd, long long env, int c) {
-  return __ldg(static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
-}
-// Every task-phase read goes through ld.global.nc: within one launch no address is re-read after it was written
-// (episode sums / metrics are read once by their only writer; the command and the episode length are rewritten
-// at finalisation only, after every reader of the tile block is done), so the compiler may hoist and batch ALL
-// loads of a group above the stores of its earlier tasks - one memory round trip per CTA instead of one per task.
-#define LDF(f, c) ld_field_ro(a.in[(f)], env, (c))
-#define JC(arr, j) CS.arr[(j)]   // per-joint constants: lane-uniform index -> constant-bank broadcast
+#define LOBS(g) ((g) == 0 ? L.obs0 : L.obs1)
+#define LOBSP(g) ((g) == 0 ? L.obs_pitch0 : L.obs_pitch1)
+#define LOBSU(g) ((g) == 0 ? L.obsu0 : L.obsu1)
+#define SMF(off, c) sm[(off) + (c) * kE + e]
+#define CJ(k, j) sm[L.cj + (k) * L.J + (j)]
 
-__device__ __forceinline__ bool first_contact(const KArgs& a, const Scalars& S, long long env, int b) {
-  const float t = LDF(IF_CCON, b);
+__device__ __forceinline__ bool first_contact(const float* sm, const Layout& L, const Scalars& S, int e, int b) {
+  const float t = SMF(L.ccon, b);
   return (t > 0.f) && (t < (S.step_dt + S.contact_time_abs_tol));
 }
-__device__ __forceinline__ V3 body_vec(const KArgs& a, int f, long long env, int b) {
-  return V3{LDF(f, 3 * b + 0), LDF(f, 3 * b + 1), LDF(f, 3 * b + 2)};
+__device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
+  return V3{SMF(off, 3 * b + 0), SMF(off, 3 * b + 1), SMF(off, 3 * b + 2)};
 }
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
-__device__ __forceinline__ float hist_max_norm(const KArgs& a, long long env, int T, int B, int b) {
+__device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int b) {
   float m = 0.f;
-  _Pragma("unroll")
+  _Pragma("unroll 1")
   for (int t = 0; t < T; ++t) {
-    const int i = (t * B + b) * 3;
-    const float fx = LDF(IF_HIST, i), fy = LDF(IF_HIST, i + 1), fz = LDF(IF_HIST, i + 2);
-    const float n = sqrtf((fx * fx + fy * fy) + fz * fz);
+    const float* f = h + (t * B + b) * 3;
+    const float n = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
     m = (t == 0) ? n : fmaxf(m, n);
   }
   return m;
@@ -489,9 +630,10 @@ __device__ __forceinline__ float hist_max_norm(const KArgs& a, long long env, in
 
 // One reward term for env e: raw value (no weight, no dt). [lo, hi) restricts body-mask terms to a body-index
 // range (the two halves of a split term add up).
-__device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalars& S, const RlStepSpec& CS, const KArgs& a,
-                                             const long long env, const EnvCtx& c, const int lo, const int hi) {
+__device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalars& S, const Layout& L, const float* sm,
+                                             const int e, const EnvCtx& c, const int lo, const int hi) {
   const int J = S.num_joints;
+  const float* h = sm + L.hist + e * L.hist_pitch;
   switch (t.type) {
     case RL_REW_IS_TERMINATED: return c.terminated ? 1.f : 0.f;
     case RL_REW_LIN_VEL_Z_L2: return (c.vb.z * c.vb.z) * c.gate;
@@ -508,113 +650,114 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_JOINT_TORQUES_L2:
     case RL_REW_JOINT_VEL_L2:
     case RL_REW_JOINT_ACC_L2: {
-      const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? IF_JTAU : (t.type == RL_REW_JOINT_VEL_L2 ? IF_JVEL : IF_JACC);
+      const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? L.jtau : (t.type == RL_REW_JOINT_VEL_L2 ? L.jvel : L.jacc);
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) { const float v = LDF(off, j); s += v * v; }
+        if ((t.joint_mask >> j) & 1ull) { const float v = SMF(off, j); s += v * v; }
       return s;
     }
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JPOS, j) - JC(default_joint_pos, j));
+        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       return s;
     }
     case RL_REW_JOINT_POS_LIMITS: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) {
-          const float q = LDF(IF_JPOS, j);
-          float o = -fminf(q - JC(soft_pos_limit_lo, j), 0.f);
-          o += fmaxf(q - JC(soft_pos_limit_hi, j), 0.f);
+          const float q = SMF(L.jpos, j);
+          float o = -fminf(q - CJ(2, j), 0.f);
+          o += fmaxf(q - CJ(3, j), 0.f);
           s += o;
         }
       return s;
     }
     case RL_REW_JOINT_VEL_LIMITS: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(LDF(IF_JVEL, j)) - JC(soft_vel_limit, j) * t.p[0], 0.f, 1.f);
+        if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
       return s;
     }
     case RL_REW_JOINT_POWER: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JVEL, j) * LDF(IF_JTAU, j));
+        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jvel, j) * SMF(L.jtau, j));
       return s;
     }
     case RL_REW_STAND_STILL: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) s += fabsf(LDF(IF_JPOS, j) - JC(default_joint_pos, j));
+        if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
       return s * c.gate;
     }
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int j = 0; j < J; ++j)
-        if ((t.joint_mask >> j) & 1ull) { const float d = LDF(IF_JPOS, j) - JC(default_joint_pos, j); s += d * d; }
+        if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - CJ(0, j); s += d * d; }
       const float running = sqrtf(s);
       const bool moving = (c.cmd_norm > t.p[2]) || (c.vxy_norm > t.p[1]);
       return (moving ? running : t.p[0] * running) * c.gate;
     }
     case RL_REW_JOINT_MIRROR: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float d = LDF(IF_JPOS, t.idx_a[i]) - LDF(IF_JPOS, t.idx_b[i]);
+        const float d = SMF(L.jpos, t.idx_a[i]) - SMF(L.jpos, t.idx_b[i]);
         s += d * d;
       }
       return (s * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float d = fabsf(LDF(IF_ACT, t.idx_a[i])) - fabsf(LDF(IF_ACT, t.idx_b[i]));
+        const float d = fabsf(SMF(L.act, t.idx_a[i])) - fabsf(SMF(L.act, t.idx_b[i]));
         s += d * d;
       }
       return (s * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_SYNC: {
       float r = 0.f;
+      _Pragma("unroll 1")
       for (int g = 0; g < t.n_idx; ++g) {
         const int start = t.idx_b[g], n = t.idx_c[g];
         if (n < 2) continue;
         float m = 0.f;
-        for (int i = 0; i < n; ++i) m += fabsf(LDF(IF_ACT, t.idx_a[start + i]));
+        for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, t.idx_a[start + i]));
         m = m / (float)n;
         float v = 0.f;
-        for (int i = 0; i < n; ++i) { const float d = fabsf(LDF(IF_ACT, t.idx_a[start + i])) - m; v += d * d; }
+        for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, t.idx_a[start + i])) - m; v += d * d; }
         r += v / (float)n;
       }
       return (r * t.p[0]) * c.gate;
     }
     case RL_REW_ACTION_RATE_L2: {
       float s = 0.f;
-      _Pragma("unroll")
-      for (int ai = 0; ai < S.n_actions; ++ai) { const float d = LDF(IF_ACT, ai) - LDF(IF_PACT, ai); s += d * d; }
+      _Pragma("unroll 1")
+      for (int a = 0; a < S.n_actions; ++a) { const float d = SMF(L.act, a) - SMF(L.pact, a); s += d * d; }
       return s;
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
-        if (((t.body_mask >> b) & 1ull) && (hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
+        if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
       return s * c.gate;   // gate distributes over the two halves of a split term
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
-        if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
+        if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
       return s;
     }
     case RL_REW_TRACK_LIN_VEL_XY_EXP: {
@@ -641,25 +784,25 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
-        s += (LDF(IF_LAIR, b) - t.p[0]) * (first_contact(a, S, env, b) ? 1.f : 0.f);
+        s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
       }
       s *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return s * c.gate;
     }
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
-      _Pragma("unroll")
-      for (int i = 0; i < t.n_idx; ++i) n_contact += (LDF(IF_CCON, t.idx_a[i]) > 0.f) ? 1 : 0;
+      _Pragma("unroll 1")
+      for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, t.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_a[i];
-        const float ct = LDF(IF_CCON, b);
-        const float mode = (ct > 0.f) ? ct : LDF(IF_CAIR, b);
+        const float ct = SMF(L.ccon, b);
+        const float mode = (ct > 0.f) ? ct : SMF(L.cair, b);
         r = fminf(r, single ? mode : 0.f);
       }
       r = fminf(r, t.p[0]);
@@ -669,12 +812,13 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_AIR_TIME_VARIANCE: {
       // torch.var (unbiased) is a Welford reduction on CPU; keep the same update order.
       float r = 0.f;
+      _Pragma("unroll 1")
       for (int which = 0; which < 2; ++which) {
-        const int off = which == 0 ? IF_LAIR : IF_LCON;
+        const int off = which == 0 ? L.lair : L.lcon;
         float mean = 0.f, m2 = 0.f;
-        _Pragma("unroll")
+        _Pragma("unroll 1")
         for (int i = 0; i < t.n_idx; ++i) {
-          const float x = fminf(LDF(off, t.idx_a[i]), 0.5f);
+          const float x = fminf(SMF(off, t.idx_a[i]), 0.5f);
           const float d = x - mean;
           mean += d / (float)(i + 1);
           m2 += d * (x - mean);
@@ -686,14 +830,14 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_GAIT: {
       const int f00 = t.idx_a[0], f01 = t.idx_a[1], f10 = t.idx_a[2], f11 = t.idx_a[3];
       const float me2 = t.p[1], sd = t.p[0];
-      auto sync = [&](int fa, int fb) {
-        const float da = LDF(IF_CAIR, fa) - LDF(IF_CAIR, fb);
-        const float dc = LDF(IF_CCON, fa) - LDF(IF_CCON, fb);
+      auto sync = [&](int a, int b) {
+        const float da = SMF(L.cair, a) - SMF(L.cair, b);
+        const float dc = SMF(L.ccon, a) - SMF(L.ccon, b);
         return rl_expf(-(fminf(da * da, me2) + fminf(dc * dc, me2)) / sd);
       };
-      auto async = [&](int fa, int fb) {
-        const float d0 = LDF(IF_CAIR, fa) - LDF(IF_CCON, fb);
-        const float d1 = LDF(IF_CCON, fa) - LDF(IF_CAIR, fb);
+      auto async = [&](int a, int b) {
+        const float d0 = SMF(L.cair, a) - SMF(L.ccon, b);
+        const float d1 = SMF(L.ccon, a) - SMF(L.cair, b);
         return rl_expf(-(fminf(d0 * d0, me2) + fminf(d1 * d1, me2)) / sd);
       };
       const float sync_r = sync(f00, f01) * sync(f10, f11);
@@ -703,47 +847,47 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
-      _Pragma("unroll")
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact(a, S, env, t.idx_a[i]) ? 1 : 0;
+      _Pragma("unroll 1")
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return r * c.gate;
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
-      _Pragma("unroll")
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact(a, S, env, t.idx_a[i]) ? 1 : 0;
+      _Pragma("unroll 1")
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
       return r * c.gate;
     }
     case RL_REW_FEET_STUMBLE: {
       bool any = false;   // t = 0 is the newest history sample = net_forces_w
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = t.idx_c[i];
-        const float fx = LDF(IF_HIST, 3 * b + 0), fy = LDF(IF_HIST, 3 * b + 1), fz = LDF(IF_HIST, 3 * b + 2);
+        const float fx = h[3 * b + 0], fy = h[3 * b + 1], fz = h[3 * b + 2];
         any = any || (sqrtf(fx * fx + fy * fy) > 4.f * fabsf(fz));
       }
       return (any ? 1.f : 0.f) * c.gate;
     }
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 vw = body_vec(a, IF_BVEL, env, t.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float lat = sqrtf(vb.x * vb.x + vb.y * vb.y);
-        s += lat * ((hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, t.idx_c[i]) > 1.0f) ? 1.f : 0.f);
+        s += lat * ((hist_max_norm(h, S.hist_len, S.num_hist_bodies, t.idx_c[i]) > 1.0f) ? 1.f : 0.f);
       }
       return s * c.gate;
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 p = body_vec(a, IF_BPOS, env, t.idx_b[i]);
-        const V3 v = body_vec(a, IF_BVEL, env, t.idx_b[i]);
+        const V3 p = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 v = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const float d = p.z - t.p[0];
         s += (d * d) * rl_tanhf(t.p[1] * sqrtf(v.x * v.x + v.y * v.y));
       }
@@ -752,10 +896,10 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec(a, IF_BPOS, env, t.idx_b[i]);
-        const V3 vw = body_vec(a, IF_BVEL, env, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float d = pb.z - t.p[0];
@@ -766,9 +910,9 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_DISTANCE_Y_EXP: {
       float s = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec(a, IF_BPOS, env, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float want = (t.p[0] / 2.f) * ((i % 2 == 0) ? 1.f : -1.f);
         const float d = want - pb.y;
@@ -778,8 +922,9 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_FEET_DISTANCE_XY_EXP: {
       float s = 0.f;
+      _Pragma("unroll 1")
       for (int i = 0; i < 4; ++i) {
-        const V3 pw = body_vec(a, IF_BPOS, env, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float wx = (i < 2) ? (t.p[1] / 2.f) : (-t.p[1] / 2.f);
         const float wy = (i % 2 == 0) ? (t.p[0] / 2.f) : (-t.p[0] / 2.f);
@@ -790,10 +935,10 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     }
     case RL_REW_WHEEL_VEL_PENALTY: {
       float run = 0.f, stand = 0.f;
-      _Pragma("unroll")
+      _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float jv = fabsf(LDF(IF_JVEL, t.idx_b[i]));
-        const float ta = LDF(IF_CAIR, t.idx_a[i]);
+        const float jv = fabsf(SMF(L.jvel, t.idx_b[i]));
+        const float ta = SMF(L.cair, t.idx_a[i]);
         const bool first_air = (ta > 0.f) && (ta < (S.step_dt + S.contact_time_abs_tol));
         run += (first_air ? 1.f : 0.f) * jv;
         stand += jv;
@@ -805,177 +950,346 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
   }
 }
 
-__device__ __forceinline__ EnvCtx make_ctx(const KArgs& a, const long long env) {
+__device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int e) {
   EnvCtx c;
-  c.qw = LDF(IF_QUAT, 0);
-  c.q = V3{LDF(IF_QUAT, 1), LDF(IF_QUAT, 2), LDF(IF_QUAT, 3)};
-  c.pos = V3{LDF(IF_ROOT_POS, 0), LDF(IF_ROOT_POS, 1), LDF(IF_ROOT_POS, 2)};
-  c.vw = V3{LDF(IF_LIN_VEL, 0), LDF(IF_LIN_VEL, 1), LDF(IF_LIN_VEL, 2)};
-  c.ww = V3{LDF(IF_ANG_VEL, 0), LDF(IF_ANG_VEL, 1), LDF(IF_ANG_VEL, 2)};
+  c.qw = SMF(L.quat, 0);
+  c.q = V3{SMF(L.quat, 1), SMF(L.quat, 2), SMF(L.quat, 3)};
+  c.pos = V3{SMF(L.root_pos, 0), SMF(L.root_pos, 1), SMF(L.root_pos, 2)};
+  c.vw = V3{SMF(L.lin_vel, 0), SMF(L.lin_vel, 1), SMF(L.lin_vel, 2)};
+  c.ww = V3{SMF(L.ang_vel, 0), SMF(L.ang_vel, 1), SMF(L.ang_vel, 2)};
   c.g = quat_apply_inverse(c.qw, c.q, V3{0.f, 0.f, -1.f});
   c.vb = quat_apply_inverse(c.qw, c.q, c.vw);
   c.wb = quat_apply_inverse(c.qw, c.q, c.ww);
   c.gate = clampf(-c.g.z, 0.f, 0.7f) / 0.7f;
-  c.c0 = LDF(IF_CMD, 0); c.c1 = LDF(IF_CMD, 1); c.c2 = LDF(IF_CMD, 2);
+  c.c0 = SMF(L.cmd, 0); c.c1 = SMF(L.cmd, 1); c.c2 = SMF(L.cmd, 2);
   c.cmd_norm = sqrtf((c.c0 * c.c0 + c.c1 * c.c1) + c.c2 * c.c2);
   c.vxy_norm = sqrtf(c.vb.x * c.vb.x + c.vb.y * c.vb.y);
   c.terminated = false;
   return c;
 }
 
-
-
-// ---------------------------------------------------------------------------------------------------
-// Stores of per-env results (thread-per-env; SoA targets coalesce)
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_field(const FieldD& fd, long long env, int c, float v) {
-  static_cast<float*>(const_cast<void*>(fd.ptr))[env * fd.es + (long long)c * fd.cs] = v;
-}
-#define STF(f, c, v) st_field(a.in[(f)], env, (c), (v))
-__device__ __forceinline__ int ld_u8(const FieldD& fd, long long env) {
-  return (int)static_cast<const uint8_t*>(fd.ptr)[env * fd.es];
-}
-__device__ __forceinline__ void st_u8(const FieldD& fd, long long env, int v) {
-  static_cast<uint8_t*>(const_cast<void*>(fd.ptr))[env * fd.es] = (uint8_t)v;
-}
-__device__ __forceinline__ int ld_eplen(const KArgs& a, long long env) {
-  return static_cast<const int32_t*>(a.in[IF_EPLEN].ptr)[env * a.in[IF_EPLEN].es];
-}
-
-// Termination terms of one env: TerminationManager.compute [IL]. bits | terminated << 8 | truncated << 9
-template <class P>
-__device__ __forceinline__ uint32_t eval_dones(const KArgs& a, const Scalars& S, const long long env, const EnvCtx& c) {
-  uint32_t bits = 0, term = 0, trunc = 0;
-  const int eplen = ld_eplen(a, env) + 1;   // episode_length_buf += 1 precedes the termination terms
-  P::for_dones(a, [&](const RlDoneTerm& t, int d) {
-    int fired = 0;
-    if (t.type == RL_DONE_TIME_OUT) {
-      fired = eplen >= S.max_episode_length;
-    } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
-      fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
-    } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
-      _Pragma("unroll")
-      for (int b = 0; b < S.num_hist_bodies; ++b)
-        if (((t.body_mask >> b) & 1ull) && (hist_max_norm(a, env, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
+// CommandTerm.compute [IL] + UniformThresholdVelocityCommand (V/mdp/commands.py:43-85; the "pits" branch
+// is identically off for the in-scope terrains, V/mdp/utils.py:27-28). The new command goes to the cmdn slot
+// (other warps still read the old one in this stage); timers, flags and metrics are updated in place.
+__device__ __forceinline__ void command_update(float* sm, const Layout& L, const Scalars& S, const RlCommandCfg& cc,
+                                               const KArgs& a, const RandState rs, int e, long long env,
+                                               const EnvCtx& c, bool write) {
+  float c0 = c.c0, c1 = c.c1, c2 = c.c2;
+  // metrics use the command and state of this step
+  {
+    const float dx = c0 - c.vb.x, dy = c1 - c.vb.y;
+    const float exy = sqrtf(dx * dx + dy * dy) / cc.max_command_step;
+    const float eyaw = fabsf(c2 - c.wb.z) / cc.max_command_step;
+    if (write) { SMF(L.mxy, 0) = SMF(L.mxy, 0) + exy; SMF(L.myaw, 0) = SMF(L.myaw, 0) + eyaw; }
+  }
+  float tleft = SMF(L.tleft, 0) - S.step_dt;
+  float head = SMF(L.head, 0);
+  int ishead = __float_as_int(SMF(L.ishead, 0));
+  int isstand = __float_as_int(SMF(L.isstand, 0));
+  if (tleft <= 0.f) {
+    float u[RL_NUM_CMD_UNIFORMS];
+    if (a.rnd.cmd_uniforms != nullptr) {
+#pragma unroll
+      for (int i = 0; i < RL_NUM_CMD_UNIFORMS; ++i) u[i] = SMF(L.cmdu, i);
+    } else {
+      const uint4 r0 = rl_philox(rs, env, RL_STREAM_COMMAND, 0), r1 = rl_philox(rs, env, RL_STREAM_COMMAND, 1);
+      u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+      u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
     }
-    if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
-  });
-  return bits | (term << 8) | (trunc << 9);
+    tleft = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
+    c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
+    c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
+    c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
+    if (cc.heading_command) {
+      head = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
+      ishead = (u[5] <= cc.rel_heading_envs) ? 1 : 0;
+    }
+    isstand = (u[6] <= cc.rel_standing_envs) ? 1 : 0;
+    const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+    c0 *= keep; c1 *= keep;
+  }
+  if (cc.heading_command && ishead) {
+    const V3 fwd = quat_apply(c.qw, c.q, V3{1.f, 0.f, 0.f});
+    const float heading = rl_atan2f(fwd.y, fwd.x);
+    const float err = wrap_to_pi(head - heading);
+    c2 = clampf(cc.heading_control_stiffness * err, cc.ang_vel_z_lo, cc.ang_vel_z_hi);
+  }
+  if (isstand) { c0 = 0.f; c1 = 0.f; c2 = 0.f; }
+  if (!write) { c0 = c.c0; c1 = c.c1; c2 = c.c2; }
+  SMF(L.cmdn, 0) = c0; SMF(L.cmdn, 1) = c1; SMF(L.cmdn, 2) = c2;
+  if (write) {
+    SMF(L.tleft, 0) = tleft; SMF(L.head, 0) = head;
+    SMF(L.ishead, 0) = __int_as_float(ishead); SMF(L.isstand, 0) = __int_as_float(isstand);
+  }
 }
 
-// Columns [lo, hi) of one observation term for the warp's 32 envs: ObservationManager.compute_group [IL]
-// (clone -> +noise -> clip -> scale). Lane e computes its env's values into a [32][33] shared-memory tile
-// (conflict-free both ways), then the warp writes row segments of the [N, D] observation rows: consecutive
-// lanes hit consecutive addresses instead of 32 partial sectors per store.
-__device__ __forceinline__ void obs_task(const KArgs& a, const Scalars& S, const RlStepSpec& CS, const RlObsTerm& t,
-                                         const bool corrupt, const RandState rs, const int g, const int ti,
-                                         const int col0, const int lo, const int hi, const long long env,
-                                         const bool valid, const EnvCtx& c, const float* cmd3, const int eplen_eff,
-                                         const bool zero_action, float (*tile)[33]) {
-  const int lane = threadIdx.x & 31;
-  float* const obs = a.out.obs[g];
-  const long long pitch = a.out.obs_pitch[g];
-  const int D = g == 0 ? CS.obs[0].dim : CS.obs[1].dim;
-  const float* urow = a.rnd.obs_uniforms[g] ? a.rnd.obs_uniforms[g] + env * D + col0 : nullptr;
+// Columns [lo, hi) of one observation term for env e: ObservationManager.compute_group [IL]
+// (clone -> +noise -> clip -> scale), written into the group's shared-memory row.
+__device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scalars& S, const RlObsTerm& t,
+                                         const bool corrupt, const KArgs& a, const RandState rs, const int g,
+                                         const int ti, const int col0, const int lo, const int hi, const int e,
+                                         const long long env, const EnvCtx& c, const int eplen_now) {
+  float* row = sm + LOBS(g) + e * LOBSP(g);
+  const float* urow = sm + LOBSU(g) + e * LOBSP(g);
+  const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
   const bool noisy = t.has_noise && corrupt;
-  for (int c0 = lo; c0 < hi; c0 += 32) {
-    const int nc = min(32, hi - c0);
-    _Pragma("unroll")
-    for (int q = 0; q < 8; ++q) {
-      if (q * 4 >= nc) break;
-      float u4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (noisy && urow == nullptr) {
-        const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)((c0 >> 2) + q));
-        u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
-      }
+  _Pragma("unroll 1")
+  for (int qd = lo / 4; qd * 4 < hi; ++qd) {
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noisy && !ext_u) {
+      const uint4 r = rl_philox(rs, env, RL_STREAM_OBS + g * RL_MAX_OBS_TERMS + ti, (uint32_t)qd);
+      u4[0] = u01(r.x); u4[1] = u01(r.y); u4[2] = u01(r.z); u4[3] = u01(r.w);
+    }
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        const int jj = q * 4 + r4;
-        const int col = c0 + jj;
-        if (jj >= nc) break;
-        float v;
-        switch (t.type) {
-          case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
-          case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
-          case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
-          case RL_OBS_GENERATED_COMMANDS: v = cmd3[col]; break;
-          case RL_OBS_JOINT_POS_REL: v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]); break;
-          case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
-            v = LDF(IF_JPOS, t.ids[col]) - JC(default_joint_pos, t.ids[col]);
-            if ((t.zero_mask >> col) & 1ull) v = 0.f;
-            break;
-          case RL_OBS_JOINT_VEL_REL: v = LDF(IF_JVEL, t.ids[col]) - JC(default_joint_vel, t.ids[col]); break;
-          case RL_OBS_LAST_ACTION: v = zero_action ? 0.f : LDF(IF_ACT, col); break;
-          case RL_OBS_HEIGHT_SCAN: v = (LDF(IF_RAYPOS, 0) - LDF(IF_RAYS, col)) - t.p[0]; break;
-          case RL_OBS_PHASE: {
-            const float ph = ((float)eplen_eff * S.step_dt) / t.p[0];
-            v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
-            break;
+    for (int r4 = 0; r4 < 4; ++r4) {
+      const int col = qd * 4 + r4;
+      if (col >= hi) break;
+      float v;
+      switch (t.type) {
+        case RL_OBS_BASE_LIN_VEL: v = col == 0 ? c.vb.x : (col == 1 ? c.vb.y : c.vb.z); break;
+        case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
+        case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
+        case RL_OBS_GENERATED_COMMANDS: v = SMF(L.cmdn, col); break;
+        case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]); break;
+        case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
+          v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]);
+          if ((t.zero_mask >> col) & 1ull) v = 0.f;
+          break;
+        case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - CJ(1, t.ids[col]); break;
+        case RL_OBS_LAST_ACTION: v = SMF(L.act, col); break;
+        case RL_OBS_HEIGHT_SCAN: v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0]; break;
+        case RL_OBS_PHASE: {
+          const float ph = ((float)eplen_now * S.step_dt) / t.p[0];
+          v = col == 0 ? rl_sinf((2.f * RL_PI_F) * ph) : rl_cosf((2.f * RL_PI_F) * ph);
+          break;
+        }
+        default: v = 0.f;
+      }
+      if (noisy) {
+        const float u = ext_u ? urow[col0 + col] : u4[r4];
+        v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
+      }
+      if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
+      if (t.has_scale) v = v * t.scale;
+      row[col0 + col] = v;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Tile movers (one code copy each)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_rows_async(float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                                bool full, int tid, int nthreads) {
+  constexpr int NV = kE / 4;
+  const int total = a.n_in_rows * NV;
+#pragma unroll 2
+  for (int i = tid; i < total; i += nthreads) {
+    const uint32_t meta = __ldg(a.in_rows + i / NV);
+    const int f = meta & 63u;
+    if (!((a.in_mask >> f) & 1u)) continue;
+    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
+    const FieldD fd = a.in[f];
+    float* dst = sm + w * kE + 4 * v;
+    if (full && ((a.in_vec4 >> f) & 1u)) {
+      cp_async16(dst, static_cast<const float*>(fd.ptr) + (size_t)c * fd.cs + env0 + 4 * v);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = 4 * v + q;
+        if (e < nvalid) {
+          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+          cp_async4(dst + q, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store_rows(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                           bool full, int tid, int nthreads) {
+  constexpr int NV = kE / 4;
+  const int total = a.n_out_rows * NV;
+#pragma unroll 2
+  for (int i = tid; i < total; i += nthreads) {
+    const uint32_t meta = __ldg(a.out_rows + i / NV);
+    const int f = meta & 63u;
+    if (!((a.out_mask >> f) & 1u)) continue;
+    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
+    const FieldD fd = a.outf[f];
+    const float* src = sm + w * kE + 4 * v;
+    float* base = static_cast<float*>(const_cast<void*>(fd.ptr));
+    if (full && ((a.out_vec4 >> f) & 1u)) {
+      *reinterpret_cast<float4*>(base + (size_t)c * fd.cs + env0 + 4 * v) = *reinterpret_cast<const float4*>(src);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = 4 * v + q;
+        if (e < nvalid) {
+          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+          base[env * fd.es + (long long)c * fd.cs] = src[q];
+        }
+      }
+    }
+  }
+}
+
+// Baked-spec movers for full SoA tiles: the row list is compile-time data, so every thread derives its rows
+// from its index with immediates - no table lookup in front of the copies. Field f's rows start at thread
+// (first word * 8) mod NT so that consecutive fields land on different warps.
+__host__ __device__ constexpr int out_field_word(const Layout& L, int f) {
+  switch (f) {
+    case OF_REWARD: return L.w_rew; case OF_EPLEN: return L.w_eplen; case OF_SUMS: return L.w_sums;
+    case OF_STEPR: return L.w_stepr; case OF_CMD: return L.w_cmd; case OF_HEAD: return L.w_head;
+    case OF_TLEFT: return L.w_tleft; case OF_MXY: return L.w_mxy; case OF_MYAW: return L.w_myaw;
+    case OF_ACT: return L.w_act; default: return L.w_pact;
+  }
+}
+template <class B, int NT>
+__device__ __forceinline__ void load_rows_static(float* sm, const KArgs& a, int env0, int tid) {
+  constexpr int NV = kE / 4;
+  static_for(std::make_integer_sequence<int, IF_COUNT>{}, [&](auto fc) {
+    constexpr int f = decltype(fc)::value;
+    constexpr int nc = in_field_ncomp(B::spec, f), w0 = in_field_word(B::spec, f);
+    constexpr int n4 = nc * NV, base = (w0 * NV) % NT;
+    if constexpr (nc > 0) {
+      if ((a.in_mask >> f) & 1u) {
+        int j = tid - base;
+        if (j < 0) j += NT;
+        const int cs = a.in[f].cs;
+        if ((a.in_vec4 >> f) & 1u) {      // SoA rows: 4 envs per copy
+          const float* src = static_cast<const float*>(a.in[f].ptr) + env0;
+          for (; j < n4; j += NT) {
+            const int c = j / NV, v = j % NV;
+            cp_async16(sm + (w0 + c) * kE + 4 * v, src + (size_t)c * cs + 4 * v);
           }
-          default: v = 0.f;
+        } else {                          // any strides (AoS action rows): 4 single-element copies
+          const int es = a.in[f].es;
+          const float* src = static_cast<const float*>(a.in[f].ptr) + (size_t)env0 * es;
+          for (; j < n4; j += NT) {
+            int c, e0;
+            if (cs == 1) { c = j % nc; e0 = (j / nc) * 4; } else { c = j / NV; e0 = (j % NV) * 4; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              cp_async4(sm + (w0 + c) * kE + e0 + q, src + (size_t)(e0 + q) * es + (size_t)c * cs);
+          }
         }
-        if (noisy) {
-          const float u = urow ? urow[col] : u4[r4];
-          v = (v + u * (t.noise_hi - t.noise_lo)) + t.noise_lo;
-        }
-        if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
-        if (t.has_scale) v = v * t.scale;
-        tile[lane][jj] = v;
       }
     }
-    __syncwarp();
-    const int env_lo = (int)env, ok = valid ? 1 : 0;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const long long env_r = (long long)__shfl_sync(0xffffffffu, env_lo, r);
-      const int ok_r = __shfl_sync(0xffffffffu, ok, r);
-      if (ok_r && lane < nc) obs[env_r * pitch + col0 + c0 + lane] = tile[r][lane];
-    }
-    __syncwarp();
-  }
+  });
 }
-
-__device__ __forceinline__ void cmd_uniforms(const KArgs& a, const RandState rs, long long env, uint32_t stream, float* u) {
-  if (a.rnd.cmd_uniforms != nullptr) {
+template <class B, int NT>
+__device__ __forceinline__ void store_rows_static(const float* sm, const KArgs& a, int env0, int tid) {
+  constexpr int NV = kE / 4;
+  static constexpr Layout SL = make_layout(B::spec);
+  static_for(std::make_integer_sequence<int, OF_COUNT>{}, [&](auto fc) {
+    constexpr int f = decltype(fc)::value;
+    constexpr int nc = out_field_ncomp(B::spec, f), w0 = out_field_word(SL, f);
+    constexpr int n4 = nc * NV, base = (w0 * NV) % NT;
+    if constexpr (nc > 0) {
+      if ((a.out_mask >> f) & 1u) {
+        int j = tid - base;
+        if (j < 0) j += NT;
+        const int cs = a.outf[f].cs;
+        if ((a.out_vec4 >> f) & 1u) {
+          float* dst = static_cast<float*>(const_cast<void*>(a.outf[f].ptr)) + env0;
+          for (; j < n4; j += NT) {
+            const int c = j / NV, v = j % NV;
+            *reinterpret_cast<float4*>(dst + (size_t)c * cs + 4 * v) = *reinterpret_cast<const float4*>(sm + (w0 + c) * kE + 4 * v);
+          }
+        } else {
+          const int es = a.outf[f].es;
+          float* dst = static_cast<float*>(const_cast<void*>(a.outf[f].ptr)) + (size_t)env0 * es;
+          for (; j < n4; j += NT) {
+            int c, e0;
+            if (cs == 1) { c = j % nc; e0 = (j / nc) * 4; } else { c = j / NV; e0 = (j % NV) * 4; }
 #pragma unroll
-    for (int i = 0; i < RL_NUM_CMD_UNIFORMS; ++i) u[i] = a.rnd.cmd_uniforms[(long long)i * a.N + env];
-  } else {
-    const uint4 r0 = rl_philox(rs, env, stream, 0), r1 = rl_philox(rs, env, stream, 1);
-    u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
-    u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
+            for (int q = 0; q < 4; ++q)
+              dst[(size_t)(e0 + q) * es + (size_t)c * cs] = sm[(w0 + c) * kE + e0 + q];
+          }
+        }
+      }
+    }
+  });
+}
+
+// AoS span [kE][pitch] <-> global rows, element-wise (used when a span is not one aligned contiguous block or the
+// shared-memory pitch is padded)
+__device__ __noinline__ void span_load_elems(float* dst, int pitch, FieldD fd, int ncomp, int env0, int nvalid,
+                                             const int32_t* ids, int tid, int nthreads) {
+  const int total = ncomp * kE;
+  const bool env_major = (fd.es == 1);
+  for (int i = tid; i < total; i += nthreads) {
+    int c, e;
+    if (env_major) { e = i % kE; c = i / kE; } else { c = i % ncomp; e = i / ncomp; }
+    if (e < nvalid) {
+      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+      cp_async4(dst + e * pitch + c, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
+    }
+  }
+}
+__device__ __noinline__ void span_store_elems(const float* src, int pitch, float* ptr, long long es, int ncomp,
+                                              int env0, int nvalid, const int32_t* ids, int tid, int nthreads) {
+  const int total = ncomp * kE;
+  for (int i = tid; i < total; i += nthreads) {
+    const int c = i % ncomp, e = i / ncomp;
+    if (e < nvalid) {
+      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
+      ptr[env * es + c] = src[e * pitch + c];
+    }
+  }
+}
+// one aligned contiguous [kE][ncomp] block in global memory AND an unpadded shared-memory pitch
+__device__ __forceinline__ bool span_bulk_ok(const FieldD& fd, int ncomp, int pitch, int env0) {
+  if (fd.ptr == nullptr || ncomp <= 0 || pitch != ncomp || fd.cs != 1 || fd.es != ncomp) return false;
+  const uintptr_t p = reinterpret_cast<uintptr_t>(fd.ptr) + (uintptr_t)env0 * (uintptr_t)ncomp * 4u;
+  return ((p & 15u) == 0) && ((((long long)kE * ncomp * 4) & 15) == 0);
+}
+__device__ __forceinline__ void load_u8(float* sm, int off, const FieldD& fd, int env0, int nvalid,
+                                        const int32_t* ids, int tid) {
+  if (fd.ptr != nullptr && tid < nvalid) {
+    const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+    sm[off + tid] = __int_as_float((int)static_cast<const uint8_t*>(fd.ptr)[env * fd.es]);
+  }
+}
+__device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD& fd, int env0, int nvalid,
+                                         const int32_t* ids, int tid) {
+  if (fd.ptr != nullptr && tid < nvalid) {
+    const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+    static_cast<uint8_t*>(const_cast<void*>(fd.ptr))[env * fd.es] = (uint8_t)__float_as_int(sm[off + tid]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The fused step kernel. grid = n_blocks x G, CTA = (tile block qb, task group g), WPC warps; warp w owns tile
-// qb*WPC + w, lane e its env e. MODE 0 = step, MODE 1 = single-term evaluation (one group, one task).
+// The fused step kernel: kE = 32 envs per CTA, NW warps. MODE 0 = step, MODE 1 = single-term evaluation.
+//   load   : everything asynchronous (TMA bulk copies + cp.async), one join
+//   stage 1: every warp runs its share of the schedule, thread-per-env (lane e = env e)
+//   stage 2: warp 0 assembles the reward in manager order, warp 1 updates the command and writes the
+//            command-dependent observation columns
+//   store  : bulk stores for the observation rows, one generic loop for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
-template <class P, int G, int WPC, int MODE>
-__global__ void __launch_bounds__(WPC * 32, 1) mdp_step_kernel(const KArgs a) {
-  extern __shared__ __align__(16) float s_dyn[];                 // [WPC][32][33] observation transpose tiles
-  float (*xpose)[33] = reinterpret_cast<float (*)[33]>(s_dyn) + (threadIdx.x >> 5) * 32;
-  __shared__ float s_red[WPC][RL_LOG_STRIDE];
-  __shared__ int s_last, s_final;
+template <class P, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_last;
   const Scalars S = P::scalars(a);
-  const RlStepSpec& CS = c_spec[a.slot];   // lane-uniform table lookups (per-joint constants) in both policies
+  const Layout L = P::layout(a);
+  constexpr int NT = NW * 32;
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const uint32_t ph = a.phases;
-#define RL_STAMP(i) do { if (a.dbg != nullptr && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#define RL_STAMP(i) do { if (a.dbg != nullptr && tid == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + (i)] = clock64(); } while (0)
   RL_STAMP(0);
+  const int warp = tid >> 5;
+  const int e = tid & 31;       // compute phase: this lane's env inside the tile
+  const uint32_t ph = a.phases;
   if (a.use_pdl) {
     // launch-latency overlap only: every read below may depend on the predecessor, so wait first
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
-  const int g = MODE == 1 ? 0 : (int)(blockIdx.x % G);
-  const int qb = MODE == 1 ? (int)blockIdx.x : (int)(blockIdx.x / G);
-  const int tile = qb * WPC + warp;
-  const int idx = tile * kE + lane;
-  const bool valid = idx < n_total;
-  const int n_tiles = (n_total + kE - 1) / kE;
-  const int n_blocks_live = (n_tiles + WPC - 1) / WPC;   // tile blocks that hold at least one env
+  const int env0 = blockIdx.x * kE;
   const int K = S.num_reward_terms;
   const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
   if (do_reset && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
@@ -984,268 +1298,351 @@ __global__ void __launch_bounds__(WPC * 32, 1) mdp_step_kernel(const KArgs a) {
     else if (tid < K + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K] = 0.f; }
     else if (tid < K + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K - RL_MAX_DONE_TERMS] = 0.f; }
   }
-  if (qb >= n_blocks_live) return;   // whole CTA beyond the data (env_ids launches are sized for the worst case)
-  // invalid lanes shadow a valid env (loads stay in bounds) and never store
-  const int idx_c = valid ? idx : 0;
-  const long long env = n_total > 0 ? (a.has_ids ? (long long)a.env_ids[idx_c] : (long long)idx_c) : 0;
+  if (env0 >= n_total && !(ph & RL_PHASE_COMPACT)) return;
+  const int nvalid = max(0, min(kE, n_total - env0));
+  const int32_t* ids = a.has_ids ? a.env_ids : nullptr;
+  const int J = S.num_joints, A = S.n_actions;
+  const int R = S.num_rays;
+  const int HW = S.hist_len * S.num_hist_bodies * 3;
+  const bool need_hist = (MODE == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
+  const bool need_rays = (MODE == 0) && (ph & RL_PHASE_OBS) && R > 0 && a.rays.ptr != nullptr;
+  const bool full = (nvalid == kE) && (ids == nullptr);
   RandState rs;
   rs.seed = a.rnd.seed;
   rs.step = a.rnd.step + (a.rnd.step_counter ? *a.rnd.step_counter : 0ull);
   rs.env_id_offset = a.rnd.env_id_offset;
 
-  if (n_total > 0) {
+  // ---- load phase: everything is asynchronous, nothing below waits until the single join point ---------
+  if (nvalid > 0) {
+    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, L.hist_pitch, env0);
+    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, L.rays_pitch, env0);
+    bool obsu_bulk[RL_NUM_OBS_GROUPS];
+    FieldD obsu[RL_NUM_OBS_GROUPS];
+#pragma unroll
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+      const int D = P::obs_dim(a, g);
+      const bool want = (MODE == 0) && (ph & RL_PHASE_OBS) && a.rnd.obs_uniforms[g] != nullptr && D > 0;
+      obsu[g] = FieldD{want ? a.rnd.obs_uniforms[g] : nullptr, D, 1};
+      obsu_bulk[g] = want && full && span_bulk_ok(obsu[g], D, LOBSP(g), env0);
+    }
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      uint32_t bytes = 0;
+      if (hist_bulk) bytes += (uint32_t)(kE * HW * 4);
+      if (rays_bulk) bytes += (uint32_t)(kE * R * 4);
+#pragma unroll
+      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
+        if (obsu_bulk[g]) bytes += (uint32_t)(kE * P::obs_dim(a, g) * 4);
+      mbar_expect_tx(&s_bar, bytes);
+      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(kE * HW * 4), &s_bar);
+      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(kE * R * 4), &s_bar);
+#pragma unroll
+      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
+        if (obsu_bulk[g])
+          bulk_g2s(sm + LOBSU(g), static_cast<const float*>(obsu[g].ptr) + (size_t)env0 * P::obs_dim(a, g),
+                   (uint32_t)(kE * P::obs_dim(a, g) * 4), &s_bar);
+    }
+    if constexpr (P::kStatic) {
+      if (full) load_rows_static<typename P::Baked, NT>(sm, a, env0, tid);
+      else load_rows_async(sm, a, env0, nvalid, ids, full, tid, NT);
+    } else {
+      load_rows_async(sm, a, env0, nvalid, ids, full, tid, NT);
+    }
+    if (need_hist && !hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, env0, nvalid, ids, tid, NT);
+    if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, env0, nvalid, ids, tid, NT);
+#pragma unroll
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
+      if (obsu[g].ptr && !obsu_bulk[g])
+        span_load_elems(sm + LOBSU(g), LOBSP(g), obsu[g], P::obs_dim(a, g), env0, nvalid, ids, tid, NT);
+    if (MODE == 0 && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET))) {
+      load_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
+      load_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
+    }
+    if (do_reset && a.out.done_bits != nullptr) {
+      FieldD f{a.out.done_bits, 1, 0};
+      load_u8(sm, L.flags, f, env0, nvalid, ids, tid);
+    }
+    // per-joint constants: constant bank -> shared
+    for (int i = tid; i < J; i += NT)
+      P::for_joint_consts(a, i, [&](float q0, float qd0, float lo, float hi, float vl) {
+        sm[L.cj + 0 * J + i] = q0; sm[L.cj + 1 * J + i] = qd0; sm[L.cj + 2 * J + i] = lo;
+        sm[L.cj + 3 * J + i] = hi; sm[L.cj + 4 * J + i] = vl;
+      });
+    RL_STAMP(1);                // all loads issued
+    cp_async_wait_all();
+    __syncthreads();            // record + mbarrier init visible to everyone
+    mbar_wait(&s_bar, 0);       // bulk copies landed
+    RL_STAMP(2);                // tile resident
+  }
+
+  const bool valid = e < nvalid;
+  const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
+  if (nvalid > 0) {
+    // ---- manager reset of the tile's envs (env_ids launches) ---------------------------------------------
+    if (do_reset) {
+      // logging partials of this CTA (summed in CTA order by the last CTA -> deterministic)
+      if (tid < K + RL_MAX_DONE_TERMS + 2) {
+        float acc = 0.f;
+        for (int el = 0; el < nvalid; ++el) {
+          if (tid < K) acc += sm[L.sums + tid * kE + el];
+          else if (tid < K + RL_MAX_DONE_TERMS)
+            acc += (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + el]) >> (tid - K)) & 1) : 0.f;
+          else acc += sm[(tid == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + el];
+        }
+        a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = acc;
+      }
+      __syncthreads();
+      // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
+      for (int i = tid; i < kE * K; i += NT) sm[L.sums + i] = 0.f;
+      for (int i = tid; i < kE * A; i += NT) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
+      if (tid < kE) {
+        const int el = tid;
+        sm[L.mxy + el] = 0.f; sm[L.myaw + el] = 0.f;
+        sm[L.eplen + el] = __int_as_float(0); sm[L.epnew + el] = __int_as_float(0);
+        const auto& cc = P::command(a);
+        const long long ev = ids ? (long long)ids[env0 + min(el, nvalid - 1)] : (long long)(env0 + el);
+        float u[RL_NUM_CMD_UNIFORMS];
+        if (a.rnd.cmd_uniforms != nullptr) {
+#pragma unroll
+          for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * kE + el];
+        } else {
+          const uint4 r0 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(rs, ev, RL_STREAM_RESET_COMMAND, 1);
+          u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+          u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
+        }
+        float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
+        float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
+        const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
+        const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+        c0 *= keep; c1 *= keep;
+        sm[L.cmd + 0 * kE + el] = c0; sm[L.cmd + 1 * kE + el] = c1; sm[L.cmd + 2 * kE + el] = c2;
+        sm[L.cmdn + 0 * kE + el] = c0; sm[L.cmdn + 1 * kE + el] = c1; sm[L.cmdn + 2 * kE + el] = c2;
+        sm[L.tleft + el] = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
+        if (cc.heading_command) {
+          sm[L.head + el] = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
+          sm[L.ishead + el] = __int_as_float((u[5] <= cc.rel_heading_envs) ? 1 : 0);
+        }
+        sm[L.isstand + el] = __int_as_float((u[6] <= cc.rel_standing_envs) ? 1 : 0);
+      }
+      __syncthreads();
+    }
+
+    // ---- stage 1: thread-per-env, warps run different tasks ------------------------------------------------
+    EnvCtx c = make_ctx(sm, L, e);
     if (MODE == 1) {
-      EnvCtx c = make_ctx(a, env);
-      if (a.ext_terminated != nullptr) c.terminated = a.ext_terminated[env] != 0;
-      const float v = reward_term(*a.adhoc, S, CS, a, env, c, 0, 64);
-      if (valid) a.term_out[env] = v;
+      if (warp == 0) {
+        if (a.ext_terminated != nullptr && valid) c.terminated = a.ext_terminated[env] != 0;
+        const float v = reward_term(*a.adhoc, S, L, sm, e, c, 0, 64);
+        if (valid) a.term_out[env] = v;
+      }
       return;
     }
-    RL_STAMP(1);                   // index setup done
-    if (ph & 0x8000u) return;      // profiling aid: empty launch
-    // ---- this group's tasks, straight-line for a baked spec ---------------------------------------------
-    const EnvCtx c = a.in[IF_QUAT].ptr != nullptr ? make_ctx(a, env) : EnvCtx{};   // reset-only launches carry no state
-    RL_STAMP(2);                   // context (root state loads + 3 quaternion rotations) done
-    if (ph & 0x4000u) { if (valid && c.gate < -1.f) a.termv[env] = c.gate; return; }   // profiling aid: context only
-    const bool with_dones = (ph & RL_PHASE_DONES) != 0;
-    P::template for_tasks<G>(a, g, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
+    const int eplen_now = __float_as_int(SMF(L.eplen, 0)) + ((ph & RL_PHASE_DONES) ? 1 : 0);
+    // TerminationManager.compute [IL] for this lane's env: bits | terminated << 8 | time_out << 9
+    auto eval_dones = [&]() -> int {
+      uint32_t bits = 0, term = 0, trunc = 0;
+      const float* h = sm + L.hist + e * L.hist_pitch;
+      P::for_dones(a, [&](const RlDoneTerm& t, int d) {
+        int fired = 0;
+        if (t.type == RL_DONE_TIME_OUT) {
+          fired = eplen_now >= S.max_episode_length;
+        } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
+          fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
+        } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
+          _Pragma("unroll 1")
+          for (int b = 0; b < S.num_hist_bodies; ++b)
+            if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
+        }
+        if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
+      });
+      return (int)(bits | (term << 8) | (trunc << 9));
+    };
+    int task_idx = -1;
+    if (a.dbg != nullptr && e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + RL_MAX_TASKS + warp] = clock64();
+    P::template for_tasks<NW>(a, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
+      ++task_idx;
+      if (tk.owner != warp) return;
+      const long long t_begin = (a.dbg != nullptr) ? clock64() : 0;
+      [&]() {
       if (tk.kind == TK_REWARD) {
         if (!(ph & RL_PHASE_REWARDS)) return;
+        const float raw = reward_term(rt, S, L, sm, e, c, tk.lo, tk.hi);
         const int k = tk.a;
-        const float raw = reward_term(rt, S, CS, a, env, c, tk.lo, tk.hi);
-        const bool late = (tk.b != 0) || (tk.hi != 64);   // one half of a split term: finalisation adds the halves
-        if (late) {
-          if (valid) a.termv[(size_t)(2 * k + tk.b) * a.Ncap + env] = raw;
+        if (tk.pad) {
+          SMF(L.termv, 2 * k + tk.b) = raw;   // partial of a split term: finished in stage 2
         } else {
           // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
           const float val = (raw * rt.weight) * S.step_dt;
-          if (valid) {
-            a.termv[(size_t)(2 * k) * a.Ncap + env] = val;
-            STF(IF_SUMS, k, LDF(IF_SUMS, k) + val);
-            if (a.in[IF_STEPR].ptr) STF(IF_STEPR, k, val / S.step_dt);
-          }
+          SMF(L.termv, 2 * k) = val;
+          SMF(L.sums, k) = SMF(L.sums, k) + val;
+          SMF(L.stepr, k) = val / S.step_dt;
         }
       } else if (tk.kind == TK_OBS) {
         if (!(ph & RL_PHASE_OBS) || a.out.obs[tk.a] == nullptr) return;
-        const int eplen_eff = do_reset ? 0 : (ld_eplen(a, env) + (with_dones ? 1 : 0));
-        obs_task(a, S, CS, ot, corrupt, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, env, valid, c, nullptr, eplen_eff, do_reset, xpose);
+        obs_task(sm, L, S, ot, corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
       } else if (tk.kind == TK_DONES) {
-        if (!with_dones) return;
-        const uint32_t fl = eval_dones<P>(a, S, env, c);
-        if (valid) {
-          if (a.out.done_bits) a.out.done_bits[env] = (uint8_t)(fl & 0xff);
-          if (a.out.terminated) a.out.terminated[env] = (uint8_t)((fl >> 8) & 1);
-          if (a.out.truncated) a.out.truncated[env] = (uint8_t)((fl >> 9) & 1);
-        }
-      } else if (tk.kind == TK_COMMAND) {
-        if (!(ph & (RL_PHASE_COMMAND | RL_PHASE_OBS | RL_PHASE_RESET))) return;
-        const auto& cc = P::command(a);
-        float c0 = c.c0, c1 = c.c1, c2 = c.c2;
-        float mxy = 0.f, myaw = 0.f, tleft = 0.f, head = 0.f;
-        int ishead = 0, isstand = 0;
-        const bool cmd_state = (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) != 0;
-        if (cmd_state) {
-          mxy = LDF(IF_MXY, 0); myaw = LDF(IF_MYAW, 0); tleft = LDF(IF_TLEFT, 0); head = LDF(IF_HEAD, 0);
-          ishead = ld_u8(a.is_heading, env); isstand = ld_u8(a.is_standing, env);
-        }
-        if (do_reset) {
-          // ---- manager reset [IL]: logging partials first (deterministic: lane tree, warp order, block order) ----
-          const int bits = (a.out.done_bits != nullptr) ? (int)a.out.done_bits[env] : 0;
-          for (int v = 0; v < K + RL_MAX_DONE_TERMS + 2; ++v) {
-            float x = 0.f;
-            if (valid) {
-              if (v < K) x = LDF(IF_SUMS, v);
-              else if (v < K + RL_MAX_DONE_TERMS) x = (float)((bits >> (v - K)) & 1);
-              else x = (v == K + RL_MAX_DONE_TERMS) ? mxy : myaw;
-            }
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-            if (lane == 0) s_red[warp][v] = x;
-          }
-          __syncthreads();
-          if (tid < K + RL_MAX_DONE_TERMS + 2) {
-            float tot = 0.f;
-            for (int w = 0; w < WPC; ++w) tot += s_red[w][tid];
-            a.log_partials[(size_t)qb * RL_LOG_STRIDE + tid] = tot;
-          }
-          // RewardManager / ActionManager / CommandTerm .reset, episode_length_buf = 0
-          if (valid) {
-            for (int k = 0; k < K; ++k) STF(IF_SUMS, k, 0.f);
-            for (int i = 0; i < S.n_actions; ++i) { STF(IF_ACT, i, 0.f); STF(IF_PACT, i, 0.f); }
-            static_cast<int32_t*>(const_cast<void*>(a.in[IF_EPLEN].ptr))[env * a.in[IF_EPLEN].es] = 0;
-          }
-          mxy = 0.f; myaw = 0.f;
-          float u[RL_NUM_CMD_UNIFORMS];
-          cmd_uniforms(a, rs, env, RL_STREAM_RESET_COMMAND, u);
-          c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
-          c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
-          c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
-          const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
-          c0 *= keep; c1 *= keep;
-          tleft = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
-          if (cc.heading_command) {
-            head = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
-            ishead = (u[5] <= cc.rel_heading_envs) ? 1 : 0;
-          }
-          isstand = (u[6] <= cc.rel_standing_envs) ? 1 : 0;
-        }
+        if (!(ph & RL_PHASE_DONES)) return;
+        SMF(L.epnew, 0) = __int_as_float(eplen_now);
+        SMF(L.flags, 0) = __int_as_float(eval_dones());
+      } else {  // TK_COMMAND: CommandManager.compute + the observation columns that show the new command
+        if (!(ph & (RL_PHASE_COMMAND | RL_PHASE_OBS))) return;
         if (ph & RL_PHASE_COMMAND) {
-          // CommandTerm.compute [IL] + UniformThresholdVelocityCommand (V/mdp/commands.py:43-85; the "pits" branch is
-          // identically off for the in-scope terrains, V/mdp/utils.py:27-28); withheld from envs done this step
           bool skip = false;
-          if ((ph & RL_PHASE_SKIP_DONE_ENVS) && with_dones) skip = ((eval_dones<P>(a, S, env, c) >> 8) & 3) != 0;
-          if (!skip) {
-            const float dx = c0 - c.vb.x, dy = c1 - c.vb.y;
-            mxy = mxy + sqrtf(dx * dx + dy * dy) / cc.max_command_step;
-            myaw = myaw + fabsf(c2 - c.wb.z) / cc.max_command_step;
-            tleft = tleft - S.step_dt;
-            if (tleft <= 0.f) {
-              float u[RL_NUM_CMD_UNIFORMS];
-              cmd_uniforms(a, rs, env, RL_STREAM_COMMAND, u);
-              tleft = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
-              c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
-              c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
-              c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
-              if (cc.heading_command) {
-                head = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
-                ishead = (u[5] <= cc.rel_heading_envs) ? 1 : 0;
-              }
-              isstand = (u[6] <= cc.rel_standing_envs) ? 1 : 0;
-              const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
-              c0 *= keep; c1 *= keep;
-            }
-            if (cc.heading_command && ishead) {
-              const V3 fwd = quat_apply(c.qw, c.q, V3{1.f, 0.f, 0.f});
-              const float heading = rl_atan2f(fwd.y, fwd.x);
-              const float err = wrap_to_pi(head - heading);
-              c2 = clampf(cc.heading_control_stiffness * err, cc.ang_vel_z_lo, cc.ang_vel_z_hi);
-            }
-            if (isstand) { c0 = 0.f; c1 = 0.f; c2 = 0.f; }
-          }
-        }
-        if (cmd_state && valid) {
-          STF(IF_MXY, 0, mxy); STF(IF_MYAW, 0, myaw); STF(IF_TLEFT, 0, tleft); STF(IF_HEAD, 0, head);
-          st_u8(a.is_heading, env, ishead); st_u8(a.is_standing, env, isstand);
-          a.cmd_new[(size_t)0 * a.Ncap + env] = c0; a.cmd_new[(size_t)1 * a.Ncap + env] = c1; a.cmd_new[(size_t)2 * a.Ncap + env] = c2;
+          if ((ph & RL_PHASE_SKIP_DONE_ENVS) && (ph & RL_PHASE_DONES)) skip = ((eval_dones() >> 8) & 3) != 0;
+          command_update(sm, L, S, P::command(a), a, rs, e, env, c, !skip);
+        } else if (!(ph & RL_PHASE_RESET)) {
+          SMF(L.cmdn, 0) = c.c0; SMF(L.cmdn, 1) = c.c1; SMF(L.cmdn, 2) = c.c2;
         }
         if (ph & RL_PHASE_OBS) {
-          const float cmd3[3] = {c0, c1, c2};
-          P::for_cmd_obs(a, [&](const RlObsTerm& ct, int og, int oti, int ocol0, bool ocorrupt) {
-            if (a.out.obs[og] == nullptr) return;
-            obs_task(a, S, CS, ct, ocorrupt, rs, og, oti, ocol0, 0, ct.dim, env, valid, c, cmd3, 0, do_reset, xpose);
+          P::for_cmd_obs(a, [&](const RlObsTerm& t, int g, int ti, int col0, bool corr) {
+            if (a.out.obs[g] == nullptr) return;
+            obs_task(sm, L, S, t, corr, a, rs, g, ti, col0, 0, t.dim, e, env, c, eplen_now);
           });
         }
       }
+      }();
+      if (a.dbg != nullptr && e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + task_idx] = clock64() - t_begin;
     });
-  }
-  RL_STAMP(3);
+    __syncthreads();
+    RL_STAMP(3);                // stage 1 done
 
-  // ---- finalisation of the tile block by the last of its G CTAs ---------------------------------------------
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(a.block_ticket + qb, 1u);
-    s_last = (prev == (unsigned)(G - 1));
-    if (s_last) a.block_ticket[qb] = 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  RL_STAMP(4);
-  uint32_t done_flag = 0;
-  if (valid && n_total > 0) {
-    if (ph & RL_PHASE_DONES) {
-      const int t8 = a.out.terminated ? (int)__ldcg(a.out.terminated + env) : 0;
-      const int r8 = a.out.truncated ? (int)__ldcg(a.out.truncated + env) : 0;
-      done_flag = (uint32_t)((t8 | r8) != 0);
-      int32_t* ep = static_cast<int32_t*>(const_cast<void*>(a.in[IF_EPLEN].ptr)) + env * a.in[IF_EPLEN].es;
-      *ep = *ep + 1;
-    }
-    if (ph & RL_PHASE_REWARDS) {
-      const bool terminated = (ph & RL_PHASE_DONES) && a.out.terminated ? (__ldcg(a.out.terminated + env) != 0) : false;
+    // ---- stage 2: warp 0 finishes the late terms and adds the reward up in manager order ------------------
+    if ((ph & RL_PHASE_REWARDS) && warp == 0) {
+      const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
+      const bool terminated = ((fl >> 8) & 1) != 0;
       float total = 0.f;
-      P::template for_rewards<G>(a, [&](const RlRewardTerm& t, int k, bool split, bool late) {
-        if (t.weight == 0.f) { if (a.in[IF_STEPR].ptr) STF(IF_STEPR, k, 0.f); return; }
+      P::template for_rewards<NW>(a, [&](const RlRewardTerm& t, int k, bool split, bool late) {
+        if (t.weight == 0.f) { SMF(L.stepr, k) = 0.f; return; }
         float val;
         if (late) {
           float raw;
           if (t.type == RL_REW_IS_TERMINATED) raw = terminated ? 1.f : 0.f;
-          else {
-            raw = __ldcg(a.termv + (size_t)(2 * k) * a.Ncap + env);
-            if (split) raw = raw + __ldcg(a.termv + (size_t)(2 * k + 1) * a.Ncap + env);
-          }
+          else raw = split ? (SMF(L.termv, 2 * k) + SMF(L.termv, 2 * k + 1)) : SMF(L.termv, 2 * k);
           val = (raw * t.weight) * S.step_dt;
-          STF(IF_SUMS, k, LDF(IF_SUMS, k) + val);
-          if (a.in[IF_STEPR].ptr) STF(IF_STEPR, k, val / S.step_dt);
+          SMF(L.sums, k) = SMF(L.sums, k) + val;
+          SMF(L.stepr, k) = val / S.step_dt;
         } else {
-          val = __ldcg(a.termv + (size_t)(2 * k) * a.Ncap + env);
+          val = SMF(L.termv, 2 * k);
         }
-        total += val;   // manager order
+        total += val;
       });
-      if (a.out.reward) a.out.reward[env] = total;
-    }
-    if (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) {
-      STF(IF_CMD, 0, __ldcg(a.cmd_new + (size_t)0 * a.Ncap + env));
-      STF(IF_CMD, 1, __ldcg(a.cmd_new + (size_t)1 * a.Ncap + env));
-      STF(IF_CMD, 2, __ldcg(a.cmd_new + (size_t)2 * a.Ncap + env));
-    }
-  }
-  const bool compact = (ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids;
-  if (compact) {
-    const unsigned m = __ballot_sync(0xffffffffu, done_flag);
-    if (lane == 0 && tile < n_tiles) a.tile_mask[tile] = m;
-  }
-  if (!(compact || do_reset)) return;
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(a.final_ticket, 1u);
-    s_final = (prev == (unsigned)(max(n_blocks_live, 1) - 1));
-    if (s_final) *a.final_ticket = 0u;
-  }
-  __syncthreads();
-  if (!s_final) return;
-  __threadfence();
-  RL_STAMP(5);
-  if (do_reset && n_total > 0) {
-    if (tid < K + RL_MAX_DONE_TERMS + 2) {
-      float tot = 0.f;
-      for (int b = 0; b < n_blocks_live; ++b) tot += __ldcg(a.log_partials + (size_t)b * RL_LOG_STRIDE + tid);
-      const RlResetLog& lg = a.out.reset_log;
-      if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / (float)n_total; }
-      else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
-      else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / (float)n_total;
-    }
-  }
-  if (compact) {
-    // ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]): thread i owns a
-    // contiguous run of tiles -> ids come out ascending
-    __shared__ int s_cnt[WPC * 32];
-    constexpr int NT = WPC * 32;
-    const int per = (n_tiles + NT - 1) / NT;
-    const int t0 = tid * per, t1 = min(n_tiles, t0 + per);
-    int cnt = 0;
-    for (int t = t0; t < t1; ++t) cnt += __popc(__ldcg(a.tile_mask + t));
-    s_cnt[tid] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int i = 0; i < NT; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
-      if (a.out.n_reset) *a.out.n_reset = run;
+      SMF(L.rew, 0) = total;
     }
     __syncthreads();
-    int pos = s_cnt[tid];
-    if (a.out.reset_ids)
-      for (int t = t0; t < t1; ++t) {
-        unsigned m = __ldcg(a.tile_mask + t);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          a.out.reset_ids[pos++] = t * kE + b;
+    RL_STAMP(4);                // stage 2 done
+
+    // ---- store phase ----------------------------------------------------------------------------
+    if (ph & RL_PHASE_OBS) {
+      fence_proxy_async();
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+        const int D = P::obs_dim(a, g);
+        if (a.out.obs[g] == nullptr || D <= 0) continue;
+        const FieldD od{a.out.obs[g], (int)a.out.obs_pitch[g], 1};
+        if (full && span_bulk_ok(od, D, LOBSP(g), env0)) {
+          if (tid == 0) bulk_s2g(a.out.obs[g] + (size_t)env0 * D, sm + LOBS(g), (uint32_t)(kE * D * 4));
+        } else {
+          span_store_elems(sm + LOBS(g), LOBSP(g), a.out.obs[g], a.out.obs_pitch[g], D, env0, nvalid, ids, tid, NT);
         }
       }
+      if (tid == 0) bulk_commit();
+    }
+    if constexpr (P::kStatic) {
+      if (full) store_rows_static<typename P::Baked, NT>(sm, a, env0, tid);
+      else store_rows(sm, a, env0, nvalid, ids, full, tid, NT);
+    } else {
+      store_rows(sm, a, env0, nvalid, ids, full, tid, NT);
+    }
+    if (ph & RL_PHASE_DONES) {
+      if (tid < nvalid) {
+        const int f2 = __float_as_int(sm[L.flags + tid]);
+        const long long ev = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+        if (a.out.done_bits) a.out.done_bits[ev] = (uint8_t)(f2 & 0xff);
+        if (a.out.terminated) a.out.terminated[ev] = (uint8_t)((f2 >> 8) & 1);
+        if (a.out.truncated) a.out.truncated[ev] = (uint8_t)((f2 >> 9) & 1);
+      }
+    }
+    if ((ph & RL_PHASE_COMMAND) || do_reset) {
+      store_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
+      store_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
+    }
+  }
+
+  RL_STAMP(5);                  // stores issued
+  // ---- ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]) -----------
+  if ((ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids) {
+    if (tid < kE) {  // per-CTA bit mask of done envs
+      const int f2 = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, (f2 >> 8) & 3);
+      if (tid == 0) a.cta_mask[blockIdx.x] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(a.ticket, 1u);
+      s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      int* s_cnt = reinterpret_cast<int*>(sm);  // this CTA's tile is dead once its own stores have been issued
+      if ((ph & RL_PHASE_OBS) && nvalid > 0) { if (tid == 0) bulk_wait_read0(); }
+      __syncthreads();
+      // gridDim.x masks; thread i owns a contiguous run of CTAs -> ids come out ascending
+      const int G = gridDim.x;
+      const int per = (G + NT - 1) / NT;
+      const int g0 = tid * per, g1 = min(G, g0 + per);
+      int cnt = 0;
+      for (int g = g0; g < g1; ++g) cnt += __popc(__ldcg(a.cta_mask + g));
+      s_cnt[tid] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < NT; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
+        if (a.out.n_reset) *a.out.n_reset = run;
+        *a.ticket = 0u;
+      }
+      __syncthreads();
+      int pos = s_cnt[tid];
+      if (a.out.reset_ids)
+        for (int g = g0; g < g1; ++g) {
+          unsigned m = __ldcg(a.cta_mask + g);
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            a.out.reset_ids[pos++] = g * kE + b;
+          }
+        }
+      return;
+    }
+  }
+  if (do_reset && nvalid > 0) {
+    const int n_cta = (n_total + kE - 1) / kE;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(a.ticket, 1u);
+      s_last = (prev == (unsigned)(n_cta - 1));
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < K + RL_MAX_DONE_TERMS + 2) {
+        float tot = 0.f;
+        for (int g = 0; g < n_cta; ++g) tot += __ldcg(a.log_partials + (size_t)g * RL_LOG_STRIDE + tid);
+        const RlResetLog& lg = a.out.reset_log;
+        if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / (float)n_total; }
+        else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
+        else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / (float)n_total;
+      }
+      if (tid == 0) *a.ticket = 0u;
+    }
   }
   RL_STAMP(6);
+  if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
+  RL_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1278,7 +1675,6 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
   }
 }
 
-
 // ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
@@ -1288,17 +1684,17 @@ struct RlCtx {
   int device;
   int slot;
   RlStepSpec spec;
-  int G, WPC;             // task groups, warps (= 32-env tiles) per CTA
+  int NW;                 // warps per CTA (kE = 32 envs per CTA is fixed)
+  Layout L;
   Schedule* sched_dev;
-  // scratch, grown on demand (outside stream capture)
-  int Ncap;
-  float* termv;
-  float* cmd_new;
-  unsigned int* block_ticket;
-  unsigned int* final_ticket;
-  uint32_t* tile_mask;
+  unsigned int* ticket;
+  uint32_t* cta_mask;
   float* log_partials;
+  int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
+  uint32_t* in_rows_dev;
+  uint32_t* out_rows_dev;
+  int n_in_rows, n_out_rows;
   int sm_count;
   int use_pdl;
   long long* dbg;
@@ -1307,24 +1703,53 @@ struct RlCtx {
 
 namespace {
 
+
+// static row tables (field, component, record word); E-independent
+int build_row_tables(RlCtx* ctx) {
+  const RlStepSpec& s = ctx->spec;
+  const Layout L = make_layout(s);
+  uint32_t rows[2048];
+  int n = 0, word = 0;
+  for (int f = 0; f < IF_COUNT; ++f) {  // same running word count as make_layout
+    for (int c = 0; c < in_field_ncomp(s, f); ++c) rows[n++] = row_pack(f, c, word + c);
+    word += in_field_ncomp(s, f);
+  }
+  ctx->n_in_rows = n;
+  CUDA_TRY(cudaMalloc(&ctx->in_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
+  CUDA_TRY(cudaMemcpy(ctx->in_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  n = 0;
+  const int K = s.num_reward_terms;
+  const int A = s.action.n_actions;
+  const int ow[OF_COUNT] = {L.w_rew, L.w_eplen, L.w_sums, L.w_stepr, L.w_cmd, L.w_head, L.w_tleft, L.w_mxy, L.w_myaw, L.w_act, L.w_pact};
+  const int oc[OF_COUNT] = {1, 1, K, K, 3, 1, 1, 1, 1, A, A};
+  for (int f = 0; f < OF_COUNT; ++f)
+    for (int c = 0; c < oc[f]; ++c) rows[n++] = row_pack(f, c, ow[f] + c);
+  ctx->n_out_rows = n;
+  CUDA_TRY(cudaMalloc(&ctx->out_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
+  CUDA_TRY(cudaMemcpy(ctx->out_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  return RL_OK;
+}
+
 bool to_fd(const RlField& f, FieldD* out) {
   if (f.env_stride > 0x7fffffffLL || f.comp_stride > 0x7fffffffLL || f.env_stride < 0 || f.comp_stride < 0) return false;
   out->ptr = f.ptr; out->es = (int)f.env_stride; out->cs = (int)f.comp_stride;
   return true;
 }
+bool vec4_ok(const FieldD& d, int ncomp) {
+  return d.ptr != nullptr && d.es == 1 && (ncomp == 1 || (d.cs % 4) == 0) && (reinterpret_cast<uintptr_t>(d.ptr) & 15u) == 0;
+}
 
-// Field descriptors of one launch. `st` may be NULL (reset-only launches).
+// Field descriptors + masks of one launch. `state` may be NULL (reset-only launches).
 int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, const RlMdpState* mdp, const RlStepOut* out,
-              const RlRandom* rnd, uint32_t ph) {
+              const RlRandom* rnd, uint32_t ph, int mode) {
+  const RlStepSpec& s = ctx->spec;
   memset(&a, 0, sizeof(a));
   a.N = (int)num_envs; a.slot = ctx->slot; a.phases = ph;
-  a.groups = ctx->G; a.tiles_per_cta = ctx->WPC;
-  const int n_tiles = (int)((num_envs + kE - 1) / kE);
-  a.n_blocks = (n_tiles + ctx->WPC - 1) / ctx->WPC;
-  a.sched = ctx->sched_dev;
-  a.termv = ctx->termv; a.cmd_new = ctx->cmd_new; a.Ncap = ctx->Ncap;
-  a.block_ticket = ctx->block_ticket; a.final_ticket = ctx->final_ticket; a.tile_mask = ctx->tile_mask;
-  a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl; a.dbg = ctx->dbg;
+  a.L = ctx->L; a.sched = ctx->sched_dev;
+  a.in_rows = ctx->in_rows_dev; a.n_in_rows = ctx->n_in_rows;
+  a.out_rows = ctx->out_rows_dev; a.n_out_rows = ctx->n_out_rows;
+  a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
+  a.dbg = ctx->dbg;
   if (out) a.out = *out;
   if (rnd) a.rnd = *rnd;
   bool ok = true;
@@ -1338,15 +1763,53 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
   ok &= to_fd(S(&RlStateView::current_contact_time), &a.in[IF_CCON]); ok &= to_fd(S(&RlStateView::last_contact_time), &a.in[IF_LCON]);
   ok &= to_fd(S(&RlStateView::body_pos_w), &a.in[IF_BPOS]); ok &= to_fd(S(&RlStateView::body_lin_vel_w), &a.in[IF_BVEL]);
   ok &= to_fd(S(&RlStateView::ray_sensor_pos_z), &a.in[IF_RAYPOS]);
-  ok &= to_fd(S(&RlStateView::net_forces_w_history), &a.in[IF_HIST]); ok &= to_fd(S(&RlStateView::ray_hits_z), &a.in[IF_RAYS]);
+  ok &= to_fd(S(&RlStateView::net_forces_w_history), &a.hist); ok &= to_fd(S(&RlStateView::ray_hits_z), &a.rays);
   ok &= to_fd(mdp->command, &a.in[IF_CMD]); ok &= to_fd(mdp->heading_target, &a.in[IF_HEAD]);
   ok &= to_fd(mdp->time_left, &a.in[IF_TLEFT]); ok &= to_fd(mdp->metric_error_vel_xy, &a.in[IF_MXY]);
   ok &= to_fd(mdp->metric_error_vel_yaw, &a.in[IF_MYAW]); ok &= to_fd(mdp->episode_length, &a.in[IF_EPLEN]);
   ok &= to_fd(mdp->episode_sums, &a.in[IF_SUMS]);
   ok &= to_fd(mdp->action, &a.in[IF_ACT]); ok &= to_fd(mdp->prev_action, &a.in[IF_PACT]);
   ok &= to_fd(mdp->is_heading_env, &a.is_heading); ok &= to_fd(mdp->is_standing_env, &a.is_standing);
-  ok &= to_fd(a.out.step_reward, &a.in[IF_STEPR]);
   if (!ok) return fail(RL_EINVAL, "field strides must be non-negative and below 2^31 elements%s", "");
+  a.in[IF_CMDU] = FieldD{a.rnd.cmd_uniforms, 1, (int)num_envs};
+  const bool need_hist = (mode == 1) || (ph & (RL_PHASE_DONES | RL_PHASE_REWARDS));
+  uint32_t m = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_JPOS) |
+               (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN) | (1u << IF_ACT);
+  if (need_hist)
+    m |= (1u << IF_PACT) | (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) | (1u << IF_LCON) |
+         (1u << IF_BPOS) | (1u << IF_BVEL);
+  if (mode == 0 && (ph & RL_PHASE_REWARDS)) m |= 1u << IF_SUMS;
+  if (mode == 0 && (ph & RL_PHASE_COMMAND)) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
+  if (mode == 0 && (ph & RL_PHASE_RESET)) m |= (1u << IF_SUMS) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_HEAD) | (1u << IF_CMDU);
+  if (mode == 0 && (ph & RL_PHASE_OBS) && s.num_rays > 0) m |= 1u << IF_RAYPOS;
+  uint32_t v4 = 0;
+  for (int f = 0; f < IF_COUNT; ++f) {
+    if (a.in[f].ptr == nullptr) m &= ~(1u << f);
+    else if (vec4_ok(a.in[f], in_field_ncomp(s, f))) v4 |= 1u << f;
+  }
+  a.in_mask = m; a.in_vec4 = v4;
+  // outputs
+  if (mode == 0) {
+    a.outf[OF_REWARD] = FieldD{a.out.reward, 1, 0};
+    a.outf[OF_EPLEN] = a.in[IF_EPLEN]; a.outf[OF_SUMS] = a.in[IF_SUMS];
+    FieldD sr; if (!to_fd(a.out.step_reward, &sr)) return fail(RL_EINVAL, "bad step_reward strides%s", "");
+    a.outf[OF_STEPR] = sr;
+    a.outf[OF_CMD] = a.in[IF_CMD]; a.outf[OF_HEAD] = a.in[IF_HEAD]; a.outf[OF_TLEFT] = a.in[IF_TLEFT];
+    a.outf[OF_MXY] = a.in[IF_MXY]; a.outf[OF_MYAW] = a.in[IF_MYAW];
+    a.outf[OF_ACT] = a.in[IF_ACT]; a.outf[OF_PACT] = a.in[IF_PACT];
+    uint32_t om = 0;
+    if (ph & RL_PHASE_DONES) om |= 1u << OF_EPLEN;
+    if (ph & RL_PHASE_REWARDS) om |= (1u << OF_REWARD) | (1u << OF_SUMS) | (1u << OF_STEPR);
+    if (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) om |= (1u << OF_CMD) | (1u << OF_HEAD) | (1u << OF_TLEFT) | (1u << OF_MXY) | (1u << OF_MYAW);
+    if (ph & RL_PHASE_RESET) om |= (1u << OF_SUMS) | (1u << OF_EPLEN) | (1u << OF_ACT) | (1u << OF_PACT);
+    const int oc[OF_COUNT] = {1, 1, s.num_reward_terms, s.num_reward_terms, 3, 1, 1, 1, 1, s.action.n_actions, s.action.n_actions};
+    uint32_t ov4 = 0;
+    for (int f = 0; f < OF_COUNT; ++f) {
+      if (a.outf[f].ptr == nullptr) om &= ~(1u << f);
+      else if (vec4_ok(a.outf[f], oc[f])) ov4 |= 1u << f;
+    }
+    a.out_mask = om; a.out_vec4 = ov4;
+  }
   return RL_OK;
 }
 
@@ -1371,7 +1834,6 @@ int validate_spec(const RlStepSpec* s) {
     if (t.type == RL_REW_FEET_AIR_TIME_VARIANCE && t.n_idx < 2) return fail(RL_EINVAL, "reward term %s%lld: variance needs >= 2 feet", "", k);
     if (t.type == RL_REW_FEET_GAIT && t.n_idx != 4) return fail(RL_EINVAL, "reward term %s%lld: feet_gait needs two synced pairs", "", k);
   }
-  int n_tasks = 2;
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
     const RlObsGroup& G = s->obs[g];
     if (G.n_terms < 0 || G.n_terms > RL_MAX_OBS_TERMS) return fail(RL_EINVAL, "obs group %s%lld: n_terms out of range", "", g);
@@ -1383,49 +1845,47 @@ int validate_spec(const RlStepSpec* s) {
       if ((o.type == RL_OBS_JOINT_POS_REL || o.type == RL_OBS_JOINT_VEL_REL || o.type == RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL) && o.dim > RL_MAX_JOINTS)
         return fail(RL_EINVAL, "obs group %s%lld: joint term wider than RL_MAX_JOINTS", "", g);
       dim += o.dim;
-      n_tasks += (o.dim + 63) / 64;
     }
     if (dim != G.dim) return fail(RL_EINVAL, "obs group %s%lld: dim %lld != sum of term dims", "", g, G.dim);
   }
-  n_tasks += 2 * s->num_reward_terms;
-  if (n_tasks > RL_MAX_TASKS) return fail(RL_EUNSUPPORTED, "spec needs %s%lld tasks, the schedule holds %lld", "", n_tasks, RL_MAX_TASKS);
   return RL_OK;
 }
 
-template <class P, int G, int WPC, int MODE>
-int launch_step(RlCtx* ctx, const KArgs& a, cudaStream_t st) {
-  const int grid = MODE == 1 ? a.n_blocks : a.n_blocks * G;
+template <class P, int NW, int MODE>
+int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
+  const size_t smem = (size_t)ctx->L.total_words * 4;
+  static thread_local int configured_device = -1;
+  static thread_local size_t configured_smem = 0;
+  if (configured_device != ctx->device || configured_smem < smem) {
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = ctx->device; configured_smem = smem;
+  }
+  const int grid = (n_items + kE - 1) / kE;
   if (grid <= 0) return RL_OK;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  constexpr size_t smem = (size_t)WPC * 32 * 33 * sizeof(float);
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, G, WPC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_device = ctx->device;
-  }
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WPC * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, G, WPC, MODE>, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE>, a));
   return RL_OK;
 }
 
-// (task groups, warps per CTA) pairs compiled for the generic kernel / for every baked spec
-#define RL_DYN_CONFIGS(X) X(8, 8) X(16, 16)
-#define RL_STATIC_CONFIGS(X) X(16, 16) X(24, 16) X(37, 32)
+// warps per CTA compiled for the generic kernel / for every baked spec
+#define RL_DYN_CONFIGS(X) X(4) X(8) X(16)
+#define RL_STATIC_CONFIGS(X) X(8) X(16) X(24) X(32)
 
-template <class P>
-int dispatch_config(RlCtx* ctx, const KArgs& a, cudaStream_t st, bool* found) {
+template <class P, int MODE>
+int dispatch_config(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st, bool* found) {
   *found = true;
   if constexpr (P::kStatic) {
-#define RL_CASE(G_, W_) if (ctx->G == (G_) && ctx->WPC == (W_)) return launch_step<P, G_, W_, 0>(ctx, a, st);
+#define RL_CASE(W_) if (ctx->NW == (W_)) return launch_step<P, W_, MODE>(ctx, a, n_items, st);
     RL_STATIC_CONFIGS(RL_CASE)
 #undef RL_CASE
   } else {
-#define RL_CASE(G_, W_) if (ctx->G == (G_) && ctx->WPC == (W_)) return launch_step<P, G_, W_, 0>(ctx, a, st);
+#define RL_CASE(W_) if (ctx->NW == (W_)) return launch_step<P, W_, MODE>(ctx, a, n_items, st);
     RL_DYN_CONFIGS(RL_CASE)
 #undef RL_CASE
   }
@@ -1433,61 +1893,37 @@ int dispatch_config(RlCtx* ctx, const KArgs& a, cudaStream_t st, bool* found) {
   return RL_OK;
 }
 
-int dispatch_step(RlCtx* ctx, const KArgs& a, cudaStream_t st) {
+template <int MODE>
+int dispatch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   bool found = false;
-  if (ctx->baked >= 0) {
+  if (MODE == 0 && ctx->baked >= 0) {
     int idx = 0, rc = RL_OK;
-#define RL_TRY_BAKED(B) if (idx++ == ctx->baked) rc = dispatch_config<StaticPolicy<baked::B>>(ctx, a, st, &found);
+#define RL_TRY_BAKED(B) if (idx++ == ctx->baked) rc = dispatch_config<StaticPolicy<baked::B>, 0>(ctx, a, n_items, st, &found);
     RL_BAKED_LIST(RL_TRY_BAKED)
 #undef RL_TRY_BAKED
     if (found) return rc;
   }
-  int rc = dispatch_config<DynPolicy>(ctx, a, st, &found);
-  if (!found) return fail(RL_EINVAL, "launch config (%s%lld groups, %lld warps per CTA) is not compiled for this spec", "", ctx->G, ctx->WPC);
+  // generic kernel (compiled for 4, 8 and 16 warps). The single-term mode ignores the schedule, so any
+  // configured warp count maps to a compiled one; the step mode needs the schedule's warp count exactly.
+  RlCtx tmp = *ctx;
+  if (MODE == 1) tmp.NW = tmp.NW >= 16 ? 16 : (tmp.NW >= 8 ? 8 : 4);
+  int rc = dispatch_config<DynPolicy, MODE>(&tmp, a, n_items, st, &found);
+  if (!found) return fail(RL_EINVAL, "the generic kernel is compiled for 4, 8 or 16 warps per CTA, not %s%lld", "", ctx->NW);
   return rc;
 }
 
-bool config_compiled(const RlCtx* ctx, int G, int W) {
-  bool ok = false;
-  if (ctx->baked >= 0) {
-#define RL_CASE(G_, W_) ok = ok || (G == (G_) && W == (W_));
-    RL_STATIC_CONFIGS(RL_CASE)
-#undef RL_CASE
-  }
-#define RL_CASE(G_, W_) ok = ok || (G == (G_) && W == (W_));
-  RL_DYN_CONFIGS(RL_CASE)
-#undef RL_CASE
-  return ok;
-}
-
-// scratch sized for num_envs (first call at a larger size must happen outside stream capture)
-int ensure_scratch(RlCtx* ctx, int64_t num_envs, cudaStream_t st) {
-  if (num_envs <= ctx->Ncap) return RL_OK;
-  cudaStreamCaptureStatus cs;
-  CUDA_TRY(cudaStreamIsCapturing(st, &cs));
-  if (cs != cudaStreamCaptureStatusNone)
-    return fail(RL_EINVAL, "the first call at this num_envs must happen outside stream capture (scratch allocation)%s", "");
-  CUDA_TRY(cudaDeviceSynchronize());
-  if (ctx->termv) cudaFree(ctx->termv);
-  if (ctx->cmd_new) cudaFree(ctx->cmd_new);
-  if (ctx->block_ticket) cudaFree(ctx->block_ticket);
-  if (ctx->tile_mask) cudaFree(ctx->tile_mask);
-  if (ctx->log_partials) cudaFree(ctx->log_partials);
-  ctx->termv = nullptr; ctx->cmd_new = nullptr; ctx->block_ticket = nullptr; ctx->tile_mask = nullptr; ctx->log_partials = nullptr;
-  const int64_t cap = ((num_envs + 1023) / 1024) * 1024;
-  const int64_t tiles = cap / kE, blocks = tiles;  // enough for any warps-per-CTA >= 1
-  const int K2 = 2 * (ctx->spec.num_reward_terms > 0 ? ctx->spec.num_reward_terms : 1);
-  CUDA_TRY(cudaMalloc(&ctx->termv, sizeof(float) * (size_t)K2 * cap));
-  CUDA_TRY(cudaMemset(ctx->termv, 0, sizeof(float) * (size_t)K2 * cap));
-  CUDA_TRY(cudaMalloc(&ctx->cmd_new, sizeof(float) * 3 * cap));
-  CUDA_TRY(cudaMemset(ctx->cmd_new, 0, sizeof(float) * 3 * cap));
-  CUDA_TRY(cudaMalloc(&ctx->block_ticket, sizeof(unsigned int) * blocks));
-  CUDA_TRY(cudaMemset(ctx->block_ticket, 0, sizeof(unsigned int) * blocks));
-  CUDA_TRY(cudaMalloc(&ctx->tile_mask, sizeof(uint32_t) * tiles));
-  CUDA_TRY(cudaMemset(ctx->tile_mask, 0, sizeof(uint32_t) * tiles));
-  CUDA_TRY(cudaMalloc(&ctx->log_partials, sizeof(float) * (size_t)blocks * RL_LOG_STRIDE));
-  CUDA_TRY(cudaMemset(ctx->log_partials, 0, sizeof(float) * (size_t)blocks * RL_LOG_STRIDE));
-  ctx->Ncap = (int)cap;
+int ensure_scratch(RlCtx* ctx, int grid) {
+  if (grid <= ctx->cta_mask_cap) return RL_OK;
+  if (ctx->cta_mask) CUDA_TRY(cudaFree(ctx->cta_mask));
+  if (ctx->log_partials) CUDA_TRY(cudaFree(ctx->log_partials));
+  ctx->cta_mask = nullptr;
+  ctx->log_partials = nullptr;
+  const int cap = grid * 2 + 64;
+  CUDA_TRY(cudaMalloc(&ctx->cta_mask, sizeof(uint32_t) * cap));
+  CUDA_TRY(cudaMemset(ctx->cta_mask, 0, sizeof(uint32_t) * cap));
+  CUDA_TRY(cudaMalloc(&ctx->log_partials, sizeof(float) * (size_t)cap * RL_LOG_STRIDE));
+  CUDA_TRY(cudaMemset(ctx->log_partials, 0, sizeof(float) * (size_t)cap * RL_LOG_STRIDE));
+  ctx->cta_mask_cap = cap;
   return RL_OK;
 }
 
@@ -1502,12 +1938,6 @@ struct DeviceGuard {
 };
 
 bool g_slots[16][RL_SPEC_SLOTS];
-
-int upload_schedule(RlCtx* ctx) {
-  const Schedule sc = make_schedule(ctx->spec, ctx->G);
-  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));
-  return RL_OK;
-}
 
 }  // namespace
 
@@ -1545,19 +1975,27 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   ctx->device = device;
   ctx->slot = slot;
   ctx->spec = *spec;
-  ctx->G = 16;
-  ctx->WPC = 16;
+  ctx->NW = 8;
+  ctx->L = make_layout(ctx->spec);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaMemcpyToSymbol(c_spec, spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * slot));
-  CUDA_TRY(cudaMalloc(&ctx->final_ticket, sizeof(unsigned int)));
-  CUDA_TRY(cudaMemset(ctx->final_ticket, 0, sizeof(unsigned int)));
-  CUDA_TRY(cudaMalloc(&ctx->adhoc_dev, sizeof(RlRewardTerm) * 64));
+  if ((size_t)ctx->L.total_words * 4 > (size_t)prop.sharedMemPerBlockOptin) {
+    delete ctx;
+    return fail(RL_EUNSUPPORTED, "the tile of %s%lld envs needs %lld bytes of shared memory", "", kE, (long long)make_layout(*spec).total_words * 4);
+  }
   CUDA_TRY(cudaMalloc(&ctx->sched_dev, sizeof(Schedule)));
-  rc = upload_schedule(ctx);
+  {
+    const Schedule sc = make_schedule(ctx->spec, ctx->NW);
+    CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(c_spec, spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * slot));
+  CUDA_TRY(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
+  CUDA_TRY(cudaMalloc(&ctx->adhoc_dev, sizeof(RlRewardTerm) * 64));
+  rc = ensure_scratch(ctx, 4096);
   if (rc != RL_OK) return rc;
-  rc = ensure_scratch(ctx, 4096, 0);
+  rc = build_row_tables(ctx);
   if (rc != RL_OK) return rc;
   ctx->baked = -1;
   {
@@ -1574,20 +2012,41 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
 void rl_ctx_destroy(RlCtx* ctx) {
   if (!ctx) return;
   DeviceGuard guard(ctx->device);
-  cudaFree(ctx->termv); cudaFree(ctx->cmd_new); cudaFree(ctx->block_ticket); cudaFree(ctx->final_ticket);
-  cudaFree(ctx->tile_mask); cudaFree(ctx->log_partials); cudaFree(ctx->adhoc_dev); cudaFree(ctx->sched_dev);
+  if (ctx->ticket) cudaFree(ctx->ticket);
+  if (ctx->cta_mask) cudaFree(ctx->cta_mask);
+  if (ctx->log_partials) cudaFree(ctx->log_partials);
+  if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
+  if (ctx->in_rows_dev) cudaFree(ctx->in_rows_dev);
+  if (ctx->sched_dev) cudaFree(ctx->sched_dev);
+  if (ctx->out_rows_dev) cudaFree(ctx->out_rows_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
 }
 
-int rl_ctx_set_launch_config(RlCtx* ctx, int groups, int warps_per_cta) {
+int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
-  const int G = groups > 0 ? groups : 16, W = warps_per_cta > 0 ? warps_per_cta : 16;
-  if (!config_compiled(ctx, G, W))
-    return fail(RL_EINVAL, "launch config (%s%lld groups, %lld warps per CTA) is not compiled (see RL_STATIC_CONFIGS / RL_DYN_CONFIGS)", "", G, W);
+  if (envs_per_cta != 0 && envs_per_cta != kE) return fail(RL_EINVAL, "envs_per_cta is fixed at %s%lld (one lane per env)", "", kE);
+  const int nw = warps_per_cta > 0 ? warps_per_cta : 8;
+  const bool generic_ok = (nw == 4 || nw == 8 || nw == 16), baked_ok = (nw == 8 || nw == 16 || nw == 24 || nw == 32);
+  if (!(ctx->baked >= 0 ? (baked_ok || generic_ok) : generic_ok))
+    return fail(RL_EINVAL, "warps_per_cta must be 4, 8 or 16 (8, 16, 24 or 32 for a build-time specialised task)%s, got %lld", "", nw);
   DeviceGuard guard(ctx->device);
-  ctx->G = G; ctx->WPC = W;
-  return upload_schedule(ctx);  // synchronous: not for hot loops
+  const Schedule sc = make_schedule(ctx->spec, nw);
+  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
+  ctx->NW = nw;
+  return RL_OK;
+}
+
+int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out, int32_t* n_tasks) {
+  if (!ctx || !out || !n_tasks) return fail(RL_EINVAL, "null argument%s", "");
+  const Schedule sc = make_schedule(ctx->spec, ctx->NW);
+  *n_tasks = sc.n;
+  for (int i = 0; i < sc.n; ++i) {
+    const Task& t = sc.t[i];
+    const int32_t row[8] = {t.kind, t.a, t.b, t.owner, t.lo, t.hi, t.col0, t.pad};
+    for (int q = 0; q < 8; ++q) out[i * 8 + q] = row[q];
+  }
+  return RL_OK;
 }
 
 int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer) {
@@ -1632,6 +2091,7 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   if (num_envs > 0x7fffffff / 8) return fail(RL_EINVAL, "rl_step: num_envs too large%s", "");
   if ((env_ids == nullptr) != (n_env_ids == nullptr)) return fail(RL_EINVAL, "rl_step: env_ids and n_env_ids go together%s", "");
   const RlStepSpec& s = ctx->spec;
+  // required pointers per phase
   if (!state->root_quat_w.ptr || !state->root_lin_vel_w.ptr || !state->root_ang_vel_w.ptr || !state->root_pos_w.ptr ||
       !state->joint_pos.ptr || !state->joint_vel.ptr || !mdp->command.ptr || !mdp->action.ptr || !mdp->episode_length.ptr)
     return fail(RL_EINVAL, "rl_step: root/joint/command/action/episode_length fields are required%s", "");
@@ -1645,10 +2105,10 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   }
   if ((phases & RL_PHASE_REWARDS) && (!mdp->episode_sums.ptr && s.num_reward_terms > 0))
     return fail(RL_EINVAL, "rl_step: episode_sums required for the reward phase%s", "");
-  if (phases & (RL_PHASE_COMMAND | RL_PHASE_RESET)) {
+  if (phases & RL_PHASE_COMMAND) {
     if (!mdp->heading_target.ptr || !mdp->time_left.ptr || !mdp->is_heading_env.ptr || !mdp->is_standing_env.ptr ||
         !mdp->metric_error_vel_xy.ptr || !mdp->metric_error_vel_yaw.ptr)
-      return fail(RL_EINVAL, "rl_step: command state fields required for the command / reset phase%s", "");
+      return fail(RL_EINVAL, "rl_step: command state fields required for the command phase%s", "");
   }
   if ((phases & RL_PHASE_OBS) && s.num_rays > 0 && (!state->ray_hits_z.ptr || !state->ray_sensor_pos_z.ptr)) {
     bool needs = false;
@@ -1660,18 +2120,27 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
     if (out->obs[g] && out->obs_pitch[g] < s.obs[g].dim) return fail(RL_EINVAL, "rl_step: obs_pitch[%s%lld] smaller than the group dim", "", g);
   if ((phases & RL_PHASE_RESET) && !env_ids) return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET needs env_ids%s", "");
   if ((phases & RL_PHASE_RESET) && (phases & (RL_PHASE_DONES | RL_PHASE_REWARDS))) return fail(RL_EINVAL, "rl_step: RESET combines with COMMAND/OBS only%s", "");
-  if ((phases & RL_PHASE_RESET) && (!mdp->episode_sums.ptr || !mdp->prev_action.ptr))
+  if ((phases & RL_PHASE_RESET) && (!mdp->episode_sums.ptr || !mdp->prev_action.ptr || !mdp->heading_target.ptr || !mdp->time_left.ptr ||
+      !mdp->is_heading_env.ptr || !mdp->is_standing_env.ptr || !mdp->metric_error_vel_xy.ptr || !mdp->metric_error_vel_yaw.ptr))
     return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET needs every RlMdpState field%s", "");
   if (env_ids && (phases & RL_PHASE_COMPACT)) return fail(RL_EINVAL, "rl_step: compaction is not available on an env_ids subset%s", "");
   if ((phases & RL_PHASE_COMPACT) && !(phases & RL_PHASE_DONES)) return fail(RL_EINVAL, "rl_step: COMPACT needs DONES%s", "");
   DeviceGuard guard(ctx->device);
-  int rc = ensure_scratch(ctx, num_envs, (cudaStream_t)stream);
-  if (rc != RL_OK) return rc;
+  const int grid = (int)((num_envs + kE - 1) / kE);
+  if (phases & (RL_PHASE_COMPACT | RL_PHASE_RESET)) {
+    if (grid > ctx->cta_mask_cap) {
+      cudaStreamCaptureStatus cs;
+      CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+      if (cs != cudaStreamCaptureStatusNone) return fail(RL_EINVAL, "rl_step: first call at this num_envs must happen outside stream capture%s", "");
+      int rc = ensure_scratch(ctx, grid);
+      if (rc != RL_OK) return rc;
+    }
+  }
   KArgs a;
-  rc = fill_args(ctx, a, num_envs, state, mdp, out, rnd, phases);
-  if (rc != RL_OK) return rc;
+  int frc = fill_args(ctx, a, num_envs, state, mdp, out, rnd, phases, 0);
+  if (frc != RL_OK) return frc;
   a.has_ids = env_ids != nullptr; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
-  return dispatch_step(ctx, a, (cudaStream_t)stream);
+  return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
 int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uint8_t* done_bits, const RlRandom* rnd,
@@ -1683,17 +2152,23 @@ int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uin
       !mdp->metric_error_vel_yaw.ptr || !mdp->episode_length.ptr)
     return fail(RL_EINVAL, "rl_reset_envs: every RlMdpState field is required%s", "");
   DeviceGuard guard(ctx->device);
-  int rc = ensure_scratch(ctx, num_envs, (cudaStream_t)stream);
-  if (rc != RL_OK) return rc;
+  const int grid = (int)((num_envs + kE - 1) / kE);
+  if (grid > ctx->cta_mask_cap) {
+    cudaStreamCaptureStatus cs;
+    CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) return fail(RL_EINVAL, "rl_reset_envs: first call at this num_envs must happen outside stream capture%s", "");
+    int rc = ensure_scratch(ctx, grid);
+    if (rc != RL_OK) return rc;
+  }
+  KArgs a;
   RlStepOut o;
   memset(&o, 0, sizeof(o));
   o.done_bits = const_cast<uint8_t*>(done_bits);
   if (log) o.reset_log = *log;
-  KArgs a;
-  rc = fill_args(ctx, a, num_envs, nullptr, mdp, &o, rnd, RL_PHASE_RESET);
-  if (rc != RL_OK) return rc;
+  int frc = fill_args(ctx, a, num_envs, nullptr, mdp, &o, rnd, RL_PHASE_RESET, 0);
+  if (frc != RL_OK) return frc;
   a.has_ids = 1; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
-  return dispatch_step(ctx, a, (cudaStream_t)stream);
+  return dispatch_step<0>(ctx, a, (int)num_envs, (cudaStream_t)stream);
 }
 
 int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const RlStateView* state, const RlMdpState* mdp,
@@ -1713,12 +2188,10 @@ int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const R
   RlRewardTerm* dev = ctx->adhoc_dev + (ring++ & 63);
   CUDA_TRY(cudaMemcpyAsync(dev, term, sizeof(RlRewardTerm), cudaMemcpyHostToDevice, st));
   KArgs a;
-  int rc = fill_args(ctx, a, num_envs, state, mdp, nullptr, nullptr, 0);
-  if (rc != RL_OK) return rc;
-  const int n_tiles = (int)((num_envs + kE - 1) / kE);
-  a.n_blocks = (n_tiles + 7) / 8;
+  int frc = fill_args(ctx, a, num_envs, state, mdp, nullptr, nullptr, 0, 1);
+  if (frc != RL_OK) return frc;
   a.adhoc = dev; a.ext_terminated = terminated; a.term_out = out; a.use_pdl = 0;
-  return launch_step<DynPolicy, 1, 8, 1>(ctx, a, st);
+  return dispatch_step<1>(ctx, a, (int)num_envs, st);
 }
 
 }  // extern "C"

@@ -42,17 +42,25 @@ class MdpStepEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def set_launch_config(self, groups: int = 0, warps_per_cta: int = 0) -> None:
-        """Task groups and warps (= 32-env tiles) per CTA of the task-sliced grid; 0 = default (16, 16)."""
-        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, groups, warps_per_cta))
+    def set_launch_config(self, warps_per_cta: int = 0) -> None:
+        """Warps per CTA (4, 8, 16; also 24, 32 for build-time specialised tasks). A CTA owns 32 envs, one lane each."""
+        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, 0, warps_per_cta))
 
     def set_pdl(self, enabled: bool) -> None:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""
         nat.check(self.lib.rl_ctx_set_pdl(self._ctx, int(enabled)))
 
     def set_debug_buffer(self, buf: torch.Tensor | None) -> None:
-        """int64 [ceil(N/32), 8] device tensor receiving per-CTA clock64 stamps of the phase boundaries."""
+        """int64 [ceil(N/32), RL_DEBUG_STRIDE] device tensor receiving per-CTA clock64 stamps (phases, tasks)."""
         nat.check(self.lib.rl_ctx_set_debug_buffer(self._ctx, nat.ptr_of(buf)))
+
+    def schedule(self) -> list[dict]:
+        """The static work schedule of the current launch config (see rl_ctx_get_schedule)."""
+        out = (C.c_int32 * (nat.RL_MAX_TASKS * 8))()
+        n = C.c_int32(0)
+        nat.check(self.lib.rl_ctx_get_schedule(self._ctx, out, C.byref(n)))
+        keys = ("kind", "a", "b", "owner", "lo", "hi", "col0", "late")
+        return [dict(zip(keys, out[i * 8:i * 8 + 8])) for i in range(n.value)]
 
     def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
         return StateBuffers(self.spec, num_envs, self.device, layout)

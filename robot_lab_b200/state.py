@@ -1,9 +1,9 @@
 """Device-resident state of the MDP step, in the HBM layout the kernels are fastest on.
 
-Layout: every per-env input field is SoA ``[C, N]`` (env innermost) - the kernels are thread-per-env, so a warp
-reading component c of its 32 envs touches exactly one 128-byte line; that includes the sensor streams
-(contact-force history ``[T*B*3, N]``, ray hits ``[R, N]``). Policy-facing tensors (actions, observation rows)
-stay AoS ``[N, D]`` because the policy network consumes rows.
+Layout: small per-env fields are SoA ``[C, N]`` (env innermost -> coalesced sector
+loads when a CTA gathers its tile), the sensor streams are AoS rows (contact-force history ``[N, T*B*3]``, ray
+hits ``[N, R]``) so that a CTA's tile is one contiguous span for a TMA bulk copy, and policy-facing tensors
+(actions, observation rows) are AoS ``[N, D]`` because the policy network consumes rows.
 
 All per-step *inputs* (what physics + sensors + the policy produce) are carved out of one contiguous device
 arena, all per-step *results* (observation rows, reward, done masks) out of another, each field 256-byte
@@ -32,8 +32,8 @@ INPUT_FIELDS = {
     "current_contact_time": (lambda s: s.Bt, _F32, "soa"), "last_contact_time": (lambda s: s.Bt, _F32, "soa"),
     "body_pos_w": (lambda s: s.Ba * 3, _F32, "soa"), "body_lin_vel_w": (lambda s: s.Ba * 3, _F32, "soa"),
     "ray_sensor_pos_z": (lambda s: 1, _F32, "soa"),
-    "net_forces_w_history": (lambda s: s.T * s.B * 3, _F32, "soa"),
-    "ray_hits_z": (lambda s: s.R, _F32, "soa"),
+    "net_forces_w_history": (lambda s: s.T * s.B * 3, _F32, "aos"),
+    "ray_hits_z": (lambda s: s.R, _F32, "aos"),
     "new_action": (lambda s: s.A, _F32, "aos"),
 }
 MDP_FIELDS = {
@@ -148,7 +148,7 @@ class StateBuffers:
         if name in ("is_heading_env", "is_standing_env"):
             return x.bool()
         if name == "net_forces_w_history":
-            return x.reshape(self.N, self.spec.T, self.spec.B, 3) if x.is_contiguous() else x.contiguous().reshape(self.N, self.spec.T, self.spec.B, 3)
+            return x.reshape(self.N, self.spec.T, self.spec.B, 3)
         if name in ("body_pos_w", "body_lin_vel_w"):
             return x.reshape(self.N, self.spec.Ba, 3)
         return x

@@ -106,7 +106,9 @@ def test_rsl_rl_wrapper_surface(native_lib):
     obs, rew, dones, extras = env.step(5.0 * torch.ones(128, 12, device="cuda:0"))
     torch.cuda.synchronize()
     assert dones.dtype == torch.long and "time_outs" in extras and "log" in extras
-    assert (env.unwrapped.action_manager.action == 1.0).all()  # clipped to clip_actions
     live = dones == 0
+    act = env.unwrapped.action_manager.action
+    assert (act[live] == 1.0).all()            # clipped to clip_actions
+    assert (act[~live] == 0.0).all()           # ActionManager.reset for the envs that were reset
     assert torch.equal(env.episode_length_buf[live], ep[live] + 1)
     env.close()

@@ -16,33 +16,36 @@ from robot_lab_b200.engine import MdpStepEngine  # noqa: E402
 from robot_lab_b200.synthetic import make_state  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-GW = sys.argv[2] if len(sys.argv) > 2 else "16x16"
-G_, W = (int(x) for x in GW.split("x"))
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
 PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DONES, "rewards": nat.PHASE_REWARDS,
           "obs": nat.PHASE_OBS, "command": nat.PHASE_COMMAND, "dones+compact": nat.PHASE_DONES | nat.PHASE_COMPACT,
-          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS, "empty": 0x8000, "ctx": 0x4000}
+          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS}
 phase_name = sys.argv[4] if len(sys.argv) > 4 else "all"
 cfg, spec = H.make_spec(key)
 eng = MdpStepEngine(spec, "cuda:0")
-eng.set_launch_config(G_, W)
+eng.set_launch_config(W)
 sets = []
 for i in range(8):
     b = eng.new_buffers(N)
     b.load_logical(make_state(spec, N, seed=1234 + i))
     b.cmd_uniforms, b.obs_uniforms = None, [None, None]
     sets.append(b)
-grid = (((N + 31) // 32 + W - 1) // W) * G_
-dbg = torch.zeros(grid, 8, dtype=torch.int64, device="cuda:0")
+grid = (N + 31) // 32
+dbg = torch.zeros(grid, nat.RL_DEBUG_STRIDE, dtype=torch.int64, device="cuda:0")
 PH = PHASES[phase_name]
 for it in range(6):
     for b in sets:
         eng.step(b, phases=PH, use_random_inputs=False)
 torch.cuda.synchronize()
 eng.set_debug_buffer(dbg)
-acc = torch.zeros(1)
-mx = torch.zeros(1)
-per_group = torch.zeros(G_)
+names = ["start->loads issued", "loads issued->tile resident", "tile resident->stage1 done", "stage1->stage2 done",
+         "stage2->stores issued", "stores->compaction", "compaction->exit"]
+acc = torch.zeros(7)
+mx = torch.zeros(7)
+sched = eng.schedule()
+task_acc = torch.zeros(len(sched))
+enter_acc = torch.zeros(W)
 tot = []
 reps = 8
 for it in range(reps):
@@ -52,18 +55,33 @@ for it in range(reps):
     eng.step(b, phases=PH, use_random_inputs=False)
     ev1.record()
     torch.cuda.synchronize()
-    d = dbg.cpu().double()
-    if phase_name in ("empty", "ctx"):
-        k = 1 if phase_name == "empty" else 2
-        print("   start->stamp%d cycles: mean %.0f max %.0f" % (k, (d[:, k] - d[:, 0]).mean().item(), (d[:, k] - d[:, 0]).max().item()),
-              " stamp1: mean %.0f" % (d[:, 1] - d[:, 0]).mean().item(), " event us %.1f" % (ev0.elapsed_time(ev1) * 1e3))
-        continue
-    span = (d[:, 3] - d[:, 0])            # start -> this CTA's tasks done
-    per_group += span.view(-1, G_).mean(0).float()
-    t0 = d[:, 0].min()
-    tot.append((span.mean().item(), span.max().item(), (d[:, 3].max() - t0).item(), ev0.elapsed_time(ev1) * 1e3))
-print(f"{key} N={N} groups x warps={G_}x{W} grid={grid} phases={phase_name}")
-if phase_name in ("empty", "ctx"):
-    sys.exit(0)
-print("  task cycles per group (mean over tile blocks):", [int(x) for x in (per_group / reps).tolist()])
-print("  per-CTA task cycles (mean, max), first start -> last tasks done, event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
+    dall = dbg.cpu().double()
+    d = dall[:, :8]
+    task_acc += dall[:, 8:8 + len(sched)].mean(0).float()
+    enter_acc += (dall[:, 8 + nat.RL_MAX_TASKS:8 + nat.RL_MAX_TASKS + W] - dall[:, 2:3]).mean(0).float()
+    dur = d[:, 1:] - d[:, :-1]
+    dur[dur.abs() > 1e8] = 0  # stamps a CTA skipped (early return of the compacting CTA)
+    acc += dur.mean(0).float()
+    mx = torch.maximum(mx, dur.max(0).values.float())
+    span = (d[:, 5] - d[:, 0])
+    tot.append((span.mean().item(), span.max().item(), ev0.elapsed_time(ev1) * 1e3))
+print(f"{key} N={N} warps={W} grid={grid} phases={phase_name}")
+for n, a_, m_ in zip(names, acc / reps, mx):
+    print(f"  {n:32s} mean {a_:9.0f} cyc   max {m_:9.0f} cyc")
+print("  per-CTA total cycles (mean, max), event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
+
+if phase_name == "all":
+    rnames = [t.name for t in spec.rewards]
+    per_warp = {}
+    for t, cyc in zip(sched, (task_acc / reps).tolist()):
+        if t["kind"] == 0:
+            label = f"reward {rnames[t['a']]}" + (f" [bodies {t['lo']}:{t['hi']}]" if t["late"] else "")
+        elif t["kind"] == 1:
+            label = f"obs g{t['a']} term {spec.obs[t['a']].terms[t['b']].name} cols {t['lo']}:{t['hi']}"
+        else:
+            label = "terminations" if t["kind"] == 2 else "command (+ its obs columns)"
+        per_warp.setdefault(t["owner"], []).append((label, cyc))
+    print("  stage-1 tasks per warp (mean cycles); 'enter' = tile resident -> warp starts its first task (ctx set-up)")
+    for w in sorted(per_warp):
+        tot_w = sum(c for _, c in per_warp[w])
+        print(f"   warp {w:2d}: enter {enter_acc[w] / reps:6.0f}  tasks {tot_w:7.0f}  " + "; ".join(f"{l} {c:.0f}" for l, c in per_warp[w]))
