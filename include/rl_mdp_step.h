@@ -355,10 +355,9 @@ int64_t rl_struct_sizeof(const char* name);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knob: warps per CTA (4, 8 or 16 for any spec; 8, 16, 24 or 32 for a spec the library was specialised
- * for at build time; 0 = default). A CTA always owns 32 consecutive envs (one lane per env); its warps share the
- * termination / reward / command / observation terms according to a static schedule. envs_per_cta must be 0 or 32.
- * Synchronous (re-uploads the schedule): call it outside hot loops and outside stream capture. */
+/* Tuning knob: warps per CTA (4, 8 or 16; 0 = default). A CTA always owns 32 consecutive envs (one lane per env);
+ * its warps share the termination / reward / command / observation terms according to a static schedule.
+ * envs_per_cta must be 0 or 32. Synchronous (re-uploads the schedule): not for hot loops or stream capture. */
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */

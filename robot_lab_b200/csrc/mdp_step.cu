@@ -72,6 +72,8 @@ struct FieldD {
   const void* ptr;
   int es;    // env stride   (elements)
   int cs;    // comp stride  (elements)
+  int meta;  // movers: components | first record word << 16 (kept next to the pointer: one parameter-bank line)
+  int pad_;
 };
 
 enum InField {
@@ -81,8 +83,6 @@ enum InField {
 };
 enum OutField { OF_REWARD = 0, OF_EPLEN, OF_SUMS, OF_STEPR, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_ACT, OF_PACT, OF_COUNT };
 
-// row meta: field (bits 0-5) | comp (6-15) | record word (16-31)
-__host__ __device__ constexpr uint32_t row_pack(int f, int c, int w) { return (uint32_t)f | ((uint32_t)c << 6) | ((uint32_t)w << 16); }
 
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory layout of one CTA tile (word offsets; SoA words already multiplied by kE).
@@ -102,14 +102,15 @@ struct Layout {
   int cmdu;
   int rew, flags, stepr;                         // outputs
   int termv;                                     // [K][2] weighted term values (or raw partials of split terms)
+  int arrive;                                    // [K] per-env arrival counters of the two halves of a split term
   int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
   int soa_words;
   int cj;                                        // per-joint constants [5][J]: q0, qd0, soft lo, soft hi, vel limit
   // AoS rows [kE][pitch]; pitches are forced ODD so that lane e reading row e is bank-conflict free
   int hist, hist_pitch;
   int rays, rays_pitch;
-  int obs0, obs1, obs_pitch0, obs_pitch1;          // selected with LOBS(g) etc.: no runtime-indexed members,
-  int obsu0, obsu1;                                // so the struct never has to live in local memory
+  int obs0, obs1, obs_pitch0, obs_pitch1;          // selected with LOBS(g) etc.: no runtime-indexed members, so
+                                                   // the struct never has to live in local memory
   int total_words;
 };
 
@@ -142,6 +143,7 @@ __host__ __device__ constexpr int out_field_ncomp(const RlStepSpec& s, int f) {
 }
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static_assert(kE == 32, "the field movers assume 8 float4 per row");
 __host__ __device__ constexpr int odd_pitch(int n) { return n <= 0 ? 1 : (n | 1); }
 
 __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
@@ -173,6 +175,7 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   L.flags = take(1) * E;
   L.w_stepr = take(K); L.stepr = L.w_stepr * E;
   L.termv = take(2 * K) * E;
+  L.arrive = take(K) * E;
   L.soa_words = w;
   int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
   L.cj = off; off = align_up(off + 5 * J, 32);
@@ -183,10 +186,17 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   L.obs_pitch0 = odd_pitch(s.obs[0].dim); L.obs_pitch1 = odd_pitch(s.obs[1].dim);
   L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
   L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
-  L.obsu0 = off; off = align_up(off + E * L.obs_pitch0, 32);
-  L.obsu1 = off; off = align_up(off + E * L.obs_pitch1, 32);
   L.total_words = off;
   return L;
+}
+
+__host__ __device__ constexpr int out_field_word(const Layout& L, int f) {
+  switch (f) {
+    case OF_REWARD: return L.w_rew; case OF_EPLEN: return L.w_eplen; case OF_SUMS: return L.w_sums;
+    case OF_STEPR: return L.w_stepr; case OF_CMD: return L.w_cmd; case OF_HEAD: return L.w_head;
+    case OF_TLEFT: return L.w_tleft; case OF_MXY: return L.w_mxy; case OF_MYAW: return L.w_myaw;
+    case OF_ACT: return L.w_act; default: return L.w_pact;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -259,7 +269,7 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
     if (body_sum && nb > 8) {
       int seen = 0, mid = 0;  // split after the first nb/2 set bits
       for (int b = 0; b < 64; ++b) if ((t.body_mask >> b) & 1ull) { if (++seen == nb / 2) { mid = b + 1; break; } }
-      sc.split[k] = 1; sc.late[k] = 1;
+      sc.split[k] = 1;   // the half that arrives second (per env) finishes the term, see the kernel
       sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, (uint16_t)mid, 0, 1}; cost[n++] = reward_cost(t, s, nb / 2);
       sc.t[n] = Task{TK_REWARD, (uint8_t)k, 1, 0, (uint16_t)mid, 64, 0, 1}; cost[n++] = reward_cost(t, s, nb - nb / 2);
     } else {
@@ -304,8 +314,8 @@ struct KArgs {
   FieldD outf[OF_COUNT];
   uint32_t in_mask, out_mask;
   uint32_t in_vec4, out_vec4;     // fields whose rows may move 4 envs at a time (SoA, 16-byte aligned)
-  const uint32_t* in_rows;  int n_in_rows;
-  const uint32_t* out_rows; int n_out_rows;
+  float rw_weight[RL_MAX_REWARD_TERMS];          // stage 2: weights and term classes come from the parameter bank
+  uint64_t rw_late, rw_split, rw_isterm, rw_zero;   // bit k: finished in stage 2 / two partials / is_terminated / weight 0
   // AoS spans (row-contiguous per env) and byte fields
   FieldD hist, rays;
   FieldD is_heading, is_standing;               // uint8
@@ -446,6 +456,7 @@ __device__ __forceinline__ float wrap_to_pi(float a) {
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 // torch.clamp semantics for NaN are irrelevant here; +-inf behave like fminf/fmaxf.
 // transcendental functions behind calls: one code copy each instead of ~100 inlined instructions per use
+__device__ __noinline__ float rl_div(float x, float y) { return x / y; }   // IEEE division, one code copy
 __device__ __noinline__ float rl_expf(float x) { return expf(x); }
 __device__ __noinline__ float rl_tanhf(float x) { return tanhf(x); }
 __device__ __noinline__ float rl_atan2f(float y, float x) { return atan2f(y, x); }
@@ -463,11 +474,12 @@ struct Scalars {
   int num_joints, num_hist_bodies, hist_len, num_time_bodies, num_asset_bodies, num_rays;
   int num_reward_terms, num_done_terms, max_episode_length, n_actions;
   float step_dt, contact_time_abs_tol;
+  int obs_dim0, obs_dim1;
 };
 __host__ __device__ constexpr Scalars scalars_of(const RlStepSpec& s) {
   return Scalars{s.num_joints, s.num_hist_bodies, s.hist_len, s.num_time_bodies, s.num_asset_bodies, s.num_rays,
                  s.num_reward_terms, s.num_done_terms, s.max_episode_length, s.action.n_actions,
-                 s.step_dt, s.contact_time_abs_tol};
+                 s.step_dt, s.contact_time_abs_tol, s.obs[0].dim, s.obs[1].dim};
 }
 
 __host__ __device__ constexpr int obs_col0(const RlObsGroup& G, int ti) {
@@ -486,14 +498,16 @@ struct DynPolicy {
   __device__ __forceinline__ static Layout layout(const KArgs& a) { return a.L; }
   __device__ __forceinline__ static Scalars scalars(const KArgs& a) { return scalars_of(c_spec[a.slot]); }
   __device__ __forceinline__ static const RlCommandCfg& command(const KArgs& a) { return c_spec[a.slot].command; }
-  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, F&& f) {
+  // f(tag, task, reward term, obs term, corruption on, task index) for every task the warp owns
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs& a, int warp, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
     const int n = a.sched->n;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       const Task tk = a.sched->t[i];
-      if (tk.kind == TK_OBS) f(tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0);
-      else f(tk, S.rewards[tk.a], S.obs[0].terms[0], false);
+      if (tk.owner != warp) continue;
+      if (tk.kind == TK_OBS) f(std::integral_constant<int, -1>{}, tk, S.rewards[0], S.obs[tk.a].terms[tk.b], S.obs[tk.a].enable_corruption != 0, i);
+      else f(std::integral_constant<int, -2>{}, tk, S.rewards[tk.a], S.obs[0].terms[0], false, i);
     }
   }
   // the command-dependent observation terms: f(term, group, term index, first column, corruption on)
@@ -508,12 +522,6 @@ struct DynPolicy {
         col0 += S.obs[g].terms[ti].dim;
       }
     }
-  }
-  // f(term, k, split, late): split = evaluated as two partial sums; late = finished in stage 2
-  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs& a, F&& f) {
-    const RlStepSpec& S = c_spec[a.slot];
-#pragma unroll 1
-    for (int k = 0; k < S.num_reward_terms; ++k) f(S.rewards[k], k, a.sched->split[k] != 0, a.sched->late[k] != 0);
   }
   template <class F> __device__ __forceinline__ static void for_dones(const KArgs& a, F&& f) {
     const RlStepSpec& S = c_spec[a.slot];
@@ -544,15 +552,31 @@ struct StaticPolicy {
     return c;
   }
   template <int NW> struct Sched { static constexpr Schedule value = make_schedule(B::spec, NW); };
-  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, F&& f) {
+  // all tasks of warp W, in schedule order; one lambda instantiation (= one call site) per task
+  template <int NW, int W, class F> __device__ __forceinline__ static void warp_tasks(F&& f) {
     static_for(std::make_integer_sequence<int, Sched<NW>::value.n>{}, [&](auto ic) {
       constexpr int i = decltype(ic)::value;
       constexpr Task tk = Sched<NW>::value.t[i];
-      static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
-      static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
-      constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
-      f(tk, rt, ot, corrupt);
+      if constexpr (tk.owner == W) {
+        static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
+        static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
+        constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+        f(ic, tk, rt, ot, corrupt, i);
+      }
     });
+  }
+  // binary search on the warp id: log2(NW) uniform branches lead to the warp's own contiguous code, so a warp
+  // never walks (or fetches) the code of the others
+  template <int NW, int LO, int HI, class F> __device__ __forceinline__ static void dispatch_warp(int warp, F&& f) {
+    if constexpr (HI - LO == 1) {
+      warp_tasks<NW, LO>(f);
+    } else {
+      constexpr int MID = (LO + HI) / 2;
+      if (warp < MID) dispatch_warp<NW, LO, MID>(warp, f); else dispatch_warp<NW, MID, HI>(warp, f);
+    }
+  }
+  template <int NW, class F> __device__ __forceinline__ static void for_tasks(const KArgs&, int warp, F&& f) {
+    dispatch_warp<NW, 0, NW>(warp, f);
   }
   template <class F> __device__ __forceinline__ static void for_cmd_obs(const KArgs&, F&& f) {
     static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS * RL_MAX_OBS_TERMS>{}, [&](auto ic) {
@@ -562,14 +586,6 @@ struct StaticPolicy {
         constexpr int col0 = obs_col0(B::spec.obs[g], ti);
         f(t, g, ti, col0, B::spec.obs[g].enable_corruption != 0);
       }
-    });
-  }
-  template <int NW, class F> __device__ __forceinline__ static void for_rewards(const KArgs&, F&& f) {
-    static_for(std::make_integer_sequence<int, B::spec.num_reward_terms>{}, [&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      static constexpr RlRewardTerm t = B::spec.rewards[k];  // static: runtime-indexed lists read it in place
-      constexpr bool split = Sched<NW>::value.split[k] != 0, late = Sched<NW>::value.late[k] != 0;
-      f(t, k, split, late);
     });
   }
   template <class F> __device__ __forceinline__ static void for_dones(const KArgs&, F&& f) {
@@ -605,7 +621,6 @@ struct EnvCtx {
 
 #define LOBS(g) ((g) == 0 ? L.obs0 : L.obs1)
 #define LOBSP(g) ((g) == 0 ? L.obs_pitch0 : L.obs_pitch1)
-#define LOBSU(g) ((g) == 0 ? L.obsu0 : L.obsu1)
 #define SMF(off, c) sm[(off) + (c) * kE + e]
 #define CJ(k, j) sm[L.cj + (k) * L.J + (j)]
 
@@ -630,8 +645,10 @@ __device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int
 
 // One reward term for env e: raw value (no weight, no dt). [lo, hi) restricts body-mask terms to a body-index
 // range (the two halves of a split term add up).
-__device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalars& S, const Layout& L, const float* sm,
-                                             const int e, const EnvCtx& c, const int lo, const int hi) {
+// `t` may be a build-time constant (scalar members fold into immediates); `tc` is the same term in __constant__
+// memory and serves every run-time indexed list (a baked object indexed at run time would be a global-memory load).
+__device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewardTerm& tc, const Scalars& S, const Layout& L,
+                                             const float* sm, const int e, const EnvCtx& c, const int lo, const int hi) {
   const int J = S.num_joints;
   const float* h = sm + L.hist + e * L.hist_pitch;
   switch (t.type) {
@@ -711,7 +728,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float d = SMF(L.jpos, t.idx_a[i]) - SMF(L.jpos, t.idx_b[i]);
+        const float d = SMF(L.jpos, tc.idx_a[i]) - SMF(L.jpos, tc.idx_b[i]);
         s += d * d;
       }
       return (s * t.p[0]) * c.gate;
@@ -720,7 +737,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float d = fabsf(SMF(L.act, t.idx_a[i])) - fabsf(SMF(L.act, t.idx_b[i]));
+        const float d = fabsf(SMF(L.act, tc.idx_a[i])) - fabsf(SMF(L.act, tc.idx_b[i]));
         s += d * d;
       }
       return (s * t.p[0]) * c.gate;
@@ -729,13 +746,13 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float r = 0.f;
       _Pragma("unroll 1")
       for (int g = 0; g < t.n_idx; ++g) {
-        const int start = t.idx_b[g], n = t.idx_c[g];
+        const int start = tc.idx_b[g], n = tc.idx_c[g];
         if (n < 2) continue;
         float m = 0.f;
-        for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, t.idx_a[start + i]));
+        for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, tc.idx_a[start + i]));
         m = m / (float)n;
         float v = 0.f;
-        for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, t.idx_a[start + i])) - m; v += d * d; }
+        for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, tc.idx_a[start + i])) - m; v += d * d; }
         r += v / (float)n;
       }
       return (r * t.p[0]) * c.gate;
@@ -786,7 +803,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const int b = t.idx_a[i];
+        const int b = tc.idx_a[i];
         s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
       }
       s *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
@@ -795,12 +812,12 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
       _Pragma("unroll 1")
-      for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, t.idx_a[i]) > 0.f) ? 1 : 0;
+      for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, tc.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const int b = t.idx_a[i];
+        const int b = tc.idx_a[i];
         const float ct = SMF(L.ccon, b);
         const float mode = (ct > 0.f) ? ct : SMF(L.cair, b);
         r = fminf(r, single ? mode : 0.f);
@@ -818,7 +835,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
         float mean = 0.f, m2 = 0.f;
         _Pragma("unroll 1")
         for (int i = 0; i < t.n_idx; ++i) {
-          const float x = fminf(SMF(off, t.idx_a[i]), 0.5f);
+          const float x = fminf(SMF(off, tc.idx_a[i]), 0.5f);
           const float d = x - mean;
           mean += d / (float)(i + 1);
           m2 += d * (x - mean);
@@ -828,7 +845,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       return r * c.gate;
     }
     case RL_REW_FEET_GAIT: {
-      const int f00 = t.idx_a[0], f01 = t.idx_a[1], f10 = t.idx_a[2], f11 = t.idx_a[3];
+      const int f00 = tc.idx_a[0], f01 = tc.idx_a[1], f10 = tc.idx_a[2], f11 = tc.idx_a[3];
       const float me2 = t.p[1], sd = t.p[0];
       auto sync = [&](int a, int b) {
         const float da = SMF(L.cair, a) - SMF(L.cair, b);
@@ -848,7 +865,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_CONTACT: {
       int n = 0;
       _Pragma("unroll 1")
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
       return r * c.gate;
@@ -856,7 +873,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
       _Pragma("unroll 1")
-      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, t.idx_a[i]) ? 1 : 0;
+      for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
       return r * c.gate;
@@ -865,7 +882,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       bool any = false;   // t = 0 is the newest history sample = net_forces_w
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const int b = t.idx_c[i];
+        const int b = tc.idx_c[i];
         const float fx = h[3 * b + 0], fy = h[3 * b + 1], fz = h[3 * b + 2];
         any = any || (sqrtf(fx * fx + fy * fy) > 4.f * fabsf(fz));
       }
@@ -875,10 +892,10 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, tc.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float lat = sqrtf(vb.x * vb.x + vb.y * vb.y);
-        s += lat * ((hist_max_norm(h, S.hist_len, S.num_hist_bodies, t.idx_c[i]) > 1.0f) ? 1.f : 0.f);
+        s += lat * ((hist_max_norm(h, S.hist_len, S.num_hist_bodies, tc.idx_c[i]) > 1.0f) ? 1.f : 0.f);
       }
       return s * c.gate;
     }
@@ -886,8 +903,8 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 p = body_vec(sm, L.bpos, e, t.idx_b[i]);
-        const V3 v = body_vec(sm, L.bvel, e, t.idx_b[i]);
+        const V3 p = body_vec(sm, L.bpos, e, tc.idx_b[i]);
+        const V3 v = body_vec(sm, L.bvel, e, tc.idx_b[i]);
         const float d = p.z - t.p[0];
         s += (d * d) * rl_tanhf(t.p[1] * sqrtf(v.x * v.x + v.y * v.y));
       }
@@ -898,8 +915,8 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
-        const V3 vw = body_vec(sm, L.bvel, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, tc.idx_b[i]);
+        const V3 vw = body_vec(sm, L.bvel, e, tc.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float d = pb.z - t.p[0];
@@ -912,7 +929,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, tc.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float want = (t.p[0] / 2.f) * ((i % 2 == 0) ? 1.f : -1.f);
         const float d = want - pb.y;
@@ -924,7 +941,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float s = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < 4; ++i) {
-        const V3 pw = body_vec(sm, L.bpos, e, t.idx_b[i]);
+        const V3 pw = body_vec(sm, L.bpos, e, tc.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
         const float wx = (i < 2) ? (t.p[1] / 2.f) : (-t.p[1] / 2.f);
         const float wy = (i % 2 == 0) ? (t.p[0] / 2.f) : (-t.p[0] / 2.f);
@@ -937,8 +954,8 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const Scalar
       float run = 0.f, stand = 0.f;
       _Pragma("unroll 1")
       for (int i = 0; i < t.n_idx; ++i) {
-        const float jv = fabsf(SMF(L.jvel, t.idx_b[i]));
-        const float ta = SMF(L.cair, t.idx_a[i]);
+        const float jv = fabsf(SMF(L.jvel, tc.idx_b[i]));
+        const float ta = SMF(L.cair, tc.idx_a[i]);
         const bool first_air = (ta > 0.f) && (ta < (S.step_dt + S.contact_time_abs_tol));
         run += (first_air ? 1.f : 0.f) * jv;
         stand += jv;
@@ -1025,12 +1042,14 @@ __device__ __forceinline__ void command_update(float* sm, const Layout& L, const
 
 // Columns [lo, hi) of one observation term for env e: ObservationManager.compute_group [IL]
 // (clone -> +noise -> clip -> scale), written into the group's shared-memory row.
-__device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scalars& S, const RlObsTerm& t,
+__device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scalars& S, const RlObsTerm& t, const RlObsTerm& tc,
                                          const bool corrupt, const KArgs& a, const RandState rs, const int g,
                                          const int ti, const int col0, const int lo, const int hi, const int e,
                                          const long long env, const EnvCtx& c, const int eplen_now) {
   float* row = sm + LOBS(g) + e * LOBSP(g);
-  const float* urow = sm + LOBSU(g) + e * LOBSP(g);
+  // noise-as-input mode (RlRandom.obs_uniforms: reproducibility hook for tests / replays, not the production
+  // path): read straight from global memory
+  const float* urow = a.rnd.obs_uniforms[g] ? a.rnd.obs_uniforms[g] + env * (g == 0 ? S.obs_dim0 : S.obs_dim1) : nullptr;
   const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
   const bool noisy = t.has_noise && corrupt;
   _Pragma("unroll 1")
@@ -1050,12 +1069,12 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
         case RL_OBS_BASE_ANG_VEL: v = col == 0 ? c.wb.x : (col == 1 ? c.wb.y : c.wb.z); break;
         case RL_OBS_PROJECTED_GRAVITY: v = col == 0 ? c.g.x : (col == 1 ? c.g.y : c.g.z); break;
         case RL_OBS_GENERATED_COMMANDS: v = SMF(L.cmdn, col); break;
-        case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]); break;
+        case RL_OBS_JOINT_POS_REL: v = SMF(L.jpos, tc.ids[col]) - CJ(0, tc.ids[col]); break;
         case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL:
-          v = SMF(L.jpos, t.ids[col]) - CJ(0, t.ids[col]);
+          v = SMF(L.jpos, tc.ids[col]) - CJ(0, tc.ids[col]);
           if ((t.zero_mask >> col) & 1ull) v = 0.f;
           break;
-        case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, t.ids[col]) - CJ(1, t.ids[col]); break;
+        case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, tc.ids[col]) - CJ(1, tc.ids[col]); break;
         case RL_OBS_LAST_ACTION: v = SMF(L.act, col); break;
         case RL_OBS_HEIGHT_SCAN: v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0]; break;
         case RL_OBS_PHASE: {
@@ -1080,164 +1099,81 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
 // ---------------------------------------------------------------------------------------------------
 // Tile movers (one code copy each)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_rows_async(float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
-                                                bool full, int tid, int nthreads) {
-  constexpr int NV = kE / 4;
-  const int total = a.n_in_rows * NV;
-#pragma unroll 2
-  for (int i = tid; i < total; i += nthreads) {
-    const uint32_t meta = __ldg(a.in_rows + i / NV);
-    const int f = meta & 63u;
+// The small per-env fields: field f is moved by warp f mod NW, its lanes stride over the field's rows (a "row" is
+// one component of one field; record word w of local env e lives at sm[w*kE + e]). Deliberately a LOOP over
+// per-field metadata and not per-field code: every SM sees this code exactly once per launch, so its size - not
+// its instruction count - is what the load phase costs (profiles/r1_front_end.md).
+__device__ __noinline__ void field_load_elems(float* sm, FieldD fd, int nc, int w0, int env0, int nvalid,
+                                              const int32_t* ids, int lane) {
+  if (lane >= nvalid) return;   // any strides, ragged tiles, env-id lists: lane = env, one element per copy
+  const long long env = ids ? (long long)ids[env0 + lane] : (long long)(env0 + lane);
+  const float* src = static_cast<const float*>(fd.ptr) + env * fd.es;
+  float* dst = sm + w0 * kE + lane;
+#pragma unroll 4
+  for (int c = 0; c < nc; ++c) cp_async4(dst + c * kE, src + (long long)c * fd.cs);
+}
+__device__ __noinline__ void field_store_elems(const float* sm, FieldD fd, int nc, int w0, int env0, int nvalid,
+                                               const int32_t* ids, int lane) {
+  if (lane >= nvalid) return;
+  const long long env = ids ? (long long)ids[env0 + lane] : (long long)(env0 + lane);
+  float* dst = static_cast<float*>(const_cast<void*>(fd.ptr)) + env * fd.es;
+  const float* src = sm + w0 * kE + lane;
+#pragma unroll 4
+  for (int c = 0; c < nc; ++c) dst[(long long)c * fd.cs] = src[c * kE];
+}
+__device__ __forceinline__ void load_fields(float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                            bool full, int warp, int lane, int nwarps) {
+#pragma unroll 1
+  for (int f = warp; f < IF_COUNT; f += nwarps) {
     if (!((a.in_mask >> f) & 1u)) continue;
-    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
     const FieldD fd = a.in[f];
-    float* dst = sm + w * kE + 4 * v;
-    if (full && ((a.in_vec4 >> f) & 1u)) {
-      cp_async16(dst, static_cast<const float*>(fd.ptr) + (size_t)c * fd.cs + env0 + 4 * v);
+    const int nc = fd.meta & 0xffff, w0 = fd.meta >> 16;
+    if (full && ((a.in_vec4 >> f) & 1u)) {   // SoA rows: 16 bytes (4 envs) per copy
+      const float* src = static_cast<const float*>(fd.ptr) + env0;
+#pragma unroll 1
+      for (int j = lane; j < nc * (kE / 4); j += 32)
+        cp_async16(sm + (w0 + (j >> 3)) * kE + 4 * (j & 7), src + (size_t)(j >> 3) * fd.cs + 4 * (j & 7));
     } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = 4 * v + q;
-        if (e < nvalid) {
-          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-          cp_async4(dst + q, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
-        }
-      }
+      field_load_elems(sm, fd, nc, w0, env0, nvalid, ids, lane);
     }
   }
 }
-
-__device__ __forceinline__ void store_rows(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
-                                           bool full, int tid, int nthreads) {
-  constexpr int NV = kE / 4;
-  const int total = a.n_out_rows * NV;
-#pragma unroll 2
-  for (int i = tid; i < total; i += nthreads) {
-    const uint32_t meta = __ldg(a.out_rows + i / NV);
-    const int f = meta & 63u;
+__device__ __forceinline__ void store_fields(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
+                                             bool full, int warp, int lane, int nwarps) {
+#pragma unroll 1
+  for (int f = warp; f < OF_COUNT; f += nwarps) {
     if (!((a.out_mask >> f) & 1u)) continue;
-    const int c = (meta >> 6) & 1023u, w = meta >> 16, v = i % NV;
     const FieldD fd = a.outf[f];
-    const float* src = sm + w * kE + 4 * v;
-    float* base = static_cast<float*>(const_cast<void*>(fd.ptr));
+    const int nc = fd.meta & 0xffff, w0 = fd.meta >> 16;
     if (full && ((a.out_vec4 >> f) & 1u)) {
-      *reinterpret_cast<float4*>(base + (size_t)c * fd.cs + env0 + 4 * v) = *reinterpret_cast<const float4*>(src);
+      float* dst = static_cast<float*>(const_cast<void*>(fd.ptr)) + env0;
+#pragma unroll 1
+      for (int j = lane; j < nc * (kE / 4); j += 32)
+        *reinterpret_cast<float4*>(dst + (size_t)(j >> 3) * fd.cs + 4 * (j & 7)) =
+            *reinterpret_cast<const float4*>(sm + (w0 + (j >> 3)) * kE + 4 * (j & 7));
     } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = 4 * v + q;
-        if (e < nvalid) {
-          const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-          base[env * fd.es + (long long)c * fd.cs] = src[q];
-        }
-      }
+      field_store_elems(sm, fd, nc, w0, env0, nvalid, ids, lane);
     }
   }
-}
-
-// Baked-spec movers for full SoA tiles: the row list is compile-time data, so every thread derives its rows
-// from its index with immediates - no table lookup in front of the copies. Field f's rows start at thread
-// (first word * 8) mod NT so that consecutive fields land on different warps.
-__host__ __device__ constexpr int out_field_word(const Layout& L, int f) {
-  switch (f) {
-    case OF_REWARD: return L.w_rew; case OF_EPLEN: return L.w_eplen; case OF_SUMS: return L.w_sums;
-    case OF_STEPR: return L.w_stepr; case OF_CMD: return L.w_cmd; case OF_HEAD: return L.w_head;
-    case OF_TLEFT: return L.w_tleft; case OF_MXY: return L.w_mxy; case OF_MYAW: return L.w_myaw;
-    case OF_ACT: return L.w_act; default: return L.w_pact;
-  }
-}
-template <class B, int NT>
-__device__ __forceinline__ void load_rows_static(float* sm, const KArgs& a, int env0, int tid) {
-  constexpr int NV = kE / 4;
-  static_for(std::make_integer_sequence<int, IF_COUNT>{}, [&](auto fc) {
-    constexpr int f = decltype(fc)::value;
-    constexpr int nc = in_field_ncomp(B::spec, f), w0 = in_field_word(B::spec, f);
-    constexpr int n4 = nc * NV, base = (w0 * NV) % NT;
-    if constexpr (nc > 0) {
-      if ((a.in_mask >> f) & 1u) {
-        int j = tid - base;
-        if (j < 0) j += NT;
-        const int cs = a.in[f].cs;
-        if ((a.in_vec4 >> f) & 1u) {      // SoA rows: 4 envs per copy
-          const float* src = static_cast<const float*>(a.in[f].ptr) + env0;
-          for (; j < n4; j += NT) {
-            const int c = j / NV, v = j % NV;
-            cp_async16(sm + (w0 + c) * kE + 4 * v, src + (size_t)c * cs + 4 * v);
-          }
-        } else {                          // any strides (AoS action rows): 4 single-element copies
-          const int es = a.in[f].es;
-          const float* src = static_cast<const float*>(a.in[f].ptr) + (size_t)env0 * es;
-          for (; j < n4; j += NT) {
-            int c, e0;
-            if (cs == 1) { c = j % nc; e0 = (j / nc) * 4; } else { c = j / NV; e0 = (j % NV) * 4; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              cp_async4(sm + (w0 + c) * kE + e0 + q, src + (size_t)(e0 + q) * es + (size_t)c * cs);
-          }
-        }
-      }
-    }
-  });
-}
-template <class B, int NT>
-__device__ __forceinline__ void store_rows_static(const float* sm, const KArgs& a, int env0, int tid) {
-  constexpr int NV = kE / 4;
-  static constexpr Layout SL = make_layout(B::spec);
-  static_for(std::make_integer_sequence<int, OF_COUNT>{}, [&](auto fc) {
-    constexpr int f = decltype(fc)::value;
-    constexpr int nc = out_field_ncomp(B::spec, f), w0 = out_field_word(SL, f);
-    constexpr int n4 = nc * NV, base = (w0 * NV) % NT;
-    if constexpr (nc > 0) {
-      if ((a.out_mask >> f) & 1u) {
-        int j = tid - base;
-        if (j < 0) j += NT;
-        const int cs = a.outf[f].cs;
-        if ((a.out_vec4 >> f) & 1u) {
-          float* dst = static_cast<float*>(const_cast<void*>(a.outf[f].ptr)) + env0;
-          for (; j < n4; j += NT) {
-            const int c = j / NV, v = j % NV;
-            *reinterpret_cast<float4*>(dst + (size_t)c * cs + 4 * v) = *reinterpret_cast<const float4*>(sm + (w0 + c) * kE + 4 * v);
-          }
-        } else {
-          const int es = a.outf[f].es;
-          float* dst = static_cast<float*>(const_cast<void*>(a.outf[f].ptr)) + (size_t)env0 * es;
-          for (; j < n4; j += NT) {
-            int c, e0;
-            if (cs == 1) { c = j % nc; e0 = (j / nc) * 4; } else { c = j / NV; e0 = (j % NV) * 4; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              dst[(size_t)(e0 + q) * es + (size_t)c * cs] = sm[(w0 + c) * kE + e0 + q];
-          }
-        }
-      }
-    }
-  });
 }
 
 // AoS span [kE][pitch] <-> global rows, element-wise (used when a span is not one aligned contiguous block or the
 // shared-memory pitch is padded)
 __device__ __noinline__ void span_load_elems(float* dst, int pitch, FieldD fd, int ncomp, int env0, int nvalid,
                                              const int32_t* ids, int tid, int nthreads) {
-  const int total = ncomp * kE;
-  const bool env_major = (fd.es == 1);
-  for (int i = tid; i < total; i += nthreads) {
-    int c, e;
-    if (env_major) { e = i % kE; c = i / kE; } else { c = i % ncomp; e = i / ncomp; }
-    if (e < nvalid) {
-      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      cp_async4(dst + e * pitch + c, static_cast<const float*>(fd.ptr) + env * fd.es + (long long)c * fd.cs);
-    }
+  const int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
+  for (int el = warp; el < nvalid; el += nw) {   // a warp walks one env's row: coalesced when rows are contiguous
+    const long long env = ids ? (long long)ids[env0 + el] : (long long)(env0 + el);
+    const float* src = static_cast<const float*>(fd.ptr) + env * fd.es;
+    for (int c = lane; c < ncomp; c += 32) cp_async4(dst + el * pitch + c, src + (long long)c * fd.cs);
   }
 }
 __device__ __noinline__ void span_store_elems(const float* src, int pitch, float* ptr, long long es, int ncomp,
                                               int env0, int nvalid, const int32_t* ids, int tid, int nthreads) {
-  const int total = ncomp * kE;
-  for (int i = tid; i < total; i += nthreads) {
-    const int c = i % ncomp, e = i / ncomp;
-    if (e < nvalid) {
-      const long long env = ids ? (long long)ids[env0 + e] : (long long)(env0 + e);
-      ptr[env * es + c] = src[e * pitch + c];
-    }
+  const int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
+  for (int el = warp; el < nvalid; el += nw) {
+    const long long env = ids ? (long long)ids[env0 + el] : (long long)(env0 + el);
+    for (int c = lane; c < ncomp; c += 32) ptr[env * es + c] = src[el * pitch + c];
   }
 }
 // one aligned contiguous [kE][ncomp] block in global memory AND an unpadded shared-memory pitch
@@ -1245,13 +1181,6 @@ __device__ __forceinline__ bool span_bulk_ok(const FieldD& fd, int ncomp, int pi
   if (fd.ptr == nullptr || ncomp <= 0 || pitch != ncomp || fd.cs != 1 || fd.es != ncomp) return false;
   const uintptr_t p = reinterpret_cast<uintptr_t>(fd.ptr) + (uintptr_t)env0 * (uintptr_t)ncomp * 4u;
   return ((p & 15u) == 0) && ((((long long)kE * ncomp * 4) & 15) == 0);
-}
-__device__ __forceinline__ void load_u8(float* sm, int off, const FieldD& fd, int env0, int nvalid,
-                                        const int32_t* ids, int tid) {
-  if (fd.ptr != nullptr && tid < nvalid) {
-    const long long env = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
-    sm[off + tid] = __int_as_float((int)static_cast<const uint8_t*>(fd.ptr)[env * fd.es]);
-  }
 }
 __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD& fd, int env0, int nvalid,
                                          const int32_t* ids, int tid) {
@@ -1269,7 +1198,7 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 //            command-dependent observation columns
 //   store  : bulk stores for the observation rows, one generic loop for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
-template <class P, int NW, int MODE>
+template <class P, int NW, int MODE, bool DBG>
 __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -1278,7 +1207,8 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const Layout L = P::layout(a);
   constexpr int NT = NW * 32;
   const int tid = threadIdx.x;
-#define RL_STAMP(i) do { if (a.dbg != nullptr && tid == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + (i)] = clock64(); } while (0)
+#define RL_STAMP(i) do { if constexpr (DBG) { if (tid == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + (i)] = clock64(); } } while (0)
+#define RL_SUB(i) RL_STAMP(8 + RL_MAX_TASKS + 32 + (i))   /* finer stamps inside the load phase (debug build only) */
   RL_STAMP(0);
   const int warp = tid >> 5;
   const int e = tid & 31;       // compute phase: this lane's env inside the tile
@@ -1314,61 +1244,49 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 
   // ---- load phase: everything is asynchronous, nothing below waits until the single join point ---------
   if (nvalid > 0) {
+    // byte-sized per-env flags: plain loads into registers, issued first so that their latency overlaps the
+    // issue of everything else
+    const bool want_cmd_flags = (MODE == 0) && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) != 0;
+    const bool want_done_bits = do_reset && a.out.done_bits != nullptr;
+    int u8_head = 0, u8_stand = 0, u8_bits = 0;
+    if (tid < nvalid) {
+      const long long ev = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+      if (want_cmd_flags) {
+        if (a.is_heading.ptr) u8_head = static_cast<const uint8_t*>(a.is_heading.ptr)[ev * a.is_heading.es];
+        if (a.is_standing.ptr) u8_stand = static_cast<const uint8_t*>(a.is_standing.ptr)[ev * a.is_standing.es];
+      }
+      if (want_done_bits) u8_bits = a.out.done_bits[ev];
+    }
     const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, L.hist_pitch, env0);
     const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, L.rays_pitch, env0);
-    bool obsu_bulk[RL_NUM_OBS_GROUPS];
-    FieldD obsu[RL_NUM_OBS_GROUPS];
-#pragma unroll
-    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
-      const int D = P::obs_dim(a, g);
-      const bool want = (MODE == 0) && (ph & RL_PHASE_OBS) && a.rnd.obs_uniforms[g] != nullptr && D > 0;
-      obsu[g] = FieldD{want ? a.rnd.obs_uniforms[g] : nullptr, D, 1};
-      obsu_bulk[g] = want && full && span_bulk_ok(obsu[g], D, LOBSP(g), env0);
-    }
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       uint32_t bytes = 0;
       if (hist_bulk) bytes += (uint32_t)(kE * HW * 4);
       if (rays_bulk) bytes += (uint32_t)(kE * R * 4);
-#pragma unroll
-      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (obsu_bulk[g]) bytes += (uint32_t)(kE * P::obs_dim(a, g) * 4);
       mbar_expect_tx(&s_bar, bytes);
       if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(kE * HW * 4), &s_bar);
       if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(kE * R * 4), &s_bar);
-#pragma unroll
-      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-        if (obsu_bulk[g])
-          bulk_g2s(sm + LOBSU(g), static_cast<const float*>(obsu[g].ptr) + (size_t)env0 * P::obs_dim(a, g),
-                   (uint32_t)(kE * P::obs_dim(a, g) * 4), &s_bar);
     }
-    if constexpr (P::kStatic) {
-      if (full) load_rows_static<typename P::Baked, NT>(sm, a, env0, tid);
-      else load_rows_async(sm, a, env0, nvalid, ids, full, tid, NT);
-    } else {
-      load_rows_async(sm, a, env0, nvalid, ids, full, tid, NT);
-    }
+    RL_SUB(0);                  // prologue + bulk copies issued
+    load_fields(sm, a, env0, nvalid, ids, full, warp, e, NW);
+    RL_SUB(1);                  // per-field copies issued
     if (need_hist && !hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, env0, nvalid, ids, tid, NT);
     if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, env0, nvalid, ids, tid, NT);
-#pragma unroll
-    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
-      if (obsu[g].ptr && !obsu_bulk[g])
-        span_load_elems(sm + LOBSU(g), LOBSP(g), obsu[g], P::obs_dim(a, g), env0, nvalid, ids, tid, NT);
-    if (MODE == 0 && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET))) {
-      load_u8(sm, L.ishead, a.is_heading, env0, nvalid, ids, tid);
-      load_u8(sm, L.isstand, a.is_standing, env0, nvalid, ids, tid);
-    }
-    if (do_reset && a.out.done_bits != nullptr) {
-      FieldD f{a.out.done_bits, 1, 0};
-      load_u8(sm, L.flags, f, env0, nvalid, ids, tid);
-    }
+    if (ph & RL_PHASE_REWARDS)
+      for (int i = tid; i < K * kE; i += NT) sm[L.arrive + i] = __int_as_float(0);
+    RL_SUB(2);                  // span loads issued
     // per-joint constants: constant bank -> shared
     for (int i = tid; i < J; i += NT)
       P::for_joint_consts(a, i, [&](float q0, float qd0, float lo, float hi, float vl) {
         sm[L.cj + 0 * J + i] = q0; sm[L.cj + 1 * J + i] = qd0; sm[L.cj + 2 * J + i] = lo;
         sm[L.cj + 3 * J + i] = hi; sm[L.cj + 4 * J + i] = vl;
       });
+    if (tid < nvalid) {         // the byte flags were requested at the top of the load phase
+      if (want_cmd_flags) { sm[L.ishead + tid] = __int_as_float(u8_head); sm[L.isstand + tid] = __int_as_float(u8_stand); }
+      if (want_done_bits) sm[L.flags + tid] = __int_as_float(u8_bits);
+    }
     RL_STAMP(1);                // all loads issued
     cp_async_wait_all();
     __syncthreads();            // record + mbarrier init visible to everyone
@@ -1382,15 +1300,19 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     // ---- manager reset of the tile's envs (env_ids launches) ---------------------------------------------
     if (do_reset) {
       // logging partials of this CTA (summed in CTA order by the last CTA -> deterministic)
-      if (tid < K + RL_MAX_DONE_TERMS + 2) {
-        float acc = 0.f;
-        for (int el = 0; el < nvalid; ++el) {
-          if (tid < K) acc += sm[L.sums + tid * kE + el];
-          else if (tid < K + RL_MAX_DONE_TERMS)
-            acc += (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + el]) >> (tid - K)) & 1) : 0.f;
-          else acc += sm[(tid == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + el];
+      // quantity q is reduced by warp q mod NW over its lanes (= envs) with a fixed shuffle tree
+#pragma unroll 1
+      for (int q = warp; q < K + RL_MAX_DONE_TERMS + 2; q += NW) {
+        float x = 0.f;
+        if (e < nvalid) {
+          if (q < K) x = sm[L.sums + q * kE + e];
+          else if (q < K + RL_MAX_DONE_TERMS)
+            x = (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + e]) >> (q - K)) & 1) : 0.f;
+          else x = sm[(q == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + e];
         }
-        a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = acc;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (e == 0) a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + q] = x;
       }
       __syncthreads();
       // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
@@ -1433,7 +1355,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     if (MODE == 1) {
       if (warp == 0) {
         if (a.ext_terminated != nullptr && valid) c.terminated = a.ext_terminated[env] != 0;
-        const float v = reward_term(*a.adhoc, S, L, sm, e, c, 0, 64);
+        const float v = reward_term(*a.adhoc, *a.adhoc, S, L, sm, e, c, 0, 64);
         if (valid) a.term_out[env] = v;
       }
       return;
@@ -1443,7 +1365,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     auto eval_dones = [&]() -> int {
       uint32_t bits = 0, term = 0, trunc = 0;
       const float* h = sm + L.hist + e * L.hist_pitch;
-      P::for_dones(a, [&](const RlDoneTerm& t, int d) {
+      P::for_dones(a, [&](const RlDoneTerm& t, int d) __attribute__((always_inline)) {
         int fired = 0;
         if (t.type == RL_DONE_TIME_OUT) {
           fired = eplen_now >= S.max_episode_length;
@@ -1458,29 +1380,40 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       });
       return (int)(bits | (term << 8) | (trunc << 9));
     };
-    int task_idx = -1;
-    if (a.dbg != nullptr && e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + RL_MAX_TASKS + warp] = clock64();
-    P::template for_tasks<NW>(a, [&](const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt) {
-      ++task_idx;
-      if (tk.owner != warp) return;
-      const long long t_begin = (a.dbg != nullptr) ? clock64() : 0;
-      [&]() {
+    if constexpr (DBG) { if (e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + RL_MAX_TASKS + warp] = clock64(); }
+    P::template for_tasks<NW>(a, warp, [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt,
+                                          const int task_idx) __attribute__((always_inline)) {
+      long long t_begin = 0;
+      if constexpr (DBG) t_begin = clock64();
+      [&]() __attribute__((always_inline)) {
       if (tk.kind == TK_REWARD) {
         if (!(ph & RL_PHASE_REWARDS)) return;
-        const float raw = reward_term(rt, S, L, sm, e, c, tk.lo, tk.hi);
+        const float raw = reward_term(rt, c_spec[a.slot].rewards[tk.a], S, L, sm, e, c, tk.lo, tk.hi);
         const int k = tk.a;
+        float full_raw = raw;
+        bool finish = true;
         if (tk.pad) {
-          SMF(L.termv, 2 * k + tk.b) = raw;   // partial of a split term: finished in stage 2
-        } else {
+          // one half of a split term: publish the partial; whoever arrives second (per env) adds the halves in
+          // slot order and finishes the term - no serial tail for it in stage 2
+          SMF(L.termv, 2 * k + tk.b) = raw;
+          __threadfence_block();
+          const int old = atomicAdd(reinterpret_cast<int*>(sm) + L.arrive + k * kE + e, 1);
+          finish = (old == 1);
+          if (finish) {
+            __threadfence_block();
+            full_raw = *(volatile float*)&SMF(L.termv, 2 * k) + *(volatile float*)&SMF(L.termv, 2 * k + 1);
+          }
+        }
+        if (finish) {
           // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
-          const float val = (raw * rt.weight) * S.step_dt;
+          const float val = (full_raw * rt.weight) * S.step_dt;
           SMF(L.termv, 2 * k) = val;
           SMF(L.sums, k) = SMF(L.sums, k) + val;
-          SMF(L.stepr, k) = val / S.step_dt;
+          SMF(L.stepr, k) = rl_div(val, S.step_dt);
         }
       } else if (tk.kind == TK_OBS) {
         if (!(ph & RL_PHASE_OBS) || a.out.obs[tk.a] == nullptr) return;
-        obs_task(sm, L, S, ot, corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
+        obs_task(sm, L, S, ot, c_spec[a.slot].obs[tk.a].terms[tk.b], corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
       } else if (tk.kind == TK_DONES) {
         if (!(ph & RL_PHASE_DONES)) return;
         SMF(L.epnew, 0) = __int_as_float(eplen_now);
@@ -1495,14 +1428,14 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
           SMF(L.cmdn, 0) = c.c0; SMF(L.cmdn, 1) = c.c1; SMF(L.cmdn, 2) = c.c2;
         }
         if (ph & RL_PHASE_OBS) {
-          P::for_cmd_obs(a, [&](const RlObsTerm& t, int g, int ti, int col0, bool corr) {
+          P::for_cmd_obs(a, [&](const RlObsTerm& t, int g, int ti, int col0, bool corr) __attribute__((always_inline)) {
             if (a.out.obs[g] == nullptr) return;
-            obs_task(sm, L, S, t, corr, a, rs, g, ti, col0, 0, t.dim, e, env, c, eplen_now);
+            obs_task(sm, L, S, t, c_spec[a.slot].obs[g].terms[ti], corr, a, rs, g, ti, col0, 0, t.dim, e, env, c, eplen_now);
           });
         }
       }
       }();
-      if (a.dbg != nullptr && e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + task_idx] = clock64() - t_begin;
+      if constexpr (DBG) { if (e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + task_idx] = clock64() - t_begin; }
     });
     __syncthreads();
     RL_STAMP(3);                // stage 1 done
@@ -1512,22 +1445,35 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
       const bool terminated = ((fl >> 8) & 1) != 0;
       float total = 0.f;
-      P::template for_rewards<NW>(a, [&](const RlRewardTerm& t, int k, bool split, bool late) {
-        if (t.weight == 0.f) { SMF(L.stepr, k) = 0.f; return; }
-        float val;
-        if (late) {
-          float raw;
-          if (t.type == RL_REW_IS_TERMINATED) raw = terminated ? 1.f : 0.f;
-          else raw = split ? (SMF(L.termv, 2 * k) + SMF(L.termv, 2 * k + 1)) : SMF(L.termv, 2 * k);
-          val = (raw * t.weight) * S.step_dt;
-          SMF(L.sums, k) = SMF(L.sums, k) + val;
-          SMF(L.stepr, k) = val / S.step_dt;
-        } else {
-          val = SMF(L.termv, 2 * k);
-        }
-        total += val;
-      });
+      // rolled loops on purpose (warp 0 runs them alone); weights / flags come from the parameter bank.
+      // pass 1: finish the late terms (partials of split terms, is_terminated) and zero the step reward of the
+      // weight-0 terms; pass 2: the reward, summed in manager order with 4 loads in flight
+      for (uint64_t m = a.rw_zero; m != 0; m &= m - 1) {
+        const int k = __ffsll((long long)m) - 1;
+        SMF(L.stepr, k) = 0.f; SMF(L.termv, 2 * k) = 0.f;
+      }
+#pragma unroll 1
+      for (uint64_t m = a.rw_late & ~a.rw_zero; m != 0; m &= m - 1) {
+        const int k = __ffsll((long long)m) - 1;
+        float raw;
+        if ((a.rw_isterm >> k) & 1ull) raw = terminated ? 1.f : 0.f;
+        else raw = ((a.rw_split >> k) & 1ull) ? (SMF(L.termv, 2 * k) + SMF(L.termv, 2 * k + 1)) : SMF(L.termv, 2 * k);
+        const float val = (raw * a.rw_weight[k]) * S.step_dt;
+        SMF(L.termv, 2 * k) = val;
+        SMF(L.sums, k) = SMF(L.sums, k) + val;
+        SMF(L.stepr, k) = rl_div(val, S.step_dt);
+      }
+      RL_SUB(3);                // late terms finished
+      int k = 0;
+#pragma unroll 1
+      for (; k + 4 <= K; k += 4) {
+        const float v0 = SMF(L.termv, 2 * k), v1 = SMF(L.termv, 2 * k + 2), v2 = SMF(L.termv, 2 * k + 4), v3 = SMF(L.termv, 2 * k + 6);
+        total += v0; total += v1; total += v2; total += v3;
+      }
+#pragma unroll 1
+      for (; k < K; ++k) total += SMF(L.termv, 2 * k);
       SMF(L.rew, 0) = total;
+      RL_SUB(4);                // reward summed
     }
     __syncthreads();
     RL_STAMP(4);                // stage 2 done
@@ -1549,12 +1495,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       }
       if (tid == 0) bulk_commit();
     }
-    if constexpr (P::kStatic) {
-      if (full) store_rows_static<typename P::Baked, NT>(sm, a, env0, tid);
-      else store_rows(sm, a, env0, nvalid, ids, full, tid, NT);
-    } else {
-      store_rows(sm, a, env0, nvalid, ids, full, tid, NT);
-    }
+    store_fields(sm, a, env0, nvalid, ids, full, warp, e, NW);
     if (ph & RL_PHASE_DONES) {
       if (tid < nvalid) {
         const int f2 = __float_as_int(sm[L.flags + tid]);
@@ -1590,31 +1531,42 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       int* s_cnt = reinterpret_cast<int*>(sm);  // this CTA's tile is dead once its own stores have been issued
       if ((ph & RL_PHASE_OBS) && nvalid > 0) { if (tid == 0) bulk_wait_read0(); }
       __syncthreads();
-      // gridDim.x masks; thread i owns a contiguous run of CTAs -> ids come out ascending
+      // one mask per CTA; thread i takes mask base+i, a block-wide exclusive scan of the popcounts gives its
+      // first output slot -> ids come out ascending
       const int G = gridDim.x;
-      const int per = (G + NT - 1) / NT;
-      const int g0 = tid * per, g1 = min(G, g0 + per);
-      int cnt = 0;
-      for (int g = g0; g < g1; ++g) cnt += __popc(__ldcg(a.cta_mask + g));
-      s_cnt[tid] = cnt;
-      __syncthreads();
-      if (tid == 0) {
-        int run = 0;
-        for (int i = 0; i < NT; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
-        if (a.out.n_reset) *a.out.n_reset = run;
-        *a.ticket = 0u;
-      }
-      __syncthreads();
-      int pos = s_cnt[tid];
-      if (a.out.reset_ids)
-        for (int g = g0; g < g1; ++g) {
-          unsigned m = __ldcg(a.cta_mask + g);
+      int run = 0;
+#pragma unroll 1
+      for (int base = 0; base < G; base += NT) {
+        const int g = base + tid;
+        unsigned m = (g < G) ? __ldcg(a.cta_mask + g) : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;   // inclusive scan inside the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (e >= d) incl += y; }
+        if (e == 31) s_cnt[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+          int wt = (e < NW) ? s_cnt[e] : 0, wi = wt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wi, d); if (e >= d) wi += y; }
+          if (e < NW) s_cnt[e] = wi - wt;           // exclusive prefix of the warp totals
+          if (e == 31) s_cnt[32] = wi;              // chunk total
+        }
+        __syncthreads();
+        int pos = run + s_cnt[warp] + incl - cnt;
+        if (a.out.reset_ids)
           while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             a.out.reset_ids[pos++] = g * kE + b;
           }
-        }
+        run += s_cnt[32];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        if (a.out.n_reset) *a.out.n_reset = run;
+        *a.ticket = 0u;
+      }
       return;
     }
   }
@@ -1657,20 +1609,20 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
   if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
   const RlActionCfg& ac = c_spec[slot].action;
   const int A = ac.n_actions;
-  const long long total = (long long)N * A;
+  const int total = N * A;   // < 2^31, checked by the host
   const bool env_major = (new_action.env_stride == 1);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long env; int col;
-    if (env_major) { env = i % N; col = (int)(i / N); } else { col = (int)(i % A); env = i / A; }
-    const float nv = static_cast<const float*>(new_action.ptr)[env * new_action.env_stride + col * new_action.comp_stride];
-    float* ap = static_cast<float*>(action.ptr) + env * action.env_stride + col * action.comp_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int env, col;
+    if (env_major) { env = i % N; col = i / N; } else { col = i % A; env = i / A; }
+    const float nv = static_cast<const float*>(new_action.ptr)[(long long)env * new_action.env_stride + col * new_action.comp_stride];
+    float* ap = static_cast<float*>(action.ptr) + (long long)env * action.env_stride + col * action.comp_stride;
     if (prev_action.ptr)
-      static_cast<float*>(prev_action.ptr)[env * prev_action.env_stride + col * prev_action.comp_stride] = *ap;
+      static_cast<float*>(prev_action.ptr)[(long long)env * prev_action.env_stride + col * prev_action.comp_stride] = *ap;
     *ap = nv;
     if (target.ptr) {
       float v = nv * ac.scale[col] + ac.offset[col];
       if (ac.has_clip) v = clampf(v, ac.clip_lo[col], ac.clip_hi[col]);
-      static_cast<float*>(target.ptr)[env * target.env_stride + (long long)ac.joint_ids[col] * target.comp_stride] = v;
+      static_cast<float*>(target.ptr)[(long long)env * target.env_stride + (long long)ac.joint_ids[col] * target.comp_stride] = v;
     }
   }
 }
@@ -1687,14 +1639,12 @@ struct RlCtx {
   int NW;                 // warps per CTA (kE = 32 envs per CTA is fixed)
   Layout L;
   Schedule* sched_dev;
+  Schedule sched;         // host copy of the schedule of the current launch config
   unsigned int* ticket;
   uint32_t* cta_mask;
   float* log_partials;
   int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
-  uint32_t* in_rows_dev;
-  uint32_t* out_rows_dev;
-  int n_in_rows, n_out_rows;
   int sm_count;
   int use_pdl;
   long long* dbg;
@@ -1703,32 +1653,6 @@ struct RlCtx {
 
 namespace {
 
-
-// static row tables (field, component, record word); E-independent
-int build_row_tables(RlCtx* ctx) {
-  const RlStepSpec& s = ctx->spec;
-  const Layout L = make_layout(s);
-  uint32_t rows[2048];
-  int n = 0, word = 0;
-  for (int f = 0; f < IF_COUNT; ++f) {  // same running word count as make_layout
-    for (int c = 0; c < in_field_ncomp(s, f); ++c) rows[n++] = row_pack(f, c, word + c);
-    word += in_field_ncomp(s, f);
-  }
-  ctx->n_in_rows = n;
-  CUDA_TRY(cudaMalloc(&ctx->in_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
-  CUDA_TRY(cudaMemcpy(ctx->in_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
-  n = 0;
-  const int K = s.num_reward_terms;
-  const int A = s.action.n_actions;
-  const int ow[OF_COUNT] = {L.w_rew, L.w_eplen, L.w_sums, L.w_stepr, L.w_cmd, L.w_head, L.w_tleft, L.w_mxy, L.w_myaw, L.w_act, L.w_pact};
-  const int oc[OF_COUNT] = {1, 1, K, K, 3, 1, 1, 1, 1, A, A};
-  for (int f = 0; f < OF_COUNT; ++f)
-    for (int c = 0; c < oc[f]; ++c) rows[n++] = row_pack(f, c, ow[f] + c);
-  ctx->n_out_rows = n;
-  CUDA_TRY(cudaMalloc(&ctx->out_rows_dev, sizeof(uint32_t) * (n > 0 ? n : 1)));
-  CUDA_TRY(cudaMemcpy(ctx->out_rows_dev, rows, sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
-  return RL_OK;
-}
 
 bool to_fd(const RlField& f, FieldD* out) {
   if (f.env_stride > 0x7fffffffLL || f.comp_stride > 0x7fffffffLL || f.env_stride < 0 || f.comp_stride < 0) return false;
@@ -1746,8 +1670,16 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
   memset(&a, 0, sizeof(a));
   a.N = (int)num_envs; a.slot = ctx->slot; a.phases = ph;
   a.L = ctx->L; a.sched = ctx->sched_dev;
-  a.in_rows = ctx->in_rows_dev; a.n_in_rows = ctx->n_in_rows;
-  a.out_rows = ctx->out_rows_dev; a.n_out_rows = ctx->n_out_rows;
+  {
+    const Schedule& sc = ctx->sched;
+    for (int k = 0; k < s.num_reward_terms; ++k) {
+      a.rw_weight[k] = s.rewards[k].weight;
+      if (sc.late[k]) a.rw_late |= 1ull << k;
+      if (sc.split[k]) a.rw_split |= 1ull << k;
+      if (s.rewards[k].type == RL_REW_IS_TERMINATED) a.rw_isterm |= 1ull << k;
+      if (s.rewards[k].weight == 0.f) a.rw_zero |= 1ull << k;
+    }
+  }
   a.ticket = ctx->ticket; a.cta_mask = ctx->cta_mask; a.log_partials = ctx->log_partials; a.use_pdl = ctx->use_pdl;
   a.dbg = ctx->dbg;
   if (out) a.out = *out;
@@ -1788,6 +1720,7 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
     else if (vec4_ok(a.in[f], in_field_ncomp(s, f))) v4 |= 1u << f;
   }
   a.in_mask = m; a.in_vec4 = v4;
+  for (int f = 0; f < IF_COUNT; ++f) a.in[f].meta = in_field_ncomp(s, f) | (in_field_word(s, f) << 16);
   // outputs
   if (mode == 0) {
     a.outf[OF_REWARD] = FieldD{a.out.reward, 1, 0};
@@ -1809,6 +1742,7 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
       else if (vec4_ok(a.outf[f], oc[f])) ov4 |= 1u << f;
     }
     a.out_mask = om; a.out_vec4 = ov4;
+    for (int f = 0; f < OF_COUNT; ++f) a.outf[f].meta = out_field_ncomp(s, f) | (out_field_word(ctx->L, f) << 16);
   }
   return RL_OK;
 }
@@ -1851,13 +1785,13 @@ int validate_spec(const RlStepSpec* s) {
   return RL_OK;
 }
 
-template <class P, int NW, int MODE>
-int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
+template <class P, int NW, int MODE, bool DBG>
+int launch_step_variant(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   const size_t smem = (size_t)ctx->L.total_words * 4;
   static thread_local int configured_device = -1;
   static thread_local size_t configured_smem = 0;
   if (configured_device != ctx->device || configured_smem < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = ctx->device; configured_smem = smem;
   }
   const int grid = (n_items + kE - 1) / kE;
@@ -1869,13 +1803,22 @@ int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE>, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE, DBG>, a));
   return RL_OK;
+}
+// the clock-stamp variant (rl_ctx_set_debug_buffer) is a separate instantiation: the production kernel carries
+// no trace of it
+template <class P, int NW, int MODE>
+int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
+  if constexpr (MODE == 0) {
+    if (a.dbg != nullptr) return launch_step_variant<P, NW, MODE, true>(ctx, a, n_items, st);
+  }
+  return launch_step_variant<P, NW, MODE, false>(ctx, a, n_items, st);
 }
 
 // warps per CTA compiled for the generic kernel / for every baked spec
 #define RL_DYN_CONFIGS(X) X(4) X(8) X(16)
-#define RL_STATIC_CONFIGS(X) X(8) X(16) X(24) X(32)
+#define RL_STATIC_CONFIGS(X) X(8) X(16)
 
 template <class P, int MODE>
 int dispatch_config(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st, bool* found) {
@@ -1975,7 +1918,7 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   ctx->device = device;
   ctx->slot = slot;
   ctx->spec = *spec;
-  ctx->NW = 8;
+  ctx->NW = 16;
   ctx->L = make_layout(ctx->spec);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1985,17 +1928,13 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
     return fail(RL_EUNSUPPORTED, "the tile of %s%lld envs needs %lld bytes of shared memory", "", kE, (long long)make_layout(*spec).total_words * 4);
   }
   CUDA_TRY(cudaMalloc(&ctx->sched_dev, sizeof(Schedule)));
-  {
-    const Schedule sc = make_schedule(ctx->spec, ctx->NW);
-    CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));
-  }
+  ctx->sched = make_schedule(ctx->spec, ctx->NW);
+  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &ctx->sched, sizeof(Schedule), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpyToSymbol(c_spec, spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * slot));
   CUDA_TRY(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
   CUDA_TRY(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(&ctx->adhoc_dev, sizeof(RlRewardTerm) * 64));
   rc = ensure_scratch(ctx, 4096);
-  if (rc != RL_OK) return rc;
-  rc = build_row_tables(ctx);
   if (rc != RL_OK) return rc;
   ctx->baked = -1;
   {
@@ -2016,9 +1955,7 @@ void rl_ctx_destroy(RlCtx* ctx) {
   if (ctx->cta_mask) cudaFree(ctx->cta_mask);
   if (ctx->log_partials) cudaFree(ctx->log_partials);
   if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
-  if (ctx->in_rows_dev) cudaFree(ctx->in_rows_dev);
   if (ctx->sched_dev) cudaFree(ctx->sched_dev);
-  if (ctx->out_rows_dev) cudaFree(ctx->out_rows_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
 }
@@ -2026,20 +1963,18 @@ void rl_ctx_destroy(RlCtx* ctx) {
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
   if (envs_per_cta != 0 && envs_per_cta != kE) return fail(RL_EINVAL, "envs_per_cta is fixed at %s%lld (one lane per env)", "", kE);
-  const int nw = warps_per_cta > 0 ? warps_per_cta : 8;
-  const bool generic_ok = (nw == 4 || nw == 8 || nw == 16), baked_ok = (nw == 8 || nw == 16 || nw == 24 || nw == 32);
-  if (!(ctx->baked >= 0 ? (baked_ok || generic_ok) : generic_ok))
-    return fail(RL_EINVAL, "warps_per_cta must be 4, 8 or 16 (8, 16, 24 or 32 for a build-time specialised task)%s, got %lld", "", nw);
+  const int nw = warps_per_cta > 0 ? warps_per_cta : 16;
+  if (nw != 4 && nw != 8 && nw != 16) return fail(RL_EINVAL, "warps_per_cta must be 4, 8 or 16%s, got %lld", "", nw);
   DeviceGuard guard(ctx->device);
-  const Schedule sc = make_schedule(ctx->spec, nw);
-  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &sc, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
+  ctx->sched = make_schedule(ctx->spec, nw);
+  CUDA_TRY(cudaMemcpy(ctx->sched_dev, &ctx->sched, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
   ctx->NW = nw;
   return RL_OK;
 }
 
 int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out, int32_t* n_tasks) {
   if (!ctx || !out || !n_tasks) return fail(RL_EINVAL, "null argument%s", "");
-  const Schedule sc = make_schedule(ctx->spec, ctx->NW);
+  const Schedule& sc = ctx->sched;
   *n_tasks = sc.n;
   for (int i = 0; i < sc.n; ++i) {
     const Task& t = sc.t[i];
@@ -2069,6 +2004,7 @@ int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, c
   DeviceGuard guard(ctx->device);
   RlField tgt = joint_target ? *joint_target : RlField{nullptr, 0, 0};
   const long long total = num_envs * ctx->spec.action.n_actions;
+  if (total >= (1ll << 31)) return fail(RL_EINVAL, "rl_process_action: num_envs * n_actions must stay below 2^31%s", "");
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
   if (blocks <= 0) return RL_OK;

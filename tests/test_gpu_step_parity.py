@@ -52,12 +52,10 @@ def test_ragged_env_counts(native_lib, n):
     H.compare_outputs(got, ref)
 
 
-@pytest.mark.parametrize("warps", [4, 8, 16, 24, 32])
+@pytest.mark.parametrize("warps", [4, 8, 16])
 @pytest.mark.parametrize("full_layout", [False, True])
 def test_launch_configs_agree(native_lib, warps, full_layout):
     """Every warp count (different static schedules), baked kernels (compact layout) and the generic kernel."""
-    if full_layout and warps > 16:
-        pytest.skip("generic kernel is compiled for 4 / 8 / 16 warps")
     got, ref = _run("go2_rough", 1000, cfg_launch=warps, full_layout=full_layout)
     H.compare_outputs(got, ref)
 

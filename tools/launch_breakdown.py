@@ -1,0 +1,82 @@
+"""Steady-state cost of each launch of one env step, measured back to back with CUDA events (production kernels,
+no debug buffer): process_action | rl_step(ALL|SKIP) | rl_step(RESET|COMMAND|OBS on reset ids) and a few phase
+subsets of the fused kernel. Rotates over independent state sets larger than L2.
+
+Usage (GPU box): python tools/launch_breakdown.py [num_envs] [warps] [task_key]
+"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+
+import torch  # noqa: E402
+
+import helpers as H  # noqa: E402
+from robot_lab_b200 import _native as nat  # noqa: E402
+from robot_lab_b200.engine import MdpStepEngine  # noqa: E402
+from robot_lab_b200.synthetic import make_state  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
+cfg, spec = H.make_spec(key)
+eng = MdpStepEngine(spec, "cuda:0")
+eng.set_launch_config(W)
+n_sets = max(2, min(24, int(400e6 / (N * 3500)) + 1))
+sets = []
+for i in range(n_sets):
+    b = eng.new_buffers(N)
+    b.load_logical(make_state(spec, N, seed=1234 + i))
+    b.cmd_uniforms, b.obs_uniforms = None, [None, None]
+    sets.append(b)
+ALL = nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS
+POST = nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS
+
+
+def run_step(b):
+    eng.step(b, phases=ALL, use_random_inputs=False, use_step_counter=True)
+
+
+def run_post(b):
+    eng.step(b, phases=POST, use_random_inputs=False, use_step_counter=True, env_ids=b.reset_ids, n_env_ids=b.n_reset)
+
+
+CASES = {
+    "process_action": lambda b: eng.process_action(b),
+    "rl_step ALL|SKIP_DONE": run_step,
+    "rl_step RESET|COMMAND|OBS (reset ids)": run_post,
+    "rl_step DONES only": lambda b: eng.step(b, phases=nat.PHASE_DONES, use_random_inputs=False),
+    "rl_step DONES|REWARDS": lambda b: eng.step(b, phases=nat.PHASE_DONES | nat.PHASE_REWARDS, use_random_inputs=False),
+    "rl_step OBS only": lambda b: eng.step(b, phases=nat.PHASE_OBS, use_random_inputs=False),
+    "rl_step COMMAND only": lambda b: eng.step(b, phases=nat.PHASE_COMMAND, use_random_inputs=False),
+    "whole env step (3 launches)": lambda b: (eng.process_action(b), run_step(b), run_post(b)),
+}
+for b in sets:  # reset ids valid for the post-reset case
+    run_step(b)
+torch.cuda.synchronize()
+print(f"{key} N={N} warps={W} state sets={n_sets}; mean reset envs per step: "
+      f"{sum(int(b.n_reset.item()) for b in sets) / len(sets):.1f}")
+for pdl in (False, True):
+    eng.set_pdl(pdl)
+    for name, fn in CASES.items():
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for b in sets:
+                fn(b)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                for b in sets:
+                    fn(b)
+            for _ in range(3):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record(s)
+            for _ in range(reps):
+                g.replay()
+            e1.record(s)
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
+        print(f"  pdl={int(pdl)}  {name:42s} {us:8.2f} us")

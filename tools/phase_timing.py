@@ -20,7 +20,8 @@ W = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
 PHASES = {"all": nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, "dones": nat.PHASE_DONES, "rewards": nat.PHASE_REWARDS,
           "obs": nat.PHASE_OBS, "command": nat.PHASE_COMMAND, "dones+compact": nat.PHASE_DONES | nat.PHASE_COMPACT,
-          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS}
+          "dones+rewards": nat.PHASE_DONES | nat.PHASE_REWARDS,
+          "post": nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS}
 phase_name = sys.argv[4] if len(sys.argv) > 4 else "all"
 cfg, spec = H.make_spec(key)
 eng = MdpStepEngine(spec, "cuda:0")
@@ -34,9 +35,24 @@ for i in range(8):
 grid = (N + 31) // 32
 dbg = torch.zeros(grid, nat.RL_DEBUG_STRIDE, dtype=torch.int64, device="cuda:0")
 PH = PHASES[phase_name]
+POST = phase_name == "post"
+
+
+def launch(b):
+    if POST:
+        eng.step(b, phases=PH, use_random_inputs=False, env_ids=b.reset_ids, n_env_ids=b.n_reset)
+    else:
+        eng.step(b, phases=PH, use_random_inputs=False)
+
+
+if POST:
+    for b in sets:
+        eng.step(b, phases=nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, use_random_inputs=False)
+    torch.cuda.synchronize()
+    print("reset envs per set:", [int(b.n_reset.item()) for b in sets])
 for it in range(6):
     for b in sets:
-        eng.step(b, phases=PH, use_random_inputs=False)
+        launch(b)
 torch.cuda.synchronize()
 eng.set_debug_buffer(dbg)
 names = ["start->loads issued", "loads issued->tile resident", "tile resident->stage1 done", "stage1->stage2 done",
@@ -46,19 +62,24 @@ mx = torch.zeros(7)
 sched = eng.schedule()
 task_acc = torch.zeros(len(sched))
 enter_acc = torch.zeros(W)
+sub_acc = torch.zeros(5)
 tot = []
 reps = 8
 for it in range(reps):
     b = sets[it % len(sets)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    eng.step(b, phases=PH, use_random_inputs=False)
+    launch(b)
     ev1.record()
     torch.cuda.synchronize()
     dall = dbg.cpu().double()
+    if POST:
+        dall = dall[: (int(b.n_reset.item()) + 31) // 32]
     d = dall[:, :8]
     task_acc += dall[:, 8:8 + len(sched)].mean(0).float()
     enter_acc += (dall[:, 8 + nat.RL_MAX_TASKS:8 + nat.RL_MAX_TASKS + W] - dall[:, 2:3]).mean(0).float()
+    sub = dall[:, 8 + nat.RL_MAX_TASKS + 32:8 + nat.RL_MAX_TASKS + 37] - dall[:, 0:1]
+    sub_acc += sub.mean(0).float()
     dur = d[:, 1:] - d[:, :-1]
     dur[dur.abs() > 1e8] = 0  # stamps a CTA skipped (early return of the compacting CTA)
     acc += dur.mean(0).float()
@@ -68,6 +89,8 @@ for it in range(reps):
 print(f"{key} N={N} warps={W} grid={grid} phases={phase_name}")
 for n, a_, m_ in zip(names, acc / reps, mx):
     print(f"  {n:32s} mean {a_:9.0f} cyc   max {m_:9.0f} cyc")
+print("  cycles since kernel start: bulk copies issued %.0f, per-field copies issued %.0f, span loads issued %.0f; "
+      "stage 2: late terms finished %.0f, reward summed %.0f" % tuple((sub_acc / reps).tolist()))
 print("  per-CTA total cycles (mean, max), event us:", [tuple(round(x, 1) for x in t) for t in tot[-3:]])
 
 if phase_name == "all":
