@@ -324,10 +324,16 @@ enum RlPhase {
   RL_PHASE_COMPACT = 16,    /* reset id compaction (ascending)                              */
   RL_PHASE_SKIP_DONE_ENVS = 32, /* COMMAND/OBS only for envs that are not done this step
                                    (they are refreshed after the external reset instead)   */
-  RL_PHASE_RESET = 64,      /* env_ids launches only: manager reset of those envs BEFORE the other phases -
-                               logging means (RlStepOut.reset_log), zero episode sums / metrics / actions /
-                               episode length, command resample. RESET|COMMAND|OBS is the whole post-reset
-                               part of ManagerBasedRLEnv.step() [IL] in one launch                     */
+  RL_PHASE_RESET = 64,      /* manager reset BEFORE the other phases of the launch - logging means
+                               (RlStepOut.reset_log), zero episode sums / metrics / actions / episode length,
+                               command resample. Combines with COMMAND / OBS only. Two forms:
+                               - with env_ids: every env of the list is reset (gathered tiles);
+                               - without: all envs are processed and those whose out->terminated |
+                                 out->truncated byte is set are reset (out->n_reset = their count, as left by
+                                 the DONES | COMPACT launch) - full-tile fast path.
+                               RESET|COMMAND|OBS is the whole post-reset part of ManagerBasedRLEnv.step() [IL]
+                               in one launch; DONES|REWARDS|COMPACT followed by it reproduces the reference's
+                               order terminations -> rewards -> reset -> command -> observations exactly.  */
   RL_PHASE_ALL = 31
 };
 

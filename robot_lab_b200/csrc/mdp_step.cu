@@ -93,6 +93,7 @@ struct Layout {
   int jpos, jvel, jacc, jtau;
   int act, pact;
   int cmd, head, tleft, ishead, isstand;
+  int rmask;                                      // 1 = this env is being reset by the launch (RESET phase)
   int cmdn, epnew;                                // updated command / episode length (committed by the store phase)
   int mxy, myaw, eplen;
   int sums;
@@ -168,6 +169,7 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   L.w_head = in_word[IF_HEAD]; L.w_tleft = in_word[IF_TLEFT]; L.w_mxy = in_word[IF_MXY]; L.w_myaw = in_word[IF_MYAW];
   L.w_act = in_word[IF_ACT]; L.w_pact = in_word[IF_PACT];
   L.ishead = take(1) * E; L.isstand = take(1) * E;
+  L.rmask = take(1) * E;
   // results the step commits at the end: tasks of the same stage still read the old command / episode length
   { const int wn = take(3); L.cmdn = wn * E; L.w_cmd = wn; }
   { const int wn = take(1); L.epnew = wn * E; L.w_eplen = wn; }
@@ -292,15 +294,27 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
     }
   }
   sc.n = n;
-  // longest-processing-time greedy over the warps
-  int load[32] = {};
-  bool done[RL_MAX_TASKS] = {};
-  for (int it = 0; it < n; ++it) {
-    int best = -1;
-    for (int i = 0; i < n; ++i) if (!done[i] && (best < 0 || cost[i] > cost[best])) best = i;
-    int w = 0;
-    for (int j = 1; j < nw; ++j) if (load[j] < load[w]) w = j;
-    sc.t[best].owner = (uint8_t)w; load[w] += cost[best]; done[best] = true;
+  // longest-processing-time greedy over the warps, separately for the two task classes an env step runs in
+  // separate launches (terminations + rewards before the reset, command + observations after it): each launch
+  // sees a balanced schedule, and so does a launch that runs everything
+  for (int cls = 0; cls < 2; ++cls) {
+    int load[32] = {};
+    bool done[RL_MAX_TASKS] = {};
+    for (int it = 0; it < n; ++it) {
+      int best = -1;
+      for (int i = 0; i < n; ++i) {
+        const bool in_cls = ((sc.t[i].kind == TK_REWARD || sc.t[i].kind == TK_DONES) ? 0 : 1) == cls;
+        if (in_cls && !done[i] && (best < 0 || cost[i] > cost[best])) best = i;
+      }
+      if (best < 0) break;
+      // ties go to the higher warp for the second class so that a launch running both does not pile up on warp 0
+      int w = cls == 0 ? 0 : nw - 1;
+      for (int j = 0; j < nw; ++j) {
+        const int jj = cls == 0 ? j : nw - 1 - j;
+        if (load[jj] < load[w]) w = jj;
+      }
+      sc.t[best].owner = (uint8_t)w; load[w] += cost[best]; done[best] = true;
+    }
   }
   return sc;
 }
@@ -1138,11 +1152,11 @@ __device__ __forceinline__ void load_fields(float* sm, const KArgs& a, int env0,
     }
   }
 }
-__device__ __forceinline__ void store_fields(const float* sm, const KArgs& a, int env0, int nvalid, const int32_t* ids,
-                                             bool full, int warp, int lane, int nwarps) {
+__device__ __forceinline__ void store_fields(const float* sm, const KArgs& a, uint32_t omask, int env0, int nvalid,
+                                             const int32_t* ids, bool full, int warp, int lane, int nwarps) {
 #pragma unroll 1
   for (int f = warp; f < OF_COUNT; f += nwarps) {
-    if (!((a.out_mask >> f) & 1u)) continue;
+    if (!((omask >> f) & 1u)) continue;
     const FieldD fd = a.outf[f];
     const int nc = fd.meta & 0xffff, w0 = fd.meta >> 16;
     if (full && ((a.out_vec4 >> f) & 1u)) {
@@ -1221,8 +1235,12 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
   const int env0 = blockIdx.x * kE;
   const int K = S.num_reward_terms;
-  const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) && a.has_ids;
-  if (do_reset && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
+  // RESET comes in two forms: on an env-id list (gathered tiles, every env of the launch is reset) or - without
+  // a list - over all envs, resetting those whose terminated | truncated byte is set (full-tile fast path)
+  const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) != 0;
+  const bool reset_masked = do_reset && !a.has_ids;
+  const int n_reset_total = do_reset ? (reset_masked ? *a.out.n_reset : n_total) : 0;
+  if (do_reset && n_reset_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
     // nothing to reset: the logged scalars are defined as 0
     if (tid < K) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
     else if (tid < K + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K] = 0.f; }
@@ -1248,9 +1266,10 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     // issue of everything else
     const bool want_cmd_flags = (MODE == 0) && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) != 0;
     const bool want_done_bits = do_reset && a.out.done_bits != nullptr;
-    int u8_head = 0, u8_stand = 0, u8_bits = 0;
+    int u8_head = 0, u8_stand = 0, u8_bits = 0, u8_reset = do_reset ? 1 : 0;
     if (tid < nvalid) {
       const long long ev = ids ? (long long)ids[env0 + tid] : (long long)(env0 + tid);
+      if (reset_masked) u8_reset = (a.out.terminated[ev] | a.out.truncated[ev]) != 0;
       if (want_cmd_flags) {
         if (a.is_heading.ptr) u8_head = static_cast<const uint8_t*>(a.is_heading.ptr)[ev * a.is_heading.es];
         if (a.is_standing.ptr) u8_stand = static_cast<const uint8_t*>(a.is_standing.ptr)[ev * a.is_standing.es];
@@ -1287,6 +1306,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       if (want_cmd_flags) { sm[L.ishead + tid] = __int_as_float(u8_head); sm[L.isstand + tid] = __int_as_float(u8_stand); }
       if (want_done_bits) sm[L.flags + tid] = __int_as_float(u8_bits);
     }
+    if (do_reset && tid < kE) sm[L.rmask + tid] = __int_as_float(tid < nvalid ? u8_reset : 0);
     RL_STAMP(1);                // all loads issued
     cp_async_wait_all();
     __syncthreads();            // record + mbarrier init visible to everyone
@@ -1297,14 +1317,19 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const bool valid = e < nvalid;
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
   if (nvalid > 0) {
-    // ---- manager reset of the tile's envs (env_ids launches) ---------------------------------------------
-    if (do_reset) {
-      // logging partials of this CTA (summed in CTA order by the last CTA -> deterministic)
+    // ---- manager reset of the tile's envs that are being reset ------------------------------------------
+    const int tile_resets = do_reset ? __syncthreads_or(tid < kE && __float_as_int(sm[L.rmask + (tid & 31)]) != 0) : 0;
+    if (do_reset && !tile_resets) {   // CTA-uniform: nothing to reset here, the logging partials are zero
+      if (tid < K + RL_MAX_DONE_TERMS + 2) a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = 0.f;
+    }
+    if (tile_resets) {
+      const bool rme = __float_as_int(sm[L.rmask + e]) != 0;
+      // logging partials of this CTA (combined by the last CTA in a fixed order -> deterministic):
       // quantity q is reduced by warp q mod NW over its lanes (= envs) with a fixed shuffle tree
 #pragma unroll 1
       for (int q = warp; q < K + RL_MAX_DONE_TERMS + 2; q += NW) {
         float x = 0.f;
-        if (e < nvalid) {
+        if (rme) {
           if (q < K) x = sm[L.sums + q * kE + e];
           else if (q < K + RL_MAX_DONE_TERMS)
             x = (a.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + e]) >> (q - K)) & 1) : 0.f;
@@ -1316,9 +1341,10 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       }
       __syncthreads();
       // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
-      for (int i = tid; i < kE * K; i += NT) sm[L.sums + i] = 0.f;
-      for (int i = tid; i < kE * A; i += NT) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
-      if (tid < kE) {
+      for (int i = tid; i < kE * K; i += NT) if (__float_as_int(sm[L.rmask + (i & 31)]) != 0) sm[L.sums + i] = 0.f;
+      for (int i = tid; i < kE * A; i += NT)
+        if (__float_as_int(sm[L.rmask + (i & 31)]) != 0) { sm[L.act + i] = 0.f; sm[L.pact + i] = 0.f; }
+      if (tid < kE && __float_as_int(sm[L.rmask + tid]) != 0) {
         const int el = tid;
         sm[L.mxy + el] = 0.f; sm[L.myaw + el] = 0.f;
         sm[L.eplen + el] = __int_as_float(0); sm[L.epnew + el] = __int_as_float(0);
@@ -1495,7 +1521,14 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       }
       if (tid == 0) bulk_commit();
     }
-    store_fields(sm, a, env0, nvalid, ids, full, warp, e, NW);
+    {
+      uint32_t omask = a.out_mask;
+      if (do_reset && !tile_resets) {   // nothing was reset here: those fields are unchanged
+        omask &= ~((1u << OF_SUMS) | (1u << OF_ACT) | (1u << OF_PACT));
+        if (!(ph & RL_PHASE_DONES)) omask &= ~(1u << OF_EPLEN);
+      }
+      store_fields(sm, a, omask, env0, nvalid, ids, full, warp, e, NW);
+    }
     if (ph & RL_PHASE_DONES) {
       if (tid < nvalid) {
         const int f2 = __float_as_int(sm[L.flags + tid]);
@@ -1581,13 +1614,25 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     __syncthreads();
     if (s_last) {
       __threadfence();
+      // quantity q = lane, the CTAs' partials strided over the warps, then the warps' sums in warp order
+      float* s_red = sm;   // this CTA's tile is dead once its own stores have been issued
+      if ((ph & RL_PHASE_OBS) && tid == 0) bulk_wait_read0();
+      __syncthreads();
+      for (int q = e; q < K + RL_MAX_DONE_TERMS + 2; q += 32) {
+        float part = 0.f;
+        for (int g = warp; g < n_cta; g += NW) part += __ldcg(a.log_partials + (size_t)g * RL_LOG_STRIDE + q);
+        s_red[warp * RL_LOG_STRIDE + q] = part;
+      }
+      __syncthreads();
       if (tid < K + RL_MAX_DONE_TERMS + 2) {
         float tot = 0.f;
-        for (int g = 0; g < n_cta; ++g) tot += __ldcg(a.log_partials + (size_t)g * RL_LOG_STRIDE + tid);
+        for (int w = 0; w < NW; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
         const RlResetLog& lg = a.out.reset_log;
-        if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / (float)n_total; }
+        const float cnt = (float)max(n_reset_total, 1);
+        if (n_reset_total == 0) tot = 0.f;
+        if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / cnt; }
         else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
-        else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / (float)n_total;
+        else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / cnt;
       }
       if (tid == 0) *a.ticket = 0u;
     }
@@ -1942,6 +1987,9 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
 #define RL_MATCH_BAKED(B) if (ctx->baked < 0 && memcmp(spec, &baked::B::spec, sizeof(RlStepSpec)) == 0) ctx->baked = idx; ++idx;
     RL_BAKED_LIST(RL_MATCH_BAKED)
 #undef RL_MATCH_BAKED
+    // RL_MDPSTEP_GENERIC=1 forces the generic (table-driven) kernel: A/B measurements and tests of that path
+    const char* force_generic = getenv("RL_MDPSTEP_GENERIC");
+    if (force_generic && force_generic[0] == '1') ctx->baked = -1;
   }
   g_slots[device][slot] = true;
   *out = ctx;
@@ -2054,7 +2102,8 @@ int rl_step(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlMdpS
   }
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
     if (out->obs[g] && out->obs_pitch[g] < s.obs[g].dim) return fail(RL_EINVAL, "rl_step: obs_pitch[%s%lld] smaller than the group dim", "", g);
-  if ((phases & RL_PHASE_RESET) && !env_ids) return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET needs env_ids%s", "");
+  if ((phases & RL_PHASE_RESET) && !env_ids && (!out->terminated || !out->truncated || !out->n_reset))
+    return fail(RL_EINVAL, "rl_step: RL_PHASE_RESET without env_ids resets the envs flagged in out->terminated | out->truncated and needs out->n_reset%s", "");
   if ((phases & RL_PHASE_RESET) && (phases & (RL_PHASE_DONES | RL_PHASE_REWARDS))) return fail(RL_EINVAL, "rl_step: RESET combines with COMMAND/OBS only%s", "");
   if ((phases & RL_PHASE_RESET) && (!mdp->episode_sums.ptr || !mdp->prev_action.ptr || !mdp->heading_target.ptr || !mdp->time_left.ptr ||
       !mdp->is_heading_env.ptr || !mdp->is_standing_env.ptr || !mdp->metric_error_vel_xy.ptr || !mdp->metric_error_vel_yaw.ptr))

@@ -97,6 +97,20 @@ class MdpStepEngine:
                   env_id_offset=env_id_offset, use_random_inputs=use_random_inputs, env_ids=b.reset_ids,
                   n_env_ids=b.n_reset, use_step_counter=use_step_counter)
 
+    # ---- the env step as two launches around the external reset (the reference's exact order) ---------------
+    PRE_RESET = nat.PHASE_DONES | nat.PHASE_REWARDS | nat.PHASE_COMPACT
+    POST_RESET = nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS
+
+    def step_pre_reset(self, b: StateBuffers, **rng) -> None:
+        """termination terms, reward terms (+ sums / step reward), reset-id compaction: what ManagerBasedRLEnv.step()
+        [IL] evaluates before ``_reset_idx``."""
+        self.step(b, phases=self.PRE_RESET, **rng)
+
+    def step_post_reset(self, b: StateBuffers, **rng) -> None:
+        """Manager reset (+ logging means) of the envs flagged done by ``step_pre_reset``, then command.compute and
+        both observation groups for ALL envs - full tiles, no gather."""
+        self.step(b, phases=self.POST_RESET, **rng)
+
     def term_eval(self, term: RewardTermSpec, b: StateBuffers, out: torch.Tensor | None = None,
                   terminated: torch.Tensor | None = None) -> torch.Tensor:
         if out is None:

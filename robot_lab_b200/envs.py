@@ -398,15 +398,14 @@ class ManagerBasedRLEnv:
         return self._obs_dict(), self.extras
 
     def step(self, action: torch.Tensor):
-        """ManagerBasedRLEnv.step() [IL] order; three launches of this library + the provider."""
+        """ManagerBasedRLEnv.step() [IL] order: three launches of this library + the provider."""
         b, eng = self.buffers, self.engine
         self.action_manager.process_action(action)                                   # 1 (+ common step counter)
         self.state_provider.advance(self)                                            # 2 physics / sensors
         self.common_step_counter += 1
-        eng.step(b, phases=nat.PHASE_ALL | nat.PHASE_SKIP_DONE_ENVS, **self._rng_kwargs())     # 3-5, 7, 9 + reset ids
+        eng.step_pre_reset(b, **self._rng_kwargs())                                  # 3-5: dones, rewards, reset ids
         self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
-        eng.post_reset(b, seed=self.seed, env_id_offset=self.rank * self.num_envs, use_random_inputs=False,
-                       use_step_counter=True)                                        # 6b + 7 + 9 for the reset ids
+        eng.step_post_reset(b, **self._rng_kwargs())                                 # 6b manager reset, 7 command, 9 obs
         self.extras = {"log": self._log()}
         return self._obs_dict(), b.reward, b.terminated.bool(), b.truncated.bool(), self.extras
 

@@ -186,6 +186,22 @@ class StepSpec:
         write = pol + crit + 1 + 2 * K + 2 * J
         return 4 * (read + write) + 3
 
+    def algorithmic_bytes_per_launch(self, kind: str) -> int:
+        """The same accounting split over the two launches of an env step. ``pre_reset`` = DONES |
+        REWARDS | COMPACT, ``post_reset`` = RESET | COMMAND | OBS over all envs. Root state, joint state and the
+        command are read by both, so the two add up to slightly more than the fused figure."""
+        J, F, R, K, B = self.J, self.Bt, self.R, self.K, self.B
+        pol, crit = self.obs[0].dim, self.obs[1].dim
+        if kind == "pre_reset":
+            read = 13 + 6 * J + 3 + 9 * B + 4 * F + 6 * F + K + 1      # + episode length
+            write = 1 + 2 * K + 1
+            return 4 * (read + write) + 3
+        if kind == "post_reset":
+            read = 13 + 3 * J + 3 + 4 + R + 1                          # + heading target, timer, 2 metrics
+            write = pol + crit + 3 + 4
+            return 4 * (read + write) + 2                              # + the two command flag bytes
+        raise ValueError(kind)
+
     # ---- ctypes image ----
     def to_ctypes(self) -> nat.RlStepSpec:
         s = nat.RlStepSpec()

@@ -120,6 +120,52 @@ def test_skip_done_envs_then_refresh(native_lib):
     eng.close()
 
 
+@pytest.mark.parametrize("key,n", [("go2_rough", 2048), ("g1_rough", 333)])
+def test_two_launch_step_in_reference_order(native_lib, key, n):
+    """DONES|REWARDS|COMPACT, then RESET|COMMAND|OBS over all envs (reset applied to the flagged ones) ==
+    terminations -> rewards -> _reset_idx -> command.compute -> observations, the order of ManagerBasedRLEnv.step()
+    [IL], checked against the oracle run in that order."""
+    cfg, spec = H.make_spec(key)
+    st = make_state(spec, n)
+    eng = _engine(spec)
+    b = eng.new_buffers(n)
+    b.load_logical(st)
+    rnd = H.rnd_inputs(st)
+    eng.step_pre_reset(b)
+    torch.cuda.synchronize()
+    ref = port.step(spec, st, rnd, skip_done_envs=True)   # dones / rewards / reset ids do not depend on the flag
+    got = H.gpu_step_outputs(b)
+    H.compare_outputs(got, ref, keys=["reward", "terminated", "truncated", "done_bits", "episode_length", "episode_sums",
+                                      "step_reward", "reset_ids"])
+    eng.step_post_reset(b)
+    torch.cuda.synchronize()
+    # oracle: reset the done envs, then command.compute and observations for everyone
+    st1 = dict(st)
+    st1.update({k: ref[k] for k in ("episode_length", "episode_sums")})
+    st2, log = port.reset_envs(spec, st1, ref["reset_ids"], ref["done_bits"], rnd)
+    st3 = dict(st1)
+    st3.update(st2)
+    cmd = port.compute_command(spec, st3, rnd, active=torch.ones(n, dtype=torch.bool))
+    st4 = dict(st3)
+    st4.update(cmd)
+    obs_p = port.compute_obs_group(spec, 0, st4, rnd)
+    obs_c = port.compute_obs_group(spec, 1, st4, rnd)
+    torch.testing.assert_close(b.obs[0].cpu(), obs_p, rtol=H.RTOL, atol=H.ATOL)
+    torch.testing.assert_close(b.obs[1].cpu(), obs_c, rtol=H.RTOL, atol=H.ATOL)
+    for k in ("command", "heading_target", "time_left", "is_heading_env", "is_standing_env", "metric_error_vel_xy",
+              "metric_error_vel_yaw", "episode_length", "episode_sums", "action", "prev_action"):
+        want = st4[k]
+        g = b.logical(k).cpu().contiguous()
+        if want.dtype in (torch.bool, torch.int32):
+            assert torch.equal(g.to(want.dtype), want), k
+        else:
+            torch.testing.assert_close(g, want, rtol=H.RTOL, atol=2e-6, msg=k)
+    torch.testing.assert_close(b.log_episode_sum_mean[: spec.K].cpu(), log["episode_sum_mean"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(b.log_done_term_count.cpu(), log["done_term_count"], rtol=0, atol=0)
+    torch.testing.assert_close(b.log_metric_mean.cpu(), log["metric_mean"], rtol=1e-4, atol=1e-6)
+    eng.close()
+
+
 def test_process_action_matches_oracle(native_lib):
     for key in ("go2_rough", "g1_rough"):
         cfg, spec = H.make_spec(key)

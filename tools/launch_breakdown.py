@@ -44,20 +44,24 @@ def run_post(b):
 
 CASES = {
     "process_action": lambda b: eng.process_action(b),
+    "rl_step DONES|REWARDS|COMPACT (pre-reset)": lambda b: eng.step_pre_reset(b, use_random_inputs=False, use_step_counter=True),
+    "rl_step RESET|COMMAND|OBS, all envs (post-reset)": lambda b: eng.step_post_reset(b, use_random_inputs=False, use_step_counter=True),
+    "env step: process_action + pre + post": lambda b: (eng.process_action(b), eng.step_pre_reset(b, use_random_inputs=False, use_step_counter=True),
+                                                       eng.step_post_reset(b, use_random_inputs=False, use_step_counter=True)),
     "rl_step ALL|SKIP_DONE": run_step,
     "rl_step RESET|COMMAND|OBS (reset ids)": run_post,
     "rl_step DONES only": lambda b: eng.step(b, phases=nat.PHASE_DONES, use_random_inputs=False),
     "rl_step DONES|REWARDS": lambda b: eng.step(b, phases=nat.PHASE_DONES | nat.PHASE_REWARDS, use_random_inputs=False),
     "rl_step OBS only": lambda b: eng.step(b, phases=nat.PHASE_OBS, use_random_inputs=False),
     "rl_step COMMAND only": lambda b: eng.step(b, phases=nat.PHASE_COMMAND, use_random_inputs=False),
-    "whole env step (3 launches)": lambda b: (eng.process_action(b), run_step(b), run_post(b)),
+    "env step, older form: process_action + ALL|SKIP + reset ids": lambda b: (eng.process_action(b), run_step(b), run_post(b)),
 }
 for b in sets:  # reset ids valid for the post-reset case
     run_step(b)
 torch.cuda.synchronize()
 print(f"{key} N={N} warps={W} state sets={n_sets}; mean reset envs per step: "
       f"{sum(int(b.n_reset.item()) for b in sets) / len(sets):.1f}")
-for pdl in (False, True):
+for pdl in (False,):
     eng.set_pdl(pdl)
     for name, fn in CASES.items():
         g = torch.cuda.CUDAGraph()
@@ -79,4 +83,4 @@ for pdl in (False, True):
             e1.record(s)
             torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
-        print(f"  pdl={int(pdl)}  {name:42s} {us:8.2f} us")
+        print(f"  pdl={int(pdl)}  {name:58s} {us:8.2f} us")
