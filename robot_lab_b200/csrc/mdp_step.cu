@@ -67,6 +67,7 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0, long lo
 // context and live in global memory; only the ~25 field descriptors (pointer + strides) travel per launch.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
+constexpr int kTermParts = 4;   // a reward term is evaluated in at most this many parts (termv holds that many slots per term)
 
 struct FieldD {
   const void* ptr;
@@ -102,7 +103,7 @@ struct Layout {
   int raypos;
   int cmdu;
   int rew, flags, stepr;                         // outputs
-  int termv;                                     // [K][2] weighted term values (or raw partials of split terms)
+  int termv;                                     // [K][kTermParts] weighted term value in slot 0 (raw partial sums of a split term before it is finished)
   int arrive;                                    // [K] per-env arrival counters of the two halves of a split term
   int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
   int soa_words;
@@ -176,7 +177,7 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   L.w_rew = take(1); L.rew = L.w_rew * E;
   L.flags = take(1) * E;
   L.w_stepr = take(K); L.stepr = L.w_stepr * E;
-  L.termv = take(2 * K) * E;
+  L.termv = take(kTermParts * K) * E;
   L.arrive = take(K) * E;
   L.soa_words = w;
   int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
@@ -213,12 +214,13 @@ enum { TK_REWARD = 0, TK_OBS = 1, TK_DONES = 2, TK_COMMAND = 3 };
 struct Task {
   uint8_t kind, a, b, owner;   // REWARD: a = term k, b = half (0/1); OBS: a = group, b = term index
   uint16_t lo, hi;             // REWARD: body-index range [lo, hi); OBS: column range within the term
-  uint16_t col0, pad;          // OBS: first column of the term inside the group row; REWARD: pad = 1 for a partial (late) term
+  uint16_t col0, pad;          // OBS: first column of the term inside the group row; REWARD: col0 = number of parts,
+                               // pad = 1 for one part of a split term
 };
 struct Schedule {
   int n;
   Task t[RL_MAX_TASKS];
-  uint8_t split[RL_MAX_REWARD_TERMS];   // term evaluated as two partial sums (termv[k][0] + termv[k][1])
+  uint8_t split[RL_MAX_REWARD_TERMS];   // > 0: the term is evaluated in that many parts (termv[k][0..parts))
   uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (split terms, is_terminated)
 };
 
@@ -266,16 +268,42 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
     const RlRewardTerm& t = s.rewards[k];
     if (t.weight == 0.f) continue;
     if (t.type == RL_REW_IS_TERMINATED) { sc.late[k] = 1; continue; }
+    // Long sums over bodies / feet can be cut into up to kTermParts parts; the parts publish raw partial sums and
+    // the one that arrives last (per env) adds them in part order. Measured (profiles/r1_summary.md): every part is
+    // its own straight-line code and costs ~4k cycles of first-touch instruction fetch whatever its length, so
+    // only the one really long term (> 8 bodies) is cut, and only in two.
     const bool body_sum = (t.type == RL_REW_UNDESIRED_CONTACTS || t.type == RL_REW_CONTACT_FORCES);
+    const bool list_sum = (t.type == RL_REW_FEET_SLIDE);
     const int nb = popc64(t.body_mask);
-    if (body_sum && nb > 8) {
-      int seen = 0, mid = 0;  // split after the first nb/2 set bits
-      for (int b = 0; b < 64; ++b) if ((t.body_mask >> b) & 1ull) { if (++seen == nb / 2) { mid = b + 1; break; } }
-      sc.split[k] = 1;   // the half that arrives second (per env) finishes the term, see the kernel
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, (uint16_t)mid, 0, 1}; cost[n++] = reward_cost(t, s, nb / 2);
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 1, 0, (uint16_t)mid, 64, 0, 1}; cost[n++] = reward_cost(t, s, nb - nb / 2);
-    } else {
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 0, 0}; cost[n++] = 30 + reward_cost(t, s, nb);
+    const int items = body_sum ? nb : (list_sum ? t.n_idx : 0);
+    int parts = items > 8 ? 2 : 1;
+    if (parts > kTermParts) parts = kTermParts;
+    if (n + parts > RL_MAX_TASKS - 24) parts = 1;   // table nearly full: stop splitting
+    if (parts < 2) {
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 1, 0}; cost[n++] = 30 + reward_cost(t, s, body_sum ? nb : t.n_idx);
+      continue;
+    }
+    sc.split[k] = (uint8_t)parts;
+    int item0 = 0;
+    for (int p = 0; p < parts; ++p) {
+      const int item1 = (items * (p + 1)) / parts;   // items [item0, item1) belong to part p
+      int lo = item0, hi = item1;
+      if (body_sum) {          // body terms take a body-index range: translate item counts into bit positions
+        int seen = 0; lo = 64; hi = 64;
+        for (int bb = 0; bb < 64; ++bb)
+          if ((t.body_mask >> bb) & 1ull) {
+            if (seen == item0) lo = bb;
+            if (seen == item1) hi = bb;
+            ++seen;
+          }
+        if (p == 0) lo = 0;
+        if (p == parts - 1) hi = 64;
+      } else if (p == parts - 1) {
+        hi = 64;
+      }
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, (uint8_t)p, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)parts, 1};
+      cost[n++] = reward_cost(t, s, item1 - item0);
+      item0 = item1;
     }
   }
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
@@ -284,8 +312,10 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
       const RlObsTerm& o = s.obs[g].terms[ti];
       const int per_col = 8 + ((o.has_noise && s.obs[g].enable_corruption) ? 24 : 0);
       if (o.type != RL_OBS_GENERATED_COMMANDS) {
-        for (int lo = 0; lo < o.dim; lo += 64) {
-          const int hi = (lo + 64 < o.dim) ? lo + 64 : o.dim;
+        // multiples of 4 (one Philox block = 4 columns); coarser when the task table is nearly full
+        const int chunk = (n > RL_MAX_TASKS - 24) ? 256 : 64;
+        for (int lo = 0; lo < o.dim; lo += chunk) {
+          const int hi = (lo + chunk < o.dim) ? lo + chunk : o.dim;
           sc.t[n] = Task{TK_OBS, (uint8_t)g, (uint8_t)ti, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)col0, 0};
           cost[n++] = 20 + per_col * (hi - lo);
         }
@@ -329,7 +359,7 @@ struct KArgs {
   uint32_t in_mask, out_mask;
   uint32_t in_vec4, out_vec4;     // fields whose rows may move 4 envs at a time (SoA, 16-byte aligned)
   float rw_weight[RL_MAX_REWARD_TERMS];          // stage 2: weights and term classes come from the parameter bank
-  uint64_t rw_late, rw_split, rw_isterm, rw_zero;   // bit k: finished in stage 2 / two partials / is_terminated / weight 0
+  uint64_t rw_late, rw_isterm, rw_zero;   // bit k: finished in stage 2 / is_terminated / weight 0
   // AoS spans (row-contiguous per env) and byte fields
   FieldD hist, rays;
   FieldD is_heading, is_standing;               // uint8
@@ -647,11 +677,14 @@ __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
 }
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
 __device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int b) {
+  // the history samples are independent: unrolled so that their loads and square roots overlap (a rolled loop
+  // pays the full dependent latency per sample); a force of exactly 0 skips the IEEE sqrt (its special-case path)
   float m = 0.f;
-  _Pragma("unroll 1")
+  _Pragma("unroll 4")
   for (int t = 0; t < T; ++t) {
     const float* f = h + (t * B + b) * 3;
-    const float n = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+    const float ss = (f[0] * f[0] + f[1] * f[1]) + f[2] * f[2];
+    const float n = (ss == 0.f) ? 0.f : sqrtf(ss);
     m = (t == 0) ? n : fmaxf(m, n);
   }
   return m;
@@ -905,7 +938,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
       _Pragma("unroll 1")
-      for (int i = 0; i < t.n_idx; ++i) {
+      for (int i = lo; i < t.n_idx && i < hi; ++i) {   // [lo, hi): this part's slice of the feet list
         const V3 vw = body_vec(sm, L.bvel, e, tc.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float lat = sqrtf(vb.x * vb.x + vb.y * vb.y);
@@ -1294,7 +1327,13 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     if (need_hist && !hist_bulk && a.hist.ptr) span_load_elems(sm + L.hist, L.hist_pitch, a.hist, HW, env0, nvalid, ids, tid, NT);
     if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, env0, nvalid, ids, tid, NT);
     if (ph & RL_PHASE_REWARDS)
-      for (int i = tid; i < K * kE; i += NT) sm[L.arrive + i] = __int_as_float(0);
+      for (int i = tid; i < K * kE; i += NT) {
+        sm[L.arrive + i] = __int_as_float(0);
+        if ((a.rw_zero >> (i / kE)) & 1ull) {   // weight-0 terms: no task evaluates them
+          sm[L.stepr + i] = 0.f;
+          sm[L.termv + (i / kE) * kTermParts * kE + (i % kE)] = 0.f;
+        }
+      }
     RL_SUB(2);                  // span loads issued
     // per-joint constants: constant bank -> shared
     for (int i = tid; i < J; i += NT)
@@ -1419,21 +1458,25 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         float full_raw = raw;
         bool finish = true;
         if (tk.pad) {
-          // one half of a split term: publish the partial; whoever arrives second (per env) adds the halves in
-          // slot order and finishes the term - no serial tail for it in stage 2
-          SMF(L.termv, 2 * k + tk.b) = raw;
+          // one part of a split term: publish the partial sum; whoever arrives last (per env) adds the parts in
+          // part order and finishes the term - no serial tail for it in stage 2
+          const int parts = tk.col0;
+          SMF(L.termv, kTermParts * k + tk.b) = raw;
           __threadfence_block();
           const int old = atomicAdd(reinterpret_cast<int*>(sm) + L.arrive + k * kE + e, 1);
-          finish = (old == 1);
+          finish = (old == parts - 1);
           if (finish) {
             __threadfence_block();
-            full_raw = *(volatile float*)&SMF(L.termv, 2 * k) + *(volatile float*)&SMF(L.termv, 2 * k + 1);
+            full_raw = *(volatile float*)&SMF(L.termv, kTermParts * k);
+#pragma unroll
+            for (int p = 1; p < kTermParts; ++p)
+              if (p < parts) full_raw += *(volatile float*)&SMF(L.termv, kTermParts * k + p);
           }
         }
         if (finish) {
           // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
           const float val = (full_raw * rt.weight) * S.step_dt;
-          SMF(L.termv, 2 * k) = val;
+          SMF(L.termv, kTermParts * k) = val;
           SMF(L.sums, k) = SMF(L.sums, k) + val;
           SMF(L.stepr, k) = rl_div(val, S.step_dt);
         }
@@ -1468,36 +1511,25 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 
     // ---- stage 2: warp 0 finishes the late terms and adds the reward up in manager order ------------------
     if ((ph & RL_PHASE_REWARDS) && warp == 0) {
-      const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
-      const bool terminated = ((fl >> 8) & 1) != 0;
+      // Kept as small as possible: warp 0 runs this alone, right after a barrier, on code no warp has touched -
+      // what it costs is its length in instruction-cache lines. Weight-0 terms were zeroed in the load phase.
       float total = 0.f;
-      // rolled loops on purpose (warp 0 runs them alone); weights / flags come from the parameter bank.
-      // pass 1: finish the late terms (partials of split terms, is_terminated) and zero the step reward of the
-      // weight-0 terms; pass 2: the reward, summed in manager order with 4 loads in flight
-      for (uint64_t m = a.rw_zero; m != 0; m &= m - 1) {
-        const int k = __ffsll((long long)m) - 1;
-        SMF(L.stepr, k) = 0.f; SMF(L.termv, 2 * k) = 0.f;
-      }
+      if (a.rw_late != 0) {   // only is_terminated, which needs the termination result, is finished here
+        const int fl = (ph & RL_PHASE_DONES) ? __float_as_int(SMF(L.flags, 0)) : 0;
+        const bool terminated = ((fl >> 8) & 1) != 0;
 #pragma unroll 1
-      for (uint64_t m = a.rw_late & ~a.rw_zero; m != 0; m &= m - 1) {
-        const int k = __ffsll((long long)m) - 1;
-        float raw;
-        if ((a.rw_isterm >> k) & 1ull) raw = terminated ? 1.f : 0.f;
-        else raw = ((a.rw_split >> k) & 1ull) ? (SMF(L.termv, 2 * k) + SMF(L.termv, 2 * k + 1)) : SMF(L.termv, 2 * k);
-        const float val = (raw * a.rw_weight[k]) * S.step_dt;
-        SMF(L.termv, 2 * k) = val;
-        SMF(L.sums, k) = SMF(L.sums, k) + val;
-        SMF(L.stepr, k) = rl_div(val, S.step_dt);
+        for (uint64_t m = a.rw_late & ~a.rw_zero; m != 0; m &= m - 1) {
+          const int k = __ffsll((long long)m) - 1;
+          const float raw = ((a.rw_isterm >> k) & 1ull) ? (terminated ? 1.f : 0.f) : SMF(L.termv, kTermParts * k);
+          const float val = (raw * a.rw_weight[k]) * S.step_dt;
+          SMF(L.termv, kTermParts * k) = val;
+          SMF(L.sums, k) = SMF(L.sums, k) + val;
+          SMF(L.stepr, k) = rl_div(val, S.step_dt);
+        }
       }
       RL_SUB(3);                // late terms finished
-      int k = 0;
 #pragma unroll 1
-      for (; k + 4 <= K; k += 4) {
-        const float v0 = SMF(L.termv, 2 * k), v1 = SMF(L.termv, 2 * k + 2), v2 = SMF(L.termv, 2 * k + 4), v3 = SMF(L.termv, 2 * k + 6);
-        total += v0; total += v1; total += v2; total += v3;
-      }
-#pragma unroll 1
-      for (; k < K; ++k) total += SMF(L.termv, 2 * k);
+      for (int k = 0; k < K; ++k) total += SMF(L.termv, kTermParts * k);   // manager order
       SMF(L.rew, 0) = total;
       RL_SUB(4);                // reward summed
     }
@@ -1720,7 +1752,6 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
     for (int k = 0; k < s.num_reward_terms; ++k) {
       a.rw_weight[k] = s.rewards[k].weight;
       if (sc.late[k]) a.rw_late |= 1ull << k;
-      if (sc.split[k]) a.rw_split |= 1ull << k;
       if (s.rewards[k].type == RL_REW_IS_TERMINATED) a.rw_isterm |= 1ull << k;
       if (s.rewards[k].weight == 0.f) a.rw_zero |= 1ull << k;
     }
