@@ -7,16 +7,21 @@
 // V/mdp/observations.py:17-35, V/mdp/commands.py:22-85, V/velocity_env_cfg.py:106-254,379-664 and the
 // IsaacLab manager loops / upstream terms listed in SURVEY.md Appendix A.
 //
-// Execution model (HBM-bound, no tensor cores - the arithmetic intensity is ~0.5 FLOP/B):
-//   * a CTA owns E consecutive envs; LPE lanes cooperate on one env (joint / body / obs-column loops are
-//     strided over the lanes, reductions are xor-shuffles inside the lane group);
-//   * load phase: the big AoS sensor rows (contact-force history, height-scan ray hits, noise inputs) are
-//     staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) while the
-//     small per-env fields are gathered with coalesced LDGs into an SoA [word][E] shared-memory record -
-//     all global reads of the tile are in flight before any arithmetic starts;
-//   * compute phase works on shared memory only and assembles the observation rows there;
-//   * store phase: observation rows leave with bulk stores (cp.async.bulk.global.shared::cta), the SoA
-//     outputs with coalesced STGs; the last CTA to finish compacts the reset ids from per-CTA bit masks.
+// Execution model (HBM-bound by arithmetic intensity, ~0.5 FLOP/B, no tensor cores; at a few thousand envs bound
+// by first-touch latency - see DESIGN.md 2 and profiles/r1_summary.md):
+//   * a CTA owns a tile of 32 consecutive envs; in the compute phase lane e of every warp IS env e (no lane
+//     repeats another lane's per-env scalar work) and the warps differ in which terms they evaluate (a constexpr
+//     longest-processing-time schedule, reached through one binary-search branch per warp);
+//   * load phase: the AoS sensor rows (contact-force history, height-scan ray hits) are staged into shared
+//     memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), the small per-env SoA fields with
+//     16-byte cp.async into an SoA [word][32] record - all global reads of the tile are in flight before any
+//     arithmetic starts, one join;
+//   * stage 1 works on shared memory only, every warp finishes its terms (weight, dt, episode sum, step reward)
+//     and assembles its observation columns in the shared-memory rows; stage 2 (warp 0) adds the reward up in
+//     manager order;
+//   * store phase: observation rows leave with bulk stores (cp.async.bulk.global.shared::cta), the SoA outputs
+//     with 16-byte stores; the last CTA to finish compacts the reset ids from per-CTA bit masks / combines the
+//     reset-logging partials.
 //
 // Built with -fmad=false on purpose: the reference is eager PyTorch, every op rounds on its own, and not
 // contracting a*b+c keeps threshold decisions (contact > 1 N, |cmd| > 0.1, ...) bit-identical.
@@ -59,12 +64,12 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0, long lo
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------
-// Per-launch field descriptors and the static row tables
+// Per-launch field descriptors
 //
 // A "row" is one component of one 4-byte per-env field. The step kernel stages rows into an SoA shared-memory
-// record (word w of local env e at sm[w*E + e]) with ONE generic loop of non-blocking cp.async copies and writes
-// result rows back with one generic loop - the row tables (field id, component, record word) are static per
-// context and live in global memory; only the ~25 field descriptors (pointer + strides) travel per launch.
+// record (word w of local env e at sm[w*32 + e]) with non-blocking cp.async copies and writes result rows back the
+// same way. Each of the ~25 fields travels per launch as {pointer, strides, component count, first record word}
+// in the kernel parameter bank - one parameter line per field, no table in global memory.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
 constexpr int kTermParts = 4;   // a reward term is evaluated in at most this many parts (termv holds that many slots per term)
@@ -1241,9 +1246,8 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 // The fused step kernel: kE = 32 envs per CTA, NW warps. MODE 0 = step, MODE 1 = single-term evaluation.
 //   load   : everything asynchronous (TMA bulk copies + cp.async), one join
 //   stage 1: every warp runs its share of the schedule, thread-per-env (lane e = env e)
-//   stage 2: warp 0 assembles the reward in manager order, warp 1 updates the command and writes the
-//            command-dependent observation columns
-//   store  : bulk stores for the observation rows, one generic loop for the SoA outputs; last CTA compacts reset ids
+//   stage 2: warp 0 adds the reward up in manager order (and finishes is_terminated)
+//   store  : bulk stores for the observation rows, per-field loops for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
 template <class P, int NW, int MODE, bool DBG>
 __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
