@@ -681,11 +681,12 @@ __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
   return V3{SMF(off, 3 * b + 0), SMF(off, 3 * b + 1), SMF(off, 3 * b + 2)};
 }
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
-__device__ __forceinline__ float hist_max_norm(const float* h, int T, int B, int b) {
-  // the history samples are independent: unrolled so that their loads and square roots overlap (a rolled loop
-  // pays the full dependent latency per sample); a force of exactly 0 skips the IEEE sqrt (its special-case path)
+__device__ __noinline__ float hist_max_norm(const float* h, int T, int B, int b) {
+  // ONE copy for every term that uses it (undesired_contacts, contact_forces, feet_slide, feet_stumble, the
+  // illegal-contact termination): warps in different terms keep the same few instruction lines hot instead of
+  // evicting each other's private copies. A force of exactly 0 skips the IEEE sqrt (its special-case path).
   float m = 0.f;
-  _Pragma("unroll 4")
+  _Pragma("unroll 1")
   for (int t = 0; t < T; ++t) {
     const float* f = h + (t * B + b) * 3;
     const float ss = (f[0] * f[0] + f[1] * f[1]) + f[2] * f[2];
