@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 6
+#define RL_ABI_VERSION 7
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -381,6 +381,23 @@ int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out /* [RL_MAX_TASKS][8] */, int32_
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
                       const RlField* joint_target /* J, native order; columns not driven are untouched */,
                       uint64_t* step_counter /* device, may be NULL: incremented by 1 */, void* stream);
+
+/* ContactSensor update [IL] (isaaclab/sensors/contact_sensor/contact_sensor.py, _update_buffers_impl; the reference
+ * configures it at V/velocity_env_cfg.py:86 and updates it every physics sub-step, :726): the step immediately in
+ * front of the path. For every env:
+ *   - history: net_forces_w_history[:, 1:] = history[:, :-1]; history[:, 0] = net_forces_w      (ring_slot < 0)
+ *     or, B200-native, only history[:, ring_slot] = net_forces_w (ring_slot in [0, T)): every consumer on the path
+ *     takes max over the history axis, which does not depend on the order of the samples - no data is moved;
+ *   - air / contact timers of the tracked bodies, with is_contact = |F| > force_threshold:
+ *       last_air        = first_contact ? current_air + dt     : last_air       (first_contact  = current_air > 0 & contact)
+ *       current_air     = contact ? 0 : current_air + dt
+ *       last_contact    = first_detach ? current_contact + dt  : last_contact   (first_detach = current_contact > 0 & !contact)
+ *       current_contact = contact ? current_contact + dt : 0
+ * net_forces_w is [N, B*3] in the body space of the history tensor; time_body_to_hist[i] is the history-space index
+ * of timer body i (device-independent host array, num_time_bodies entries). */
+int rl_contact_sensor_update(RlCtx* ctx, int64_t num_envs, const RlField* net_forces_w, const RlStateView* state,
+                             const int32_t* time_body_to_hist, float dt, float force_threshold, int32_t ring_slot,
+                             void* stream);
 
 /* The fused step over envs [0, num_envs), or over env_ids[0 .. *n_env_ids) when env_ids != NULL
  * (n_env_ids is a DEVICE pointer so that no host sync is needed after the reset compaction). */

@@ -643,6 +643,31 @@ def step(spec: StepSpec, st: State, rnd: dict, skip_done_envs: bool = False) -> 
     }
 
 
+def contact_sensor_update(spec: StepSpec, st: State, net_forces_w: torch.Tensor, dt: float,
+                          force_threshold: float = 1.0) -> dict:
+    """ContactSensor._update_buffers_impl [IL] (isaaclab/sensors/contact_sensor/contact_sensor.py, IsaacLab v2.3.2;
+    configured at V/velocity_env_cfg.py:86 with history_length=3, track_air_time=True, updated every physics
+    sub-step, :726). PARITY UNPINNED: the file is not vendored; restated from the upstream algorithm.
+
+    ``net_forces_w`` is [N, B, 3] in the history body space; the timers live in the (feet) timer body space."""
+    hist = st["net_forces_w_history"]
+    out = {}
+    new_hist = torch.roll(hist, 1, dims=1)
+    new_hist[:, 0] = net_forces_w
+    out["net_forces_w_history"] = new_hist
+    names_h = list(spec.layout.hist_body_names)
+    t2h = torch.tensor([names_h.index(n) for n in spec.layout.time_body_names], dtype=torch.long)
+    is_contact = torch.norm(net_forces_w[:, t2h, :], dim=-1) > force_threshold
+    cur_air, cur_con = st["current_air_time"], st["current_contact_time"]
+    is_first_contact = (cur_air > 0) * is_contact
+    is_first_detached = (cur_con > 0) * ~is_contact
+    out["last_air_time"] = torch.where(is_first_contact, cur_air + dt, st["last_air_time"])
+    out["current_air_time"] = torch.where(~is_contact, cur_air + dt, torch.zeros(()))
+    out["last_contact_time"] = torch.where(is_first_detached, cur_con + dt, st["last_contact_time"])
+    out["current_contact_time"] = torch.where(is_contact, cur_con + dt, torch.zeros(()))
+    return out
+
+
 def reset_envs(spec: StepSpec, st: State, ids: torch.Tensor, done_bits: torch.Tensor, rnd: dict) -> tuple[dict, dict]:
     """Manager part of ManagerBasedRLEnv._reset_idx [IL]: logging means, zeroing, command resample."""
     ids = ids.long()

@@ -14,7 +14,7 @@ from pathlib import Path
 
 import torch
 
-RL_ABI_VERSION = 6
+RL_ABI_VERSION = 7
 RL_MAX_TASKS = 112
 RL_DEBUG_STRIDE = 160
 RL_MAX_JOINTS = 64
@@ -168,7 +168,7 @@ _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlAct
 EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
     "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_ctx_get_schedule",
-    "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
+    "rl_contact_sensor_update", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -211,6 +211,8 @@ def load() -> C.CDLL:
     lib.rl_ctx_set_pdl.argtypes = [C.c_void_p, C.c_int]
     lib.rl_ctx_set_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.rl_ctx_get_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.rl_contact_sensor_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlStateView),
+                                             C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_int32, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),
                                       C.POINTER(RlField), C.c_void_p, C.c_void_p]
     lib.rl_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlStateView), C.POINTER(RlMdpState),

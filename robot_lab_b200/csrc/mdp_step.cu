@@ -1710,6 +1710,64 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ContactSensor update [IL]: history roll (or ring-slot write) + air / contact timers. One thread per
+// (env, history element) for the history, one per (env, timer body) for the timers.
+// ---------------------------------------------------------------------------------------------------
+struct SensorArgs {
+  int N, B, T, Bt, ring_slot;
+  float dt, thr;
+  RlField net, hist, cair, lair, ccon, lcon;
+  int t2h[RL_MAX_TIME_BODIES];
+};
+__global__ void contact_sensor_kernel(const SensorArgs a) {
+  // Work items: N * B*3 history elements, then N * Bt timer bodies. Consecutive threads walk the contiguous axis of
+  // the tensor they write (components for AoS rows, envs for SoA) so that either layout coalesces.
+  const int n_hist = a.N * a.B * 3, total = n_hist + a.N * a.Bt;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < n_hist) {
+      int env, item;
+      if (a.hist.comp_stride == 1) { item = i % (a.B * 3); env = i / (a.B * 3); } else { env = i % a.N; item = i / a.N; }
+      const float v = static_cast<const float*>(a.net.ptr)[(long long)env * a.net.env_stride + (long long)item * a.net.comp_stride];
+      float* h = static_cast<float*>(a.hist.ptr) + (long long)env * a.hist.env_stride;
+      const long long cs = a.hist.comp_stride;
+      if (a.ring_slot >= 0) {
+        h[(long long)(a.ring_slot * a.B * 3 + item) * cs] = v;
+      } else {
+        // newest first: slot 0 <- net, slot t <- old slot t-1. All loads first, then all stores (hist_len <= 8):
+        // one memory round trip instead of a load -> store chain per slot
+        float old[8];
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+          if (t < a.T - 1) old[t] = h[(long long)(t * a.B * 3 + item) * cs];
+        h[(long long)item * cs] = v;
+#pragma unroll
+        for (int t = 1; t < 8; ++t)
+          if (t < a.T) h[(long long)(t * a.B * 3 + item) * cs] = old[t - 1];
+      }
+    } else {
+      const int j = i - n_hist;
+      int env, f;
+      if (a.cair.comp_stride == 1 && a.Bt > 1) { f = j % a.Bt; env = j / a.Bt; } else { env = j % a.N; f = j / a.N; }
+      const int b = a.t2h[f];
+      const float* net = static_cast<const float*>(a.net.ptr) + (long long)env * a.net.env_stride;
+      const float fx = net[(long long)(3 * b) * a.net.comp_stride], fy = net[(long long)(3 * b + 1) * a.net.comp_stride],
+                  fz = net[(long long)(3 * b + 2) * a.net.comp_stride];
+      const bool contact = sqrtf((fx * fx + fy * fy) + fz * fz) > a.thr;
+      float* ca = static_cast<float*>(a.cair.ptr) + (long long)env * a.cair.env_stride + (long long)f * a.cair.comp_stride;
+      float* la = static_cast<float*>(a.lair.ptr) + (long long)env * a.lair.env_stride + (long long)f * a.lair.comp_stride;
+      float* cc = static_cast<float*>(a.ccon.ptr) + (long long)env * a.ccon.env_stride + (long long)f * a.ccon.comp_stride;
+      float* lc = static_cast<float*>(a.lcon.ptr) + (long long)env * a.lcon.env_stride + (long long)f * a.lcon.comp_stride;
+      const float cur_air = *ca, cur_con = *cc;
+      const bool first_contact = (cur_air > 0.f) && contact, first_detach = (cur_con > 0.f) && !contact;
+      if (first_contact) *la = cur_air + a.dt;
+      *ca = contact ? 0.f : cur_air + a.dt;
+      if (first_detach) *lc = cur_con + a.dt;
+      *cc = contact ? cur_con + a.dt : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
 }  // namespace
@@ -2077,6 +2135,41 @@ int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer) {
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
   ctx->use_pdl = enabled ? 1 : 0;
+  return RL_OK;
+}
+
+int rl_contact_sensor_update(RlCtx* ctx, int64_t num_envs, const RlField* net_forces_w, const RlStateView* state,
+                             const int32_t* time_body_to_hist, float dt, float force_threshold, int32_t ring_slot,
+                             void* stream) {
+  if (!ctx || !net_forces_w || !state) return fail(RL_EINVAL, "rl_contact_sensor_update: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  const RlStepSpec& s = ctx->spec;
+  if (!net_forces_w->ptr || !state->net_forces_w_history.ptr) return fail(RL_EINVAL, "rl_contact_sensor_update: net_forces_w and net_forces_w_history required%s", "");
+  if (s.num_time_bodies > 0 && (!time_body_to_hist || !state->current_air_time.ptr || !state->last_air_time.ptr ||
+                                !state->current_contact_time.ptr || !state->last_contact_time.ptr))
+    return fail(RL_EINVAL, "rl_contact_sensor_update: the four timer fields and time_body_to_hist are required%s", "");
+  if (ring_slot >= s.hist_len) return fail(RL_EINVAL, "rl_contact_sensor_update: ring_slot %s%lld outside the history length", "", ring_slot);
+  if (!(dt > 0.f)) return fail(RL_EINVAL, "rl_contact_sensor_update: dt must be positive%s", "");
+  SensorArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.B = s.num_hist_bodies; a.T = s.hist_len; a.Bt = s.num_time_bodies; a.ring_slot = ring_slot;
+  a.dt = dt; a.thr = force_threshold;
+  a.net = *net_forces_w; a.hist = state->net_forces_w_history;
+  a.cair = state->current_air_time; a.lair = state->last_air_time;
+  a.ccon = state->current_contact_time; a.lcon = state->last_contact_time;
+  for (int f = 0; f < s.num_time_bodies; ++f) {
+    if (time_body_to_hist[f] < 0 || time_body_to_hist[f] >= s.num_hist_bodies)
+      return fail(RL_EINVAL, "rl_contact_sensor_update: time_body_to_hist[%s%lld] outside the history bodies", "", f);
+    a.t2h[f] = time_body_to_hist[f];
+  }
+  const long long total = num_envs * (long long)(a.B * 3 + a.Bt);
+  if (total >= (1ll << 31)) return fail(RL_EINVAL, "rl_contact_sensor_update: problem too large for 32-bit indexing%s", "");
+  if (total == 0) return RL_OK;
+  DeviceGuard guard(ctx->device);
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads);
+  contact_sensor_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
   return RL_OK;
 }
 

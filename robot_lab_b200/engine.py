@@ -65,6 +65,19 @@ class MdpStepEngine:
     def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
         return StateBuffers(self.spec, num_envs, self.device, layout)
 
+    def contact_sensor_update(self, b: StateBuffers, net_forces_w: torch.Tensor, dt: float, force_threshold: float = 1.0,
+                              ring_slot: int = -1) -> None:
+        """ContactSensor._update_buffers_impl [IL] for one physics sub-step: history roll (or ring-slot write) and the
+        air / contact timers. ``net_forces_w`` is ``[N, B, 3]`` in the history body space."""
+        spec = self.spec
+        names_h = list(spec.layout.hist_body_names)
+        t2h = (C.c_int32 * max(1, spec.Bt))(*[names_h.index(n) for n in spec.layout.time_body_names])
+        nf = net_forces_w.reshape(b.N, -1)
+        fld = nat.RlField(nf.data_ptr(), nf.stride(0), nf.stride(1) if nf.shape[1] > 1 else 1)
+        st = b.state_view()
+        nat.check(self.lib.rl_contact_sensor_update(self._ctx, b.N, C.byref(fld), C.byref(st), t2h, float(dt),
+                                                    float(force_threshold), int(ring_slot), self._stream()))
+
     # ---- the five entry points ----------------------------------------------------------------------
     def process_action(self, b: StateBuffers, with_target: bool = True, advance_step_counter: bool = True) -> None:
         na = b.field("new_action")

@@ -111,3 +111,17 @@ def test_unsupported_configurations_are_rejected():
     with pytest.raises(ValueError, match="two pairs"):
         compile_step_spec(cfg, cfg.scene.make_layout())
     del SceneEntityCfg
+
+
+def test_per_launch_byte_accounting():
+    """the fused figure of SURVEY.md 8(d) and its split over the two launches of an env step."""
+    import helpers as H
+
+    _, spec = H.make_spec("go2_rough")
+    assert spec.algorithmic_bytes_per_env_step() == 3423
+    pre, post = spec.algorithmic_bytes_per_launch("pre_reset"), spec.algorithmic_bytes_per_launch("post_reset")
+    assert (pre, post) == (1463, 2126)
+    # both launches read root state (13 words), joint pos/vel (2J) and the command (3): the split exceeds the fused
+    # figure by those re-reads plus command state the fused accounting keeps on chip, minus the joint target /
+    # stored action that process_action owns
+    assert 3423 < pre + post < 3423 + 4 * (13 + 2 * spec.J + 3 + 20)

@@ -42,7 +42,10 @@ def run_post(b):
     eng.step(b, phases=POST, use_random_inputs=False, use_step_counter=True, env_ids=b.reset_ids, n_env_ids=b.n_reset)
 
 
+net_forces = torch.randn(N, spec.B, 3, device="cuda:0") * (torch.rand(N, spec.B, 1, device="cuda:0") < 0.3)
 CASES = {
+    "contact_sensor_update (history roll + timers)": lambda b: eng.contact_sensor_update(b, net_forces, 0.005),
+    "contact_sensor_update (ring slot + timers)": lambda b: eng.contact_sensor_update(b, net_forces, 0.005, ring_slot=0),
     "process_action": lambda b: eng.process_action(b),
     "rl_step DONES|REWARDS|COMPACT (pre-reset)": lambda b: eng.step_pre_reset(b, use_random_inputs=False, use_step_counter=True),
     "rl_step RESET|COMMAND|OBS, all envs (post-reset)": lambda b: eng.step_post_reset(b, use_random_inputs=False, use_step_counter=True),
