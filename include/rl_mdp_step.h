@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 7
+#define RL_ABI_VERSION 8
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -381,6 +381,31 @@ int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out /* [RL_MAX_TASKS][8] */, int32_
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
                       const RlField* joint_target /* J, native order; columns not driven are untouched */,
                       uint64_t* step_counter /* device, may be NULL: incremented by 1 */, void* stream);
+
+/* Reset events of the reference (mode="reset", V/velocity_env_cfg.py:326-363): `reset_root_state_uniform`
+ * (V/mdp/events.py:205-271, the non-pit branch; the "pits" sub-terrain is absent from the in-scope terrains) and
+ * `reset_joints_by_scale` [IL]. Ranges are x, y, z, roll, pitch, yaw. */
+typedef struct RlResetStateCfg {
+  float default_root_state[13];   /* asset.data.default_root_state: pos 3, quat (w,x,y,z) 4, lin vel 3, ang vel 3 */
+  float pose_lo[6], pose_hi[6];
+  float vel_lo[6], vel_hi[6];
+  float joint_pos_scale_lo, joint_pos_scale_hi;   /* reset_joints_by_scale position_range */
+  float joint_vel_scale_lo, joint_vel_scale_hi;   /* reset_joints_by_scale velocity_range */
+} RlResetStateCfg;
+
+/* writes the post-reset physical state of the envs being reset, i.e. what the two events
+ * above write into the simulator:
+ *   root_pos_w   = default_pos + env_origin + U(pose xyz)
+ *   root_quat_w  = quat_mul(default_quat, quat_from_euler_xyz(U(roll), U(pitch), U(yaw)))
+ *   root_lin/ang_vel_w = default_vel + U(velocity ranges)
+ *   joint_pos    = clamp(default_joint_pos * U(position_range), soft limits), joint_vel likewise (soft vel limit)
+ * for env_ids[0 .. *n_env_ids) or, when env_ids is NULL, for the envs whose terminated | truncated byte is set.
+ * Uniforms: Philox streams RL_STREAM_RESET_STATE (12 per env) / RL_STREAM_RESET_JOINTS (2J per env) of `rnd`, or
+ * `uniforms` = [12 + 2J][N] U[0,1) when not NULL (pose 6, velocity 6, joint pos J, joint vel J). */
+int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cfg, const RlField* env_origins /* [N,3] */,
+                         const RlStateView* state, const uint8_t* terminated, const uint8_t* truncated,
+                         const int32_t* env_ids, const int32_t* n_env_ids, const RlRandom* rnd,
+                         const float* uniforms, void* stream);
 
 /* ContactSensor update [IL] (isaaclab/sensors/contact_sensor/contact_sensor.py, _update_buffers_impl; the reference
  * configures it at V/velocity_env_cfg.py:86 and updates it every physics sub-step, :726): the step immediately in

@@ -49,6 +49,19 @@ def _math_module() -> types.ModuleType:
     m.quat_conjugate = quat_conjugate
     m.yaw_quat = lambda q: port.yaw_quat(q.reshape(-1, 4)).view(q.shape)
     m.wrap_to_pi = port.wrap_to_pi
+    m.quat_from_euler_xyz = port.quat_from_euler_xyz   # [IL], restated
+    m.quat_mul = port.quat_mul                         # [IL], restated
+
+    # sample_uniform [IL] = torch.rand(size) * (upper - lower) + lower; the harness feeds the uniforms so that the
+    # reference and the port see the same draws (ref_harness.reference_reset_root_state)
+    m._uniform_queue = []
+
+    def sample_uniform(lower, upper, size, device=None):
+        u = m._uniform_queue.pop(0) if m._uniform_queue else torch.rand(size)
+        assert tuple(u.shape) == tuple(size), (u.shape, size)
+        return u * (upper - lower) + lower
+
+    m.sample_uniform = sample_uniform
     return m
 
 

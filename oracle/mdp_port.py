@@ -643,6 +643,67 @@ def step(spec: StepSpec, st: State, rnd: dict, skip_done_envs: bool = False) -> 
     }
 
 
+def quat_from_euler_xyz(roll: torch.Tensor, pitch: torch.Tensor, yaw: torch.Tensor) -> torch.Tensor:
+    """isaaclab.utils.math.quat_from_euler_xyz [IL] -> (w, x, y, z)."""
+    cy, sy = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)
+    cr, sr = torch.cos(roll * 0.5), torch.sin(roll * 0.5)
+    cp, sp = torch.cos(pitch * 0.5), torch.sin(pitch * 0.5)
+    qw = cy * cr * cp + sy * sr * sp
+    qx = cy * sr * cp - sy * cr * sp
+    qy = cy * cr * sp + sy * sr * cp
+    qz = sy * cr * cp - cy * sr * sp
+    return torch.stack([qw, qx, qy, qz], dim=-1)
+
+
+def quat_mul(q1: torch.Tensor, q2: torch.Tensor) -> torch.Tensor:
+    """isaaclab.utils.math.quat_mul [IL]."""
+    w1, x1, y1, z1 = q1[..., 0], q1[..., 1], q1[..., 2], q1[..., 3]
+    w2, x2, y2, z2 = q2[..., 0], q2[..., 1], q2[..., 2], q2[..., 3]
+    ww = (z1 + x1) * (x2 + y2)
+    yy = (w1 - y1) * (w2 + z2)
+    zz = (w1 + y1) * (w2 - z2)
+    xx = ww + yy + zz
+    qq = 0.5 * (xx + (z1 - x1) * (x2 - y2))
+    w = qq - ww + (z1 - y1) * (y2 - z2)
+    x = qq - xx + (x1 + w1) * (x2 + w2)
+    y = qq - yy + (w1 - x1) * (y2 + z2)
+    z = qq - zz + (z1 + y1) * (w2 - x2)
+    return torch.stack([w, x, y, z], dim=-1)
+
+
+def reset_scene_state(spec: StepSpec, st: State, ids: torch.Tensor, cfg, env_origins: torch.Tensor,
+                      uniforms: torch.Tensor) -> dict:
+    """``reset_root_state_uniform`` (V/mdp/events.py:205-271, non-pit branch) followed by ``reset_joints_by_scale``
+    [IL] (wired at V/velocity_env_cfg.py:326-363) for ``ids``. ``uniforms`` is [12 + 2J, N] U[0,1): pose 6, velocity 6,
+    joint position J, joint velocity J; ``sample_uniform`` [IL] = rand * (hi - lo) + lo. ``cfg``: cfg.ResetStateCfg."""
+    ids = ids.long()
+    J = spec.J
+    out = {k: st[k].clone() for k in ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_w", "joint_pos", "joint_vel")}
+    keys = ("x", "y", "z", "roll", "pitch", "yaw")
+    drs = torch.tensor([0.0, 0.0, spec.layout.asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6)
+    root = drs.unsqueeze(0).repeat(len(ids), 1)
+    pr = torch.tensor([cfg.pose_range.get(k, (0.0, 0.0)) for k in keys])
+    vr = torch.tensor([cfg.velocity_range.get(k, (0.0, 0.0)) for k in keys])
+    up, uv = uniforms[0:6, ids].t(), uniforms[6:12, ids].t()
+    pose = up * (pr[:, 1] - pr[:, 0]) + pr[:, 0]
+    vel = uv * (vr[:, 1] - vr[:, 0]) + vr[:, 0]
+    out["root_pos_w"][ids] = root[:, 0:3] + env_origins[ids] + pose[:, 0:3]
+    out["root_quat_w"][ids] = quat_mul(root[:, 3:7], quat_from_euler_xyz(pose[:, 3], pose[:, 4], pose[:, 5]))
+    velocities = root[:, 7:13] + vel
+    out["root_lin_vel_w"][ids] = velocities[:, 0:3]
+    out["root_ang_vel_w"][ids] = velocities[:, 3:6]
+    q0, qd0 = torch.tensor(spec.default_joint_pos), torch.tensor(spec.default_joint_vel)
+    lim = torch.tensor(spec.soft_pos_limits)
+    vlim = torch.tensor(spec.soft_vel_limits)
+    plo, phi = cfg.joint_position_range
+    vlo, vhi = cfg.joint_velocity_range
+    jp = q0.unsqueeze(0) * (uniforms[12:12 + J, ids].t() * (phi - plo) + plo)
+    jv = qd0.unsqueeze(0) * (uniforms[12 + J:12 + 2 * J, ids].t() * (vhi - vlo) + vlo)
+    out["joint_pos"][ids] = torch.maximum(torch.minimum(jp, lim[:, 1]), lim[:, 0])
+    out["joint_vel"][ids] = torch.maximum(torch.minimum(jv, vlim), -vlim)
+    return out
+
+
 def contact_sensor_update(spec: StepSpec, st: State, net_forces_w: torch.Tensor, dt: float,
                           force_threshold: float = 1.0) -> dict:
     """ContactSensor._update_buffers_impl [IL] (isaaclab/sensors/contact_sensor/contact_sensor.py, IsaacLab v2.3.2;

@@ -282,3 +282,46 @@ def reference_command_compute(spec: StepSpec, st: dict, uniform_table: torch.Ten
         "is_heading_env": term.is_heading_env, "is_standing_env": term.is_standing_env,
         "metric_error_vel_xy": term.metrics["error_vel_xy"], "metric_error_vel_yaw": term.metrics["error_vel_yaw"],
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# reset event: the reference's reset_root_state_uniform (V/mdp/events.py:205-271) on a fake asset
+# ------------------------------------------------------------------------------------------------
+def reference_reset_root_state(spec: StepSpec, st: dict, ids: torch.Tensor, cfg, env_origins: torch.Tensor,
+                               uniforms: torch.Tensor) -> dict:
+    """Run the unmodified ``reset_root_state_uniform`` for ``ids`` with the given uniforms ([12+, N]: pose 6, velocity
+    6) and return what it writes into the simulator (root pose + velocity of those envs)."""
+    _install_command_context(torch.zeros(7, st["root_quat_w"].shape[0]))   # package context for the relative imports
+    import importlib.util
+
+    pkg = "robot_lab.tasks.manager_based.locomotion.velocity.mdp"
+    full = f"{pkg}.events"
+    if full not in sys.modules:
+        sp = importlib.util.spec_from_file_location(full, shim.MDP_DIR / "events.py")
+        module = importlib.util.module_from_spec(sp)
+        module.__package__ = pkg
+        sys.modules[full] = module
+        sp.loader.exec_module(module)
+    events = sys.modules[full]
+    env = FakeEnv(spec, st)
+    n = env.num_envs
+    asset = env.scene["robot"]
+    drs = torch.tensor([0.0, 0.0, spec.layout.asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6)
+    asset.data.default_root_state = drs.unsqueeze(0).repeat(n, 1)
+    written = {}
+
+    def write_pose(pose, env_ids=None):
+        written["pose"], written["pose_ids"] = pose.clone(), env_ids.clone()
+
+    def write_vel(vel, env_ids=None):
+        written["vel"], written["vel_ids"] = vel.clone(), env_ids.clone()
+
+    asset.write_root_pose_to_sim, asset.write_root_velocity_to_sim = write_pose, write_vel
+    env.scene.env_origins = env_origins
+    ids = ids.long()
+    math_mod = sys.modules["isaaclab.utils.math"]
+    math_mod._uniform_queue[:] = [uniforms[0:6, ids].t().contiguous(), uniforms[6:12, ids].t().contiguous()]
+    events.reset_root_state_uniform(env, ids, dict(cfg.pose_range), dict(cfg.velocity_range))
+    assert not math_mod._uniform_queue and torch.equal(written["pose_ids"], ids) and torch.equal(written["vel_ids"], ids)
+    return {"root_pos_w": written["pose"][:, 0:3], "root_quat_w": written["pose"][:, 3:7],
+            "root_lin_vel_w": written["vel"][:, 0:3], "root_ang_vel_w": written["vel"][:, 3:6]}

@@ -14,7 +14,7 @@ from pathlib import Path
 
 import torch
 
-RL_ABI_VERSION = 7
+RL_ABI_VERSION = 8
 RL_MAX_TASKS = 112
 RL_DEBUG_STRIDE = 160
 RL_MAX_JOINTS = 64
@@ -147,6 +147,15 @@ class RlResetLog(C.Structure):
     _fields_ = [("episode_sum_mean", C.c_void_p), ("done_term_count", C.c_void_p), ("metric_mean", C.c_void_p)]
 
 
+class RlResetStateCfg(C.Structure):
+    _fields_ = [
+        ("default_root_state", C.c_float * 13), ("pose_lo", C.c_float * 6), ("pose_hi", C.c_float * 6),
+        ("vel_lo", C.c_float * 6), ("vel_hi", C.c_float * 6),
+        ("joint_pos_scale_lo", C.c_float), ("joint_pos_scale_hi", C.c_float),
+        ("joint_vel_scale_lo", C.c_float), ("joint_vel_scale_hi", C.c_float),
+    ]
+
+
 class RlStepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p * RL_NUM_OBS_GROUPS), ("obs_pitch", C.c_int64 * RL_NUM_OBS_GROUPS),
@@ -163,12 +172,12 @@ class RlRandom(C.Structure):
 
 
 _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlActionCfg, RlStepSpec, RlField,
-            RlStateView, RlMdpState, RlStepOut, RlRandom, RlResetLog)
+            RlStateView, RlMdpState, RlStepOut, RlRandom, RlResetLog, RlResetStateCfg)
 
 EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
     "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_ctx_get_schedule",
-    "rl_contact_sensor_update", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
+    "rl_contact_sensor_update", "rl_reset_scene_state", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -211,6 +220,9 @@ def load() -> C.CDLL:
     lib.rl_ctx_set_pdl.argtypes = [C.c_void_p, C.c_int]
     lib.rl_ctx_set_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.rl_ctx_get_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.rl_reset_scene_state.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlResetStateCfg), C.POINTER(RlField),
+                                         C.POINTER(RlStateView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(RlRandom), C.c_void_p, C.c_void_p]
     lib.rl_contact_sensor_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlStateView),
                                              C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_int32, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),

@@ -253,3 +253,20 @@ class ContactSensorCfg:
     history_length: int = 3
     track_air_time: bool = True
     force_threshold: float = 1.0
+
+
+@dataclass
+class ResetStateCfg:
+    """The two mode="reset" events that write physical state (V/velocity_env_cfg.py:326-363): ``reset_root_state_uniform``
+    pose / velocity ranges (x, y, z, roll, pitch, yaw; missing keys = (0, 0)) and ``reset_joints_by_scale`` ranges."""
+
+    pose_range: dict = field(default_factory=lambda: {"x": (-0.5, 0.5), "y": (-0.5, 0.5), "yaw": (-3.14, 3.14)})
+    velocity_range: dict = field(default_factory=lambda: {k: (-0.5, 0.5) for k in ("x", "y", "z", "roll", "pitch", "yaw")})
+    joint_position_range: tuple = (1.0, 1.0)
+    joint_velocity_range: tuple = (0.0, 0.0)
+
+    @staticmethod
+    def go2_rough() -> "ResetStateCfg":
+        """GO2/rough_env_cfg.py:56-73."""
+        return ResetStateCfg(pose_range={"x": (-0.5, 0.5), "y": (-0.5, 0.5), "z": (0.0, 0.2), "roll": (-3.14, 3.14),
+                                         "pitch": (-3.14, 3.14), "yaw": (-3.14, 3.14)})

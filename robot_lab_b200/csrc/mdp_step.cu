@@ -456,7 +456,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-enum { RL_STREAM_COMMAND = 1, RL_STREAM_RESET_COMMAND = 2, RL_STREAM_OBS = 16 };
+enum { RL_STREAM_COMMAND = 1, RL_STREAM_RESET_COMMAND = 2, RL_STREAM_RESET_STATE = 3, RL_STREAM_RESET_JOINTS = 4, RL_STREAM_OBS = 16 };
 
 struct RandState {
   unsigned long long seed, step;   // step already includes the device-side common step counter
@@ -1277,9 +1277,10 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   // a list - over all envs, resetting those whose terminated | truncated byte is set (full-tile fast path)
   const bool do_reset = (MODE == 0) && (ph & RL_PHASE_RESET) != 0;
   const bool reset_masked = do_reset && !a.has_ids;
-  const int n_reset_total = do_reset ? (reset_masked ? *a.out.n_reset : n_total) : 0;
-  if (do_reset && n_reset_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
-    // nothing to reset: the logged scalars are defined as 0
+  // (the masked form reads its reset count only in the tail: a dependent global load up here would stall the
+  // whole prologue; the id-list form needs its count for the bounds anyway)
+  if (do_reset && !reset_masked && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
+    // nothing to reset and no CTA reaches the tail: the logged scalars are defined as 0
     if (tid < K) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
     else if (tid < K + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K] = 0.f; }
     else if (tid < K + RL_MAX_DONE_TERMS + 2) { if (a.out.reset_log.metric_mean) a.out.reset_log.metric_mean[tid - K - RL_MAX_DONE_TERMS] = 0.f; }
@@ -1300,7 +1301,20 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 
   // ---- load phase: everything is asynchronous, nothing below waits until the single join point ---------
   if (nvalid > 0) {
-    // byte-sized per-env flags: plain loads into registers, issued first so that their latency overlaps the
+    // the big transfers first: their DRAM latency overlaps everything else the prologue does
+    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, L.hist_pitch, env0);
+    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, L.rays_pitch, env0);
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      uint32_t bytes = 0;
+      if (hist_bulk) bytes += (uint32_t)(kE * HW * 4);
+      if (rays_bulk) bytes += (uint32_t)(kE * R * 4);
+      mbar_expect_tx(&s_bar, bytes);
+      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(kE * HW * 4), &s_bar);
+      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(kE * R * 4), &s_bar);
+    }
+    // byte-sized per-env flags: plain loads into registers, issued early so that their latency overlaps the
     // issue of everything else
     const bool want_cmd_flags = (MODE == 0) && (ph & (RL_PHASE_COMMAND | RL_PHASE_RESET)) != 0;
     const bool want_done_bits = do_reset && a.out.done_bits != nullptr;
@@ -1313,18 +1327,6 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         if (a.is_standing.ptr) u8_stand = static_cast<const uint8_t*>(a.is_standing.ptr)[ev * a.is_standing.es];
       }
       if (want_done_bits) u8_bits = a.out.done_bits[ev];
-    }
-    const bool hist_bulk = need_hist && full && span_bulk_ok(a.hist, HW, L.hist_pitch, env0);
-    const bool rays_bulk = need_rays && full && span_bulk_ok(a.rays, R, L.rays_pitch, env0);
-    if (tid == 0) {
-      mbar_init(&s_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      uint32_t bytes = 0;
-      if (hist_bulk) bytes += (uint32_t)(kE * HW * 4);
-      if (rays_bulk) bytes += (uint32_t)(kE * R * 4);
-      mbar_expect_tx(&s_bar, bytes);
-      if (hist_bulk) bulk_g2s(sm + L.hist, static_cast<const float*>(a.hist.ptr) + (size_t)env0 * HW, (uint32_t)(kE * HW * 4), &s_bar);
-      if (rays_bulk) bulk_g2s(sm + L.rays, static_cast<const float*>(a.rays.ptr) + (size_t)env0 * R, (uint32_t)(kE * R * 4), &s_bar);
     }
     RL_SUB(0);                  // prologue + bulk copies issued
     load_fields(sm, a, env0, nvalid, ids, full, warp, e, NW);
@@ -1665,6 +1667,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         float tot = 0.f;
         for (int w = 0; w < NW; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
         const RlResetLog& lg = a.out.reset_log;
+        const int n_reset_total = reset_masked ? *a.out.n_reset : n_total;
         const float cnt = (float)max(n_reset_total, 1);
         if (n_reset_total == 0) tot = 0.f;
         if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / cnt; }
@@ -1705,6 +1708,102 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
       float v = nv * ac.scale[col] + ac.offset[col];
       if (ac.has_clip) v = clampf(v, ac.clip_lo[col], ac.clip_hi[col]);
       static_cast<float*>(target.ptr)[(long long)env * target.env_stride + (long long)ac.joint_ids[col] * target.comp_stride] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Reset events: reset_root_state_uniform (V/mdp/events.py:205-271) + reset_joints_by_scale [IL]. One thread per
+// env being reset (they are few); isaaclab.utils.math [IL]: quat_from_euler_xyz, quat_mul, sample_uniform.
+// ---------------------------------------------------------------------------------------------------
+struct ResetStateArgs {
+  int N, slot, has_ids;
+  RlResetStateCfg cfg;
+  RlField origins, pos, quat, lin, ang, jpos, jvel;
+  const uint8_t* terminated;
+  const uint8_t* truncated;
+  const int32_t* env_ids;
+  const int32_t* n_env_ids;
+  RlRandom rnd;
+  const float* uniforms;   // [12 + 2J][N] or NULL
+};
+__device__ __forceinline__ void st_f(const RlField& f, long long env, int c, float v) {
+  static_cast<float*>(f.ptr)[env * f.env_stride + (long long)c * f.comp_stride] = v;
+}
+__global__ void reset_scene_state_kernel(const ResetStateArgs a) {
+  const RlStepSpec& S = c_spec[a.slot];
+  const int n = a.has_ids ? *a.n_env_ids : a.N;
+  RandState rs;
+  rs.seed = a.rnd.seed;
+  rs.step = a.rnd.step + (a.rnd.step_counter ? *a.rnd.step_counter : 0ull);
+  rs.env_id_offset = a.rnd.env_id_offset;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long env = i;
+    if (a.has_ids) env = a.env_ids[i];
+    else if (!((a.terminated && a.terminated[i]) || (a.truncated && a.truncated[i]))) continue;
+    float u[12];
+    if (a.uniforms) {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) u[q] = a.uniforms[(long long)q * a.N + env];
+    } else {
+#pragma unroll
+      for (int blk = 0; blk < 3; ++blk) {
+        const uint4 r = rl_philox(rs, env, RL_STREAM_RESET_STATE, (uint32_t)blk);
+        u[4 * blk] = u01(r.x); u[4 * blk + 1] = u01(r.y); u[4 * blk + 2] = u01(r.z); u[4 * blk + 3] = u01(r.w);
+      }
+    }
+    const RlResetStateCfg& c = a.cfg;
+    float pose[6], vel[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {   // sample_uniform [IL]: (hi - lo) * u + lo
+      pose[q] = (c.pose_hi[q] - c.pose_lo[q]) * u[q] + c.pose_lo[q];
+      vel[q] = (c.vel_hi[q] - c.vel_lo[q]) * u[6 + q] + c.vel_lo[q];
+    }
+    const float* org = static_cast<const float*>(a.origins.ptr);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float o = org ? org[env * a.origins.env_stride + (long long)q * a.origins.comp_stride] : 0.f;
+      st_f(a.pos, env, q, (c.default_root_state[q] + o) + pose[q]);
+    }
+    // quat_from_euler_xyz [IL] (roll, pitch, yaw)
+    const float cr = rl_cosf(pose[3] * 0.5f), sr = rl_sinf(pose[3] * 0.5f);
+    const float cp = rl_cosf(pose[4] * 0.5f), sp = rl_sinf(pose[4] * 0.5f);
+    const float cy = rl_cosf(pose[5] * 0.5f), sy = rl_sinf(pose[5] * 0.5f);
+    const float dw = (cy * cr) * cp + (sy * sr) * sp;
+    const float dx = (cy * sr) * cp - (sy * cr) * sp;
+    const float dy = (cy * cr) * sp + (sy * sr) * cp;
+    const float dz = (sy * cr) * cp - (cy * sr) * sp;
+    // quat_mul(default_quat, delta) [IL]
+    const float w1 = c.default_root_state[3], x1 = c.default_root_state[4], y1 = c.default_root_state[5], z1 = c.default_root_state[6];
+    const float ww = (z1 + x1) * (dx + dy), yy = (w1 - y1) * (dw + dz), zz = (w1 + y1) * (dw - dz);
+    const float xx = ww + yy + zz;
+    const float qq = 0.5f * (xx + (z1 - x1) * (dx - dy));
+    st_f(a.quat, env, 0, qq - ww + (z1 - y1) * (dy - dz));
+    st_f(a.quat, env, 1, qq - xx + (x1 + w1) * (dx + dw));
+    st_f(a.quat, env, 2, qq - yy + (w1 - x1) * (dy + dz));
+    st_f(a.quat, env, 3, qq - zz + (z1 + y1) * (dw - dx));
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      st_f(a.lin, env, q, c.default_root_state[7 + q] + vel[q]);
+      st_f(a.ang, env, q, c.default_root_state[10 + q] + vel[3 + q]);
+    }
+    // reset_joints_by_scale [IL]
+    const int J = S.num_joints;
+    for (int j = 0; j < J; ++j) {
+      float up, uv;
+      if (a.uniforms) {
+        up = a.uniforms[(long long)(12 + j) * a.N + env];
+        uv = a.uniforms[(long long)(12 + J + j) * a.N + env];
+      } else {
+        const uint4 r = rl_philox(rs, env, RL_STREAM_RESET_JOINTS, (uint32_t)(j >> 1));
+        up = u01((j & 1) ? r.z : r.x); uv = u01((j & 1) ? r.w : r.y);
+      }
+      float qp = S.default_joint_pos[j] * ((c.joint_pos_scale_hi - c.joint_pos_scale_lo) * up + c.joint_pos_scale_lo);
+      float qv = S.default_joint_vel[j] * ((c.joint_vel_scale_hi - c.joint_vel_scale_lo) * uv + c.joint_vel_scale_lo);
+      qp = clampf(qp, S.soft_pos_limit_lo[j], S.soft_pos_limit_hi[j]);
+      qv = clampf(qv, -S.soft_vel_limit[j], S.soft_vel_limit[j]);
+      if (a.jpos.ptr) st_f(a.jpos, env, j, qp);
+      if (a.jvel.ptr) st_f(a.jvel, env, j, qv);
     }
   }
 }
@@ -2033,7 +2132,7 @@ int64_t rl_struct_sizeof(const char* name) {
 #define RL_SZ(T) if (strcmp(name, #T) == 0) return (int64_t)sizeof(T)
   RL_SZ(RlRewardTerm); RL_SZ(RlObsTerm); RL_SZ(RlObsGroup); RL_SZ(RlDoneTerm); RL_SZ(RlCommandCfg);
   RL_SZ(RlActionCfg); RL_SZ(RlStepSpec); RL_SZ(RlField); RL_SZ(RlStateView); RL_SZ(RlMdpState);
-  RL_SZ(RlStepOut); RL_SZ(RlRandom); RL_SZ(RlResetLog);
+  RL_SZ(RlStepOut); RL_SZ(RlRandom); RL_SZ(RlResetLog); RL_SZ(RlResetStateCfg);
 #undef RL_SZ
   return -1;
 }
@@ -2135,6 +2234,33 @@ int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer) {
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
   ctx->use_pdl = enabled ? 1 : 0;
+  return RL_OK;
+}
+
+int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cfg, const RlField* env_origins,
+                         const RlStateView* state, const uint8_t* terminated, const uint8_t* truncated,
+                         const int32_t* env_ids, const int32_t* n_env_ids, const RlRandom* rnd,
+                         const float* uniforms, void* stream) {
+  if (!ctx || !cfg || !state || !rnd) return fail(RL_EINVAL, "rl_reset_scene_state: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  if (!state->root_pos_w.ptr || !state->root_quat_w.ptr || !state->root_lin_vel_w.ptr || !state->root_ang_vel_w.ptr)
+    return fail(RL_EINVAL, "rl_reset_scene_state: the four root state fields are required%s", "");
+  if (env_ids && !n_env_ids) return fail(RL_EINVAL, "rl_reset_scene_state: env_ids needs n_env_ids%s", "");
+  if (!env_ids && !terminated && !truncated) return fail(RL_EINVAL, "rl_reset_scene_state: env_ids or the done masks are required%s", "");
+  ResetStateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.slot = ctx->slot; a.has_ids = env_ids != nullptr;
+  a.cfg = *cfg;
+  if (env_origins) a.origins = *env_origins;
+  a.pos = state->root_pos_w; a.quat = state->root_quat_w; a.lin = state->root_lin_vel_w; a.ang = state->root_ang_vel_w;
+  a.jpos = state->joint_pos; a.jvel = state->joint_vel;
+  a.terminated = terminated; a.truncated = truncated; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
+  a.rnd = *rnd; a.uniforms = uniforms;
+  DeviceGuard guard(ctx->device);
+  const int threads = 128;
+  const int blocks = (int)((num_envs + threads - 1) / threads);
+  reset_scene_state_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
   return RL_OK;
 }
 

@@ -65,6 +65,31 @@ class MdpStepEngine:
     def new_buffers(self, num_envs: int, layout: str = "soa") -> StateBuffers:
         return StateBuffers(self.spec, num_envs, self.device, layout)
 
+    def reset_scene_state(self, b: StateBuffers, cfg, env_origins: torch.Tensor | None = None,
+                          env_ids: torch.Tensor | None = None, n_env_ids: torch.Tensor | None = None,
+                          uniforms: torch.Tensor | None = None, seed: int = 0, step: int = 0, env_id_offset: int = 0,
+                          use_step_counter: bool = False) -> None:
+        """``reset_root_state_uniform`` (V/mdp/events.py:205-271) + ``reset_joints_by_scale`` [IL] for the env ids, or -
+        without ids - for the envs flagged by the last ``step_pre_reset``. ``cfg`` is a ``cfg.ResetStateCfg``."""
+        c = nat.RlResetStateCfg()
+        drs = [0.0, 0.0, self.spec.layout.asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6
+        for i, v in enumerate(drs):
+            c.default_root_state[i] = v
+        for i, k in enumerate(("x", "y", "z", "roll", "pitch", "yaw")):
+            c.pose_lo[i], c.pose_hi[i] = cfg.pose_range.get(k, (0.0, 0.0))
+            c.vel_lo[i], c.vel_hi[i] = cfg.velocity_range.get(k, (0.0, 0.0))
+        c.joint_pos_scale_lo, c.joint_pos_scale_hi = cfg.joint_position_range
+        c.joint_vel_scale_lo, c.joint_vel_scale_hi = cfg.joint_velocity_range
+        st = b.state_view()
+        rnd = b.random(seed, step, env_id_offset, False, use_step_counter)
+        org = None
+        if env_origins is not None:
+            org = nat.RlField(env_origins.data_ptr(), env_origins.stride(0), env_origins.stride(1))
+        nat.check(self.lib.rl_reset_scene_state(
+            self._ctx, b.N, C.byref(c), C.byref(org) if org is not None else None, C.byref(st),
+            b.terminated.data_ptr(), b.truncated.data_ptr(), nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), C.byref(rnd),
+            nat.ptr_of(uniforms), self._stream()))
+
     def contact_sensor_update(self, b: StateBuffers, net_forces_w: torch.Tensor, dt: float, force_threshold: float = 1.0,
                               ring_slot: int = -1) -> None:
         """ContactSensor._update_buffers_impl [IL] for one physics sub-step: history roll (or ring-slot write) and the

@@ -86,6 +86,23 @@ class SyntheticStateProvider(StateProvider):
         return  # synthetic state has no notion of a physical reset
 
 
+class ResetEventStateProvider(SyntheticStateProvider):
+    """Synthetic producer whose ``reset`` applies the reference's mode="reset" state events on the device
+    (``reset_root_state_uniform`` V/mdp/events.py:205-271 + ``reset_joints_by_scale`` [IL]) through
+    ``rl_reset_scene_state`` - the post-reset root / joint state the observation launch then reads."""
+
+    def __init__(self, spec: StepSpec, num_envs: int, device, reset_cfg=None, env_origins: torch.Tensor | None = None, **kw):
+        super().__init__(spec, num_envs, device, **kw)
+        from .cfg import ResetStateCfg
+
+        self.reset_cfg = reset_cfg if reset_cfg is not None else ResetStateCfg()
+        self.env_origins = env_origins if env_origins is not None else torch.zeros(num_envs, 3, device=device)
+
+    def reset(self, env, env_ids, n_ids):
+        env.engine.reset_scene_state(env.buffers, self.reset_cfg, self.env_origins, env_ids=env_ids, n_env_ids=n_ids,
+                                     seed=env.seed, env_id_offset=env.rank * env.num_envs, use_step_counter=True)
+
+
 class ReplayStateProvider(StateProvider):
     """Feeds a fixed list of logical state dicts, one per step (tests: the oracle replays the same list)."""
 

@@ -52,5 +52,27 @@ def main():
         print(key, n, "envs,", sum(1 for k in arrays if k.startswith("reward/")), "reference-owned reward terms")
 
 
+def reset_event():
+    """reset_state_<task>.npz: inputs (ids, uniforms, env origins) and what the reference's reset_root_state_uniform
+    (V/mdp/events.py:205-271) writes into the simulator for them (Go2 rough ranges, GO2/rough_env_cfg.py:56-73)."""
+    from robot_lab_b200.cfg import ResetStateCfg
+
+    out_dir = Path(__file__).resolve().parent
+    for key, n in (("go2_rough", 96), ("g1_rough", 40)):
+        cfg, spec = H.make_spec(key)
+        st = make_state(spec, n, seed=SEED)
+        g = torch.Generator().manual_seed(SEED + 1)
+        uniforms = torch.rand(12 + 2 * spec.J, n, generator=g)
+        origins = torch.randn(n, 3, generator=g) * 20.0
+        ids = torch.randperm(n, generator=g)[: n // 3].sort().values.int()
+        ref = ref_harness.reference_reset_root_state(spec, st, ids, ResetStateCfg.go2_rough(), origins, uniforms)
+        arrays = {"ids": ids.numpy(), "uniforms": uniforms.numpy(), "env_origins": origins.numpy()}
+        arrays.update({f"out/{k}": v.numpy() for k, v in ref.items()})
+        np.savez_compressed(out_dir / f"reset_state_{key}.npz", **arrays)
+        print("reset_state", key, n, "envs,", len(ids), "reset")
+
+
 if __name__ == "__main__":
-    main()
+    if "--reset-event-only" not in sys.argv:
+        main()
+    reset_event()

@@ -9,6 +9,7 @@ import torch
 
 import helpers as H
 from oracle import mdp_port as port
+from robot_lab_b200.synthetic import make_state
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 KEYS = ["a1_flat", "go2_flat", "go2_rough", "g1_rough", "g1_rough_37", "go2_catalogue"]
@@ -70,3 +71,21 @@ def test_cuda_terms_reproduce_reference_outputs(native_lib, key):
             else:
                 torch.testing.assert_close(g, v, rtol=H.RTOL, atol=H.ATOL, msg=k)
     eng.close()
+
+
+@pytest.mark.parametrize("key", ["go2_rough", "g1_rough"])
+def test_oracle_reset_event_reproduces_reference_output(key):
+    """oracle.reset_scene_state vs the committed output of the reference's reset_root_state_uniform."""
+    import numpy as np
+
+    from robot_lab_b200.cfg import ResetStateCfg
+
+    z = np.load(GOLDEN / f"reset_state_{key}.npz")
+    cfg, spec = H.make_spec(key)
+    n = z["uniforms"].shape[1]
+    st = make_state(spec, n, seed=20260922)
+    ids = torch.from_numpy(z["ids"])
+    got = port.reset_scene_state(spec, st, ids, ResetStateCfg.go2_rough(), torch.from_numpy(z["env_origins"]),
+                                 torch.from_numpy(z["uniforms"]))
+    for k in ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_w"):
+        torch.testing.assert_close(got[k][ids.long()], torch.from_numpy(z[f"out/{k}"]), rtol=0, atol=0, msg=k)

@@ -55,3 +55,28 @@ def test_observation_functions_match_reference():
     got = port.compute_obs_group(spec, 0, st, {})
     torch.testing.assert_close(got[:, :2], ref["phase"].float(), rtol=1e-6, atol=1e-6)
     assert torch.equal(got[:, 2:], ref["joint_pos_rel_without_wheel"])
+
+
+@pytest.mark.parametrize("key", ["go2_rough", "g1_rough"])
+def test_reset_root_state_matches_reference_function(key):
+    """oracle.reset_scene_state vs the unmodified reset_root_state_uniform (V/mdp/events.py:205-271) on a fake asset,
+    same uniforms (the [IL] helpers quat_from_euler_xyz / quat_mul / sample_uniform are restated in both)."""
+    from robot_lab_b200.cfg import ResetStateCfg
+
+    cfg, spec = H.make_spec(key)
+    n = 80
+    st = make_state(spec, n)
+    g = torch.Generator().manual_seed(11)
+    u = torch.rand(12 + 2 * spec.J, n, generator=g)
+    org = torch.randn(n, 3, generator=g) * 15.0
+    ids = torch.tensor([0, 3, 4, 17, 42, 79], dtype=torch.int32)
+    for rc in (ResetStateCfg(), ResetStateCfg.go2_rough()):
+        got = port.reset_scene_state(spec, st, ids, rc, org, u)
+        from oracle import ref_harness
+
+        ref = ref_harness.reference_reset_root_state(spec, st, ids, rc, org, u)
+        for k, v in ref.items():
+            torch.testing.assert_close(got[k][ids.long()], v, rtol=0, atol=0, msg=k)
+        untouched = torch.ones(n, dtype=torch.bool)
+        untouched[ids.long()] = False
+        assert torch.equal(got["root_pos_w"][untouched], st["root_pos_w"][untouched])

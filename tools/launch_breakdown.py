@@ -43,7 +43,12 @@ def run_post(b):
 
 
 net_forces = torch.randn(N, spec.B, 3, device="cuda:0") * (torch.rand(N, spec.B, 1, device="cuda:0") < 0.3)
+from robot_lab_b200.cfg import ResetStateCfg  # noqa: E402
+
+reset_cfg = ResetStateCfg.go2_rough()
+origins = torch.zeros(N, 3, device="cuda:0")
 CASES = {
+    "reset_scene_state (root + joints of the done envs)": lambda b: eng.reset_scene_state(b, reset_cfg, origins, use_step_counter=True),
     "contact_sensor_update (history roll + timers)": lambda b: eng.contact_sensor_update(b, net_forces, 0.005),
     "contact_sensor_update (ring slot + timers)": lambda b: eng.contact_sensor_update(b, net_forces, 0.005, ring_slot=0),
     "process_action": lambda b: eng.process_action(b),
