@@ -2056,7 +2056,7 @@ int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
 
 // warps per CTA compiled for the generic kernel / for every baked spec
 #define RL_DYN_CONFIGS(X) X(4) X(8) X(16)
-#define RL_STATIC_CONFIGS(X) X(8) X(16)
+#define RL_STATIC_CONFIGS(X) X(4) X(8) X(16)
 
 template <class P, int MODE>
 int dispatch_config(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st, bool* found) {
