@@ -268,21 +268,32 @@ def main():
     use_graph = not args.no_graph
     G = ROLLOUT
     full_graph = capture(G, 0) if use_graph else None
+    single = {}   # one-step graphs per state set, for the steps that do not fill a whole rollout
 
     def run_steps(n: int, start: int = 0) -> None:
-        """Exactly n steps on `stream`; whole rollouts replay the captured graph, the remainder launches eagerly."""
+        """Exactly n steps on `stream`; whole rollouts replay the 24-step graph, the remainder one-step graphs."""
         i = 0
         with torch.cuda.stream(stream):
             while i < n:
-                if use_graph and n - i >= G and (start + i) % S == 0:
+                k = (start + i) % S
+                if use_graph and n - i >= G and k == 0:
                     full_graph.replay()
                     i += G
+                elif use_graph:
+                    if k not in single:
+                        single[k] = capture(1, k)
+                    single[k].replay()
+                    i += 1
                 else:
-                    one_step(sets[(start + i) % S])
+                    one_step(sets[k])
                     i += 1
 
-    # warm-up (>= 3 steps)
+    # warm-up (>= 3 steps); the one-step graphs the timed region may need are captured here, not inside it
     run_steps(W)
+    if use_graph:
+        for k in range(S):
+            if k not in single:
+                single[k] = capture(1, k)
     stream.synchronize()
 
     def barrier():
@@ -446,7 +457,7 @@ def measure_e2e(eng, spec, sets, N, K, W, rank, world, dev, local_rank, one_step
     ev_in = [torch.cuda.Event() for _ in range(ring)]
     ev_cmp = [torch.cuda.Event() for _ in range(ring)]
     ev_out = [torch.cuda.Event() for _ in range(ring)]
-    steps = min(K, 600)
+    steps = max(200, min(K, 600))   # its own step count: long enough for the 4-deep pipeline to reach steady state
 
     # the three launches of a set, captured once through the C-ABI calls: replaying them keeps the host side of a
     # step at a handful of stream operations (the Python / ctypes cost of three rl_* calls would otherwise bound it)
@@ -479,7 +490,7 @@ def measure_e2e(eng, spec, sets, N, K, W, rank, world, dev, local_rank, one_step
                 host_out[r].copy_(b.outputs.buf[:out_bytes], non_blocking=True)
                 ev_out[r].record(s_out)
 
-    run(max(3, min(W, 24)))
+    run(max(24, min(W, 48)))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier(device_ids=[local_rank])

@@ -234,3 +234,37 @@ def test_production_philox_stream_matches_oracle(native_lib):
     ref = port.step(spec, st, rnd)
     H.compare_outputs(got, ref)
     eng.close()
+
+
+def test_empty_inputs_and_bad_arguments(native_lib):
+    """num_envs == 0 is a no-op for every entry point; malformed calls come back as RL_EINVAL with a message, never as
+    a CUDA error or a crash (the reference raises Python exceptions at the same places)."""
+    import ctypes as C
+
+    cfg, spec = H.make_spec("go2_rough")
+    eng = _engine(spec)
+    b = eng.new_buffers(64)
+    b.load_logical(make_state(spec, 64))
+    lib = eng.lib
+    st, mdp, out, rnd = b.state_view(), b.mdp_state(), b.step_out(), b.random()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.rl_step(eng._ctx, 0, C.byref(st), C.byref(mdp), C.byref(out), C.byref(rnd), nat.PHASE_ALL, None, None, stream) == 0
+    na = b.field("new_action")
+    assert lib.rl_process_action(eng._ctx, 0, C.byref(na), C.byref(mdp), None, None, stream) == 0
+    # COMPACT without DONES, RESET together with REWARDS, RESET without the masks it needs, a missing observation input
+    for phases in (nat.PHASE_COMPACT, nat.PHASE_RESET | nat.PHASE_REWARDS):
+        with pytest.raises(nat.NativeError):
+            eng.step(b, phases=phases)
+    bad = b.step_out()
+    bad.terminated = None
+    with pytest.raises(nat.NativeError):
+        nat.check(lib.rl_step(eng._ctx, 64, C.byref(st), C.byref(mdp), C.byref(bad), C.byref(rnd),
+                              nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS, None, None, stream))
+    st2 = b.state_view()
+    st2.ray_hits_z = nat.RlField(None, 0, 0)
+    with pytest.raises(nat.NativeError):
+        nat.check(lib.rl_step(eng._ctx, 64, C.byref(st2), C.byref(mdp), C.byref(out), C.byref(rnd), nat.PHASE_OBS, None, None, stream))
+    torch.cuda.synchronize()
+    eng.step(b)   # the context is still usable afterwards
+    torch.cuda.synchronize()
+    eng.close()
