@@ -17,6 +17,16 @@
  *                       means, zeroing, command resample (V/mdp/commands.py:43-47), action reset
  *   rl_term_eval        one reward term function called on its own: func(env, **params) -> Tensor[N]
  *                       (term protocol, V/mdp/rewards.py:22 ff.)
+ *   neighbours of the path:
+ *   rl_contact_sensor_update   ContactSensor._update_buffers_impl [IL] (V/velocity_env_cfg.py:86,726)
+ *   rl_reset_scene_state       reset_root_state_uniform (V/mdp/events.py:205-271) + reset_joints_by_scale [IL]
+ *   rl_actuator_step           Articulation._apply_actuator_model [IL] with the DCMotor / IdealPD / Implicit
+ *                              actuator models the reference selects at assets/unitree.py:55-63,107-115,504-575
+ *   rl_is_robot_on_terrain     is_robot_on_terrain (V/mdp/utils.py:73-127)
+ *   rl_command_pit_restrict    the terrain-aware tail of UniformThresholdVelocityCommand._update_command
+ *                              (V/mdp/commands.py:61-85)
+ *   rl_height_scan_cast        the grid-pattern RayCaster [IL] (V/velocity_env_cfg.py:70-77) over a height-field
+ *                              terrain: produces ray_hits_z / ray_sensor_pos_z for the height_scan observation
  *
  * Conventions: every function returns 0 on success or a negative RL_E* code; rl_last_error() gives the
  * message (thread-local). All data pointers are DEVICE pointers borrowed for the duration of the call;
@@ -33,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 8
+#define RL_ABI_VERSION 9
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -405,7 +415,11 @@ typedef struct RlResetStateCfg {
 int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cfg, const RlField* env_origins /* [N,3] */,
                          const RlStateView* state, const uint8_t* terminated, const uint8_t* truncated,
                          const int32_t* env_ids, const int32_t* n_env_ids, const RlRandom* rnd,
-                         const float* uniforms, void* stream);
+                         const float* uniforms,
+                         const uint8_t* assigned_to_pits /* [N] is_env_assigned_to_terrain(env, "pits")
+                            (V/mdp/utils.py:44-70) or NULL: those envs get the default root state at their
+                            origin with zero velocity and no perturbation (V/mdp/events.py:232-244) */,
+                         void* stream);
 
 /* ContactSensor update [IL] (isaaclab/sensors/contact_sensor/contact_sensor.py, _update_buffers_impl; the reference
  * configures it at V/velocity_env_cfg.py:86 and updates it every physics sub-step, :726): the step immediately in
@@ -423,6 +437,97 @@ int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cf
 int rl_contact_sensor_update(RlCtx* ctx, int64_t num_envs, const RlField* net_forces_w, const RlStateView* state,
                              const int32_t* time_body_to_hist, float dt, float force_threshold, int32_t ring_slot,
                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * the actuator models between process_action and physics. IsaacLab runs them inside
+ * Articulation.write_data_to_sim() -> _apply_actuator_model() [IL], once per physics sub-step (decimation = 4,
+ * V/velocity_env_cfg.py:714), on the joint position target rl_process_action wrote:
+ *   error_pos = target_pos - joint_pos;  error_vel = target_vel - joint_vel
+ *   computed  = stiffness * error_pos + damping * error_vel + target_effort            (IdealPDActuator.compute [IL])
+ *   IDEAL_PD / IMPLICIT:  applied = clip(computed, -effort_limit, effort_limit)
+ *   DC_MOTOR (DCMotor._clip_effort [IL], the four-quadrant torque-speed curve):
+ *       vel       = clip(joint_vel, -vel_at_effort_lim, vel_at_effort_lim),
+ *                   vel_at_effort_lim = velocity_limit * (1 + effort_limit / saturation_effort)
+ *       top       = saturation_effort * ( 1 - vel / velocity_limit);  max_effort = min(top, effort_limit)
+ *       bottom    = saturation_effort * (-1 - vel / velocity_limit);  min_effort = max(bottom, -effort_limit)
+ *       applied   = clip(computed, min_effort, max_effort)
+ * For IMPLICIT actuators PhysX integrates the PD law itself; computed / applied are the approximations IsaacLab
+ * logs in data.computed_torque / data.applied_torque - exactly what joint_torques_l2 and joint_power read.
+ * The reference's actuator groups: A1 / Go2 "legs" DCMotor (assets/unitree.py:55-63, 107-115), G1 ImplicitActuator
+ * groups (:504-575).
+ */
+enum RlActuatorType { RL_ACT_NONE = 0, RL_ACT_IDEAL_PD = 1, RL_ACT_IMPLICIT = 2, RL_ACT_DC_MOTOR = 3 };
+
+typedef struct RlActuatorCfg {
+  int32_t num_joints;
+  int32_t reserved;
+  uint8_t type[RL_MAX_JOINTS];              /* RlActuatorType per native joint (RL_ACT_NONE: joint left untouched) */
+  float stiffness[RL_MAX_JOINTS];
+  float damping[RL_MAX_JOINTS];
+  float effort_limit[RL_MAX_JOINTS];
+  float saturation_effort[RL_MAX_JOINTS];   /* DC_MOTOR only */
+  float velocity_limit[RL_MAX_JOINTS];      /* DC_MOTOR only */
+} RlActuatorCfg;
+
+/* Reads state->joint_pos / joint_vel and the targets, writes state->applied_torque and (optionally) computed_torque.
+ * joint_vel_target / joint_effort_target may be NULL (zeros: the velocity tasks only set position targets). */
+int rl_actuator_step(RlCtx* ctx, int64_t num_envs, const RlActuatorCfg* cfg, const RlField* joint_pos_target,
+                     const RlField* joint_vel_target, const RlField* joint_effort_target, const RlStateView* state,
+                     const RlField* computed_torque, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * terrain-aware command restriction.
+ * Terrain grid: terrain_origins is the DEVICE tensor terrain.terrain_origins [num_rows, num_cols, 3] (contiguous);
+ * [col_start, col_end) is _get_terrain_column_range(cfg, name) (V/mdp/utils.py:16-41), computed on the host.
+ */
+typedef struct RlTerrainGrid {
+  const float* terrain_origins;   /* device, [num_rows * num_cols * 3] */
+  int32_t num_rows, num_cols;
+  int32_t col_start, col_end;     /* columns of the named sub-terrain; col_start >= col_end = terrain absent */
+} RlTerrainGrid;
+
+/* is_robot_on_terrain (V/mdp/utils.py:73-127): nearest terrain origin in the xy plane (first minimum in flat
+ * row-major order, like torch.argmin), out[env] = col_start <= (argmin % num_cols) < col_end. */
+int rl_is_robot_on_terrain(RlCtx* ctx, int64_t num_envs, const RlField* root_pos_w, const RlTerrainGrid* grid,
+                           uint8_t* out /* [N] */, void* stream);
+
+/* The tail of UniformThresholdVelocityCommand._update_command (V/mdp/commands.py:61-85), to be launched after
+ * rl_step(... | RL_PHASE_COMMAND) and before the observations when the terrain has a "pits" sub-terrain:
+ *   on_pits  = is_robot_on_terrain(env, "pits")
+ *   left pit (was_on_pit & !on_pits): _resample_command - new vx, vy, wz, heading target, heading / standing flags,
+ *            xy command zeroed below small_cmd_threshold (:43-47); time_left is NOT touched
+ *   on pits: vx = clamp(|vx|, 0.3, 0.6), vy = wz = 0, heading_target = 0
+ *   was_on_pit = on_pits
+ * Uniforms: rnd->cmd_uniforms rows 1..6 ([RL_NUM_CMD_UNIFORMS][N], row 0 unused) or the Philox stream
+ * RL_STREAM_PIT_RESAMPLE. Uses the command ranges of the context's spec. */
+int rl_command_pit_restrict(RlCtx* ctx, int64_t num_envs, const RlField* root_pos_w, const RlTerrainGrid* grid,
+                            const RlMdpState* mdp, uint8_t* was_on_pit /* [N] in/out */, const RlRandom* rnd,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Height scanner: RayCasterCfg(offset (0,0,20), ray_alignment "yaw", GridPatternCfg(resolution 0.1, size
+ * [1.6, 1.0]), mesh_prim_paths ["/World/ground"]) at V/velocity_env_cfg.py:70-77 -> 17 x 11 = 187 vertical rays.
+ * Upstream [IL] casts them against the terrain triangle mesh with Warp; the generated rough terrains are height
+ * fields (isaaclab.terrains.height_field), whose mesh is the regular triangulation of a height grid, so the hit
+ * point of a vertical ray is the piecewise-linear interpolation of that grid at the ray's (x, y):
+ *   ray start = root_pos_w + quat_apply(yaw_quat(root_quat_w), ray_starts[r])     (quat_apply_yaw [IL])
+ *   data.pos_w = root_pos_w (the 20 m offset lives in ray_starts, not in pos_w)
+ *   hit z = interpolation over the cell's two triangles (diagonal from vertex (i, j) to (i+1, j+1), the
+ *           triangulation of convert_height_field_to_mesh [IL]); rays that leave the grid hit nothing -> +inf
+ * Output: ray_hits_z [N, R] and ray_sensor_pos_z [N] of RlStateView - what the height_scan observation reads.
+ */
+typedef struct RlHeightField {
+  const float* heights;          /* device [num_x * num_y] vertex heights (m), x-major: h[ix * num_y + iy] */
+  int32_t num_x, num_y;
+  float x0, y0;                  /* world position of vertex (0, 0) */
+  float horizontal_scale;        /* vertex spacing (m) */
+  int32_t num_rays;              /* R = spec.num_rays */
+  const float* ray_starts;       /* device [R * 3]: pattern offsets in the sensor frame INCLUDING the sensor offset
+                                    (RayCaster.ray_starts [IL]); rays point along -z */
+} RlHeightField;
+
+int rl_height_scan_cast(RlCtx* ctx, int64_t num_envs, const RlHeightField* hf, const RlStateView* state /* reads
+                        root_pos_w, root_quat_w; writes ray_hits_z, ray_sensor_pos_z */, void* stream);
 
 /* The fused step over envs [0, num_envs), or over env_ids[0 .. *n_env_ids) when env_ids != NULL
  * (n_env_ids is a DEVICE pointer so that no host sync is needed after the reset compaction). */

@@ -12,7 +12,8 @@ source/robot_lab/robot_lab/tasks/manager_based/locomotion/velocity/):
     ``oracle/isaaclab_shim.py`` in the build container and compares every term; the committed fixtures under
     ``tests/golden/`` were produced by the reference functions themselves (``tests/golden/make_golden.py``).
   * robot_lab-owned observation terms and command logic - V/mdp/observations.py:17-35, V/mdp/commands.py:43-85
-    (the "pits" branch is identically off for the in-scope terrains: V/mdp/utils.py:27-28).
+    (the "pits" branch is identically off for the in-scope terrains, V/mdp/utils.py:27-28; it is restated
+    separately in ``command_pit_restrict`` / ``is_robot_on_terrain`` for terrains that do have pits).
   * IsaacLab-owned pieces [IL] - upstream reward / observation / termination terms, the manager loops
     (RewardManager.compute, ObservationManager.compute_group, TerminationManager.compute, CommandTerm.compute,
     UniformVelocityCommand, JointAction.process_actions), math helpers and ContactSensor.compute_first_contact.
@@ -672,7 +673,7 @@ def quat_mul(q1: torch.Tensor, q2: torch.Tensor) -> torch.Tensor:
 
 
 def reset_scene_state(spec: StepSpec, st: State, ids: torch.Tensor, cfg, env_origins: torch.Tensor,
-                      uniforms: torch.Tensor) -> dict:
+                      uniforms: torch.Tensor, assigned_to_pits: torch.Tensor | None = None) -> dict:
     """``reset_root_state_uniform`` (V/mdp/events.py:205-271, non-pit branch) followed by ``reset_joints_by_scale``
     [IL] (wired at V/velocity_env_cfg.py:326-363) for ``ids``. ``uniforms`` is [12 + 2J, N] U[0,1): pose 6, velocity 6,
     joint position J, joint velocity J; ``sample_uniform`` [IL] = rand * (hi - lo) + lo. ``cfg``: cfg.ResetStateCfg."""
@@ -699,6 +700,15 @@ def reset_scene_state(spec: StepSpec, st: State, ids: torch.Tensor, cfg, env_ori
     vlo, vhi = cfg.joint_velocity_range
     jp = q0.unsqueeze(0) * (uniforms[12:12 + J, ids].t() * (phi - plo) + plo)
     jv = qd0.unsqueeze(0) * (uniforms[12 + J:12 + 2 * J, ids].t() * (vhi - vlo) + vlo)
+    if assigned_to_pits is not None:
+        # V/mdp/events.py:232-244: envs assigned to the "pits" sub-terrain get the default root state at their origin
+        pit = ids[assigned_to_pits[ids].bool()]
+        if len(pit) > 0:
+            rp = drs.unsqueeze(0).repeat(len(pit), 1)
+            out["root_pos_w"][pit] = rp[:, 0:3] + env_origins[pit]
+            out["root_quat_w"][pit] = rp[:, 3:7]
+            out["root_lin_vel_w"][pit] = 0.0
+            out["root_ang_vel_w"][pit] = 0.0
     out["joint_pos"][ids] = torch.maximum(torch.minimum(jp, lim[:, 1]), lim[:, 0])
     out["joint_vel"][ids] = torch.maximum(torch.minimum(jv, vlim), -vlim)
     return out
@@ -751,3 +761,147 @@ def reset_envs(spec: StepSpec, st: State, ids: torch.Tensor, done_bits: torch.Te
     if len(ids) > 0:
         _resample(spec, ids, command_uniforms(spec, st, rnd, philox.STREAM_RESET_COMMAND), out)
     return out, log
+
+
+# ------------------------------------------------------------------------------------------------
+# actuator models between process_action and physics
+# ------------------------------------------------------------------------------------------------
+def actuator_step(table: dict, joint_pos_target: torch.Tensor, joint_pos: torch.Tensor, joint_vel: torch.Tensor,
+                  joint_vel_target: torch.Tensor | None = None, joint_effort_target: torch.Tensor | None = None):
+    """Articulation._apply_actuator_model [IL] for every actuator group of the asset (isaaclab/assets/articulation/
+    articulation.py; isaaclab/actuators/actuator_pd.py: ImplicitActuator / IdealPDActuator / DCMotor, IsaacLab
+    v2.3.2). The reference selects the models at assets/unitree.py:55-63 (A1, DCMotor), :107-115 (Go2, DCMotor),
+    :504-621 (G1, ImplicitActuator). PARITY UNPINNED: the file is not vendored; restated from the upstream algorithm
+    (the v2.2+ four-quadrant form of DCMotor._clip_effort).
+
+    ``table`` = RobotAsset.actuator_table(). Returns (computed_torque, applied_torque), [N, J]; joints without an
+    actuator keep 0."""
+    n, J = joint_pos.shape
+    f32 = torch.float32
+    kp = torch.tensor(table["stiffness"], dtype=f32)
+    kd = torch.tensor(table["damping"], dtype=f32)
+    lim = torch.tensor(table["effort_limit"], dtype=f32).unsqueeze(0).repeat(n, 1)   # parsed into [N, J] tensors [IL]
+    vlim = torch.tensor(table["velocity_limit"], dtype=f32).unsqueeze(0).repeat(n, 1)
+    vt = torch.zeros_like(joint_pos) if joint_vel_target is None else joint_vel_target
+    et = torch.zeros_like(joint_pos) if joint_effort_target is None else joint_effort_target
+    # IdealPDActuator.compute / ImplicitActuator.compute
+    error_pos = joint_pos_target - joint_pos
+    error_vel = vt - joint_vel
+    computed = kp * error_pos + kd * error_vel + et
+    applied = torch.clip(computed, min=-lim, max=lim)
+    # DCMotor._clip_effort
+    for j, kind in enumerate(table["kind"]):
+        if kind == "dc_motor":
+            sat = float(table["saturation_effort"][j])
+            vel_at_effort_lim = vlim[:, j] * (1 + lim[:, j] / sat)
+            vel = torch.clip(joint_vel[:, j], min=-vel_at_effort_lim, max=vel_at_effort_lim)
+            torque_speed_top = sat * (1.0 - vel / vlim[:, j])
+            torque_speed_bottom = sat * (-1.0 - vel / vlim[:, j])
+            max_effort = torch.clip(torque_speed_top, max=lim[:, j])
+            min_effort = torch.clip(torque_speed_bottom, min=-lim[:, j])
+            applied[:, j] = torch.clip(computed[:, j], min=min_effort, max=max_effort)
+        elif kind == "none":
+            computed[:, j] = 0.0
+            applied[:, j] = 0.0
+    return computed, applied
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) row 4: terrain-aware command restriction (V/mdp/utils.py, V/mdp/commands.py:49-85)
+# ------------------------------------------------------------------------------------------------
+def terrain_column_range(sub_terrains: list[str], proportions: list[float], num_cols: int, name: str):
+    """``_get_terrain_column_range`` (V/mdp/utils.py:16-41): fp32 torch cumsum of the normalised proportions, python
+    ``round`` of (cumsum * num_cols)."""
+    if name not in sub_terrains:
+        return None
+    p = torch.tensor(proportions)
+    p = p / p.sum()
+    c = torch.cumsum(p, dim=0)
+    i = sub_terrains.index(name)
+    col_start = round((0.0 if i == 0 else c[i - 1].item()) * num_cols)
+    col_end = round(c[i].item() * num_cols)
+    return col_start, col_end
+
+
+def is_robot_on_terrain(root_pos_w: torch.Tensor, terrain_origins: torch.Tensor, col_range) -> torch.Tensor:
+    """``is_robot_on_terrain`` (V/mdp/utils.py:73-127) for a generator terrain: argmin over the xy distance to every
+    terrain origin (flat row-major index, first minimum), column = index % num_cols, inside [col_start, col_end).
+    The distance is evaluated as sqrt(dx^2 + dy^2) - the definition of torch.cdist; the reference call goes through
+    cdist's matmul path for these sizes, which rounds differently (robots within ~1e-4 m of a cell boundary)."""
+    n = root_pos_w.shape[0]
+    if col_range is None:
+        return torch.zeros(n, dtype=torch.bool)
+    rows, cols, _ = terrain_origins.shape
+    o = terrain_origins[:, :, :2].reshape(rows * cols, 2)
+    dx = root_pos_w[:, 0:1] - o[:, 0].unsqueeze(0)
+    dy = root_pos_w[:, 1:2] - o[:, 1].unsqueeze(0)
+    d = torch.sqrt(dx * dx + dy * dy)
+    col = torch.argmin(d, dim=1) % cols
+    return (col >= col_range[0]) & (col < col_range[1])
+
+
+def command_pit_restrict(spec: StepSpec, st: State, on_pits: torch.Tensor, was_on_pit: torch.Tensor,
+                         u: torch.Tensor) -> dict:
+    """The tail of ``UniformThresholdVelocityCommand._update_command`` (V/mdp/commands.py:61-85) applied to the
+    command state in ``st`` (i.e. after the parent's _update_command). ``u`` is the [7, N] uniform table (row 0
+    unused: _resample_command does not touch time_left)."""
+    c = spec.command
+    out = {k: st[k].clone() for k in ("command", "heading_target", "is_heading_env", "is_standing_env")}
+    left = (was_on_pit & ~on_pits).nonzero(as_tuple=False).flatten()
+    if len(left) > 0:
+        tmp = dict(out)
+        tmp["time_left"] = torch.zeros(on_pits.shape[0])
+        _resample(spec, left, u, tmp)
+    pit = on_pits.nonzero(as_tuple=False).flatten()
+    if len(pit) > 0:
+        out["command"][pit, 0] = torch.clamp(torch.abs(out["command"][pit, 0]), min=0.3, max=0.6)
+        out["command"][pit, 1] = 0.0
+        out["command"][pit, 2] = 0.0
+        if c.heading_command:
+            out["heading_target"][pit] = 0.0
+    out["was_on_pit"] = on_pits.clone()
+    return out
+
+
+def grid_pattern_ray_starts(size: tuple[float, float], resolution: float, offset_z: float) -> torch.Tensor:
+    """patterns.grid_pattern [IL] with ordering "xy" + RayCaster._initialize_rays_impl [IL]: [R, 3] ray starts in the
+    sensor frame, x fastest, the sensor offset (0, 0, offset_z) already added (V/velocity_env_cfg.py:70-77)."""
+    x = torch.arange(start=-size[0] / 2, end=size[0] / 2 + 1.0e-9, step=resolution)
+    y = torch.arange(start=-size[1] / 2, end=size[1] / 2 + 1.0e-9, step=resolution)
+    gx, gy = torch.meshgrid(x, y, indexing="xy")
+    starts = torch.zeros(gx.numel(), 3)
+    starts[:, 0] = gx.flatten()
+    starts[:, 1] = gy.flatten()
+    starts[:, 2] += offset_z
+    return starts
+
+
+def height_scan_cast(heights: torch.Tensor, x0: float, y0: float, horizontal_scale: float, ray_starts: torch.Tensor,
+                     root_pos_w: torch.Tensor, root_quat_w: torch.Tensor):
+    """RayCaster._update_buffers_impl [IL] with ray_alignment="yaw" over the triangle mesh of a height field
+    (isaaclab/terrains/height_field/utils.py: convert_height_field_to_mesh - vertex (i, j) at (i, j) * scale, two
+    triangles per cell, (v00, v11, v01) and (v00, v10, v11)). A vertical ray hits the mesh at the piecewise-linear
+    interpolation of the vertex heights; rays outside the field hit nothing (+inf). PARITY UNPINNED (upstream casts
+    with Warp's mesh query; equal up to the rounding of t * direction, ~1e-5 m for 20 m rays).
+
+    Returns (ray_hits_z [N, R], sensor_pos_z [N])."""
+    n, R = root_pos_w.shape[0], ray_starts.shape[0]
+    q = yaw_quat(root_quat_w)
+    starts = quat_apply(q.repeat_interleave(R, dim=0), ray_starts.repeat(n, 1)).reshape(n, R, 3)
+    wx = starts[:, :, 0] + root_pos_w[:, 0:1]
+    wy = starts[:, :, 1] + root_pos_w[:, 1:2]
+    gx = (wx - x0) / horizontal_scale
+    gy = (wy - y0) / horizontal_scale
+    nx, ny = heights.shape
+    inside = (gx >= 0) & (gy >= 0) & (gx <= nx - 1) & (gy <= ny - 1)
+    ix = gx.clamp(0, nx - 1).long().clamp(max=nx - 2)
+    iy = gy.clamp(0, ny - 1).long().clamp(max=ny - 2)
+    fx = gx - ix.float()
+    fy = gy - iy.float()
+    h00, h01 = heights[ix, iy], heights[ix, iy + 1]
+    h10, h11 = heights[ix + 1, iy], heights[ix + 1, iy + 1]
+    za = (h00 + fx * (h11 - h01)) + fy * (h01 - h00)
+    zb = (h00 + fx * (h10 - h00)) + fy * (h11 - h10)
+    z = torch.where(fy >= fx, za, zb)
+    z = torch.where(inside, z, torch.full_like(z, float("inf")))
+    return z, root_pos_w[:, 2].clone()

@@ -255,15 +255,34 @@ def _install_command_context(uniform_table: torch.Tensor):
     return sys.modules[f"{pkg}.commands"]
 
 
-def reference_command_compute(spec: StepSpec, st: dict, uniform_table: torch.Tensor, terrain_type: str) -> dict:
-    """One CommandTerm.compute(dt) through the reference's UniformThresholdVelocityCommand class."""
+def fake_terrain(terrain_cfg, terrain_type: str, num_envs: int, terrain_origins: torch.Tensor | None = None,
+                 terrain_types: torch.Tensor | None = None):
+    """A terrain importer the way V/mdp/utils.py inspects it (:56-66, :86-107): cfg.terrain_type,
+    cfg.terrain_generator.{sub_terrains{name: .proportion}, num_cols}, terrain_types, terrain_origins."""
+    props = getattr(terrain_cfg, "proportions", None) or [1.0] * len(terrain_cfg.sub_terrains)
+    gen = _NS(sub_terrains={k: _NS(proportion=float(p)) for k, p in zip(terrain_cfg.sub_terrains, props)},
+              num_cols=terrain_cfg.num_cols)
+    ter = _NS(cfg=_NS(terrain_type=terrain_type, terrain_generator=gen if terrain_type == "generator" else None),
+              terrain_types=torch.zeros(num_envs, dtype=torch.long) if terrain_types is None else terrain_types)
+    if terrain_origins is not None:
+        ter.terrain_origins = terrain_origins
+    return ter
+
+
+def reference_terrain_utils():
+    """The unmodified V/mdp/utils.py module (no isaaclab import at run time)."""
+    _install_command_context(torch.zeros(7, 1))
+    return sys.modules["robot_lab.tasks.manager_based.locomotion.velocity.mdp.utils"]
+
+
+def reference_command_compute(spec: StepSpec, st: dict, uniform_table: torch.Tensor, terrain_type: str,
+                              terrain=None, was_on_pit: torch.Tensor | None = None) -> dict:
+    """One CommandTerm.compute(dt) through the reference's UniformThresholdVelocityCommand class. ``terrain`` (a
+    ``fake_terrain`` with origins) + ``was_on_pit`` exercise the pit branch of _update_command (:61-85)."""
     commands = _install_command_context(uniform_table)
     env = FakeEnv(spec, st)
     c = spec.command
-    # a terrain the way utils.is_robot_on_terrain inspects it (V/mdp/utils.py:86-96)
-    gen = _NS(sub_terrains={k: _NS(proportion=1.0) for k in spec.layout.terrain.sub_terrains}, num_cols=spec.layout.terrain.num_cols)
-    env.scene.terrain = _NS(cfg=_NS(terrain_type=terrain_type, terrain_generator=gen if terrain_type == "generator" else None),
-                            terrain_types=torch.zeros(env.num_envs, dtype=torch.long))
+    env.scene.terrain = terrain if terrain is not None else fake_terrain(spec.layout.terrain, terrain_type, env.num_envs)
     cfg = _NS(asset_name="robot", resampling_time_range=c.resampling_time, rel_standing_envs=c.rel_standing_envs,
               rel_heading_envs=c.rel_heading_envs, heading_command=c.heading_command,
               heading_control_stiffness=c.heading_control_stiffness,
@@ -276,8 +295,11 @@ def reference_command_compute(spec: StepSpec, st: dict, uniform_table: torch.Ten
     term.is_standing_env = st["is_standing_env"].clone()
     term.metrics["error_vel_xy"] = st["metric_error_vel_xy"].clone()
     term.metrics["error_vel_yaw"] = st["metric_error_vel_yaw"].clone()
+    if was_on_pit is not None:
+        term.was_on_pit = was_on_pit.clone()
     term.compute(spec.step_dt)
     return {
+        "was_on_pit": term.was_on_pit,
         "command": term.vel_command_b, "heading_target": term.heading_target, "time_left": term.time_left,
         "is_heading_env": term.is_heading_env, "is_standing_env": term.is_standing_env,
         "metric_error_vel_xy": term.metrics["error_vel_xy"], "metric_error_vel_yaw": term.metrics["error_vel_yaw"],
@@ -288,7 +310,7 @@ def reference_command_compute(spec: StepSpec, st: dict, uniform_table: torch.Ten
 # reset event: the reference's reset_root_state_uniform (V/mdp/events.py:205-271) on a fake asset
 # ------------------------------------------------------------------------------------------------
 def reference_reset_root_state(spec: StepSpec, st: dict, ids: torch.Tensor, cfg, env_origins: torch.Tensor,
-                               uniforms: torch.Tensor) -> dict:
+                               uniforms: torch.Tensor, terrain=None) -> dict:
     """Run the unmodified ``reset_root_state_uniform`` for ``ids`` with the given uniforms ([12+, N]: pose 6, velocity
     6) and return what it writes into the simulator (root pose + velocity of those envs)."""
     _install_command_context(torch.zeros(7, st["root_quat_w"].shape[0]))   # package context for the relative imports
@@ -308,20 +330,29 @@ def reference_reset_root_state(spec: StepSpec, st: dict, ids: torch.Tensor, cfg,
     asset = env.scene["robot"]
     drs = torch.tensor([0.0, 0.0, spec.layout.asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6)
     asset.data.default_root_state = drs.unsqueeze(0).repeat(n, 1)
-    written = {}
+    pose_w = torch.full((n, 7), float("nan"))
+    vel_w = torch.full((n, 6), float("nan"))
 
     def write_pose(pose, env_ids=None):
-        written["pose"], written["pose_ids"] = pose.clone(), env_ids.clone()
+        pose_w[env_ids] = pose
 
     def write_vel(vel, env_ids=None):
-        written["vel"], written["vel_ids"] = vel.clone(), env_ids.clone()
+        vel_w[env_ids] = vel
 
     asset.write_root_pose_to_sim, asset.write_root_velocity_to_sim = write_pose, write_vel
     env.scene.env_origins = env_origins
+    if terrain is not None:
+        env.scene.terrain = terrain
     ids = ids.long()
     math_mod = sys.modules["isaaclab.utils.math"]
-    math_mod._uniform_queue[:] = [uniforms[0:6, ids].t().contiguous(), uniforms[6:12, ids].t().contiguous()]
+    rnd_ids = ids
+    if terrain is not None:   # the reference samples only for the non-pit envs (V/mdp/events.py:247-265)
+        utils = sys.modules[f"{pkg}.utils"]
+        rnd_ids = ids[~utils.is_env_assigned_to_terrain(env, "pits")[ids]]
+    math_mod._uniform_queue[:] = [uniforms[0:6, rnd_ids].t().contiguous(), uniforms[6:12, rnd_ids].t().contiguous()]
     events.reset_root_state_uniform(env, ids, dict(cfg.pose_range), dict(cfg.velocity_range))
-    assert not math_mod._uniform_queue and torch.equal(written["pose_ids"], ids) and torch.equal(written["vel_ids"], ids)
-    return {"root_pos_w": written["pose"][:, 0:3], "root_quat_w": written["pose"][:, 3:7],
-            "root_lin_vel_w": written["vel"][:, 0:3], "root_ang_vel_w": written["vel"][:, 3:6]}
+    assert (not math_mod._uniform_queue) or len(rnd_ids) == 0
+    math_mod._uniform_queue[:] = []
+    assert not torch.isnan(pose_w[ids]).any() and not torch.isnan(vel_w[ids]).any()
+    return {"root_pos_w": pose_w[ids, 0:3], "root_quat_w": pose_w[ids, 3:7],
+            "root_lin_vel_w": vel_w[ids, 0:3], "root_ang_vel_w": vel_w[ids, 3:6]}

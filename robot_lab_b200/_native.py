@@ -14,7 +14,7 @@ from pathlib import Path
 
 import torch
 
-RL_ABI_VERSION = 8
+RL_ABI_VERSION = 9
 RL_MAX_TASKS = 112
 RL_DEBUG_STRIDE = 160
 RL_MAX_JOINTS = 64
@@ -156,6 +156,31 @@ class RlResetStateCfg(C.Structure):
     ]
 
 
+# enum RlActuatorType
+ACT_NONE, ACT_IDEAL_PD, ACT_IMPLICIT, ACT_DC_MOTOR = 0, 1, 2, 3
+ACTUATOR_TYPES = {"none": ACT_NONE, "ideal_pd": ACT_IDEAL_PD, "implicit": ACT_IMPLICIT, "dc_motor": ACT_DC_MOTOR}
+
+
+class RlActuatorCfg(C.Structure):
+    _fields_ = [
+        ("num_joints", C.c_int32), ("reserved", C.c_int32), ("type", C.c_uint8 * RL_MAX_JOINTS),
+        ("stiffness", C.c_float * RL_MAX_JOINTS), ("damping", C.c_float * RL_MAX_JOINTS),
+        ("effort_limit", C.c_float * RL_MAX_JOINTS), ("saturation_effort", C.c_float * RL_MAX_JOINTS),
+        ("velocity_limit", C.c_float * RL_MAX_JOINTS),
+    ]
+
+
+class RlTerrainGrid(C.Structure):
+    _fields_ = [("terrain_origins", C.c_void_p), ("num_rows", C.c_int32), ("num_cols", C.c_int32),
+                ("col_start", C.c_int32), ("col_end", C.c_int32)]
+
+
+class RlHeightField(C.Structure):
+    _fields_ = [("heights", C.c_void_p), ("num_x", C.c_int32), ("num_y", C.c_int32), ("x0", C.c_float),
+                ("y0", C.c_float), ("horizontal_scale", C.c_float), ("num_rays", C.c_int32),
+                ("ray_starts", C.c_void_p)]
+
+
 class RlStepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p * RL_NUM_OBS_GROUPS), ("obs_pitch", C.c_int64 * RL_NUM_OBS_GROUPS),
@@ -172,12 +197,14 @@ class RlRandom(C.Structure):
 
 
 _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlActionCfg, RlStepSpec, RlField,
-            RlStateView, RlMdpState, RlStepOut, RlRandom, RlResetLog, RlResetStateCfg)
+            RlStateView, RlMdpState, RlStepOut, RlRandom, RlResetLog, RlResetStateCfg, RlActuatorCfg, RlTerrainGrid,
+            RlHeightField)
 
 EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
     "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_ctx_get_schedule",
     "rl_contact_sensor_update", "rl_reset_scene_state", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
+    "rl_actuator_step", "rl_is_robot_on_terrain", "rl_command_pit_restrict", "rl_height_scan_cast",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -222,7 +249,16 @@ def load() -> C.CDLL:
     lib.rl_ctx_get_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.rl_reset_scene_state.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlResetStateCfg), C.POINTER(RlField),
                                          C.POINTER(RlStateView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.POINTER(RlRandom), C.c_void_p, C.c_void_p]
+                                         C.POINTER(RlRandom), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rl_actuator_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlActuatorCfg), C.POINTER(RlField),
+                                     C.POINTER(RlField), C.POINTER(RlField), C.POINTER(RlStateView),
+                                     C.POINTER(RlField), C.c_void_p]
+    lib.rl_is_robot_on_terrain.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlTerrainGrid),
+                                           C.c_void_p, C.c_void_p]
+    lib.rl_command_pit_restrict.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlTerrainGrid),
+                                            C.POINTER(RlMdpState), C.c_void_p, C.POINTER(RlRandom), C.c_void_p]
+    lib.rl_height_scan_cast.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlHeightField), C.POINTER(RlStateView),
+                                        C.c_void_p]
     lib.rl_contact_sensor_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlStateView),
                                              C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_int32, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),

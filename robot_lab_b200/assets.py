@@ -1,7 +1,8 @@
 """Robot constants for the MDP step (joint / body tables, default pose, limits, action scales).
 
-Only the *constants* the MDP terms read are kept here - spawning, meshes and actuator models
-belong to the physics side, which is out of scope.
+Only the *constants* the MDP terms and their neighbours read are kept here - spawning and meshes belong to the
+physics side, which is out of scope. The actuator groups (``ActuatorGroup``) are the
+parameters of ``rl_actuator_step``.
 
 Sources (reference, file:line):
   * A1   : source/robot_lab/robot_lab/assets/unitree.py:19-65,  a1_description/urdf/a1.urdf:363-895
@@ -33,6 +34,25 @@ def _match_first(patterns: dict[str, float], name: str, default: float | None = 
 
 
 @dataclass(frozen=True)
+class ActuatorGroup:
+    """One entry of ``ArticulationCfg.actuators`` [IL]: ``kind`` is "dc_motor" (DCMotorCfg), "implicit"
+    (ImplicitActuatorCfg) or "ideal_pd"; every value is a float or a {joint-name regex: float} table."""
+
+    name: str
+    kind: str
+    joint_names_expr: tuple[str, ...]
+    stiffness: float | dict
+    damping: float | dict
+    effort_limit: float | dict
+    saturation_effort: float | dict = 0.0
+    velocity_limit: float | dict = 0.0
+
+    def value(self, attr: str, joint: str) -> float:
+        v = getattr(self, attr)
+        return float(_match_first(v, joint)) if isinstance(v, dict) else float(v)
+
+
+@dataclass(frozen=True)
 class RobotAsset:
     """Constant tables of one articulation, in native order."""
 
@@ -45,6 +65,7 @@ class RobotAsset:
     soft_joint_pos_limit_factor: float = 0.9
     init_root_height: float = 0.38
     action_scale_patterns: dict[str, float] = field(default_factory=dict)
+    actuators: tuple[ActuatorGroup, ...] = ()
 
     # -- derived tables -------------------------------------------------------------------
     @property
@@ -63,6 +84,17 @@ class RobotAsset:
 
     def joint_vel_limits(self) -> list[float]:
         return [_match_first(self.joint_vel_limit_patterns, n) for n in self.joint_names]
+
+    def actuator_table(self) -> dict[str, list]:
+        """Per native joint: kind, stiffness, damping, effort_limit, saturation_effort, velocity_limit (the first
+        group whose ``joint_names_expr`` matches the joint owns it, like Articulation._process_actuators_cfg [IL])."""
+        tab = {k: [] for k in ("kind", "stiffness", "damping", "effort_limit", "saturation_effort", "velocity_limit")}
+        for n in self.joint_names:
+            grp = next((g for g in self.actuators if any(re.fullmatch(e, n) for e in g.joint_names_expr)), None)
+            tab["kind"].append("none" if grp is None else grp.kind)
+            for k in ("stiffness", "damping", "effort_limit", "saturation_effort", "velocity_limit"):
+                tab[k].append(0.0 if grp is None else grp.value(k, n))
+        return tab
 
     def soft_joint_pos_limits(self) -> list[tuple[float, float]]:
         """mid -/+ 0.5 * range * factor (IsaacLab ArticulationData)."""
@@ -111,6 +143,8 @@ UNITREE_GO2 = RobotAsset(
     default_joint_pos_patterns=_QUAD_DEFAULT_POSE,
     joint_vel_limit_patterns={".*": 30.0},  # DCMotorCfg.velocity_limit, assets/unitree.py:111
     init_root_height=0.38,
+    actuators=(ActuatorGroup("legs", "dc_motor", (".*",), stiffness=25.0, damping=0.5, effort_limit=23.5,
+                             saturation_effort=23.5, velocity_limit=30.0),),  # assets/unitree.py:107-115
 )
 
 UNITREE_A1 = RobotAsset(
@@ -132,6 +166,8 @@ UNITREE_A1 = RobotAsset(
     default_joint_pos_patterns=_QUAD_DEFAULT_POSE,
     joint_vel_limit_patterns={".*": 21.0},  # assets/unitree.py:59
     init_root_height=0.38,
+    actuators=(ActuatorGroup("legs", "dc_motor", (".*_joint",), stiffness=20.0, damping=0.5, effort_limit=33.5,
+                             saturation_effort=33.5, velocity_limit=21.0),),  # assets/unitree.py:55-63
 )
 
 # ---------------------------------------------------------------------------------------------
@@ -243,6 +279,17 @@ _G1_VEL_LIMITS = {  # velocity_limit_sim, assets/unitree.py:518-591
     ".*_elbow_joint": 37.0, ".*_wrist_roll_joint": 37.0, ".*_wrist_pitch_joint": 22.0, ".*_wrist_yaw_joint": 22.0,
 }
 
+# ImplicitActuatorCfg groups of assets/unitree.py:504-621 folded into one table: stiffness / effort from
+# _G1_EFFORT_STIFFNESS, damping = 2 * DAMPING_RATIO * armature * NATURAL_FREQ = stiffness * 2 * DAMPING_RATIO /
+# NATURAL_FREQ (assets/unitree.py:454-464, DAMPING_RATIO = 2), velocity_limit_sim from _G1_VEL_LIMITS
+_G1_DAMPING_RATIO = 2.0
+_G1_ACTUATORS = (ActuatorGroup(
+    "all", "implicit", (".*",),
+    stiffness={k: s for k, (_e, s) in _G1_EFFORT_STIFFNESS.items()},
+    damping={k: s * 2.0 * _G1_DAMPING_RATIO / _NATURAL_FREQ for k, (_e, s) in _G1_EFFORT_STIFFNESS.items()},
+    effort_limit={k: e for k, (e, _s) in _G1_EFFORT_STIFFNESS.items()},
+    velocity_limit=_G1_VEL_LIMITS),)
+
 UNITREE_G1_29DOF = RobotAsset(
     name="unitree_g1_29dof",
     joint_names=_G1_JOINTS,
@@ -252,6 +299,7 @@ UNITREE_G1_29DOF = RobotAsset(
     joint_vel_limit_patterns=_G1_VEL_LIMITS,
     init_root_height=0.76,
     action_scale_patterns=UNITREE_G1_29DOF_ACTION_SCALE,
+    actuators=_G1_ACTUATORS,
 )
 
 # J = 37 synthetic variant: the 29-DoF body plus 8 finger joints (4 per hand). It exists to honour
@@ -266,6 +314,8 @@ UNITREE_G1_37DOF = RobotAsset(
     joint_vel_limit_patterns={**_G1_VEL_LIMITS, ".*_finger_.*": 22.0},
     init_root_height=0.76,
     action_scale_patterns={**UNITREE_G1_29DOF_ACTION_SCALE, ".*_finger_.*": 0.25},
+    actuators=(ActuatorGroup("fingers", "ideal_pd", (".*_finger_.*",), stiffness=2.0, damping=0.1, effort_limit=1.0),)
+    + _G1_ACTUATORS,
 )
 
 

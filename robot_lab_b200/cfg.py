@@ -231,6 +231,10 @@ class TerrainCfg:
     sub_terrains: tuple[str, ...] = (
         "pyramid_stairs", "pyramid_stairs_inv", "boxes", "random_rough", "hf_pyramid_slope", "hf_pyramid_slope_inv",
     )
+    # SubTerrainBaseCfg.proportion of each entry above (ROUGH_TERRAINS_CFG [IL]); read by
+    # _get_terrain_column_range (V/mdp/utils.py:16-41)
+    proportions: tuple[float, ...] = (0.2, 0.2, 0.2, 0.2, 0.1, 0.1)
+    horizontal_scale: float = 0.1   # height-field vertex spacing [IL]
 
 
 @dataclass

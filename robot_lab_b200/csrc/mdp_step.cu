@@ -26,12 +26,7 @@
 // Built with -fmad=false on purpose: the reference is eager PyTorch, every op rounds on its own, and not
 // contracting a*b+c keeps threshold decisions (contact > 1 N, |cmd| > 0.1, ...) bit-identical.
 
-#include "rl_mdp_step.h"
-
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
+#include "rl_common.cuh"
 
 #include <new>
 #include <utility>
@@ -46,22 +41,9 @@ __constant__ RlStepSpec c_spec[RL_SPEC_SLOTS];
 
 namespace {
 
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
-  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
-  return code;
-}
-
-#define CUDA_TRY(expr)                                                                            \
-  do {                                                                                            \
-    cudaError_t _e = (expr);                                                                      \
-    if (_e != cudaSuccess) {                                                                      \
-      snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
-               __FILE__, __LINE__);                                                               \
-      return RL_ECUDA;                                                                            \
-    }                                                                                             \
-  } while (0)
+#define fail rl_fail
+#define g_err g_rl_err
+using DeviceGuard = RlDeviceGuard;
 
 // ---------------------------------------------------------------------------------------------------
 // Per-launch field descriptors
@@ -436,38 +418,6 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-
-// ---------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11) - counter-based, so noise needs no state and no bytes.
-// counter = (global env id, step lo, step hi, stream<<16 | block), key = seed.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
-
-enum { RL_STREAM_COMMAND = 1, RL_STREAM_RESET_COMMAND = 2, RL_STREAM_RESET_STATE = 3, RL_STREAM_RESET_JOINTS = 4, RL_STREAM_OBS = 16 };
-
-struct RandState {
-  unsigned long long seed, step;   // step already includes the device-side common step counter
-  long long env_id_offset;
-};
-__device__ __noinline__ uint4 rl_philox(const RandState r, long long env, uint32_t stream, uint32_t block) {
-  const unsigned long long genv = (unsigned long long)(env + r.env_id_offset);
-  uint4 ctr = make_uint4((uint32_t)genv, (uint32_t)r.step, (uint32_t)(r.step >> 32) ^ (uint32_t)(genv >> 32),
-                         (stream << 16) | block);
-  return philox4x32_10(ctr, make_uint2((uint32_t)r.seed, (uint32_t)(r.seed >> 32)));
-}
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -1726,10 +1676,8 @@ struct ResetStateArgs {
   const int32_t* n_env_ids;
   RlRandom rnd;
   const float* uniforms;   // [12 + 2J][N] or NULL
+  const uint8_t* pits;     // [N] is_env_assigned_to_terrain(env, "pits") or NULL
 };
-__device__ __forceinline__ void st_f(const RlField& f, long long env, int c, float v) {
-  static_cast<float*>(f.ptr)[env * f.env_stride + (long long)c * f.comp_stride] = v;
-}
 __global__ void reset_scene_state_kernel(const ResetStateArgs a) {
   const RlStepSpec& S = c_spec[a.slot];
   const int n = a.has_ids ? *a.n_env_ids : a.N;
@@ -1753,13 +1701,26 @@ __global__ void reset_scene_state_kernel(const ResetStateArgs a) {
       }
     }
     const RlResetStateCfg& c = a.cfg;
+    const float* org = static_cast<const float*>(a.origins.ptr);
+    if (a.pits != nullptr && a.pits[env]) {
+      // V/mdp/events.py:237-244: envs assigned to the "pits" sub-terrain get the default root state at their
+      // origin, zero velocity, no random perturbation (the joints are still reset by reset_joints_by_scale below)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float o = org ? org[env * a.origins.env_stride + (long long)q * a.origins.comp_stride] : 0.f;
+        st_f(a.pos, env, q, c.default_root_state[q] + o);
+        st_f(a.lin, env, q, 0.f);
+        st_f(a.ang, env, q, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_f(a.quat, env, q, c.default_root_state[3 + q]);
+    } else {
     float pose[6], vel[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) {   // sample_uniform [IL]: (hi - lo) * u + lo
       pose[q] = (c.pose_hi[q] - c.pose_lo[q]) * u[q] + c.pose_lo[q];
       vel[q] = (c.vel_hi[q] - c.vel_lo[q]) * u[6 + q] + c.vel_lo[q];
     }
-    const float* org = static_cast<const float*>(a.origins.ptr);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const float o = org ? org[env * a.origins.env_stride + (long long)q * a.origins.comp_stride] : 0.f;
@@ -1786,6 +1747,7 @@ __global__ void reset_scene_state_kernel(const ResetStateArgs a) {
     for (int q = 0; q < 3; ++q) {
       st_f(a.lin, env, q, c.default_root_state[7 + q] + vel[q]);
       st_f(a.ang, env, q, c.default_root_state[10 + q] + vel[3 + q]);
+    }
     }
     // reset_joints_by_scale [IL]
     const int J = S.num_joints;
@@ -1889,6 +1851,9 @@ struct RlCtx {
   long long* dbg;
   int baked;   // index into RL_BAKED_LIST when the spec equals a build-time specialised one, else -1
 };
+
+int rl_ctx_device_of(const RlCtx* ctx) { return ctx->device; }
+const RlStepSpec* rl_ctx_spec_of(const RlCtx* ctx) { return &ctx->spec; }
 
 namespace {
 
@@ -2108,16 +2073,6 @@ int ensure_scratch(RlCtx* ctx, int grid) {
   return RL_OK;
 }
 
-struct DeviceGuard {
-  int prev;
-  bool ok;
-  explicit DeviceGuard(int dev) : prev(-1), ok(true) {
-    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-  }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
 bool g_slots[16][RL_SPEC_SLOTS];
 
 }  // namespace
@@ -2133,6 +2088,7 @@ int64_t rl_struct_sizeof(const char* name) {
   RL_SZ(RlRewardTerm); RL_SZ(RlObsTerm); RL_SZ(RlObsGroup); RL_SZ(RlDoneTerm); RL_SZ(RlCommandCfg);
   RL_SZ(RlActionCfg); RL_SZ(RlStepSpec); RL_SZ(RlField); RL_SZ(RlStateView); RL_SZ(RlMdpState);
   RL_SZ(RlStepOut); RL_SZ(RlRandom); RL_SZ(RlResetLog); RL_SZ(RlResetStateCfg);
+  RL_SZ(RlActuatorCfg); RL_SZ(RlTerrainGrid); RL_SZ(RlHeightField);
 #undef RL_SZ
   return -1;
 }
@@ -2240,7 +2196,7 @@ int rl_ctx_set_pdl(RlCtx* ctx, int enabled) {
 int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cfg, const RlField* env_origins,
                          const RlStateView* state, const uint8_t* terminated, const uint8_t* truncated,
                          const int32_t* env_ids, const int32_t* n_env_ids, const RlRandom* rnd,
-                         const float* uniforms, void* stream) {
+                         const float* uniforms, const uint8_t* assigned_to_pits, void* stream) {
   if (!ctx || !cfg || !state || !rnd) return fail(RL_EINVAL, "rl_reset_scene_state: null argument%s", "");
   if (num_envs <= 0) return RL_OK;
   if (!state->root_pos_w.ptr || !state->root_quat_w.ptr || !state->root_lin_vel_w.ptr || !state->root_ang_vel_w.ptr)
@@ -2255,7 +2211,7 @@ int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cf
   a.pos = state->root_pos_w; a.quat = state->root_quat_w; a.lin = state->root_lin_vel_w; a.ang = state->root_ang_vel_w;
   a.jpos = state->joint_pos; a.jvel = state->joint_vel;
   a.terminated = terminated; a.truncated = truncated; a.env_ids = env_ids; a.n_env_ids = n_env_ids;
-  a.rnd = *rnd; a.uniforms = uniforms;
+  a.rnd = *rnd; a.uniforms = uniforms; a.pits = assigned_to_pits;
   DeviceGuard guard(ctx->device);
   const int threads = 128;
   const int blocks = (int)((num_envs + threads - 1) / threads);

@@ -1,0 +1,320 @@
+// scene_kernels.cu - the neighbours of the MDP step, hand-written for sm_100a, behind
+// the same C-ABI (include/rl_mdp_step.h):
+//
+//   rl_actuator_step         Articulation._apply_actuator_model [IL] with the IdealPD / Implicit / DCMotor models the
+//                            reference selects per robot (assets/unitree.py:55-63, 107-115, 504-575)
+//   rl_is_robot_on_terrain   is_robot_on_terrain (V/mdp/utils.py:73-127)
+//   rl_command_pit_restrict  tail of UniformThresholdVelocityCommand._update_command (V/mdp/commands.py:61-85)
+//   rl_height_scan_cast      grid-pattern RayCaster [IL] (V/velocity_env_cfg.py:70-77) over a height-field terrain
+//
+// All four are per-env maps over a few hundred bytes per env: HBM / L2 bound elementwise work, no tensor cores.
+// Index order follows the layout of the tensor being written so that SoA [C][N] and IsaacLab-shaped AoS [N][C]
+// tensors both coalesce. Built with -fmad=false like mdp_step.cu: the reference is eager PyTorch, every op rounds.
+
+#include "rl_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------------
+// Actuator models [IL] (isaaclab/actuators/actuator_pd.py): one thread per (env, joint).
+// ---------------------------------------------------------------------------------------------------
+struct ActuatorArgs {
+  int N, J;
+  RlField tgt, vtgt, etgt, jpos, jvel, applied, computed;
+  RlActuatorCfg cfg;
+};
+
+__global__ void __launch_bounds__(256) actuator_kernel(const __grid_constant__ ActuatorArgs a) {
+  const int total = a.N * a.J;   // < 2^31, checked by the host
+  const bool env_major = (a.applied.env_stride == 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int env, j;
+    if (env_major) { env = i % a.N; j = i / a.N; } else { j = i % a.J; env = i / a.J; }
+    const int type = a.cfg.type[j];
+    if (type == RL_ACT_NONE) continue;
+    const float q = ld_f(a.jpos, env, j), qd = ld_f(a.jvel, env, j);
+    const float pt = ld_f(a.tgt, env, j);
+    const float vt = a.vtgt.ptr ? ld_f(a.vtgt, env, j) : 0.f;
+    const float et = a.etgt.ptr ? ld_f(a.etgt, env, j) : 0.f;
+    // IdealPDActuator.compute [IL]: stiffness * error_pos + damping * error_vel + feed-forward effort
+    const float error_pos = pt - q, error_vel = vt - qd;
+    const float computed = (a.cfg.stiffness[j] * error_pos + a.cfg.damping[j] * error_vel) + et;
+    const float lim = a.cfg.effort_limit[j];
+    float lo = -lim, hi = lim;
+    if (type == RL_ACT_DC_MOTOR) {
+      // DCMotor._clip_effort [IL]: four-quadrant torque-speed curve
+      const float sat = a.cfg.saturation_effort[j], vlim = a.cfg.velocity_limit[j];
+      const float vel_at_effort_lim = vlim * (1.f + lim / sat);
+      const float vel = clampf(qd, -vel_at_effort_lim, vel_at_effort_lim);
+      const float top = sat * (1.f - vel / vlim);
+      const float bottom = sat * (-1.f - vel / vlim);
+      hi = fminf(top, lim);
+      lo = fmaxf(bottom, -lim);
+    }
+    const float applied = fminf(fmaxf(computed, lo), hi);   // torch.clip(x, min, max) = min(max(x, min), max)
+    if (a.computed.ptr) st_f(a.computed, env, j, computed);
+    st_f(a.applied, env, j, applied);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Terrain queries (V/mdp/utils.py:73-127) and the pit branch of the command term (V/mdp/commands.py:61-85).
+// One thread per env; the terrain origins (x, y of every grid cell) are staged in shared memory once per CTA, then
+// every thread scans them in flat row-major order with a strict "<" - the first minimum, like torch.argmin.
+// The distance is sqrt(dx^2 + dy^2) as torch.cdist defines it (the reference's matmul-based cdist path differs
+// from it only in rounding, i.e. for robots within ~1e-4 m of a cell boundary).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxTerrainCells = 4096;   // 32 KB of shared memory for (x, y)
+
+struct TerrainArgs {
+  int N;
+  RlField pos;
+  RlTerrainGrid grid;
+  // rl_is_robot_on_terrain
+  uint8_t* out;
+  // rl_command_pit_restrict
+  RlField cmd, head, ishead, isstand;
+  uint8_t* was_on_pit;
+  RlRandom rnd;
+  RlCommandCfg cc;
+};
+
+__device__ __forceinline__ void stage_origins(float* s_xy, const RlTerrainGrid& g) {
+  const int cells = g.num_rows * g.num_cols;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+    s_xy[2 * i] = g.terrain_origins[3 * i];
+    s_xy[2 * i + 1] = g.terrain_origins[3 * i + 1];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool on_terrain(const float* s_xy, const RlTerrainGrid& g, float x, float y) {
+  const int cells = g.num_rows * g.num_cols;
+  float best = INFINITY;
+  int arg = 0;
+#pragma unroll 4
+  for (int i = 0; i < cells; ++i) {
+    const float dx = x - s_xy[2 * i], dy = y - s_xy[2 * i + 1];
+    const float d = sqrtf(dx * dx + dy * dy);
+    if (d < best) { best = d; arg = i; }
+  }
+  const int col = arg % g.num_cols;
+  return (col >= g.col_start) && (col < g.col_end);
+}
+
+template <bool RESTRICT>
+__global__ void __launch_bounds__(128) terrain_kernel(const __grid_constant__ TerrainArgs a) {
+  extern __shared__ float s_xy[];
+  stage_origins(s_xy, a.grid);
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.N) return;
+  const bool on = on_terrain(s_xy, a.grid, ld_f(a.pos, env, 0), ld_f(a.pos, env, 1));
+  if constexpr (!RESTRICT) {
+    a.out[env] = on ? 1 : 0;
+  } else {
+    const bool was = a.was_on_pit[env] != 0;
+    const RlCommandCfg& cc = a.cc;
+    if (was && !on) {
+      // UniformVelocityCommand._resample_command [IL] + the small-command threshold (V/mdp/commands.py:43-47)
+      float u[RL_NUM_CMD_UNIFORMS];
+      if (a.rnd.cmd_uniforms != nullptr) {
+#pragma unroll
+        for (int i = 1; i < RL_NUM_CMD_UNIFORMS; ++i) u[i] = a.rnd.cmd_uniforms[(long long)i * a.N + env];
+      } else {
+        const RandState rs = rl_rand_state(a.rnd);
+        const uint4 r0 = rl_philox(rs, env, RL_STREAM_PIT_RESAMPLE, 0), r1 = rl_philox(rs, env, RL_STREAM_PIT_RESAMPLE, 1);
+        u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+        u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
+      }
+      float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
+      float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
+      const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
+      if (cc.heading_command) {
+        st_f(a.head, env, 0, u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo);
+        static_cast<uint8_t*>(a.ishead.ptr)[(long long)env * a.ishead.env_stride] = (u[5] <= cc.rel_heading_envs) ? 1 : 0;
+      }
+      static_cast<uint8_t*>(a.isstand.ptr)[(long long)env * a.isstand.env_stride] = (u[6] <= cc.rel_standing_envs) ? 1 : 0;
+      const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+      c0 *= keep; c1 *= keep;
+      st_f(a.cmd, env, 0, c0); st_f(a.cmd, env, 1, c1); st_f(a.cmd, env, 2, c2);
+    }
+    if (on) {
+      // forward only, 0.3 .. 0.6 m/s, no lateral / yaw command, heading target 0 (V/mdp/commands.py:72-82)
+      const float c0 = ld_f(a.cmd, env, 0);
+      st_f(a.cmd, env, 0, clampf(fabsf(c0), 0.3f, 0.6f));
+      st_f(a.cmd, env, 1, 0.f);
+      st_f(a.cmd, env, 2, 0.f);
+      if (cc.heading_command) st_f(a.head, env, 0, 0.f);
+    }
+    a.was_on_pit[env] = on ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Height-scan ray caster over a height field. One thread per (env, ray); the rays of an env are consecutive
+// threads, so the 3-4 vertex loads of neighbouring rays hit the same L1 lines and the hit row is written coalesced.
+// The height field (1200 x 2000 vertices = 9.6 MB for the default rough terrain) stays L2-resident.
+// isaaclab.utils.math [IL]: yaw_quat, quat_apply.
+// ---------------------------------------------------------------------------------------------------
+struct CastArgs {
+  int N;
+  RlHeightField hf;
+  RlField pos, quat, hits, sensor_z;
+};
+
+__global__ void __launch_bounds__(256) height_scan_kernel(const __grid_constant__ CastArgs a) {
+  const int R = a.hf.num_rays;
+  const long long total = (long long)a.N * R;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int env = (int)(i / R), r = (int)(i - (long long)env * R);
+    const float px = ld_f(a.pos, env, 0), py = ld_f(a.pos, env, 1);
+    const float qw = ld_f(a.quat, env, 0), qx = ld_f(a.quat, env, 1), qy = ld_f(a.quat, env, 2), qz = ld_f(a.quat, env, 3);
+    if (r == 0 && a.sensor_z.ptr) st_f(a.sensor_z, env, 0, ld_f(a.pos, env, 2));
+    // yaw_quat [IL]
+    const float yaw = atan2f(2.f * (qw * qz + qx * qy), 1.f - 2.f * (qy * qy + qz * qz));
+    float yw = cosf(yaw / 2.f), yz = sinf(yaw / 2.f);
+    const float nrm = fmaxf(sqrtf(yw * yw + yz * yz), 1e-9f);
+    yw = yw / nrm; yz = yz / nrm;
+    // quat_apply [IL] with xyz = (0, 0, yz): t = 2 * (xyz x v); v + w * t + xyz x t
+    const float vx = a.hf.ray_starts[3 * r], vy = a.hf.ray_starts[3 * r + 1];
+    const float tx = (0.f - yz * vy) * 2.f, ty = (yz * vx - 0.f) * 2.f;
+    const float cx = 0.f - yz * ty, cy = yz * tx - 0.f;
+    const float wx = ((vx + yw * tx) + cx) + px, wy = ((vy + yw * ty) + cy) + py;
+    // cell and triangle of the height-field mesh under (wx, wy)
+    const float gx = (wx - a.hf.x0) / a.hf.horizontal_scale, gy = (wy - a.hf.y0) / a.hf.horizontal_scale;
+    float z = INFINITY;
+    if (gx >= 0.f && gy >= 0.f && gx <= (float)(a.hf.num_x - 1) && gy <= (float)(a.hf.num_y - 1)) {
+      int ix = min((int)gx, a.hf.num_x - 2), iy = min((int)gy, a.hf.num_y - 2);
+      const float fx = gx - (float)ix, fy = gy - (float)iy;
+      const float* h = a.hf.heights + (long long)ix * a.hf.num_y + iy;
+      const float h00 = __ldg(h), h11 = __ldg(h + a.hf.num_y + 1);
+      if (fy >= fx) {   // triangle (v00, v11, v01)
+        const float h01 = __ldg(h + 1);
+        z = (h00 + fx * (h11 - h01)) + fy * (h01 - h00);
+      } else {          // triangle (v00, v10, v11)
+        const float h10 = __ldg(h + a.hf.num_y);
+        z = (h00 + fx * (h10 - h00)) + fy * (h11 - h10);
+      }
+    }
+    st_f(a.hits, env, r, z);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rl_actuator_step(RlCtx* ctx, int64_t num_envs, const RlActuatorCfg* cfg, const RlField* joint_pos_target,
+                     const RlField* joint_vel_target, const RlField* joint_effort_target, const RlStateView* state,
+                     const RlField* computed_torque, void* stream) {
+  if (!ctx || !cfg || !joint_pos_target || !state) return rl_fail(RL_EINVAL, "rl_actuator_step: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  const RlStepSpec* s = rl_ctx_spec_of(ctx);
+  if (cfg->num_joints != s->num_joints)
+    return rl_fail(RL_EINVAL, "rl_actuator_step: cfg has %s%lld joints, the context's spec %lld", "", cfg->num_joints, s->num_joints);
+  if (!joint_pos_target->ptr || !state->joint_pos.ptr || !state->joint_vel.ptr || !state->applied_torque.ptr)
+    return rl_fail(RL_EINVAL, "rl_actuator_step: joint_pos_target, joint_pos, joint_vel and applied_torque are required%s", "");
+  for (int j = 0; j < cfg->num_joints; ++j) {
+    const int t = cfg->type[j];
+    if (t < RL_ACT_NONE || t > RL_ACT_DC_MOTOR) return rl_fail(RL_EINVAL, "rl_actuator_step: joint %s%lld has an unknown actuator type", "", j);
+    if (t == RL_ACT_DC_MOTOR && !(cfg->saturation_effort[j] > 0.f && cfg->velocity_limit[j] > 0.f))
+      return rl_fail(RL_EINVAL, "rl_actuator_step: DC motor joint %s%lld needs positive saturation_effort and velocity_limit", "", j);
+  }
+  const long long total = num_envs * (long long)cfg->num_joints;
+  if (total >= (1ll << 31)) return rl_fail(RL_EINVAL, "rl_actuator_step: num_envs * num_joints must stay below 2^31%s", "");
+  ActuatorArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.J = cfg->num_joints;
+  a.tgt = *joint_pos_target;
+  if (joint_vel_target) a.vtgt = *joint_vel_target;
+  if (joint_effort_target) a.etgt = *joint_effort_target;
+  a.jpos = state->joint_pos; a.jvel = state->joint_vel; a.applied = state->applied_torque;
+  if (computed_torque) a.computed = *computed_torque;
+  a.cfg = *cfg;
+  RlDeviceGuard guard(rl_ctx_device_of(ctx));
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads);
+  actuator_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return RL_OK;
+}
+
+static int check_grid(const char* who, const RlTerrainGrid* g) {
+  if (!g->terrain_origins || g->num_rows <= 0 || g->num_cols <= 0)
+    return rl_fail(RL_EINVAL, "%s: terrain_origins with positive num_rows / num_cols required", who);
+  if ((long long)g->num_rows * g->num_cols > kMaxTerrainCells)
+    return rl_fail(RL_EUNSUPPORTED, "%s: more than %lld terrain cells", who, kMaxTerrainCells);
+  return RL_OK;
+}
+
+int rl_is_robot_on_terrain(RlCtx* ctx, int64_t num_envs, const RlField* root_pos_w, const RlTerrainGrid* grid,
+                           uint8_t* out, void* stream) {
+  if (!ctx || !root_pos_w || !grid || !out) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  if (!root_pos_w->ptr) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: root_pos_w required%s", "");
+  if (int rc = check_grid("rl_is_robot_on_terrain", grid)) return rc;
+  if (num_envs >= (1ll << 31)) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: too many envs%s", "");
+  TerrainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.pos = *root_pos_w; a.grid = *grid; a.out = out;
+  RlDeviceGuard guard(rl_ctx_device_of(ctx));
+  const int threads = 128;
+  const size_t smem = sizeof(float) * 2 * (size_t)grid->num_rows * grid->num_cols;
+  terrain_kernel<false><<<(int)((num_envs + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return RL_OK;
+}
+
+int rl_command_pit_restrict(RlCtx* ctx, int64_t num_envs, const RlField* root_pos_w, const RlTerrainGrid* grid,
+                            const RlMdpState* mdp, uint8_t* was_on_pit, const RlRandom* rnd, void* stream) {
+  if (!ctx || !root_pos_w || !grid || !mdp || !was_on_pit || !rnd)
+    return rl_fail(RL_EINVAL, "rl_command_pit_restrict: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  if (int rc = check_grid("rl_command_pit_restrict", grid)) return rc;
+  if (num_envs >= (1ll << 31)) return rl_fail(RL_EINVAL, "rl_command_pit_restrict: too many envs%s", "");
+  const RlStepSpec* s = rl_ctx_spec_of(ctx);
+  if (!root_pos_w->ptr || !mdp->command.ptr || !mdp->is_standing_env.ptr ||
+      (s->command.heading_command && (!mdp->heading_target.ptr || !mdp->is_heading_env.ptr)))
+    return rl_fail(RL_EINVAL, "rl_command_pit_restrict: root_pos_w and the command state fields are required%s", "");
+  TerrainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.pos = *root_pos_w; a.grid = *grid;
+  a.cmd = mdp->command; a.head = mdp->heading_target; a.ishead = mdp->is_heading_env; a.isstand = mdp->is_standing_env;
+  a.was_on_pit = was_on_pit; a.rnd = *rnd; a.cc = s->command;
+  RlDeviceGuard guard(rl_ctx_device_of(ctx));
+  const int threads = 128;
+  const size_t smem = sizeof(float) * 2 * (size_t)grid->num_rows * grid->num_cols;
+  terrain_kernel<true><<<(int)((num_envs + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return RL_OK;
+}
+
+int rl_height_scan_cast(RlCtx* ctx, int64_t num_envs, const RlHeightField* hf, const RlStateView* state, void* stream) {
+  if (!ctx || !hf || !state) return rl_fail(RL_EINVAL, "rl_height_scan_cast: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  const RlStepSpec* s = rl_ctx_spec_of(ctx);
+  if (hf->num_rays != s->num_rays) return rl_fail(RL_EINVAL, "rl_height_scan_cast: %s%lld rays, the context's spec has %lld", "", hf->num_rays, s->num_rays);
+  if (hf->num_rays <= 0) return RL_OK;
+  if (!hf->heights || !hf->ray_starts || hf->num_x < 2 || hf->num_y < 2 || !(hf->horizontal_scale > 0.f))
+    return rl_fail(RL_EINVAL, "rl_height_scan_cast: heights (>= 2 x 2), ray_starts and a positive horizontal_scale are required%s", "");
+  if (!state->root_pos_w.ptr || !state->root_quat_w.ptr || !state->ray_hits_z.ptr)
+    return rl_fail(RL_EINVAL, "rl_height_scan_cast: root_pos_w, root_quat_w and ray_hits_z are required%s", "");
+  CastArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs; a.hf = *hf;
+  a.pos = state->root_pos_w; a.quat = state->root_quat_w; a.hits = state->ray_hits_z; a.sensor_z = state->ray_sensor_pos_z;
+  RlDeviceGuard guard(rl_ctx_device_of(ctx));
+  const long long total = num_envs * (long long)hf->num_rays;
+  const int threads = 256;
+  const long long want = (total + threads - 1) / threads;
+  const int blocks = (int)(want < (1ll << 20) ? want : (1ll << 20));
+  height_scan_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return RL_OK;
+}
+
+}  // extern "C"

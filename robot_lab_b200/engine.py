@@ -68,9 +68,10 @@ class MdpStepEngine:
     def reset_scene_state(self, b: StateBuffers, cfg, env_origins: torch.Tensor | None = None,
                           env_ids: torch.Tensor | None = None, n_env_ids: torch.Tensor | None = None,
                           uniforms: torch.Tensor | None = None, seed: int = 0, step: int = 0, env_id_offset: int = 0,
-                          use_step_counter: bool = False) -> None:
+                          use_step_counter: bool = False, assigned_to_pits: torch.Tensor | None = None) -> None:
         """``reset_root_state_uniform`` (V/mdp/events.py:205-271) + ``reset_joints_by_scale`` [IL] for the env ids, or -
-        without ids - for the envs flagged by the last ``step_pre_reset``. ``cfg`` is a ``cfg.ResetStateCfg``."""
+        without ids - for the envs flagged by the last ``step_pre_reset``. ``cfg`` is a ``cfg.ResetStateCfg``;
+        ``assigned_to_pits`` (uint8 [N], ``terrain.is_env_assigned_to_terrain``) selects the pit branch (:232-244)."""
         c = nat.RlResetStateCfg()
         drs = [0.0, 0.0, self.spec.layout.asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6
         for i, v in enumerate(drs):
@@ -88,7 +89,62 @@ class MdpStepEngine:
         nat.check(self.lib.rl_reset_scene_state(
             self._ctx, b.N, C.byref(c), C.byref(org) if org is not None else None, C.byref(st),
             b.terminated.data_ptr(), b.truncated.data_ptr(), nat.ptr_of(env_ids), nat.ptr_of(n_env_ids), C.byref(rnd),
-            nat.ptr_of(uniforms), self._stream()))
+            nat.ptr_of(uniforms), nat.ptr_of(assigned_to_pits), self._stream()))
+
+    # ---- neighbours of the path -------------------------------------------------------
+    def actuator_cfg(self) -> nat.RlActuatorCfg:
+        """RlActuatorCfg of the task's robot (``RobotAsset.actuators``; assets/unitree.py:55-63, 107-115, 504-621)."""
+        if getattr(self, "_act_cfg", None) is None:
+            tab = self.spec.layout.asset.actuator_table()
+            c = nat.RlActuatorCfg()
+            c.num_joints = self.spec.J
+            for j in range(self.spec.J):
+                c.type[j] = nat.ACTUATOR_TYPES[tab["kind"][j]]
+                c.stiffness[j], c.damping[j] = tab["stiffness"][j], tab["damping"][j]
+                c.effort_limit[j], c.saturation_effort[j] = tab["effort_limit"][j], tab["saturation_effort"][j]
+                c.velocity_limit[j] = tab["velocity_limit"][j]
+            self._act_cfg = c
+        return self._act_cfg
+
+    def actuator_step(self, b: StateBuffers, computed_torque: torch.Tensor | None = None,
+                      joint_vel_target: torch.Tensor | None = None, joint_effort_target: torch.Tensor | None = None) -> None:
+        """Articulation._apply_actuator_model [IL] for one physics sub-step: reads ``joint_target`` (written by
+        ``process_action``), ``joint_pos``, ``joint_vel``; writes ``applied_torque`` (+ ``computed_torque`` [J, N] /
+        [N, J] in the buffers' layout when given)."""
+        tgt = b.field("joint_target")
+        st = b.state_view()
+        lay = b.layout
+        opt = lambda t: C.byref(nat.field_of(t, lay)) if t is not None else None  # noqa: E731
+        nat.check(self.lib.rl_actuator_step(self._ctx, b.N, C.byref(self.actuator_cfg()), C.byref(tgt),
+                                            opt(joint_vel_target), opt(joint_effort_target), C.byref(st),
+                                            opt(computed_torque), self._stream()))
+
+    def is_robot_on_terrain(self, b: StateBuffers, grid, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``is_robot_on_terrain`` (V/mdp/utils.py:73-127) -> uint8 [N]; ``grid`` is a ``terrain.TerrainGridBuffers``."""
+        if out is None:
+            out = torch.empty(b.N, dtype=torch.uint8, device=self.device)
+        pos = b.field("root_pos_w")
+        g = grid.to_ctypes()
+        nat.check(self.lib.rl_is_robot_on_terrain(self._ctx, b.N, C.byref(pos), C.byref(g), out.data_ptr(), self._stream()))
+        return out
+
+    def command_pit_restrict(self, b: StateBuffers, grid, was_on_pit: torch.Tensor, seed: int = 0, step: int = 0,
+                             env_id_offset: int = 0, use_random_inputs: bool = True, use_step_counter: bool = False) -> None:
+        """Tail of ``UniformThresholdVelocityCommand._update_command`` (V/mdp/commands.py:61-85): launch it between
+        ``step(RESET | COMMAND)`` and ``step(OBS)`` when the terrain has a "pits" sub-terrain."""
+        pos = b.field("root_pos_w")
+        g = grid.to_ctypes()
+        mdp = b.mdp_state()
+        rnd = b.random(seed, step, env_id_offset, use_random_inputs, use_step_counter)
+        nat.check(self.lib.rl_command_pit_restrict(self._ctx, b.N, C.byref(pos), C.byref(g), C.byref(mdp),
+                                                   was_on_pit.data_ptr(), C.byref(rnd), self._stream()))
+
+    def height_scan_cast(self, b: StateBuffers, hf) -> None:
+        """Grid-pattern RayCaster [IL] over a height field (``terrain.HeightFieldBuffers``): writes ``ray_hits_z`` and
+        ``ray_sensor_pos_z`` of the buffers from ``root_pos_w`` / ``root_quat_w``."""
+        st = b.state_view()
+        h = hf.to_ctypes()
+        nat.check(self.lib.rl_height_scan_cast(self._ctx, b.N, C.byref(h), C.byref(st), self._stream()))
 
     def contact_sensor_update(self, b: StateBuffers, net_forces_w: torch.Tensor, dt: float, force_threshold: float = 1.0,
                               ring_slot: int = -1) -> None:

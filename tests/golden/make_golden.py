@@ -43,7 +43,8 @@ def main():
             print(key, n, "envs,", sum(1 for k in arrays if k.startswith("reward/")), "reference-owned reward terms")
             continue
         for name, val in ref_harness.reference_command_compute(spec, st, st["cmd_uniforms"], ter).items():
-            arrays[f"command/{name}"] = val.numpy()
+            if name != "was_on_pit":   # all False without a "pits" sub-terrain; pit_terrain_*.npz covers that branch
+                arrays[f"command/{name}"] = val.numpy()
         obs = ref_harness.reference_observation_terms(spec, st)
         arrays["obs/phase"] = obs["phase"].numpy()
         arrays["obs/joint_pos_rel_without_wheel"] = obs["joint_pos_rel_without_wheel"].numpy()
@@ -72,7 +73,59 @@ def reset_event():
         print("reset_state", key, n, "envs,", len(ids), "reset")
 
 
+PIT_SUB_TERRAINS = ("pyramid_stairs", "pits", "boxes", "random_rough", "hf_pyramid_slope")
+PIT_PROPORTIONS = (0.2, 0.15, 0.25, 0.3, 0.1)
+
+
+def pits():
+    """pit_terrain_<task>.npz: a generator terrain WITH a "pits" sub-terrain (none of the reference's task configs
+    has one, so the golden vectors of main() never reach that code): the reference's is_robot_on_terrain /
+    is_env_assigned_to_terrain (V/mdp/utils.py:44-127), UniformThresholdVelocityCommand.compute() with the pit
+    branch of _update_command live (V/mdp/commands.py:61-85) and the pit branch of reset_root_state_uniform
+    (V/mdp/events.py:232-244)."""
+    from robot_lab_b200 import terrain as terrain_host
+    from robot_lab_b200.cfg import ResetStateCfg, TerrainCfg
+
+    out_dir = Path(__file__).resolve().parent
+    ter_cfg = TerrainCfg(sub_terrains=PIT_SUB_TERRAINS, proportions=PIT_PROPORTIONS)
+    for key, n in (("go2_rough", 512), ("g1_rough", 256)):
+        cfg, spec = H.make_spec(key)
+        st = make_state(spec, n, seed=SEED + 7)
+        g = torch.Generator().manual_seed(SEED + 8)
+        st["root_pos_w"] = torch.stack([(torch.rand(n, generator=g) - 0.5) * 70.0, (torch.rand(n, generator=g) - 0.5) * 150.0,
+                                        torch.rand(n, generator=g)], dim=1)
+        origins = terrain_host.grid_origins(ter_cfg)
+        origins[:, :, 2] = torch.rand(origins.shape[:2], generator=g)
+        types = torch.randint(0, ter_cfg.num_cols, (n,), generator=g)
+        was = torch.rand(n, generator=g) < 0.35
+        ter = ref_harness.fake_terrain(ter_cfg, "generator", n, origins, types)
+        keep = ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_w", "command", "heading_target", "time_left",
+                "is_heading_env", "is_standing_env", "metric_error_vel_xy", "metric_error_vel_yaw", "cmd_uniforms")
+        arrays = {f"in/{k}": st[k].numpy() for k in keep}   # everything the command term and the reset event read
+        arrays.update({"terrain_origins": origins.numpy(), "terrain_types": types.numpy(), "was_on_pit": was.numpy()})
+        ref = ref_harness.reference_command_compute(spec, st, st["cmd_uniforms"], "generator", terrain=ter, was_on_pit=was)
+        arrays.update({f"command/{k}": v.numpy() for k, v in ref.items()})
+        utils = ref_harness.reference_terrain_utils()
+        env = ref_harness.FakeEnv(spec, st)
+        env.scene.terrain = ter
+        for name in ("pits", "boxes"):
+            arrays[f"on_terrain/{name}"] = utils.is_robot_on_terrain(env, name).numpy()
+            arrays[f"assigned/{name}"] = utils.is_env_assigned_to_terrain(env, name).numpy()
+        uniforms = torch.rand(12 + 2 * spec.J, n, generator=g)
+        env_origins = torch.randn(n, 3, generator=g) * 20.0
+        ids = torch.randperm(n, generator=g)[: n // 3].sort().values.int()
+        rr = ref_harness.reference_reset_root_state(spec, st, ids, ResetStateCfg.go2_rough(), env_origins, uniforms, terrain=ter)
+        arrays.update({"reset/ids": ids.numpy(), "reset/uniforms": uniforms.numpy(), "reset/env_origins": env_origins.numpy()})
+        arrays.update({f"reset/out/{k}": v.numpy() for k, v in rr.items()})
+        np.savez_compressed(out_dir / f"pit_terrain_{key}.npz", **arrays)
+        print("pit_terrain", key, n, "envs,", int(ref["was_on_pit"].sum()), "on pits,", int((was & ~ref["was_on_pit"]).sum()), "left a pit")
+
+
 if __name__ == "__main__":
-    if "--reset-event-only" not in sys.argv:
-        main()
-    reset_event()
+    if "--pits-only" in sys.argv:
+        pits()
+    else:
+        if "--reset-event-only" not in sys.argv:
+            main()
+        reset_event()
+        pits()

@@ -37,6 +37,7 @@ def test_command_term_matches_reference_class(key, terrain):
     st = make_state(spec, 1024, seed=5)
     ref = ref_harness.reference_command_compute(spec, st, st["cmd_uniforms"], terrain)
     got = port.compute_command(spec, st, {"cmd_uniforms": st["cmd_uniforms"]})
+    assert not ref.pop("was_on_pit").any()   # no "pits" sub-terrain in the in-scope terrains (V/mdp/utils.py:27-28)
     for k, v in ref.items():
         assert torch.equal(got[k], v), k  # same op sequence -> bit-identical
 
