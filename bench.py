@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU baseline sample")
     p.add_argument("--skip-handoff", action="store_true")
+    p.add_argument("--no-neighbours", action="store_true", help="skip the side measurements of the SURVEY 8(f) kernels")
     return p.parse_args()
 
 
@@ -375,6 +376,11 @@ def main():
     roofline["other_kernel"] = kernels["post_reset" if dom == "pre_reset" else "pre_reset"]
     roofline["bytes_per_env_step_fused_accounting"] = spec.algorithmic_bytes_per_env_step()
 
+    # ---- the neighbours of the path: each kernel alone, same rotation over the state sets ----
+    neighbours = None
+    if rank == 0 and world == 1 and not args.no_neighbours:
+        neighbours = measure_neighbours(eng, spec, sets, N, time_kernel, peak, dev)
+
     # ---- the same step with an L2-resident working set (one state set, 14 MB): labelled separately ----
     l2_resident = None
     if use_graph and not args.no_e2e:
@@ -432,12 +438,55 @@ def main():
             },
             "gpu_launches": launches_per_step * K,
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "handoff": handoff,
-            "l2_resident": l2_resident,
+            "l2_resident": l2_resident, "neighbours": neighbours,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_neighbours(eng, spec, sets, N, time_kernel, peak, dev):
+    """Side measurements (not part of `value`): the SURVEY.md 8(f) kernels that run around the step in a simulator
+    loop - per physics sub-step the actuator model and the contact-sensor update, per env step the height scanner, per
+    env step on pit terrains the command restriction. bytes = per-env tensors read + written (the height field and the
+    terrain origins are shared, L2-resident tables)."""
+    from robot_lab_b200 import terrain as terrain_host
+    from robot_lab_b200.cfg import RayCasterCfg, TerrainCfg
+
+    out = {}
+
+    def add(name, fn, bytes_per_env, note):
+        us = time_kernel(fn)
+        gbs = bytes_per_env * N / (us * 1e-6) / 1e9
+        out[name] = {"kernel_us": us, "bytes_per_env": bytes_per_env, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+                     "note": note}
+
+    J, R, B, Bt, T = spec.J, spec.R, spec.B, spec.Bt, spec.T
+    add("rl_actuator_step", lambda b: eng.actuator_step(b), 4 * 4 * J,
+        "DCMotor: reads target, joint_pos, joint_vel, writes applied_torque; x decimation per env step")
+    forces = torch.randn(N, B, 3, device=dev)
+    add("rl_contact_sensor_update(ring)", lambda b: eng.contact_sensor_update(b, forces, 0.005, ring_slot=1),
+        4 * (3 * B + 3 * B + 6 * Bt), "reads net_forces_w, writes one history slot, read-modify-writes 4 timers")
+    if R > 0:
+        ter = TerrainCfg()
+        nx = int(round((ter.num_rows * ter.size[0] + 2 * ter.border_width) / ter.horizontal_scale)) + 1
+        ny = int(round((ter.num_cols * ter.size[1] + 2 * ter.border_width) / ter.horizontal_scale)) + 1
+        g = torch.Generator(device="cpu").manual_seed(7)
+        heights = (torch.rand(nx // 8 + 2, ny // 8 + 2, generator=g) * 0.8)
+        heights = torch.nn.functional.interpolate(heights[None, None], size=(nx, ny), mode="bilinear", align_corners=True)[0, 0]
+        hf = terrain_host.HeightFieldBuffers(heights.contiguous().to(dev), -0.5 * (nx - 1) * ter.horizontal_scale,
+                                             -0.5 * (ny - 1) * ter.horizontal_scale, ter.horizontal_scale,
+                                             terrain_host.grid_pattern_ray_starts(RayCasterCfg()).to(dev))
+        add("rl_height_scan_cast", lambda b: eng.height_scan_cast(b, hf), 4 * (7 + R + 1),
+            f"{R} vertical rays per env over a {nx} x {ny} height field ({nx * ny * 4 / 1e6:.1f} MB, L2-resident gathers)")
+    pit = TerrainCfg(sub_terrains=("pyramid_stairs", "pits", "boxes", "random_rough", "hf_pyramid_slope"),
+                     proportions=(0.2, 0.15, 0.25, 0.3, 0.1))
+    grid = terrain_host.TerrainGridBuffers.create(pit, "pits", dev)
+    was = torch.zeros(N, dtype=torch.uint8, device=dev)
+    add("rl_command_pit_restrict", lambda b: eng.command_pit_restrict(b, grid, was, seed=1, use_random_inputs=False),
+        4 * 2 + 2, "argmin over 200 terrain origins per env (shared memory) + command rewrite for pit envs")
+    return out
 
 
 def measure_e2e(eng, spec, sets, N, K, W, rank, world, dev, local_rank, one_step):

@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(128) terrain_kernel(const __grid_constant__ Te
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Height-scan ray caster over a height field. One thread per (env, ray); the rays of an env are consecutive
-// threads, so the 3-4 vertex loads of neighbouring rays hit the same L1 lines and the hit row is written coalesced.
-// The height field (1200 x 2000 vertices = 9.6 MB for the default rough terrain) stays L2-resident.
+// Height-scan ray caster over a height field. One warp per env: every lane evaluates the yaw rotation of its env once
+// (not once per ray), then the lanes stride over the env's rays - neighbouring rays read neighbouring vertices (same
+// L1 lines) and the hit row [R] is written coalesced. The height field (1201 x 2001 vertices = 9.6 MB for the default
+// rough terrain) stays L2-resident; 8 envs per CTA, grid = N / 8.
 // isaaclab.utils.math [IL]: yaw_quat, quat_apply.
 // ---------------------------------------------------------------------------------------------------
 struct CastArgs {
@@ -168,39 +169,41 @@ struct CastArgs {
 
 __global__ void __launch_bounds__(256) height_scan_kernel(const __grid_constant__ CastArgs a) {
   const int R = a.hf.num_rays;
-  const long long total = (long long)a.N * R;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int env = (int)(i / R), r = (int)(i - (long long)env * R);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; env < a.N; env += warps_per_grid) {
     const float px = ld_f(a.pos, env, 0), py = ld_f(a.pos, env, 1);
     const float qw = ld_f(a.quat, env, 0), qx = ld_f(a.quat, env, 1), qy = ld_f(a.quat, env, 2), qz = ld_f(a.quat, env, 3);
-    if (r == 0 && a.sensor_z.ptr) st_f(a.sensor_z, env, 0, ld_f(a.pos, env, 2));
+    if (lane == 0 && a.sensor_z.ptr) st_f(a.sensor_z, env, 0, ld_f(a.pos, env, 2));
     // yaw_quat [IL]
     const float yaw = atan2f(2.f * (qw * qz + qx * qy), 1.f - 2.f * (qy * qy + qz * qz));
     float yw = cosf(yaw / 2.f), yz = sinf(yaw / 2.f);
     const float nrm = fmaxf(sqrtf(yw * yw + yz * yz), 1e-9f);
     yw = yw / nrm; yz = yz / nrm;
-    // quat_apply [IL] with xyz = (0, 0, yz): t = 2 * (xyz x v); v + w * t + xyz x t
-    const float vx = a.hf.ray_starts[3 * r], vy = a.hf.ray_starts[3 * r + 1];
-    const float tx = (0.f - yz * vy) * 2.f, ty = (yz * vx - 0.f) * 2.f;
-    const float cx = 0.f - yz * ty, cy = yz * tx - 0.f;
-    const float wx = ((vx + yw * tx) + cx) + px, wy = ((vy + yw * ty) + cy) + py;
-    // cell and triangle of the height-field mesh under (wx, wy)
-    const float gx = (wx - a.hf.x0) / a.hf.horizontal_scale, gy = (wy - a.hf.y0) / a.hf.horizontal_scale;
-    float z = INFINITY;
-    if (gx >= 0.f && gy >= 0.f && gx <= (float)(a.hf.num_x - 1) && gy <= (float)(a.hf.num_y - 1)) {
-      int ix = min((int)gx, a.hf.num_x - 2), iy = min((int)gy, a.hf.num_y - 2);
-      const float fx = gx - (float)ix, fy = gy - (float)iy;
-      const float* h = a.hf.heights + (long long)ix * a.hf.num_y + iy;
-      const float h00 = __ldg(h), h11 = __ldg(h + a.hf.num_y + 1);
-      if (fy >= fx) {   // triangle (v00, v11, v01)
-        const float h01 = __ldg(h + 1);
-        z = (h00 + fx * (h11 - h01)) + fy * (h01 - h00);
-      } else {          // triangle (v00, v10, v11)
-        const float h10 = __ldg(h + a.hf.num_y);
-        z = (h00 + fx * (h10 - h00)) + fy * (h11 - h10);
+    for (int r = lane; r < R; r += 32) {
+      // quat_apply [IL] with xyz = (0, 0, yz): t = 2 * (xyz x v); v + w * t + xyz x t
+      const float vx = __ldg(a.hf.ray_starts + 3 * r), vy = __ldg(a.hf.ray_starts + 3 * r + 1);
+      const float tx = (0.f - yz * vy) * 2.f, ty = (yz * vx - 0.f) * 2.f;
+      const float cx = 0.f - yz * ty, cy = yz * tx - 0.f;
+      const float wx = ((vx + yw * tx) + cx) + px, wy = ((vy + yw * ty) + cy) + py;
+      // cell and triangle of the height-field mesh under (wx, wy)
+      const float gx = (wx - a.hf.x0) / a.hf.horizontal_scale, gy = (wy - a.hf.y0) / a.hf.horizontal_scale;
+      float z = INFINITY;
+      if (gx >= 0.f && gy >= 0.f && gx <= (float)(a.hf.num_x - 1) && gy <= (float)(a.hf.num_y - 1)) {
+        const int ix = min((int)gx, a.hf.num_x - 2), iy = min((int)gy, a.hf.num_y - 2);
+        const float fx = gx - (float)ix, fy = gy - (float)iy;
+        const float* h = a.hf.heights + (long long)ix * a.hf.num_y + iy;
+        const float h00 = __ldg(h), h11 = __ldg(h + a.hf.num_y + 1);
+        if (fy >= fx) {   // triangle (v00, v11, v01)
+          const float h01 = __ldg(h + 1);
+          z = (h00 + fx * (h11 - h01)) + fy * (h01 - h00);
+        } else {          // triangle (v00, v10, v11)
+          const float h10 = __ldg(h + a.hf.num_y);
+          z = (h00 + fx * (h10 - h00)) + fy * (h11 - h10);
+        }
       }
+      st_f(a.hits, env, r, z);
     }
-    st_f(a.hits, env, r, z);
   }
 }
 
@@ -308,9 +311,8 @@ int rl_height_scan_cast(RlCtx* ctx, int64_t num_envs, const RlHeightField* hf, c
   a.N = (int)num_envs; a.hf = *hf;
   a.pos = state->root_pos_w; a.quat = state->root_quat_w; a.hits = state->ray_hits_z; a.sensor_z = state->ray_sensor_pos_z;
   RlDeviceGuard guard(rl_ctx_device_of(ctx));
-  const long long total = num_envs * (long long)hf->num_rays;
-  const int threads = 256;
-  const long long want = (total + threads - 1) / threads;
+  const int threads = 256;   // 8 warps = 8 envs per CTA
+  const long long want = (num_envs + 7) / 8;
   const int blocks = (int)(want < (1ll << 20) ? want : (1ll << 20));
   height_scan_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
   CUDA_TRY(cudaGetLastError());

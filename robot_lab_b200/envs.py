@@ -103,6 +103,37 @@ class ResetEventStateProvider(SyntheticStateProvider):
                                      seed=env.seed, env_id_offset=env.rank * env.num_envs, use_step_counter=True)
 
 
+class SensorChainStateProvider(ResetEventStateProvider):
+    """Synthetic root / joint / contact-force state, with everything the library can derive from it computed on the
+    device in IsaacLab's order for every physics sub-step (``decimation`` of them, V/velocity_env_cfg.py:714):
+    ``rl_actuator_step`` (joint target -> applied torque), ``rl_contact_sensor_update`` (force
+    history + air / contact timers, row 1) and - once per env step, on the final pose - ``rl_height_scan_cast`` (the
+    height scanner over a height field, row 4). ``reset`` is ``rl_reset_scene_state`` (row 2)."""
+
+    def __init__(self, spec: StepSpec, num_envs: int, device, height_field=None, decimation: int = 4,
+                 physics_dt: float = 0.005, **kw):
+        super().__init__(spec, num_envs, device, **kw)
+        self.height_field, self.decimation, self.physics_dt = height_field, decimation, physics_dt
+        self.forces = [st["net_forces_w_history"][:, 0].contiguous().to(device) for st in self.sets]
+        derived = ("applied_torque", "net_forces_w_history", "current_air_time", "last_air_time", "current_contact_time",
+                   "last_contact_time") + (("ray_hits_z", "ray_sensor_pos_z") if height_field is not None else ())
+        for st in self.sets:
+            for k in derived:
+                st.pop(k, None)
+        self.substep = 0
+
+    def advance(self, env):
+        i = self.i % len(self.sets)
+        super().advance(env)
+        b, eng = env.buffers, env.engine
+        for _ in range(self.decimation):
+            eng.actuator_step(b)
+            eng.contact_sensor_update(b, self.forces[i], self.physics_dt, ring_slot=self.substep % env.spec.T)
+            self.substep += 1
+        if self.height_field is not None and env.spec.R > 0:
+            eng.height_scan_cast(b, self.height_field)
+
+
 class ReplayStateProvider(StateProvider):
     """Feeds a fixed list of logical state dicts, one per step (tests: the oracle replays the same list)."""
 
@@ -359,6 +390,14 @@ class ManagerBasedRLEnv:
         self.observation_space = {g.name: Box(-math.inf, math.inf, (self.num_envs, g.dim)) for g in self.spec.obs if g.dim > 0}
         self.single_action_space = Box(-math.inf, math.inf, (self.spec.A,))
         self.action_space = Box(-math.inf, math.inf, (self.num_envs, self.spec.A))
+        # terrain-aware command restriction (V/mdp/commands.py:61-85): only when the terrain has a "pits" sub-terrain
+        self.pit_grid = None
+        from . import terrain as _terrain
+
+        if _terrain.terrain_column_range(layout.terrain, "pits") is not None:
+            self.pit_grid = _terrain.TerrainGridBuffers.create(layout.terrain, "pits", self.device,
+                                                               origins=kwargs.get("terrain_origins"))
+            self.was_on_pit = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         self._all_ids = torch.arange(self.num_envs, dtype=torch.int32, device=self.device)
         self._n_all = torch.tensor([self.num_envs], dtype=torch.int32, device=self.device)
         self._closed = False
@@ -422,7 +461,13 @@ class ManagerBasedRLEnv:
         self.common_step_counter += 1
         eng.step_pre_reset(b, **self._rng_kwargs())                                  # 3-5: dones, rewards, reset ids
         self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
-        eng.step_post_reset(b, **self._rng_kwargs())                                 # 6b manager reset, 7 command, 9 obs
+        if self.pit_grid is None:
+            eng.step_post_reset(b, **self._rng_kwargs())                             # 6b manager reset, 7 command, 9 obs
+        else:   # the pit branch of _update_command sits between the command update and the observations
+            rng = self._rng_kwargs()
+            eng.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND, **rng)
+            eng.command_pit_restrict(b, self.pit_grid, self.was_on_pit, **rng)
+            eng.step(b, phases=nat.PHASE_OBS, **rng)
         self.extras = {"log": self._log()}
         return self._obs_dict(), b.reward, b.terminated.bool(), b.truncated.bool(), self.extras
 

@@ -112,3 +112,82 @@ def test_rsl_rl_wrapper_surface(native_lib):
     assert (act[~live] == 0.0).all()           # ActionManager.reset for the envs that were reset
     assert torch.equal(env.episode_length_buf[live], ep[live] + 1)
     env.close()
+
+
+def test_env_step_on_a_terrain_with_pits(native_lib):
+    """A terrain with a "pits" sub-terrain switches env.step() to command -> rl_command_pit_restrict -> observations
+    (V/mdp/commands.py:61-85): the restricted command is what the policy observes."""
+    from robot_lab_b200 import terrain as terrain_host
+    from robot_lab_b200.cfg import TerrainCfg
+    from robot_lab_b200.envs import ManagerBasedRLEnv, ReplayStateProvider
+    from robot_lab_b200.tasks import make_env_cfg
+
+    n = 1024
+    cfg = make_env_cfg(H.TASKS["go2_rough"], n)
+    cfg.sim.device = "cuda:0"
+    cfg.scene.terrain = TerrainCfg(sub_terrains=("pyramid_stairs", "pits", "boxes", "random_rough", "hf_pyramid_slope"),
+                                   proportions=(0.2, 0.15, 0.25, 0.3, 0.1))
+    _, spec = H.make_spec("go2_rough")
+    g = torch.Generator().manual_seed(8)
+    states = []
+    for i in range(4):
+        st = make_state(spec, n, seed=70 + i)
+        st["root_pos_w"] = torch.stack([(torch.rand(n, generator=g) - 0.5) * 70.0, (torch.rand(n, generator=g) - 0.5) * 110.0,
+                                        torch.rand(n, generator=g)], dim=1)   # inside the terrain: no out-of-bounds resets
+        states.append(st)
+    env = ManagerBasedRLEnv(cfg, state_provider=ReplayStateProvider(states))
+    assert env.pit_grid is not None and (env.pit_grid.col_start, env.pit_grid.col_end) == (4, 7)
+    env.reset()
+    origins = terrain_host.grid_origins(cfg.scene.terrain)
+    prev_on = None
+    for i in range(1, 4):
+        obs, rew, terminated, truncated, _ = env.step(torch.zeros(n, 12, device="cuda:0"))
+        torch.cuda.synchronize()
+        on = port.is_robot_on_terrain(states[i]["root_pos_w"], origins, (4, 7))
+        assert torch.equal(env.was_on_pit.cpu().bool(), on) and 50 < int(on.sum()) < n // 2
+        cmd = env.command_manager.get_command("base_velocity").cpu()
+        assert ((cmd[on, 0] >= 0.3) & (cmd[on, 0] <= 0.6)).all() and (cmd[on, 1:] == 0).all()
+        assert torch.equal(obs["policy"][:, 6:9].cpu(), cmd)      # generated_commands columns of the policy row
+        if prev_on is not None:
+            left = prev_on & ~on
+            assert int(left.sum()) > 10   # ... whose commands were resampled: not all of them forward-only any more
+            assert (cmd[left, 1] != 0).any()
+        prev_on = on
+    env.close()
+
+
+def test_sensor_chain_state_provider(native_lib):
+    """env.step() with every neighbour of the path computed on the device: actuator model, contact sensor, height
+    scanner, reset events."""
+    from robot_lab_b200 import terrain as terrain_host
+    from robot_lab_b200.cfg import RayCasterCfg
+    from robot_lab_b200.envs import ManagerBasedRLEnv, SensorChainStateProvider
+    from robot_lab_b200.tasks import make_env_cfg
+
+    n = 512
+    cfg = make_env_cfg(H.TASKS["go2_rough"], n)
+    cfg.sim.device = "cuda:0"
+    _, spec = H.make_spec("go2_rough")
+    nx = ny = 1400
+    g = torch.Generator().manual_seed(9)
+    heights = (torch.rand(nx, ny, generator=g) * 0.1).cuda()
+    hf = terrain_host.HeightFieldBuffers(heights, -70.0, -70.0, 0.1, terrain_host.grid_pattern_ray_starts(RayCasterCfg()).cuda())
+    prov = SensorChainStateProvider(spec, n, "cuda:0", height_field=hf, num_sets=2)
+    env = ManagerBasedRLEnv(cfg, state_provider=prov)
+    env.reset()
+    act = torch.randn(n, 12, device="cuda:0")
+    obs, rew, terminated, truncated, _ = env.step(act)
+    torch.cuda.synchronize()
+    b = env.buffers
+    tab = spec.layout.asset.actuator_table()
+    _, want = port.actuator_step(tab, b.logical("joint_target").cpu().contiguous(), b.logical("joint_pos").cpu().contiguous(),
+                                 b.logical("joint_vel").cpu().contiguous())
+    done = (terminated | truncated).cpu()
+    torch.testing.assert_close(b.logical("applied_torque").cpu().contiguous()[~done], want[~done], rtol=H.RTOL, atol=H.ATOL)
+    hits = b.logical("ray_hits_z").cpu()
+    inside = (b.logical("root_pos_w").cpu()[:, :2].abs() < 65.0).all(dim=1)
+    assert torch.isfinite(hits[inside]).all() and (hits[inside] >= 0).all() and (hits[inside] <= 0.1).all()
+    t = b.logical("current_air_time").cpu() + b.logical("current_contact_time").cpu()
+    assert (t > 0).all()      # four sub-steps of 5 ms were accumulated on one of the two timers of every foot
+    assert torch.isfinite(obs["critic"]).all() and torch.isfinite(rew).all()
+    env.close()
