@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 9
+#define RL_ABI_VERSION 10
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -219,11 +219,18 @@ typedef struct RlCommandCfg {
   float max_command_step;             /* resampling_time_hi / step_dt [IL] */
 } RlCommandCfg;
 
-/* JointPositionActionCfg: target = clamp(action * scale + offset, clip) on joints joint_ids[a]. */
+/* The action terms of the ActionManager [IL], concatenated in declaration order into one action vector:
+ * JointPositionActionCfg (V/velocity_env_cfg.py:124-126) and, for the wheeled robots, a second JointVelocityActionCfg
+ * term (e.g. V/config/wheeled/unitree_go2w/rough_env_cfg.py:22-32,101-106). Column a drives native joint joint_ids[a]:
+ * target = clamp(action * scale + offset, clip), written to the joint POSITION target (target_kind 0, offset =
+ * default joint position) or the joint VELOCITY target (target_kind 1, offset = default joint velocity). */
+enum RlActionTargetKind { RL_ACTION_JOINT_POSITION = 0, RL_ACTION_JOINT_VELOCITY = 1 };
+
 typedef struct RlActionCfg {
   int32_t n_actions;
   int32_t has_clip;
   uint8_t joint_ids[RL_MAX_JOINTS];
+  uint8_t target_kind[RL_MAX_JOINTS];
   float scale[RL_MAX_JOINTS];
   float offset[RL_MAX_JOINTS];
   float clip_lo[RL_MAX_JOINTS];
@@ -387,9 +394,11 @@ int rl_ctx_set_debug_buffer(RlCtx* ctx, void* device_i64_buffer);
  * 3 command), a (reward term / obs group), b (half / obs term), owner warp, lo, hi, first column, late}. */
 int rl_ctx_get_schedule(RlCtx* ctx, int32_t* out /* [RL_MAX_TASKS][8] */, int32_t* n_tasks);
 
-/* prev_action <- action; action <- new_action; joint_target[:, joint_ids[a]] = clamp(a*scale+offset). */
+/* prev_action <- action; action <- new_action; column a: target = clamp(a*scale+offset) written to
+ * joint_target[:, joint_ids[a]] (position columns) or joint_vel_target[:, joint_ids[a]] (velocity columns). */
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
                       const RlField* joint_target /* J, native order; columns not driven are untouched */,
+                      const RlField* joint_vel_target /* J; may be NULL when no column is a velocity column */,
                       uint64_t* step_counter /* device, may be NULL: incremented by 1 */, void* stream);
 
 /* Reset events of the reference (mode="reset", V/velocity_env_cfg.py:326-363): `reset_root_state_uniform`

@@ -14,7 +14,7 @@ from pathlib import Path
 
 import torch
 
-RL_ABI_VERSION = 9
+RL_ABI_VERSION = 10
 RL_MAX_TASKS = 112
 RL_DEBUG_STRIDE = 160
 RL_MAX_JOINTS = 64
@@ -98,7 +98,7 @@ class RlCommandCfg(C.Structure):
 class RlActionCfg(C.Structure):
     _fields_ = [
         ("n_actions", C.c_int32), ("has_clip", C.c_int32),
-        ("joint_ids", C.c_uint8 * RL_MAX_JOINTS),
+        ("joint_ids", C.c_uint8 * RL_MAX_JOINTS), ("target_kind", C.c_uint8 * RL_MAX_JOINTS),
         ("scale", C.c_float * RL_MAX_JOINTS), ("offset", C.c_float * RL_MAX_JOINTS),
         ("clip_lo", C.c_float * RL_MAX_JOINTS), ("clip_hi", C.c_float * RL_MAX_JOINTS),
     ]
@@ -262,7 +262,7 @@ def load() -> C.CDLL:
     lib.rl_contact_sensor_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlStateView),
                                              C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_int32, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),
-                                      C.POINTER(RlField), C.c_void_p, C.c_void_p]
+                                      C.POINTER(RlField), C.POINTER(RlField), C.c_void_p, C.c_void_p]
     lib.rl_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlStateView), C.POINTER(RlMdpState),
                             C.POINTER(RlStepOut), C.POINTER(RlRandom), C.c_uint32, C.c_void_p, C.c_void_p,
                             C.c_void_p]

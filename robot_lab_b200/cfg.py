@@ -216,6 +216,13 @@ class JointPositionActionCfg:
 
 
 @dataclass
+class JointVelocityActionCfg(JointPositionActionCfg):
+    """JointVelocityActionCfg [IL]: the second action term of the wheeled robots (e.g.
+    V/config/wheeled/unitree_go2w/rough_env_cfg.py:29-32, scale 5.0 at :102): same processing, the result is the joint
+    VELOCITY target and ``use_default_offset`` takes the default joint velocity."""
+
+
+@dataclass
 class TerrainCfg:
     """The part of TerrainImporterCfg / TerrainGeneratorCfg [IL] the MDP terms read.
 

@@ -1636,7 +1636,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 // process_action: ActionManager.process_action + JointAction.process_actions [IL]
 // ---------------------------------------------------------------------------------------------------
 __global__ void process_action_kernel(int N, int slot, RlField new_action, RlField action, RlField prev_action,
-                                      RlField target, unsigned long long* step_counter, int use_pdl) {
+                                      RlField target, RlField vel_target, unsigned long long* step_counter, int use_pdl) {
   if (use_pdl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1654,10 +1654,11 @@ __global__ void process_action_kernel(int N, int slot, RlField new_action, RlFie
     if (prev_action.ptr)
       static_cast<float*>(prev_action.ptr)[(long long)env * prev_action.env_stride + col * prev_action.comp_stride] = *ap;
     *ap = nv;
-    if (target.ptr) {
+    const RlField& dst = (ac.target_kind[col] == RL_ACTION_JOINT_VELOCITY) ? vel_target : target;
+    if (dst.ptr) {
       float v = nv * ac.scale[col] + ac.offset[col];
       if (ac.has_clip) v = clampf(v, ac.clip_lo[col], ac.clip_hi[col]);
-      static_cast<float*>(target.ptr)[(long long)env * target.env_stride + (long long)ac.joint_ids[col] * target.comp_stride] = v;
+      static_cast<float*>(dst.ptr)[(long long)env * dst.env_stride + (long long)ac.joint_ids[col] * dst.comp_stride] = v;
     }
   }
 }
@@ -2256,12 +2257,13 @@ int rl_contact_sensor_update(RlCtx* ctx, int64_t num_envs, const RlField* net_fo
 }
 
 int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, const RlMdpState* mdp,
-                      const RlField* joint_target, uint64_t* step_counter, void* stream) {
+                      const RlField* joint_target, const RlField* joint_vel_target, uint64_t* step_counter, void* stream) {
   if (!ctx || !new_action || !mdp) return fail(RL_EINVAL, "rl_process_action: null argument%s", "");
   if (num_envs <= 0) return RL_OK;
   if (!new_action->ptr || !mdp->action.ptr) return fail(RL_EINVAL, "rl_process_action: action pointers required%s", "");
   DeviceGuard guard(ctx->device);
   RlField tgt = joint_target ? *joint_target : RlField{nullptr, 0, 0};
+  RlField vtgt = joint_vel_target ? *joint_vel_target : RlField{nullptr, 0, 0};
   const long long total = num_envs * ctx->spec.action.n_actions;
   if (total >= (1ll << 31)) return fail(RL_EINVAL, "rl_process_action: num_envs * n_actions must stay below 2^31%s", "");
   const int threads = 256;
@@ -2275,7 +2277,7 @@ int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, process_action_kernel, (int)num_envs, ctx->slot, *new_action, mdp->action,
-                              mdp->prev_action, tgt, (unsigned long long*)step_counter, ctx->use_pdl));
+                              mdp->prev_action, tgt, vtgt, (unsigned long long*)step_counter, ctx->use_pdl));
   return RL_OK;
 }
 

@@ -115,9 +115,11 @@ class MdpStepEngine:
         st = b.state_view()
         lay = b.layout
         opt = lambda t: C.byref(nat.field_of(t, lay)) if t is not None else None  # noqa: E731
-        nat.check(self.lib.rl_actuator_step(self._ctx, b.N, C.byref(self.actuator_cfg()), C.byref(tgt),
-                                            opt(joint_vel_target), opt(joint_effort_target), C.byref(st),
-                                            opt(computed_torque), self._stream()))
+        vt = opt(joint_vel_target)
+        if vt is None and self.spec.action.kind is not None and any(self.spec.action.kind):
+            vt = C.byref(b.field("joint_vel_target"))   # the velocity columns of the action (wheels)
+        nat.check(self.lib.rl_actuator_step(self._ctx, b.N, C.byref(self.actuator_cfg()), C.byref(tgt), vt,
+                                            opt(joint_effort_target), C.byref(st), opt(computed_torque), self._stream()))
 
     def is_robot_on_terrain(self, b: StateBuffers, grid, out: torch.Tensor | None = None) -> torch.Tensor:
         """``is_robot_on_terrain`` (V/mdp/utils.py:73-127) -> uint8 [N]; ``grid`` is a ``terrain.TerrainGridBuffers``."""
@@ -164,8 +166,11 @@ class MdpStepEngine:
         na = b.field("new_action")
         mdp = b.mdp_state()
         tgt = b.field("joint_target") if with_target else nat.RlField(None, 0, 0)
+        has_vel = with_target and self.spec.action.kind is not None and any(self.spec.action.kind)
+        vtgt = b.field("joint_vel_target") if has_vel else nat.RlField(None, 0, 0)
         ctr = b.step_counter.data_ptr() if advance_step_counter else None
-        nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), ctr, self._stream()))
+        nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), C.byref(vtgt), ctr,
+                                             self._stream()))
 
     def step(self, b: StateBuffers, phases: int = nat.PHASE_ALL, seed: int = 0, step: int = 0, env_id_offset: int = 0,
              use_random_inputs: bool = True, env_ids: torch.Tensor | None = None,

@@ -17,6 +17,7 @@ from . import _native as nat
 from .assets import RobotAsset
 from .cfg import (
     JointPositionActionCfg,
+    JointVelocityActionCfg,
     ObservationGroupCfg,
     ObservationTermCfg,
     RewardTermCfg,
@@ -124,6 +125,7 @@ class ActionSpec:
     scale: list[float]
     offset: list[float]
     clip: list[tuple[float, float]] | None
+    kind: list[int] | None = None   # per column: 0 joint position target, 1 joint velocity target (None = all 0)
 
 
 @dataclass
@@ -269,6 +271,7 @@ class StepSpec:
         ac.has_clip = int(act.clip is not None)
         for a in range(self.A):
             ac.joint_ids[a] = act.joint_ids[a]
+            ac.target_kind[a] = act.kind[a] if act.kind is not None else 0
             ac.scale[a] = act.scale[a]
             ac.offset[a] = act.offset[a]
             lo, hi = act.clip[a] if act.clip is not None else (-math.inf, math.inf)
@@ -577,8 +580,9 @@ def compile_action(cfg: JointPositionActionCfg, asset: RobotAsset) -> ActionSpec
             scale[i] = float(v)
     else:
         scale = [float(cfg.scale)] * n
+    is_vel = isinstance(cfg, JointVelocityActionCfg)
     if cfg.use_default_offset:
-        dj = asset.default_joint_pos()
+        dj = asset.default_joint_vel() if is_vel else asset.default_joint_pos()
         offset = [dj[j] for j in ids]
     elif isinstance(cfg.offset, dict):
         offset = [0.0] * n
@@ -593,7 +597,23 @@ def compile_action(cfg: JointPositionActionCfg, asset: RobotAsset) -> ActionSpec
         idx, _, vals = resolve_matching_names_values(cfg.clip, names)
         for i, v in zip(idx, vals):
             clip[i] = (float(v[0]), float(v[1]))
-    return ActionSpec(joint_ids=ids, joint_names=names, scale=scale, offset=offset, clip=clip)
+    return ActionSpec(joint_ids=ids, joint_names=names, scale=scale, offset=offset, clip=clip, kind=[int(is_vel)] * n)
+
+
+def compile_actions(actions_cfg: Any, asset: RobotAsset) -> ActionSpec:
+    """ActionManager [IL]: the active action terms in declaration order, concatenated into one action vector."""
+    terms = [compile_action(c, asset) for _n, c in actions_cfg.active(JointPositionActionCfg)]
+    if not terms:
+        raise ValueError("no action term")
+    any_clip = any(t.clip is not None for t in terms)
+    clip = None
+    if any_clip:
+        clip = []
+        for t in terms:
+            clip += t.clip if t.clip is not None else [(-math.inf, math.inf)] * len(t.joint_ids)
+    return ActionSpec(joint_ids=sum((t.joint_ids for t in terms), []), joint_names=sum((t.joint_names for t in terms), []),
+                      scale=sum((t.scale for t in terms), []), offset=sum((t.offset for t in terms), []), clip=clip,
+                      kind=sum((t.kind for t in terms), []))
 
 
 def compile_command(cfg: UniformThresholdVelocityCommandCfg, step_dt: float) -> CommandSpec:
@@ -619,7 +639,7 @@ def compile_step_spec(env_cfg: Any, layout: SceneLayout | None = None) -> StepSp
         layout = env_cfg.scene.make_layout()
     asset = layout.asset
     step_dt = env_cfg.sim.dt * env_cfg.decimation
-    action = compile_action(env_cfg.actions.joint_pos, asset)
+    action = compile_actions(env_cfg.actions, asset)
     rewards = [compile_reward_term(n, c, layout) for n, c in env_cfg.rewards.active(RewardTermCfg)]
     dones = [compile_done_term(n, c, layout) for n, c in env_cfg.terminations.active(TerminationTermCfg)]
     groups = []

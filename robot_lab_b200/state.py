@@ -43,7 +43,8 @@ MDP_FIELDS = {
     "metric_error_vel_yaw": (lambda s: 1, _F32, "soa"), "episode_length": (lambda s: 1, _I32, "soa"),
     "episode_sums": (lambda s: s.K, _F32, "soa"),
     "action": (lambda s: s.A, _F32, "aos"), "prev_action": (lambda s: s.A, _F32, "aos"),
-    "joint_target": (lambda s: s.J, _F32, "soa"), "step_reward": (lambda s: s.K, _F32, "soa"),
+    "joint_target": (lambda s: s.J, _F32, "soa"), "joint_vel_target": (lambda s: s.J, _F32, "soa"),
+    "step_reward": (lambda s: s.K, _F32, "soa"),
 }
 
 

@@ -250,7 +250,7 @@ def test_empty_inputs_and_bad_arguments(native_lib):
     stream = torch.cuda.current_stream().cuda_stream
     assert lib.rl_step(eng._ctx, 0, C.byref(st), C.byref(mdp), C.byref(out), C.byref(rnd), nat.PHASE_ALL, None, None, stream) == 0
     na = b.field("new_action")
-    assert lib.rl_process_action(eng._ctx, 0, C.byref(na), C.byref(mdp), None, None, stream) == 0
+    assert lib.rl_process_action(eng._ctx, 0, C.byref(na), C.byref(mdp), None, None, None, stream) == 0
     # COMPACT without DONES, RESET together with REWARDS, RESET without the masks it needs, a missing observation input
     for phases in (nat.PHASE_COMPACT, nat.PHASE_RESET | nat.PHASE_REWARDS):
         with pytest.raises(nat.NativeError):
@@ -267,4 +267,39 @@ def test_empty_inputs_and_bad_arguments(native_lib):
     torch.cuda.synchronize()
     eng.step(b)   # the context is still usable afterwards
     torch.cuda.synchronize()
+    eng.close()
+
+
+def test_two_action_terms_position_and_velocity_targets(native_lib):
+    """JointPositionAction + JointVelocityAction in one action vector (the wheeled robots' ActionsCfg,
+    V/config/wheeled/unitree_go2w/rough_env_cfg.py:22-32): position columns land in joint_target, velocity columns in
+    joint_vel_target, the stored action / last_action observation carry all of them."""
+    from test_spec_compile import _two_term_action_cfg
+
+    from robot_lab_b200.spec import compact_layout, compile_step_spec
+
+    cfg, legs, wheels = _two_term_action_cfg()
+    spec = compile_step_spec(cfg, compact_layout(cfg))
+    n = 700
+    st = make_state(spec, n)
+    eng = _engine(spec)
+    b = eng.new_buffers(n)
+    b.load_logical(st)
+    b.t["joint_target"].fill_(-7.0)
+    b.t["joint_vel_target"].fill_(-9.0)
+    eng.process_action(b)
+    torch.cuda.synchronize()
+    action, prev, processed = port.process_action(spec, st, st["new_action"])
+    assert torch.equal(b.logical("action").cpu(), action) and torch.equal(b.logical("prev_action").cpu(), prev)
+    pos_ids, vel_ids = spec.action.joint_ids[:8], spec.action.joint_ids[8:]
+    jt, jv = b.logical("joint_target").cpu(), b.logical("joint_vel_target").cpu()
+    torch.testing.assert_close(jt[:, pos_ids], processed[:, :8], rtol=H.RTOL, atol=H.ATOL)
+    torch.testing.assert_close(jv[:, vel_ids], processed[:, 8:], rtol=H.RTOL, atol=H.ATOL)
+    assert (jt[:, vel_ids] == -7.0).all() and (jv[:, pos_ids] == -9.0).all()     # columns not driven are untouched
+    # the full step (generic kernel: this spec is not one of the baked ones) against the oracle
+    st2 = dict(st)
+    st2["action"], st2["prev_action"] = action, prev
+    eng.step(b)
+    torch.cuda.synchronize()
+    H.compare_outputs(H.gpu_step_outputs(b), H.oracle_step(spec, st2))
     eng.close()

@@ -125,3 +125,38 @@ def test_per_launch_byte_accounting():
     # figure by those re-reads plus command state the fused accounting keeps on chip, minus the joint target /
     # stored action that process_action owns
     assert 3423 < pre + post < 3423 + 4 * (13 + 2 * spec.J + 3 + 20)
+
+
+def _two_term_action_cfg():
+    """Go2 with the calf joints driven like the wheels of the wheeled robots: a JointPositionAction term for hips and
+    thighs and a JointVelocityAction term for the rest (V/config/wheeled/unitree_go2w/rough_env_cfg.py:22-32,101-106)."""
+    from robot_lab_b200.cfg import JointPositionActionCfg, JointVelocityActionCfg
+    from robot_lab_b200.tasks import make_env_cfg
+
+    cfg = make_env_cfg(H.TASKS["go2_rough"])
+    legs = [f"{leg}_{part}_joint" for leg in ("FR", "FL", "RR", "RL") for part in ("hip", "thigh")]
+    wheels = [f"{leg}_calf_joint" for leg in ("FR", "FL", "RR", "RL")]
+    cfg.actions.joint_pos = JointPositionActionCfg(joint_names=legs, scale={".*_hip_joint": 0.125, "^(?!.*_hip_joint).*": 0.25},
+                                                   use_default_offset=True, clip={".*": (-100.0, 100.0)}, preserve_order=True)
+    cfg.actions.joint_vel = JointVelocityActionCfg(joint_names=wheels, scale=5.0, use_default_offset=True,
+                                                   clip={".*": (-100.0, 100.0)}, preserve_order=True)
+    return cfg, legs, wheels
+
+
+def test_two_action_terms_concatenate_in_declaration_order():
+    from robot_lab_b200.spec import compact_layout, compile_step_spec
+
+    cfg, legs, wheels = _two_term_action_cfg()
+    spec = compile_step_spec(cfg, compact_layout(cfg))
+    a = spec.action
+    assert spec.A == 12 and a.joint_names == legs + wheels
+    assert a.kind == [0] * 8 + [1] * 4
+    names = list(spec.layout.asset.joint_names)
+    assert a.joint_ids == [names.index(n) for n in legs + wheels]
+    assert a.scale[:2] == [0.125, 0.25] and a.scale[8:] == [5.0] * 4
+    dj = spec.layout.asset.default_joint_pos()
+    assert a.offset[:8] == [dj[j] for j in a.joint_ids[:8]] and a.offset[8:] == [0.0] * 4   # default joint velocity
+    c = spec.to_ctypes().action
+    assert list(c.target_kind[:12]) == a.kind and c.n_actions == 12
+    # last_action / action_rate_l2 see the full 12-wide action vector
+    assert spec.obs[0].terms[-1].type_name == "last_action" and spec.obs[0].terms[-1].dim == 12
