@@ -498,10 +498,43 @@ def measure_e2e(eng, spec, sets, N, K, W, rank, world, dev, local_rank, one_step
     ring = min(4, len(sets))
     dsets = sets[:ring]
     in_bytes, out_bytes = dsets[0].inputs.nbytes, dsets[0].outputs.nbytes
+    # first-touch the pinned staging buffers on the NUMA node the GPU hangs off (a remote node costs up to 40 % of
+    # the PCIe rate on a two-socket host); the affinity is restored right after the allocation
+    numa = None
+    old_aff = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        props = torch.cuda.get_device_properties(dev)
+        if all(hasattr(props, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{int(props.pci_domain_id):04x}:{int(props.pci_bus_id):02x}:{int(props.pci_device_id):02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+            if len(bdf.split(":")[0]) == 8:
+                bdf = bdf[4:]
+        cpus = Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text().strip()
+        want = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            want.update(range(int(lo), int(hi or lo) + 1))
+        want &= old_aff
+        if want:
+            os.sched_setaffinity(0, want)
+            numa = f"pinned buffers first-touched on the GPU-local CPUs ({cpus})"
+    except Exception as e:   # not fatal: the buffers land wherever the allocator puts them
+        numa = f"no NUMA placement ({type(e).__name__})"
     host_in = [torch.empty(in_bytes, dtype=torch.uint8).pin_memory() for _ in range(ring)]
     host_out = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(ring)]
     for h, b in zip(host_in, dsets):
         h.copy_(b.inputs.buf[:in_bytes].cpu())
+    for h in host_out:
+        h.zero_()
+    if old_aff is not None:
+        try:
+            os.sched_setaffinity(0, old_aff)
+        except Exception:
+            pass
     s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
     ev_in = [torch.cuda.Event() for _ in range(ring)]
     ev_cmp = [torch.cuda.Event() for _ in range(ring)]
@@ -557,7 +590,7 @@ def measure_e2e(eng, spec, sets, N, K, W, rank, world, dev, local_rank, one_step
         ms = float(t.item())
     return {"value": world * N * steps / (ms * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": dsets[0].input_bytes(), "d2h_bytes_per_step": dsets[0].output_bytes(),
-            "steps": steps, "ms_per_step": ms / steps,
+            "steps": steps, "ms_per_step": ms / steps, "numa": numa,
             "path": "pinned host buffers -> 1 H2D -> rl_process_action + 2 x rl_step (C-ABI calls captured once, replayed as a CUDA graph) -> 1 D2H per step, 3-stream pipeline over a ring of 4 device sets"}
 
 

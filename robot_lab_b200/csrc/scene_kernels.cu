@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) actuator_kernel(const __grid_constant__ A
 
 // ---------------------------------------------------------------------------------------------------
 // Terrain queries (V/mdp/utils.py:73-127) and the pit branch of the command term (V/mdp/commands.py:61-85).
-// One thread per env; the terrain origins (x, y of every grid cell) are staged in shared memory once per CTA, then
-// every thread scans them in flat row-major order with a strict "<" - the first minimum, like torch.argmin.
+// The terrain origins (x, y of every grid cell) are staged in shared memory once per CTA; a group of 8 lanes scans
+// them for one env and reduces to the first minimum in flat row-major order, like torch.argmin.
 // The distance is sqrt(dx^2 + dy^2) as torch.cdist defines it (the reference's matmul-based cdist path differs
 // from it only in rounding, i.e. for robots within ~1e-4 m of a cell boundary).
 // ---------------------------------------------------------------------------------------------------
@@ -92,16 +92,32 @@ __device__ __forceinline__ void stage_origins(float* s_xy, const RlTerrainGrid& 
   __syncthreads();
 }
 
-__device__ __forceinline__ bool on_terrain(const float* s_xy, const RlTerrainGrid& g, float x, float y) {
+// kLanesPerEnv lanes share one env: lane l scans cells l, l + kLanesPerEnv, ... and keeps ITS first minimum; the
+// group then reduces to the smallest distance, ties to the smallest flat index - exactly the first minimum of the
+// whole scan. sqrt is monotone, so a cell whose squared distance is not below the running best cannot win: the IEEE
+// square root is only taken for the few candidates that pass that filter (a smaller squared distance can still round
+// to the same distance - then the earlier index stays, as in torch.argmin over the rounded distances).
+constexpr int kLanesPerEnv = 8;
+
+__device__ __forceinline__ bool on_terrain(const float* s_xy, const RlTerrainGrid& g, float x, float y, int sub) {
   const int cells = g.num_rows * g.num_cols;
-  float best = INFINITY;
-  int arg = 0;
-#pragma unroll 4
-  for (int i = 0; i < cells; ++i) {
+  float best = INFINITY, best2 = INFINITY;
+  int arg = 0x7fffffff;
+  for (int i = sub; i < cells; i += kLanesPerEnv) {
     const float dx = x - s_xy[2 * i], dy = y - s_xy[2 * i + 1];
-    const float d = sqrtf(dx * dx + dy * dy);
-    if (d < best) { best = d; arg = i; }
+    const float d2 = dx * dx + dy * dy;
+    if (d2 < best2) {
+      const float d = sqrtf(d2);
+      if (d < best) { best = d; best2 = d2; arg = i; }
+    }
   }
+#pragma unroll
+  for (int off = 1; off < kLanesPerEnv; off <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (arg == 0x7fffffff) arg = 0;   // nothing compared below +inf (NaN position): torch.argmin returns index 0
   const int col = arg % g.num_cols;
   return (col >= g.col_start) && (col < g.col_end);
 }
@@ -110,9 +126,12 @@ template <bool RESTRICT>
 __global__ void __launch_bounds__(128) terrain_kernel(const __grid_constant__ TerrainArgs a) {
   extern __shared__ float s_xy[];
   stage_origins(s_xy, a.grid);
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= a.N) return;
-  const bool on = on_terrain(s_xy, a.grid, ld_f(a.pos, env, 0), ld_f(a.pos, env, 1));
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = gid % kLanesPerEnv;
+  const int env_raw = gid / kLanesPerEnv;
+  const int env = min(env_raw, a.N - 1);       // whole lane groups stay converged for the shuffles
+  const bool on = on_terrain(s_xy, a.grid, ld_f(a.pos, env, 0), ld_f(a.pos, env, 1), sub);
+  if (env_raw >= a.N || sub != 0) return;
   if constexpr (!RESTRICT) {
     a.out[env] = on ? 1 : 0;
   } else {
@@ -180,29 +199,37 @@ __global__ void __launch_bounds__(256) height_scan_kernel(const __grid_constant_
     float yw = cosf(yaw / 2.f), yz = sinf(yaw / 2.f);
     const float nrm = fmaxf(sqrtf(yw * yw + yz * yz), 1e-9f);
     yw = yw / nrm; yz = yz / nrm;
-    for (int r = lane; r < R; r += 32) {
-      // quat_apply [IL] with xyz = (0, 0, yz): t = 2 * (xyz x v); v + w * t + xyz x t
-      const float vx = __ldg(a.hf.ray_starts + 3 * r), vy = __ldg(a.hf.ray_starts + 3 * r + 1);
-      const float tx = (0.f - yz * vy) * 2.f, ty = (yz * vx - 0.f) * 2.f;
-      const float cx = 0.f - yz * ty, cy = yz * tx - 0.f;
-      const float wx = ((vx + yw * tx) + cx) + px, wy = ((vy + yw * ty) + cy) + py;
-      // cell and triangle of the height-field mesh under (wx, wy)
-      const float gx = (wx - a.hf.x0) / a.hf.horizontal_scale, gy = (wy - a.hf.y0) / a.hf.horizontal_scale;
-      float z = INFINITY;
-      if (gx >= 0.f && gy >= 0.f && gx <= (float)(a.hf.num_x - 1) && gy <= (float)(a.hf.num_y - 1)) {
-        const int ix = min((int)gx, a.hf.num_x - 2), iy = min((int)gy, a.hf.num_y - 2);
-        const float fx = gx - (float)ix, fy = gy - (float)iy;
+    // batches of kRaysPerLane rays per lane: all vertex loads of a batch are issued before the first interpolation,
+    // so the L2 round trips of the batch overlap instead of queueing behind each other (187 rays = one batch)
+    constexpr int kRaysPerLane = 6;
+    for (int base = 0; base < R; base += 32 * kRaysPerLane) {
+      float fx[kRaysPerLane], fy[kRaysPerLane], h00[kRaysPerLane], h01[kRaysPerLane], h10[kRaysPerLane], h11[kRaysPerLane];
+      bool inside[kRaysPerLane];
+#pragma unroll
+      for (int k = 0; k < kRaysPerLane; ++k) {
+        const int r = min(base + k * 32 + lane, R - 1);
+        // quat_apply [IL] with xyz = (0, 0, yz): t = 2 * (xyz x v); v + w * t + xyz x t
+        const float vx = __ldg(a.hf.ray_starts + 3 * r), vy = __ldg(a.hf.ray_starts + 3 * r + 1);
+        const float tx = (0.f - yz * vy) * 2.f, ty = (yz * vx - 0.f) * 2.f;
+        const float cx = 0.f - yz * ty, cy = yz * tx - 0.f;
+        const float wx = ((vx + yw * tx) + cx) + px, wy = ((vy + yw * ty) + cy) + py;
+        // cell of the height-field mesh under (wx, wy)
+        const float gx = (wx - a.hf.x0) / a.hf.horizontal_scale, gy = (wy - a.hf.y0) / a.hf.horizontal_scale;
+        inside[k] = gx >= 0.f && gy >= 0.f && gx <= (float)(a.hf.num_x - 1) && gy <= (float)(a.hf.num_y - 1);
+        const int ix = inside[k] ? min((int)gx, a.hf.num_x - 2) : 0, iy = inside[k] ? min((int)gy, a.hf.num_y - 2) : 0;
+        fx[k] = gx - (float)ix; fy[k] = gy - (float)iy;
         const float* h = a.hf.heights + (long long)ix * a.hf.num_y + iy;
-        const float h00 = __ldg(h), h11 = __ldg(h + a.hf.num_y + 1);
-        if (fy >= fx) {   // triangle (v00, v11, v01)
-          const float h01 = __ldg(h + 1);
-          z = (h00 + fx * (h11 - h01)) + fy * (h01 - h00);
-        } else {          // triangle (v00, v10, v11)
-          const float h10 = __ldg(h + a.hf.num_y);
-          z = (h00 + fx * (h10 - h00)) + fy * (h11 - h10);
-        }
+        h00[k] = __ldg(h); h01[k] = __ldg(h + 1); h10[k] = __ldg(h + a.hf.num_y); h11[k] = __ldg(h + a.hf.num_y + 1);
       }
-      st_f(a.hits, env, r, z);
+#pragma unroll
+      for (int k = 0; k < kRaysPerLane; ++k) {
+        const int r = base + k * 32 + lane;
+        // triangle (v00, v11, v01) above the diagonal, (v00, v10, v11) below it
+        const float za = (h00[k] + fx[k] * (h11[k] - h01[k])) + fy[k] * (h01[k] - h00[k]);
+        const float zb = (h00[k] + fx[k] * (h10[k] - h00[k])) + fy[k] * (h11[k] - h10[k]);
+        const float z = inside[k] ? ((fy[k] >= fx[k]) ? za : zb) : INFINITY;
+        if (r < R) st_f(a.hits, env, r, z);
+      }
     }
   }
 }
@@ -260,14 +287,15 @@ int rl_is_robot_on_terrain(RlCtx* ctx, int64_t num_envs, const RlField* root_pos
   if (num_envs <= 0) return RL_OK;
   if (!root_pos_w->ptr) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: root_pos_w required%s", "");
   if (int rc = check_grid("rl_is_robot_on_terrain", grid)) return rc;
-  if (num_envs >= (1ll << 31)) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: too many envs%s", "");
+  if (num_envs >= (1ll << 27)) return rl_fail(RL_EINVAL, "rl_is_robot_on_terrain: too many envs%s", "");
   TerrainArgs a;
   memset(&a, 0, sizeof(a));
   a.N = (int)num_envs; a.pos = *root_pos_w; a.grid = *grid; a.out = out;
   RlDeviceGuard guard(rl_ctx_device_of(ctx));
   const int threads = 128;
   const size_t smem = sizeof(float) * 2 * (size_t)grid->num_rows * grid->num_cols;
-  terrain_kernel<false><<<(int)((num_envs + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
+  const long long work = num_envs * kLanesPerEnv;
+  terrain_kernel<false><<<(int)((work + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   return RL_OK;
 }
@@ -278,7 +306,7 @@ int rl_command_pit_restrict(RlCtx* ctx, int64_t num_envs, const RlField* root_po
     return rl_fail(RL_EINVAL, "rl_command_pit_restrict: null argument%s", "");
   if (num_envs <= 0) return RL_OK;
   if (int rc = check_grid("rl_command_pit_restrict", grid)) return rc;
-  if (num_envs >= (1ll << 31)) return rl_fail(RL_EINVAL, "rl_command_pit_restrict: too many envs%s", "");
+  if (num_envs >= (1ll << 27)) return rl_fail(RL_EINVAL, "rl_command_pit_restrict: too many envs%s", "");
   const RlStepSpec* s = rl_ctx_spec_of(ctx);
   if (!root_pos_w->ptr || !mdp->command.ptr || !mdp->is_standing_env.ptr ||
       (s->command.heading_command && (!mdp->heading_target.ptr || !mdp->is_heading_env.ptr)))
@@ -291,7 +319,8 @@ int rl_command_pit_restrict(RlCtx* ctx, int64_t num_envs, const RlField* root_po
   RlDeviceGuard guard(rl_ctx_device_of(ctx));
   const int threads = 128;
   const size_t smem = sizeof(float) * 2 * (size_t)grid->num_rows * grid->num_cols;
-  terrain_kernel<true><<<(int)((num_envs + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
+  const long long work = num_envs * kLanesPerEnv;
+  terrain_kernel<true><<<(int)((work + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   return RL_OK;
 }
