@@ -228,6 +228,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout: keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     N, S, K, W = args.num_envs, max(1, args.sets), args.steps, max(3, args.warmup)

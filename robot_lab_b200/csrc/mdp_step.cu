@@ -54,7 +54,10 @@ using DeviceGuard = RlDeviceGuard;
 // in the kernel parameter bank - one parameter line per field, no table in global memory.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
-constexpr int kTermParts = 4;   // a reward term is evaluated in at most this many parts (termv holds that many slots per term)
+// A reward term is evaluated in at most this many parts (termv holds that many slots per term). 2, not more: finer
+// cuts measured slower, and every extra slot costs K * 128 bytes of the tile record - at 4 the Go2-rough record grew
+// from 114.6 to 119.9 KB and lost the second resident CTA per SM (1.5 x slower from 16 k envs up)
+constexpr int kTermParts = 2;
 
 struct FieldD {
   const void* ptr;
