@@ -375,6 +375,11 @@ const char* rl_last_error(void);
  * language binding verify its mirror of the layouts before the first call. */
 int64_t rl_struct_sizeof(const char* name);
 
+/* Dynamic shared memory (bytes) one CTA of rl_step - a tile of 32 envs - needs for this spec; no device required.
+ * An SM of the B200 holds two such CTAs when 2 * (bytes + 1024) <= 233472: from the second wave of tiles on
+ * (> ~4700 envs) that second resident CTA is worth 1.5 x (profiles/r1_summary.md section 5). -1: invalid spec. */
+int64_t rl_tile_record_bytes(const RlStepSpec* spec);
+
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 

@@ -201,7 +201,7 @@ _STRUCTS = (RlRewardTerm, RlObsTerm, RlObsGroup, RlDoneTerm, RlCommandCfg, RlAct
             RlHeightField)
 
 EXPORTED_SYMBOLS = (
-    "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_ctx_create", "rl_ctx_destroy",
+    "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_tile_record_bytes", "rl_ctx_create", "rl_ctx_destroy",
     "rl_ctx_set_launch_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_ctx_get_schedule",
     "rl_contact_sensor_update", "rl_reset_scene_state", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
     "rl_actuator_step", "rl_is_robot_on_terrain", "rl_command_pit_restrict", "rl_height_scan_cast",
@@ -240,6 +240,8 @@ def load() -> C.CDLL:
         want = lib.rl_struct_sizeof(st.__name__.encode())
         if want != C.sizeof(st):
             raise NativeError(f"layout mismatch for {st.__name__}: C {want} vs ctypes {C.sizeof(st)}")
+    lib.rl_tile_record_bytes.restype = C.c_int64
+    lib.rl_tile_record_bytes.argtypes = [C.POINTER(RlStepSpec)]
     lib.rl_ctx_create.argtypes = [C.POINTER(RlStepSpec), C.c_int, C.POINTER(C.c_void_p)]
     lib.rl_ctx_destroy.argtypes = [C.c_void_p]
     lib.rl_ctx_destroy.restype = None

@@ -2097,6 +2097,11 @@ int64_t rl_struct_sizeof(const char* name) {
   return -1;
 }
 
+int64_t rl_tile_record_bytes(const RlStepSpec* spec) {
+  if (!spec || validate_spec(spec) != RL_OK) return -1;
+  return (int64_t)make_layout(*spec).total_words * 4;
+}
+
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   if (!spec || !out) return fail(RL_EINVAL, "rl_ctx_create: null argument%s", "");
   *out = nullptr;
