@@ -48,7 +48,9 @@ def parse_args():
     p.add_argument("--task", default=TASK_DEFAULT)
     p.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (weak scaling)")
     p.add_argument("--sets", type=int, default=24, help="independent state sets the step rotates over (L2 defeat)")
-    p.add_argument("--warps", type=int, default=0, help="warps per CTA (4/8/16; a CTA owns 32 envs)")
+    p.add_argument("--warps", type=int, default=0, help="warps per tile (4/8/16; a tile is 32 envs)")
+    p.add_argument("--envs-per-cta", type=int, default=0, choices=[0, 32, 64],
+                   help="32 = one tile per CTA (default), 64 = two tiles per CTA (1024 threads)")
     p.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels (measured slower)")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -234,8 +236,8 @@ def main():
 
     N, S, K, W = args.num_envs, max(1, args.sets), args.steps, max(3, args.warmup)
     eng = MdpStepEngine(spec, dev)
-    if args.warps:
-        eng.set_launch_config(args.warps)
+    if args.warps or args.envs_per_cta:
+        eng.set_launch_config(args.warps, args.envs_per_cta)
     eng.set_pdl(args.pdl)
     sets = []
     for i in range(S):
@@ -433,7 +435,7 @@ def main():
                 "workload": f"{args.task} (BASELINE.json configs[2]), {N} envs/GPU, J={spec.J} B={spec.B} F={spec.Bt} "
                             f"R={spec.R} K={spec.K}, policy/critic rows {spec.obs[0].dim}/{spec.obs[1].dim}",
                 "num_envs_per_gpu": N, "state_sets": S, "cuda_graph_steps": G if use_graph else 0,
-                "pdl": args.pdl, "launch": {"envs_per_cta": 32, "warps_per_cta": args.warps or 16},
+                "pdl": args.pdl, "launch": eng.launch_config(),
                 "l2_policy": f"rotating over {S} independent state sets (inputs+outputs+manager state "
                              f"{S * (sets[0].inputs.nbytes + sets[0].outputs.nbytes + sets[0].mdp.nbytes) / 1e6:.0f} MB > 126 MB L2)",
                 "noise": "in-kernel Philox4x32-10 (0 bytes)", "parallelism": f"dp{world} (env shards, no data-path collective)",

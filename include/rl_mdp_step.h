@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 10
+#define RL_ABI_VERSION 11
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -383,10 +383,16 @@ int64_t rl_tile_record_bytes(const RlStepSpec* spec);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knob: warps per CTA (4, 8 or 16; 0 = default). A CTA always owns 32 consecutive envs (one lane per env);
- * its warps share the termination / reward / command / observation terms according to a static schedule.
- * envs_per_cta must be 0 or 32. Synchronous (re-uploads the schedule): not for hot loops or stream capture. */
+/* Tuning knobs: warps per tile (4, 8 or 16; 0 = default 16) and tiles per CTA. A tile is 32 consecutive envs (one
+ * lane per env); its warps share the termination / reward / command / observation terms according to a static
+ * schedule. envs_per_cta: 0 or 32 = one tile per CTA; 64 = two tiles per CTA (1024 threads: warps w and w + 16 run
+ * the same task on neighbouring tiles, so an SM fetches the kernel's code once for 64 envs) - available for the
+ * build-time specialised specs at 16 warps whose two tile records fit the shared memory of one CTA, otherwise
+ * RL_EUNSUPPORTED. The environment variable RL_MDPSTEP_TILES=2 selects it at rl_ctx_create wherever it exists.
+ * Synchronous (re-uploads the schedule): not for hot loops or stream capture. */
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
+/* The configuration in effect (after rl_ctx_create's defaults / RL_MDPSTEP_TILES, or the last successful set). */
+int rl_ctx_get_launch_config(const RlCtx* ctx, int* envs_per_cta, int* warps_per_tile);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);

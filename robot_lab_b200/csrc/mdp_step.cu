@@ -359,6 +359,8 @@ struct KArgs {
   const int32_t* n_env_ids;
   Layout L;                // generic kernel only; baked kernels compute theirs at compile time
   const Schedule* sched;   // device copy (generic kernel); baked kernels carry theirs as constexpr data
+  int vgrid;               // number of tiles ("virtual CTAs") of the launch; == gridDim.x when a CTA carries one tile
+  int tile_words;          // distance between the records of a CTA's tiles in shared memory (words; multi-tile CTAs)
   unsigned int* ticket;
   uint32_t* cta_mask;
   float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions
@@ -1203,16 +1205,48 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 //   stage 2: warp 0 adds the reward up in manager order (and finishes is_terminated)
 //   store  : bulk stores for the observation rows, per-field loops for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
-template <class P, int NW, int MODE, bool DBG>
-__global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
-  extern __shared__ __align__(128) float sm[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_last;
+template <class P, int NW, int MODE, bool DBG, int TILES>
+__global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a) {
+  extern __shared__ __align__(128) float sm_cta[];
+  __shared__ __align__(8) uint64_t s_bar_all[TILES];
+  __shared__ int s_last_all[TILES];
   const Scalars S = P::scalars(a);
   const Layout L = P::layout(a);
-  constexpr int NT = NW * 32;
-  const int tid = threadIdx.x;
-#define RL_STAMP(i) do { if constexpr (DBG) { if (tid == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + (i)] = clock64(); } } while (0)
+  constexpr int NT = NW * 32;   // threads per tile
+  // TILES > 1: the CTA carries TILES independent tiles; threads [t*NT, (t+1)*NT) are "virtual CTA" vb of tile t with
+  // their own record, mbarrier and named barrier, so warp w of every tile runs the same task code at about the same
+  // time (one instruction fetch per SM serves all of them). Everything below is written in terms of the virtual CTA.
+  const int tile = (TILES > 1) ? (int)(threadIdx.x / NT) : 0;
+  const int tid = (TILES > 1) ? (int)(threadIdx.x - tile * NT) : (int)threadIdx.x;
+  const int vb = (TILES > 1) ? (int)(blockIdx.x * TILES + tile) : (int)blockIdx.x;        // virtual CTA = tile index
+  const int vgrid = (TILES > 1) ? a.vgrid : (int)gridDim.x;
+  if (TILES > 1 && vb >= vgrid) return;   // odd tile count: the spare half of the last CTA
+  float* const sm = sm_cta + (TILES > 1 ? (size_t)tile * (size_t)a.tile_words : (size_t)0);
+  uint64_t& s_bar = s_bar_all[tile];
+  int& s_last = s_last_all[tile];
+  auto tile_sync = [&]() __attribute__((always_inline)) {
+    if constexpr (TILES > 1) asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "n"(NT) : "memory");
+    else __syncthreads();
+  };
+  auto tile_sync_or = [&](bool pred) __attribute__((always_inline)) -> int {
+    if constexpr (TILES > 1) {
+      uint32_t r;
+      asm volatile(
+          "{\n"
+          ".reg .pred p, q;\n"
+          "setp.ne.u32 q, %3, 0;\n"
+          "bar.red.or.pred p, %1, %2, q;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(r)
+          : "r"(tile + 1), "n"(NT), "r"((uint32_t)pred)
+          : "memory");
+      return (int)r;
+    } else {
+      return __syncthreads_or(pred);
+    }
+  };
+#define RL_STAMP(i) do { if constexpr (DBG) { if (tid == 0) a.dbg[(size_t)vb * RL_DEBUG_STRIDE + (i)] = clock64(); } } while (0)
 #define RL_SUB(i) RL_STAMP(8 + RL_MAX_TASKS + 32 + (i))   /* finer stamps inside the load phase (debug build only) */
   RL_STAMP(0);
   const int warp = tid >> 5;
@@ -1224,7 +1258,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   const int n_total = a.has_ids ? *a.n_env_ids : a.N;
-  const int env0 = blockIdx.x * kE;
+  const int env0 = vb * kE;
   const int K = S.num_reward_terms;
   // RESET comes in two forms: on an env-id list (gathered tiles, every env of the launch is reset) or - without
   // a list - over all envs, resetting those whose terminated | truncated byte is set (full-tile fast path)
@@ -1232,7 +1266,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const bool reset_masked = do_reset && !a.has_ids;
   // (the masked form reads its reset count only in the tail: a dependent global load up here would stall the
   // whole prologue; the id-list form needs its count for the bounds anyway)
-  if (do_reset && !reset_masked && n_total == 0 && blockIdx.x == 0 && tid < RL_LOG_STRIDE) {
+  if (do_reset && !reset_masked && n_total == 0 && vb == 0 && tid < RL_LOG_STRIDE) {
     // nothing to reset and no CTA reaches the tail: the logged scalars are defined as 0
     if (tid < K) { if (a.out.reset_log.episode_sum_mean) a.out.reset_log.episode_sum_mean[tid] = 0.f; }
     else if (tid < K + RL_MAX_DONE_TERMS) { if (a.out.reset_log.done_term_count) a.out.reset_log.done_term_count[tid - K] = 0.f; }
@@ -1308,7 +1342,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     if (do_reset && tid < kE) sm[L.rmask + tid] = __int_as_float(tid < nvalid ? u8_reset : 0);
     RL_STAMP(1);                // all loads issued
     cp_async_wait_all();
-    __syncthreads();            // record + mbarrier init visible to everyone
+    tile_sync();            // record + mbarrier init visible to everyone
     mbar_wait(&s_bar, 0);       // bulk copies landed
     RL_STAMP(2);                // tile resident
   }
@@ -1317,9 +1351,9 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
   if (nvalid > 0) {
     // ---- manager reset of the tile's envs that are being reset ------------------------------------------
-    const int tile_resets = do_reset ? __syncthreads_or(tid < kE && __float_as_int(sm[L.rmask + (tid & 31)]) != 0) : 0;
+    const int tile_resets = do_reset ? tile_sync_or(tid < kE && __float_as_int(sm[L.rmask + (tid & 31)]) != 0) : 0;
     if (do_reset && !tile_resets) {   // CTA-uniform: nothing to reset here, the logging partials are zero
-      if (tid < K + RL_MAX_DONE_TERMS + 2) a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + tid] = 0.f;
+      if (tid < K + RL_MAX_DONE_TERMS + 2) a.log_partials[(size_t)vb * RL_LOG_STRIDE + tid] = 0.f;
     }
     if (tile_resets) {
       const bool rme = __float_as_int(sm[L.rmask + e]) != 0;
@@ -1336,9 +1370,9 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-        if (e == 0) a.log_partials[(size_t)blockIdx.x * RL_LOG_STRIDE + q] = x;
+        if (e == 0) a.log_partials[(size_t)vb * RL_LOG_STRIDE + q] = x;
       }
-      __syncthreads();
+      tile_sync();
       // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
       for (int i = tid; i < kE * K; i += NT) if (__float_as_int(sm[L.rmask + (i & 31)]) != 0) sm[L.sums + i] = 0.f;
       for (int i = tid; i < kE * A; i += NT)
@@ -1372,7 +1406,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         }
         sm[L.isstand + el] = __int_as_float((u[6] <= cc.rel_standing_envs) ? 1 : 0);
       }
-      __syncthreads();
+      tile_sync();
     }
 
     // ---- stage 1: thread-per-env, warps run different tasks ------------------------------------------------
@@ -1405,7 +1439,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       });
       return (int)(bits | (term << 8) | (trunc << 9));
     };
-    if constexpr (DBG) { if (e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + RL_MAX_TASKS + warp] = clock64(); }
+    if constexpr (DBG) { if (e == 0) a.dbg[(size_t)vb * RL_DEBUG_STRIDE + 8 + RL_MAX_TASKS + warp] = clock64(); }
     P::template for_tasks<NW>(a, warp, [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm& ot, const bool corrupt,
                                           const int task_idx) __attribute__((always_inline)) {
       long long t_begin = 0;
@@ -1464,9 +1498,9 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         }
       }
       }();
-      if constexpr (DBG) { if (e == 0) a.dbg[(size_t)blockIdx.x * RL_DEBUG_STRIDE + 8 + task_idx] = clock64() - t_begin; }
+      if constexpr (DBG) { if (e == 0) a.dbg[(size_t)vb * RL_DEBUG_STRIDE + 8 + task_idx] = clock64() - t_begin; }
     });
-    __syncthreads();
+    tile_sync();
     RL_STAMP(3);                // stage 1 done
 
     // ---- stage 2: warp 0 finishes the late terms and adds the reward up in manager order ------------------
@@ -1493,13 +1527,13 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
       SMF(L.rew, 0) = total;
       RL_SUB(4);                // reward summed
     }
-    __syncthreads();
+    tile_sync();
     RL_STAMP(4);                // stage 2 done
 
     // ---- store phase ----------------------------------------------------------------------------
     if (ph & RL_PHASE_OBS) {
       fence_proxy_async();
-      __syncthreads();
+      tile_sync();
 #pragma unroll
       for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
         const int D = P::obs_dim(a, g);
@@ -1542,23 +1576,23 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     if (tid < kE) {  // per-CTA bit mask of done envs
       const int f2 = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
       const unsigned m = __ballot_sync(0xffffffffu, (f2 >> 8) & 3);
-      if (tid == 0) a.cta_mask[blockIdx.x] = m;
+      if (tid == 0) a.cta_mask[vb] = m;
     }
-    __syncthreads();
+    tile_sync();
     if (tid == 0) {
       __threadfence();
       const unsigned prev = atomicAdd(a.ticket, 1u);
-      s_last = (prev == gridDim.x - 1);
+      s_last = (prev == (unsigned)(vgrid - 1));
     }
-    __syncthreads();
+    tile_sync();
     if (s_last) {
       __threadfence();
       int* s_cnt = reinterpret_cast<int*>(sm);  // this CTA's tile is dead once its own stores have been issued
       if ((ph & RL_PHASE_OBS) && nvalid > 0) { if (tid == 0) bulk_wait_read0(); }
-      __syncthreads();
+      tile_sync();
       // one mask per CTA; thread i takes mask base+i, a block-wide exclusive scan of the popcounts gives its
       // first output slot -> ids come out ascending
-      const int G = gridDim.x;
+      const int G = vgrid;
       int run = 0;
 #pragma unroll 1
       for (int base = 0; base < G; base += NT) {
@@ -1569,7 +1603,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (e >= d) incl += y; }
         if (e == 31) s_cnt[warp] = incl;
-        __syncthreads();
+        tile_sync();
         if (warp == 0) {
           int wt = (e < NW) ? s_cnt[e] : 0, wi = wt;
 #pragma unroll
@@ -1577,7 +1611,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
           if (e < NW) s_cnt[e] = wi - wt;           // exclusive prefix of the warp totals
           if (e == 31) s_cnt[32] = wi;              // chunk total
         }
-        __syncthreads();
+        tile_sync();
         int pos = run + s_cnt[warp] + incl - cnt;
         if (a.out.reset_ids)
           while (m) {
@@ -1586,7 +1620,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
             a.out.reset_ids[pos++] = g * kE + b;
           }
         run += s_cnt[32];
-        __syncthreads();
+        tile_sync();
       }
       if (tid == 0) {
         if (a.out.n_reset) *a.out.n_reset = run;
@@ -1597,25 +1631,25 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
   }
   if (do_reset && nvalid > 0) {
     const int n_cta = (n_total + kE - 1) / kE;
-    __syncthreads();
+    tile_sync();
     if (tid == 0) {
       __threadfence();
       const unsigned prev = atomicAdd(a.ticket, 1u);
       s_last = (prev == (unsigned)(n_cta - 1));
     }
-    __syncthreads();
+    tile_sync();
     if (s_last) {
       __threadfence();
       // quantity q = lane, the CTAs' partials strided over the warps, then the warps' sums in warp order
       float* s_red = sm;   // this CTA's tile is dead once its own stores have been issued
       if ((ph & RL_PHASE_OBS) && tid == 0) bulk_wait_read0();
-      __syncthreads();
+      tile_sync();
       for (int q = e; q < K + RL_MAX_DONE_TERMS + 2; q += 32) {
         float part = 0.f;
         for (int g = warp; g < n_cta; g += NW) part += __ldcg(a.log_partials + (size_t)g * RL_LOG_STRIDE + q);
         s_red[warp * RL_LOG_STRIDE + q] = part;
       }
-      __syncthreads();
+      tile_sync();
       if (tid < K + RL_MAX_DONE_TERMS + 2) {
         float tot = 0.f;
         for (int w = 0; w < NW; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
@@ -1841,7 +1875,8 @@ struct RlCtx {
   int device;
   int slot;
   RlStepSpec spec;
-  int NW;                 // warps per CTA (kE = 32 envs per CTA is fixed)
+  int NW;                 // warps per tile (kE = 32 envs per tile is fixed)
+  int tiles;              // tiles per CTA: 1, or 2 (baked specs at 16 warps whose two records fit one SM)
   Layout L;
   Schedule* sched_dev;
   Schedule sched;         // host copy of the schedule of the current launch config
@@ -1851,6 +1886,7 @@ struct RlCtx {
   int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
   int sm_count;
+  size_t smem_optin;      // largest dynamic shared memory a CTA may ask for on this device
   int use_pdl;
   long long* dbg;
   int baked;   // index into RL_BAKED_LIST when the spec equals a build-time specialised one, else -1
@@ -1992,35 +2028,43 @@ int validate_spec(const RlStepSpec* s) {
   return RL_OK;
 }
 
-template <class P, int NW, int MODE, bool DBG>
-int launch_step_variant(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
-  const size_t smem = (size_t)ctx->L.total_words * 4;
+template <class P, int NW, int MODE, bool DBG, int TILES>
+int launch_step_variant(RlCtx* ctx, const KArgs& a_in, int n_items, cudaStream_t st) {
+  // every tile record starts 128-byte aligned (bulk copies need 16)
+  const int tile_words = (ctx->L.total_words + 31) & ~31;
+  const size_t smem = TILES > 1 ? (size_t)tile_words * 4 * TILES : (size_t)ctx->L.total_words * 4;
   static thread_local int configured_device = -1;
   static thread_local size_t configured_smem = 0;
   if (configured_device != ctx->device || configured_smem < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(mdp_step_kernel<P, NW, MODE, DBG, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = ctx->device; configured_smem = smem;
   }
-  const int grid = (n_items + kE - 1) / kE;
-  if (grid <= 0) return RL_OK;
+  const int vgrid = (n_items + kE - 1) / kE;
+  if (vgrid <= 0) return RL_OK;
+  KArgs a = a_in;
+  a.vgrid = vgrid; a.tile_words = tile_words;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((vgrid + TILES - 1) / TILES); cfg.blockDim = dim3(NW * 32 * TILES); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = a.use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE, DBG>, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mdp_step_kernel<P, NW, MODE, DBG, TILES>, a));
   return RL_OK;
 }
 // the clock-stamp variant (rl_ctx_set_debug_buffer) is a separate instantiation: the production kernel carries
-// no trace of it
+// no trace of it. Two tiles per CTA (rl_ctx_set_launch_config(ctx, 64, 16)) exist for the build-time specialised
+// kernels at 16 warps per tile only - 1024 threads, two records in shared memory.
 template <class P, int NW, int MODE>
 int launch_step(RlCtx* ctx, const KArgs& a, int n_items, cudaStream_t st) {
   if constexpr (MODE == 0) {
-    if (a.dbg != nullptr) return launch_step_variant<P, NW, MODE, true>(ctx, a, n_items, st);
+    if (a.dbg != nullptr) return launch_step_variant<P, NW, MODE, true, 1>(ctx, a, n_items, st);
+    if constexpr (P::kStatic && NW == 16) {
+      if (ctx->tiles == 2) return launch_step_variant<P, NW, MODE, false, 2>(ctx, a, n_items, st);
+    }
   }
-  return launch_step_variant<P, NW, MODE, false>(ctx, a, n_items, st);
+  return launch_step_variant<P, NW, MODE, false, 1>(ctx, a, n_items, st);
 }
 
 // warps per CTA compiled for the generic kernel / for every baked spec
@@ -2079,6 +2123,12 @@ int ensure_scratch(RlCtx* ctx, int grid) {
 
 bool g_slots[16][RL_SPEC_SLOTS];
 
+// two tiles per CTA: a build-time specialised kernel at 16 warps per tile, both records resident in one CTA
+bool two_tiles_ok(const RlCtx* ctx) {
+  const size_t tile_bytes = (size_t)((ctx->L.total_words + 31) & ~31) * 4;
+  return ctx->baked >= 0 && ctx->NW == 16 && 2 * tile_bytes <= ctx->smem_optin;
+}
+
 }  // namespace
 
 extern "C" {
@@ -2126,6 +2176,8 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  ctx->tiles = 1;
   if ((size_t)ctx->L.total_words * 4 > (size_t)prop.sharedMemPerBlockOptin) {
     delete ctx;
     return fail(RL_EUNSUPPORTED, "the tile of %s%lld envs needs %lld bytes of shared memory", "", kE, (long long)make_layout(*spec).total_words * 4);
@@ -2148,6 +2200,10 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
     // RL_MDPSTEP_GENERIC=1 forces the generic (table-driven) kernel: A/B measurements and tests of that path
     const char* force_generic = getenv("RL_MDPSTEP_GENERIC");
     if (force_generic && force_generic[0] == '1') ctx->baked = -1;
+    // RL_MDPSTEP_TILES=2: two tiles per CTA wherever that configuration exists (A/B measurements, test runs of
+    // that path); contexts it does not apply to keep one tile
+    const char* want_tiles = getenv("RL_MDPSTEP_TILES");
+    if (want_tiles && want_tiles[0] == '2' && two_tiles_ok(ctx)) ctx->tiles = 2;
   }
   g_slots[device][slot] = true;
   *out = ctx;
@@ -2168,13 +2224,29 @@ void rl_ctx_destroy(RlCtx* ctx) {
 
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
-  if (envs_per_cta != 0 && envs_per_cta != kE) return fail(RL_EINVAL, "envs_per_cta is fixed at %s%lld (one lane per env)", "", kE);
+  if (envs_per_cta != 0 && envs_per_cta != kE && envs_per_cta != 2 * kE)
+    return fail(RL_EINVAL, "envs_per_cta must be %s%lld (one tile, one lane per env) or twice that (two tiles per CTA)", "", kE);
   const int nw = warps_per_cta > 0 ? warps_per_cta : 16;
   if (nw != 4 && nw != 8 && nw != 16) return fail(RL_EINVAL, "warps_per_cta must be 4, 8 or 16%s, got %lld", "", nw);
+  if (envs_per_cta == 2 * kE) {
+    RlCtx probe = *ctx;
+    probe.NW = nw;
+    if (!two_tiles_ok(&probe))
+      return fail(RL_EUNSUPPORTED, "two tiles per CTA need a build-time specialised spec, 16 warps per tile and 2 x %s%lld bytes of shared memory", "",
+                  (long long)ctx->L.total_words * 4);
+  }
   DeviceGuard guard(ctx->device);
   ctx->sched = make_schedule(ctx->spec, nw);
   CUDA_TRY(cudaMemcpy(ctx->sched_dev, &ctx->sched, sizeof(Schedule), cudaMemcpyHostToDevice));  // synchronous: not for hot loops
   ctx->NW = nw;
+  ctx->tiles = envs_per_cta == 2 * kE ? 2 : 1;
+  return RL_OK;
+}
+
+int rl_ctx_get_launch_config(const RlCtx* ctx, int* envs_per_cta, int* warps_per_tile) {
+  if (!ctx || !envs_per_cta || !warps_per_tile) return fail(RL_EINVAL, "null argument%s", "");
+  *envs_per_cta = kE * ctx->tiles;
+  *warps_per_tile = ctx->NW;
   return RL_OK;
 }
 

@@ -42,9 +42,16 @@ class MdpStepEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def set_launch_config(self, warps_per_cta: int = 0) -> None:
-        """Warps per CTA (4, 8, 16; also 24, 32 for build-time specialised tasks). A CTA owns 32 envs, one lane each."""
-        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, 0, warps_per_cta))
+    def set_launch_config(self, warps_per_cta: int = 0, envs_per_cta: int = 0) -> None:
+        """Warps per tile (4, 8, 16) and envs per CTA: 32 = one tile (one lane per env), 64 = two tiles per CTA
+        (build-time specialised tasks at 16 warps whose two tile records fit one SM; NativeError otherwise)."""
+        nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, envs_per_cta, warps_per_cta))
+
+    def launch_config(self) -> dict:
+        """The launch configuration in effect: ``{"envs_per_cta": 32 | 64, "warps_per_tile": 4 | 8 | 16}``."""
+        epc, nw = C.c_int(0), C.c_int(0)
+        nat.check(self.lib.rl_ctx_get_launch_config(self._ctx, C.byref(epc), C.byref(nw)))
+        return {"envs_per_cta": epc.value, "warps_per_tile": nw.value}
 
     def set_pdl(self, enabled: bool) -> None:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""

@@ -107,6 +107,9 @@ def test_headline_task_keeps_two_tiles_per_sm(native_lib):
         assert 0 < sizes[key] <= 232448, (key, sizes[key])          # fits one CTA at all (227 KiB)
     for key in ("go2_rough", "go2_flat", "a1_flat"):
         assert 2 * (sizes[key] + 1024) <= 233472, (key, sizes[key])
+        # ... and the two-tiles-per-CTA launch config (rl_ctx_set_launch_config(ctx, 64, 16)): both records, each
+        # starting 128-byte aligned, plus the kernel's static shared memory inside one CTA's 227 KiB
+        assert 2 * ((sizes[key] + 127) // 128 * 128) + 128 <= 232448, (key, sizes[key])
     bad = spec.to_ctypes()
     bad.num_joints = 0
     assert native_lib.rl_tile_record_bytes(C.byref(bad)) == -1

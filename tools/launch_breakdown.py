@@ -2,7 +2,7 @@
 no debug buffer): process_action | rl_step(ALL|SKIP) | rl_step(RESET|COMMAND|OBS on reset ids) and a few phase
 subsets of the fused kernel. Rotates over independent state sets larger than L2.
 
-Usage (GPU box): python tools/launch_breakdown.py [num_envs] [warps] [task_key]
+Usage (GPU box): python tools/launch_breakdown.py [num_envs] [warps] [task_key] [envs_per_cta: 32 | 64] [--short]
 """
 import sys
 from pathlib import Path
@@ -20,9 +20,11 @@ from robot_lab_b200.synthetic import make_state  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 key = sys.argv[3] if len(sys.argv) > 3 else "go2_rough"
+EPC = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+SHORT = "--short" in sys.argv   # only the three launches of an env step and their sum
 cfg, spec = H.make_spec(key)
 eng = MdpStepEngine(spec, "cuda:0")
-eng.set_launch_config(W)
+eng.set_launch_config(W, EPC)
 n_sets = max(2, min(24, int(400e6 / (N * 3500)) + 1))
 sets = []
 for i in range(n_sets):
@@ -64,10 +66,12 @@ CASES = {
     "rl_step COMMAND only": lambda b: eng.step(b, phases=nat.PHASE_COMMAND, use_random_inputs=False),
     "env step, older form: process_action + ALL|SKIP + reset ids": lambda b: (eng.process_action(b), run_step(b), run_post(b)),
 }
+if SHORT:
+    CASES = {k: v for k, v in CASES.items() if k.startswith(("process_action", "rl_step DONES|REWARDS|COMPACT", "rl_step RESET|COMMAND|OBS, all", "env step: "))}
 for b in sets:  # reset ids valid for the post-reset case
     run_step(b)
 torch.cuda.synchronize()
-print(f"{key} N={N} warps={W} state sets={n_sets}; mean reset envs per step: "
+print(f"{key} N={N} warps={W} envs_per_cta={EPC or 32} state sets={n_sets}; mean reset envs per step: "
       f"{sum(int(b.n_reset.item()) for b in sets) / len(sets):.1f}")
 for pdl in (False,):
     eng.set_pdl(pdl)
