@@ -423,6 +423,15 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// "last CTA" tickets: the increment is a release at device scope (everything this thread wrote or observed through a
+// CTA barrier before it is visible to whoever reads the final count and then fences) - one MEMBAR.ALL.GPU instead of
+// the sequentially-consistent fence of __threadfence() (MEMBAR.SC.GPU + L1 invalidation), and no result is needed
+// until the tail, so the issuing warp does not wait for the round trip
+__device__ __forceinline__ unsigned ticket_arrive_release(unsigned int* ticket) {
+  unsigned prev;
+  asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket) : "memory");
+  return prev;
+}
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -1347,13 +1356,31 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
     RL_STAMP(2);                // tile resident
   }
 
+  // Tickets of the two "last CTA" tails are taken EARLY - as soon as what the last CTA will read has been written -
+  // and only looked at in the tail: the fence + atomic round trip (~1 us) overlaps the rest of the tile's work.
+  unsigned early_prev = 0;
+  const bool compact = (ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids;
+  constexpr int kCompactWarp = 1;   // idle during stage 2 (warp 0 sums the reward up)
+  auto compact_arrive = [&]() __attribute__((always_inline)) {   // one warp: the tile's done mask, then its ticket
+    const int f2 = (e < nvalid) ? __float_as_int(sm[L.flags + e]) : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, (f2 >> 8) & 3);
+    if (e == 0) {
+      a.cta_mask[vb] = m;
+      early_prev = ticket_arrive_release(a.ticket);
+    }
+  };
   const bool valid = e < nvalid;
   const long long env = valid ? (ids ? (long long)ids[env0 + e] : (long long)(env0 + e)) : 0;
   if (nvalid > 0) {
     // ---- manager reset of the tile's envs that are being reset ------------------------------------------
     const int tile_resets = do_reset ? tile_sync_or(tid < kE && __float_as_int(sm[L.rmask + (tid & 31)]) != 0) : 0;
     if (do_reset && !tile_resets) {   // CTA-uniform: nothing to reset here, the logging partials are zero
-      if (tid < K + RL_MAX_DONE_TERMS + 2) a.log_partials[(size_t)vb * RL_LOG_STRIDE + tid] = 0.f;
+      if (warp == 0) {
+        for (int q = e; q < K + RL_MAX_DONE_TERMS + 2; q += 32) a.log_partials[(size_t)vb * RL_LOG_STRIDE + q] = 0.f;
+        __syncwarp();
+        // the tile's arrival at the logging reduction, long before the tail needs the answer (see the tail)
+        if (e == 0) early_prev = ticket_arrive_release(a.ticket);
+      }
     }
     if (tile_resets) {
       const bool rme = __float_as_int(sm[L.rmask + e]) != 0;
@@ -1373,6 +1400,7 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
         if (e == 0) a.log_partials[(size_t)vb * RL_LOG_STRIDE + q] = x;
       }
       tile_sync();
+      if (tid == 0) early_prev = ticket_arrive_release(a.ticket);   // partials of every warp ordered by the barrier
       // RewardManager / ActionManager / CommandTerm .reset [IL], episode_length_buf = 0
       for (int i = tid; i < kE * K; i += NT) if (__float_as_int(sm[L.rmask + (i & 31)]) != 0) sm[L.sums + i] = 0.f;
       for (int i = tid; i < kE * A; i += NT)
@@ -1502,6 +1530,7 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
     });
     tile_sync();
     RL_STAMP(3);                // stage 1 done
+    if (compact && warp == kCompactWarp) compact_arrive();   // the termination flags are final
 
     // ---- stage 2: warp 0 finishes the late terms and adds the reward up in manager order ------------------
     if ((ph & RL_PHASE_REWARDS) && warp == 0) {
@@ -1572,18 +1601,9 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
 
   RL_STAMP(5);                  // stores issued
   // ---- ordered compaction of reset ids (ManagerBasedRLEnv.step: reset_buf.nonzero() [IL]) -----------
-  if ((ph & RL_PHASE_COMPACT) && (ph & RL_PHASE_DONES) && !a.has_ids) {
-    if (tid < kE) {  // per-CTA bit mask of done envs
-      const int f2 = (tid < nvalid) ? __float_as_int(sm[L.flags + tid]) : 0;
-      const unsigned m = __ballot_sync(0xffffffffu, (f2 >> 8) & 3);
-      if (tid == 0) a.cta_mask[vb] = m;
-    }
-    tile_sync();
-    if (tid == 0) {
-      __threadfence();
-      const unsigned prev = atomicAdd(a.ticket, 1u);
-      s_last = (prev == (unsigned)(vgrid - 1));
-    }
+  if (compact) {
+    if (nvalid == 0 && warp == kCompactWarp) compact_arrive();   // tiles past the end: an empty mask
+    if (tid == kCompactWarp * 32) s_last = (early_prev == (unsigned)(vgrid - 1));
     tile_sync();
     if (s_last) {
       __threadfence();
@@ -1631,12 +1651,7 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
   }
   if (do_reset && nvalid > 0) {
     const int n_cta = (n_total + kE - 1) / kE;
-    tile_sync();
-    if (tid == 0) {
-      __threadfence();
-      const unsigned prev = atomicAdd(a.ticket, 1u);
-      s_last = (prev == (unsigned)(n_cta - 1));
-    }
+    if (tid == 0) s_last = (early_prev == (unsigned)(n_cta - 1));   // arrived right after the partials were written
     tile_sync();
     if (s_last) {
       __threadfence();
