@@ -1,4 +1,4 @@
-"""Build the CUDA extension in-tree: ``python -m robot_lab_b200.build [--force]``.
+"""Build the CUDA extension in-tree: ``python -m robot_lab_b200.build [--force] [--variant NAME]``.
 
 One shared library (``robot_lab_b200/_lib/libmdpstep.so``), compiled for sm_100a only, from two translation units
 that are compiled in parallel and cached as objects: ``csrc/mdp_step.cu`` (the fused step kernels and the C-ABI
@@ -6,6 +6,10 @@ around them; minutes to compile because every baked task spec is its own set of 
 ``csrc/scene_kernels.cu`` (the neighbours of the path: actuator models, terrain queries, height-scan casting;
 seconds). ``-fmad=false`` is deliberate (see the header comment of csrc/mdp_step.cu). The built ``.so`` is
 git-ignored but travels to the GPU box with the repo snapshot.
+
+``--variant NAME`` builds an experimental configuration of the step kernels next to the default library
+(``_lib/libmdpstep_NAME.so``, loaded with ``RL_MDPSTEP_LIB=...`` for A/B runs and for running the test-suite against
+it); the default library and its objects are not touched. Variants: see ``VARIANTS`` below.
 """
 
 from __future__ import annotations
@@ -29,8 +33,41 @@ NVCC_FLAGS = [
 ]
 
 
+VARIANTS = {
+    "shared_norms": ["-DRL_SHARED_NORMS=1"],               # contact-force norms computed once per env (prepass)
+    "shared_ctx": ["-DRL_SHARED_CTX=1"],                   # the three root-frame rotations computed once per env
+    "shared": ["-DRL_SHARED_NORMS=1", "-DRL_SHARED_CTX=1"],
+}
+
+
 def _obj(src: Path) -> Path:
     return OUT.parent / (src.stem + ".o")
+
+
+def build_variant(name: str, verbose: bool = False) -> Path:
+    """Compile csrc/mdp_step.cu with the variant's defines into its own object / library; scene_kernels.o is shared."""
+    from . import codegen
+
+    if name not in VARIANTS:
+        raise KeyError(f"unknown variant '{name}'; known: {sorted(VARIANTS)}")
+    build()   # the default library (and scene_kernels.o) first
+    codegen.write()
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    obj = OUT.parent / f"mdp_step.{name}.o"
+    out = OUT.parent / f"libmdpstep_{name}.so"
+    cmd = [nvcc, *NVCC_FLAGS, *VARIANTS[name], "-c", str(SOURCES[0]), "-o", str(obj)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = " ".join(cmd) + "\n" + res.stdout + res.stderr
+    (OUT.parent / f"build.{name}.log").write_text(log)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{log[-4000:]}")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", str(obj), str(_obj(SOURCES[1])), "-o", str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout + res.stderr}")
+    if verbose:
+        print(log)
+    return out
 
 
 def _stale(target: Path, deps: list[Path]) -> bool:
@@ -82,5 +119,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--variant" in sys.argv:
+        path = build_variant(sys.argv[sys.argv.index("--variant") + 1], verbose="-v" in sys.argv)
+    else:
+        path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -57,7 +57,27 @@ constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase l
 // A reward term is evaluated in at most this many parts (termv holds that many slots per term). 2, not more: finer
 // cuts measured slower, and every extra slot costs K * 128 bytes of the tile record - at 4 the Go2-rough record grew
 // from 114.6 to 119.9 KB and lost the second resident CTA per SM (1.5 x slower from 16 k envs up)
+// RL_SHARED_NORMS=1 (build variant, robot_lab_b200/build.py --variant shared_norms; NOT the default, not yet measured on a
+// GPU): the max-over-history contact-force norm of every body is computed ONCE per env by a prepass in which all warps
+// run the same code (body b by warp b mod NW, lane = env) and kept in the record (hnorm); undesired_contacts,
+// contact_forces, feet_slide and illegal_contact read it instead of each recomputing T norms per body inside its own
+// single-warp chain. Same function, same operand order: bit-identical values. With the long body sums gone no
+// term is split, so termv needs one slot per term and the record does not grow.
+#ifndef RL_SHARED_NORMS
+#define RL_SHARED_NORMS 0
+#endif
+#if RL_SHARED_NORMS
+constexpr int kTermParts = 1;
+#else
 constexpr int kTermParts = 2;
+#endif
+// RL_SHARED_CTX=1 (build variant shared_ctx, also part of variant "shared"; not the default, not yet measured): the three
+// quaternion rotations every warp needs for its lane's env (projected gravity, base-frame linear / angular velocity)
+// are computed once by warps 0-2 and published in the record (ctxv) instead of sixteen times; same functions, same
+// operands: bit-identical values. One barrier in front of stage 1 (shared with the norm prepass when both are on).
+#ifndef RL_SHARED_CTX
+#define RL_SHARED_CTX 0
+#endif
 
 struct FieldD {
   const void* ptr;
@@ -95,6 +115,12 @@ struct Layout {
   int rew, flags, stepr;                         // outputs
   int termv;                                     // [K][kTermParts] weighted term value in slot 0 (raw partial sums of a split term before it is finished)
   int arrive;                                    // [K] per-env arrival counters of the two halves of a split term
+#if RL_SHARED_NORMS
+  int hnorm;                                     // [B] max over the history of |F_b| (written by the prepass)
+#endif
+#if RL_SHARED_CTX
+  int ctxv;                                      // [9] projected gravity, base-frame lin vel, base-frame ang vel
+#endif
   int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
   int soa_words;
   int cj;                                        // per-joint constants [5][J]: q0, qd0, soft lo, soft hi, vel limit
@@ -169,6 +195,12 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s) {
   L.w_stepr = take(K); L.stepr = L.w_stepr * E;
   L.termv = take(kTermParts * K) * E;
   L.arrive = take(K) * E;
+#if RL_SHARED_NORMS
+  L.hnorm = take(s.num_hist_bodies) * E;
+#endif
+#if RL_SHARED_CTX
+  L.ctxv = take(9) * E;
+#endif
   L.soa_words = w;
   int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
   L.cj = off; off = align_up(off + 5 * J, 32);
@@ -225,7 +257,11 @@ __host__ __device__ constexpr int reward_cost(const RlRewardTerm& t, const RlSte
     case RL_REW_JOINT_MIRROR: case RL_REW_ACTION_MIRROR: return 30 + 8 * F;
     case RL_REW_ACTION_SYNC: return 40 + 30 * F;
     case RL_REW_ACTION_RATE_L2: return 30 + 5 * s.action.n_actions;
+#if RL_SHARED_NORMS
+    case RL_REW_UNDESIRED_CONTACTS: case RL_REW_CONTACT_FORCES: return 30 + nbodies * 5;
+#else
     case RL_REW_UNDESIRED_CONTACTS: case RL_REW_CONTACT_FORCES: return 30 + nbodies * T * 18;
+#endif
     case RL_REW_TRACK_LIN_VEL_XY_EXP: case RL_REW_TRACK_ANG_VEL_Z_EXP: case RL_REW_TRACK_ANG_VEL_Z_WORLD_EXP: return 70;
     case RL_REW_TRACK_LIN_VEL_XY_YAW_FRAME_EXP: return 260;
     case RL_REW_FEET_AIR_TIME: case RL_REW_FEET_CONTACT: case RL_REW_FEET_CONTACT_WITHOUT_CMD: return 30 + 10 * F;
@@ -233,7 +269,11 @@ __host__ __device__ constexpr int reward_cost(const RlRewardTerm& t, const RlSte
     case RL_REW_FEET_AIR_TIME_VARIANCE: return 40 + 40 * F;
     case RL_REW_FEET_GAIT: return 260;
     case RL_REW_FEET_STUMBLE: return 30 + 20 * F;
+#if RL_SHARED_NORMS
+    case RL_REW_FEET_SLIDE: return 30 + F * 62;
+#else
     case RL_REW_FEET_SLIDE: return 30 + F * (60 + T * 18);
+#endif
     case RL_REW_FEET_HEIGHT: return 40 + 60 * F;
     case RL_REW_FEET_HEIGHT_BODY: return 40 + 130 * F;
     case RL_REW_FEET_DISTANCE_Y_EXP: case RL_REW_FEET_DISTANCE_XY_EXP: return 80 + 60 * F;
@@ -644,6 +684,12 @@ __device__ __forceinline__ bool first_contact(const float* sm, const Layout& L, 
 __device__ __forceinline__ V3 body_vec(const float* sm, int off, int e, int b) {
   return V3{SMF(off, 3 * b + 0), SMF(off, 3 * b + 1), SMF(off, 3 * b + 2)};
 }
+// what the norm consumers call: the record's cached value (prepass) or the computation itself
+#if RL_SHARED_NORMS
+#define HIST_MAX_NORM(h, b) SMF(L.hnorm, (b))
+#else
+#define HIST_MAX_NORM(h, b) hist_max_norm(h, S.hist_len, S.num_hist_bodies, b)   /* arguments are plain identifiers / subscripts */
+#endif
 // max over the history of |F_b| (net_forces_w_history[:, :, b].norm(-1).max(1))
 __device__ __noinline__ float hist_max_norm(const float* h, int T, int B, int b) {
   // ONE copy for every term that uses it (undesired_contacts, contact_forces, feet_slide, feet_stumble, the
@@ -784,14 +830,14 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
       float s = 0.f;
       _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
-        if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) s += 1.f;
+        if (((t.body_mask >> b) & 1ull) && (HIST_MAX_NORM(h, b) > t.p[0])) s += 1.f;
       return s * c.gate;   // gate distributes over the two halves of a split term
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
       _Pragma("unroll 1")
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
-        if ((t.body_mask >> b) & 1ull) s += fmaxf(hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) - t.p[0], 0.f);
+        if ((t.body_mask >> b) & 1ull) s += fmaxf(HIST_MAX_NORM(h, b) - t.p[0], 0.f);
       return s;
     }
     case RL_REW_TRACK_LIN_VEL_XY_EXP: {
@@ -912,7 +958,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
         const V3 vw = body_vec(sm, L.bvel, e, tc.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
         const float lat = sqrtf(vb.x * vb.x + vb.y * vb.y);
-        s += lat * ((hist_max_norm(h, S.hist_len, S.num_hist_bodies, tc.idx_c[i]) > 1.0f) ? 1.f : 0.f);
+        s += lat * ((HIST_MAX_NORM(h, tc.idx_c[i]) > 1.0f) ? 1.f : 0.f);
       }
       return s * c.gate;
     }
@@ -991,9 +1037,15 @@ __device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int
   c.pos = V3{SMF(L.root_pos, 0), SMF(L.root_pos, 1), SMF(L.root_pos, 2)};
   c.vw = V3{SMF(L.lin_vel, 0), SMF(L.lin_vel, 1), SMF(L.lin_vel, 2)};
   c.ww = V3{SMF(L.ang_vel, 0), SMF(L.ang_vel, 1), SMF(L.ang_vel, 2)};
+#if RL_SHARED_CTX
+  c.g = V3{SMF(L.ctxv, 0), SMF(L.ctxv, 1), SMF(L.ctxv, 2)};     // published by warps 0-2 in front of stage 1
+  c.vb = V3{SMF(L.ctxv, 3), SMF(L.ctxv, 4), SMF(L.ctxv, 5)};
+  c.wb = V3{SMF(L.ctxv, 6), SMF(L.ctxv, 7), SMF(L.ctxv, 8)};
+#else
   c.g = quat_apply_inverse(c.qw, c.q, V3{0.f, 0.f, -1.f});
   c.vb = quat_apply_inverse(c.qw, c.q, c.vw);
   c.wb = quat_apply_inverse(c.qw, c.q, c.ww);
+#endif
   c.gate = clampf(-c.g.z, 0.f, 0.7f) / 0.7f;
   c.c0 = SMF(L.cmd, 0); c.c1 = SMF(L.cmd, 1); c.c2 = SMF(L.cmd, 2);
   c.cmd_norm = sqrtf((c.c0 * c.c0 + c.c1 * c.c1) + c.c2 * c.c2);
@@ -1437,6 +1489,29 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
       tile_sync();
     }
 
+#if RL_SHARED_NORMS || RL_SHARED_CTX
+    {  // prepass in front of stage 1: work every warp would otherwise repeat, done once; lane = env
+#if RL_SHARED_CTX
+      if (warp < 3) {   // NW >= 4
+        const float qw = SMF(L.quat, 0);
+        const V3 q{SMF(L.quat, 1), SMF(L.quat, 2), SMF(L.quat, 3)};
+        const int src = (warp == 1) ? L.lin_vel : L.ang_vel;
+        const V3 v = (warp == 0) ? V3{0.f, 0.f, -1.f} : V3{SMF(src, 0), SMF(src, 1), SMF(src, 2)};
+        const V3 r = quat_apply_inverse(qw, q, v);
+        SMF(L.ctxv, 3 * warp + 0) = r.x; SMF(L.ctxv, 3 * warp + 1) = r.y; SMF(L.ctxv, 3 * warp + 2) = r.z;
+      }
+#endif
+#if RL_SHARED_NORMS
+      if (need_hist) {   // contact norms: one code copy for all warps; the warps without a rotation go first
+        const float* hrow = sm + L.hist + e * L.hist_pitch;
+        const int first = RL_SHARED_CTX ? (warp + NW - 3) % NW : warp;
+#pragma unroll 1
+        for (int b = first; b < S.num_hist_bodies; b += NW) SMF(L.hnorm, b) = hist_max_norm(hrow, S.hist_len, S.num_hist_bodies, b);
+      }
+#endif
+      tile_sync();
+    }
+#endif
     // ---- stage 1: thread-per-env, warps run different tasks ------------------------------------------------
     EnvCtx c = make_ctx(sm, L, e);
     if (MODE == 1) {
@@ -1461,7 +1536,7 @@ __global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a
         } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
           _Pragma("unroll 1")
           for (int b = 0; b < S.num_hist_bodies; ++b)
-            if (((t.body_mask >> b) & 1ull) && (hist_max_norm(h, S.hist_len, S.num_hist_bodies, b) > t.p[0])) fired = 1;
+            if (((t.body_mask >> b) & 1ull) && (HIST_MAX_NORM(h, b) > t.p[0])) fired = 1;
         }
         if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
       });
