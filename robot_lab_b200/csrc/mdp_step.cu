@@ -1266,8 +1266,14 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 //   stage 2: warp 0 adds the reward up in manager order (and finishes is_terminated)
 //   store  : bulk stores for the observation rows, per-field loops for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
+// the variants keep the second resident CTA per SM (<= 64 registers at 512 threads): without the hint ptxas took 104
+#if RL_SHARED_NORMS || RL_SHARED_CTX
+#define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES, (NW * 32 * TILES <= 512) ? 2 : 1)
+#else
+#define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES)
+#endif
 template <class P, int NW, int MODE, bool DBG, int TILES>
-__global__ void __launch_bounds__(NW * 32 * TILES) mdp_step_kernel(const KArgs a) {
+__global__ void RL_STEP_BOUNDS mdp_step_kernel(const KArgs a) {
   extern __shared__ __align__(128) float sm_cta[];
   __shared__ __align__(8) uint64_t s_bar_all[TILES];
   __shared__ int s_last_all[TILES];

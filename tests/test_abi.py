@@ -113,3 +113,39 @@ def test_headline_task_keeps_two_tiles_per_sm(native_lib):
     bad = spec.to_ctypes()
     bad.num_joints = 0
     assert native_lib.rl_tile_record_bytes(C.byref(bad)) == -1
+
+
+def test_build_variants_if_present_export_the_same_abi_and_do_not_grow_the_record(native_lib):
+    """Experimental builds of the step kernels (robot_lab_b200/build.py VARIANTS -> _lib/libmdpstep_<name>.so, built on
+    demand, git-ignored): same exports, same ABI version, and a tile record that keeps the second resident CTA per SM for
+    the quadruped tasks (the shared-norm variant drops the split-term slots and is no larger than the default)."""
+    import ctypes as C
+
+    import helpers as H
+    from robot_lab_b200 import _native as nat
+    from robot_lab_b200 import build as b
+
+    assert all(all(f.startswith("-D") for f in flags) for flags in b.VARIANTS.values())
+    found = 0
+    for name in b.VARIANTS:
+        path = b.OUT.parent / f"libmdpstep_{name}.so"
+        if not path.exists():
+            continue
+        found += 1
+        lib = C.CDLL(str(path))
+        for sym in nat.EXPORTED_SYMBOLS:
+            assert hasattr(lib, sym), (name, sym)
+        assert lib.rl_abi_version() == nat.RL_ABI_VERSION
+        lib.rl_tile_record_bytes.restype = C.c_int64
+        lib.rl_tile_record_bytes.argtypes = [C.POINTER(nat.RlStepSpec)]
+        for key in ("go2_rough", "go2_flat", "a1_flat", "g1_rough"):
+            _, spec = H.make_spec(key)
+            cs = spec.to_ctypes()
+            size, base = lib.rl_tile_record_bytes(C.byref(cs)), native_lib.rl_tile_record_bytes(C.byref(cs))
+            assert 0 < size <= 232448, (name, key, size)
+            if key != "g1_rough":
+                assert 2 * (size + 1024) <= 233472, (name, key, size)      # second resident CTA per SM kept
+            if "-DRL_SHARED_NORMS=1" in b.VARIANTS[name] and "-DRL_SHARED_CTX=1" not in b.VARIANTS[name]:
+                assert size <= base, (name, key, size, base)                # split-term slots gone, norms added
+    if not found:
+        pytest.skip("no variant library built (python -m robot_lab_b200.build --variant NAME)")
