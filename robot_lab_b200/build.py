@@ -37,6 +37,9 @@ VARIANTS = {
     "shared_norms": ["-DRL_SHARED_NORMS=1"],               # contact-force norms computed once per env (prepass)
     "shared_ctx": ["-DRL_SHARED_CTX=1"],                   # the three root-frame rotations computed once per env
     "shared": ["-DRL_SHARED_NORMS=1", "-DRL_SHARED_CTX=1"],
+    # same source, no parallel split of the optimiser: --split-compile=0 produced two different codegen "modes" for the
+    # same source in round 1; this is the reproducible build to A/B them against ("!" = drop a flag)
+    "nosplit": ["!--split-compile=0"],
 }
 
 
@@ -55,7 +58,9 @@ def build_variant(name: str, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     obj = OUT.parent / f"mdp_step.{name}.o"
     out = OUT.parent / f"libmdpstep_{name}.so"
-    cmd = [nvcc, *NVCC_FLAGS, *VARIANTS[name], "-c", str(SOURCES[0]), "-o", str(obj)]
+    drop = {f[1:] for f in VARIANTS[name] if f.startswith("!")}
+    flags = [f for f in NVCC_FLAGS if f not in drop] + [f for f in VARIANTS[name] if not f.startswith("!")]
+    cmd = [nvcc, *flags, "-c", str(SOURCES[0]), "-o", str(obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = " ".join(cmd) + "\n" + res.stdout + res.stderr
     (OUT.parent / f"build.{name}.log").write_text(log)
