@@ -167,3 +167,52 @@ def oracle_env_rollout(spec, mdp0: dict, phys: list[dict], actions: list[torch.T
         outs.append({"obs_policy": obs_p, "obs_critic": obs_c, "reward": out["reward"], "terminated": out["terminated"],
                      "truncated": out["truncated"], "mdp": {k: v.clone() for k, v in mdp.items()}})
     return outs
+
+
+def make_edge_case_state(spec, n: int = 64, seed: int = 4321) -> dict:
+    """Synthetic state whose first envs sit exactly ON the decision boundaries of the path:
+    upright / inverted / sideways base (gate 1, 0, 0), zero and threshold-norm commands, contact forces of exactly the
+    1 N / 100 N thresholds, +-inf ray hits, episode length one step before / at the time-out, root position exactly on
+    the terrain bound, contact / air timers exactly at step_dt and at the 0.5 s threshold, joints exactly on their
+    soft limits. The remaining envs keep the ordinary synthetic values (Go2 body layout assumed)."""
+    st = make_state(spec, n, seed=seed)
+    names = list(spec.layout.hist_body_names)
+    foot, calf = names.index("FL_foot"), names.index("FL_calf")
+    inf = float("inf")
+    q = st["root_quat_w"]
+    q[0] = torch.tensor([1.0, 0.0, 0.0, 0.0])                     # upright: gate 1
+    q[1] = torch.tensor([0.0, 1.0, 0.0, 0.0])                     # upside down: gate 0
+    q[2] = torch.tensor([0.5 ** 0.5, 0.5 ** 0.5, 0.0, 0.0])       # 90 deg roll: projected gravity z ~ 0
+    for e in (0, 1, 2):
+        st["root_lin_vel_w"][e] = 0.0
+        st["root_ang_vel_w"][e] = 0.0
+    st["command"][0] = 0.0                                        # standing still
+    st["command"][3] = torch.tensor([0.1, 0.0, 0.0])              # |cmd| == 0.1: strict comparisons on both sides
+    st["command"][4] = torch.tensor([0.06, 0.08, 0.0])            # |cmd| == 0.1 up to rounding
+    h = st["net_forces_w_history"]
+    h[5] = 0.0
+    h[5, 1, calf] = torch.tensor([1.0, 0.0, 0.0])                 # |F| == 1.0: NOT an undesired contact (strict >)
+    h[5, 2, foot] = torch.tensor([0.0, 0.0, 100.0])               # |F| == 100: contact_forces adds exactly 0
+    h[6] = 0.0
+    h[6, 0, calf] = torch.tensor([0.6, 0.8, 0.0])                 # 1.0 up to rounding
+    st["ray_hits_z"][7] = inf                                     # every ray misses: height scan clips to -1
+    st["ray_hits_z"][8] = -inf
+    st["ray_hits_z"][9, ::2] = inf
+    st["episode_length"][10] = spec.max_episode_length - 2        # 998 -> 999: no time-out
+    st["episode_length"][11] = spec.max_episode_length - 1        # 999 -> 1000: time-out
+    bound = [d.p for d in spec.dones if d.type_name == "terrain_out_of_bounds"]
+    if bound:
+        st["root_pos_w"][12, 0] = bound[0][0]                     # |x| == bound: strict >, stays in
+        st["root_pos_w"][12, 1] = 0.0
+        st["root_pos_w"][13, 0] = 0.0
+        st["root_pos_w"][13, 1] = -bound[0][1] - 1e-3             # just outside in y
+    dt = float(spec.step_dt)
+    st["current_contact_time"][14] = dt                           # first contact exactly one step ago
+    st["current_air_time"][14] = 0.0
+    st["last_air_time"][14] = 0.5                                 # feet_air_time: (last_air - 0.5) == 0
+    st["last_contact_time"][14] = 0.5
+    st["command"][14] = torch.tensor([0.5, 0.0, 0.0])
+    lims = torch.tensor(spec.layout.asset.soft_joint_pos_limits(), dtype=torch.float32)   # [J, 2]
+    st["joint_pos"][15] = lims[:, 0]                              # exactly on the lower soft limits: violation 0
+    st["joint_pos"][16] = lims[:, 1]                              # ... and on the upper ones
+    return st

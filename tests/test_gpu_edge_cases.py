@@ -1,0 +1,58 @@
+"""GPU counterpart of tests/test_oracle_edge_cases.py: the fused step and every reward term alone on envs that sit
+exactly on the decision boundaries of the path (gate 0 / 1, |cmd| == 0.1, |F| == 1 N / 100 N, +-inf ray hits, time-out
+edge, terrain bound, timers at step_dt / 0.5 s, joints on their soft limits), against the oracle.
+
+Written at the end of round 1 with no GPU time left to run it: marked xfail(strict=False) so that it reports (XPASS /
+xfail) without being able to stop the suite. Two envs are *rounding* ties by construction (|cmd| = |(0.06, 0.08, 0)|,
+|F| = |(0.6, 0.8, 0)|): if the kernel's left-to-right sum of squares and torch's vector norm round differently there,
+the affected terms flip a 0/1 factor - that would be a finding about tie-breaking, not about the formulas. Remove the
+marker once a GPU run has been recorded."""
+
+import pytest
+import torch
+
+import helpers as H
+from oracle import mdp_port as port
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="new at the end of round 1: not yet run on a GPU")]
+
+
+@pytest.mark.parametrize("key", ["go2_rough", "a1_flat"])
+def test_fused_step_on_boundary_envs(native_lib, key):
+    from robot_lab_b200.engine import MdpStepEngine
+
+    cfg, spec = H.make_spec(key)
+    st = H.make_edge_case_state(spec)
+    eng = MdpStepEngine(spec, "cuda:0")
+    b = eng.new_buffers(st["root_pos_w"].shape[0])
+    b.load_logical(st)
+    eng.step(b)
+    torch.cuda.synchronize()
+    got, ref = H.gpu_step_outputs(b), H.oracle_step(spec, st)
+    eng.close()
+    H.compare_outputs(got, ref)
+
+
+def test_every_reward_term_on_boundary_envs(native_lib):
+    from robot_lab_b200.engine import MdpStepEngine
+
+    cfg, spec = H.make_spec("go2_rough")
+    st = H.make_edge_case_state(spec)
+    n = st["root_pos_w"].shape[0]
+    st["terminated"] = torch.zeros(n, dtype=torch.bool)
+    eng = MdpStepEngine(spec, "cuda:0")
+    b = eng.new_buffers(n)
+    b.load_logical(st)
+    d = port.Derived(st, spec)
+    term_dev = st["terminated"].to(torch.uint8).cuda()
+    failures = []
+    for t in spec.rewards:
+        got = eng.term_eval(t, b, terminated=term_dev).cpu()
+        ref = port.reward_term(t, st, spec, d)
+        atol = 1e-6 * max(1.0, abs(t.p[0])) if t.type_name == "contact_forces" else H.ATOL
+        bad = (got - ref).abs() > atol + H.RTOL * ref.abs()
+        if bad.any():
+            failures.append(f"{t.name}: envs {bad.nonzero().flatten().tolist()[:8]} got {got[bad][:4].tolist()} want {ref[bad][:4].tolist()}")
+    eng.close()
+    assert not failures, "\n".join(failures)
