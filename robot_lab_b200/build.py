@@ -37,6 +37,7 @@ VARIANTS = {
     "shared_norms": ["-DRL_SHARED_NORMS=1"],               # contact-force norms computed once per env (prepass)
     "shared_ctx": ["-DRL_SHARED_CTX=1"],                   # the three root-frame rotations computed once per env
     "shared": ["-DRL_SHARED_NORMS=1", "-DRL_SHARED_CTX=1"],
+    "persistent": ["-DRL_PERSISTENT=1"],                    # a CTA walks several tiles: warm instructions from 16 k envs up
     # same source, no parallel split of the optimiser: --split-compile=0 produced two different codegen "modes" for the
     # same source in round 1; this is the reproducible build to A/B them against ("!" = drop a flag)
     "nosplit": ["!--split-compile=0"],

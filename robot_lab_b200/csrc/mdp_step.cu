@@ -78,6 +78,13 @@ constexpr int kTermParts = 2;
 #ifndef RL_SHARED_CTX
 #define RL_SHARED_CTX 0
 #endif
+// RL_PERSISTENT=1 (build variant persistent; not the default, not yet measured): a launch never has more CTAs than the
+// GPU holds at once; a CTA walks tiles blockIdx, blockIdx + gridDim, ... with the same code, so from its second tile on
+// the kernel's instructions are already in the SM's caches - the multi-wave regime (> ~4700 envs), where every wave of
+// fresh CTAs starts cold today (profiles/r1_summary.md section 5). One tile per CTA per iteration, record reused.
+#ifndef RL_PERSISTENT
+#define RL_PERSISTENT 0
+#endif
 
 struct FieldD {
   const void* ptr;
@@ -1267,7 +1274,7 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 //   store  : bulk stores for the observation rows, per-field loops for the SoA outputs; last CTA compacts reset ids
 // ---------------------------------------------------------------------------------------------------
 // the variants keep the second resident CTA per SM (<= 64 registers at 512 threads): without the hint ptxas took 104
-#if RL_SHARED_NORMS || RL_SHARED_CTX
+#if RL_SHARED_NORMS || RL_SHARED_CTX || RL_PERSISTENT
 #define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES, (NW * 32 * TILES <= 512) ? 2 : 1)
 #else
 #define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES)
@@ -1285,9 +1292,14 @@ __global__ void RL_STEP_BOUNDS mdp_step_kernel(const KArgs a) {
   // time (one instruction fetch per SM serves all of them). Everything below is written in terms of the virtual CTA.
   const int tile = (TILES > 1) ? (int)(threadIdx.x / NT) : 0;
   const int tid = (TILES > 1) ? (int)(threadIdx.x - tile * NT) : (int)threadIdx.x;
+#if RL_PERSISTENT
+  const int vb_first = (int)(blockIdx.x * TILES + tile);
+  const int vgrid = a.vgrid;
+#else
   const int vb = (TILES > 1) ? (int)(blockIdx.x * TILES + tile) : (int)blockIdx.x;        // virtual CTA = tile index
   const int vgrid = (TILES > 1) ? a.vgrid : (int)gridDim.x;
   if (TILES > 1 && vb >= vgrid) return;   // odd tile count: the spare half of the last CTA
+#endif
   float* const sm = sm_cta + (TILES > 1 ? (size_t)tile * (size_t)a.tile_words : (size_t)0);
   uint64_t& s_bar = s_bar_all[tile];
   int& s_last = s_last_all[tile];
@@ -1313,6 +1325,11 @@ __global__ void RL_STEP_BOUNDS mdp_step_kernel(const KArgs a) {
       return __syncthreads_or(pred);
     }
   };
+#if RL_PERSISTENT
+  for (int vb_it = vb_first; vb_it < vgrid; vb_it += (int)gridDim.x * TILES) {
+  const int vb = vb_it;   // the tile of this iteration; the body below is the one-tile kernel, "return" = next tile
+  [&]() __attribute__((always_inline)) {
+#endif
 #define RL_STAMP(i) do { if constexpr (DBG) { if (tid == 0) a.dbg[(size_t)vb * RL_DEBUG_STRIDE + (i)] = clock64(); } } while (0)
 #define RL_SUB(i) RL_STAMP(8 + RL_MAX_TASKS + 32 + (i))   /* finer stamps inside the load phase (debug build only) */
   RL_STAMP(0);
@@ -1763,6 +1780,11 @@ __global__ void RL_STEP_BOUNDS mdp_step_kernel(const KArgs a) {
   RL_STAMP(6);
   if ((ph & RL_PHASE_OBS) && nvalid > 0 && tid == 0) bulk_wait_read0();  // smem must outlive the bulk reads
   RL_STAMP(7);
+#if RL_PERSISTENT
+  }();
+  tile_sync();   // every thread is done with the record (bulk reads drained by thread 0 above): the next tile may load
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -2142,6 +2164,13 @@ int launch_step_variant(RlCtx* ctx, const KArgs& a_in, int n_items, cudaStream_t
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((vgrid + TILES - 1) / TILES); cfg.blockDim = dim3(NW * 32 * TILES); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+#if RL_PERSISTENT
+  {  // no more CTAs than are resident at once: two per SM when two records (and 2 x 512 threads x 64 registers) fit
+    const int per_sm = (TILES == 1 && NW * 32 <= 512 && 2 * (smem + 1024) <= (size_t)233472) ? 2 : 1;
+    const int resident = ctx->sm_count * per_sm;
+    if ((int)cfg.gridDim.x > resident) cfg.gridDim = dim3(resident);
+  }
+#endif
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
