@@ -1275,7 +1275,7 @@ __device__ __forceinline__ void store_u8(const float* sm, int off, const FieldD&
 // ---------------------------------------------------------------------------------------------------
 // the variants keep the second resident CTA per SM (<= 64 registers at 512 threads): without the hint ptxas took 104
 #if RL_SHARED_NORMS || RL_SHARED_CTX || RL_PERSISTENT
-#define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES, (NW * 32 * TILES <= 512) ? 2 : 1)
+#define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES, (P::kStatic && NW * 32 * TILES <= 512) ? 2 : 1)   /* the generic kernel keeps its registers */
 #else
 #define RL_STEP_BOUNDS __launch_bounds__(NW * 32 * TILES)
 #endif
