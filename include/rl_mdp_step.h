@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 11
+#define RL_ABI_VERSION 12
 
 #define RL_MAX_JOINTS 64
 #define RL_MAX_BODIES 64        /* bodies in the contact-force history tensor                  */
@@ -383,16 +383,24 @@ int64_t rl_tile_record_bytes(const RlStepSpec* spec);
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
-/* Tuning knobs: warps per tile (4, 8 or 16; 0 = default 16) and tiles per CTA. A tile is 32 consecutive envs (one
- * lane per env); its warps share the termination / reward / command / observation terms according to a static
- * schedule. envs_per_cta: 0 or 32 = one tile per CTA; 64 = two tiles per CTA (1024 threads: warps w and w + 16 run
- * the same task on neighbouring tiles, so an SM fetches the kernel's code once for 64 envs) - available for the
- * build-time specialised specs at 16 warps whose two tile records fit the shared memory of one CTA, otherwise
- * RL_EUNSUPPORTED. The environment variable RL_MDPSTEP_TILES=2 selects it at rl_ctx_create wherever it exists.
- * Synchronous (re-uploads the schedule): not for hot loops or stream capture. */
+/* Tuning knob of the general step kernel: warps per tile (4, 8 or 16; 0 = default 16). A tile is 32 consecutive envs
+ * (one lane per env); its warps share the termination / reward / command / observation terms according to a static
+ * schedule. envs_per_cta must be 0 or 32 (two tiles per CTA were measured slower in round 1 and removed; the cluster
+ * kernels below are what shares code between tiles). Build-time specialised specs have their own kernel at 16 warps;
+ * at 4 / 8 warps they run the generic one. Synchronous (re-uploads the schedule): not for hot loops or stream capture. */
 int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
-/* The configuration in effect (after rl_ctx_create's defaults / RL_MDPSTEP_TILES, or the last successful set). */
+/* The configuration of the general kernel in effect (after rl_ctx_create's defaults or the last successful set). */
 int rl_ctx_get_launch_config(const RlCtx* ctx, int* envs_per_cta, int* warps_per_tile);
+/* The two launches of an env step - rl_step(DONES | REWARDS | COMPACT) and rl_step(RESET | COMMAND | OBS) without an
+ * env-id list - have thread-block-cluster kernels for the build-time specialised specs (csrc/mdp_step_v2.cu): a cluster
+ * of C CTAs shares G tiles, CTA r evaluating the r-th share of the term list for all of them; SoA fields arrive by 2-D
+ * TMA tensor-map copies. A launch uses them when num_envs is a multiple of 32 * G, every staged field is an SoA tensor
+ * ({1, row stride}, 16-byte aligned) and the sensor rows are contiguous; anything else runs the general kernel with
+ * bit-identical results. This call reports what a launch of num_envs envs would use - *cluster_size = 0: the general
+ * kernel - and how many launches the cluster kernels have handled so far on this context (any pointer may be NULL).
+ * Environment: RL_MDPSTEP_V2=0 switches them off at rl_ctx_create, RL_MDPSTEP_V2_CFG="CxG" pins a configuration. */
+int rl_ctx_get_cluster_config(const RlCtx* ctx, int64_t num_envs, int32_t* cluster_size, int32_t* tiles_per_cta,
+                              int64_t* launches);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
@@ -445,8 +453,10 @@ int rl_reset_scene_state(RlCtx* ctx, int64_t num_envs, const RlResetStateCfg* cf
  * configures it at V/velocity_env_cfg.py:86 and updates it every physics sub-step, :726): the step immediately in
  * front of the path. For every env:
  *   - history: net_forces_w_history[:, 1:] = history[:, :-1]; history[:, 0] = net_forces_w      (ring_slot < 0)
- *     or, B200-native, only history[:, ring_slot] = net_forces_w (ring_slot in [0, T)): every consumer on the path
- *     takes max over the history axis, which does not depend on the order of the samples - no data is moved;
+ *     or, B200-native, only history[:, ring_slot] = net_forces_w (ring_slot in [0, T)): no data is moved. Every
+ *     consumer of the history takes the max over the history axis, which does not depend on the order of the samples -
+ *     EXCEPT feet_stumble (V/mdp/rewards.py:428-436), which reads net_forces_w = history[:, 0], the NEWEST sample: a
+ *     spec with an active feet_stumble term must use the rolling form (the Python providers check this);
  *   - air / contact timers of the tracked bodies, with is_contact = |F| > force_threshold:
  *       last_air        = first_contact ? current_air + dt     : last_air       (first_contact  = current_air > 0 & contact)
  *       current_air     = contact ? 0 : current_air + dt

@@ -23,8 +23,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-SOURCES = [CSRC / "mdp_step.cu", CSRC / "scene_kernels.cu"]
+SOURCES = [CSRC / "mdp_step.cu", CSRC / "mdp_step_v2.cu", CSRC / "scene_kernels.cu"]
 HEADERS = [ROOT / "include" / "rl_mdp_step.h", CSRC / "rl_common.cuh"]
+STEP_HEADERS = [CSRC / "mdp_terms.cuh", CSRC / "mdp_ctx.h"]   # shared by the two step-kernel translation units
 OUT = PKG / "_lib" / "libmdpstep.so"
 
 NVCC_FLAGS = [
@@ -33,14 +34,11 @@ NVCC_FLAGS = [
 ]
 
 
-VARIANTS = {
-    "shared_norms": ["-DRL_SHARED_NORMS=1"],               # contact-force norms computed once per env (prepass)
-    "shared_ctx": ["-DRL_SHARED_CTX=1"],                   # the three root-frame rotations computed once per env
-    "shared": ["-DRL_SHARED_NORMS=1", "-DRL_SHARED_CTX=1"],
-    "persistent": ["-DRL_PERSISTENT=1"],                    # a CTA walks several tiles: warm instructions from 16 k envs up
-    # same source, no parallel split of the optimiser: --split-compile=0 produced two different codegen "modes" for the
-    # same source in round 1; this is the reproducible build to A/B them against ("!" = drop a flag)
-    "nosplit": ["!--split-compile=0"],
+# Build variants: experimental configurations of a translation unit, built next to the default library as
+# ``_lib/libmdpstep_NAME.so`` and loaded with ``RL_MDPSTEP_LIB=...`` for A/B runs. (The round-1 variants shared_norms /
+# shared_ctx / persistent / nosplit were measured in round 2 - profiles/r2_variant_probe.txt - and removed.)
+VARIANTS: dict[str, list[str]] = {
+    "v2dev": ["-DRL_V2_DEV_ONE=1"],   # cluster kernels for Go2-rough only: seconds to compile while iterating on them
 }
 
 
@@ -49,30 +47,35 @@ def _obj(src: Path) -> Path:
 
 
 def build_variant(name: str, verbose: bool = False) -> Path:
-    """Compile csrc/mdp_step.cu with the variant's defines into its own object / library; scene_kernels.o is shared."""
+    """Compile the step-kernel translation units with the variant's defines into their own objects / library."""
     from . import codegen
 
     if name not in VARIANTS:
         raise KeyError(f"unknown variant '{name}'; known: {sorted(VARIANTS)}")
-    build()   # the default library (and scene_kernels.o) first
+    build()   # the default library (and the objects the variant shares with it) first
     codegen.write()
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    obj = OUT.parent / f"mdp_step.{name}.o"
     out = OUT.parent / f"libmdpstep_{name}.so"
-    drop = {f[1:] for f in VARIANTS[name] if f.startswith("!")}
-    flags = [f for f in NVCC_FLAGS if f not in drop] + [f for f in VARIANTS[name] if not f.startswith("!")]
-    cmd = [nvcc, *flags, "-c", str(SOURCES[0]), "-o", str(obj)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = " ".join(cmd) + "\n" + res.stdout + res.stderr
-    (OUT.parent / f"build.{name}.log").write_text(log)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{log[-4000:]}")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", str(obj), str(_obj(SOURCES[1])), "-o", str(out)]
+    flags = NVCC_FLAGS + VARIANTS[name]
+    objs = []
+    for src in SOURCES:
+        if src.name != "mdp_step_v2.cu":   # the variants so far only touch the cluster kernels
+            objs.append(_obj(src))
+            continue
+        obj = OUT.parent / f"{src.stem}.{name}.o"
+        cmd = [nvcc, *flags, "-c", str(src), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log = " ".join(cmd) + "\n" + res.stdout + res.stderr
+        (OUT.parent / f"build.{name}.log").write_text(log)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{log[-4000:]}")
+        if verbose:
+            print(log)
+        objs.append(obj)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *[str(o) for o in objs], "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout + res.stderr}")
-    if verbose:
-        print(log)
     return out
 
 
@@ -85,8 +88,12 @@ def needs_build() -> bool:
 
     gen = codegen.write()  # rewrites the baked specs only when the task cfgs changed
     common = HEADERS + [Path(__file__)]
-    deps = {SOURCES[0]: common + [SOURCES[0], gen], SOURCES[1]: common + [SOURCES[1]]}
+    deps = _deps(common, gen)
     return any(_stale(_obj(s), deps[s]) for s in SOURCES) or _stale(OUT, [_obj(s) for s in SOURCES if _obj(s).exists()] + common)
+
+
+def _deps(common: list[Path], gen: Path) -> dict[Path, list[Path]]:
+    return {src: common + [src] + (STEP_HEADERS + [gen] if src.name.startswith("mdp_step") else []) for src in SOURCES}
 
 
 def _compile(nvcc: str, src: Path) -> tuple[int, str]:
@@ -100,7 +107,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     gen = codegen.write()
     common = HEADERS + [Path(__file__)]
-    deps = {SOURCES[0]: common + [SOURCES[0], gen], SOURCES[1]: common + [SOURCES[1]]}
+    deps = _deps(common, gen)
     todo = [s for s in SOURCES if force or _stale(_obj(s), deps[s])]
     if not todo and not _stale(OUT, [_obj(s) for s in SOURCES]):
         return OUT

@@ -1,0 +1,992 @@
+// mdp_step_v2.cu - the two launches of an env step as thread-block-cluster kernels for sm_100a (B200).
+//
+// What profiles/r1_summary.md measured on the general kernel (csrc/mdp_step.cu) at 4096 envs: every SM runs one tile
+// and executes 35-41 KB of distinct code exactly once per launch; instruction supply, a 590-instruction load prologue
+// and the serial phases of a tile - not bytes - are the time. This file is the answer to that for the two launch
+// kinds an env step consists of (ManagerBasedRLEnv.step [IL]):
+//
+//   RL_V2_PRE   = DONES | REWARDS | COMPACT          (termination terms, reward terms, ordered reset ids)
+//   RL_V2_POST  = RESET (masked) | COMMAND | OBS     (manager reset of the done envs, command.compute, both obs groups)
+//
+//   * a cluster of C CTAs owns G tiles (32 G consecutive envs); CTA r of the cluster is ROLE r: it evaluates the r-th
+//     share of the term list for all G tiles. A CTA has 16 warps = G tiles x W task slots; warp (tile, slot) runs the
+//     tasks of bin role*W + slot for its tile, lane = env. An SM therefore executes 1/C of the term code and every
+//     instruction serves G warps; the code an SM sees is the same in every launch (role = cluster rank, placement is
+//     deterministic), so it stays in that SM's instruction cache across launches;
+//   * load: ONE thread issues a 2-D TMA tensor-map copy per SoA field ({32 G envs} x {components} box of the [C, N]
+//     tensor, SASS UTMALDG) and one 1-D bulk copy for the contact-force rows; nobody else touches the load path;
+//   * contact-force norms (max over the history of |F_b|) are computed once per env by a prepass of the role that holds
+//     their consumers and cached in the record (every consumer used to recompute them in its own serial chain);
+//   * results leave from registers: lane = env makes every SoA result row a coalesced 128-byte store by the warp that
+//     produced it - there is no store phase; the weighted term values meet in role 0's shared memory through DSMEM
+//     (st.shared::cluster) and one cluster barrier, where one warp per tile adds them up in manager order - the same
+//     summation order as the general kernel and the reference (RewardManager.compute [IL]);
+//   * the height-scan observation (187 of the 235 critic columns) never enters shared memory: every warp of the cluster
+//     streams env rows global -> registers -> global with lanes = columns while the TMA loads are still in flight.
+//
+// Same term functions (csrc/mdp_terms.cuh), same operand order as the general kernel: all results are bit-identical to
+// it (tests/test_gpu_v2_parity.py). Launches that do not qualify (ragged env counts, env-id lists, strided IsaacLab
+// tensors, a spec that is not baked) run the general kernel.
+
+#include "mdp_ctx.h"
+
+#include <cuda.h>
+
+#ifndef RL_V2_DEV_ONE
+#define RL_V2_DEV_ONE 0   // development builds: compile the cluster kernels for Go2-rough only (seconds instead of minutes)
+#endif
+
+namespace {
+
+constexpr int kWarps2 = 16;
+constexpr int kThreads2 = kWarps2 * 32;
+
+// ---------------------------------------------------------------------------------------------------
+// Which input fields a launch kind stages (the sets fill_args() of the general kernel uses for the same phases)
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t v2_field_mask(const RlStepSpec& s, int kind) {
+  uint32_t m = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_JPOS) |
+               (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN) | (1u << IF_ACT);
+  if (kind == RL_V2_PRE) {
+    m |= (1u << IF_PACT) | (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) |
+         (1u << IF_LCON) | (1u << IF_BPOS) | (1u << IF_BVEL) | (1u << IF_SUMS);
+  } else {
+    m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU) | (1u << IF_SUMS);
+    if (s.num_rays > 0) m |= 1u << IF_RAYPOS;
+  }
+  for (int f = 0; f < IF_COUNT; ++f)
+    if (in_field_ncomp(s, f) <= 0) m &= ~(1u << f);
+  return m;
+}
+
+// index of the group's height-scan term (must be its last term: checked by v2_spec_ok) or -1
+__host__ __device__ constexpr int scan_term_of(const RlObsGroup& G) {
+  for (int t = 0; t < G.n_terms; ++t)
+    if (G.terms[t].type == RL_OBS_HEIGHT_SCAN) return t;
+  return -1;
+}
+// columns of a group row that are assembled per env in shared memory (everything but the streamed height scan)
+__host__ __device__ constexpr int env_cols_of(const RlObsGroup& G) {
+  const int st = scan_term_of(G);
+  return st < 0 ? G.dim : G.dim - G.terms[st].dim;
+}
+
+// what the cluster kernels cover (everything else runs the general kernel)
+__host__ __device__ constexpr bool v2_spec_ok(const RlStepSpec& s) {
+  for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+    const RlObsGroup& G = s.obs[g];
+    int scans = 0;
+    for (int t = 0; t < G.n_terms; ++t)
+      if (G.terms[t].type == RL_OBS_HEIGHT_SCAN) {
+        ++scans;
+        if (t != G.n_terms - 1) return false;                          // streamed columns must end the row
+        if (G.terms[t].has_noise && G.enable_corruption) return false;   // noise is generated lane = env
+      }
+    if (scans > 1) return false;
+  }
+  if (s.num_hist_bodies > 0 && s.hist_len <= 0) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Record layout of a CTA: 32 G envs; the term functions address it through the same Layout members as the general
+// kernel (SoA word w of env e at sm[w*E + e]).
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const int E, const int kind) {
+  Layout L{};
+  L.E = E;
+  int w = 0;
+  auto take = [&w](int n) { int o = w; w += n; return o; };
+  const int J = s.num_joints, A = s.action.n_actions, K = s.num_reward_terms;
+  L.A = A; L.J = J; L.K = K;
+  const uint32_t mask = v2_field_mask(s, kind);
+  int iw[IF_COUNT] = {};
+  for (int f = 0; f < IF_COUNT; ++f) iw[f] = ((mask >> f) & 1u) ? take(in_field_ncomp(s, f)) : 0;
+  L.root_pos = iw[IF_ROOT_POS] * E; L.quat = iw[IF_QUAT] * E; L.lin_vel = iw[IF_LIN_VEL] * E; L.ang_vel = iw[IF_ANG_VEL] * E;
+  L.jpos = iw[IF_JPOS] * E; L.jvel = iw[IF_JVEL] * E; L.jacc = iw[IF_JACC] * E; L.jtau = iw[IF_JTAU] * E;
+  L.cair = iw[IF_CAIR] * E; L.lair = iw[IF_LAIR] * E; L.ccon = iw[IF_CCON] * E; L.lcon = iw[IF_LCON] * E;
+  L.bpos = iw[IF_BPOS] * E; L.bvel = iw[IF_BVEL] * E; L.raypos = iw[IF_RAYPOS] * E;
+  L.cmd = iw[IF_CMD] * E; L.head = iw[IF_HEAD] * E; L.tleft = iw[IF_TLEFT] * E;
+  L.mxy = iw[IF_MXY] * E; L.myaw = iw[IF_MYAW] * E; L.eplen = iw[IF_EPLEN] * E;
+  L.sums = iw[IF_SUMS] * E; L.cmdu = iw[IF_CMDU] * E; L.act = iw[IF_ACT] * E; L.pact = iw[IF_PACT] * E;
+  L.w_sums = iw[IF_SUMS];
+  L.ishead = take(1) * E; L.isstand = take(1) * E; L.rmask = take(1) * E;
+  L.cmdn = take(3) * E; L.epnew = take(1) * E; L.flags = take(1) * E;
+  if (kind == RL_V2_PRE) {
+    L.termv = take(K) * E;                      // role 0: weighted value of every term (DSMEM target)
+    L.hnorm = take(s.num_hist_bodies) * E;      // cached contact-force norms
+  }
+  L.soa_words = w;
+  int off = align_up(w * E, 32);
+  L.cj = off; off = align_up(off + 5 * J, 32);
+  if (kind == RL_V2_PRE) {
+    L.hist_pitch = s.hist_len * s.num_hist_bodies * 3;   // dense rows: one bulk copy; only the norm prepass reads them
+    L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
+  } else {
+    L.obs_pitch0 = odd_pitch(env_cols_of(s.obs[0])); L.obs_pitch1 = odd_pitch(env_cols_of(s.obs[1]));
+    L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
+    L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+  }
+  L.total_words = off;
+  return L;
+}
+// record word a field is staged at (host side of the TMA issue loop)
+__host__ __device__ constexpr int v2_field_word(const RlStepSpec& s, int kind, int f) {
+  const uint32_t mask = v2_field_mask(s, kind);
+  int w = 0;
+  for (int i = 0; i < f; ++i)
+    if ((mask >> i) & 1u) w += in_field_ncomp(s, i);
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Schedule: tasks -> bins (bin = role * W + slot). Longest-processing-time greedy with two placement rules:
+//   PRE : the termination terms and every consumer of contact-force norms live in role 0 (it stages the force rows,
+//         runs the norm prepass and owns the final sum); everything else is balanced over all bins;
+//   POST: the command task lives in role 0, slot 0; the per-env columns of observation group g are assembled by role
+//         owner(g) (policy: role 1 if it exists, critic: role 2 if it exists, else role 0).
+// ---------------------------------------------------------------------------------------------------
+struct Sched2 {
+  int n;
+  Task t[RL_MAX_TASKS];
+  uint64_t late;          // reward terms finished by the final sum (is_terminated)
+  uint32_t hist_roles;    // roles that stage the contact-force rows and run the norm prepass
+  int obs_owner[RL_NUM_OBS_GROUPS];
+};
+
+__host__ __device__ constexpr bool term_uses_hist(const RlRewardTerm& t) {
+  return t.type == RL_REW_UNDESIRED_CONTACTS || t.type == RL_REW_CONTACT_FORCES || t.type == RL_REW_FEET_SLIDE ||
+         t.type == RL_REW_FEET_STUMBLE;
+}
+__host__ __device__ constexpr bool dones_use_hist(const RlStepSpec& s) {
+  for (int d = 0; d < s.num_done_terms; ++d)
+    if (s.dones[d].type == RL_DONE_ILLEGAL_CONTACT) return true;
+  return false;
+}
+
+__host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int kind, int C, int W, int G) {
+  Sched2 sc{};
+  int cost[RL_MAX_TASKS] = {};
+  int lo_bin[RL_MAX_TASKS] = {}, hi_bin[RL_MAX_TASKS] = {};   // bins a task may go to: [lo, hi)
+  const int BINS = C * W;
+  int n = 0;
+  int load[64] = {};
+  sc.obs_owner[0] = C > 1 ? 1 : 0;
+  sc.obs_owner[1] = C > 2 ? 2 : 0;
+  if (kind == RL_V2_PRE) {
+    bool any_hist = dones_use_hist(s);
+    sc.t[n] = Task{TK_DONES, 0, 0, 0, 0, 0, 0, 0}; cost[n] = 120; lo_bin[n] = 0; hi_bin[n] = W; ++n;
+    for (int k = 0; k < s.num_reward_terms; ++k) {
+      const RlRewardTerm& t = s.rewards[k];
+      if (t.weight == 0.f) continue;
+      if (t.type == RL_REW_IS_TERMINATED) { sc.late |= 1ull << k; continue; }
+      const bool body_sum = (t.type == RL_REW_UNDESIRED_CONTACTS || t.type == RL_REW_CONTACT_FORCES);
+      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 1, 0};
+      cost[n] = 60 + reward_cost(t, s, body_sum ? popc64(t.body_mask) : t.n_idx, true);
+      const bool h = term_uses_hist(t) && s.num_hist_bodies > 0;
+      any_hist = any_hist || h;
+      lo_bin[n] = 0; hi_bin[n] = h ? W : BINS;
+      ++n;
+    }
+    if (any_hist) {
+      sc.hist_roles = 1u;
+      // what the prepass costs every warp of role 0 before its tasks start
+      const int pre = ((G * s.num_hist_bodies + kWarps2 - 1) / kWarps2) * (s.hist_len * 18 + 12) + 40;
+      for (int b = 0; b < W; ++b) load[b] = pre;
+    }
+    for (int b = 0; b < W; ++b) load[b] += 80;   // role 0 also runs the final sum and the compaction tail
+  } else {
+    {
+      int c = 520;  // manager reset bookkeeping + command update + heading control
+      for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g)
+        for (int ti = 0; ti < s.obs[g].n_terms; ++ti)
+          if (s.obs[g].terms[ti].type == RL_OBS_GENERATED_COMMANDS) c += 40;
+      sc.t[n] = Task{TK_COMMAND, 0, 0, 0, 0, 0, 0, 0}; cost[n] = c; lo_bin[n] = 0; hi_bin[n] = 1; ++n;
+    }
+    for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
+      int col0 = 0;
+      for (int ti = 0; ti < s.obs[g].n_terms; ++ti) {
+        const RlObsTerm& o = s.obs[g].terms[ti];
+        const int per_col = 8 + ((o.has_noise && s.obs[g].enable_corruption) ? 24 : 0);
+        if (o.type != RL_OBS_GENERATED_COMMANDS && o.type != RL_OBS_HEIGHT_SCAN) {
+          constexpr int chunk = 32;   // multiples of 4 (one Philox block = 4 columns)
+          for (int lo = 0; lo < o.dim; lo += chunk) {
+            const int hi = (lo + chunk < o.dim) ? lo + chunk : o.dim;
+            if (n >= RL_MAX_TASKS) break;
+            sc.t[n] = Task{TK_OBS, (uint8_t)g, (uint8_t)ti, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)col0, 0};
+            cost[n] = 20 + per_col * (hi - lo);
+            lo_bin[n] = sc.obs_owner[g] * W; hi_bin[n] = lo_bin[n] + W;
+            ++n;
+          }
+        }
+        col0 += o.dim;
+      }
+    }
+  }
+  sc.n = n;
+  // longest-processing-time greedy; the constrained tasks first so that the free ones balance around them
+  bool done[RL_MAX_TASKS] = {};
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int it = 0; it < n; ++it) {
+      int best = -1;
+      for (int i = 0; i < n; ++i) {
+        const bool constrained = (hi_bin[i] - lo_bin[i]) < BINS;
+        if (done[i] || constrained != (pass == 0)) continue;
+        if (best < 0 || cost[i] > cost[best]) best = i;
+      }
+      if (best < 0) break;
+      int w = lo_bin[best];
+      for (int j = lo_bin[best]; j < hi_bin[best]; ++j)
+        if (load[j] < load[w]) w = j;
+      sc.t[best].owner = (uint8_t)w; load[w] += cost[best]; done[best] = true;
+    }
+  }
+  return sc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers of the cluster kernels
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// generic address of `p` (a pointer into this CTA's shared memory) in CTA `rank` of the cluster
+template <class T> __device__ __forceinline__ T* map_to_rank(T* p, uint32_t rank) {
+  uint64_t r;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"(reinterpret_cast<uint64_t>(p)), "r"(rank));
+  return reinterpret_cast<T*>(r);
+}
+// 2-D tiled tensor-map copy global -> shared (SASS UTMALDG), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+struct alignas(64) V2Args {
+  KArgs k;                  // the parameter block of the general kernel (pointers, strides, phases, random streams)
+  uint32_t soa_bytes;       // bytes the tensor-map copies of one CTA deliver
+  uint32_t tm_mask;         // fields staged by a tensor map
+  int32_t field_word[IF_COUNT];
+  alignas(64) CUtensorMap tm[IF_COUNT];
+};
+
+template <class B, int KIND, int C, int G>
+struct Cfg2 {
+  static_assert(kWarps2 % G == 0, "tiles per CTA must divide the warp count");
+  static constexpr int W = kWarps2 / G;   // task slots per (role, tile)
+  static constexpr int E = 32 * G;        // envs per cluster
+  static constexpr int BINS = C * W;
+  static constexpr Layout L = make_layout_v2(B::spec, E, KIND);
+  static constexpr Sched2 sched = make_schedule_v2(B::spec, KIND, C, W, G);
+  static constexpr Scalars S = scalars_of(B::spec);
+  // scalar copies: device code must not odr-use the schedule object itself
+  static constexpr int n_tasks = sched.n;
+  static constexpr uint64_t late = sched.late;
+  static constexpr uint32_t hist_roles = sched.hist_roles;
+  static constexpr int obs_owner0 = sched.obs_owner[0], obs_owner1 = sched.obs_owner[1];
+};
+
+// all tasks of one bin, in schedule order, behind ONE per-env context (members no task of the bin reads fold away)
+template <class B, class CF, int BIN, class F>
+__device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f) {
+  constexpr Layout L = CF::L;
+  const EnvCtx c = make_ctx(sm, L, e);
+  static_for(std::make_integer_sequence<int, CF::n_tasks>{}, [&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr Task tk = CF::sched.t[i];
+    if constexpr (tk.owner == BIN) {
+      static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
+      static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
+      constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+      f(ic, tk, rt, ot, corrupt, c);
+    }
+  });
+}
+template <class B, class CF, int LO, int HI, class F>
+__device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, const int e, F&& f) {
+  if constexpr (HI - LO == 1) {
+    bin_tasks<B, CF, LO>(sm, e, f);
+  } else {
+    constexpr int MID = (LO + HI) / 2;
+    if (bin < MID) dispatch_bin<B, CF, LO, MID>(bin, sm, e, f); else dispatch_bin<B, CF, MID, HI>(bin, sm, e, f);
+  }
+}
+
+// the load every CTA starts with: one thread, one instruction per field
+template <class CF>
+__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const int env0, uint64_t* bar, const bool with_hist) {
+  constexpr Layout L = CF::L;
+  constexpr Scalars S = CF::S;
+  constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
+  mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  uint32_t bytes = a.soa_bytes;
+  if (with_hist) bytes += (uint32_t)(CF::E * HW * 4);
+  mbar_expect_tx(bar, bytes);
+#pragma unroll 1
+  for (uint32_t m = a.tm_mask; m != 0; m &= m - 1) {
+    const int f = __ffs((int)m) - 1;
+    tma_load_2d(sm + a.field_word[f] * CF::E, &a.tm[f], env0, 0, bar);
+  }
+  if (with_hist)
+    bulk_g2s(sm + L.hist, static_cast<const float*>(a.k.hist.ptr) + (size_t)env0 * HW, (uint32_t)(CF::E * HW * 4), bar);
+}
+
+// reset_buf.nonzero() [IL]: ascending reset ids from one 32-bit done mask per tile (runs in the ONE CTA whose ticket
+// was the last of the launch; same result as the general kernel's tail)
+__device__ __noinline__ void compact_reset_ids(const KArgs& a, const int n_tiles, int* s_cnt, const int tid) {
+  const int warp = tid >> 5, e = tid & 31;
+  int run = 0;
+#pragma unroll 1
+  for (int base = 0; base < n_tiles; base += kThreads2) {
+    const int g = base + tid;
+    unsigned m = (g < n_tiles) ? __ldcg(a.cta_mask + g) : 0u;
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (e >= d) incl += y; }
+    if (e == 31) s_cnt[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int wt = (e < kWarps2) ? s_cnt[e] : 0, wi = wt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wi, d); if (e >= d) wi += y; }
+      if (e < kWarps2) s_cnt[e] = wi - wt;
+      if (e == 31) s_cnt[32] = wi;
+    }
+    __syncthreads();
+    int pos = run + s_cnt[warp] + incl - cnt;
+    if (a.out.reset_ids)
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        a.out.reset_ids[pos++] = g * kE + b;
+      }
+    run += s_cnt[32];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (a.out.n_reset) *a.out.n_reset = run;
+    *a.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PRE: TerminationManager.compute + RewardManager.compute [IL] + reset_buf.nonzero()
+// ---------------------------------------------------------------------------------------------------
+template <class B, int C, int G>
+__global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const __grid_constant__ V2Args a) {
+  using CF = Cfg2<B, RL_V2_PRE, C, G>;
+  constexpr Layout L = CF::L;
+  constexpr Scalars S = CF::S;
+  constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms;
+  constexpr bool CN = true;   // HIST_MAX_NORM reads the cached norms
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_last;
+  __shared__ int s_cnt[40];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = warp / W, slot = warp - tile * W;
+  const int e = tile * 32 + lane;
+  const uint32_t role = C > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = (int)blockIdx.x / C;
+  const int env0 = cluster_id * E;
+  const long long env = (long long)env0 + e;
+  const bool my_hist = ((CF::hist_roles >> role) & 1u) != 0 && S.num_hist_bodies > 0;
+  if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
+  if (tid == 0) {
+    s_last = 0;
+    issue_loads<CF>(sm, a, env0, &s_bar, my_hist);
+  }
+  // per-joint constants: constant bank -> shared
+  for (int i = tid; i < S.num_joints; i += kThreads2)
+    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
+      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
+      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
+    });
+  if (role == 0)   // weight-0 terms: no task writes their slot of the final sum
+    for (int i = tid; i < K * E; i += kThreads2)
+      if ((a.k.rw_zero >> (i / E)) & 1ull) sm[L.termv + i] = 0.f;
+  __syncthreads();           // mbarrier init + the stores above visible to the CTA
+  mbar_wait(&s_bar, 0);      // record resident
+  if (my_hist) {
+    // contact-force norm prepass: (tile, body) items over the warps, lane = env; ONE code copy for every consumer
+    constexpr int Bh = S.num_hist_bodies;
+#pragma unroll 1
+    for (int it = warp; it < G * Bh; it += kWarps2) {
+      const int t = it / Bh, b = it - t * Bh;
+      const int ee = t * 32 + lane;
+      sm[L.hnorm + b * E + ee] = hist_max_norm(sm + L.hist + ee * L.hist_pitch, S.hist_len, Bh, b);
+    }
+    __syncthreads();
+  }
+  if (C > 1) cluster_wait_acquire();
+
+  float* const termv0 = C > 1 ? map_to_rank(sm + L.termv, 0u) : sm + L.termv;   // role 0's term values
+  const FieldD f_sums = a.k.outf[OF_SUMS], f_stepr = a.k.outf[OF_STEPR];
+  unsigned early_prev = 0xffffffffu;
+  dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
+      [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm&, const bool, const EnvCtx& c) __attribute__((always_inline)) {
+    if (tk.kind == TK_REWARD) {
+      const int k = tk.a;
+      const float raw = reward_term<CN>(rt, c_spec[a.k.slot].rewards[tk.a], S, L, sm, e, c, 0, 64);
+      // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
+      const float val = (raw * rt.weight) * S.step_dt;
+      termv0[k * E + e] = val;
+      static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)k * f_sums.cs + env] = SMF(L.sums, k) + val;
+      if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = rl_div(val, S.step_dt);
+    } else if (tk.kind == TK_DONES) {
+      // TerminationManager.compute [IL]: bits | terminated << 8 | time_out << 9
+      const int eplen_now = __float_as_int(SMF(L.eplen, 0)) + 1;
+      static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = eplen_now;
+      uint32_t bits = 0, term = 0, trunc = 0;
+      StaticPolicy<B>::for_dones(a.k, [&](const RlDoneTerm& t, int d) __attribute__((always_inline)) {
+        int fired = 0;
+        if (t.type == RL_DONE_TIME_OUT) {
+          fired = eplen_now >= S.max_episode_length;
+        } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
+          fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
+        } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
+          _Pragma("unroll 1")
+          for (int b = 0; b < S.num_hist_bodies; ++b)
+            if (((t.body_mask >> b) & 1ull) && (SMF(L.hnorm, b) > t.p[0])) fired = 1;
+        }
+        if (fired) { bits |= 1u << d; if (t.time_out) trunc = 1; else term = 1; }
+      });
+      SMF(L.flags, 0) = __int_as_float((int)(bits | (term << 8) | (trunc << 9)));
+      if (a.k.out.done_bits) a.k.out.done_bits[env] = (uint8_t)bits;
+      if (a.k.out.terminated) a.k.out.terminated[env] = (uint8_t)term;
+      if (a.k.out.truncated) a.k.out.truncated[env] = (uint8_t)trunc;
+      // the tile's done mask and its ticket, long before the tail looks at the answer
+      const unsigned m = __ballot_sync(0xffffffffu, (term | trunc) != 0);
+      if (lane == 0) {
+        a.k.cta_mask[cluster_id * G + tile] = m;
+        early_prev = ticket_arrive_release(a.k.ticket);
+      }
+    }
+  });
+  if (lane == 0 && early_prev == (unsigned)(a.k.vgrid - 1)) s_last = 1;   // this tile's ticket was the last of the launch
+  if (C > 1) { cluster_arrive_release(); if (role != 0) return; cluster_wait_acquire(); }
+  __syncthreads();   // the term values of role 0's own warps, the termination flags, s_last
+
+  // ---- final sum: one warp per tile adds the weighted values up in manager order (is_terminated is finished here) ----
+  if (slot == 0) {
+    const int fl = __float_as_int(SMF(L.flags, 0));
+    if (CF::late != 0) {
+#pragma unroll 1
+      for (uint64_t m = CF::late; m != 0; m &= m - 1) {
+        const int k = __ffsll((long long)m) - 1;
+        const float raw = ((fl >> 8) & 1) ? 1.f : 0.f;
+        const float val = (raw * a.k.rw_weight[k]) * S.step_dt;
+        SMF(L.termv, k) = val;
+        static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)k * f_sums.cs + env] = SMF(L.sums, k) + val;
+        if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = rl_div(val, S.step_dt);
+      }
+    }
+    float total = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) total += SMF(L.termv, k);   // manager order
+    if (a.k.out.reward) a.k.out.reward[env] = total;
+    if (f_stepr.ptr)
+#pragma unroll 1
+      for (uint64_t m = a.k.rw_zero; m != 0; m &= m - 1)
+        static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)(__ffsll((long long)m) - 1) * f_stepr.cs + env] = 0.f;
+  }
+  if (s_last) {   // CTA-uniform: ordered compaction of the reset ids by the CTA that arrived last
+    __threadfence();
+    compact_reset_ids(a.k, a.k.vgrid, s_cnt, tid);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// POST: ManagerBasedRLEnv._reset_idx (manager part) for the done envs + CommandManager.compute +
+// ObservationManager.compute [IL] for all envs
+// ---------------------------------------------------------------------------------------------------
+template <class B, int C, int G>
+__global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(const __grid_constant__ V2Args a) {
+  using CF = Cfg2<B, RL_V2_POST, C, G>;
+  constexpr Layout L = CF::L;
+  constexpr Scalars S = CF::S;
+  constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms, A = S.n_actions;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = warp / W, slot = warp - tile * W;
+  const int e = tile * 32 + lane;
+  const uint32_t role = C > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = (int)blockIdx.x / C;
+  const int env0 = cluster_id * E;
+  const long long env = (long long)env0 + e;
+  if (C > 1) cluster_arrive_relaxed();
+  if (tid == 0) {
+    s_last = 0;
+    issue_loads<CF>(sm, a, env0, &s_bar, false);
+  }
+  // byte flags of this lane's env (every role needs the reset mask; role 0 also the command flags)
+  const int u8_reset = (a.k.out.terminated[env] | a.k.out.truncated[env]) != 0;
+  int u8_head = 0, u8_stand = 0, u8_bits = 0;
+  if (role == 0 && slot == 0) {
+    u8_head = static_cast<const uint8_t*>(a.k.is_heading.ptr)[env];
+    u8_stand = static_cast<const uint8_t*>(a.k.is_standing.ptr)[env];
+    if (a.k.out.done_bits) u8_bits = a.k.out.done_bits[env];
+  }
+  RandState rs;
+  rs.seed = a.k.rnd.seed;
+  rs.step = a.k.rnd.step + (a.k.rnd.step_counter ? *a.k.rnd.step_counter : 0ull);
+  rs.env_id_offset = a.k.rnd.env_id_offset;
+
+  // ---- height scan: global -> registers -> global, lanes = columns, while the record is still in flight ----------
+  // height_scan [IL] = sensor z - ray hit z - offset, then clip, then scale (no noise: v2_spec_ok)
+  static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
+    constexpr int g = decltype(gc)::value;
+    constexpr int st = scan_term_of(B::spec.obs[g]);
+    if constexpr (st >= 0) {
+      static constexpr RlObsTerm t = B::spec.obs[g].terms[st];
+      constexpr int col0 = obs_col0(B::spec.obs[g], st);
+      constexpr int R = t.dim;
+      if (a.k.out.obs[g] != nullptr) {
+        constexpr int rows_per_cta = E / C;   // this role's share of the cluster's env rows
+        const float* rays = static_cast<const float*>(a.k.rays.ptr);
+        const float* rz = static_cast<const float*>(a.k.in[IF_RAYPOS].ptr);
+#pragma unroll 1
+        for (int r = warp; r < rows_per_cta; r += kWarps2) {
+          const long long ev = (long long)env0 + (int)role * rows_per_cta + r;
+          const float z = __ldg(rz + ev);
+          const float* src = rays + ev * R;
+          float* dst = a.k.out.obs[g] + ev * a.k.out.obs_pitch[g] + col0;
+#pragma unroll
+          for (int c0 = 0; c0 < R; c0 += 32) {
+            const int col = c0 + lane;
+            if (col < R) {
+              float v = (z - __ldg(src + col)) - t.p[0];
+              if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
+              if (t.has_scale) v = v * t.scale;
+              dst[col] = v;
+            }
+          }
+        }
+      }
+    }
+  });
+
+  for (int i = tid; i < S.num_joints; i += kThreads2)
+    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
+      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
+      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
+    });
+  if (slot == 0) {
+    sm[L.rmask + e] = __int_as_float(u8_reset);
+    if (role == 0) {
+      sm[L.ishead + e] = __int_as_float(u8_head); sm[L.isstand + e] = __int_as_float(u8_stand);
+      sm[L.flags + e] = __int_as_float(u8_bits);
+    }
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
+  // ---- manager reset of the envs flagged done (RewardManager / ActionManager / CommandTerm .reset [IL]) -----------
+  // every role: what its own tasks read (stored actions, episode length); role 0: logging, zeroing, command resample
+  const bool rme = u8_reset != 0;
+  unsigned early_prev = 0xffffffffu;
+  const int n_tiles = a.k.N / 32;
+  if (role == 0) {
+    // logging partials of the tile (combined by the last tile to arrive, in a fixed order -> deterministic):
+    // quantity q is reduced over the lanes (= envs) of one warp with a fixed shuffle tree
+    const int tile_resets = __syncthreads_or(rme);   // CTA-uniform: anything to reset in these G tiles?
+    const int gt = cluster_id * G + tile;
+    if (!tile_resets) {
+      if (slot == 0) {
+        for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;
+        __syncwarp();
+        if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);
+      }
+    } else {
+#pragma unroll 1
+      for (int q = slot; q < K + RL_MAX_DONE_TERMS + 2; q += W) {
+        float x = 0.f;
+        if (rme) {
+          if (q < K) x = sm[L.sums + q * E + e];
+          else if (q < K + RL_MAX_DONE_TERMS)
+            x = (a.k.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + e]) >> (q - K)) & 1) : 0.f;
+          else x = sm[(q == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + e];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
+      }
+      __syncthreads();   // the partials of every slot of a tile are written
+      if (slot == 0 && lane == 0) early_prev = ticket_arrive_release(a.k.ticket);
+      if (rme) {
+        // zero the episode sums / stored actions of the reset envs in global memory (the record copy is dead after
+        // the logging reduction above; nobody in this launch reads the sums again)
+        float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
+        float* ga = static_cast<float*>(const_cast<void*>(a.k.outf[OF_ACT].ptr));
+        float* gp = static_cast<float*>(const_cast<void*>(a.k.outf[OF_PACT].ptr));
+#pragma unroll 1
+        for (int k = slot; k < K; k += W) gs[(size_t)k * a.k.outf[OF_SUMS].cs + env] = 0.f;
+#pragma unroll 1
+        for (int q = slot; q < A; q += W) {
+          ga[(size_t)q * a.k.outf[OF_ACT].cs + env] = 0.f;
+          gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
+        }
+      }
+      if (slot == 0 && rme) {
+        sm[L.mxy + e] = 0.f; sm[L.myaw + e] = 0.f;
+        constexpr RlCommandCfg cc = B::spec.command;
+        float u[RL_NUM_CMD_UNIFORMS];
+        if (a.k.rnd.cmd_uniforms != nullptr) {
+#pragma unroll
+          for (int q = 0; q < RL_NUM_CMD_UNIFORMS; ++q) u[q] = sm[L.cmdu + q * E + e];
+        } else {
+          const uint4 r0 = rl_philox(rs, env, RL_STREAM_RESET_COMMAND, 0), r1 = rl_philox(rs, env, RL_STREAM_RESET_COMMAND, 1);
+          u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
+          u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
+        }
+        float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
+        float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
+        const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
+        const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+        c0 *= keep; c1 *= keep;
+        sm[L.cmd + 0 * E + e] = c0; sm[L.cmd + 1 * E + e] = c1; sm[L.cmd + 2 * E + e] = c2;
+        sm[L.tleft + e] = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
+        if (cc.heading_command) {
+          sm[L.head + e] = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
+          sm[L.ishead + e] = __int_as_float((u[5] <= cc.rel_heading_envs) ? 1 : 0);
+        }
+        sm[L.isstand + e] = __int_as_float((u[6] <= cc.rel_standing_envs) ? 1 : 0);
+      }
+    }
+  }
+  // every role: its own copy of what a reset changes for the observation terms
+  if (rme) {
+#pragma unroll 1
+    for (int q = slot; q < A; q += W) sm[L.act + q * E + e] = 0.f;
+    if (slot == 0) sm[L.eplen + e] = __int_as_float(0);
+  }
+  if (role == 0 && slot == 0 && rme) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
+  __syncthreads();
+  if (C > 1) cluster_wait_acquire();
+
+  // ---- tasks ----------------------------------------------------------------------------------------------------
+  const int eplen_now = __float_as_int(SMF(L.eplen, 0));
+  dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
+      [&](auto, const Task& tk, const RlRewardTerm&, const RlObsTerm& ot, const bool corrupt, const EnvCtx& c) __attribute__((always_inline)) {
+    if (tk.kind == TK_OBS) {
+      if (a.k.out.obs[tk.a] == nullptr) return;
+      obs_task(sm, L, S, ot, c_spec[a.k.slot].obs[tk.a].terms[tk.b], corrupt, a.k, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
+    } else if (tk.kind == TK_COMMAND) {
+      // CommandManager.compute + the observation columns that show the new command (written into their owners' rows)
+      command_update(sm, L, S, StaticPolicy<B>::command(a.k), a.k, rs, e, env, c, true);
+      StaticPolicy<B>::for_cmd_obs(a.k, [&](const RlObsTerm& t, int g, int ti, int col0, bool corr) __attribute__((always_inline)) {
+        if (a.k.out.obs[g] == nullptr) return;
+        const uint32_t owner = (uint32_t)(g == 0 ? CF::obs_owner0 : CF::obs_owner1);
+        float* smo = (C > 1 && owner != 0) ? map_to_rank(sm, owner) : sm;   // the owner's record: same offsets
+        obs_task(sm, L, S, t, c_spec[a.k.slot].obs[g].terms[ti], corr, a.k, rs, g, ti, col0, 0, t.dim, e, env, c, eplen_now, smo);
+      });
+      // command state of the step (CommandTerm fields), straight from registers / the record
+      float* gc = static_cast<float*>(const_cast<void*>(a.k.outf[OF_CMD].ptr));
+      gc[env] = SMF(L.cmdn, 0); gc[(size_t)a.k.outf[OF_CMD].cs + env] = SMF(L.cmdn, 1); gc[2 * (size_t)a.k.outf[OF_CMD].cs + env] = SMF(L.cmdn, 2);
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_HEAD].ptr))[env] = SMF(L.head, 0);
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_TLEFT].ptr))[env] = SMF(L.tleft, 0);
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MXY].ptr))[env] = SMF(L.mxy, 0);
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MYAW].ptr))[env] = SMF(L.myaw, 0);
+      static_cast<uint8_t*>(const_cast<void*>(a.k.is_heading.ptr))[env] = (uint8_t)__float_as_int(SMF(L.ishead, 0));
+      static_cast<uint8_t*>(const_cast<void*>(a.k.is_standing.ptr))[env] = (uint8_t)__float_as_int(SMF(L.isstand, 0));
+    }
+  });
+  if (lane == 0 && early_prev == (unsigned)(n_tiles - 1)) s_last = 1;
+  if (C > 1) { cluster_arrive_release(); cluster_wait_acquire(); }   // the command columns have reached their rows
+  __syncthreads();
+
+  // ---- observation rows: this role's groups, per-env columns, lanes = columns (coalesced) -------------------------
+  static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
+    constexpr int g = decltype(gc)::value;
+    constexpr int D = env_cols_of(B::spec.obs[g]);
+    if constexpr (D > 0) {
+      if ((uint32_t)(g == 0 ? CF::obs_owner0 : CF::obs_owner1) == role && a.k.out.obs[g] != nullptr) {
+        const float* rows = sm + LOBS(g);
+        constexpr int P = LOBSP(g);
+#pragma unroll 1
+        for (int r = warp; r < E; r += kWarps2) {
+          float* dst = a.k.out.obs[g] + ((long long)env0 + r) * a.k.out.obs_pitch[g];
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32)
+            if (c0 + lane < D) dst[c0 + lane] = rows[r * P + c0 + lane];
+        }
+      }
+    }
+  });
+
+  // ---- logging means of the reset (extras["log"] [IL]): the CTA whose ticket was the last of the launch -------------
+  if (role == 0 && s_last) {
+    __threadfence();
+    float* s_red = sm;   // the record is dead
+    __syncthreads();
+    for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32) {
+      float part = 0.f;
+      for (int g = warp; g < n_tiles; g += kWarps2) part += __ldcg(a.k.log_partials + (size_t)g * RL_LOG_STRIDE + q);
+      s_red[warp * RL_LOG_STRIDE + q] = part;
+    }
+    __syncthreads();
+    if (tid < K + RL_MAX_DONE_TERMS + 2) {
+      float tot = 0.f;
+      for (int w = 0; w < kWarps2; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
+      const RlResetLog& lg = a.k.out.reset_log;
+      const int n_reset_total = *a.k.out.n_reset;
+      const float cnt = (float)max(n_reset_total, 1);
+      if (n_reset_total == 0) tot = 0.f;
+      if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / cnt; }
+      else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
+      else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / cnt;
+    }
+    if (tid == 0) *a.k.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side: tensor maps, eligibility, launch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+struct TmKey {
+  const void* ptr;
+  int cs, nc, n, box;
+};
+struct TmEntry {
+  TmKey key;
+  CUtensorMap map;
+};
+constexpr int kTmCache = 96;   // per field: the bench rotates over 24 state sets, tests over a handful
+
+}  // namespace
+
+struct RlV2State {
+  int baked;
+  long long launches;        // launches the cluster kernels handled (rl_ctx_get_cluster_config)
+  int force_c, force_g;      // RL_MDPSTEP_V2_CFG="CxG" pins a configuration (A/B measurements); 0 = choose by env count
+  int n_tm[IF_COUNT];
+  int next_tm[IF_COUNT];
+  TmEntry tm[IF_COUNT][kTmCache];
+};
+
+namespace {
+
+// tensor map of one SoA field: [nc, N] fp32, row stride cs elements, box {box envs, nc components}
+int tensor_map_for(RlV2State* v, int f, const FieldD& fd, int nc, int n, int box, CUtensorMap* out) {
+  const TmKey key{fd.ptr, fd.cs, nc, n, box};
+  for (int i = 0; i < v->n_tm[f]; ++i) {
+    const TmKey& k = v->tm[f][i].key;
+    if (k.ptr == key.ptr && k.cs == key.cs && k.nc == key.nc && k.n == key.n && k.box == key.box) { *out = v->tm[f][i].map; return RL_OK; }
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(RL_ECUDA, "cuTensorMapEncodeTiled is not available through cudaGetDriverEntryPoint%s", "");
+  // single-component fields: the (unused) row stride still has to be a multiple of 16 bytes
+  const unsigned long long row_bytes = nc > 1 ? (unsigned long long)fd.cs * 4ull : (((unsigned long long)n * 4ull + 15ull) & ~15ull);
+  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)nc};
+  const cuuint64_t gstr[1] = {(cuuint64_t)row_bytes};
+  const cuuint32_t bdim[2] = {(cuuint32_t)box, (cuuint32_t)nc};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(fd.ptr), gdim, gstr, bdim, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RL_ECUDA, "cuTensorMapEncodeTiled failed for input field %s%lld (CUresult %lld)", "", f, (long long)r);
+  int slot = v->n_tm[f] < kTmCache ? v->n_tm[f]++ : (v->next_tm[f]++ % kTmCache);
+  v->tm[f][slot].key = key; v->tm[f][slot].map = m;
+  *out = m;
+  return RL_OK;
+}
+
+bool soa_ok(const FieldD& d, int nc) {   // what a tensor map (or a lane = env access) can describe
+  return d.ptr != nullptr && d.es == 1 && (reinterpret_cast<uintptr_t>(d.ptr) & 15u) == 0 && (nc == 1 || (d.cs % 4) == 0);
+}
+
+template <class B, int KIND, int C, int G>
+int launch_v2(RlCtx* ctx, const KArgs& k, cudaStream_t st) {
+  using CF = Cfg2<B, KIND, C, G>;
+  RlV2State* v = ctx->v2;
+  const RlStepSpec& s = ctx->spec;
+  V2Args a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.k.vgrid = k.N / 32;
+  const uint32_t mask = v2_field_mask(s, KIND) & k.in_mask;
+  uint32_t bytes = 0;
+  for (int f = 0; f < IF_COUNT; ++f) {
+    if (!((mask >> f) & 1u)) continue;
+    const int nc = in_field_ncomp(s, f);
+    int rc = tensor_map_for(v, f, k.in[f], nc, k.N, CF::E, &a.tm[f]);
+    if (rc != RL_OK) return rc;
+    a.field_word[f] = v2_field_word(s, KIND, f);
+    bytes += (uint32_t)(nc * CF::E * 4);
+  }
+  a.tm_mask = mask; a.soa_bytes = bytes;
+  auto kern = KIND == RL_V2_PRE ? v2_pre_kernel<B, C, G> : v2_post_kernel<B, C, G>;
+  const size_t smem = (size_t)CF::L.total_words * 4;
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = ctx->device;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(k.N / CF::E) * C); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+  return RL_OK;
+}
+
+// configurations compiled for every baked spec: (cluster size, tiles per CTA)
+#define RL_V2_CONFIGS(X) X(4, 4) X(2, 2) X(1, 1)
+
+template <class B, int KIND>
+int dispatch_v2_cfg(RlCtx* ctx, const KArgs& k, int c, int g, cudaStream_t st, bool* found) {
+  *found = true;
+#define RL_CASE(C_, G_) if (c == (C_) && g == (G_)) return launch_v2<B, KIND, C_, G_>(ctx, k, st);
+  RL_V2_CONFIGS(RL_CASE)
+#undef RL_CASE
+  *found = false;
+  return RL_OK;
+}
+
+bool cfg_compiled(int c, int g) {
+#define RL_CASE(C_, G_) if (c == (C_) && g == (G_)) return true;
+  RL_V2_CONFIGS(RL_CASE)
+#undef RL_CASE
+  return false;
+}
+
+// the configuration a launch of n envs uses: the widest cluster whose tile group divides the env count
+void choose_cfg(const RlV2State* v, int64_t n, int* c, int* g) {
+  *c = 0; *g = 0;
+  if (v->force_c > 0) {
+    if (n % (32 * v->force_g) == 0) { *c = v->force_c; *g = v->force_g; }
+    return;
+  }
+#define RL_CASE(C_, G_) if (*c == 0 && n % (32 * (G_)) == 0) { *c = (C_); *g = (G_); }
+  RL_V2_CONFIGS(RL_CASE)
+#undef RL_CASE
+}
+
+#if RL_V2_DEV_ONE
+#define RL_V2_BAKED_LIST(X) X(Baked6)
+#else
+#define RL_V2_BAKED_LIST(X) RL_BAKED_LIST(X)
+#endif
+
+}  // namespace
+
+int rl_v2_create(RlCtx* ctx) {
+  ctx->v2 = nullptr;
+  if (ctx->baked < 0) return RL_OK;
+  const char* sw = getenv("RL_MDPSTEP_V2");
+  if (sw && sw[0] == '0') return RL_OK;
+  if (!v2_spec_ok(ctx->spec)) return RL_OK;
+#if RL_V2_DEV_ONE
+  if (memcmp(&ctx->spec, &baked::Baked6::spec, sizeof(RlStepSpec)) != 0) return RL_OK;
+#endif
+  RlV2State* v = new (std::nothrow) RlV2State();
+  if (!v) return fail(RL_ENOMEM, "rl_ctx_create: out of host memory%s", "");
+  memset(v, 0, sizeof(*v));
+  v->baked = ctx->baked;
+  const char* cfg = getenv("RL_MDPSTEP_V2_CFG");
+  if (cfg && cfg[0] >= '1' && cfg[0] <= '8' && cfg[1] == 'x' && cfg[2] >= '1' && cfg[2] <= '8') {
+    v->force_c = cfg[0] - '0'; v->force_g = cfg[2] - '0';
+    if (!cfg_compiled(v->force_c, v->force_g)) {
+      delete v;
+      return fail(RL_EINVAL, "RL_MDPSTEP_V2_CFG=%s is not a compiled (cluster size x tiles per CTA) configuration", cfg);
+    }
+  }
+  // this translation unit's copy of the spec slots (the term functions read run-time indexed lists from it)
+  CUDA_TRY(cudaMemcpyToSymbol(c_spec, &ctx->spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * ctx->slot));
+  ctx->v2 = v;
+  return RL_OK;
+}
+
+void rl_v2_destroy(RlCtx* ctx) {
+  delete ctx->v2;
+  ctx->v2 = nullptr;
+}
+
+void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, long long* launches) {
+  *cluster_size = 0; *tiles_per_cta = 0; *launches = 0;
+  if (!ctx->v2) return;
+  choose_cfg(ctx->v2, num_envs, cluster_size, tiles_per_cta);
+  *launches = ctx->v2->launches;
+}
+
+int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool* handled) {
+  *handled = false;
+  RlV2State* v = ctx->v2;
+  if (!v || k.has_ids || k.use_pdl || k.dbg != nullptr) return RL_OK;
+  const RlStepSpec& s = ctx->spec;
+  int c = 0, g = 0;
+  choose_cfg(v, k.N, &c, &g);
+  if (c == 0) return RL_OK;
+  // every staged field must be an SoA tensor a tensor map can describe; the sensor rows one contiguous block
+  const uint32_t want = v2_field_mask(s, kind);
+  for (int f = 0; f < IF_COUNT; ++f) {
+    if (!((want >> f) & 1u)) continue;
+    if (f == IF_CMDU && k.in[f].ptr == nullptr) continue;   // production mode: in-kernel Philox
+    if (!((k.in_mask >> f) & 1u) || !soa_ok(k.in[f], in_field_ncomp(s, f))) return RL_OK;
+  }
+  if (kind == RL_V2_PRE) {
+    const int HW = s.hist_len * s.num_hist_bodies * 3;
+    if (HW > 0 && (k.hist.ptr == nullptr || k.hist.cs != 1 || k.hist.es != HW || (reinterpret_cast<uintptr_t>(k.hist.ptr) & 15u) != 0 ||
+                   (((long long)32 * g * HW * 4) & 15) != 0))
+      return RL_OK;
+    if (!soa_ok(k.outf[OF_SUMS], s.num_reward_terms) || !k.outf[OF_EPLEN].ptr || k.outf[OF_EPLEN].es != 1) return RL_OK;
+    if (k.outf[OF_STEPR].ptr && k.outf[OF_STEPR].es != 1) return RL_OK;
+    if (!k.cta_mask || !k.ticket) return RL_OK;
+  } else {
+    if (!k.out.terminated || !k.out.truncated || !k.out.n_reset) return RL_OK;
+    if (!k.is_heading.ptr || !k.is_standing.ptr || k.is_heading.es != 1 || k.is_standing.es != 1) return RL_OK;
+    for (int f : {OF_SUMS, OF_ACT, OF_PACT, OF_CMD, OF_HEAD, OF_TLEFT, OF_MXY, OF_MYAW, OF_EPLEN})
+      if (!k.outf[f].ptr || k.outf[f].es != 1) return RL_OK;
+    if (s.num_rays > 0) {
+      bool scan = false;
+      for (int gi = 0; gi < RL_NUM_OBS_GROUPS; ++gi) scan = scan || (scan_term_of(s.obs[gi]) >= 0 && k.out.obs[gi] != nullptr);
+      if (scan && (k.rays.ptr == nullptr || k.rays.cs != 1 || k.rays.es != s.num_rays || k.in[IF_RAYPOS].ptr == nullptr || k.in[IF_RAYPOS].es != 1))
+        return RL_OK;
+    }
+  }
+  bool found = false;
+  int rc = RL_OK, idx = 0;
+#if RL_V2_DEV_ONE
+  idx = 6;
+#endif
+#define RL_TRY(B_)                                                                                        \
+  if (idx++ == v->baked) {                                                                               \
+    rc = kind == RL_V2_PRE ? dispatch_v2_cfg<baked::B_, RL_V2_PRE>(ctx, k, c, g, st, &found)             \
+                           : dispatch_v2_cfg<baked::B_, RL_V2_POST>(ctx, k, c, g, st, &found);           \
+  }
+  RL_V2_BAKED_LIST(RL_TRY)
+#undef RL_TRY
+  *handled = found;
+  if (found && rc == RL_OK) ++v->launches;
+  return rc;
+}

@@ -43,15 +43,21 @@ class MdpStepEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def set_launch_config(self, warps_per_cta: int = 0, envs_per_cta: int = 0) -> None:
-        """Warps per tile (4, 8, 16) and envs per CTA: 32 = one tile (one lane per env), 64 = two tiles per CTA
-        (build-time specialised tasks at 16 warps whose two tile records fit one SM; NativeError otherwise)."""
+        """Warps per tile of the general kernel (4, 8, 16); envs per CTA is 32 (one lane per env)."""
         nat.check(self.lib.rl_ctx_set_launch_config(self._ctx, envs_per_cta, warps_per_cta))
 
     def launch_config(self) -> dict:
-        """The launch configuration in effect: ``{"envs_per_cta": 32 | 64, "warps_per_tile": 4 | 8 | 16}``."""
+        """The launch configuration of the general kernel: ``{"envs_per_cta": 32, "warps_per_tile": 4 | 8 | 16}``."""
         epc, nw = C.c_int(0), C.c_int(0)
         nat.check(self.lib.rl_ctx_get_launch_config(self._ctx, C.byref(epc), C.byref(nw)))
         return {"envs_per_cta": epc.value, "warps_per_tile": nw.value}
+
+    def cluster_config(self, num_envs: int) -> dict:
+        """What ``step_pre_reset`` / ``step_post_reset`` of ``num_envs`` envs run: ``cluster_size`` C and ``tiles_per_cta``
+        G of the cluster kernels (csrc/mdp_step_v2.cu; C = 0: the general kernel) and the launches they handled so far."""
+        c, g, n = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        nat.check(self.lib.rl_ctx_get_cluster_config(self._ctx, int(num_envs), C.byref(c), C.byref(g), C.byref(n)))
+        return {"cluster_size": c.value, "tiles_per_cta": g.value, "launches": n.value}
 
     def set_pdl(self, enabled: bool) -> None:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""

@@ -126,9 +126,12 @@ class SensorChainStateProvider(ResetEventStateProvider):
         i = self.i % len(self.sets)
         super().advance(env)
         b, eng = env.buffers, env.engine
+        # ring-slot writes move no data, but feet_stumble reads history slot 0 as "the newest sample" (net_forces_w,
+        # V/mdp/rewards.py:431-434): a spec with that term active keeps IsaacLab's rolling history
+        ring = not any(r.type_name == "feet_stumble" and r.weight != 0.0 for r in env.spec.rewards)
         for _ in range(self.decimation):
             eng.actuator_step(b)
-            eng.contact_sensor_update(b, self.forces[i], self.physics_dt, ring_slot=self.substep % env.spec.T)
+            eng.contact_sensor_update(b, self.forces[i], self.physics_dt, ring_slot=(self.substep % env.spec.T) if ring else -1)
             self.substep += 1
         if self.height_field is not None and env.spec.R > 0:
             eng.height_scan_cast(b, self.height_field)

@@ -42,7 +42,9 @@ MDP_FIELDS = {
     "is_standing_env": (lambda s: 1, _U8, "soa"), "metric_error_vel_xy": (lambda s: 1, _F32, "soa"),
     "metric_error_vel_yaw": (lambda s: 1, _F32, "soa"), "episode_length": (lambda s: 1, _I32, "soa"),
     "episode_sums": (lambda s: s.K, _F32, "soa"),
-    "action": (lambda s: s.A, _F32, "aos"), "prev_action": (lambda s: s.A, _F32, "aos"),
+    # manager-internal copies of the action (the policy-facing row tensor is new_action): SoA like every small field, so
+    # that the step kernels stage them with one tensor-map copy and write them back as coalesced rows
+    "action": (lambda s: s.A, _F32, "soa"), "prev_action": (lambda s: s.A, _F32, "soa"),
     "joint_target": (lambda s: s.J, _F32, "soa"), "joint_vel_target": (lambda s: s.J, _F32, "soa"),
     "step_reward": (lambda s: s.K, _F32, "soa"),
 }

@@ -1,0 +1,162 @@
+"""The cluster kernels of the two env-step launches (csrc/mdp_step_v2.cu) against the general kernel (csrc/mdp_step.cu):
+same term functions, same operand order -> every output BIT-IDENTICAL, for every compiled (cluster size x tiles per CTA)
+configuration, every baked task, noise-as-input and production Philox streams, several chained env steps. The general
+kernel itself is checked against the CPU oracle in test_gpu_step_parity.py; test_v2_two_launch_step_matches_oracle closes
+the triangle directly.
+"""
+
+import os
+
+import pytest
+import torch
+
+import helpers as H
+from robot_lab_b200 import _native as nat
+from robot_lab_b200.synthetic import make_state
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ["4x4", "2x2", "1x1"]
+FIELDS = ("command", "heading_target", "time_left", "is_heading_env", "is_standing_env", "metric_error_vel_xy",
+          "metric_error_vel_yaw", "episode_length", "episode_sums", "action", "prev_action", "step_reward", "joint_target")
+
+
+def _engine(spec, v2_cfg):
+    """v2_cfg: None = general kernel only, else 'CxG'."""
+    from robot_lab_b200.engine import MdpStepEngine
+
+    old = {k: os.environ.get(k) for k in ("RL_MDPSTEP_V2", "RL_MDPSTEP_V2_CFG")}
+    try:
+        if v2_cfg is None:
+            os.environ["RL_MDPSTEP_V2"] = "0"
+            os.environ.pop("RL_MDPSTEP_V2_CFG", None)
+        else:
+            os.environ.pop("RL_MDPSTEP_V2", None)
+            os.environ["RL_MDPSTEP_V2_CFG"] = v2_cfg
+        return MdpStepEngine(spec, "cuda:0")   # the switches are read at rl_ctx_create
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _snapshot(b) -> dict:
+    out = {k: b.t[k].clone() for k in FIELDS}
+    n = int(b.n_reset.item())
+    out.update(reward=b.reward.clone(), terminated=b.terminated.clone(), truncated=b.truncated.clone(),
+               done_bits=b.done_bits.clone(), n_reset=b.n_reset.clone(), reset_ids=b.reset_ids[:n].clone(),
+               log_sum=b.log_episode_sum_mean.clone(), log_done=b.log_done_term_count.clone(), log_metric=b.log_metric_mean.clone())
+    for g in (0, 1):
+        if b.obs[g] is not None:
+            out[f"obs{g}"] = b.obs[g].clone()
+    return out
+
+
+def _assert_identical(a: dict, b: dict, where: str):
+    bad = []
+    for k in a:
+        x, y = a[k], b[k]
+        same = x.shape == y.shape and torch.equal(x.view(torch.uint8) if x.dtype != torch.bool else x, y.view(torch.uint8) if y.dtype != torch.bool else y)
+        if not same:
+            n = int((x != y).sum()) if x.shape == y.shape else -1
+            bad.append(f"{k} ({n} elements differ)")
+    assert not bad, f"{where}: cluster kernel != general kernel in: " + ", ".join(bad)
+
+
+def _three_steps(key, n, v2_cfg, philox, steps=3):
+    cfg, spec = H.make_spec(key)
+    eng_a, eng_b = _engine(spec, None), _engine(spec, v2_cfg)
+    assert eng_a.cluster_config(n)["cluster_size"] == 0
+    cc = eng_b.cluster_config(n)
+    assert f"{cc['cluster_size']}x{cc['tiles_per_cta']}" == v2_cfg
+    ba, bb = eng_a.new_buffers(n), eng_b.new_buffers(n)
+    rng = dict(seed=7, env_id_offset=3 * n, use_random_inputs=not philox, use_step_counter=True)
+    for t in range(steps):
+        st = make_state(spec, n, seed=100 + t)
+        if t > 0:   # fresh physics + a fresh policy action every step; the manager state chains from the previous step
+            st = {k: v for k, v in st.items() if k in nat._STATE_FIELDS or k in ("new_action", "cmd_uniforms", "obs_uniforms_policy", "obs_uniforms_critic")}
+        for eng, b in ((eng_a, ba), (eng_b, bb)):
+            b.load_logical(st)
+            if philox:
+                b.cmd_uniforms, b.obs_uniforms = None, [None, None]
+            eng.process_action(b)
+            eng.step_pre_reset(b, **rng)
+            eng.step_post_reset(b, **rng)
+        torch.cuda.synchronize()
+        _assert_identical(_snapshot(ba), _snapshot(bb), f"{key} N={n} cfg={v2_cfg} philox={philox} step {t}")
+        assert int(bb.n_reset.item()) > 0
+    assert eng_b.cluster_config(n)["launches"] == 2 * steps, "the cluster kernels did not run"
+    assert eng_a.cluster_config(n)["launches"] == 0
+    eng_a.close()
+    eng_b.close()
+
+
+@pytest.mark.parametrize("v2_cfg", CONFIGS)
+@pytest.mark.parametrize("philox", [False, True])
+def test_go2_rough_bit_identical(native_lib, v2_cfg, philox):
+    _three_steps("go2_rough", 4096, v2_cfg, philox)
+
+
+@pytest.mark.parametrize("key", ["a1_flat", "go2_flat", "g1_rough", "g1_rough_37", "g1_flat", "a1_rough"])
+@pytest.mark.parametrize("v2_cfg", CONFIGS)
+def test_every_baked_task_bit_identical(native_lib, key, v2_cfg):
+    _three_steps(key, 1024, v2_cfg, philox=True, steps=2)
+
+
+@pytest.mark.parametrize("n", [128, 256, 640, 16384])
+def test_env_counts(native_lib, n):
+    """One cluster, an odd number of clusters, several waves of clusters."""
+    _three_steps("go2_rough", n, "4x4", philox=True, steps=2)
+
+
+def test_default_config_choice_and_fallback(native_lib):
+    """Without RL_MDPSTEP_V2_CFG: the widest cluster whose tile group divides the env count; env counts that are not a
+    multiple of 32, env-id lists and IsaacLab-shaped tensors run the general kernel (and still match the oracle)."""
+    from robot_lab_b200.engine import MdpStepEngine
+
+    cfg, spec = H.make_spec("go2_rough")
+    eng = MdpStepEngine(spec, "cuda:0")
+    assert eng.cluster_config(4096)["cluster_size"] == 4 and eng.cluster_config(4096)["tiles_per_cta"] == 4
+    assert eng.cluster_config(4096 + 64)["cluster_size"] == 2
+    assert eng.cluster_config(4096 + 32)["cluster_size"] == 1
+    assert eng.cluster_config(1000)["cluster_size"] == 0
+    for n, layout, want in ((1000, "soa", 0), (1024, "aos", 0), (1024, "soa", 2)):
+        st = make_state(spec, n)
+        b = eng.new_buffers(n, layout=layout)
+        b.load_logical(st)
+        before = eng.cluster_config(n)["launches"]
+        eng.step_pre_reset(b)
+        eng.step_post_reset(b)
+        torch.cuda.synchronize()
+        assert eng.cluster_config(n)["launches"] - before == want
+    eng.close()
+
+
+@pytest.mark.parametrize("key", ["go2_rough", "g1_rough"])
+@pytest.mark.parametrize("v2_cfg", CONFIGS)
+def test_v2_two_launch_step_matches_oracle(native_lib, monkeypatch, key, v2_cfg):
+    """The env step in the reference's order through the cluster kernels against the CPU oracle (noise as input): the
+    body of test_gpu_step_parity.test_two_launch_step_in_reference_order with an engine pinned to one configuration."""
+    import test_gpu_step_parity as T
+
+    engines = []
+
+    def pinned(spec):
+        engines.append(_engine(spec, v2_cfg))
+        return engines[-1]
+
+    monkeypatch.setattr(T, "_engine", pinned)
+    launches = []
+    from robot_lab_b200.engine import MdpStepEngine
+
+    orig_close = MdpStepEngine.close
+
+    def counting_close(self):
+        launches.append(self.cluster_config(2048)["launches"])
+        orig_close(self)
+
+    monkeypatch.setattr("robot_lab_b200.engine.MdpStepEngine.close", counting_close)
+    T.test_two_launch_step_in_reference_order(native_lib, key, 2048)
+    assert launches and launches[-1] == 2, "the cluster kernels did not run"

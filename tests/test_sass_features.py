@@ -1,7 +1,7 @@
-"""What the compiled step kernels actually contain (cuobjdump -sass of the in-tree library, no GPU needed): the TMA
-bulk copies and async copies the load phase is built on, the release-ticket tails, the named barriers of the
-two-tile configuration, sm_100a as the only target, and (next to) no local-memory traffic in the production kernels
-(16 warps per tile)."""
+"""What the compiled step kernels actually contain (cuobjdump -sass of the in-tree library, no GPU needed): the 2-D TMA
+tensor-map copies (UTMALDG), the bulk copies, the cluster barriers and DSMEM addressing of the cluster kernels
+(csrc/mdp_step_v2.cu); the bulk / async copies and release-ticket tails of the general kernel (csrc/mdp_step.cu);
+sm_100a as the only target; (next to) no local-memory traffic in the production kernels."""
 
 import os
 import re
@@ -11,6 +11,7 @@ import subprocess
 import pytest
 
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+N_BAKED = 7   # tasks with a build-time specialised spec (csrc/generated/baked_specs.cuh)
 
 
 @pytest.fixture(scope="module")
@@ -33,14 +34,59 @@ def kernels(native_lib):
     return funcs
 
 
-def _step_kernels(funcs, nw=16, dbg=0, tiles=1, static=True):
-    pat = re.compile(r"mdp_step_kernelINS_(\w+?)E?Li%dELi0ELb%dELi%dEEEv" % (nw, dbg, tiles))
+def _step_kernels(funcs, nw=16, dbg=0, static=True):
+    """Instantiations of the general kernel mdp_step_kernel<Policy, NW, MODE = 0, DBG>."""
+    pat = re.compile(r"mdp_step_kernelINS_(\w+?)E?Li%dELi0ELb%dEEEv" % (nw, dbg))
     return {k: v for k, v in funcs.items() if (m := pat.search(k)) and (("StaticPolicy" in m.group(1)) == static)}
 
 
-def test_load_phase_uses_tma_bulk_copies_and_async_copies(kernels):
+def _cluster_kernels(funcs, kind, c=None, g=None):
+    """Instantiations of v2_pre_kernel / v2_post_kernel <Baked, C, G>."""
+    pat = re.compile(r"v2_%s_kernelIN5baked\w+?ELi(\d+)ELi(\d+)EEEv" % kind)
+    return {k: v for k, v in funcs.items()
+            if (m := pat.search(k)) and (c is None or int(m.group(1)) == c) and (g is None or int(m.group(2)) == g)}
+
+
+def test_cluster_kernels_stage_fields_with_tensor_map_copies(kernels):
+    """Every cluster kernel: SoA fields by cp.async.bulk.tensor (UTMALDG) issued from a compact loop, the mbarrier they
+    complete on, and NO per-thread async-copy loops (LDGSTS) - the load prologue of the general kernel is gone."""
+    for kind in ("pre", "post"):
+        ks = _cluster_kernels(kernels, kind)
+        assert len(ks) == 3 * N_BAKED, f"{kind}: {len(ks)} cluster kernels, want 3 configurations x {N_BAKED} tasks"
+        for name, body in ks.items():
+            text = "\n".join(body)
+            assert "UTMALDG.2D" in text, f"{name}: no 2-D tensor-map copy"
+            assert "SYNCS" in text, f"{name}: no mbarrier"
+            assert "LDGSTS" not in text, f"{name}: per-thread async copies are back"
+    for name, body in _cluster_kernels(kernels, "pre").items():
+        has_forces = "Baked0" not in name or True
+        if has_forces:
+            assert "UBLKCP" in "\n".join(body), f"{name}: the contact-force rows should arrive by one bulk copy"
+
+
+def test_cluster_kernels_use_cluster_barriers_and_dsmem(kernels):
+    for kind in ("pre", "post"):
+        for (c, g) in ((4, 4), (2, 2)):
+            ks = _cluster_kernels(kernels, kind, c, g)
+            assert len(ks) == N_BAKED
+            for name, body in ks.items():
+                text = "\n".join(body)
+                assert "UCGABAR_ARV" in text and "UCGABAR_WAIT" in text, f"{name}: no cluster barrier"
+        for name, body in _cluster_kernels(kernels, kind, 1, 1).items():
+            assert "UCGABAR" not in "\n".join(body), f"{name}: a one-CTA configuration needs no cluster barrier"
+
+
+def test_cluster_kernels_are_small(kernels):
+    """The point of the role split: distinct code. A cluster kernel is well under half of the general kernel of the same
+    task (5.3 - 5.6 k instructions in round 1), and an SM executes only its role's share of it."""
+    for kind in ("pre", "post"):
+        for name, body in _cluster_kernels(kernels, kind).items():
+            assert len(body) < 4500, f"{name}: {len(body)} instructions"
+
+
+def test_general_kernel_load_phase_uses_bulk_and_async_copies(kernels):
     ks = _step_kernels(kernels)
-    assert len(ks) >= 5, "one production instantiation per baked task"
+    assert len(ks) == N_BAKED, "one production instantiation per baked task"
     for name, body in ks.items():
         text = "\n".join(body)
         assert "UBLKCP" in text, f"{name}: no TMA bulk copy (cp.async.bulk)"
@@ -54,22 +100,19 @@ def test_last_cta_tickets_are_release_atomics_not_sc_fences(kernels):
         assert len(re.findall(r"ATOM\.E\.ADD\.STRONG\.GPU", text)) >= 2, name          # early arrivals (pre- / post-reset)
         assert len(re.findall(r"MEMBAR\.ALL\.GPU", text)) >= 2, name                   # their release fences
         assert len(re.findall(r"MEMBAR\.SC\.GPU", text)) <= 2, name                    # only the two acquiring tails
-
-
-def test_two_tile_kernels_use_named_barriers_of_512_threads(kernels):
-    ks = _step_kernels(kernels, tiles=2)
-    assert len(ks) >= 5
-    for name, body in ks.items():
-        text = "\n".join(body)
-        assert re.search(r"BAR\.SYNC\.DEFER_BLOCKING R\d+, 0x200", text), name
-        assert re.search(r"BAR\.RED\.OR\.DEFER_BLOCKING R\d+, 0x200", text), name
-        assert not re.search(r"BAR\.SYNC\.DEFER_BLOCKING 0x0", text), f"{name}: a CTA-wide barrier would dead-lock the tiles"
+    for kind in ("pre", "post"):
+        for name, body in _cluster_kernels(kernels, kind).items():
+            text = "\n".join(body)
+            assert len(re.findall(r"ATOM\.E\.ADD\.STRONG\.GPU", text)) >= 1, name
+            assert len(re.findall(r"MEMBAR\.SC\.GPU", text)) <= 1, name
 
 
 def test_production_kernels_keep_their_state_in_registers(kernels):
     """Local-memory instructions only as the few callee-save slots around the shared (noinline) helpers: well under 1 %
-    of a kernel (the Go2-rough kernels of the round-1 build have none; ptxas -v per build: _lib/build.log)."""
-    for tiles in (1, 2):
-        for name, body in _step_kernels(kernels, tiles=tiles).items():
+    of a kernel."""
+    groups = [_step_kernels(kernels), _cluster_kernels(kernels, "pre"), _cluster_kernels(kernels, "post")]
+    for ks in groups:
+        assert ks
+        for name, body in ks.items():
             local = sum(1 for line in body if re.search(r"\b(STL|LDL)\b", line))
             assert local * 100 <= len(body), f"{name}: {local} local-memory instructions of {len(body)}"
