@@ -392,15 +392,17 @@ int rl_ctx_set_launch_config(RlCtx* ctx, int envs_per_cta, int warps_per_cta);
 /* The configuration of the general kernel in effect (after rl_ctx_create's defaults or the last successful set). */
 int rl_ctx_get_launch_config(const RlCtx* ctx, int* envs_per_cta, int* warps_per_tile);
 /* The two launches of an env step - rl_step(DONES | REWARDS | COMPACT) and rl_step(RESET | COMMAND | OBS) without an
- * env-id list - have thread-block-cluster kernels for the build-time specialised specs (csrc/mdp_step_v2.cu): a cluster
- * of C CTAs shares G tiles, CTA r evaluating the r-th share of the term list for all of them; SoA fields arrive by 2-D
- * TMA tensor-map copies. A launch uses them when num_envs is a multiple of 32 * G, every staged field is an SoA tensor
- * ({1, row stride}, 16-byte aligned) and the sensor rows are contiguous; anything else runs the general kernel with
- * bit-identical results. This call reports what a launch of num_envs envs would use - *cluster_size = 0: the general
- * kernel - and how many launches the cluster kernels have handled so far on this context (any pointer may be NULL).
- * Environment: RL_MDPSTEP_V2=0 switches them off at rl_ctx_create, RL_MDPSTEP_V2_CFG="CxG" pins a configuration. */
+ * env-id list - have their own kernels for the build-time specialised specs (csrc/mdp_step_v2.cu): SoA fields arrive by
+ * 2-D TMA tensor-map copies issued by one thread, contact-force norms are computed once per env, results leave from
+ * registers as coalesced rows. A configuration is (C, G, NW): a thread-block cluster of C CTAs shares G tiles, CTA r
+ * evaluating the r-th share of the term list for all of them (C = G = 1: one tile per CTA, no cluster), NW warps per
+ * CTA. A launch uses these kernels when num_envs is a multiple of 32 * G, every staged field is an SoA tensor ({1, row
+ * stride}, 16-byte aligned) and the sensor rows are contiguous; anything else runs the general kernel, with bit-identical
+ * results. This call reports what a launch of num_envs envs would use - *cluster_size = 0: the general kernel - and how
+ * many launches these kernels have handled so far on this context (any pointer may be NULL).
+ * Environment: RL_MDPSTEP_V2=0 switches them off at rl_ctx_create, RL_MDPSTEP_V2_CFG="CxG[xNW]" pins a configuration. */
 int rl_ctx_get_cluster_config(const RlCtx* ctx, int64_t num_envs, int32_t* cluster_size, int32_t* tiles_per_cta,
-                              int64_t* launches);
+                              int32_t* warps_per_cta, int64_t* launches);
 /* Programmatic dependent launch: let each kernel's launch latency overlap the tail of its predecessor on
  * the stream (data dependencies are still honoured through cudaGridDependencySynchronize). Default off. */
 int rl_ctx_set_pdl(RlCtx* ctx, int enabled);
@@ -575,6 +577,13 @@ int rl_reset_envs(RlCtx* ctx, int64_t num_envs, const RlMdpState* mdp, const uin
 int rl_term_eval(RlCtx* ctx, int64_t num_envs, const RlRewardTerm* term, const RlStateView* state,
                  const RlMdpState* mdp, const uint8_t* terminated /* may be NULL */, float* out,
                  void* stream);
+
+/* Derived articulation views [IL] (ArticulationData properties) for Python term functions that run against the env
+ * surface (e.g. V/mdp/rewards.py:34 reads projected_gravity_b, :226 root_com_lin_vel_b): one launch
+ * writes projected_gravity_b [3], root_lin_vel_b [3] (= root_com_lin_vel_b), root_ang_vel_b [3] and heading_w [1] from
+ * the root state, with the arithmetic of the step kernels. Any output may be NULL / have a NULL pointer. */
+int rl_derived_views(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlField* projected_gravity_b,
+                     const RlField* root_lin_vel_b, const RlField* root_ang_vel_b, const RlField* heading_w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -204,7 +204,7 @@ EXPORTED_SYMBOLS = (
     "rl_abi_version", "rl_last_error", "rl_struct_sizeof", "rl_tile_record_bytes", "rl_ctx_create", "rl_ctx_destroy",
     "rl_ctx_set_launch_config", "rl_ctx_get_launch_config", "rl_ctx_get_cluster_config", "rl_ctx_set_pdl", "rl_ctx_set_debug_buffer", "rl_ctx_get_schedule",
     "rl_contact_sensor_update", "rl_reset_scene_state", "rl_process_action", "rl_step", "rl_reset_envs", "rl_term_eval",
-    "rl_actuator_step", "rl_is_robot_on_terrain", "rl_command_pit_restrict", "rl_height_scan_cast",
+    "rl_actuator_step", "rl_is_robot_on_terrain", "rl_command_pit_restrict", "rl_height_scan_cast", "rl_derived_views",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmdpstep.so"
@@ -247,7 +247,7 @@ def load() -> C.CDLL:
     lib.rl_ctx_destroy.restype = None
     lib.rl_ctx_set_launch_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.rl_ctx_get_launch_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    lib.rl_ctx_get_cluster_config.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    lib.rl_ctx_get_cluster_config.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     lib.rl_ctx_set_pdl.argtypes = [C.c_void_p, C.c_int]
     lib.rl_ctx_set_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.rl_ctx_get_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]

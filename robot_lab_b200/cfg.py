@@ -100,6 +100,10 @@ class SceneEntityCfg:
         self.body_ids = slice(None) if ids == list(range(len(body_names))) else ids
         return ids
 
+    def resolve(self, scene) -> None:
+        """isaaclab.managers.SceneEntityCfg.resolve(scene) [IL]: fill joint_ids / body_ids against the named entity."""
+        scene.resolve(self)
+
 
 @dataclass
 class AdditiveUniformNoiseCfg:

@@ -40,6 +40,6 @@ void rl_v2_destroy(RlCtx* ctx);
 // parameter block fill_args() built for the general kernel.
 int rl_v2_try_launch(RlCtx* ctx, const rlk::KArgs& a, int kind, cudaStream_t st, bool* handled);
 // what rl_ctx_get_cluster_config reports: (0, 0) = no cluster kernel applies to a launch of num_envs
-void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, long long* launches);
+void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, int* warps_per_cta, long long* launches);
 
 #endif  // RL_MDP_CTX_H_

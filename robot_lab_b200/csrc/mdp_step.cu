@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 #pragma unroll
             for (int p = 1; p < kTermParts; ++p)
               if (p < parts) full_raw += *(volatile float*)&SMF(L.termv, kTermParts * k + p);
+            if (rt.type == RL_REW_UNDESIRED_CONTACTS) full_raw = full_raw * c.gate;   // the parts are raw counts
           }
         }
         if (finish) {
@@ -1136,13 +1137,15 @@ int rl_ctx_get_launch_config(const RlCtx* ctx, int* envs_per_cta, int* warps_per
   return RL_OK;
 }
 
-int rl_ctx_get_cluster_config(const RlCtx* ctx, int64_t num_envs, int32_t* cluster_size, int32_t* tiles_per_cta, int64_t* launches) {
+int rl_ctx_get_cluster_config(const RlCtx* ctx, int64_t num_envs, int32_t* cluster_size, int32_t* tiles_per_cta, int32_t* warps_per_cta,
+                              int64_t* launches) {
   if (!ctx) return fail(RL_EINVAL, "null ctx%s", "");
-  int c = 0, g = 0;
+  int c = 0, g = 0, w = 0;
   long long n = 0;
-  rl_v2_config_for(ctx, num_envs, &c, &g, &n);
+  rl_v2_config_for(ctx, num_envs, &c, &g, &w, &n);
   if (cluster_size) *cluster_size = c;
   if (tiles_per_cta) *tiles_per_cta = g;
+  if (warps_per_cta) *warps_per_cta = w;
   if (launches) *launches = n;
   return RL_OK;
 }

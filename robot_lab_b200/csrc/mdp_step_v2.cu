@@ -28,6 +28,12 @@
 // it (tests/test_gpu_v2_parity.py). Launches that do not qualify (ragged env counts, env-id lists, strided IsaacLab
 // tensors, a spec that is not baked) run the general kernel.
 
+#ifndef RL_V2_UNROLL
+#define RL_V2_UNROLL 1
+#endif
+#if RL_V2_UNROLL
+#define RL_TERM_LOOP _Pragma("unroll")   // see csrc/mdp_terms.cuh: the term loops unroll against the baked spec
+#endif
 #include "mdp_ctx.h"
 
 #include <cuda.h>
@@ -38,8 +44,7 @@
 
 namespace {
 
-constexpr int kWarps2 = 16;
-constexpr int kThreads2 = kWarps2 * 32;
+constexpr int kLogWarps = 16;   // the logging reduction keeps the general kernel's order: 16 strided partial sums, then their sum
 
 // ---------------------------------------------------------------------------------------------------
 // Which input fields a launch kind stages (the sets fill_args() of the general kernel uses for the same phases)
@@ -52,7 +57,6 @@ __host__ __device__ constexpr uint32_t v2_field_mask(const RlStepSpec& s, int ki
          (1u << IF_LCON) | (1u << IF_BPOS) | (1u << IF_BVEL) | (1u << IF_SUMS);
   } else {
     m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU) | (1u << IF_SUMS);
-    if (s.num_rays > 0) m |= 1u << IF_RAYPOS;
   }
   for (int f = 0; f < IF_COUNT; ++f)
     if (in_field_ncomp(s, f) <= 0) m &= ~(1u << f);
@@ -105,7 +109,7 @@ __host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const i
   L.root_pos = iw[IF_ROOT_POS] * E; L.quat = iw[IF_QUAT] * E; L.lin_vel = iw[IF_LIN_VEL] * E; L.ang_vel = iw[IF_ANG_VEL] * E;
   L.jpos = iw[IF_JPOS] * E; L.jvel = iw[IF_JVEL] * E; L.jacc = iw[IF_JACC] * E; L.jtau = iw[IF_JTAU] * E;
   L.cair = iw[IF_CAIR] * E; L.lair = iw[IF_LAIR] * E; L.ccon = iw[IF_CCON] * E; L.lcon = iw[IF_LCON] * E;
-  L.bpos = iw[IF_BPOS] * E; L.bvel = iw[IF_BVEL] * E; L.raypos = iw[IF_RAYPOS] * E;
+  L.bpos = iw[IF_BPOS] * E; L.bvel = iw[IF_BVEL] * E;
   L.cmd = iw[IF_CMD] * E; L.head = iw[IF_HEAD] * E; L.tleft = iw[IF_TLEFT] * E;
   L.mxy = iw[IF_MXY] * E; L.myaw = iw[IF_MYAW] * E; L.eplen = iw[IF_EPLEN] * E;
   L.sums = iw[IF_SUMS] * E; L.cmdu = iw[IF_CMDU] * E; L.act = iw[IF_ACT] * E; L.pact = iw[IF_PACT] * E;
@@ -164,7 +168,7 @@ __host__ __device__ constexpr bool dones_use_hist(const RlStepSpec& s) {
   return false;
 }
 
-__host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int kind, int C, int W, int G) {
+__host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int kind, int C, int W, int G, int NW) {
   Sched2 sc{};
   int cost[RL_MAX_TASKS] = {};
   int lo_bin[RL_MAX_TASKS] = {}, hi_bin[RL_MAX_TASKS] = {};   // bins a task may go to: [lo, hi)
@@ -191,7 +195,7 @@ __host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int k
     if (any_hist) {
       sc.hist_roles = 1u;
       // what the prepass costs every warp of role 0 before its tasks start
-      const int pre = ((G * s.num_hist_bodies + kWarps2 - 1) / kWarps2) * (s.hist_len * 18 + 12) + 40;
+      const int pre = ((G * s.num_hist_bodies + NW - 1) / NW) * (s.hist_len * 18 + 12) + 40;
       for (int b = 0; b < W; ++b) load[b] = pre;
     }
     for (int b = 0; b < W; ++b) load[b] += 80;   // role 0 also runs the final sum and the compaction tail
@@ -245,6 +249,59 @@ __host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int k
 }
 
 // ---------------------------------------------------------------------------------------------------
+// What a role stages: the union of the input fields its tasks read (a CTA of a 4-role cluster would otherwise pull the
+// whole record of 128 envs through its SM for a quarter of the terms).
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kCoreFields = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_CMD);   // make_ctx
+
+__host__ __device__ constexpr uint32_t reward_fields(int type) {
+  uint32_t m = kCoreFields | (1u << IF_SUMS);
+  switch (type) {
+    case RL_REW_JOINT_TORQUES_L2: m |= 1u << IF_JTAU; break;
+    case RL_REW_JOINT_VEL_L2: case RL_REW_JOINT_VEL_LIMITS: m |= 1u << IF_JVEL; break;
+    case RL_REW_JOINT_ACC_L2: m |= 1u << IF_JACC; break;
+    case RL_REW_JOINT_DEVIATION_L1: case RL_REW_JOINT_POS_LIMITS: case RL_REW_STAND_STILL: case RL_REW_JOINT_POS_PENALTY:
+    case RL_REW_JOINT_MIRROR: m |= 1u << IF_JPOS; break;
+    case RL_REW_JOINT_POWER: m |= (1u << IF_JVEL) | (1u << IF_JTAU); break;
+    case RL_REW_ACTION_MIRROR: case RL_REW_ACTION_SYNC: m |= 1u << IF_ACT; break;
+    case RL_REW_ACTION_RATE_L2: m |= (1u << IF_ACT) | (1u << IF_PACT); break;
+    case RL_REW_FEET_AIR_TIME: m |= (1u << IF_LAIR) | (1u << IF_CCON); break;
+    case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: case RL_REW_FEET_GAIT: m |= (1u << IF_CAIR) | (1u << IF_CCON); break;
+    case RL_REW_FEET_AIR_TIME_VARIANCE: m |= (1u << IF_LAIR) | (1u << IF_LCON); break;
+    case RL_REW_FEET_CONTACT: case RL_REW_FEET_CONTACT_WITHOUT_CMD: m |= 1u << IF_CCON; break;
+    case RL_REW_FEET_SLIDE: m |= 1u << IF_BVEL; break;
+    case RL_REW_FEET_HEIGHT: case RL_REW_FEET_HEIGHT_BODY: m |= (1u << IF_BPOS) | (1u << IF_BVEL); break;
+    case RL_REW_FEET_DISTANCE_Y_EXP: case RL_REW_FEET_DISTANCE_XY_EXP: m |= 1u << IF_BPOS; break;
+    case RL_REW_WHEEL_VEL_PENALTY: m |= (1u << IF_JVEL) | (1u << IF_CAIR); break;
+    default: break;
+  }
+  return m;
+}
+__host__ __device__ constexpr uint32_t obs_fields(int type) {
+  switch (type) {
+    case RL_OBS_JOINT_POS_REL: case RL_OBS_JOINT_POS_REL_WITHOUT_WHEEL: return kCoreFields | (1u << IF_JPOS);
+    case RL_OBS_JOINT_VEL_REL: return kCoreFields | (1u << IF_JVEL);
+    case RL_OBS_LAST_ACTION: return kCoreFields | (1u << IF_ACT);
+    case RL_OBS_PHASE: return kCoreFields | (1u << IF_EPLEN);
+    default: return kCoreFields;
+  }
+}
+__host__ __device__ constexpr uint32_t role_field_mask(const RlStepSpec& s, const Sched2& sc, int kind, int role, int W) {
+  uint32_t m = kCoreFields | (1u << IF_EPLEN);
+  if (role == 0) {
+    m |= 1u << IF_SUMS;   // PRE: is_terminated is finished by the final sum; POST: the logging means of the reset
+    if (kind == RL_V2_POST) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
+  }
+  for (int i = 0; i < sc.n; ++i) {
+    const Task& t = sc.t[i];
+    if (t.owner / W != role) continue;
+    if (t.kind == TK_REWARD) m |= reward_fields(s.rewards[t.a].type);
+    else if (t.kind == TK_OBS) m |= obs_fields(s.obs[t.a].terms[t.b].type);
+  }
+  return m & v2_field_mask(s, kind);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // PTX helpers of the cluster kernels
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -255,6 +312,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// programmatic dependent launch: let the next kernel of the stream start its CTAs (their prologue overlaps this kernel),
+// and - in the dependent - wait until the predecessor has completed and its memory is visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// L2 prefetch of a contiguous span (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // generic address of `p` (a pointer into this CTA's shared memory) in CTA `rank` of the cluster
 template <class T> __device__ __forceinline__ T* map_to_rank(T* p, uint32_t rank) {
   uint64_t r;
@@ -272,20 +337,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 
 struct alignas(64) V2Args {
   KArgs k;                  // the parameter block of the general kernel (pointers, strides, phases, random streams)
-  uint32_t soa_bytes;       // bytes the tensor-map copies of one CTA deliver
-  uint32_t tm_mask;         // fields staged by a tensor map
+  uint32_t role_bytes[8];   // bytes the tensor-map copies of one CTA of role r deliver
+  uint32_t role_mask[8];    // fields role r stages (what its tasks read)
   int32_t field_word[IF_COUNT];
+  const char* prefetch_rays;   // PRE: the ray-hit rows the post-reset launch will stream (L2 prefetch), or NULL
+  uint32_t prefetch_row_bytes;
   alignas(64) CUtensorMap tm[IF_COUNT];
 };
 
-template <class B, int KIND, int C, int G>
+template <class B, int KIND, int C, int G, int NW>
 struct Cfg2 {
-  static_assert(kWarps2 % G == 0, "tiles per CTA must divide the warp count");
-  static constexpr int W = kWarps2 / G;   // task slots per (role, tile)
+  static_assert(NW % G == 0 && NW <= 16, "tiles per CTA must divide the warp count");
+  static constexpr int W = NW / G;        // task slots per (role, tile)
+  static constexpr int NT = NW * 32;      // threads per CTA
   static constexpr int E = 32 * G;        // envs per cluster
   static constexpr int BINS = C * W;
   static constexpr Layout L = make_layout_v2(B::spec, E, KIND);
-  static constexpr Sched2 sched = make_schedule_v2(B::spec, KIND, C, W, G);
+  static constexpr Sched2 sched = make_schedule_v2(B::spec, KIND, C, W, G, NW);
   static constexpr Scalars S = scalars_of(B::spec);
   // scalar copies: device code must not odr-use the schedule object itself
   static constexpr int n_tasks = sched.n;
@@ -322,17 +390,18 @@ __device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, con
 
 // the load every CTA starts with: one thread, one instruction per field
 template <class CF>
-__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const int env0, uint64_t* bar, const bool with_hist) {
+__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar, const bool with_hist) {
   constexpr Layout L = CF::L;
   constexpr Scalars S = CF::S;
   constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
   mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  uint32_t bytes = a.soa_bytes;
+  if (a.k.use_pdl) pdl_wait();   // the copies read what the predecessor on the stream wrote
+  uint32_t bytes = a.role_bytes[role];
   if (with_hist) bytes += (uint32_t)(CF::E * HW * 4);
   mbar_expect_tx(bar, bytes);
 #pragma unroll 1
-  for (uint32_t m = a.tm_mask; m != 0; m &= m - 1) {
+  for (uint32_t m = a.role_mask[role]; m != 0; m &= m - 1) {
     const int f = __ffs((int)m) - 1;
     tma_load_2d(sm + a.field_word[f] * CF::E, &a.tm[f], env0, 0, bar);
   }
@@ -342,7 +411,9 @@ __device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const in
 
 // reset_buf.nonzero() [IL]: ascending reset ids from one 32-bit done mask per tile (runs in the ONE CTA whose ticket
 // was the last of the launch; same result as the general kernel's tail)
+template <int NW>
 __device__ __noinline__ void compact_reset_ids(const KArgs& a, const int n_tiles, int* s_cnt, const int tid) {
+  constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   const int warp = tid >> 5, e = tid & 31;
   int run = 0;
 #pragma unroll 1
@@ -382,9 +453,10 @@ __device__ __noinline__ void compact_reset_ids(const KArgs& a, const int n_tiles
 // ---------------------------------------------------------------------------------------------------
 // PRE: TerminationManager.compute + RewardManager.compute [IL] + reset_buf.nonzero()
 // ---------------------------------------------------------------------------------------------------
-template <class B, int C, int G>
-__global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const __grid_constant__ V2Args a) {
-  using CF = Cfg2<B, RL_V2_PRE, C, G>;
+template <class B, int C, int G, int NW>
+__global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pre_kernel(const __grid_constant__ V2Args a) {
+  using CF = Cfg2<B, RL_V2_PRE, C, G, NW>;
+  constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
   constexpr Scalars S = CF::S;
   constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms;
@@ -402,9 +474,13 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const
   const long long env = (long long)env0 + e;
   const bool my_hist = ((CF::hist_roles >> role) & 1u) != 0 && S.num_hist_bodies > 0;
   if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
+  if (a.k.use_pdl) pdl_launch_dependents();   // the successor's prologue may overlap this kernel
   if (tid == 0) {
     s_last = 0;
-    issue_loads<CF>(sm, a, env0, &s_bar, my_hist);
+    issue_loads<CF>(sm, a, role, env0, &s_bar, my_hist);   // (waits for the predecessor first when PDL is on)
+    // the post-reset launch of this env step streams the tile's ray hits: have them in L2 by then
+    if (role == 0 && a.prefetch_rays != nullptr)
+      prefetch_l2(a.prefetch_rays + (size_t)env0 * a.prefetch_row_bytes, (uint32_t)(E * a.prefetch_row_bytes));
   }
   // per-joint constants: constant bank -> shared
   for (int i = tid; i < S.num_joints; i += kThreads2)
@@ -415,6 +491,7 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const
   if (role == 0)   // weight-0 terms: no task writes their slot of the final sum
     for (int i = tid; i < K * E; i += kThreads2)
       if ((a.k.rw_zero >> (i / E)) & 1ull) sm[L.termv + i] = 0.f;
+  if (a.k.use_pdl && tid != 0) pdl_wait();   // no global access of this kernel before its predecessor is complete
   __syncthreads();           // mbarrier init + the stores above visible to the CTA
   mbar_wait(&s_bar, 0);      // record resident
   if (my_hist) {
@@ -502,7 +579,7 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const
   }
   if (s_last) {   // CTA-uniform: ordered compaction of the reset ids by the CTA that arrived last
     __threadfence();
-    compact_reset_ids(a.k, a.k.vgrid, s_cnt, tid);
+    compact_reset_ids<NW>(a.k, a.k.vgrid, s_cnt, tid);
   }
 }
 
@@ -510,9 +587,10 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_pre_kernel(const
 // POST: ManagerBasedRLEnv._reset_idx (manager part) for the done envs + CommandManager.compute +
 // ObservationManager.compute [IL] for all envs
 // ---------------------------------------------------------------------------------------------------
-template <class B, int C, int G>
-__global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(const __grid_constant__ V2Args a) {
-  using CF = Cfg2<B, RL_V2_POST, C, G>;
+template <class B, int C, int G, int NW>
+__global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_post_kernel(const __grid_constant__ V2Args a) {
+  using CF = Cfg2<B, RL_V2_POST, C, G, NW>;
+  constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
   constexpr Scalars S = CF::S;
   constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms, A = S.n_actions;
@@ -527,9 +605,17 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(cons
   const int env0 = cluster_id * E;
   const long long env = (long long)env0 + e;
   if (C > 1) cluster_arrive_relaxed();
+  if (a.k.use_pdl) pdl_launch_dependents();
+  for (int i = tid; i < S.num_joints; i += kThreads2)
+    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
+      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
+      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
+    });
   if (tid == 0) {
     s_last = 0;
-    issue_loads<CF>(sm, a, env0, &s_bar, false);
+    issue_loads<CF>(sm, a, role, env0, &s_bar, false);   // (waits for the predecessor first when PDL is on)
+  } else if (a.k.use_pdl) {
+    pdl_wait();
   }
   // byte flags of this lane's env (every role needs the reset mask; role 0 also the command flags)
   const int u8_reset = (a.k.out.terminated[env] | a.k.out.truncated[env]) != 0;
@@ -557,20 +643,34 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(cons
         constexpr int rows_per_cta = E / C;   // this role's share of the cluster's env rows
         const float* rays = static_cast<const float*>(a.k.rays.ptr);
         const float* rz = static_cast<const float*>(a.k.in[IF_RAYPOS].ptr);
-#pragma unroll 1
-        for (int r = warp; r < rows_per_cta; r += kWarps2) {
-          const long long ev = (long long)env0 + (int)role * rows_per_cta + r;
-          const float z = __ldg(rz + ev);
-          const float* src = rays + ev * R;
-          float* dst = a.k.out.obs[g] + ev * a.k.out.obs_pitch[g] + col0;
+        constexpr int RPW = (rows_per_cta + kWarps2 - 1) / kWarps2;   // rows per warp
+        constexpr int CH = (R + 31) / 32;                              // 32-column chunks per row
+        float z[RPW], v[RPW][CH];
 #pragma unroll
-          for (int c0 = 0; c0 < R; c0 += 32) {
-            const int col = c0 + lane;
-            if (col < R) {
-              float v = (z - __ldg(src + col)) - t.p[0];
-              if (t.has_clip) v = clampf(v, t.clip_lo, t.clip_hi);
-              if (t.has_scale) v = v * t.scale;
-              dst[col] = v;
+        for (int i = 0; i < RPW; ++i) {   // every load of the warp's rows is in flight before the first use
+          const int r = warp + i * kWarps2;
+          const long long ev = (long long)env0 + (int)role * rows_per_cta + r;
+          if (r < rows_per_cta) {
+            z[i] = __ldg(rz + ev);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[i][c] = (c * 32 + lane < R) ? __ldg(rays + ev * R + c * 32 + lane) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const int r = warp + i * kWarps2;
+          const long long ev = (long long)env0 + (int)role * rows_per_cta + r;
+          if (r < rows_per_cta) {
+            float* dst = a.k.out.obs[g] + ev * a.k.out.obs_pitch[g] + col0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              const int col = c * 32 + lane;
+              if (col < R) {
+                float x = (z[i] - v[i][c]) - t.p[0];
+                if (t.has_clip) x = clampf(x, t.clip_lo, t.clip_hi);
+                if (t.has_scale) x = x * t.scale;
+                dst[col] = x;
+              }
             }
           }
         }
@@ -578,11 +678,6 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(cons
     }
   });
 
-  for (int i = tid; i < S.num_joints; i += kThreads2)
-    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
-      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
-      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
-    });
   if (slot == 0) {
     sm[L.rmask + e] = __int_as_float(u8_reset);
     if (role == 0) {
@@ -731,15 +826,16 @@ __global__ void __launch_bounds__(kThreads2, G <= 2 ? 2 : 1) v2_post_kernel(cons
     __threadfence();
     float* s_red = sm;   // the record is dead
     __syncthreads();
-    for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32) {
-      float part = 0.f;
-      for (int g = warp; g < n_tiles; g += kWarps2) part += __ldcg(a.k.log_partials + (size_t)g * RL_LOG_STRIDE + q);
-      s_red[warp * RL_LOG_STRIDE + q] = part;
-    }
+    for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32)
+      for (int vw = warp; vw < kLogWarps; vw += kWarps2) {   // 16 strided partial sums whatever the warp count of this CTA
+        float part = 0.f;
+        for (int g = vw; g < n_tiles; g += kLogWarps) part += __ldcg(a.k.log_partials + (size_t)g * RL_LOG_STRIDE + q);
+        s_red[vw * RL_LOG_STRIDE + q] = part;
+      }
     __syncthreads();
     if (tid < K + RL_MAX_DONE_TERMS + 2) {
       float tot = 0.f;
-      for (int w = 0; w < kWarps2; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
+      for (int w = 0; w < kLogWarps; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
       const RlResetLog& lg = a.k.out.reset_log;
       const int n_reset_total = *a.k.out.n_reset;
       const float cnt = (float)max(n_reset_total, 1);
@@ -784,7 +880,8 @@ constexpr int kTmCache = 96;   // per field: the bench rotates over 24 state set
 struct RlV2State {
   int baked;
   long long launches;        // launches the cluster kernels handled (rl_ctx_get_cluster_config)
-  int force_c, force_g;      // RL_MDPSTEP_V2_CFG="CxG" pins a configuration (A/B measurements); 0 = choose by env count
+  int force_c, force_g, force_nw;   // RL_MDPSTEP_V2_CFG="CxGxNW" pins a configuration (A/B measurements); 0 = choose by env count
+  int large_n, large_nw;            // from large_n envs on: large_nw warps per tile
   int n_tm[IF_COUNT];
   int next_tm[IF_COUNT];
   TmEntry tm[IF_COUNT][kTmCache];
@@ -822,27 +919,35 @@ bool soa_ok(const FieldD& d, int nc) {   // what a tensor map (or a lane = env a
   return d.ptr != nullptr && d.es == 1 && (reinterpret_cast<uintptr_t>(d.ptr) & 15u) == 0 && (nc == 1 || (d.cs % 4) == 0);
 }
 
-template <class B, int KIND, int C, int G>
+template <class B, int KIND, int C, int G, int NW>
 int launch_v2(RlCtx* ctx, const KArgs& k, cudaStream_t st) {
-  using CF = Cfg2<B, KIND, C, G>;
+  using CF = Cfg2<B, KIND, C, G, NW>;
   RlV2State* v = ctx->v2;
   const RlStepSpec& s = ctx->spec;
   V2Args a;
   memset(&a, 0, sizeof(a));
   a.k = k;
   a.k.vgrid = k.N / 32;
-  const uint32_t mask = v2_field_mask(s, KIND) & k.in_mask;
-  uint32_t bytes = 0;
+  const uint32_t staged = v2_field_mask(s, KIND) & k.in_mask;
   for (int f = 0; f < IF_COUNT; ++f) {
-    if (!((mask >> f) & 1u)) continue;
-    const int nc = in_field_ncomp(s, f);
-    int rc = tensor_map_for(v, f, k.in[f], nc, k.N, CF::E, &a.tm[f]);
+    if (!((staged >> f) & 1u)) continue;
+    int rc = tensor_map_for(v, f, k.in[f], in_field_ncomp(s, f), k.N, CF::E, &a.tm[f]);
     if (rc != RL_OK) return rc;
     a.field_word[f] = v2_field_word(s, KIND, f);
-    bytes += (uint32_t)(nc * CF::E * 4);
   }
-  a.tm_mask = mask; a.soa_bytes = bytes;
-  auto kern = KIND == RL_V2_PRE ? v2_pre_kernel<B, C, G> : v2_post_kernel<B, C, G>;
+  for (int r = 0; r < C; ++r) {
+    const uint32_t m = role_field_mask(s, CF::sched, KIND, r, CF::W) & staged;
+    uint32_t bytes = 0;
+    for (int f = 0; f < IF_COUNT; ++f)
+      if ((m >> f) & 1u) bytes += (uint32_t)(in_field_ncomp(s, f) * CF::E * 4);
+    a.role_mask[r] = m; a.role_bytes[r] = bytes;
+  }
+  if (KIND == RL_V2_PRE && s.num_rays > 0 && k.rays.ptr != nullptr && k.rays.cs == 1 && k.rays.es == s.num_rays &&
+      ((size_t)CF::E * s.num_rays * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(k.rays.ptr) & 15u) == 0) {
+    a.prefetch_rays = static_cast<const char*>(k.rays.ptr);
+    a.prefetch_row_bytes = (uint32_t)s.num_rays * 4u;
+  }
+  auto kern = KIND == RL_V2_PRE ? v2_pre_kernel<B, C, G, NW> : v2_post_kernel<B, C, G, NW>;
   const size_t smem = (size_t)CF::L.total_words * 4;
   static thread_local int configured_device = -1;
   if (configured_device != ctx->device) {
@@ -851,45 +956,49 @@ int launch_v2(RlCtx* ctx, const KArgs& k, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(k.N / CF::E) * C); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3((unsigned)(k.N / CF::E) * C); cfg.blockDim = dim3(CF::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = k.use_pdl ? 2 : 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   return RL_OK;
 }
 
-// configurations compiled for every baked spec: (cluster size, tiles per CTA)
-#define RL_V2_CONFIGS(X) X(4, 4) X(2, 2) X(1, 1)
+// configurations compiled for every baked spec: (cluster size, tiles per CTA, warps per CTA)
+#define RL_V2_CONFIGS(X) X(1, 1, 16) X(1, 1, 8) X(1, 1, 4) X(2, 2, 16) X(4, 4, 16)
 
 template <class B, int KIND>
-int dispatch_v2_cfg(RlCtx* ctx, const KArgs& k, int c, int g, cudaStream_t st, bool* found) {
+int dispatch_v2_cfg(RlCtx* ctx, const KArgs& k, int c, int g, int nw, cudaStream_t st, bool* found) {
   *found = true;
-#define RL_CASE(C_, G_) if (c == (C_) && g == (G_)) return launch_v2<B, KIND, C_, G_>(ctx, k, st);
+#define RL_CASE(C_, G_, NW_) if (c == (C_) && g == (G_) && nw == (NW_)) return launch_v2<B, KIND, C_, G_, NW_>(ctx, k, st);
   RL_V2_CONFIGS(RL_CASE)
 #undef RL_CASE
   *found = false;
   return RL_OK;
 }
 
-bool cfg_compiled(int c, int g) {
-#define RL_CASE(C_, G_) if (c == (C_) && g == (G_)) return true;
+bool cfg_compiled(int c, int g, int nw) {
+#define RL_CASE(C_, G_, NW_) if (c == (C_) && g == (G_) && nw == (NW_)) return true;
   RL_V2_CONFIGS(RL_CASE)
 #undef RL_CASE
   return false;
 }
 
-// the configuration a launch of n envs uses: the widest cluster whose tile group divides the env count
-void choose_cfg(const RlV2State* v, int64_t n, int* c, int* g) {
-  *c = 0; *g = 0;
+// The configuration a launch of n envs uses (measured on B200, profiles/r2_summary.md): up to a few waves of tiles one
+// tile per CTA with 16 warps (shortest serial chain per tile); beyond that fewer warps per tile, so that more tiles are
+// in flight per SM and less per-warp context work is repeated.
+void choose_cfg(const RlV2State* v, int64_t n, int* c, int* g, int* nw) {
+  *c = 0; *g = 0; *nw = 0;
+  if (n <= 0 || n % 32 != 0) return;
   if (v->force_c > 0) {
-    if (n % (32 * v->force_g) == 0) { *c = v->force_c; *g = v->force_g; }
+    if (n % (32 * v->force_g) == 0) { *c = v->force_c; *g = v->force_g; *nw = v->force_nw; }
     return;
   }
-#define RL_CASE(C_, G_) if (*c == 0 && n % (32 * (G_)) == 0) { *c = (C_); *g = (G_); }
-  RL_V2_CONFIGS(RL_CASE)
-#undef RL_CASE
+  *c = 1; *g = 1;
+  *nw = n >= v->large_n ? v->large_nw : 16;
 }
 
 #if RL_V2_DEV_ONE
@@ -913,13 +1022,16 @@ int rl_v2_create(RlCtx* ctx) {
   if (!v) return fail(RL_ENOMEM, "rl_ctx_create: out of host memory%s", "");
   memset(v, 0, sizeof(*v));
   v->baked = ctx->baked;
-  const char* cfg = getenv("RL_MDPSTEP_V2_CFG");
-  if (cfg && cfg[0] >= '1' && cfg[0] <= '8' && cfg[1] == 'x' && cfg[2] >= '1' && cfg[2] <= '8') {
-    v->force_c = cfg[0] - '0'; v->force_g = cfg[2] - '0';
-    if (!cfg_compiled(v->force_c, v->force_g)) {
+  v->large_n = 16384; v->large_nw = 8;
+  const char* cfg = getenv("RL_MDPSTEP_V2_CFG");   // "CxG" (16 warps) or "CxGxNW"
+  if (cfg && cfg[0]) {
+    int c = 0, g = 0, nw = 16;
+    const int got = sscanf(cfg, "%dx%dx%d", &c, &g, &nw);
+    if (got < 2 || !cfg_compiled(c, g, nw)) {
       delete v;
-      return fail(RL_EINVAL, "RL_MDPSTEP_V2_CFG=%s is not a compiled (cluster size x tiles per CTA) configuration", cfg);
+      return fail(RL_EINVAL, "RL_MDPSTEP_V2_CFG=%s is not a compiled (cluster size x tiles per CTA [x warps]) configuration", cfg);
     }
+    v->force_c = c; v->force_g = g; v->force_nw = nw;
   }
   // this translation unit's copy of the spec slots (the term functions read run-time indexed lists from it)
   CUDA_TRY(cudaMemcpyToSymbol(c_spec, &ctx->spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * ctx->slot));
@@ -932,20 +1044,20 @@ void rl_v2_destroy(RlCtx* ctx) {
   ctx->v2 = nullptr;
 }
 
-void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, long long* launches) {
-  *cluster_size = 0; *tiles_per_cta = 0; *launches = 0;
+void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, int* warps_per_cta, long long* launches) {
+  *cluster_size = 0; *tiles_per_cta = 0; *warps_per_cta = 0; *launches = 0;
   if (!ctx->v2) return;
-  choose_cfg(ctx->v2, num_envs, cluster_size, tiles_per_cta);
+  choose_cfg(ctx->v2, num_envs, cluster_size, tiles_per_cta, warps_per_cta);
   *launches = ctx->v2->launches;
 }
 
 int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool* handled) {
   *handled = false;
   RlV2State* v = ctx->v2;
-  if (!v || k.has_ids || k.use_pdl || k.dbg != nullptr) return RL_OK;
+  if (!v || k.has_ids || k.dbg != nullptr) return RL_OK;
   const RlStepSpec& s = ctx->spec;
-  int c = 0, g = 0;
-  choose_cfg(v, k.N, &c, &g);
+  int c = 0, g = 0, nw = 0;
+  choose_cfg(v, k.N, &c, &g, &nw);
   if (c == 0) return RL_OK;
   // every staged field must be an SoA tensor a tensor map can describe; the sensor rows one contiguous block
   const uint32_t want = v2_field_mask(s, kind);
@@ -981,8 +1093,8 @@ int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool
 #endif
 #define RL_TRY(B_)                                                                                        \
   if (idx++ == v->baked) {                                                                               \
-    rc = kind == RL_V2_PRE ? dispatch_v2_cfg<baked::B_, RL_V2_PRE>(ctx, k, c, g, st, &found)             \
-                           : dispatch_v2_cfg<baked::B_, RL_V2_POST>(ctx, k, c, g, st, &found);           \
+    rc = kind == RL_V2_PRE ? dispatch_v2_cfg<baked::B_, RL_V2_PRE>(ctx, k, c, g, nw, st, &found)             \
+                           : dispatch_v2_cfg<baked::B_, RL_V2_POST>(ctx, k, c, g, nw, st, &found);           \
   }
   RL_V2_BAKED_LIST(RL_TRY)
 #undef RL_TRY

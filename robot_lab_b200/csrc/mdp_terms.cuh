@@ -38,6 +38,13 @@ using DeviceGuard = RlDeviceGuard;
 // same way. Each of the ~25 fields travels per launch as {pointer, strides, component count, first record word}
 // in the kernel parameter bank - one parameter line per field, no table in global memory.
 // ---------------------------------------------------------------------------------------------------
+// Loops inside the term functions (over joints, feet, bodies). The general kernel keeps them rolled: every SM executes all
+// of its code once per launch, and code size is what that costs. The kernels of mdp_step_v2.cu define RL_TERM_LOOP as a
+// full unroll before including this header: with a baked spec the trip counts, masks and addresses are constants, the
+// independent parts of the iterations overlap, and the sums keep their order (bit-identical).
+#ifndef RL_TERM_LOOP
+#define RL_TERM_LOOP _Pragma("unroll 1")
+#endif
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
 // A reward term is evaluated in at most this many parts (termv holds that many slots per term). 2, not more: finer
 // cuts measured slower, and every extra slot costs K * 128 bytes of the tile record - at 4 the Go2-rough record grew
@@ -256,7 +263,9 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
     const bool list_sum = (t.type == RL_REW_FEET_SLIDE);
     const int nb = popc64(t.body_mask);
     const int items = body_sum ? nb : (list_sum ? t.n_idx : 0);
-    int parts = items > 8 ? 2 : 1;
+    // only COUNTS are cut (undesired_contacts): their parts add up exactly in any order, so the split term equals the
+    // reference's single sum bit for bit; a float sum (contact_forces, feet_slide) cut in two would round differently
+    int parts = (items > 8 && t.type == RL_REW_UNDESIRED_CONTACTS) ? 2 : 1;
     if (parts > kTermParts) parts = kTermParts;
     if (n + parts > RL_MAX_TASKS - 24) parts = 1;   // table nearly full: stop splitting
     if (parts < 2) {
@@ -647,15 +656,16 @@ __device__ __noinline__ float hist_max_norm(const float* h, int T, int B, int b)
   // ONE copy for every term that uses it (undesired_contacts, contact_forces, feet_slide, feet_stumble, the
   // illegal-contact termination): warps in different terms keep the same few instruction lines hot instead of
   // evicting each other's private copies. A force of exactly 0 skips the IEEE sqrt (its special-case path).
-  float m = 0.f;
-  _Pragma("unroll 1")
+  // max_t sqrt(ss_t) == sqrt(max_t ss_t) bit for bit: the correctly rounded square root is monotonic - ONE IEEE sqrt per
+  // body instead of one per history sample
+  float m2 = 0.f;
+  RL_TERM_LOOP
   for (int t = 0; t < T; ++t) {
     const float* f = h + (t * B + b) * 3;
     const float ss = (f[0] * f[0] + f[1] * f[1]) + f[2] * f[2];
-    const float n = (ss == 0.f) ? 0.f : sqrtf(ss);
-    m = (t == 0) ? n : fmaxf(m, n);
+    m2 = (t == 0) ? ss : fmaxf(m2, ss);
   }
-  return m;
+  return (m2 == 0.f) ? 0.f : sqrtf(m2);
 }
 
 // One reward term for env e: raw value (no weight, no dt). [lo, hi) restricts body-mask terms to a body-index
@@ -685,21 +695,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     case RL_REW_JOINT_ACC_L2: {
       const int off = t.type == RL_REW_JOINT_TORQUES_L2 ? L.jtau : (t.type == RL_REW_JOINT_VEL_L2 ? L.jvel : L.jacc);
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float v = SMF(off, j); s += v * v; }
       return s;
     }
     case RL_REW_JOINT_DEVIATION_L1: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       return s;
     }
     case RL_REW_JOINT_POS_LIMITS: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) {
           const float q = SMF(L.jpos, j);
@@ -711,21 +721,21 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_JOINT_VEL_LIMITS: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += clampf(fabsf(SMF(L.jvel, j)) - CJ(4, j) * t.p[0], 0.f, 1.f);
       return s;
     }
     case RL_REW_JOINT_POWER: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jvel, j) * SMF(L.jtau, j));
       return s;
     }
     case RL_REW_STAND_STILL: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) s += fabsf(SMF(L.jpos, j) - CJ(0, j));
       s *= (c.cmd_norm < t.p[0]) ? 1.f : 0.f;
@@ -733,7 +743,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_JOINT_POS_PENALTY: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int j = 0; j < J; ++j)
         if ((t.joint_mask >> j) & 1ull) { const float d = SMF(L.jpos, j) - CJ(0, j); s += d * d; }
       const float running = sqrtf(s);
@@ -742,7 +752,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_JOINT_MIRROR: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = SMF(L.jpos, tc.idx_a[i]) - SMF(L.jpos, tc.idx_b[i]);
         s += d * d;
@@ -751,7 +761,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_ACTION_MIRROR: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const float d = fabsf(SMF(L.act, tc.idx_a[i])) - fabsf(SMF(L.act, tc.idx_b[i]));
         s += d * d;
@@ -760,7 +770,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_ACTION_SYNC: {
       float r = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int g = 0; g < t.n_idx; ++g) {
         const int start = tc.idx_b[g], n = tc.idx_c[g];
         if (n < 2) continue;
@@ -775,20 +785,23 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_ACTION_RATE_L2: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int a = 0; a < S.n_actions; ++a) { const float d = SMF(L.act, a) - SMF(L.pact, a); s += d * d; }
       return s;
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if (((t.body_mask >> b) & 1ull) && (HIST_MAX_NORM(h, b) > t.p[0])) s += 1.f;
-      return s * c.gate;   // gate distributes over the two halves of a split term
+      // one part of a split term (a restricted body range) returns its raw COUNT: the finisher adds the counts (exact)
+      // and applies the gate once, as the reference does (V/mdp/rewards.py:672-675) - count_a * gate + count_b * gate
+      // rounds differently from (count_a + count_b) * gate
+      return (lo > 0 || hi < 64) ? s : s * c.gate;
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if ((t.body_mask >> b) & 1ull) s += fmaxf(HIST_MAX_NORM(h, b) - t.p[0], 0.f);
       return s;
@@ -817,7 +830,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = tc.idx_a[i];
         s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
@@ -827,11 +840,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, tc.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = tc.idx_a[i];
         const float ct = SMF(L.ccon, b);
@@ -845,11 +858,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     case RL_REW_FEET_AIR_TIME_VARIANCE: {
       // torch.var (unbiased) is a Welford reduction on CPU; keep the same update order.
       float r = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int which = 0; which < 2; ++which) {
         const int off = which == 0 ? L.lair : L.lcon;
         float mean = 0.f, m2 = 0.f;
-        _Pragma("unroll 1")
+        RL_TERM_LOOP
         for (int i = 0; i < t.n_idx; ++i) {
           const float x = fminf(SMF(off, tc.idx_a[i]), 0.5f);
           const float d = x - mean;
@@ -880,7 +893,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
@@ -888,7 +901,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
@@ -896,7 +909,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_STUMBLE: {
       bool any = false;   // t = 0 is the newest history sample = net_forces_w
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = tc.idx_c[i];
         const float fx = h[3 * b + 0], fy = h[3 * b + 1], fz = h[3 * b + 2];
@@ -906,7 +919,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = lo; i < t.n_idx && i < hi; ++i) {   // [lo, hi): this part's slice of the feet list
         const V3 vw = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
@@ -917,7 +930,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 p = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 v = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);
@@ -929,7 +942,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 vw = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);
@@ -943,7 +956,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_DISTANCE_Y_EXP: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
@@ -955,7 +968,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_DISTANCE_XY_EXP: {
       float s = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < 4; ++i) {
         const V3 pw = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 pb = quat_apply_inverse(c.qw, c.q, V3{pw.x - c.pos.x, pw.y - c.pos.y, pw.z - c.pos.z});
@@ -968,7 +981,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_WHEEL_VEL_PENALTY: {
       float run = 0.f, stand = 0.f;
-      _Pragma("unroll 1")
+      RL_TERM_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const float jv = fabsf(SMF(L.jvel, tc.idx_b[i]));
         const float ta = SMF(L.cair, tc.idx_a[i]);
@@ -1070,7 +1083,7 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
   const float* urow = a.rnd.obs_uniforms[g] ? a.rnd.obs_uniforms[g] + env * (g == 0 ? S.obs_dim0 : S.obs_dim1) : nullptr;
   const bool ext_u = (a.rnd.obs_uniforms[g] != nullptr);
   const bool noisy = t.has_noise && corrupt;
-  _Pragma("unroll 1")
+  RL_TERM_LOOP
   for (int qd = lo / 4; qd * 4 < hi; ++qd) {
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (noisy && !ext_u) {

@@ -234,6 +234,49 @@ __global__ void __launch_bounds__(256) height_scan_kernel(const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Derived articulation views [IL] (ArticulationData properties that Python term functions read: V/mdp/rewards.py:34,
+// 226 and 28 more uses): projected_gravity_b, root_lin_vel_b (= root_com_lin_vel_b), root_ang_vel_b, heading_w.
+// One thread per env; same arithmetic, same operand order as make_ctx / command_update of the step kernels
+// (isaaclab.utils.math.quat_apply_inverse / quat_apply [IL]).
+// ---------------------------------------------------------------------------------------------------
+struct DerivedArgs {
+  int N;
+  RlField quat, lin, ang;
+  RlField grav_b, lin_b, ang_b, heading;
+};
+struct D3 { float x, y, z; };
+__device__ __forceinline__ D3 d_cross(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ D3 d_rot(float w, D3 q, D3 v, float sign) {   // sign -1: quat_apply_inverse, +1: quat_apply
+  D3 t = d_cross(q, v);
+  t.x *= 2.f; t.y *= 2.f; t.z *= 2.f;
+  const D3 c = d_cross(q, t);
+  const float sw = sign * w;
+  return D3{(v.x + sw * t.x) + c.x, (v.y + sw * t.y) + c.y, (v.z + sw * t.z) + c.z};
+}
+__global__ void __launch_bounds__(256) derived_views_kernel(const __grid_constant__ DerivedArgs a) {
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < a.N; env += gridDim.x * blockDim.x) {
+    const float w = ld_f(a.quat, env, 0);
+    const D3 q{ld_f(a.quat, env, 1), ld_f(a.quat, env, 2), ld_f(a.quat, env, 3)};
+    if (a.grav_b.ptr) {
+      const D3 g = d_rot(w, q, D3{0.f, 0.f, -1.f}, -1.f);
+      st_f(a.grav_b, env, 0, g.x); st_f(a.grav_b, env, 1, g.y); st_f(a.grav_b, env, 2, g.z);
+    }
+    if (a.lin_b.ptr) {
+      const D3 v = d_rot(w, q, D3{ld_f(a.lin, env, 0), ld_f(a.lin, env, 1), ld_f(a.lin, env, 2)}, -1.f);
+      st_f(a.lin_b, env, 0, v.x); st_f(a.lin_b, env, 1, v.y); st_f(a.lin_b, env, 2, v.z);
+    }
+    if (a.ang_b.ptr) {
+      const D3 v = d_rot(w, q, D3{ld_f(a.ang, env, 0), ld_f(a.ang, env, 1), ld_f(a.ang, env, 2)}, -1.f);
+      st_f(a.ang_b, env, 0, v.x); st_f(a.ang_b, env, 1, v.y); st_f(a.ang_b, env, 2, v.z);
+    }
+    if (a.heading.ptr) {
+      const D3 f = d_rot(w, q, D3{1.f, 0.f, 0.f}, 1.f);
+      st_f(a.heading, env, 0, atan2f(f.y, f.x));
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -344,6 +387,29 @@ int rl_height_scan_cast(RlCtx* ctx, int64_t num_envs, const RlHeightField* hf, c
   const long long want = (num_envs + 7) / 8;
   const int blocks = (int)(want < (1ll << 20) ? want : (1ll << 20));
   height_scan_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return RL_OK;
+}
+
+int rl_derived_views(RlCtx* ctx, int64_t num_envs, const RlStateView* state, const RlField* projected_gravity_b,
+                     const RlField* root_lin_vel_b, const RlField* root_ang_vel_b, const RlField* heading_w, void* stream) {
+  if (!ctx || !state) return rl_fail(RL_EINVAL, "rl_derived_views: null argument%s", "");
+  if (num_envs <= 0) return RL_OK;
+  if (!state->root_quat_w.ptr) return rl_fail(RL_EINVAL, "rl_derived_views: root_quat_w is required%s", "");
+  if ((root_lin_vel_b && root_lin_vel_b->ptr && !state->root_lin_vel_w.ptr) || (root_ang_vel_b && root_ang_vel_b->ptr && !state->root_ang_vel_w.ptr))
+    return rl_fail(RL_EINVAL, "rl_derived_views: the world-frame velocity of a requested base-frame velocity is missing%s", "");
+  DerivedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = (int)num_envs;
+  a.quat = state->root_quat_w; a.lin = state->root_lin_vel_w; a.ang = state->root_ang_vel_w;
+  if (projected_gravity_b) a.grav_b = *projected_gravity_b;
+  if (root_lin_vel_b) a.lin_b = *root_lin_vel_b;
+  if (root_ang_vel_b) a.ang_b = *root_ang_vel_b;
+  if (heading_w) a.heading = *heading_w;
+  RlDeviceGuard guard(rl_ctx_device_of(ctx));
+  const int threads = 256;
+  const int blocks = (int)((num_envs + threads - 1) / threads);
+  derived_views_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   return RL_OK;
 }

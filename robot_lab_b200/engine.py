@@ -53,11 +53,11 @@ class MdpStepEngine:
         return {"envs_per_cta": epc.value, "warps_per_tile": nw.value}
 
     def cluster_config(self, num_envs: int) -> dict:
-        """What ``step_pre_reset`` / ``step_post_reset`` of ``num_envs`` envs run: ``cluster_size`` C and ``tiles_per_cta``
-        G of the cluster kernels (csrc/mdp_step_v2.cu; C = 0: the general kernel) and the launches they handled so far."""
-        c, g, n = C.c_int32(0), C.c_int32(0), C.c_int64(0)
-        nat.check(self.lib.rl_ctx_get_cluster_config(self._ctx, int(num_envs), C.byref(c), C.byref(g), C.byref(n)))
-        return {"cluster_size": c.value, "tiles_per_cta": g.value, "launches": n.value}
+        """What ``step_pre_reset`` / ``step_post_reset`` of ``num_envs`` envs run: cluster size C, tiles per CTA G and warps
+        per CTA of the kernels of csrc/mdp_step_v2.cu (C = 0: the general kernel), and the launches they handled so far."""
+        c, g, w, n = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        nat.check(self.lib.rl_ctx_get_cluster_config(self._ctx, int(num_envs), C.byref(c), C.byref(g), C.byref(w), C.byref(n)))
+        return {"cluster_size": c.value, "tiles_per_cta": g.value, "warps_per_cta": w.value, "launches": n.value}
 
     def set_pdl(self, enabled: bool) -> None:
         """Programmatic dependent launch between consecutive kernels of this context (launch-latency overlap)."""

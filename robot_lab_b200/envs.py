@@ -151,44 +151,107 @@ class ReplayStateProvider(StateProvider):
 
 
 # --------------------------------------------------------------------------------------------------
-# scene views (env.scene["robot"].data.*, env.scene.sensors["contact_forces"].data.*)
+# scene views: what Python term functions read through ``env``. Raw fields are views of the device
+# buffers; derived fields (ArticulationData properties [IL]) are device tensors filled lazily by ``rl_derived_views``,
+# once per state version (the env bumps the version whenever a provider or a launch changes the physical state).
 # --------------------------------------------------------------------------------------------------
-class _BufferView:
-    def __init__(self, env, mapping: dict[str, str]):
-        object.__setattr__(self, "_env", env)
-        object.__setattr__(self, "_map", mapping)
+class _ArticulationData:
+    _RAW = ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_w", "joint_pos", "joint_vel", "joint_acc",
+            "applied_torque", "body_pos_w", "body_lin_vel_w")
+    _ALIAS = {"root_link_pos_w": "root_pos_w", "root_link_quat_w": "root_quat_w", "body_link_pos_w": "body_pos_w",
+              "root_com_lin_vel_w": "root_lin_vel_w", "root_com_ang_vel_w": "root_ang_vel_w",
+              "body_com_lin_vel_w": "body_lin_vel_w", "joint_pos_target": "joint_target"}
+    _DERIVED = {"projected_gravity_b": 0, "root_lin_vel_b": 1, "root_ang_vel_b": 2, "root_com_lin_vel_b": 1,
+                "root_com_ang_vel_b": 2, "root_link_lin_vel_b": 1, "root_link_ang_vel_b": 2}
+
+    def __init__(self, env):
+        self._env = env
+        n, dev = env.num_envs, env.device
+        self._vec = torch.zeros(3, n, 3, device=dev)       # projected_gravity_b, root_lin_vel_b, root_ang_vel_b
+        self._heading = torch.zeros(n, device=dev)
+        self._version = -1
+        asset = env.spec.layout.asset
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.default_joint_pos = torch.tensor(asset.default_joint_pos(), **f32).unsqueeze(0).expand(n, -1)
+        self.default_joint_vel = torch.tensor(asset.default_joint_vel(), **f32).unsqueeze(0).expand(n, -1)
+        self.soft_joint_pos_limits = torch.tensor(asset.soft_joint_pos_limits(), **f32).unsqueeze(0).expand(n, -1, -1)
+        self.soft_joint_vel_limits = torch.tensor(asset.joint_vel_limits(), **f32).unsqueeze(0).expand(n, -1)
+        root = [0.0, 0.0, asset.init_root_height, 1.0, 0.0, 0.0, 0.0] + [0.0] * 6
+        self.default_root_state = torch.tensor(root, **f32).unsqueeze(0).expand(n, -1)
+
+    def _refresh(self):
+        env = self._env
+        if self._version == env._state_version:
+            return
+        b = env.buffers
+        st = b.state_view()
+        vec = [nat.RlField(self._vec[i].data_ptr(), 3, 1) for i in range(3)]
+        head = nat.RlField(self._heading.data_ptr(), 1, 1)
+        import ctypes as C
+
+        nat.check(env.engine.lib.rl_derived_views(env.engine._ctx, b.N, C.byref(st), C.byref(vec[0]), C.byref(vec[1]),
+                                                  C.byref(vec[2]), C.byref(head), env.engine._stream()))
+        self._version = env._state_version
 
     def __getattr__(self, name):
-        m = object.__getattribute__(self, "_map")
-        if name in m:
-            return object.__getattribute__(self, "_env").buffers.logical(m[name])
-        raise AttributeError(name)
+        cls = type(self)
+        if name in cls._RAW:
+            return self._env.buffers.logical(name)
+        if name in cls._ALIAS:
+            return self._env.buffers.logical(cls._ALIAS[name])
+        if name in cls._DERIVED:
+            self._refresh()
+            return self._vec[cls._DERIVED[name]]
+        if name == "heading_w":
+            self._refresh()
+            return self._heading
+        raise AttributeError(f"ArticulationData has no field '{name}' on this env surface")
 
 
 class _Articulation:
     def __init__(self, env):
         self._env = env
-        names = ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_w", "joint_pos", "joint_vel", "joint_acc",
-                 "applied_torque", "body_pos_w", "body_lin_vel_w")
-        mapping = {n: n for n in names}
-        mapping.update(root_link_pos_w="root_pos_w", root_link_quat_w="root_quat_w", body_link_pos_w="body_pos_w")
-        self.data = _BufferView(env, mapping)
+        self.data = _ArticulationData(env)
         asset = env.spec.layout.asset
         self.joint_names, self.body_names = list(asset.joint_names), list(env.spec.layout.asset_body_names)
-        self.num_joints = asset.num_joints
+        self.num_joints, self.num_bodies = asset.num_joints, len(self.body_names)
 
     def find_joints(self, name_keys, preserve_order: bool = False):
         from .cfg import resolve_matching_names
 
         return resolve_matching_names(name_keys, self.joint_names, preserve_order)
 
+    def find_bodies(self, name_keys, preserve_order: bool = False):
+        from .cfg import resolve_matching_names
 
-class _ContactSensor:
+        return resolve_matching_names(name_keys, self.body_names, preserve_order)
+
+
+class _ContactSensorData:
+    _RAW = ("net_forces_w_history", "current_air_time", "last_air_time", "current_contact_time", "last_contact_time")
+
     def __init__(self, env):
         self._env = env
-        names = ("net_forces_w_history", "current_air_time", "last_air_time", "current_contact_time", "last_contact_time")
-        self.data = _BufferView(env, {n: n for n in names})
+
+    def __getattr__(self, name):
+        if name in type(self)._RAW:
+            return self._env.buffers.logical(name)
+        if name == "net_forces_w":   # the newest history sample (slot 0 unless the provider writes ring slots)
+            slot = int(getattr(self._env.state_provider, "newest_history_slot", 0))
+            return self._env.buffers.logical("net_forces_w_history")[:, slot]
+        raise AttributeError(f"ContactSensorData has no field '{name}' on this env surface")
+
+
+class _ContactSensor:
+    """ContactSensor [IL] surface. With the compact body layout the timer tensors hold the timer bodies only and the
+    force history its own body list; ``body_tensors="full"`` gives every tensor every body, IsaacLab-style, so that one
+    ``SceneEntityCfg.body_ids`` indexes them all."""
+
+    def __init__(self, env):
+        self._env = env
+        self.data = _ContactSensorData(env)
         self.body_names = list(env.spec.layout.time_body_names)
+        self.history_body_names = list(env.spec.layout.hist_body_names)
 
     def find_bodies(self, name_keys, preserve_order: bool = False):
         from .cfg import resolve_matching_names
@@ -199,14 +262,107 @@ class _ContactSensor:
         t = self.data.current_contact_time
         return (t > 0.0) & (t < (dt + abs_tol))
 
+    def compute_first_air(self, dt: float, abs_tol: float = 1.0e-8) -> torch.Tensor:
+        t = self.data.current_air_time
+        return (t > 0.0) & (t < (dt + abs_tol))
+
+
+class _RayCasterData:
+    def __init__(self, env):
+        self._env = env
+        from . import terrain as _terrain
+        from .cfg import RayCasterCfg
+
+        self._starts = _terrain.grid_pattern_ray_starts(RayCasterCfg()).to(env.device)   # [R, 3] sensor frame
+
+    @property
+    def pos_w(self) -> torch.Tensor:
+        b = self._env.buffers
+        pos = b.logical("root_pos_w")
+        return torch.stack([pos[:, 0], pos[:, 1], b.logical("ray_sensor_pos_z")], dim=-1)
+
+    @property
+    def ray_hits_w(self) -> torch.Tensor:
+        """[N, R, 3]: x, y of the yaw-aligned grid pattern under the sensor, z = the hit heights the step consumes."""
+        b = self._env.buffers
+        heading = self._env.scene["robot"].data.heading_w
+        c, s = torch.cos(heading)[:, None], torch.sin(heading)[:, None]
+        sx, sy = self._starts[None, :, 0], self._starts[None, :, 1]
+        pos = b.logical("root_pos_w")
+        x = pos[:, 0:1] + c * sx - s * sy
+        y = pos[:, 1:2] + s * sx + c * sy
+        return torch.stack([x, y, b.logical("ray_hits_z")], dim=-1)
+
+
+class _RayCaster:
+    """The grid height scanner (V/velocity_env_cfg.py:70-77) as terms see it: ``data.pos_w``, ``data.ray_hits_w``."""
+
+    def __init__(self, env):
+        self.data = _RayCasterData(env)
+
+
+class _TerrainGeneratorCfgView:
+    """The attributes of TerrainGeneratorCfg [IL] the reference reads (V/mdp/utils.py:16-41)."""
+
+    class _Sub:
+        def __init__(self, proportion):
+            self.proportion = proportion
+
+    def __init__(self, cfg):
+        self.num_rows, self.num_cols, self.size, self.border_width = cfg.num_rows, cfg.num_cols, cfg.size, cfg.border_width
+        self.sub_terrains = {name: self._Sub(p) for name, p in zip(cfg.sub_terrains, cfg.proportions)}
+
+
+class _TerrainCfgView:
+    def __init__(self, cfg):
+        self.terrain_type = cfg.terrain_type
+        self.terrain_generator = _TerrainGeneratorCfgView(cfg) if cfg.terrain_type == "generator" else None
+
+
+class _Terrain:
+    """TerrainImporter [IL] surface: ``cfg.terrain_type``, ``cfg.terrain_generator``, ``terrain_origins`` [rows, cols, 3],
+    ``terrain_types`` [N] (column of every env's cell), ``env_origins`` [N, 3] (V/mdp/utils.py:42-127, events.py:240,257)."""
+
+    def __init__(self, env, terrain_origins=None, terrain_types=None, env_origins=None):
+        from . import terrain as _terrain
+
+        tcfg = env.spec.layout.terrain
+        self.cfg = _TerrainCfgView(tcfg)
+        n, dev = env.num_envs, env.device
+        if tcfg.terrain_type == "generator":
+            self.terrain_origins = (terrain_origins if terrain_origins is not None else _terrain.grid_origins(tcfg)).to(dev)
+            if terrain_types is None:   # TerrainImporter._compute_env_origins_curriculum [IL]: envs dealt round-robin to the columns
+                terrain_types = torch.div(torch.arange(n), max(n / tcfg.num_cols, 1.0), rounding_mode="floor").to(torch.long)
+            self.terrain_types = terrain_types.to(dev)
+            if env_origins is None:
+                env_origins = self.terrain_origins[0, self.terrain_types.clamp(max=tcfg.num_cols - 1)]
+        else:
+            self.terrain_origins, self.terrain_types = None, None
+            if env_origins is None:
+                env_origins = torch.zeros(n, 3)
+        self.env_origins = env_origins.to(dev, torch.float32)
+
 
 class _Scene(dict):
-    def __init__(self, env):
+    def __init__(self, env, **terrain_kw):
         super().__init__(robot=_Articulation(env))
         self.sensors = {"contact_forces": _ContactSensor(env)}
         self["contact_forces"] = self.sensors["contact_forces"]
+        if env.spec.R > 0:
+            self.sensors["height_scanner"] = _RayCaster(env)
+            self["height_scanner"] = self.sensors["height_scanner"]
+        self.terrain = _Terrain(env, **terrain_kw)
+        self.env_origins = self.terrain.env_origins
         self.num_envs = env.num_envs
         self.cfg = env.cfg.scene
+
+    def resolve(self, entity_cfg):
+        """``SceneEntityCfg.resolve(scene)`` [IL]: fill ``joint_ids`` / ``body_ids`` against this scene's entity."""
+        ent = self[entity_cfg.name]
+        if hasattr(ent, "joint_names"):
+            entity_cfg.resolve_joints(ent.joint_names)
+        entity_cfg.resolve_bodies(ent.body_names)
+        return entity_cfg
 
 
 # --------------------------------------------------------------------------------------------------
@@ -355,6 +511,55 @@ class ObservationManager(_ManagerBase):
         raise NotImplementedError("observation terms are evaluated inside the fused step; slice the group row instead")
 
 
+class _LazyLog(dict):
+    """``extras["log"]``: a dict that fills itself from a snapshot of the device logging buffer on first access."""
+
+    def __init__(self, env, snap: torch.Tensor):
+        super().__init__()
+        self._env, self._snap, self._built = env, snap, False
+
+    def _fill(self):
+        if not self._built:
+            self._built = True
+            super().update(self._env._build_log(self._snap))
+
+    def __getitem__(self, k):
+        self._fill()
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        self._fill()
+        return super().__contains__(k)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def get(self, k, default=None):
+        self._fill()
+        return super().get(k, default)
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
+
+
 # --------------------------------------------------------------------------------------------------
 # the env
 # --------------------------------------------------------------------------------------------------
@@ -382,7 +587,9 @@ class ManagerBasedRLEnv:
         self.max_episode_length = self.spec.max_episode_length
         self.common_step_counter = 0
         self.extras: dict[str, Any] = {}
-        self.scene = _Scene(self)
+        self._state_version = 0   # bumped whenever the physical state buffers change (derived views refresh lazily)
+        self.scene = _Scene(self, terrain_origins=kwargs.get("terrain_origins"), terrain_types=kwargs.get("terrain_types"),
+                            env_origins=kwargs.get("env_origins"))
         self.action_manager = ActionManager(self)
         self.observation_manager = ObservationManager(self)
         self.reward_manager = RewardManager(self)
@@ -432,15 +639,25 @@ class ManagerBasedRLEnv:
     def _obs_dict(self) -> dict[str, torch.Tensor]:
         return {g.name: self.buffers.obs[i] for i, g in enumerate(self.spec.obs) if g.dim > 0}
 
-    def _log(self) -> dict[str, torch.Tensor]:
-        b, log = self.buffers, {}
+    def _log(self) -> "_LazyLog":
+        """extras["log"] [IL]: the reset logging means of this step - one stream-ordered snapshot of the packed logging
+        buffer now, the ~30 named scalars only when somebody looks (rsl_rl reads them once per iteration)."""
+        return _LazyLog(self, self.buffers.log_all.clone())
+
+    def _build_log(self, snap: torch.Tensor) -> dict[str, torch.Tensor]:
+        log, kk = {}, max(self.spec.K, 1)
+        sums = snap[:kk] / self.max_episode_length_s
         for k, name in enumerate(self.reward_manager.active_terms):
-            log[f"Episode_Reward/{name}"] = b.log_episode_sum_mean[k] / self.max_episode_length_s
+            log[f"Episode_Reward/{name}"] = sums[k]
         for i, name in enumerate(self.termination_manager.active_terms):
-            log[f"Episode_Termination/{name}"] = b.log_done_term_count[i]
-        log["Metrics/base_velocity/error_vel_xy"] = b.log_metric_mean[0]
-        log["Metrics/base_velocity/error_vel_yaw"] = b.log_metric_mean[1]
+            log[f"Episode_Termination/{name}"] = snap[kk + i]
+        log["Metrics/base_velocity/error_vel_xy"] = snap[kk + nat.RL_MAX_DONE_TERMS]
+        log["Metrics/base_velocity/error_vel_yaw"] = snap[kk + nat.RL_MAX_DONE_TERMS + 1]
         return log
+
+    def invalidate_derived(self) -> None:
+        """Call after writing physical state into ``buffers`` by hand: the derived articulation views refresh lazily."""
+        self._state_version += 1
 
     # -- gym API -------------------------------------------------------------------------------------------
     def reset(self, seed: int | None = None, options: dict | None = None):
@@ -450,6 +667,7 @@ class ManagerBasedRLEnv:
         b = self.buffers
         self.state_provider.advance(self)
         self.state_provider.reset(self, self._all_ids, self._n_all)
+        self._state_version += 1
         b.done_bits.zero_()
         self.engine.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS, env_ids=self._all_ids,
                          n_env_ids=self._n_all, **self._rng_kwargs())
@@ -464,6 +682,7 @@ class ManagerBasedRLEnv:
         self.common_step_counter += 1
         eng.step_pre_reset(b, **self._rng_kwargs())                                  # 3-5: dones, rewards, reset ids
         self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
+        self._state_version += 1
         if self.pit_grid is None:
             eng.step_post_reset(b, **self._rng_kwargs())                             # 6b manager reset, 7 command, 9 obs
         else:   # the pit branch of _update_command sits between the command update and the observations

@@ -1,10 +1,23 @@
 """Rollout storage and the multi-GPU hand-off to PPO.
 
 Envs shard by contiguous env-id ranges, one process per GPU; the MDP step itself needs no collective
-(SURVEY.md 8(e)). The one exchange on the path is here: at the end of a rollout every rank all-gathers its
-``[steps, N_local, width]`` buffer so that the learner sees the global batch (NCCL over NVLink 5 / NVSwitch through
-``torch.distributed``; ``gloo`` in the CPU tests). rsl_rl's own alternative - keep rollouts local and all-reduce
-gradients - needs nothing from this module.
+(SURVEY.md 8(e)). The one exchange on the path is here (reference recipe: README.md:323-337,
+scripts/reinforcement_learning/rsl_rl/train.py:143-150): every rank all-gathers its rollout so that the learner sees
+the global batch (NCCL over NVLink 5 / NVSwitch through ``torch.distributed``; ``gloo`` in the CPU tests).
+
+Two things keep that exchange off the critical path of the rollout:
+
+* **no copy into the rollout**: a step's results are *written* there. ``RolloutStorage`` owns one contiguous slab per
+  step - policy rows, critic rows, reward, done masks (+ the policy's own outputs) - and ``bind(buffers, t)`` points
+  the step kernels' outputs at slab ``t`` (observation rows take any pitch, everything else is a plain ``[N]`` plane),
+  so ``RolloutBuffer.add``'s nine slice copies per step do not exist;
+* **streamed gather**: ``gather_step(t)`` issues the all-gather of slab ``t`` on a side stream as soon as step ``t`` has
+  finished, while step ``t + 1`` runs; ``finish()`` joins. What stays exposed is what the links cannot hide: every rank
+  has to *receive* ``(world - 1) x steps x N x width`` bytes - 881 MB for 8 x 4096 envs x 24 steps - through its own
+  NVLink ingress.
+
+rsl_rl's own alternative - keep rollouts local and all-reduce gradients - needs nothing from
+this module; ``bench.py`` measures it beside the gather.
 """
 
 from __future__ import annotations
@@ -27,8 +40,97 @@ def shard_range(num_envs_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+class RolloutStorage:
+    """``steps`` slabs of ``N * width`` fp32 words each; inside a slab every quantity is its own contiguous plane:
+
+        obs_policy [N, Dp] | obs_critic [N, Dc] | action [N, A] | mean [N, A] | sigma [N, A] | reward [N] | value [N] |
+        log_prob [N] | done [N] (fp32 view of: terminated u8 [N], truncated u8 [N], 2 N spare bytes)
+
+    The step kernels write obs_policy / obs_critic / reward / terminated / truncated of step ``t`` straight into slab
+    ``t`` (``bind``); the policy side fills action / mean / sigma / value / log_prob. ``gathered`` (allocated when the
+    process group has more than one rank) is ``[steps, world, N * width]``: slab ``t`` of every rank, rank-major, so the
+    global env id of row ``e`` of rank ``r`` is ``r * N + e`` - and ``gathered[t]`` is exactly the contiguous output an
+    all-gather of ``data[t]`` produces (no staging copy)."""
+
+    def __init__(self, spec: StepSpec, num_envs: int, steps: int, device: torch.device | str, group=None):
+        self.spec, self.N, self.steps, self.group = spec, int(num_envs), int(steps), group
+        self.width = rollout_row_width(spec)
+        dev = torch.device(device)
+        self.data = torch.zeros(self.steps, self.N * self.width, device=dev)
+        N, dp, dc, a = self.N, spec.obs[0].dim, spec.obs[1].dim, spec.A
+        self._planes, o = {}, 0
+        for name, w in (("obs_policy", dp), ("obs_critic", dc), ("action", a), ("mean", a), ("sigma", a), ("reward", 1),
+                        ("value", 1), ("log_prob", 1), ("done", 1)):
+            self._planes[name] = (o, w)
+            o += N * w
+        assert o == N * self.width
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.gathered = torch.empty(self.steps, self.world, self.N * self.width, device=dev) if self.world > 1 else None
+        self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._events = [torch.cuda.Event() for _ in range(self.steps)] if dev.type == "cuda" else None
+        self._whole = None   # [world, steps * N * width], only for the un-streamed baseline (gather_all)
+
+    # ---- views -----------------------------------------------------------------------------------------------------
+    def plane(self, name: str, t: int, data: torch.Tensor | None = None) -> torch.Tensor:
+        """Quantity ``name`` of step ``t``: ``[N, w]`` (``[N]`` for scalars). ``data``: another ``[steps, N * width]`` tensor
+        of the same layout (e.g. one rank's part of ``gathered``: ``gathered[:, r]``)."""
+        o, w = self._planes[name]
+        slab = (self.data if data is None else data)[t]
+        v = slab[o:o + self.N * w]
+        return v.view(self.N, w) if w > 1 else v
+
+    def done_bytes(self, t: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """terminated / truncated of step ``t`` as uint8 ``[N]`` views into the slab's done plane."""
+        raw = self.plane("done", t).view(torch.uint8)
+        return raw[: self.N], raw[self.N: 2 * self.N]
+
+    def bind(self, buffers, t: int) -> None:
+        """Point the outputs of ``buffers``' step launches at slab ``t`` (call before issuing - or capturing - the step)."""
+        term, trunc = self.done_bytes(t)
+        obs = [self.plane("obs_policy", t) if self.spec.obs[0].dim > 0 else None,
+               self.plane("obs_critic", t) if self.spec.obs[1].dim > 0 else None]
+        buffers.rebind_outputs(obs=obs, reward=self.plane("reward", t), terminated=term, truncated=trunc)
+
+    # ---- hand-off ---------------------------------------------------------------------------------------------------
+    def gather_step(self, t: int, after: "torch.cuda.Stream | None" = None) -> None:
+        """All-gather slab ``t`` on the side stream, ordered after everything ``after`` (default: the current stream) has
+        been given so far. Returns immediately; the next step can be issued right away."""
+        if self.world == 1:
+            return
+        if self._side is None:   # CPU process groups (gloo tests): synchronous
+            dist.all_gather_into_tensor(self.gathered[t].view(-1), self.data[t], group=self.group)
+            return
+        src = after if after is not None else torch.cuda.current_stream(self.data.device)
+        self._events[t].record(src)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._events[t])
+            dist.all_gather_into_tensor(self.gathered[t].view(-1), self.data[t], group=self.group)
+
+    def gather_all(self) -> torch.Tensor | None:
+        """The un-streamed form: ONE all-gather of the whole rollout on the current stream, into ``[world, steps * N *
+        width]`` (the baseline ``gather_step`` is measured against)."""
+        if self.world == 1:
+            return None
+        if self._whole is None:
+            self._whole = torch.empty(self.world, self.steps * self.N * self.width, device=self.data.device)
+        dist.all_gather_into_tensor(self._whole.view(-1), self.data.view(-1), group=self.group)
+        return self._whole
+
+    def finish(self) -> None:
+        """Make the current stream wait for every gather issued so far."""
+        if self.world > 1 and self._side is not None:
+            torch.cuda.current_stream(self.data.device).wait_stream(self._side)
+
+    def global_plane(self, name: str, t: int) -> torch.Tensor:
+        """``[world * N, w]`` view-copy of quantity ``name`` of step ``t`` over all ranks (rank-major = global env ids)."""
+        if self.world == 1:
+            return self.plane(name, t)
+        return torch.cat([self.plane(name, t, self.gathered[:, r]) for r in range(self.world)], dim=0)
+
+
 class RolloutBuffer:
-    """``[steps, N_local, width]`` fp32, filled step by step straight from the step outputs."""
+    """``[steps, N_local, width]`` fp32 rows filled with ``add`` - the copy-based form (kept for row-major consumers and
+    as the baseline of ``RolloutStorage``; nine slice copies per step)."""
 
     def __init__(self, spec: StepSpec, num_envs: int, steps: int, device: torch.device | str):
         self.spec, self.N, self.steps = spec, num_envs, steps

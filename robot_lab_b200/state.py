@@ -85,6 +85,7 @@ class StateBuffers:
             raise nat.NativeError("StateBuffers live on a CUDA device - the MDP step has no CPU path")
         N, dev = self.N, self.device
         self.kind: dict[str, str] = {}
+        self._cache: dict = {}
 
         def shape_of(name, comps, pref):
             c = comps(spec)
@@ -112,9 +113,12 @@ class StateBuffers:
         self.cmd_uniforms: torch.Tensor | None = None
         self.obs_uniforms: list[torch.Tensor | None] = [None, None]
         # reset logging
-        self.log_episode_sum_mean = torch.zeros(max(spec.K, 1), device=dev)
-        self.log_done_term_count = torch.zeros(nat.RL_MAX_DONE_TERMS, device=dev)
-        self.log_metric_mean = torch.zeros(2, device=dev)
+        # one contiguous buffer (a per-step snapshot of the log is then ONE small device copy), three views
+        kk = max(spec.K, 1)
+        self.log_all = torch.zeros(kk + nat.RL_MAX_DONE_TERMS + 2, device=dev)
+        self.log_episode_sum_mean = self.log_all[:kk]
+        self.log_done_term_count = self.log_all[kk:kk + nat.RL_MAX_DONE_TERMS]
+        self.log_metric_mean = self.log_all[kk + nat.RL_MAX_DONE_TERMS:]
 
     # ---- logical <-> device --------------------------------------------------------------------
     def _to_device(self, name: str, logical: torch.Tensor) -> None:
@@ -165,19 +169,51 @@ class StateBuffers:
             return nat.field_of(x, None)
         return nat.field_of(x, self.kind[name])
 
-    def state_view(self) -> nat.RlStateView:
+    # The three pointer structs of a call are built once per StateBuffers: the tensors they point to never move (every
+    # update is an in-place copy). Callers that need a private, modifiable struct pass fresh=True.
+    def state_view(self, fresh: bool = False) -> nat.RlStateView:
+        if not fresh and self._cache.get("state") is not None:
+            return self._cache["state"]
         v = nat.RlStateView()
         for name in nat._STATE_FIELDS:
             setattr(v, name, self.field(name))
+        if not fresh:
+            self._cache["state"] = v
         return v
 
-    def mdp_state(self) -> nat.RlMdpState:
+    def mdp_state(self, fresh: bool = False) -> nat.RlMdpState:
+        if not fresh and self._cache.get("mdp") is not None:
+            return self._cache["mdp"]
         m = nat.RlMdpState()
         for name in nat._MDP_FIELDS:
             setattr(m, name, self.field(name))
+        if not fresh:
+            self._cache["mdp"] = m
         return m
 
-    def step_out(self) -> nat.RlStepOut:
+    def step_out(self, fresh: bool = False) -> nat.RlStepOut:
+        if not fresh and self._cache.get("out") is not None:
+            return self._cache["out"]
+        o = self._step_out()
+        if not fresh:
+            self._cache["out"] = o
+        return o
+
+    def rebind_outputs(self, obs: list | None = None, reward: torch.Tensor | None = None,
+                       terminated: torch.Tensor | None = None, truncated: torch.Tensor | None = None) -> None:
+        """Point the step's results at other device tensors (e.g. the current row of a rollout buffer: the kernels
+        write observation rows with any pitch, so a rollout needs no copy of the step outputs)."""
+        if obs is not None:
+            self.obs = list(obs)
+        if reward is not None:
+            self.reward = reward
+        if terminated is not None:
+            self.terminated = terminated
+        if truncated is not None:
+            self.truncated = truncated
+        self._cache.pop("out", None)
+
+    def _step_out(self) -> nat.RlStepOut:
         o = nat.RlStepOut()
         for g in range(nat.RL_NUM_OBS_GROUPS):
             if self.obs[g] is not None:

@@ -255,12 +255,12 @@ def test_empty_inputs_and_bad_arguments(native_lib):
     for phases in (nat.PHASE_COMPACT, nat.PHASE_RESET | nat.PHASE_REWARDS):
         with pytest.raises(nat.NativeError):
             eng.step(b, phases=phases)
-    bad = b.step_out()
+    bad = b.step_out(fresh=True)
     bad.terminated = None
     with pytest.raises(nat.NativeError):
         nat.check(lib.rl_step(eng._ctx, 64, C.byref(st), C.byref(mdp), C.byref(bad), C.byref(rnd),
                               nat.PHASE_RESET | nat.PHASE_COMMAND | nat.PHASE_OBS, None, None, stream))
-    st2 = b.state_view()
+    st2 = b.state_view(fresh=True)
     st2.ray_hits_z = nat.RlField(None, 0, 0)
     with pytest.raises(nat.NativeError):
         nat.check(lib.rl_step(eng._ctx, 64, C.byref(st2), C.byref(mdp), C.byref(out), C.byref(rnd), nat.PHASE_OBS, None, None, stream))

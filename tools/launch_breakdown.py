@@ -2,7 +2,7 @@
 no debug buffer): process_action | rl_step(ALL|SKIP) | rl_step(RESET|COMMAND|OBS on reset ids) and a few phase
 subsets of the fused kernel. Rotates over independent state sets larger than L2.
 
-Usage (GPU box): python tools/launch_breakdown.py [num_envs] [warps] [task_key] [envs_per_cta: 32 | 64] [--short]
+Usage (GPU box): python tools/launch_breakdown.py [num_envs] [warps] [task_key] [envs_per_cta: 32] [--short] [--pdl]
 """
 import sys
 from pathlib import Path
@@ -73,7 +73,7 @@ for b in sets:  # reset ids valid for the post-reset case
 torch.cuda.synchronize()
 print(f"{key} N={N} warps={W} envs_per_cta={EPC or 32} state sets={n_sets}; mean reset envs per step: "
       f"{sum(int(b.n_reset.item()) for b in sets) / len(sets):.1f}")
-for pdl in (False,):
+for pdl in ((False, True) if "--pdl" in sys.argv else (False,)):
     eng.set_pdl(pdl)
     for name, fn in CASES.items():
         g = torch.cuda.CUDAGraph()
