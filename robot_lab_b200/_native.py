@@ -263,6 +263,8 @@ def load() -> C.CDLL:
                                             C.POINTER(RlMdpState), C.c_void_p, C.POINTER(RlRandom), C.c_void_p]
     lib.rl_height_scan_cast.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlHeightField), C.POINTER(RlStateView),
                                         C.c_void_p]
+    lib.rl_derived_views.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlStateView), C.POINTER(RlField), C.POINTER(RlField),
+                                     C.POINTER(RlField), C.POINTER(RlField), C.c_void_p]
     lib.rl_contact_sensor_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlStateView),
                                              C.POINTER(C.c_int32), C.c_float, C.c_float, C.c_int32, C.c_void_p]
     lib.rl_process_action.argtypes = [C.c_void_p, C.c_int64, C.POINTER(RlField), C.POINTER(RlMdpState),

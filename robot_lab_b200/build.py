@@ -39,7 +39,8 @@ NVCC_FLAGS = [
 # shared_ctx / persistent / nosplit were measured in round 2 - profiles/r2_variant_probe.txt - and removed.)
 VARIANTS: dict[str, list[str]] = {
     "v2dev": ["-DRL_V2_DEV_ONE=1"],   # cluster kernels for Go2-rough only: seconds to compile while iterating on them
-    "rolled": ["-DRL_V2_UNROLL=0"],   # A/B: term loops rolled as in the general kernel (smaller code, serial iterations)
+    "stamps": ["-DRL_V2_STAMPS=1"],     # clock stamps per CTA / warp into the debug buffer (tools/v2_timeline.py)
+    "unrolled": ["-DRL_V2_UNROLL=1"],   # A/B: term loops of the new kernels fully unrolled against the baked spec
 }
 
 

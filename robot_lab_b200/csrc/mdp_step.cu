@@ -225,10 +225,9 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
     if (need_rays && !rays_bulk) span_load_elems(sm + L.rays, L.rays_pitch, a.rays, R, env0, nvalid, ids, tid, NT);
     if (ph & RL_PHASE_REWARDS)
       for (int i = tid; i < K * kE; i += NT) {
-        sm[L.arrive + i] = __int_as_float(0);
         if ((a.rw_zero >> (i / kE)) & 1ull) {   // weight-0 terms: no task evaluates them
           sm[L.stepr + i] = 0.f;
-          sm[L.termv + (i / kE) * kTermParts * kE + (i % kE)] = 0.f;
+          sm[L.termv + i] = 0.f;
         }
       }
     RL_SUB(2);                  // span loads issued
@@ -375,32 +374,11 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
         if (!(ph & RL_PHASE_REWARDS)) return;
         const float raw = reward_term<CN>(rt, c_spec[a.slot].rewards[tk.a], S, L, sm, e, c, tk.lo, tk.hi);
         const int k = tk.a;
-        float full_raw = raw;
-        bool finish = true;
-        if (tk.pad) {
-          // one part of a split term: publish the partial sum; whoever arrives last (per env) adds the parts in
-          // part order and finishes the term - no serial tail for it in stage 2
-          const int parts = tk.col0;
-          SMF(L.termv, kTermParts * k + tk.b) = raw;
-          __threadfence_block();
-          const int old = atomicAdd(reinterpret_cast<int*>(sm) + L.arrive + k * kE + e, 1);
-          finish = (old == parts - 1);
-          if (finish) {
-            __threadfence_block();
-            full_raw = *(volatile float*)&SMF(L.termv, kTermParts * k);
-#pragma unroll
-            for (int p = 1; p < kTermParts; ++p)
-              if (p < parts) full_raw += *(volatile float*)&SMF(L.termv, kTermParts * k + p);
-            if (rt.type == RL_REW_UNDESIRED_CONTACTS) full_raw = full_raw * c.gate;   // the parts are raw counts
-          }
-        }
-        if (finish) {
-          // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
-          const float val = (full_raw * rt.weight) * S.step_dt;
-          SMF(L.termv, kTermParts * k) = val;
-          SMF(L.sums, k) = SMF(L.sums, k) + val;
-          SMF(L.stepr, k) = rl_div(val, S.step_dt);
-        }
+        // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
+        const float val = (raw * rt.weight) * S.step_dt;
+        SMF(L.termv, k) = val;
+        SMF(L.sums, k) = SMF(L.sums, k) + val;
+        SMF(L.stepr, k) = rl_div(val, S.step_dt);
       } else if (tk.kind == TK_OBS) {
         if (!(ph & RL_PHASE_OBS) || a.out.obs[tk.a] == nullptr) return;
         obs_task(sm, L, S, ot, c_spec[a.slot].obs[tk.a].terms[tk.b], corrupt, a, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
@@ -442,16 +420,16 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 #pragma unroll 1
         for (uint64_t m = a.rw_late & ~a.rw_zero; m != 0; m &= m - 1) {
           const int k = __ffsll((long long)m) - 1;
-          const float raw = ((a.rw_isterm >> k) & 1ull) ? (terminated ? 1.f : 0.f) : SMF(L.termv, kTermParts * k);
+          const float raw = ((a.rw_isterm >> k) & 1ull) ? (terminated ? 1.f : 0.f) : SMF(L.termv, k);
           const float val = (raw * a.rw_weight[k]) * S.step_dt;
-          SMF(L.termv, kTermParts * k) = val;
+          SMF(L.termv, k) = val;
           SMF(L.sums, k) = SMF(L.sums, k) + val;
           SMF(L.stepr, k) = rl_div(val, S.step_dt);
         }
       }
       RL_SUB(3);                // late terms finished
 #pragma unroll 1
-      for (int k = 0; k < K; ++k) total += SMF(L.termv, kTermParts * k);   // manager order
+      for (int k = 0; k < K; ++k) total += SMF(L.termv, k);   // manager order
       SMF(L.rew, 0) = total;
       RL_SUB(4);                // reward summed
     }
@@ -863,7 +841,10 @@ int fill_args(RlCtx* ctx, KArgs& a, int64_t num_envs, const RlStateView* st, con
          (1u << IF_BPOS) | (1u << IF_BVEL);
   if (mode == 0 && (ph & RL_PHASE_REWARDS)) m |= 1u << IF_SUMS;
   if (mode == 0 && (ph & RL_PHASE_COMMAND)) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
-  if (mode == 0 && (ph & RL_PHASE_RESET)) m |= (1u << IF_SUMS) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_HEAD) | (1u << IF_CMDU);
+  // (IF_PACT: the RESET launch stores the previous-action rows of every tile that resets anything - the live lanes must
+  //  carry their own values, not whatever the record held. Found in round 2: at more than one wave of tiles the general
+  //  kernel wrote stale shared memory into prev_action of envs that were NOT reset.)
+  if (mode == 0 && (ph & RL_PHASE_RESET)) m |= (1u << IF_SUMS) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_HEAD) | (1u << IF_CMDU) | (1u << IF_PACT);
   if (mode == 0 && (ph & RL_PHASE_OBS) && s.num_rays > 0) m |= 1u << IF_RAYPOS;
   uint32_t v4 = 0;
   for (int f = 0; f < IF_COUNT; ++f) {

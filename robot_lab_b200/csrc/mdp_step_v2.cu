@@ -29,7 +29,7 @@
 // tensors, a spec that is not baked) run the general kernel.
 
 #ifndef RL_V2_UNROLL
-#define RL_V2_UNROLL 1
+#define RL_V2_UNROLL 0   // measured (profiles/r2_summary.md): unrolling the term loops costs more cold code than it saves
 #endif
 #if RL_V2_UNROLL
 #define RL_TERM_LOOP _Pragma("unroll")   // see csrc/mdp_terms.cuh: the term loops unroll against the baked spec
@@ -40,6 +40,19 @@
 
 #ifndef RL_V2_DEV_ONE
 #define RL_V2_DEV_ONE 0   // development builds: compile the cluster kernels for Go2-rough only (seconds instead of minutes)
+#endif
+
+#ifndef RL_V2_STAMPS
+#define RL_V2_STAMPS 0   // build variant "stamps": clock64 / globaltimer stamps per CTA and warp into KArgs::dbg (tools/v2_timeline.py)
+#endif
+#if RL_V2_STAMPS
+#define V2_STAMP(slot) do { if (a.k.dbg != nullptr && lane == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#define V2_STAMP_T0(slot) do { if (a.k.dbg != nullptr && tid == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#define V2_GTIME(slot) do { if (a.k.dbg != nullptr && tid == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
+#else
+#define V2_STAMP(slot) do { } while (0)
+#define V2_STAMP_T0(slot) do { } while (0)
+#define V2_GTIME(slot) do { } while (0)
 #endif
 
 namespace {
@@ -156,6 +169,7 @@ struct Sched2 {
   uint64_t late;          // reward terms finished by the final sum (is_terminated)
   uint32_t hist_roles;    // roles that stage the contact-force rows and run the norm prepass
   int obs_owner[RL_NUM_OBS_GROUPS];
+  int log_parts;          // POST: number of TK_LOG tasks per tile (= ticket arrivals per tile)
 };
 
 __host__ __device__ constexpr bool term_uses_hist(const RlRewardTerm& t) {
@@ -206,6 +220,15 @@ __host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int k
         for (int ti = 0; ti < s.obs[g].n_terms; ++ti)
           if (s.obs[g].terms[ti].type == RL_OBS_GENERATED_COMMANDS) c += 40;
       sc.t[n] = Task{TK_COMMAND, 0, 0, 0, 0, 0, 0, 0}; cost[n] = c; lo_bin[n] = 0; hi_bin[n] = 1; ++n;
+      // logging reductions of the reset + zeroing of the reset envs' sums / stored actions, in up to four parts (part p
+      // takes the quantities q = p mod parts): any warp but the command's
+      const int parts = BINS > 4 ? 4 : (BINS > 1 ? BINS - 1 : 1);
+      sc.log_parts = parts;
+      for (int p = 0; p < parts; ++p) {
+        sc.t[n] = Task{TK_LOG, 0, (uint8_t)p, 0, 0, 0, (uint16_t)parts, 0};
+        cost[n] = 120 + 40 * ((s.num_reward_terms + RL_MAX_DONE_TERMS + 2 + parts - 1) / parts);
+        lo_bin[n] = BINS > 1 ? 1 : 0; hi_bin[n] = BINS; ++n;
+      }
     }
     for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
       int col0 = 0;
@@ -297,6 +320,7 @@ __host__ __device__ constexpr uint32_t role_field_mask(const RlStepSpec& s, cons
     if (t.owner / W != role) continue;
     if (t.kind == TK_REWARD) m |= reward_fields(s.rewards[t.a].type);
     else if (t.kind == TK_OBS) m |= obs_fields(s.obs[t.a].terms[t.b].type);
+    else if (t.kind == TK_LOG) m |= (1u << IF_SUMS) | (1u << IF_MXY) | (1u << IF_MYAW);
   }
   return m & v2_field_mask(s, kind);
 }
@@ -360,11 +384,13 @@ struct Cfg2 {
   static constexpr uint64_t late = sched.late;
   static constexpr uint32_t hist_roles = sched.hist_roles;
   static constexpr int obs_owner0 = sched.obs_owner[0], obs_owner1 = sched.obs_owner[1];
+  static constexpr int log_parts = sched.log_parts;
 };
 
-// all tasks of one bin, in schedule order, behind ONE per-env context (members no task of the bin reads fold away)
-template <class B, class CF, int BIN, class F>
-__device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f) {
+// all tasks of one bin, in schedule order, behind ONE per-env context (members no task of the bin reads fold away);
+// `fin` closes the bin's straight-line code (every warp runs exactly one bin, also an empty one)
+template <class B, class CF, int BIN, class F, class FIN>
+__device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f, FIN&& fin) {
   constexpr Layout L = CF::L;
   const EnvCtx c = make_ctx(sm, L, e);
   static_for(std::make_integer_sequence<int, CF::n_tasks>{}, [&](auto ic) {
@@ -377,36 +403,48 @@ __device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f) {
       f(ic, tk, rt, ot, corrupt, c);
     }
   });
+  fin();
 }
-template <class B, class CF, int LO, int HI, class F>
-__device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, const int e, F&& f) {
+template <class B, class CF, int LO, int HI, class F, class FIN>
+__device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, const int e, F&& f, FIN&& fin) {
   if constexpr (HI - LO == 1) {
-    bin_tasks<B, CF, LO>(sm, e, f);
+    bin_tasks<B, CF, LO>(sm, e, f, fin);
   } else {
     constexpr int MID = (LO + HI) / 2;
-    if (bin < MID) dispatch_bin<B, CF, LO, MID>(bin, sm, e, f); else dispatch_bin<B, CF, MID, HI>(bin, sm, e, f);
+    if (bin < MID) dispatch_bin<B, CF, LO, MID>(bin, sm, e, f, fin); else dispatch_bin<B, CF, MID, HI>(bin, sm, e, f, fin);
   }
 }
 
-// the load every CTA starts with: one thread, one instruction per field
+// The load every CTA starts with: one instruction per field. Thread 0 arms the mbarrier with the byte count of the whole
+// record (arm_loads, followed by a CTA barrier); then lane 0 of EVERY warp issues its share of the copies (issue_loads):
+// the tensor maps live in the kernel's parameter bank, the first touch of each is a ~300-cycle miss, and one thread
+// issuing all ~20 of them in a row serialised those misses into 2.9 us of a 4096-env launch (measured: profiles/
+// r2_summary.md). Spread over the warps they overlap.
 template <class CF>
-__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar, const bool with_hist) {
-  constexpr Layout L = CF::L;
+__device__ __forceinline__ void arm_loads(const V2Args& a, const uint32_t role, uint64_t* bar, const bool with_hist) {
   constexpr Scalars S = CF::S;
   constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
   mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (a.k.use_pdl) pdl_wait();   // the copies read what the predecessor on the stream wrote
   uint32_t bytes = a.role_bytes[role];
   if (with_hist) bytes += (uint32_t)(CF::E * HW * 4);
   mbar_expect_tx(bar, bytes);
+}
+template <class CF>
+__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar,
+                                            const bool with_hist, const int warp) {
+  constexpr Layout L = CF::L;
+  constexpr Scalars S = CF::S;
+  constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
+  if (with_hist && warp == 0)   // the largest transfer first
+    bulk_g2s(sm + L.hist, static_cast<const float*>(a.k.hist.ptr) + (size_t)env0 * HW, (uint32_t)(CF::E * HW * 4), bar);
+  const uint32_t m = a.role_mask[role];
+  const int n = __popc(m);
 #pragma unroll 1
-  for (uint32_t m = a.role_mask[role]; m != 0; m &= m - 1) {
-    const int f = __ffs((int)m) - 1;
+  for (int i = warp; i < n; i += CF::NT / 32) {
+    const int f = (int)__fns(m, 0u, i + 1);   // the (i+1)-th staged field
     tma_load_2d(sm + a.field_word[f] * CF::E, &a.tm[f], env0, 0, bar);
   }
-  if (with_hist)
-    bulk_g2s(sm + L.hist, static_cast<const float*>(a.k.hist.ptr) + (size_t)env0 * HW, (uint32_t)(CF::E * HW * 4), bar);
 }
 
 // reset_buf.nonzero() [IL]: ascending reset ids from one 32-bit done mask per tile (runs in the ONE CTA whose ticket
@@ -473,27 +511,38 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
   const int env0 = cluster_id * E;
   const long long env = (long long)env0 + e;
   const bool my_hist = ((CF::hist_roles >> role) & 1u) != 0 && S.num_hist_bodies > 0;
+  V2_GTIME(0); V2_STAMP_T0(1);
   if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
   if (a.k.use_pdl) pdl_launch_dependents();   // the successor's prologue may overlap this kernel
   if (tid == 0) {
     s_last = 0;
-    issue_loads<CF>(sm, a, role, env0, &s_bar, my_hist);   // (waits for the predecessor first when PDL is on)
+    arm_loads<CF>(a, role, &s_bar, my_hist);
+  }
+  V2_STAMP_T0(9);
+  __syncthreads();                            // the armed mbarrier is visible to every issuing warp
+  V2_STAMP_T0(10);
+  if (a.k.use_pdl) pdl_wait();                // no global access of this kernel before its predecessor is complete
+  if (lane == 0) {
+    issue_loads<CF>(sm, a, role, env0, &s_bar, my_hist, warp);
     // the post-reset launch of this env step streams the tile's ray hits: have them in L2 by then
-    if (role == 0 && a.prefetch_rays != nullptr)
+    if (role == 0 && warp == kWarps2 - 1 && a.prefetch_rays != nullptr)
       prefetch_l2(a.prefetch_rays + (size_t)env0 * a.prefetch_row_bytes, (uint32_t)(E * a.prefetch_row_bytes));
   }
+  V2_STAMP_T0(11);
   // per-joint constants: constant bank -> shared
   for (int i = tid; i < S.num_joints; i += kThreads2)
     DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
       sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
       sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
     });
+  V2_STAMP_T0(12);
   if (role == 0)   // weight-0 terms: no task writes their slot of the final sum
     for (int i = tid; i < K * E; i += kThreads2)
       if ((a.k.rw_zero >> (i / E)) & 1ull) sm[L.termv + i] = 0.f;
-  if (a.k.use_pdl && tid != 0) pdl_wait();   // no global access of this kernel before its predecessor is complete
   __syncthreads();           // mbarrier init + the stores above visible to the CTA
+  V2_STAMP_T0(2);
   mbar_wait(&s_bar, 0);      // record resident
+  V2_STAMP_T0(3);
   if (my_hist) {
     // contact-force norm prepass: (tile, body) items over the warps, lane = env; ONE code copy for every consumer
     constexpr int Bh = S.num_hist_bodies;
@@ -506,10 +555,16 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
     __syncthreads();
   }
   if (C > 1) cluster_wait_acquire();
+  V2_STAMP_T0(4);
 
   float* const termv0 = C > 1 ? map_to_rank(sm + L.termv, 0u) : sm + L.termv;   // role 0's term values
   const FieldD f_sums = a.k.outf[OF_SUMS], f_stepr = a.k.outf[OF_STEPR];
   unsigned early_prev = 0xffffffffu;
+  // In a cluster the weighted value goes to role 0 first (DSMEM), the CTA's arrival at the cluster barrier follows, and the
+  // global result rows leave AFTER it: an arrive.release waits for the thread's earlier stores, global ones included.
+  constexpr int kPend = 6;
+  float p_sum[kPend], p_step[kPend];
+  int p_k[kPend], np = 0;
   dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
       [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm&, const bool, const EnvCtx& c) __attribute__((always_inline)) {
     if (tk.kind == TK_REWARD) {
@@ -518,8 +573,13 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
       // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
       const float val = (raw * rt.weight) * S.step_dt;
       termv0[k * E + e] = val;
-      static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)k * f_sums.cs + env] = SMF(L.sums, k) + val;
-      if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = rl_div(val, S.step_dt);
+      const float ns = SMF(L.sums, k) + val, sr = rl_div(val, S.step_dt);
+      if (C > 1 && np < kPend) {
+        p_sum[np] = ns; p_step[np] = sr; p_k[np] = k; ++np;
+      } else {
+        static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)k * f_sums.cs + env] = ns;
+        if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = sr;
+      }
     } else if (tk.kind == TK_DONES) {
       // TerminationManager.compute [IL]: bits | terminated << 8 | time_out << 9
       const int eplen_now = __float_as_int(SMF(L.eplen, 0)) + 1;
@@ -549,10 +609,20 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
         early_prev = ticket_arrive_release(a.k.ticket);
       }
     }
+  }, [&]() __attribute__((always_inline)) {
+    if (C > 1) cluster_arrive_release();   // this warp's term values are in role 0's record
+#pragma unroll
+    for (int i = 0; i < kPend; ++i)
+      if (i < np) {
+        static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)p_k[i] * f_sums.cs + env] = p_sum[i];
+        if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)p_k[i] * f_stepr.cs + env] = p_step[i];
+      }
   });
+  V2_STAMP(16 + warp);
   if (lane == 0 && early_prev == (unsigned)(a.k.vgrid - 1)) s_last = 1;   // this tile's ticket was the last of the launch
-  if (C > 1) { cluster_arrive_release(); if (role != 0) return; cluster_wait_acquire(); }
+  if (C > 1) { if (role != 0) return; cluster_wait_acquire(); }
   __syncthreads();   // the term values of role 0's own warps, the termination flags, s_last
+  V2_STAMP_T0(5);
 
   // ---- final sum: one warp per tile adds the weighted values up in manager order (is_terminated is finished here) ----
   if (slot == 0) {
@@ -568,18 +638,23 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
         if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = rl_div(val, S.step_dt);
       }
     }
+    float tv[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) tv[k] = SMF(L.termv, k);    // all K loads in flight, then the serial sum
     float total = 0.f;
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) total += SMF(L.termv, k);   // manager order
+#pragma unroll
+    for (int k = 0; k < K; ++k) total += tv[k];             // manager order
     if (a.k.out.reward) a.k.out.reward[env] = total;
     if (f_stepr.ptr)
 #pragma unroll 1
       for (uint64_t m = a.k.rw_zero; m != 0; m &= m - 1)
         static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)(__ffsll((long long)m) - 1) * f_stepr.cs + env] = 0.f;
   }
+  V2_STAMP_T0(6); V2_GTIME(7);
   if (s_last) {   // CTA-uniform: ordered compaction of the reset ids by the CTA that arrived last
     __threadfence();
     compact_reset_ids<NW>(a.k, a.k.vgrid, s_cnt, tid);
+    V2_GTIME(8);
   }
 }
 
@@ -604,6 +679,7 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
   const int cluster_id = (int)blockIdx.x / C;
   const int env0 = cluster_id * E;
   const long long env = (long long)env0 + e;
+  V2_GTIME(0); V2_STAMP_T0(1);
   if (C > 1) cluster_arrive_relaxed();
   if (a.k.use_pdl) pdl_launch_dependents();
   for (int i = tid; i < S.num_joints; i += kThreads2)
@@ -613,25 +689,28 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
     });
   if (tid == 0) {
     s_last = 0;
-    issue_loads<CF>(sm, a, role, env0, &s_bar, false);   // (waits for the predecessor first when PDL is on)
-  } else if (a.k.use_pdl) {
-    pdl_wait();
+    arm_loads<CF>(a, role, &s_bar, false);
   }
+  __syncthreads();
+  if (a.k.use_pdl) pdl_wait();
+  if (lane == 0) issue_loads<CF>(sm, a, role, env0, &s_bar, false, warp);
   // byte flags of this lane's env (every role needs the reset mask; role 0 also the command flags)
   const int u8_reset = (a.k.out.terminated[env] | a.k.out.truncated[env]) != 0;
-  int u8_head = 0, u8_stand = 0, u8_bits = 0;
+  int u8_head = 0, u8_stand = 0;
   if (role == 0 && slot == 0) {
     u8_head = static_cast<const uint8_t*>(a.k.is_heading.ptr)[env];
     u8_stand = static_cast<const uint8_t*>(a.k.is_standing.ptr)[env];
-    if (a.k.out.done_bits) u8_bits = a.k.out.done_bits[env];
   }
   RandState rs;
   rs.seed = a.k.rnd.seed;
   rs.step = a.k.rnd.step + (a.k.rnd.step_counter ? *a.k.rnd.step_counter : 0ull);
   rs.env_id_offset = a.k.rnd.env_id_offset;
 
-  // ---- height scan: global -> registers -> global, lanes = columns, while the record is still in flight ----------
-  // height_scan [IL] = sensor z - ray hit z - offset, then clip, then scale (no noise: v2_spec_ok)
+  // ---- height scan: global -> registers -> global, lanes = columns ------------------------------------------------
+  // height_scan [IL] = sensor z - ray hit z - offset, then clip, then scale (no noise: v2_spec_ok). One CTA per tile: right
+  // here, while the record is still in flight. In a cluster: after the cluster barrier (a release arrival would wait for
+  // these ~190 stores per row).
+  auto stream_height_scan = [&]() __attribute__((always_inline)) {
   static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
     constexpr int g = decltype(gc)::value;
     constexpr int st = scan_term_of(B::spec.obs[g]);
@@ -677,66 +756,84 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
       }
     }
   });
+  };
+  if (C == 1) stream_height_scan();
 
-  if (slot == 0) {
-    sm[L.rmask + e] = __int_as_float(u8_reset);
-    if (role == 0) {
-      sm[L.ishead + e] = __int_as_float(u8_head); sm[L.isstand + e] = __int_as_float(u8_stand);
-      sm[L.flags + e] = __int_as_float(u8_bits);
-    }
+  if (slot == 0 && role == 0) {   // the command task's warp: its own lanes read these back
+    sm[L.ishead + e] = __int_as_float(u8_head); sm[L.isstand + e] = __int_as_float(u8_stand);
   }
   __syncthreads();
+  V2_STAMP_T0(2);
   mbar_wait(&s_bar, 0);
+  V2_STAMP_T0(3);
 
-  // ---- manager reset of the envs flagged done (RewardManager / ActionManager / CommandTerm .reset [IL]) -----------
-  // every role: what its own tasks read (stored actions, episode length); role 0: logging, zeroing, command resample
+  // ---- tasks: no barrier between the load and the row stores ------------------------------------------------------
+  // The manager reset of the envs flagged done (RewardManager / ActionManager / CommandTerm .reset [IL]) is part of the
+  // tasks that own the state it touches: the LOG task reduces the logging partials of its tile and zeroes the reset envs'
+  // episode sums / stored actions / episode length in global memory, the COMMAND task resamples their command before its
+  // own update, the observation tasks see a reset env's stored action as 0 and its episode length as 0.
   const bool rme = u8_reset != 0;
   unsigned early_prev = 0xffffffffu;
   const int n_tiles = a.k.N / 32;
-  if (role == 0) {
-    // logging partials of the tile (combined by the last tile to arrive, in a fixed order -> deterministic):
-    // quantity q is reduced over the lanes (= envs) of one warp with a fixed shuffle tree
-    const int tile_resets = __syncthreads_or(rme);   // CTA-uniform: anything to reset in these G tiles?
-    const int gt = cluster_id * G + tile;
-    if (!tile_resets) {
-      if (slot == 0) {
-        for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;
-        __syncwarp();
-        if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);
-      }
-    } else {
-#pragma unroll 1
-      for (int q = slot; q < K + RL_MAX_DONE_TERMS + 2; q += W) {
-        float x = 0.f;
-        if (rme) {
-          if (q < K) x = sm[L.sums + q * E + e];
-          else if (q < K + RL_MAX_DONE_TERMS)
-            x = (a.k.out.done_bits != nullptr) ? (float)((__float_as_int(sm[L.flags + e]) >> (q - K)) & 1) : 0.f;
-          else x = sm[(q == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + e];
-        }
+  V2_STAMP_T0(4);
+  const int eplen_now = rme ? 0 : __float_as_int(SMF(L.eplen, 0));
+  if (C > 1) cluster_wait_acquire();   // every CTA of the cluster runs: DSMEM may be written
+  bool arrived = false;                // this thread's arrival at the second cluster barrier (as early as its DSMEM stores allow)
+  dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
+      [&](auto, const Task& tk, const RlRewardTerm&, const RlObsTerm& ot, const bool corrupt, const EnvCtx& c) __attribute__((always_inline)) {
+    if (tk.kind == TK_OBS) {
+      if (a.k.out.obs[tk.a] == nullptr) return;
+      obs_task(sm, L, S, ot, c_spec[a.k.slot].obs[tk.a].terms[tk.b], corrupt, a.k, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now,
+               nullptr, rme);
+    } else if (tk.kind == TK_LOG) {
+      // logging partials of the tile (combined by the last tile to arrive, in a fixed order -> deterministic):
+      // every quantity is reduced over the lanes (= envs) with a fixed shuffle tree
+      if (C > 1 && !arrived) { cluster_arrive_release(); arrived = true; }   // nothing of this task goes through DSMEM
+      const int gt = cluster_id * G + tile;
+      const int part = tk.b, parts = tk.col0;
+      const int fl = (a.k.out.done_bits != nullptr) ? (int)a.k.out.done_bits[env] : 0;
+      constexpr int NQ = K + RL_MAX_DONE_TERMS + 2;
+      if (__ballot_sync(0xffffffffu, rme) == 0u) {   // nothing to reset in this tile: the partials are zero
+        for (int q = part + lane * parts; q < NQ; q += 32 * parts) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;
+      } else {
+#pragma unroll 4
+        for (int q = part; q < NQ; q += parts) {   // independent reductions: their shuffle trees overlap
+          float x = 0.f;
+          if (rme) {
+            if (q < K) x = sm[L.sums + q * E + e];
+            else if (q < K + RL_MAX_DONE_TERMS) x = (float)((fl >> (q - K)) & 1);
+            else x = sm[(q == K + RL_MAX_DONE_TERMS ? L.mxy : L.myaw) + e];
+          }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-        if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
-      }
-      __syncthreads();   // the partials of every slot of a tile are written
-      if (slot == 0 && lane == 0) early_prev = ticket_arrive_release(a.k.ticket);
-      if (rme) {
-        // zero the episode sums / stored actions of the reset envs in global memory (the record copy is dead after
-        // the logging reduction above; nobody in this launch reads the sums again)
-        float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
-        float* ga = static_cast<float*>(const_cast<void*>(a.k.outf[OF_ACT].ptr));
-        float* gp = static_cast<float*>(const_cast<void*>(a.k.outf[OF_PACT].ptr));
+          for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+          if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
+        }
+        if (rme) {
+          float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
+          float* ga = static_cast<float*>(const_cast<void*>(a.k.outf[OF_ACT].ptr));
+          float* gp = static_cast<float*>(const_cast<void*>(a.k.outf[OF_PACT].ptr));
 #pragma unroll 1
-        for (int k = slot; k < K; k += W) gs[(size_t)k * a.k.outf[OF_SUMS].cs + env] = 0.f;
+          for (int k = part; k < K; k += parts) gs[(size_t)k * a.k.outf[OF_SUMS].cs + env] = 0.f;
 #pragma unroll 1
-        for (int q = slot; q < A; q += W) {
-          ga[(size_t)q * a.k.outf[OF_ACT].cs + env] = 0.f;
-          gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
+          for (int q = part; q < A; q += parts) {
+            ga[(size_t)q * a.k.outf[OF_ACT].cs + env] = 0.f;
+            gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
+          }
+          if (part == 0) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
         }
       }
-      if (slot == 0 && rme) {
-        sm[L.mxy + e] = 0.f; sm[L.myaw + e] = 0.f;
-        constexpr RlCommandCfg cc = B::spec.command;
+      __syncwarp();
+      if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);   // the tile's partials are written
+    } else if (tk.kind == TK_COMMAND) {
+      // CommandTerm.reset [IL] of the reset envs (resample: V/mdp/commands.py:43-47), then CommandManager.compute and the
+      // observation columns that show the new command (written into their owners' rows). The metric accumulators work on
+      // a private copy (the LOG task reads the old values concurrently).
+      constexpr Layout LC = [] { Layout l = CF::L; l.mxy = CF::L.rmask; l.myaw = CF::L.epnew; return l; }();
+      sm[LC.mxy + e] = rme ? 0.f : sm[L.mxy + e];
+      sm[LC.myaw + e] = rme ? 0.f : sm[L.myaw + e];
+      EnvCtx cc = c;
+      if (rme) {
+        constexpr RlCommandCfg cfgc = B::spec.command;
         float u[RL_NUM_CMD_UNIFORMS];
         if (a.k.rnd.cmd_uniforms != nullptr) {
 #pragma unroll
@@ -746,62 +843,46 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
           u[0] = u01(r0.x); u[1] = u01(r0.y); u[2] = u01(r0.z); u[3] = u01(r0.w);
           u[4] = u01(r1.x); u[5] = u01(r1.y); u[6] = u01(r1.z);
         }
-        float c0 = u[1] * (cc.lin_vel_x_hi - cc.lin_vel_x_lo) + cc.lin_vel_x_lo;
-        float c1 = u[2] * (cc.lin_vel_y_hi - cc.lin_vel_y_lo) + cc.lin_vel_y_lo;
-        const float c2 = u[3] * (cc.ang_vel_z_hi - cc.ang_vel_z_lo) + cc.ang_vel_z_lo;
-        const float keep = (sqrtf(c0 * c0 + c1 * c1) > cc.small_cmd_threshold) ? 1.f : 0.f;
+        float c0 = u[1] * (cfgc.lin_vel_x_hi - cfgc.lin_vel_x_lo) + cfgc.lin_vel_x_lo;
+        float c1 = u[2] * (cfgc.lin_vel_y_hi - cfgc.lin_vel_y_lo) + cfgc.lin_vel_y_lo;
+        const float c2 = u[3] * (cfgc.ang_vel_z_hi - cfgc.ang_vel_z_lo) + cfgc.ang_vel_z_lo;
+        const float keep = (sqrtf(c0 * c0 + c1 * c1) > cfgc.small_cmd_threshold) ? 1.f : 0.f;
         c0 *= keep; c1 *= keep;
-        sm[L.cmd + 0 * E + e] = c0; sm[L.cmd + 1 * E + e] = c1; sm[L.cmd + 2 * E + e] = c2;
-        sm[L.tleft + e] = u[0] * (cc.resampling_time_hi - cc.resampling_time_lo) + cc.resampling_time_lo;
-        if (cc.heading_command) {
-          sm[L.head + e] = u[4] * (cc.heading_hi - cc.heading_lo) + cc.heading_lo;
-          sm[L.ishead + e] = __int_as_float((u[5] <= cc.rel_heading_envs) ? 1 : 0);
+        cc.c0 = c0; cc.c1 = c1; cc.c2 = c2;
+        sm[L.tleft + e] = u[0] * (cfgc.resampling_time_hi - cfgc.resampling_time_lo) + cfgc.resampling_time_lo;
+        if (cfgc.heading_command) {
+          sm[L.head + e] = u[4] * (cfgc.heading_hi - cfgc.heading_lo) + cfgc.heading_lo;
+          sm[L.ishead + e] = __int_as_float((u[5] <= cfgc.rel_heading_envs) ? 1 : 0);
         }
-        sm[L.isstand + e] = __int_as_float((u[6] <= cc.rel_standing_envs) ? 1 : 0);
+        sm[L.isstand + e] = __int_as_float((u[6] <= cfgc.rel_standing_envs) ? 1 : 0);
       }
-    }
-  }
-  // every role: its own copy of what a reset changes for the observation terms
-  if (rme) {
-#pragma unroll 1
-    for (int q = slot; q < A; q += W) sm[L.act + q * E + e] = 0.f;
-    if (slot == 0) sm[L.eplen + e] = __int_as_float(0);
-  }
-  if (role == 0 && slot == 0 && rme) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
-  __syncthreads();
-  if (C > 1) cluster_wait_acquire();
-
-  // ---- tasks ----------------------------------------------------------------------------------------------------
-  const int eplen_now = __float_as_int(SMF(L.eplen, 0));
-  dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
-      [&](auto, const Task& tk, const RlRewardTerm&, const RlObsTerm& ot, const bool corrupt, const EnvCtx& c) __attribute__((always_inline)) {
-    if (tk.kind == TK_OBS) {
-      if (a.k.out.obs[tk.a] == nullptr) return;
-      obs_task(sm, L, S, ot, c_spec[a.k.slot].obs[tk.a].terms[tk.b], corrupt, a.k, rs, tk.a, tk.b, tk.col0, tk.lo, tk.hi, e, env, c, eplen_now);
-    } else if (tk.kind == TK_COMMAND) {
-      // CommandManager.compute + the observation columns that show the new command (written into their owners' rows)
-      command_update(sm, L, S, StaticPolicy<B>::command(a.k), a.k, rs, e, env, c, true);
+      command_update(sm, LC, S, StaticPolicy<B>::command(a.k), a.k, rs, e, env, cc, true);
       StaticPolicy<B>::for_cmd_obs(a.k, [&](const RlObsTerm& t, int g, int ti, int col0, bool corr) __attribute__((always_inline)) {
         if (a.k.out.obs[g] == nullptr) return;
         const uint32_t owner = (uint32_t)(g == 0 ? CF::obs_owner0 : CF::obs_owner1);
         float* smo = (C > 1 && owner != 0) ? map_to_rank(sm, owner) : sm;   // the owner's record: same offsets
-        obs_task(sm, L, S, t, c_spec[a.k.slot].obs[g].terms[ti], corr, a.k, rs, g, ti, col0, 0, t.dim, e, env, c, eplen_now, smo);
+        obs_task(sm, LC, S, t, c_spec[a.k.slot].obs[g].terms[ti], corr, a.k, rs, g, ti, col0, 0, t.dim, e, env, cc, eplen_now, smo);
       });
+      if (C > 1 && !arrived) { cluster_arrive_release(); arrived = true; }   // the command columns are in their owners' rows
       // command state of the step (CommandTerm fields), straight from registers / the record
       float* gc = static_cast<float*>(const_cast<void*>(a.k.outf[OF_CMD].ptr));
-      gc[env] = SMF(L.cmdn, 0); gc[(size_t)a.k.outf[OF_CMD].cs + env] = SMF(L.cmdn, 1); gc[2 * (size_t)a.k.outf[OF_CMD].cs + env] = SMF(L.cmdn, 2);
-      static_cast<float*>(const_cast<void*>(a.k.outf[OF_HEAD].ptr))[env] = SMF(L.head, 0);
-      static_cast<float*>(const_cast<void*>(a.k.outf[OF_TLEFT].ptr))[env] = SMF(L.tleft, 0);
-      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MXY].ptr))[env] = SMF(L.mxy, 0);
-      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MYAW].ptr))[env] = SMF(L.myaw, 0);
-      static_cast<uint8_t*>(const_cast<void*>(a.k.is_heading.ptr))[env] = (uint8_t)__float_as_int(SMF(L.ishead, 0));
-      static_cast<uint8_t*>(const_cast<void*>(a.k.is_standing.ptr))[env] = (uint8_t)__float_as_int(SMF(L.isstand, 0));
+      gc[env] = SMF(LC.cmdn, 0); gc[(size_t)a.k.outf[OF_CMD].cs + env] = SMF(LC.cmdn, 1); gc[2 * (size_t)a.k.outf[OF_CMD].cs + env] = SMF(LC.cmdn, 2);
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_HEAD].ptr))[env] = sm[L.head + e];
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_TLEFT].ptr))[env] = sm[L.tleft + e];
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MXY].ptr))[env] = sm[LC.mxy + e];
+      static_cast<float*>(const_cast<void*>(a.k.outf[OF_MYAW].ptr))[env] = sm[LC.myaw + e];
+      static_cast<uint8_t*>(const_cast<void*>(a.k.is_heading.ptr))[env] = (uint8_t)__float_as_int(sm[L.ishead + e]);
+      static_cast<uint8_t*>(const_cast<void*>(a.k.is_standing.ptr))[env] = (uint8_t)__float_as_int(sm[L.isstand + e]);
     }
+  }, [&]() __attribute__((always_inline)) {
+    if (C > 1 && !arrived) cluster_arrive_release();
   });
-  if (lane == 0 && early_prev == (unsigned)(n_tiles - 1)) s_last = 1;
-  if (C > 1) { cluster_arrive_release(); cluster_wait_acquire(); }   // the command columns have reached their rows
+  V2_STAMP(16 + warp);
+  if (lane == 0 && early_prev == (unsigned)(n_tiles * CF::log_parts - 1)) s_last = 1;   // the last ticket of the launch
+  if (C > 1) cluster_wait_acquire();   // the command columns have reached their rows
   __syncthreads();
 
+  V2_STAMP_T0(5);
   // ---- observation rows: this role's groups, per-env columns, lanes = columns (coalesced) -------------------------
   static_for(std::make_integer_sequence<int, RL_NUM_OBS_GROUPS>{}, [&](auto gc) {
     constexpr int g = decltype(gc)::value;
@@ -821,8 +902,10 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
     }
   });
 
+  if (C > 1) stream_height_scan();
+  V2_STAMP_T0(6); V2_GTIME(7);
   // ---- logging means of the reset (extras["log"] [IL]): the CTA whose ticket was the last of the launch -------------
-  if (role == 0 && s_last) {
+  if (s_last) {   // CTA-uniform (any role: the CTA whose LOG warp drew the last ticket)
     __threadfence();
     float* s_red = sm;   // the record is dead
     __syncthreads();
@@ -1054,7 +1137,7 @@ void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int
 int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool* handled) {
   *handled = false;
   RlV2State* v = ctx->v2;
-  if (!v || k.has_ids || k.dbg != nullptr) return RL_OK;
+  if (!v || k.has_ids || (k.dbg != nullptr && !RL_V2_STAMPS)) return RL_OK;
   const RlStepSpec& s = ctx->spec;
   int c = 0, g = 0, nw = 0;
   choose_cfg(v, k.N, &c, &g, &nw);

@@ -46,10 +46,10 @@ using DeviceGuard = RlDeviceGuard;
 #define RL_TERM_LOOP _Pragma("unroll 1")
 #endif
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
-// A reward term is evaluated in at most this many parts (termv holds that many slots per term). 2, not more: finer
-// cuts measured slower, and every extra slot costs K * 128 bytes of the tile record - at 4 the Go2-rough record grew
-// from 114.6 to 119.9 KB and lost the second resident CTA per SM (1.5 x slower from 16 k envs up)
-constexpr int kTermParts = 2;
+// (Round 1 cut the one long body sum - undesired_contacts over 15 bodies - into two parts that met through a lock-free
+// arrival counter in shared memory. Round 2 removed it: compute-sanitizer racecheck flags the protocol, the parts rounded
+// differently from the reference's single sum unless gated once, and the kernels that matter for speed - mdp_step_v2.cu -
+// cache the contact norms instead, which makes the term short.)
 // (Round-1 build variants RL_SHARED_NORMS / RL_SHARED_CTX / RL_PERSISTENT were measured in round 2 - profiles/
 // r2_variant_probe.txt: norms + context prepass -9 % on the pre-reset launch, persistent tile loop < 3 % at any size - and
 // removed; the cluster kernels of csrc/mdp_step_v2.cu carry the norm prepass.)
@@ -89,8 +89,7 @@ struct Layout {
   int raypos;
   int cmdu;
   int rew, flags, stepr;                         // outputs
-  int termv;                                     // [K][kTermParts] weighted term value in slot 0 (raw partial sums of a split term before it is finished)
-  int arrive;                                    // [K] per-env arrival counters of the two halves of a split term
+  int termv;                                     // [K] weighted value of every term (the manager-order sum reads them)
   int hnorm;                                     // [B] max over the history of |F_b| (written by a prepass; cached-norm kernels only)
   int w_rew, w_eplen, w_sums, w_stepr, w_cmd, w_head, w_tleft, w_mxy, w_myaw, w_act, w_pact;  // record words of out fields
   int soa_words;
@@ -164,8 +163,7 @@ __host__ __device__ constexpr Layout make_layout(const RlStepSpec& s, const int 
   L.w_rew = take(1); L.rew = L.w_rew * E;
   L.flags = take(1) * E;
   L.w_stepr = take(K); L.stepr = L.w_stepr * E;
-  L.termv = take(kTermParts * K) * E;
-  L.arrive = take(K) * E;
+  L.termv = take(K) * E;
   L.soa_words = w;
   int off = align_up(w * E, 32);  // 128-byte aligned sections (bulk copies need 16 B)
   L.cj = off; off = align_up(off + 5 * J, 32);
@@ -196,18 +194,16 @@ __host__ __device__ constexpr int out_field_word(const Layout& L, int f) {
 // balanced over the warps by a longest-processing-time greedy on rough instruction costs. constexpr, so a baked
 // spec gets its schedule at compile time and every warp's code is straight-line.
 // ---------------------------------------------------------------------------------------------------
-enum { TK_REWARD = 0, TK_OBS = 1, TK_DONES = 2, TK_COMMAND = 3 };
+enum { TK_REWARD = 0, TK_OBS = 1, TK_DONES = 2, TK_COMMAND = 3, TK_LOG = 4 /* reset logging + zeroing (mdp_step_v2.cu) */ };
 
 struct Task {
   uint8_t kind, a, b, owner;   // REWARD: a = term k, b = half (0/1); OBS: a = group, b = term index
   uint16_t lo, hi;             // REWARD: body-index range [lo, hi); OBS: column range within the term
-  uint16_t col0, pad;          // OBS: first column of the term inside the group row; REWARD: col0 = number of parts,
-                               // pad = 1 for one part of a split term
+  uint16_t col0, pad;          // OBS: first column of the term inside the group row
 };
 struct Schedule {
   int n;
   Task t[RL_MAX_TASKS];
-  uint8_t split[RL_MAX_REWARD_TERMS];   // > 0: the term is evaluated in that many parts (termv[k][0..parts))
   uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (split terms, is_terminated)
 };
 
@@ -255,45 +251,9 @@ __host__ __device__ constexpr Schedule make_schedule(const RlStepSpec& s, int nw
     const RlRewardTerm& t = s.rewards[k];
     if (t.weight == 0.f) continue;
     if (t.type == RL_REW_IS_TERMINATED) { sc.late[k] = 1; continue; }
-    // Long sums over bodies / feet can be cut into up to kTermParts parts; the parts publish raw partial sums and
-    // the one that arrives last (per env) adds them in part order. Measured (profiles/r1_summary.md): every part is
-    // its own straight-line code and costs ~4k cycles of first-touch instruction fetch whatever its length, so
-    // only the one really long term (> 8 bodies) is cut, and only in two.
     const bool body_sum = (t.type == RL_REW_UNDESIRED_CONTACTS || t.type == RL_REW_CONTACT_FORCES);
-    const bool list_sum = (t.type == RL_REW_FEET_SLIDE);
-    const int nb = popc64(t.body_mask);
-    const int items = body_sum ? nb : (list_sum ? t.n_idx : 0);
-    // only COUNTS are cut (undesired_contacts): their parts add up exactly in any order, so the split term equals the
-    // reference's single sum bit for bit; a float sum (contact_forces, feet_slide) cut in two would round differently
-    int parts = (items > 8 && t.type == RL_REW_UNDESIRED_CONTACTS) ? 2 : 1;
-    if (parts > kTermParts) parts = kTermParts;
-    if (n + parts > RL_MAX_TASKS - 24) parts = 1;   // table nearly full: stop splitting
-    if (parts < 2) {
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 1, 0}; cost[n++] = 30 + reward_cost(t, s, body_sum ? nb : t.n_idx);
-      continue;
-    }
-    sc.split[k] = (uint8_t)parts;
-    int item0 = 0;
-    for (int p = 0; p < parts; ++p) {
-      const int item1 = (items * (p + 1)) / parts;   // items [item0, item1) belong to part p
-      int lo = item0, hi = item1;
-      if (body_sum) {          // body terms take a body-index range: translate item counts into bit positions
-        int seen = 0; lo = 64; hi = 64;
-        for (int bb = 0; bb < 64; ++bb)
-          if ((t.body_mask >> bb) & 1ull) {
-            if (seen == item0) lo = bb;
-            if (seen == item1) hi = bb;
-            ++seen;
-          }
-        if (p == 0) lo = 0;
-        if (p == parts - 1) hi = 64;
-      } else if (p == parts - 1) {
-        hi = 64;
-      }
-      sc.t[n] = Task{TK_REWARD, (uint8_t)k, (uint8_t)p, 0, (uint16_t)lo, (uint16_t)hi, (uint16_t)parts, 1};
-      cost[n++] = reward_cost(t, s, item1 - item0);
-      item0 = item1;
-    }
+    sc.t[n] = Task{TK_REWARD, (uint8_t)k, 0, 0, 0, 64, 1, 0};
+    cost[n++] = 30 + reward_cost(t, s, body_sum ? popc64(t.body_mask) : t.n_idx);
   }
   for (int g = 0; g < RL_NUM_OBS_GROUPS; ++g) {
     int col0 = 0;
@@ -1075,8 +1035,9 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
                                          const bool corrupt, const KArgs& a, const RandState rs, const int g,
                                          const int ti, const int col0, const int lo, const int hi, const int e,
                                          const long long env, const EnvCtx& c, const int eplen_now,
-                                         float* const out_sm = nullptr) {
-  // out_sm: the record the row lives in when that is not `sm` (cluster kernels: another CTA's shared memory)
+                                         float* const out_sm = nullptr, const bool act_zero = false) {
+  // out_sm: the record the row lives in when that is not `sm` (cluster kernels: another CTA's shared memory);
+  // act_zero: ActionManager.reset [IL] has zeroed this env's stored action in this launch (not yet in the record)
   float* row = (out_sm ? out_sm : sm) + LOBS(g) + e * LOBSP(g);
   // noise-as-input mode (RlRandom.obs_uniforms: reproducibility hook for tests / replays, not the production
   // path): read straight from global memory
@@ -1106,7 +1067,7 @@ __device__ __forceinline__ void obs_task(float* sm, const Layout& L, const Scala
           if ((t.zero_mask >> col) & 1ull) v = 0.f;
           break;
         case RL_OBS_JOINT_VEL_REL: v = SMF(L.jvel, tc.ids[col]) - CJ(1, tc.ids[col]); break;
-        case RL_OBS_LAST_ACTION: v = SMF(L.act, col); break;
+        case RL_OBS_LAST_ACTION: v = act_zero ? 0.f : SMF(L.act, col); break;   // act_zero: this env's stored action was just reset
         case RL_OBS_HEIGHT_SCAN: v = (SMF(L.raypos, 0) - sm[L.rays + e * L.rays_pitch + col]) - t.p[0]; break;
         case RL_OBS_PHASE: {
           const float ph = ((float)eplen_now * S.step_dt) / t.p[0];

@@ -31,6 +31,10 @@ from .spec import StepSpec, compact_layout, compile_reward_term, compile_step_sp
 from .state import StateBuffers
 from .synthetic import make_state
 
+import os as _os
+
+_NVTX = _os.environ.get("RL_MDP_NVTX", "0") == "1"
+
 try:  # optional: real gymnasium spaces / registration when the package exists
     import gymnasium as gym  # type: ignore
 except Exception:  # pragma: no cover - not installed in the build image
@@ -636,6 +640,15 @@ class ManagerBasedRLEnv:
     def _rng_kwargs(self) -> dict:
         return dict(seed=self.seed, env_id_offset=self.rank * self.num_envs, use_random_inputs=False, use_step_counter=True)
 
+    @property
+    def _rng(self) -> dict:
+        """``_rng_kwargs()`` cached (rebuilt when the seed changes): the hot loop does not build a dict per launch."""
+        c = self.__dict__.get("_rng_cache")
+        if c is None or c[0] != self.seed:
+            c = (self.seed, self._rng_kwargs())
+            self.__dict__["_rng_cache"] = c
+        return c[1]
+
     def _obs_dict(self) -> dict[str, torch.Tensor]:
         return {g.name: self.buffers.obs[i] for i, g in enumerate(self.spec.obs) if g.dim > 0}
 
@@ -677,19 +690,34 @@ class ManagerBasedRLEnv:
     def step(self, action: torch.Tensor):
         """ManagerBasedRLEnv.step() [IL] order: three launches of this library + the provider."""
         b, eng = self.buffers, self.engine
+        nvtx = _NVTX   # RL_MDP_NVTX=1: ranges around the launches for nsys / ncu timelines (SURVEY.md section 5, "Tracing")
+        if nvtx:
+            torch.cuda.nvtx.range_push("mdp.process_action")
         self.action_manager.process_action(action)                                   # 1 (+ common step counter)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("mdp.state_provider.advance")
         self.state_provider.advance(self)                                            # 2 physics / sensors
         self.common_step_counter += 1
-        eng.step_pre_reset(b, **self._rng_kwargs())                                  # 3-5: dones, rewards, reset ids
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("mdp.step_pre_reset")
+        eng.step_pre_reset(b, **self._rng)                                           # 3-5: dones, rewards, reset ids
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
         self._state_version += 1
+        if nvtx:
+            torch.cuda.nvtx.range_push("mdp.step_post_reset")
         if self.pit_grid is None:
-            eng.step_post_reset(b, **self._rng_kwargs())                             # 6b manager reset, 7 command, 9 obs
+            eng.step_post_reset(b, **self._rng)                                      # 6b manager reset, 7 command, 9 obs
         else:   # the pit branch of _update_command sits between the command update and the observations
-            rng = self._rng_kwargs()
+            rng = self._rng
             eng.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND, **rng)
             eng.command_pit_restrict(b, self.pit_grid, self.was_on_pit, **rng)
             eng.step(b, phases=nat.PHASE_OBS, **rng)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         self.extras = {"log": self._log()}
         return self._obs_dict(), b.reward, b.terminated.bool(), b.truncated.bool(), self.extras
 

@@ -49,11 +49,14 @@ class RolloutStorage:
     The step kernels write obs_policy / obs_critic / reward / terminated / truncated of step ``t`` straight into slab
     ``t`` (``bind``); the policy side fills action / mean / sigma / value / log_prob. ``gathered`` (allocated when the
     process group has more than one rank) is ``[steps, world, N * width]``: slab ``t`` of every rank, rank-major, so the
-    global env id of row ``e`` of rank ``r`` is ``r * N + e`` - and ``gathered[t]`` is exactly the contiguous output an
-    all-gather of ``data[t]`` produces (no staging copy)."""
+    global env id of row ``e`` of rank ``r`` is ``r * N + e``; it is stored by chunks of ``gather_every`` steps so that every
+    all-gather writes its contiguous output in place (no staging copy)."""
 
-    def __init__(self, spec: StepSpec, num_envs: int, steps: int, device: torch.device | str, group=None):
+    def __init__(self, spec: StepSpec, num_envs: int, steps: int, device: torch.device | str, group=None, gather_every: int = 1):
         self.spec, self.N, self.steps, self.group = spec, int(num_envs), int(steps), group
+        self.every = max(1, int(gather_every))      # slabs per all-gather: fewer, larger collectives (launch latency vs overlap)
+        if self.steps % self.every:
+            raise ValueError("gather_every must divide the number of steps")
         self.width = rollout_row_width(spec)
         dev = torch.device(device)
         self.data = torch.zeros(self.steps, self.N * self.width, device=dev)
@@ -65,10 +68,30 @@ class RolloutStorage:
             o += N * w
         assert o == N * self.width
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.gathered = torch.empty(self.steps, self.world, self.N * self.width, device=dev) if self.world > 1 else None
+        # [chunks, world, every * slab]: chunk c of every rank, rank-major - exactly what an all-gather of data[c*every:(c+1)*every] produces
+        self._gath = (torch.empty(self.steps // self.every, self.world, self.every * self.N * self.width, device=dev)
+                      if self.world > 1 else None)
         self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._events = [torch.cuda.Event() for _ in range(self.steps)] if dev.type == "cuda" else None
         self._whole = None   # [world, steps * N * width], only for the un-streamed baseline (gather_all)
+
+    def set_gather_every(self, k: int) -> None:
+        """Change the chunking of the streamed gather (re-allocates the gathered buffer; the slabs stay where they are)."""
+        k = max(1, int(k))
+        if self.steps % k:
+            raise ValueError("gather_every must divide the number of steps")
+        self.every = k
+        if self.world > 1:
+            self._gath = torch.empty(self.steps // k, self.world, k * self.N * self.width, device=self.data.device)
+
+    @property
+    def gathered(self) -> torch.Tensor | None:
+        """``[steps, world, N * width]`` view of the gathered rollout (slab ``t`` of rank ``r`` at ``[t, r]``)."""
+        if self._gath is None:
+            return None
+        c, w = self._gath.shape[0], self.world
+        return self._gath.view(c, w, self.every, self.N * self.width).permute(0, 2, 1, 3).reshape(self.steps, w, self.N * self.width) \
+            if self.every > 1 else self._gath
 
     # ---- views -----------------------------------------------------------------------------------------------------
     def plane(self, name: str, t: int, data: torch.Tensor | None = None) -> torch.Tensor:
@@ -93,18 +116,21 @@ class RolloutStorage:
 
     # ---- hand-off ---------------------------------------------------------------------------------------------------
     def gather_step(self, t: int, after: "torch.cuda.Stream | None" = None) -> None:
-        """All-gather slab ``t`` on the side stream, ordered after everything ``after`` (default: the current stream) has
-        been given so far. Returns immediately; the next step can be issued right away."""
-        if self.world == 1:
+        """Step ``t`` is complete: when it closes a chunk of ``gather_every`` steps, all-gather that chunk on the side stream,
+        ordered after everything ``after`` (default: the current stream) has been given so far. Returns immediately; the
+        next step can be issued right away."""
+        if self.world == 1 or (t + 1) % self.every:
             return
+        c = t // self.every
+        src_rows = self.data[c * self.every:(c + 1) * self.every].view(-1)
         if self._side is None:   # CPU process groups (gloo tests): synchronous
-            dist.all_gather_into_tensor(self.gathered[t].view(-1), self.data[t], group=self.group)
+            dist.all_gather_into_tensor(self._gath[c].view(-1), src_rows, group=self.group)
             return
         src = after if after is not None else torch.cuda.current_stream(self.data.device)
         self._events[t].record(src)
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._events[t])
-            dist.all_gather_into_tensor(self.gathered[t].view(-1), self.data[t], group=self.group)
+            dist.all_gather_into_tensor(self._gath[c].view(-1), src_rows, group=self.group)
 
     def gather_all(self) -> torch.Tensor | None:
         """The un-streamed form: ONE all-gather of the whole rollout on the current stream, into ``[world, steps * N *
@@ -125,7 +151,8 @@ class RolloutStorage:
         """``[world * N, w]`` view-copy of quantity ``name`` of step ``t`` over all ranks (rank-major = global env ids)."""
         if self.world == 1:
             return self.plane(name, t)
-        return torch.cat([self.plane(name, t, self.gathered[:, r]) for r in range(self.world)], dim=0)
+        g = self.gathered
+        return torch.cat([self.plane(name, t, g[:, r]) for r in range(self.world)], dim=0)
 
 
 class RolloutBuffer:

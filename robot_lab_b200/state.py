@@ -231,6 +231,19 @@ class StateBuffers:
 
     def random(self, seed: int = 0, step: int = 0, env_id_offset: int = 0, use_inputs: bool = True,
                use_step_counter: bool = False) -> nat.RlRandom:
+        key = ("rnd", seed, step, env_id_offset, use_inputs, use_step_counter, id(self.cmd_uniforms),
+               id(self.obs_uniforms[0]), id(self.obs_uniforms[1]))
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        r = self._random(seed, step, env_id_offset, use_inputs, use_step_counter)
+        if len(self._cache) > 64:   # rolling seeds / steps: do not grow without bound
+            for k in [k for k in self._cache if isinstance(k, tuple) and k[0] == "rnd"]:
+                del self._cache[k]
+        self._cache[key] = r
+        return r
+
+    def _random(self, seed, step, env_id_offset, use_inputs, use_step_counter) -> nat.RlRandom:
         r = nat.RlRandom()
         r.seed, r.step, r.env_id_offset = seed, step, env_id_offset
         if use_step_counter:

@@ -149,3 +149,16 @@ def test_build_variants_if_present_export_the_same_abi_and_do_not_grow_the_recor
                 assert size <= base, (name, key, size, base)                # split-term slots gone, norms added
     if not found:
         pytest.skip("no variant library built (python -m robot_lab_b200.build --variant NAME)")
+
+
+def test_every_entry_point_has_declared_argument_types(native_lib):
+    """ctypes without argtypes passes Python ints as 32-bit C ints: a 64-bit num_envs or a stream handle gets truncated
+    and the call crashes on the GPU box (it did once, rl_derived_views in round 2). Every exported function that takes
+    arguments must have its argtypes set by _native.load()."""
+    from robot_lab_b200 import _native as nat
+
+    no_args = {"rl_abi_version", "rl_last_error"}
+    for sym in nat.EXPORTED_SYMBOLS:
+        if sym in no_args:
+            continue
+        assert getattr(native_lib, sym).argtypes is not None, f"{sym}: argtypes not declared in _native.load()"

@@ -26,9 +26,15 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference"
     assert d["metric"].startswith("env-steps/sec") and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
-    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    # both arms report the warm-up they honour: at least 3 (the timing rules), i.e. max(3, --warmup)
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert "Rough-Unitree-Go2" in d["config"]["workload"]
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    # the SAME workload string as the GPU arm prints (the driver compares the two lines' config)
+    assert d["config"]["workload"] == bench.workload_string(bench.TASK_DEFAULT, 4096) and "configs[2]" in d["config"]["workload"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -50,13 +50,13 @@ def test_two_rank_rollout_all_gather(tmp_path):
         assert ok == 1 and n == world * n_local
 
 
-def _storage_worker(rank, world, port, steps, n_local, out_dir):
+def _storage_worker(rank, world, port, steps, n_local, out_dir, every=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from robot_lab_b200.rollout import RolloutStorage
 
     cfg, spec = H.make_spec("go2_rough")
-    store = RolloutStorage(spec, n_local, steps, "cpu")
+    store = RolloutStorage(spec, n_local, steps, "cpu", gather_every=every)
     g = torch.Generator().manual_seed(1)
     names = ("obs_policy", "obs_critic", "action", "mean", "sigma", "reward", "value", "log_prob")
     full = {n: torch.randn(steps, world * n_local, *( (store._planes[n][1],) if store._planes[n][1] > 1 else ()), generator=g) for n in names}
@@ -74,7 +74,7 @@ def _storage_worker(rank, world, port, steps, n_local, out_dir):
     for t in range(steps):
         for n in names:
             ok = ok and torch.equal(store.global_plane(n, t), full[n][t])
-        got = torch.cat([store.plane("done", t, store.gathered[:, r]).view(torch.uint8)[:n_local] for r in range(world)])
+        got = torch.cat([store.plane("done", t, store.gathered[:, r].contiguous()).view(torch.uint8)[:n_local] for r in range(world)])
         ok = ok and torch.equal(got.bool(), done[t])
     whole = store.gather_all()
     ok = ok and torch.equal(whole[rank], store.data.view(-1)) and whole.shape == (world, steps * n_local * store.width)
@@ -82,11 +82,12 @@ def _storage_worker(rank, world, port, steps, n_local, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_rollout_storage_streamed_gather(tmp_path):
-    """RolloutStorage: the step's results live in per-step slabs (written in place), every slab is gathered as soon as it
-    is complete, and the gathered planes are the single-process tensors in global env-id order."""
+@pytest.mark.parametrize("every", [1, 2])
+def test_two_rank_rollout_storage_streamed_gather(tmp_path, every):
+    """RolloutStorage: the step's results live in per-step slabs (written in place), every chunk of slabs is gathered as
+    soon as it is complete, and the gathered planes are the single-process tensors in global env-id order."""
     world, steps, n_local = 2, 4, 32
-    mp.spawn(_storage_worker, args=(world, _free_port(), steps, n_local, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_storage_worker, args=(world, _free_port(), steps, n_local, str(tmp_path), every), nprocs=world, join=True)
     for r in range(world):
         assert torch.load(tmp_path / f"s{r}.pt").item() == 1
 

@@ -77,13 +77,11 @@ def test_cluster_kernels_use_cluster_barriers_and_dsmem(kernels):
 
 
 def test_new_kernels_are_smaller_than_the_general_kernel(kernels):
-    """No load prologue, no store phase, no per-warp protocols: although their term loops are UNROLLED against the baked
-    spec (independent iterations overlap; the general kernel keeps them rolled for code size), the Go2 / A1 kernels stay
-    well below the general kernel of the same task (5.3 - 5.6 k instructions in round 1)."""
+    """No load prologue, no store phase, no per-warp protocols: a new kernel is under half of the general kernel of the
+    same task (5.3 - 5.6 k instructions in round 1). Code size is time here: every SM executes each instruction once."""
     for kind in ("pre", "post"):
         for name, body in _cluster_kernels(kernels, kind).items():
-            quad = any(b in name for b in ("Baked0", "Baked2", "Baked3", "Baked6"))   # A1 / Go2: 12 joints
-            assert len(body) < (4500 if quad else 9000), f"{name}: {len(body)} instructions"
+            assert len(body) < 4000, f"{name}: {len(body)} instructions"
 
 
 def test_general_kernel_load_phase_uses_bulk_and_async_copies(kernels):

@@ -1,0 +1,84 @@
+"""Where a launch of the new step kernels goes (build variant "stamps": python -m robot_lab_b200.build --variant stamps;
+run with RL_MDPSTEP_LIB=robot_lab_b200/_lib/libmdpstep_stamps.so). Per CTA clock64 stamps: 1 entry, 2 loads issued +
+prologue done, 3 record resident, 4 tasks start, 16+w end of warp w's tasks, 5 after the task barrier, 6 tail done;
+globaltimer (ns) at entry / end of every CTA gives the launch's spread over the grid.
+
+Usage (GPU box): python tools/v2_timeline.py [num_envs] [task_key]
+"""
+import statistics
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+
+import torch  # noqa: E402
+
+import helpers as H  # noqa: E402
+from robot_lab_b200.engine import MdpStepEngine  # noqa: E402
+from robot_lab_b200.synthetic import make_state  # noqa: E402
+
+WARM = "--warm" in sys.argv   # stamp the 4th of four identical back-to-back launches (same state set, nothing in between)
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+N = int(argv[0]) if len(argv) > 0 else 4096
+key = argv[1] if len(argv) > 1 else "go2_rough"
+cfg, spec = H.make_spec(key)
+eng = MdpStepEngine(spec, "cuda:0")
+cc = eng.cluster_config(N)
+nw = cc["warps_per_cta"]
+sets = []
+for i in range(6):
+    b = eng.new_buffers(N)
+    b.load_logical(make_state(spec, N, seed=1234 + i))
+    b.cmd_uniforms, b.obs_uniforms = None, [None, None]
+    sets.append(b)
+rng = dict(use_random_inputs=False, use_step_counter=True)
+grid = (N // (32 * cc["tiles_per_cta"])) * cc["cluster_size"]
+dbg = torch.zeros(grid, 64, dtype=torch.int64, device="cuda:0")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
+print(f"{key} N={N} config {cc} grid {grid} {'WARM (4th identical launch)' if WARM else 'cold (L2 flushed, other kernels in between)'}")
+for kind in ("pre", "post"):
+    rows = []
+    for rep in range(8):
+        b = sets[rep % len(sets)]
+        eng.set_debug_buffer(None)
+        eng.process_action(b)
+        if kind == "post":
+            eng.step_pre_reset(b, **rng)
+        fn = eng.step_pre_reset if kind == "pre" else eng.step_post_reset
+        if WARM:
+            for _ in range(3):
+                fn(b, **rng)
+        else:
+            flush.fill_(rep)                  # the launch reads HBM
+        torch.cuda.synchronize()
+        dbg.zero_()
+        eng.set_debug_buffer(dbg)
+        fn(b, **rng)
+        torch.cuda.synchronize()
+        eng.set_debug_buffer(None)
+        if kind == "pre":
+            eng.step_post_reset(b, **rng)
+        d = dbg.cpu()
+        if rep >= 2:
+            rows.append(d)
+    med = lambda xs: statistics.median(xs)
+    out = {}
+    if kind == "pre":
+        for name, a_, b_ in (("  entry -> mbarrier armed", 1, 9), ("  first CTA barrier", 9, 10), ("  this warp's copies issued", 10, 11),
+                             ("  joint constants -> smem", 11, 12), ("  zero slots + second barrier", 12, 2)):
+            out[name] = med([float((d[:, b_] - d[:, a_]).float().median()) for d in rows])
+    for name, a_, b_ in (("prologue + load issue", 1, 2), ("wait for the record", 2, 3), ("reset / prepass", 3, 4),
+                         ("tasks + barrier", 4, 5), ("tail", 5, 6), ("entry -> tail done", 1, 6)):
+        out[name] = med([float((d[:, b_] - d[:, a_]).float().median()) for d in rows])
+    task_end = [d[:, 16:16 + nw] - d[:, 4:5] for d in rows]
+    out["slowest warp's tasks"] = med([float(t.max(dim=1).values.float().median()) for t in task_end])
+    out["fastest warp's tasks"] = med([float(t.min(dim=1).values.float().median()) for t in task_end])
+    per_warp = torch.stack([t.float().median(dim=0).values for t in task_end]).median(dim=0).values
+    span = med([float((d[:, 7].max() - d[:, 0].min())) for d in rows])
+    first_last_entry = med([float((d[:, 0].max() - d[:, 0].min())) for d in rows])
+    print(f"--- {kind}: cycles per CTA (median over CTAs, then over launches); SM clock ~1.9 GHz")
+    for k, v in out.items():
+        print(f"   {k:28s} {v:9.0f} cycles  {v / 1.9e3:6.2f} us")
+    print("   per-warp task cycles:", " ".join(f"{int(x)}" for x in per_warp.tolist()))
+    print(f"   globaltimer: first CTA entry -> last CTA tail {span / 1e3:.2f} us; entry spread over the grid {first_last_entry / 1e3:.2f} us")
