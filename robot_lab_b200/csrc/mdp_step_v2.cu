@@ -46,9 +46,9 @@
 #define RL_V2_STAMPS 0   // build variant "stamps": clock64 / globaltimer stamps per CTA and warp into KArgs::dbg (tools/v2_timeline.py)
 #endif
 #if RL_V2_STAMPS
-#define V2_STAMP(slot) do { if (a.k.dbg != nullptr && lane == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
-#define V2_STAMP_T0(slot) do { if (a.k.dbg != nullptr && tid == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
-#define V2_GTIME(slot) do { if (a.k.dbg != nullptr && tid == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
+#define V2_STAMP(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && lane == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#define V2_STAMP_T0(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && tid == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#define V2_GTIME(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && tid == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
 #else
 #define V2_STAMP(slot) do { } while (0)
 #define V2_STAMP_T0(slot) do { } while (0)
@@ -369,6 +369,22 @@ struct alignas(64) V2Args {
   alignas(64) CUtensorMap tm[IF_COUNT];
 };
 
+// The parameter block of these kernels is ~5 KB (25 tensor maps of 128 bytes): the first touch of each of its lines is a
+// miss in the constant path, and the issuing lanes would take theirs one after the other. One lane per line touches the
+// whole block at kernel entry instead - the misses overlap each other and the mbarrier set-up.
+#ifndef RL_V2_PARAM_PREFETCH
+#define RL_V2_PARAM_PREFETCH 1
+#endif
+__device__ __forceinline__ void touch_params(const V2Args& a, const int tid) {
+#if RL_V2_PARAM_PREFETCH
+  constexpr int kLines = (int)((sizeof(V2Args) + 127) / 128);
+  if (tid < kLines) {
+    const int x = reinterpret_cast<const int*>(&a)[tid * 32];
+    asm volatile("" ::"r"(x));
+  }
+#endif
+}
+
 template <class B, int KIND, int C, int G, int NW>
 struct Cfg2 {
   static_assert(NW % G == 0 && NW <= 16, "tiles per CTA must divide the warp count");
@@ -511,7 +527,11 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
   const int env0 = cluster_id * E;
   const long long env = (long long)env0 + e;
   const bool my_hist = ((CF::hist_roles >> role) & 1u) != 0 && S.num_hist_bodies > 0;
+#if RL_V2_STAMPS
+  if (a.k.dbg == reinterpret_cast<long long*>(1)) return;   // launch-overhead probe (tools/v2_timeline.py --empty)
+#endif
   V2_GTIME(0); V2_STAMP_T0(1);
+  touch_params(a, tid);
   if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
   if (a.k.use_pdl) pdl_launch_dependents();   // the successor's prologue may overlap this kernel
   if (tid == 0) {
@@ -529,12 +549,8 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
       prefetch_l2(a.prefetch_rays + (size_t)env0 * a.prefetch_row_bytes, (uint32_t)(E * a.prefetch_row_bytes));
   }
   V2_STAMP_T0(11);
-  // per-joint constants: constant bank -> shared
-  for (int i = tid; i < S.num_joints; i += kThreads2)
-    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
-      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
-      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
-    });
+  // per-joint constants: device table -> shared
+  for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
   V2_STAMP_T0(12);
   if (role == 0)   // weight-0 terms: no task writes their slot of the final sum
     for (int i = tid; i < K * E; i += kThreads2)
@@ -542,6 +558,9 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
   __syncthreads();           // mbarrier init + the stores above visible to the CTA
   V2_STAMP_T0(2);
   mbar_wait(&s_bar, 0);      // record resident
+#if RL_V2_STAMPS
+  if (a.k.dbg == reinterpret_cast<long long*>(2)) return;   // probe: launch + load only
+#endif
   V2_STAMP_T0(3);
   if (my_hist) {
     // contact-force norm prepass: (tile, body) items over the warps, lane = env; ONE code copy for every consumer
@@ -679,14 +698,14 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
   const int cluster_id = (int)blockIdx.x / C;
   const int env0 = cluster_id * E;
   const long long env = (long long)env0 + e;
+#if RL_V2_STAMPS
+  if (a.k.dbg == reinterpret_cast<long long*>(1)) return;
+#endif
   V2_GTIME(0); V2_STAMP_T0(1);
+  touch_params(a, tid);
   if (C > 1) cluster_arrive_relaxed();
   if (a.k.use_pdl) pdl_launch_dependents();
-  for (int i = tid; i < S.num_joints; i += kThreads2)
-    DynPolicy::for_joint_consts(a.k, i, [&](float q0, float qd0, float lo, float hi, float vl) {
-      sm[L.cj + 0 * L.J + i] = q0; sm[L.cj + 1 * L.J + i] = qd0; sm[L.cj + 2 * L.J + i] = lo;
-      sm[L.cj + 3 * L.J + i] = hi; sm[L.cj + 4 * L.J + i] = vl;
-    });
+  for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
   if (tid == 0) {
     s_last = 0;
     arm_loads<CF>(a, role, &s_bar, false);
@@ -701,6 +720,7 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
     u8_head = static_cast<const uint8_t*>(a.k.is_heading.ptr)[env];
     u8_stand = static_cast<const uint8_t*>(a.k.is_standing.ptr)[env];
   }
+  const int u8_bits = (a.k.out.done_bits != nullptr) ? (int)a.k.out.done_bits[env] : 0;   // LOG tasks; requested early
   RandState rs;
   rs.seed = a.k.rnd.seed;
   rs.step = a.k.rnd.step + (a.k.rnd.step_counter ? *a.k.rnd.step_counter : 0ull);
@@ -765,6 +785,9 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
   __syncthreads();
   V2_STAMP_T0(2);
   mbar_wait(&s_bar, 0);
+#if RL_V2_STAMPS
+  if (a.k.dbg == reinterpret_cast<long long*>(2)) return;
+#endif
   V2_STAMP_T0(3);
 
   // ---- tasks: no barrier between the load and the row stores ------------------------------------------------------
@@ -791,7 +814,7 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
       if (C > 1 && !arrived) { cluster_arrive_release(); arrived = true; }   // nothing of this task goes through DSMEM
       const int gt = cluster_id * G + tile;
       const int part = tk.b, parts = tk.col0;
-      const int fl = (a.k.out.done_bits != nullptr) ? (int)a.k.out.done_bits[env] : 0;
+      const int fl = u8_bits;
       constexpr int NQ = K + RL_MAX_DONE_TERMS + 2;
       if (__ballot_sync(0xffffffffu, rme) == 0u) {   // nothing to reset in this tile: the partials are zero
         for (int q = part + lane * parts; q < NQ; q += 32 * parts) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;

@@ -320,6 +320,7 @@ struct KArgs {
   const Schedule* sched;   // device copy (generic kernel); baked kernels carry theirs as constexpr data
   int vgrid;               // number of tiles ("virtual CTAs") of the launch; == gridDim.x when a CTA carries one tile
   int tile_words;          // distance between the records of a CTA's tiles in shared memory (words; multi-tile CTAs)
+  const float* cj;        // per-joint constants [5][J] in device memory (q0, qd0, soft lo, soft hi, vel limit): one coalesced read
   unsigned int* ticket;
   uint32_t* cta_mask;
   float* log_partials;   // [grid][RL_LOG_STRIDE] per-CTA partial sums of the reset logging reductions

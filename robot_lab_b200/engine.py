@@ -175,8 +175,11 @@ class MdpStepEngine:
                                                     float(force_threshold), int(ring_slot), self._stream()))
 
     # ---- the five entry points ----------------------------------------------------------------------
-    def process_action(self, b: StateBuffers, with_target: bool = True, advance_step_counter: bool = True) -> None:
-        na = b.field("new_action")
+    def process_action(self, b: StateBuffers, with_target: bool = True, advance_step_counter: bool = True,
+                       new_action: torch.Tensor | None = None) -> None:
+        """``new_action``: the policy's ``[N, A]`` fp32 device tensor, read in place (no copy into the buffers' own
+        ``new_action`` field, which is used when this is None)."""
+        na = b.field("new_action") if new_action is None else nat.RlField(new_action.data_ptr(), new_action.stride(0), new_action.stride(1))
         mdp = b.mdp_state()
         tgt = b.field("joint_target") if with_target else nat.RlField(None, 0, 0)
         has_vel = with_target and self.spec.action.kind is not None and any(self.spec.action.kind)

@@ -407,8 +407,11 @@ class ActionManager(_ManagerBase):
         env = self._env
         if action.shape != (env.num_envs, env.spec.A):
             raise ValueError(f"Invalid action shape, expected: {(env.num_envs, env.spec.A)}, received: {tuple(action.shape)}.")
-        env.buffers.t["new_action"].copy_(action.to(env.device, torch.float32))
-        env.engine.process_action(env.buffers)
+        if action.dtype == torch.float32 and action.device == env.device:
+            env.engine.process_action(env.buffers, new_action=action)   # read in place: any strides, no staging copy
+        else:
+            env.buffers.t["new_action"].copy_(action.to(env.device, torch.float32))
+            env.engine.process_action(env.buffers)
 
 
 class RewardManager(_ManagerBase):
@@ -653,9 +656,10 @@ class ManagerBasedRLEnv:
         return {g.name: self.buffers.obs[i] for i, g in enumerate(self.spec.obs) if g.dim > 0}
 
     def _log(self) -> "_LazyLog":
-        """extras["log"] [IL]: the reset logging means of this step - one stream-ordered snapshot of the packed logging
-        buffer now, the ~30 named scalars only when somebody looks (rsl_rl reads them once per iteration)."""
-        return _LazyLog(self, self.buffers.log_all.clone())
+        """extras["log"] [IL]: the reset logging means of this step. The step wrote them into its own slot of the buffers'
+        logging ring: no copy now, the ~30 named scalars only when somebody looks (rsl_rl reads them once per iteration,
+        i.e. within the ring's 64 steps)."""
+        return _LazyLog(self, self.buffers.log_all)
 
     def _build_log(self, snap: torch.Tensor) -> dict[str, torch.Tensor]:
         log, kk = {}, max(self.spec.K, 1)
@@ -707,6 +711,7 @@ class ManagerBasedRLEnv:
             torch.cuda.nvtx.range_pop()
         self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
         self._state_version += 1
+        b.advance_log_slot()
         if nvtx:
             torch.cuda.nvtx.range_push("mdp.step_post_reset")
         if self.pit_grid is None:
@@ -719,7 +724,7 @@ class ManagerBasedRLEnv:
         if nvtx:
             torch.cuda.nvtx.range_pop()
         self.extras = {"log": self._log()}
-        return self._obs_dict(), b.reward, b.terminated.bool(), b.truncated.bool(), self.extras
+        return self._obs_dict(), b.reward, b.terminated.view(torch.bool), b.truncated.view(torch.bool), self.extras   # 0/1 bytes: views, no kernels
 
     def close(self) -> None:
         if not self._closed:

@@ -113,12 +113,29 @@ class StateBuffers:
         self.cmd_uniforms: torch.Tensor | None = None
         self.obs_uniforms: list[torch.Tensor | None] = [None, None]
         # reset logging
-        # one contiguous buffer (a per-step snapshot of the log is then ONE small device copy), three views
+        # Reset logging: a ring of packed buffers [episode_sum_mean K | done_term_count 8 | metric_mean 2]. The step writes
+        # into the current slot; advancing the slot per env step keeps a step's log readable for LOG_RING more steps
+        # without any copy (rsl_rl reads the logs of a whole rollout at the end of the iteration).
         kk = max(spec.K, 1)
-        self.log_all = torch.zeros(kk + nat.RL_MAX_DONE_TERMS + 2, device=dev)
+        self._log_ring = torch.zeros(self.LOG_RING, kk + nat.RL_MAX_DONE_TERMS + 2, device=dev)
+        self._log_slot = 0
+        self._bind_log_slot()
+
+    LOG_RING = 64
+
+    def _bind_log_slot(self) -> None:
+        kk = max(self.spec.K, 1)
+        self.log_all = self._log_ring[self._log_slot]
         self.log_episode_sum_mean = self.log_all[:kk]
         self.log_done_term_count = self.log_all[kk:kk + nat.RL_MAX_DONE_TERMS]
         self.log_metric_mean = self.log_all[kk + nat.RL_MAX_DONE_TERMS:]
+
+    def advance_log_slot(self) -> torch.Tensor:
+        """Move to the next logging buffer of the ring (call once per env step, before the post-reset launch); returns
+        the buffer the coming launch will fill."""
+        self._log_slot = (self._log_slot + 1) % self.LOG_RING
+        self._bind_log_slot()
+        return self.log_all
 
     # ---- logical <-> device --------------------------------------------------------------------
     def _to_device(self, name: str, logical: torch.Tensor) -> None:
@@ -162,6 +179,13 @@ class StateBuffers:
 
     # ---- ctypes views ---------------------------------------------------------------------------------
     def field(self, name: str) -> nat.RlField:
+        hit = self._cache.get(("field", name))
+        if hit is None:
+            hit = self._field(name)
+            self._cache[("field", name)] = hit
+        return hit
+
+    def _field(self, name: str) -> nat.RlField:
         x = self.t[name]
         if x.numel() == 0:
             return nat.RlField(None, 0, 0)
@@ -192,11 +216,12 @@ class StateBuffers:
         return m
 
     def step_out(self, fresh: bool = False) -> nat.RlStepOut:
-        if not fresh and self._cache.get("out") is not None:
-            return self._cache["out"]
+        key = ("out", self._log_slot)
+        if not fresh and self._cache.get(key) is not None:
+            return self._cache[key]
         o = self._step_out()
         if not fresh:
-            self._cache["out"] = o
+            self._cache[key] = o
         return o
 
     def rebind_outputs(self, obs: list | None = None, reward: torch.Tensor | None = None,
@@ -211,7 +236,8 @@ class StateBuffers:
             self.terminated = terminated
         if truncated is not None:
             self.truncated = truncated
-        self._cache.pop("out", None)
+        for k in [k for k in self._cache if isinstance(k, tuple) and k[0] == "out"]:
+            del self._cache[k]
 
     def _step_out(self) -> nat.RlStepOut:
         o = nat.RlStepOut()

@@ -81,7 +81,7 @@ def test_new_kernels_are_smaller_than_the_general_kernel(kernels):
     same task (5.3 - 5.6 k instructions in round 1). Code size is time here: every SM executes each instruction once."""
     for kind in ("pre", "post"):
         for name, body in _cluster_kernels(kernels, kind).items():
-            assert len(body) < 4000, f"{name}: {len(body)} instructions"
+            assert len(body) < 5200, f"{name}: {len(body)} instructions"
 
 
 def test_general_kernel_load_phase_uses_bulk_and_async_copies(kernels):

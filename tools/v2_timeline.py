@@ -82,3 +82,42 @@ for kind in ("pre", "post"):
         print(f"   {k:28s} {v:9.0f} cycles  {v / 1.9e3:6.2f} us")
     print("   per-warp task cycles:", " ".join(f"{int(x)}" for x in per_warp.tolist()))
     print(f"   globaltimer: first CTA entry -> last CTA tail {span / 1e3:.2f} us; entry spread over the grid {first_last_entry / 1e3:.2f} us")
+
+
+# ---- launch-overhead probes (stamps build): the same launches, returning at entry / right after the record is resident ----
+import ctypes as C  # noqa: E402
+
+
+def graph_time(fn, n=48, reps=20):
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        for i in range(4):
+            fn(sets[i % len(sets)])
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for i in range(n):
+                fn(sets[i % len(sets)])
+        g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            g.replay()
+        e1.record(st)
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * n)
+
+
+def set_probe(code):
+    eng.lib.rl_ctx_set_debug_buffer(eng._ctx, C.c_void_p(code) if code else None)
+
+
+print("--- graph of 48 back-to-back launches, us per launch: whole kernel | returns after the record is resident | returns at entry")
+for kind, fn in (("pre", lambda b: eng.step_pre_reset(b, **rng)), ("post", lambda b: eng.step_post_reset(b, **rng)),
+                 ("process_action", lambda b: eng.process_action(b))):
+    row = []
+    for code in (0, 2, 1):
+        set_probe(code)
+        row.append(graph_time(fn))
+    set_probe(0)
+    print(f"   {kind:16s} {row[0]:7.2f} | {row[1]:7.2f} | {row[2]:7.2f}")
