@@ -250,8 +250,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout: keep stdout to the ONE JSON line
+        # NCCL's version banner / debug lines go to stdout by default: keep stdout to the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     N, S, K, W = args.num_envs, max(1, args.sets), args.steps, max(3, args.warmup)
@@ -945,6 +945,29 @@ def measure_handoff(eng, spec, sets, N, world, dev, local_rank, one_step):
     best_k = min(sweep, key=sweep.get)
     store.set_gather_every(best_k)
     ms_s = sweep[best_k]
+    # the whole streamed rollout - 24 steps on the main stream, the chunk gathers forked onto the side stream, the join - as
+    # ONE CUDA graph (NCCL collectives are capturable): no host work between the steps at all
+    ms_sg, graph_note = None, None
+    try:
+        torch.cuda.synchronize(dev)
+        dist.barrier(device_ids=[local_rank])
+        g_stream = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_stream, stream=main):
+            for t in range(ROLLOUT):
+                one_step(sets[t % S])
+                store.gather_step(t, after=main)
+            store.finish()
+
+        def streamed_graph():
+            with torch.cuda.stream(main):
+                g_stream.replay()
+
+        ms_sg = timed(streamed_graph)
+        if ms_sg < ms_s:
+            ms_s, graph_note = ms_sg, "whole streamed rollout (steps + side-stream gathers) replayed as one CUDA graph"
+    except Exception as e:   # capture of collectives not supported in this build: keep the eager pipeline's number
+        graph_note = f"graph capture of the streamed rollout failed ({type(e).__name__}): eager pipeline timed"
+        torch.cuda.synchronize(dev)
     nbytes = store.data.numel() * 4
     ingress = nbytes * (world - 1)
     floor_ms = ingress / (NVLINK_PEER_GBS * 1e9) * 1e3
@@ -965,7 +988,7 @@ def measure_handoff(eng, spec, sets, N, world, dev, local_rank, one_step):
                           "in place into per-step rollout slabs",
             "bytes_per_rank_per_rollout": nbytes, "ingress_bytes_per_rank": ingress, "per_rollout_steps": ROLLOUT,
             "compute_only_ms": ms_c, "unstreamed_ms": ms_u, "streamed_ms": ms_s, "gather_alone_ms": ms_g,
-            "streamed_ms_by_steps_per_gather": sweep, "steps_per_gather": best_k,
+            "streamed_ms_by_steps_per_gather": sweep, "steps_per_gather": best_k, "streamed_graph_ms": ms_sg, "streamed_note": graph_note,
             "exposed_handoff_ms": ms_s - ms_c, "exposed_handoff_ms_unstreamed": ms_u - ms_c,
             "floor_ms": floor_ms, "floor_note": f"{ingress / 1e6:.0f} MB must enter every GPU; {NVLINK_PEER_GBS:.0f} GB/s measured peer copy per "
                                                 "direction per GPU (900 nominal): NVLink INGRESS per GPU is the limiting link",

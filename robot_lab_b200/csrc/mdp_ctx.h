@@ -21,6 +21,7 @@ struct RlCtx {
   float* log_partials;
   int cta_mask_cap;
   RlRewardTerm* adhoc_dev;
+  float* action_tab_dev;  // per-column action table [5][A]: scale, offset, clip lo / hi, joint id | target kind << 8 (rl_process_action)
   float* cj_dev;          // per-joint constants [5][J] (default pos / vel, soft limits, velocity limit) for the kernels' records
   int sm_count;
   size_t smem_optin;      // largest dynamic shared memory a CTA may ask for on this device

@@ -564,40 +564,59 @@ __global__ void __launch_bounds__(NW * 32) mdp_step_kernel(const KArgs a) {
 // One CTA = 32 consecutive envs. Phase 1 reads the policy's action rows in the order they lie in memory into shared
 // memory; phase 2 walks (column, env) with env fastest, so that every SoA destination (stored action, previous
 // action, joint targets) is written as coalesced rows - and any other layout through the same strides.
+// The per-column action table (scale, offset, clip, joint id, target kind) comes from a packed device copy with one
+// coalesced read: six lane-uniform reads of six different __constant__ arrays are six serialised cold misses, 1 us of a
+// 3 us launch (launch probe of round 2: an empty kernel node costs 0.6 us).
 constexpr int kPaEnvs = 32;
-__global__ void __launch_bounds__(256) process_action_kernel(int N, int slot, RlField new_action, RlField action, RlField prev_action,
-                                                            RlField target, RlField vel_target, unsigned long long* step_counter, int use_pdl) {
+// table layout, [A] each: scale | offset | clip_lo | clip_hi | (joint id | target kind << 8) as int bits
+__global__ void __launch_bounds__(256) process_action_kernel(int N, int A, int has_clip, const float* __restrict__ tab, RlField new_action,
+                                                            RlField action, RlField prev_action, RlField target, RlField vel_target,
+                                                            unsigned long long* step_counter, int use_pdl) {
   __shared__ float s_act[kPaEnvs * (RL_MAX_JOINTS + 1)];
+  __shared__ float s_tab[5 * RL_MAX_JOINTS];
   if (use_pdl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
-  const RlActionCfg& ac = c_spec[slot].action;
-  const int A = ac.n_actions;
   const int env0 = (int)blockIdx.x * kPaEnvs;
   const int ne = min(kPaEnvs, N - env0);
   const int P = A + 1;   // odd-ish pitch: phase 2 reads a column of the tile without bank conflicts for the usual A
   const bool env_major = (new_action.env_stride == 1);
+  for (int i = threadIdx.x; i < 5 * A; i += blockDim.x) s_tab[i] = __ldg(tab + i);
+  // the stored actions this thread will overwrite in phase 2 are requested NOW, together with the policy's rows: one
+  // memory round trip for the launch instead of two dependent ones (kPaEnvs * RL_MAX_JOINTS / 256 = 8 values at most)
+  constexpr int kMine = kPaEnvs * RL_MAX_JOINTS / 256;
+  float old_a[kMine];
+#pragma unroll
+  for (int q = 0; q < kMine; ++q) {
+    const int i = threadIdx.x + q * 256;
+    old_a[q] = 0.f;
+    if (i < ne * A && blockDim.x == 256)
+      old_a[q] = static_cast<const float*>(action.ptr)[(long long)(env0 + i % ne) * action.env_stride + (long long)(i / ne) * action.comp_stride];
+  }
   for (int i = threadIdx.x; i < ne * A; i += blockDim.x) {
     int el, col;
     if (env_major) { el = i % ne; col = i / ne; } else { col = i % A; el = i / A; }
     s_act[el * P + col] = static_cast<const float*>(new_action.ptr)[(long long)(env0 + el) * new_action.env_stride + (long long)col * new_action.comp_stride];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < ne * A; i += blockDim.x) {
+#pragma unroll
+  for (int q = 0; q < kMine; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i >= ne * A) break;
     const int el = i % ne, col = i / ne;
     const long long env = env0 + el;
     const float nv = s_act[el * P + col];
-    float* ap = static_cast<float*>(action.ptr) + env * action.env_stride + (long long)col * action.comp_stride;
     if (prev_action.ptr)
-      static_cast<float*>(prev_action.ptr)[env * prev_action.env_stride + (long long)col * prev_action.comp_stride] = *ap;
-    *ap = nv;
-    const RlField& dst = (ac.target_kind[col] == RL_ACTION_JOINT_VELOCITY) ? vel_target : target;
+      static_cast<float*>(prev_action.ptr)[env * prev_action.env_stride + (long long)col * prev_action.comp_stride] = old_a[q];
+    static_cast<float*>(action.ptr)[env * action.env_stride + (long long)col * action.comp_stride] = nv;
+    const int idk = __float_as_int(s_tab[4 * A + col]);
+    const RlField& dst = ((idk >> 8) == RL_ACTION_JOINT_VELOCITY) ? vel_target : target;
     if (dst.ptr) {
-      float v = nv * ac.scale[col] + ac.offset[col];
-      if (ac.has_clip) v = clampf(v, ac.clip_lo[col], ac.clip_hi[col]);
-      static_cast<float*>(dst.ptr)[env * dst.env_stride + (long long)ac.joint_ids[col] * dst.comp_stride] = v;
+      float v = nv * s_tab[col] + s_tab[A + col];
+      if (has_clip) v = clampf(v, s_tab[2 * A + col], s_tab[3 * A + col]);
+      static_cast<float*>(dst.ptr)[env * dst.env_stride + (long long)(idk & 0xff) * dst.comp_stride] = v;
     }
   }
 }
@@ -1074,6 +1093,18 @@ int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out) {
     CUDA_TRY(cudaMalloc(&ctx->cj_dev, sizeof(float) * 5 * RL_MAX_JOINTS));
     CUDA_TRY(cudaMemcpy(ctx->cj_dev, cj, sizeof(float) * 5 * J, cudaMemcpyHostToDevice));
   }
+  {
+    const RlActionCfg& ac = spec->action;
+    const int A = ac.n_actions;
+    float tab[5 * RL_MAX_JOINTS];
+    for (int c = 0; c < A; ++c) {
+      tab[c] = ac.scale[c]; tab[A + c] = ac.offset[c]; tab[2 * A + c] = ac.clip_lo[c]; tab[3 * A + c] = ac.clip_hi[c];
+      const int idk = (int)ac.joint_ids[c] | ((int)ac.target_kind[c] << 8);
+      memcpy(&tab[4 * A + c], &idk, sizeof(int));
+    }
+    CUDA_TRY(cudaMalloc(&ctx->action_tab_dev, sizeof(float) * 5 * RL_MAX_JOINTS));
+    CUDA_TRY(cudaMemcpy(ctx->action_tab_dev, tab, sizeof(float) * 5 * (A > 0 ? A : 1), cudaMemcpyHostToDevice));
+  }
   rc = ensure_scratch(ctx, 4096);
   if (rc != RL_OK) return rc;
   ctx->baked = -1;
@@ -1103,6 +1134,7 @@ void rl_ctx_destroy(RlCtx* ctx) {
   if (ctx->log_partials) cudaFree(ctx->log_partials);
   if (ctx->adhoc_dev) cudaFree(ctx->adhoc_dev);
   if (ctx->cj_dev) cudaFree(ctx->cj_dev);
+  if (ctx->action_tab_dev) cudaFree(ctx->action_tab_dev);
   if (ctx->sched_dev) cudaFree(ctx->sched_dev);
   g_slots[ctx->device][ctx->slot] = false;
   delete ctx;
@@ -1247,8 +1279,9 @@ int rl_process_action(RlCtx* ctx, int64_t num_envs, const RlField* new_action, c
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, process_action_kernel, (int)num_envs, ctx->slot, *new_action, mdp->action,
-                              mdp->prev_action, tgt, vtgt, (unsigned long long*)step_counter, ctx->use_pdl));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, process_action_kernel, (int)num_envs, (int)ctx->spec.action.n_actions, (int)ctx->spec.action.has_clip,
+                              (const float*)ctx->action_tab_dev, *new_action, mdp->action, mdp->prev_action, tgt, vtgt,
+                              (unsigned long long*)step_counter, ctx->use_pdl));
   return RL_OK;
 }
 

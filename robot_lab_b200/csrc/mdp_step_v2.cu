@@ -66,8 +66,10 @@ __host__ __device__ constexpr uint32_t v2_field_mask(const RlStepSpec& s, int ki
   uint32_t m = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_JPOS) |
                (1u << IF_JVEL) | (1u << IF_CMD) | (1u << IF_EPLEN) | (1u << IF_ACT);
   if (kind == RL_V2_PRE) {
+    // (the episode sums are not staged: the task that updates sum k reads its row from global memory when it starts and
+    //  writes it when it ends - the same bytes, 21 fewer record rows: a fifth resident CTA per SM at 8 warps per tile)
     m |= (1u << IF_PACT) | (1u << IF_JACC) | (1u << IF_JTAU) | (1u << IF_CAIR) | (1u << IF_LAIR) | (1u << IF_CCON) |
-         (1u << IF_LCON) | (1u << IF_BPOS) | (1u << IF_BVEL) | (1u << IF_SUMS);
+         (1u << IF_LCON) | (1u << IF_BPOS) | (1u << IF_BVEL);
   } else {
     m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU) | (1u << IF_SUMS);
   }
@@ -102,6 +104,8 @@ __host__ __device__ constexpr bool v2_spec_ok(const RlStepSpec& s) {
     if (scans > 1) return false;
   }
   if (s.num_hist_bodies > 0 && s.hist_len <= 0) return false;
+  for (int k = 0; k < s.num_reward_terms; ++k)   // feet_stumble reads raw force rows (the newest sample), which are not staged here
+    if (s.rewards[k].type == RL_REW_FEET_STUMBLE && s.rewards[k].weight != 0.f) return false;
   return true;
 }
 
@@ -109,7 +113,7 @@ __host__ __device__ constexpr bool v2_spec_ok(const RlStepSpec& s) {
 // Record layout of a CTA: 32 G envs; the term functions address it through the same Layout members as the general
 // kernel (SoA word w of env e at sm[w*E + e]).
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const int E, const int kind) {
+__host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const int E, const int kind, const int NW) {
   Layout L{};
   L.E = E;
   int w = 0;
@@ -127,8 +131,11 @@ __host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const i
   L.mxy = iw[IF_MXY] * E; L.myaw = iw[IF_MYAW] * E; L.eplen = iw[IF_EPLEN] * E;
   L.sums = iw[IF_SUMS] * E; L.cmdu = iw[IF_CMDU] * E; L.act = iw[IF_ACT] * E; L.pact = iw[IF_PACT] * E;
   L.w_sums = iw[IF_SUMS];
-  L.ishead = take(1) * E; L.isstand = take(1) * E; L.rmask = take(1) * E;
-  L.cmdn = take(3) * E; L.epnew = take(1) * E; L.flags = take(1) * E;
+  if (kind == RL_V2_POST) {
+    L.ishead = take(1) * E; L.isstand = take(1) * E; L.rmask = take(1) * E;
+    L.cmdn = take(3) * E; L.epnew = take(1) * E;
+  }
+  L.flags = take(1) * E;
   if (kind == RL_V2_PRE) {
     L.termv = take(K) * E;                      // role 0: weighted value of every term (DSMEM target)
     L.hnorm = take(s.num_hist_bodies) * E;      // cached contact-force norms
@@ -137,8 +144,10 @@ __host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const i
   int off = align_up(w * E, 32);
   L.cj = off; off = align_up(off + 5 * J, 32);
   if (kind == RL_V2_PRE) {
-    L.hist_pitch = s.hist_len * s.num_hist_bodies * 3;   // dense rows: one bulk copy; only the norm prepass reads them
-    L.hist = off; off = align_up(off + E * L.hist_pitch, 32);
+    // the contact-force rows are NOT staged: the norm prepass streams them from global memory; per warp a scratch row of
+    // hist_len * bodies squared norms (hist = scratch base, hist_pitch = words per warp)
+    L.hist_pitch = align_up(s.hist_len * s.num_hist_bodies, 32);
+    L.hist = off; off = align_up(off + NW * L.hist_pitch, 32);
   } else {
     L.obs_pitch0 = odd_pitch(env_cols_of(s.obs[0])); L.obs_pitch1 = odd_pitch(env_cols_of(s.obs[1]));
     L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
@@ -278,7 +287,7 @@ __host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int k
 constexpr uint32_t kCoreFields = (1u << IF_ROOT_POS) | (1u << IF_QUAT) | (1u << IF_LIN_VEL) | (1u << IF_ANG_VEL) | (1u << IF_CMD);   // make_ctx
 
 __host__ __device__ constexpr uint32_t reward_fields(int type) {
-  uint32_t m = kCoreFields | (1u << IF_SUMS);
+  uint32_t m = kCoreFields;
   switch (type) {
     case RL_REW_JOINT_TORQUES_L2: m |= 1u << IF_JTAU; break;
     case RL_REW_JOINT_VEL_L2: case RL_REW_JOINT_VEL_LIMITS: m |= 1u << IF_JVEL; break;
@@ -312,7 +321,6 @@ __host__ __device__ constexpr uint32_t obs_fields(int type) {
 __host__ __device__ constexpr uint32_t role_field_mask(const RlStepSpec& s, const Sched2& sc, int kind, int role, int W) {
   uint32_t m = kCoreFields | (1u << IF_EPLEN);
   if (role == 0) {
-    m |= 1u << IF_SUMS;   // PRE: is_terminated is finished by the final sum; POST: the logging means of the reset
     if (kind == RL_V2_POST) m |= (1u << IF_HEAD) | (1u << IF_TLEFT) | (1u << IF_MXY) | (1u << IF_MYAW) | (1u << IF_CMDU);
   }
   for (int i = 0; i < sc.n; ++i) {
@@ -369,22 +377,6 @@ struct alignas(64) V2Args {
   alignas(64) CUtensorMap tm[IF_COUNT];
 };
 
-// The parameter block of these kernels is ~5 KB (25 tensor maps of 128 bytes): the first touch of each of its lines is a
-// miss in the constant path, and the issuing lanes would take theirs one after the other. One lane per line touches the
-// whole block at kernel entry instead - the misses overlap each other and the mbarrier set-up.
-#ifndef RL_V2_PARAM_PREFETCH
-#define RL_V2_PARAM_PREFETCH 1
-#endif
-__device__ __forceinline__ void touch_params(const V2Args& a, const int tid) {
-#if RL_V2_PARAM_PREFETCH
-  constexpr int kLines = (int)((sizeof(V2Args) + 127) / 128);
-  if (tid < kLines) {
-    const int x = reinterpret_cast<const int*>(&a)[tid * 32];
-    asm volatile("" ::"r"(x));
-  }
-#endif
-}
-
 template <class B, int KIND, int C, int G, int NW>
 struct Cfg2 {
   static_assert(NW % G == 0 && NW <= 16, "tiles per CTA must divide the warp count");
@@ -392,7 +384,7 @@ struct Cfg2 {
   static constexpr int NT = NW * 32;      // threads per CTA
   static constexpr int E = 32 * G;        // envs per cluster
   static constexpr int BINS = C * W;
-  static constexpr Layout L = make_layout_v2(B::spec, E, KIND);
+  static constexpr Layout L = make_layout_v2(B::spec, E, KIND, NW);
   static constexpr Sched2 sched = make_schedule_v2(B::spec, KIND, C, W, G, NW);
   static constexpr Scalars S = scalars_of(B::spec);
   // scalar copies: device code must not odr-use the schedule object itself
@@ -437,29 +429,64 @@ __device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, con
 // issuing all ~20 of them in a row serialised those misses into 2.9 us of a 4096-env launch (measured: profiles/
 // r2_summary.md). Spread over the warps they overlap.
 template <class CF>
-__device__ __forceinline__ void arm_loads(const V2Args& a, const uint32_t role, uint64_t* bar, const bool with_hist) {
-  constexpr Scalars S = CF::S;
-  constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
+__device__ __forceinline__ void arm_loads(const V2Args& a, const uint32_t role, uint64_t* bar) {
   mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  uint32_t bytes = a.role_bytes[role];
-  if (with_hist) bytes += (uint32_t)(CF::E * HW * 4);
-  mbar_expect_tx(bar, bytes);
+  mbar_expect_tx(bar, a.role_bytes[role]);
 }
 template <class CF>
-__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar,
-                                            const bool with_hist, const int warp) {
-  constexpr Layout L = CF::L;
-  constexpr Scalars S = CF::S;
-  constexpr int HW = S.hist_len * S.num_hist_bodies * 3;
-  if (with_hist && warp == 0)   // the largest transfer first
-    bulk_g2s(sm + L.hist, static_cast<const float*>(a.k.hist.ptr) + (size_t)env0 * HW, (uint32_t)(CF::E * HW * 4), bar);
+__device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar, const int warp) {
   const uint32_t m = a.role_mask[role];
   const int n = __popc(m);
 #pragma unroll 1
   for (int i = warp; i < n; i += CF::NT / 32) {
     const int f = (int)__fns(m, 0u, i + 1);   // the (i+1)-th staged field
     tma_load_2d(sm + a.field_word[f] * CF::E, &a.tm[f], env0, 0, bar);
+  }
+}
+
+// Contact-force norm prepass: max over the history of |F_b| for every body of every env of the CTA, ONCE, straight from
+// global memory. A warp takes an env at a time with lanes = (history sample, body) pairs: its 3 * T * B floats are one
+// contiguous, coalesced row; the squared norms go through a per-warp scratch row, lanes = bodies take the max over the
+// history (same order as hist_max_norm) and ONE IEEE sqrt. All loads of the warp's envs are in flight before the first
+// use, and the whole prepass runs while the tensor-map copies of the record are still in flight. Nothing of the force
+// history is staged in shared memory (round-2 first cut: a 22 KB bulk copy per tile, half of the record).
+template <class CF>
+__device__ __forceinline__ void norm_prepass(float* sm, const float* __restrict__ hist_tile, const int warp, const int lane) {
+  constexpr Layout L = CF::L;
+  constexpr Scalars S = CF::S;
+  constexpr int T = S.hist_len, Bh = S.num_hist_bodies, TB = T * Bh, HW = TB * 3;
+  constexpr int NWARPS = CF::NT / 32, EPW = CF::E / NWARPS, PASSES = (TB + 31) / 32;
+  static_assert(CF::E % NWARPS == 0, "envs of a CTA must divide over its warps");
+  float ss[EPW][PASSES];
+#pragma unroll
+  for (int i = 0; i < EPW; ++i) {
+    const float* row = hist_tile + (size_t)(warp + i * NWARPS) * HW;
+#pragma unroll
+    for (int q = 0; q < PASSES; ++q) {
+      const int p = q * 32 + lane;
+      ss[i][q] = 0.f;
+      if (p < TB) {
+        const float f0 = __ldg(row + 3 * p), f1 = __ldg(row + 3 * p + 1), f2 = __ldg(row + 3 * p + 2);
+        ss[i][q] = (f0 * f0 + f1 * f1) + f2 * f2;
+      }
+    }
+  }
+  float* scr = sm + L.hist + warp * L.hist_pitch;
+#pragma unroll
+  for (int i = 0; i < EPW; ++i) {
+    const int ee = warp + i * NWARPS;
+#pragma unroll
+    for (int q = 0; q < PASSES; ++q)
+      if (q * 32 + lane < TB) scr[q * 32 + lane] = ss[i][q];
+    __syncwarp();
+    for (int b = lane; b < Bh; b += 32) {
+      float m2 = scr[b];
+#pragma unroll
+      for (int t = 1; t < T; ++t) m2 = fmaxf(m2, scr[t * Bh + b]);
+      sm[L.hnorm + b * CF::E + ee] = (m2 == 0.f) ? 0.f : sqrtf(m2);
+    }
+    __syncwarp();
   }
 }
 
@@ -508,7 +535,7 @@ __device__ __noinline__ void compact_reset_ids(const KArgs& a, const int n_tiles
 // PRE: TerminationManager.compute + RewardManager.compute [IL] + reset_buf.nonzero()
 // ---------------------------------------------------------------------------------------------------
 template <class B, int C, int G, int NW>
-__global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pre_kernel(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? 5 : 2))) v2_pre_kernel(const __grid_constant__ V2Args a) {
   using CF = Cfg2<B, RL_V2_PRE, C, G, NW>;
   constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
@@ -531,24 +558,25 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
   if (a.k.dbg == reinterpret_cast<long long*>(1)) return;   // launch-overhead probe (tools/v2_timeline.py --empty)
 #endif
   V2_GTIME(0); V2_STAMP_T0(1);
-  touch_params(a, tid);
   if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
   if (a.k.use_pdl) pdl_launch_dependents();   // the successor's prologue may overlap this kernel
   if (tid == 0) {
     s_last = 0;
-    arm_loads<CF>(a, role, &s_bar, my_hist);
+    arm_loads<CF>(a, role, &s_bar);
   }
   V2_STAMP_T0(9);
   __syncthreads();                            // the armed mbarrier is visible to every issuing warp
   V2_STAMP_T0(10);
   if (a.k.use_pdl) pdl_wait();                // no global access of this kernel before its predecessor is complete
   if (lane == 0) {
-    issue_loads<CF>(sm, a, role, env0, &s_bar, my_hist, warp);
+    issue_loads<CF>(sm, a, role, env0, &s_bar, warp);
     // the post-reset launch of this env step streams the tile's ray hits: have them in L2 by then
     if (role == 0 && warp == kWarps2 - 1 && a.prefetch_rays != nullptr)
       prefetch_l2(a.prefetch_rays + (size_t)env0 * a.prefetch_row_bytes, (uint32_t)(E * a.prefetch_row_bytes));
   }
   V2_STAMP_T0(11);
+  if (my_hist)   // contact-force norms from global memory, in the shadow of the record's copies
+    norm_prepass<CF>(sm, static_cast<const float*>(a.k.hist.ptr) + (size_t)env0 * (S.hist_len * S.num_hist_bodies * 3), warp, lane);
   // per-joint constants: device table -> shared
   for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
   V2_STAMP_T0(12);
@@ -562,17 +590,6 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
   if (a.k.dbg == reinterpret_cast<long long*>(2)) return;   // probe: launch + load only
 #endif
   V2_STAMP_T0(3);
-  if (my_hist) {
-    // contact-force norm prepass: (tile, body) items over the warps, lane = env; ONE code copy for every consumer
-    constexpr int Bh = S.num_hist_bodies;
-#pragma unroll 1
-    for (int it = warp; it < G * Bh; it += kWarps2) {
-      const int t = it / Bh, b = it - t * Bh;
-      const int ee = t * 32 + lane;
-      sm[L.hnorm + b * E + ee] = hist_max_norm(sm + L.hist + ee * L.hist_pitch, S.hist_len, Bh, b);
-    }
-    __syncthreads();
-  }
   if (C > 1) cluster_wait_acquire();
   V2_STAMP_T0(4);
 
@@ -588,11 +605,12 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
       [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm&, const bool, const EnvCtx& c) __attribute__((always_inline)) {
     if (tk.kind == TK_REWARD) {
       const int k = tk.a;
+      const float sum_old = __ldg(static_cast<const float*>(f_sums.ptr) + (size_t)k * f_sums.cs + env);   // in flight while the term is evaluated
       const float raw = reward_term<CN>(rt, c_spec[a.k.slot].rewards[tk.a], S, L, sm, e, c, 0, 64);
       // RewardManager.compute [IL]: value = func * weight * dt; sums += value; step_reward = value / dt
       const float val = (raw * rt.weight) * S.step_dt;
       termv0[k * E + e] = val;
-      const float ns = SMF(L.sums, k) + val, sr = rl_div(val, S.step_dt);
+      const float ns = sum_old + val, sr = rl_div(val, S.step_dt);
       if (C > 1 && np < kPend) {
         p_sum[np] = ns; p_step[np] = sr; p_k[np] = k; ++np;
       } else {
@@ -653,7 +671,8 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
         const float raw = ((fl >> 8) & 1) ? 1.f : 0.f;
         const float val = (raw * a.k.rw_weight[k]) * S.step_dt;
         SMF(L.termv, k) = val;
-        static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)k * f_sums.cs + env] = SMF(L.sums, k) + val;
+        float* gsum = static_cast<float*>(const_cast<void*>(f_sums.ptr)) + (size_t)k * f_sums.cs + env;
+        *gsum = *gsum + val;
         if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)k * f_stepr.cs + env] = rl_div(val, S.step_dt);
       }
     }
@@ -682,7 +701,7 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_pr
 // ObservationManager.compute [IL] for all envs
 // ---------------------------------------------------------------------------------------------------
 template <class B, int C, int G, int NW>
-__global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_post_kernel(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? 6 : 3))) v2_post_kernel(const __grid_constant__ V2Args a) {
   using CF = Cfg2<B, RL_V2_POST, C, G, NW>;
   constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
@@ -702,17 +721,16 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
   if (a.k.dbg == reinterpret_cast<long long*>(1)) return;
 #endif
   V2_GTIME(0); V2_STAMP_T0(1);
-  touch_params(a, tid);
   if (C > 1) cluster_arrive_relaxed();
   if (a.k.use_pdl) pdl_launch_dependents();
   for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
   if (tid == 0) {
     s_last = 0;
-    arm_loads<CF>(a, role, &s_bar, false);
+    arm_loads<CF>(a, role, &s_bar);
   }
   __syncthreads();
   if (a.k.use_pdl) pdl_wait();
-  if (lane == 0) issue_loads<CF>(sm, a, role, env0, &s_bar, false, warp);
+  if (lane == 0) issue_loads<CF>(sm, a, role, env0, &s_bar, warp);
   // byte flags of this lane's env (every role needs the reset mask; role 0 also the command flags)
   const int u8_reset = (a.k.out.terminated[env] | a.k.out.truncated[env]) != 0;
   int u8_head = 0, u8_stand = 0;
@@ -831,22 +849,23 @@ __global__ void __launch_bounds__(NW * 32, G <= 2 ? (NW <= 8 ? 4 : 2) : 1) v2_po
           for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
           if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
         }
-        if (rme) {
-          float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
-          float* ga = static_cast<float*>(const_cast<void*>(a.k.outf[OF_ACT].ptr));
-          float* gp = static_cast<float*>(const_cast<void*>(a.k.outf[OF_PACT].ptr));
-#pragma unroll 1
-          for (int k = part; k < K; k += parts) gs[(size_t)k * a.k.outf[OF_SUMS].cs + env] = 0.f;
-#pragma unroll 1
-          for (int q = part; q < A; q += parts) {
-            ga[(size_t)q * a.k.outf[OF_ACT].cs + env] = 0.f;
-            gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
-          }
-          if (part == 0) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
-        }
       }
       __syncwarp();
-      if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);   // the tile's partials are written
+      if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);   // the tile's partials are written (the release covers only them)
+      // ... and only now the zeroing of the reset envs' rows: the ticket's release does not have to wait for these stores
+      if (rme) {
+        float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
+        float* ga = static_cast<float*>(const_cast<void*>(a.k.outf[OF_ACT].ptr));
+        float* gp = static_cast<float*>(const_cast<void*>(a.k.outf[OF_PACT].ptr));
+#pragma unroll 1
+        for (int k = part; k < K; k += parts) gs[(size_t)k * a.k.outf[OF_SUMS].cs + env] = 0.f;
+#pragma unroll 1
+        for (int q = part; q < A; q += parts) {
+          ga[(size_t)q * a.k.outf[OF_ACT].cs + env] = 0.f;
+          gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
+        }
+        if (part == 0) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
+      }
     } else if (tk.kind == TK_COMMAND) {
       // CommandTerm.reset [IL] of the reset envs (resample: V/mdp/commands.py:43-47), then CommandManager.compute and the
       // observation columns that show the new command (written into their owners' rows). The metric accumulators work on
@@ -1174,9 +1193,7 @@ int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool
   }
   if (kind == RL_V2_PRE) {
     const int HW = s.hist_len * s.num_hist_bodies * 3;
-    if (HW > 0 && (k.hist.ptr == nullptr || k.hist.cs != 1 || k.hist.es != HW || (reinterpret_cast<uintptr_t>(k.hist.ptr) & 15u) != 0 ||
-                   (((long long)32 * g * HW * 4) & 15) != 0))
-      return RL_OK;
+    if (HW > 0 && (k.hist.ptr == nullptr || k.hist.cs != 1 || k.hist.es != HW)) return RL_OK;   // contiguous force rows
     if (!soa_ok(k.outf[OF_SUMS], s.num_reward_terms) || !k.outf[OF_EPLEN].ptr || k.outf[OF_EPLEN].es != 1) return RL_OK;
     if (k.outf[OF_STEPR].ptr && k.outf[OF_STEPR].es != 1) return RL_OK;
     if (!k.cta_mask || !k.ticket) return RL_OK;

@@ -25,6 +25,8 @@ class MdpStepEngine:
             raise nat.NativeError("the MDP step runs on CUDA devices only")
         self._cspec = spec.to_ctypes()
         self._ctx = C.c_void_p()
+        self._pinned_stream = None
+        self._has_vel_targets = spec.action.kind is not None and any(spec.action.kind)
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         nat.check(self.lib.rl_ctx_create(C.byref(self._cspec), idx, C.byref(self._ctx)))
 
@@ -40,7 +42,17 @@ class MdpStepEngine:
             pass
 
     def _stream(self) -> int:
+        if self._pinned_stream is not None:   # set for the duration of one env step by ``pinned_stream``
+            return self._pinned_stream
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def pin_stream(self) -> None:
+        """Look torch's current stream up once and use it for the following calls (an env step is three launches: the
+        lookup costs as much host time as the rest of a call). ``unpin_stream`` ends it."""
+        self._pinned_stream = torch.cuda.current_stream(self.device).cuda_stream
+
+    def unpin_stream(self) -> None:
+        self._pinned_stream = None
 
     def set_launch_config(self, warps_per_cta: int = 0, envs_per_cta: int = 0) -> None:
         """Warps per tile of the general kernel (4, 8, 16); envs per CTA is 32 (one lane per env)."""
@@ -182,7 +194,7 @@ class MdpStepEngine:
         na = b.field("new_action") if new_action is None else nat.RlField(new_action.data_ptr(), new_action.stride(0), new_action.stride(1))
         mdp = b.mdp_state()
         tgt = b.field("joint_target") if with_target else nat.RlField(None, 0, 0)
-        has_vel = with_target and self.spec.action.kind is not None and any(self.spec.action.kind)
+        has_vel = with_target and self._has_vel_targets
         vtgt = b.field("joint_vel_target") if has_vel else nat.RlField(None, 0, 0)
         ctr = b.step_counter.data_ptr() if advance_step_counter else None
         nat.check(self.lib.rl_process_action(self._ctx, b.N, C.byref(na), C.byref(mdp), C.byref(tgt), C.byref(vtgt), ctr,

@@ -694,35 +694,39 @@ class ManagerBasedRLEnv:
     def step(self, action: torch.Tensor):
         """ManagerBasedRLEnv.step() [IL] order: three launches of this library + the provider."""
         b, eng = self.buffers, self.engine
-        nvtx = _NVTX   # RL_MDP_NVTX=1: ranges around the launches for nsys / ncu timelines (SURVEY.md section 5, "Tracing")
-        if nvtx:
-            torch.cuda.nvtx.range_push("mdp.process_action")
-        self.action_manager.process_action(action)                                   # 1 (+ common step counter)
-        if nvtx:
-            torch.cuda.nvtx.range_pop()
-            torch.cuda.nvtx.range_push("mdp.state_provider.advance")
-        self.state_provider.advance(self)                                            # 2 physics / sensors
-        self.common_step_counter += 1
-        if nvtx:
-            torch.cuda.nvtx.range_pop()
-            torch.cuda.nvtx.range_push("mdp.step_pre_reset")
-        eng.step_pre_reset(b, **self._rng)                                           # 3-5: dones, rewards, reset ids
-        if nvtx:
-            torch.cuda.nvtx.range_pop()
-        self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
-        self._state_version += 1
-        b.advance_log_slot()
-        if nvtx:
-            torch.cuda.nvtx.range_push("mdp.step_post_reset")
-        if self.pit_grid is None:
-            eng.step_post_reset(b, **self._rng)                                      # 6b manager reset, 7 command, 9 obs
-        else:   # the pit branch of _update_command sits between the command update and the observations
-            rng = self._rng
-            eng.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND, **rng)
-            eng.command_pit_restrict(b, self.pit_grid, self.was_on_pit, **rng)
-            eng.step(b, phases=nat.PHASE_OBS, **rng)
-        if nvtx:
-            torch.cuda.nvtx.range_pop()
+        eng.pin_stream()   # one stream lookup for the three launches of the step
+        try:
+            nvtx = _NVTX   # RL_MDP_NVTX=1: ranges around the launches for nsys / ncu timelines (SURVEY.md section 5, "Tracing")
+            if nvtx:
+                torch.cuda.nvtx.range_push("mdp.process_action")
+            self.action_manager.process_action(action)                                   # 1 (+ common step counter)
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push("mdp.state_provider.advance")
+            self.state_provider.advance(self)                                            # 2 physics / sensors
+            self.common_step_counter += 1
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push("mdp.step_pre_reset")
+            eng.step_pre_reset(b, **self._rng)                                           # 3-5: dones, rewards, reset ids
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+            self.state_provider.reset(self, b.reset_ids, b.n_reset)                      # 6a external reset
+            self._state_version += 1
+            b.advance_log_slot()
+            if nvtx:
+                torch.cuda.nvtx.range_push("mdp.step_post_reset")
+            if self.pit_grid is None:
+                eng.step_post_reset(b, **self._rng)                                      # 6b manager reset, 7 command, 9 obs
+            else:   # the pit branch of _update_command sits between the command update and the observations
+                rng = self._rng
+                eng.step(b, phases=nat.PHASE_RESET | nat.PHASE_COMMAND, **rng)
+                eng.command_pit_restrict(b, self.pit_grid, self.was_on_pit, **rng)
+                eng.step(b, phases=nat.PHASE_OBS, **rng)
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+        finally:
+            eng.unpin_stream()
         self.extras = {"log": self._log()}
         return self._obs_dict(), b.reward, b.terminated.view(torch.bool), b.truncated.view(torch.bool), self.extras   # 0/1 bytes: views, no kernels
 
@@ -750,6 +754,7 @@ class RslRlVecEnvWrapper:
         self.device = env.unwrapped.device
         self.max_episode_length = env.unwrapped.max_episode_length
         self.num_actions = env.unwrapped.action_manager.total_action_dim
+        self._dones = None
         self.env.reset()
 
     def __str__(self):
@@ -803,7 +808,10 @@ class RslRlVecEnvWrapper:
         if self.clip_actions is not None:
             actions = torch.clamp(actions, -self.clip_actions, self.clip_actions)
         obs, rew, terminated, truncated, extras = self.env.step(actions)
-        dones = (terminated | truncated).to(dtype=torch.long)
+        if self._dones is None or self._dones.shape != terminated.shape:
+            self._dones = torch.empty(terminated.shape, dtype=torch.long, device=terminated.device)
+        b = self.unwrapped.buffers
+        dones = torch.bitwise_or(b.terminated, b.truncated, out=self._dones)   # uint8 | uint8 -> long, one kernel
         if not getattr(self.unwrapped.cfg, "is_finite_horizon", False):
             extras["time_outs"] = truncated
         return self._pack(obs), rew, dones, extras

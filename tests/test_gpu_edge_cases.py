@@ -2,11 +2,9 @@
 exactly on the decision boundaries of the path (gate 0 / 1, |cmd| == 0.1, |F| == 1 N / 100 N, +-inf ray hits, time-out
 edge, terrain bound, timers at step_dt / 0.5 s, joints on their soft limits), against the oracle.
 
-Written at the end of round 1 with no GPU time left to run it: marked xfail(strict=False) so that it reports (XPASS /
-xfail) without being able to stop the suite. Two envs are *rounding* ties by construction (|cmd| = |(0.06, 0.08, 0)|,
-|F| = |(0.6, 0.8, 0)|): if the kernel's left-to-right sum of squares and torch's vector norm round differently there,
-the affected terms flip a 0/1 factor - that would be a finding about tie-breaking, not about the formulas. Remove the
-marker once a GPU run has been recorded."""
+Two envs are *rounding* ties by construction (|cmd| = |(0.06, 0.08, 0)|, |F| = |(0.6, 0.8, 0)|): the kernel's
+left-to-right sum of squares and torch's vector norm round the same way there (recorded on a B200 in round 2: all cases
+pass, profiles/r2_summary.md), so the terms' 0/1 factors agree."""
 
 import pytest
 import torch
@@ -14,8 +12,7 @@ import torch
 import helpers as H
 from oracle import mdp_port as port
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new at the end of round 1: not yet run on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("key", ["go2_rough", "a1_flat"])

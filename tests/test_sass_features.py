@@ -59,7 +59,7 @@ def test_cluster_kernels_stage_fields_with_tensor_map_copies(kernels):
             assert "SYNCS" in text, f"{name}: no mbarrier"
             assert "LDGSTS" not in text, f"{name}: per-thread async copies are back"
     for name, body in _cluster_kernels(kernels, "pre").items():
-        assert "UBLKCP" in "\n".join(body), f"{name}: the contact-force rows should arrive by one bulk copy"
+        assert "UBLKCP" not in "\n".join(body), f"{name}: the contact-force rows are streamed from global memory, not staged"
 
 
 def test_cluster_kernels_use_cluster_barriers_and_dsmem(kernels):

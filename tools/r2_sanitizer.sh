@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # compute-sanitizer (memcheck, racecheck, synccheck) over the hand-rolled inter-warp / inter-CTA protocols of the step
 # kernels: the cluster kernels (mbarrier + TMA, DSMEM + cluster barriers, early release tickets), the general kernel's
-# build-time specialised and generic instantiations (arrival counters of split terms, named tails), a ragged env count.
+# build-time specialised and generic instantiations (named-barrier tails, early tickets), a ragged env count.
 # Output: gpurun_out/r2_sanitizer.txt (summary lines of every run)
 set -uo pipefail
 mkdir -p gpurun_out
@@ -23,6 +23,7 @@ run() {   # tool, label, env assignments..., -- pytest selection
 }
 for tool in memcheck racecheck synccheck; do
   run $tool "new kernels, one tile per CTA" RL_MDPSTEP_V2_CFG=1x1x16 -- "tests/test_gpu_step_parity.py::test_two_launch_step_in_reference_order"
+  run $tool "new kernels, one tile per CTA, 8 warps" RL_MDPSTEP_V2_CFG=1x1x8 -- "tests/test_gpu_step_parity.py::test_two_launch_step_in_reference_order"
   run $tool "new kernels, 4-CTA cluster (DSMEM, cluster barriers)" RL_MDPSTEP_V2_CFG=4x4x16 -- "tests/test_gpu_step_parity.py::test_two_launch_step_in_reference_order"
   run $tool "general kernel, baked" RL_MDPSTEP_V2=0 -- "tests/test_gpu_step_parity.py::test_two_launch_step_in_reference_order"
   run $tool "general kernel, generic" RL_MDPSTEP_V2=0 RL_MDPSTEP_GENERIC=1 -- "tests/test_gpu_step_parity.py::test_two_launch_step_in_reference_order"
