@@ -34,7 +34,15 @@
 #if RL_V2_UNROLL
 #define RL_TERM_LOOP _Pragma("unroll")   // see csrc/mdp_terms.cuh: the term loops unroll against the baked spec
 #endif
+#ifndef RL_V2_FEW_UNROLL
+#define RL_V2_FEW_UNROLL 1   // the short loops (feet, contact-mask bodies) unroll: they were the critical path of a tile
+#endif
+#if RL_V2_FEW_UNROLL
+#define RL_FEW_LOOP _Pragma("unroll")
+#endif
 #include "mdp_ctx.h"
+
+#include <algorithm>
 
 #include <cuda.h>
 
@@ -49,10 +57,16 @@
 #define V2_STAMP(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && lane == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 #define V2_STAMP_T0(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && tid == 0) a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 #define V2_GTIME(slot) do { if (a.k.dbg > reinterpret_cast<long long*>(2) && tid == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); a.k.dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
+#define V2_DBG_ROW (a.k.dbg > reinterpret_cast<long long*>(2) ? a.k.dbg + (size_t)blockIdx.x * 64 : nullptr)
+#define V2_GTIME_L(k_, slot) do { if ((k_).dbg > reinterpret_cast<long long*>(2) && (threadIdx.x & 31) == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); (k_).dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
+#define V2_GTIME_K(k_, slot) do { if ((k_).dbg > reinterpret_cast<long long*>(2) && threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); (k_).dbg[(size_t)blockIdx.x * 64 + (slot)] = (long long)g_; } } while (0)
 #else
 #define V2_STAMP(slot) do { } while (0)
 #define V2_STAMP_T0(slot) do { } while (0)
 #define V2_GTIME(slot) do { } while (0)
+#define V2_DBG_ROW nullptr
+#define V2_GTIME_L(k_, slot) do { } while (0)
+#define V2_GTIME_K(k_, slot) do { } while (0)
 #endif
 
 namespace {
@@ -109,6 +123,11 @@ __host__ __device__ constexpr bool v2_spec_ok(const RlStepSpec& s) {
   return true;
 }
 
+constexpr int kLogStageWords = 4096;   // 16 KB: 128 partial rows of 32 floats (64 rows of 64 floats when a spec logs more than 32 quantities)
+__host__ __device__ constexpr int log_row_floats(const RlStepSpec& s) {
+  return (s.num_reward_terms + RL_MAX_DONE_TERMS + 2) <= 32 ? 32 : RL_LOG_STRIDE;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Record layout of a CTA: 32 G envs; the term functions address it through the same Layout members as the general
 // kernel (SoA word w of env e at sm[w*E + e]).
@@ -145,13 +164,18 @@ __host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const i
   L.cj = off; off = align_up(off + 5 * J, 32);
   if (kind == RL_V2_PRE) {
     // the contact-force rows are NOT staged: the norm prepass streams them from global memory; per warp a scratch row of
-    // hist_len * bodies squared norms (hist = scratch base, hist_pitch = words per warp)
-    L.hist_pitch = align_up(s.hist_len * s.num_hist_bodies, 32);
+    // envs-per-warp * hist_len * bodies squared norms (hist = scratch base, hist_pitch = words per warp)
+    L.hist_pitch = align_up((E / NW) * s.hist_len * s.num_hist_bodies, 32);   // all of a warp's envs at once
     L.hist = off; off = align_up(off + NW * L.hist_pitch, 32);
   } else {
     L.obs_pitch0 = odd_pitch(env_cols_of(s.obs[0])); L.obs_pitch1 = odd_pitch(env_cols_of(s.obs[1]));
     L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
     L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
+    // staging area of the logging reduction (one tile per CTA): kLogStageWords words of partial rows, bulk-copied by the
+    // LOG warp that finishes the launch (or its class of tiles) WHILE the record is alive (hist = base, hist_pitch =
+    // floats of a row; both members are otherwise unused in this launch)
+    L.hist_pitch = log_row_floats(s);
+    if (E == 32) { L.hist = off; off = align_up(off + kLogStageWords, 32); }
   }
   L.total_words = off;
   return L;
@@ -202,7 +226,8 @@ __host__ __device__ constexpr Sched2 make_schedule_v2(const RlStepSpec& s, int k
   sc.obs_owner[1] = C > 2 ? 2 : 0;
   if (kind == RL_V2_PRE) {
     bool any_hist = dones_use_hist(s);
-    sc.t[n] = Task{TK_DONES, 0, 0, 0, 0, 0, 0, 0}; cost[n] = 120; lo_bin[n] = 0; hi_bin[n] = W; ++n;
+    // the termination task: not in bin 0 (the final sum's warp) when there is a choice - its look-back overlaps the final sum
+    sc.t[n] = Task{TK_DONES, 0, 0, 0, 0, 0, 0, 0}; cost[n] = 120; lo_bin[n] = W > 1 ? 1 : 0; hi_bin[n] = W; ++n;
     for (int k = 0; k < s.num_reward_terms; ++k) {
       const RlRewardTerm& t = s.rewards[k];
       if (t.weight == 0.f) continue;
@@ -370,10 +395,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 struct alignas(64) V2Args {
   KArgs k;                  // the parameter block of the general kernel (pointers, strides, phases, random streams)
   uint32_t role_bytes[8];   // bytes the tensor-map copies of one CTA of role r deliver
-  uint32_t role_mask[8];    // fields role r stages (what its tasks read)
+  uint8_t role_n[8];                  // fields role r stages (what its tasks read) ...
+  uint8_t role_field[8][IF_COUNT];    // ... as a list (a bit mask walked with __fns cost ~100 instructions per copy, 7-8 % of a launch)
   int32_t field_word[IF_COUNT];
   const char* prefetch_rays;   // PRE: the ray-hit rows the post-reset launch will stream (L2 prefetch), or NULL
   uint32_t prefetch_row_bytes;
+  // launch-wide results without a launch-wide tail (scratch owned by the context, see RlV2State):
+  unsigned long long* scan_state;   // PRE: one status word per tile (epoch | flag | reset count or prefix): decoupled look-back
+  unsigned int* scan_ctl;           // [0] epoch of the look-back; [16 + c] ticket of logging class c; [32] ticket of the classes
+  float* log_class;                 // POST: [16][RL_LOG_STRIDE] partial sums of the 16 strided classes of tiles
   alignas(64) CUtensorMap tm[IF_COUNT];
 };
 
@@ -398,7 +428,7 @@ struct Cfg2 {
 // all tasks of one bin, in schedule order, behind ONE per-env context (members no task of the bin reads fold away);
 // `fin` closes the bin's straight-line code (every warp runs exactly one bin, also an empty one)
 template <class B, class CF, int BIN, class F, class FIN>
-__device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f, FIN&& fin) {
+__device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f, FIN&& fin, long long* dbg_row) {
   constexpr Layout L = CF::L;
   const EnvCtx c = make_ctx(sm, L, e);
   static_for(std::make_integer_sequence<int, CF::n_tasks>{}, [&](auto ic) {
@@ -408,47 +438,55 @@ __device__ __forceinline__ void bin_tasks(const float* sm, const int e, F&& f, F
       static constexpr RlRewardTerm rt = B::spec.rewards[tk.kind == TK_REWARD ? tk.a : 0];
       static constexpr RlObsTerm ot = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].terms[tk.kind == TK_OBS ? tk.b : 0];
       constexpr bool corrupt = B::spec.obs[tk.kind == TK_OBS ? tk.a : 0].enable_corruption != 0;
+#if RL_V2_STAMPS
+      const long long t0_ = clock64();
+#endif
       f(ic, tk, rt, ot, corrupt, c);
+#if RL_V2_STAMPS
+      if (dbg_row != nullptr && (threadIdx.x & 31) == 0 && i < 32) dbg_row[32 + i] = clock64() - t0_;   // cycles of task i
+#endif
     }
   });
+  (void)dbg_row;
   fin();
 }
 template <class B, class CF, int LO, int HI, class F, class FIN>
-__device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, const int e, F&& f, FIN&& fin) {
+__device__ __forceinline__ void dispatch_bin(const int bin, const float* sm, const int e, F&& f, FIN&& fin, long long* dbg_row = nullptr) {
   if constexpr (HI - LO == 1) {
-    bin_tasks<B, CF, LO>(sm, e, f, fin);
+    bin_tasks<B, CF, LO>(sm, e, f, fin, dbg_row);
   } else {
     constexpr int MID = (LO + HI) / 2;
-    if (bin < MID) dispatch_bin<B, CF, LO, MID>(bin, sm, e, f, fin); else dispatch_bin<B, CF, MID, HI>(bin, sm, e, f, fin);
+    if (bin < MID) dispatch_bin<B, CF, LO, MID>(bin, sm, e, f, fin, dbg_row); else dispatch_bin<B, CF, MID, HI>(bin, sm, e, f, fin, dbg_row);
   }
 }
 
-// The load every CTA starts with: one instruction per field. Thread 0 arms the mbarrier with the byte count of the whole
-// record (arm_loads, followed by a CTA barrier); then lane 0 of EVERY warp issues its share of the copies (issue_loads):
-// the tensor maps live in the kernel's parameter bank, the first touch of each is a ~300-cycle miss, and one thread
+// The load every CTA starts with: one instruction per field, issued by lane 0 of EVERY warp (issue_loads): the tensor maps live in the kernel's parameter bank, the first touch of each is a ~300-cycle miss, and one thread
 // issuing all ~20 of them in a row serialised those misses into 2.9 us of a 4096-env launch (measured: profiles/
 // r2_summary.md). Spread over the warps they overlap.
-template <class CF>
-__device__ __forceinline__ void arm_loads(const V2Args& a, const uint32_t role, uint64_t* bar) {
+// Thread 0 initialises the mbarrier (one arrival); after the CTA barrier that publishes it, lane 0 of warp 0 makes that
+// arrival with the byte count of the record (arrive.expect_tx) and lane 0 of every warp issues its share of the copies.
+// A copy of another warp may complete before the expect_tx is performed - the transaction count may run negative; the
+// phase cannot complete before the one pending arrival is made. (init and expect_tx on either side of the CTA barrier
+// also keeps compute-sanitizer racecheck quiet about the two accesses of thread 0.)
+__device__ __forceinline__ void init_load_barrier(uint64_t* bar) {
   mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  mbar_expect_tx(bar, a.role_bytes[role]);
 }
 template <class CF>
 __device__ __forceinline__ void issue_loads(float* sm, const V2Args& a, const uint32_t role, const int env0, uint64_t* bar, const int warp) {
-  const uint32_t m = a.role_mask[role];
-  const int n = __popc(m);
+  if (warp == 0) mbar_expect_tx(bar, a.role_bytes[role]);
+  const int n = a.role_n[role];
 #pragma unroll 1
   for (int i = warp; i < n; i += CF::NT / 32) {
-    const int f = (int)__fns(m, 0u, i + 1);   // the (i+1)-th staged field
+    const int f = a.role_field[role][i];
     tma_load_2d(sm + a.field_word[f] * CF::E, &a.tm[f], env0, 0, bar);
   }
 }
 
 // Contact-force norm prepass: max over the history of |F_b| for every body of every env of the CTA, ONCE, straight from
 // global memory. A warp takes an env at a time with lanes = (history sample, body) pairs: its 3 * T * B floats are one
-// contiguous, coalesced row; the squared norms go through a per-warp scratch row, lanes = bodies take the max over the
-// history (same order as hist_max_norm) and ONE IEEE sqrt. All loads of the warp's envs are in flight before the first
+// contiguous, coalesced row; the squared norms go through a per-warp scratch row, lanes = (env, body) items take the max
+// over the history (same order as hist_max_norm) and ONE IEEE sqrt. All loads of the warp's envs are in flight before the first
 // use, and the whole prepass runs while the tensor-map copies of the record are still in flight. Nothing of the force
 // history is staged in shared memory (round-2 first cut: a 22 KB bulk copy per tile, half of the record).
 template <class CF>
@@ -474,68 +512,267 @@ __device__ __forceinline__ void norm_prepass(float* sm, const float* __restrict_
   }
   float* scr = sm + L.hist + warp * L.hist_pitch;
 #pragma unroll
-  for (int i = 0; i < EPW; ++i) {
-    const int ee = warp + i * NWARPS;
+  for (int i = 0; i < EPW; ++i)
 #pragma unroll
     for (int q = 0; q < PASSES; ++q)
-      if (q * 32 + lane < TB) scr[q * 32 + lane] = ss[i][q];
-    __syncwarp();
-    for (int b = lane; b < Bh; b += 32) {
-      float m2 = scr[b];
+      if (q * 32 + lane < TB) scr[i * TB + q * 32 + lane] = ss[i][q];
+  __syncwarp();
+  // lanes = (env of the warp, body) items: every lane busy (bodies alone would leave 19 of 32 lanes idle on a quadruped)
+#pragma unroll 1
+  for (int it = lane; it < EPW * Bh; it += 32) {
+    const int i = it / Bh, b = it - i * Bh;
+    const float* sc = scr + i * TB + b;
+    float m2 = sc[0];
 #pragma unroll
-      for (int t = 1; t < T; ++t) m2 = fmaxf(m2, scr[t * Bh + b]);
-      sm[L.hnorm + b * CF::E + ee] = (m2 == 0.f) ? 0.f : sqrtf(m2);
-    }
-    __syncwarp();
+    for (int t = 1; t < T; ++t) m2 = fmaxf(m2, sc[t * Bh]);
+    const bool z = (m2 == 0.f);                   // a body without contact: keep the warp off sqrt's special-operand path
+    const float r = sqrtf(z ? 1.f : m2);
+    sm[L.hnorm + b * CF::E + (warp + i * NWARPS)] = z ? 0.f : r;
   }
 }
 
-// reset_buf.nonzero() [IL]: ascending reset ids from one 32-bit done mask per tile (runs in the ONE CTA whose ticket
-// was the last of the launch; same result as the general kernel's tail)
-template <int NW>
-__device__ __noinline__ void compact_reset_ids(const KArgs& a, const int n_tiles, int* s_cnt, const int tid) {
-  constexpr int kWarps2 = NW, kThreads2 = NW * 32;
-  const int warp = tid >> 5, e = tid & 31;
-  int run = 0;
-#pragma unroll 1
-  for (int base = 0; base < n_tiles; base += kThreads2) {
-    const int g = base + tid;
-    unsigned m = (g < n_tiles) ? __ldcg(a.cta_mask + g) : 0u;
-    const int cnt = __popc(m);
-    int incl = cnt;
+// reset_buf.nonzero() [IL]: ascending reset ids WITHOUT a launch-wide tail. Every tile publishes the number of its reset
+// envs as soon as its termination terms are evaluated (one warp, early in the tile's life) and gets its offset into the
+// id list by a decoupled look-back over the tiles in front of it (Merrill & Garland's single-pass scan): a status word is
+// (epoch << 32) | (flag << 24) | value with flag 1 = the tile's own count, 2 = inclusive prefix. The whole payload is in
+// the one 64-bit word, so relaxed loads and stores are enough. The epoch (a word in device memory, bumped by the LAST
+// tile once its own look-back is complete - by then every tile has published, i.e. has read the epoch) makes the words
+// of earlier launches invalid without clearing them, also when a captured graph replays the same arguments.
+// Forward progress: a tile waits only for tiles with a smaller block index, which the hardware dispatches first (the
+// assumption of every single-pass scan); the spin is bounded and traps instead of hanging.
+// (First cut of this round: the CTA that drew the last ticket compacted the ids of the whole launch with every other SM
+// idle - 1.6 us of a 9.5 us launch at 4096 envs, 5.4 us at 65536; profiles/r2_summary.md.)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Two halves, both run by the warp of the tile's termination task: publish (as soon as the terms are evaluated) and
+// resolve (after the tile's task barrier, next to the final sum: by then the tiles in front have published long ago, at
+// 4096 envs - every tile in lock step - as well as in the later waves of a large launch, so the resolve is one round
+// trip that overlaps the final sum instead of a spin inside the longest task of the tile).
+__device__ __forceinline__ void lookback_publish(unsigned long long* st, const unsigned epoch, const int gt, const unsigned cnt, const int lane) {
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  if (lane == 0) st_relaxed_u64(st + gt, tag | ((gt == 0 ? 2ull : 1ull) << 24) | cnt);
+}
+// one warp; returns the number of reset envs in the tiles in front of tile gt (uniform over the warp)
+__device__ __noinline__ unsigned lookback_resolve(unsigned long long* st, const unsigned epoch, const int gt, const unsigned cnt, const int lane) {
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  if (gt == 0) return 0u;
+  unsigned excl = 0;
+  int idx = gt - 1;
+  constexpr int kWin = 4;   // windows of 32 tiles read per round: one L2 round trip covers the 128 tiles of a 4096-env launch
+  for (;;) {
+    unsigned long long w[kWin];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (e >= d) incl += y; }
-    if (e == 31) s_cnt[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int wt = (e < kWarps2) ? s_cnt[e] : 0, wi = wt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wi, d); if (e >= d) wi += y; }
-      if (e < kWarps2) s_cnt[e] = wi - wt;
-      if (e == 31) s_cnt[32] = wi;
+    for (int k = 0; k < kWin; ++k) {
+      const int j = idx - 32 * k - lane;   // lane 0 of window 0 looks at the nearest tile
+      w[k] = (j >= 0) ? ld_relaxed_u64(st + j) : (tag | (2ull << 24));   // in front of tile 0: prefix 0
     }
-    __syncthreads();
-    int pos = run + s_cnt[warp] + incl - cnt;
-    if (a.out.reset_ids)
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        a.out.reset_ids[pos++] = g * kE + b;
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      if (done) break;
+      const int j = idx - 32 * k - lane;
+      int tries = 0;
+      for (;;) {
+        const bool ok = ((unsigned)(w[k] >> 32) == epoch) && ((((unsigned)w[k]) >> 24) & 3u) != 0u;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (++tries > (1 << 22)) __trap();   // a predecessor never published: fail loudly instead of hanging
+        w[k] = (j >= 0) ? ld_relaxed_u64(st + j) : (tag | (2ull << 24));
       }
-    run += s_cnt[32];
-    __syncthreads();
+      const unsigned is_p = __ballot_sync(0xffffffffu, ((((unsigned)w[k]) >> 24) & 3u) == 2u);
+      unsigned v = ((unsigned)w[k]) & 0xffffffu;
+      if (is_p != 0u && lane > __ffs(is_p) - 1) v = 0u;   // nothing beyond the nearest inclusive prefix
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      excl += v;
+      done = (is_p != 0u);
+    }
+    if (done) break;
+    idx -= 32 * kWin;
   }
-  if (tid == 0) {
-    if (a.out.n_reset) *a.out.n_reset = run;
-    *a.ticket = 0u;
+  if (lane == 0) st_relaxed_u64(st + gt, tag | (2ull << 24) | (excl + cnt));
+  return excl;
+}
+
+// Logging means of the reset (extras["log"] [IL]) WITHOUT a launch-wide tail, in the general kernel's order of additions
+// (16 strided partial sums over the tiles - class c = tiles c, c + 16, ... - then their sum in class order: bit-identical).
+// A tile's partial row lives class-major: row (tile % 16) * ceil(tiles / 16) + tile / 16, so that the rows of a class are
+// one contiguous block. Every memory round trip at the end of a launch is expensive (0.6 us cold at 4096 envs, 2 - 3 us
+// while 65536 envs' result rows drain), so the reduction is built around ONE bulk copy:
+//   * up to 128 tiles (4096 envs): the LOG warp that makes the last arrival of the LAUNCH (an acq_rel atomic: no separate
+//     acquiring load) bulk-copies all rows into the staging area of its CTA - while the other warps of the CTA carry on
+//     with their tasks - adds the 16 chains from shared memory and writes the means;
+//   * beyond: the warp that makes the last arrival of its CLASS does the same for the class's rows, publishes the class
+//     sum and arrives for the class; the last of those 16 arrivals adds the class sums.
+// (First cuts of this round, profiles/r2_summary.md: one CTA after the last tile, one L2 round trip per 16 tiles - 2 us of
+// a 9.7 us launch at 4096 envs, 14 - 30 us of 62 at 65536; then class finishers with register-staged loads - 5 round trips.)
+__device__ __forceinline__ unsigned ticket_arrive_acq_rel(unsigned int* ticket) {
+  unsigned prev;
+  asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket) : "memory");
+  return prev;
+}
+// lanes = quantities; the means from the 16 class sums p[w] (register) - shared tail of both forms
+template <int K>
+__device__ __forceinline__ void log_write_means(const KArgs& k, const int q, float tot, const int n_reset_total) {
+  const RlResetLog& lg = k.out.reset_log;
+  const float cnt = (float)max(n_reset_total, 1);
+  if (n_reset_total == 0) tot = 0.f;
+  if (q < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[q] = tot / cnt; }
+  else if (q < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[q - K] = tot; }
+  else if (lg.metric_mean) lg.metric_mean[q - K - RL_MAX_DONE_TERMS] = tot / cnt;
+}
+// one warp: bulk copy of `rows` partial rows starting at row `row0` into the staging area, complete on return
+template <class CF>
+__device__ __forceinline__ void log_stage_rows(const V2Args& a, float* buf, uint64_t* bar, uint32_t& phase, const int row0, const int rows, const int lane) {
+  constexpr int ROW = CF::L.hist_pitch;
+  if (lane == 0) {
+    const uint32_t bytes = (uint32_t)(rows * ROW * 4);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the staging area before the copy overwrites it
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(buf, a.k.log_partials + (size_t)row0 * ROW, bytes, bar);
   }
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+}
+template <class CF>
+__device__ __noinline__ void log_finish_launch(const V2Args& a, float* sm, uint64_t* bar, const int n_tiles, const int lane) {
+  constexpr int K = CF::S.num_reward_terms, NQ = K + RL_MAX_DONE_TERMS + 2, QI = (NQ + 31) / 32, ROW = CF::L.hist_pitch;
+  float* buf = sm + CF::L.hist;
+  const int cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
+  const int n_reset_total = a.k.out.n_reset ? __ldcg(a.k.out.n_reset) : 0;   // written by the pre-reset launch
+  uint32_t phase = 0;
+  V2_GTIME_L(a.k, 56);
+  log_stage_rows<CF>(a, buf, bar, phase, 0, kLogWarps * cls_cap, lane);
+  V2_GTIME_L(a.k, 57);
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+    const int q = lane + qi * 32;
+    if (q < NQ) {
+      float tot = 0.f;
+#pragma unroll 1
+      for (int w0 = 0; w0 < kLogWarps; w0 += 8) {   // 8 independent chains at a time, each in tile order
+        float part[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) part[w] = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < cls_cap; ++i)
+#pragma unroll
+          for (int w = 0; w < 8; ++w)
+            if (w0 + w + kLogWarps * i < n_tiles) part[w] += buf[((w0 + w) * cls_cap + i) * ROW + q];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += part[w];   // class order
+      }
+      log_write_means<K>(a.k, q, tot, n_reset_total);
+    }
+  }
+  if (lane == 0) a.scan_ctl[32] = 0u;   // every arrival of this launch has been made
+  V2_GTIME_L(a.k, 58);
+}
+template <class CF>
+__device__ __noinline__ void log_finish_class(const V2Args& a, float* sm, uint64_t* bar, const int vw, const int n_tiles, const int lane) {
+  constexpr int K = CF::S.num_reward_terms, NQ = K + RL_MAX_DONE_TERMS + 2, QI = (NQ + 31) / 32, ROW = CF::L.hist_pitch;
+  constexpr bool kStaged = (CF::E == 32);        // one tile per CTA: the staging area exists
+  constexpr int CHR = kLogStageWords / ROW;      // rows per bulk copy
+  float* buf = sm + CF::L.hist;
+  unsigned int* ctl = a.scan_ctl;
+  const int cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
+  const int class_tiles = (n_tiles - vw + kLogWarps - 1) / kLogWarps;
+  float part[QI];
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) part[qi] = 0.f;
+  if constexpr (kStaged) {
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < class_tiles; i0 += CHR) {
+      const int rows = class_tiles - i0 < CHR ? class_tiles - i0 : CHR;
+      if (i0 > 0) __syncwarp();   // every lane is done with the previous chunk
+      log_stage_rows<CF>(a, buf, bar, phase, vw * cls_cap + i0, rows, lane);
+#pragma unroll
+      for (int qi = 0; qi < QI; ++qi) {
+        const int q = lane + qi * 32;
+        if (q < NQ)
+#pragma unroll 4
+          for (int i = 0; i < rows; ++i) part[qi] += buf[i * ROW + q];   // tile order
+      }
+    }
+  } else {   // several tiles per CTA (cluster configurations): rows through registers, 8 loads in flight per round
+#pragma unroll
+    for (int qi = 0; qi < QI; ++qi) {
+      const int q = lane + qi * 32;
+      if (q < NQ) {
+#pragma unroll 1
+        for (int i0 = 0; i0 < class_tiles; i0 += 8) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (i0 + j < class_tiles) ? __ldcg(a.k.log_partials + (size_t)(vw * cls_cap + i0 + j) * ROW + q) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (i0 + j < class_tiles) part[qi] += x[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+    const int q = lane + qi * 32;
+    if (q < NQ) a.log_class[vw * RL_LOG_STRIDE + q] = part[qi];
+  }
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0) prev = ticket_arrive_acq_rel(ctl + 32);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  const int n_classes = n_tiles < kLogWarps ? n_tiles : kLogWarps;
+  if (prev != (unsigned)(n_classes - 1)) return;
+  const int n_reset_total = a.k.out.n_reset ? __ldcg(a.k.out.n_reset) : 0;   // written by the pre-reset launch
+#pragma unroll
+  for (int qi = 0; qi < QI; ++qi) {
+    const int q = lane + qi * 32;
+    if (q < NQ) {
+      float tot = 0.f;
+#pragma unroll 1
+      for (int w0 = 0; w0 < kLogWarps; w0 += 8) {
+        float p[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) p[w] = (w0 + w < n_classes) ? __ldcg(a.log_class + (w0 + w) * RL_LOG_STRIDE + q) : 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += p[w];   // class order
+      }
+      log_write_means<K>(a.k, q, tot, n_reset_total);
+    }
+  }
+  // every arrival of this launch has been made: the tickets start the next launch at zero
+  if (lane < kLogWarps) ctl[16 + lane] = 0u;
+  if (lane == 0) ctl[32] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // PRE: TerminationManager.compute + RewardManager.compute [IL] + reset_buf.nonzero()
 // ---------------------------------------------------------------------------------------------------
+// resident CTAs per SM the register allocation aims at (8 / 16 warps per CTA)
+#ifndef RL_V2_PRE_MINB8
+#define RL_V2_PRE_MINB8 5
+#endif
+#ifndef RL_V2_PRE_MINB16
+#define RL_V2_PRE_MINB16 2
+#endif
+#ifndef RL_V2_POST_MINB8
+#define RL_V2_POST_MINB8 6
+#endif
+#ifndef RL_V2_POST_MINB16
+#define RL_V2_POST_MINB16 3
+#endif
 template <class B, int C, int G, int NW>
-__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? 5 : 2))) v2_pre_kernel(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? RL_V2_PRE_MINB8 : RL_V2_PRE_MINB16))) v2_pre_kernel(const __grid_constant__ V2Args a) {
   using CF = Cfg2<B, RL_V2_PRE, C, G, NW>;
   constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
@@ -544,8 +781,6 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   constexpr bool CN = true;   // HIST_MAX_NORM reads the cached norms
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_last;
-  __shared__ int s_cnt[40];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = warp / W, slot = warp - tile * W;
   const int e = tile * 32 + lane;
@@ -560,10 +795,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   V2_GTIME(0); V2_STAMP_T0(1);
   if (C > 1) cluster_arrive_relaxed();   // "every CTA of the cluster runs": waited for in front of the first DSMEM store
   if (a.k.use_pdl) pdl_launch_dependents();   // the successor's prologue may overlap this kernel
-  if (tid == 0) {
-    s_last = 0;
-    arm_loads<CF>(a, role, &s_bar);
-  }
+  if (tid == 0) init_load_barrier(&s_bar);
   V2_STAMP_T0(9);
   __syncthreads();                            // the armed mbarrier is visible to every issuing warp
   V2_STAMP_T0(10);
@@ -595,12 +827,13 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
 
   float* const termv0 = C > 1 ? map_to_rank(sm + L.termv, 0u) : sm + L.termv;   // role 0's term values
   const FieldD f_sums = a.k.outf[OF_SUMS], f_stepr = a.k.outf[OF_STEPR];
-  unsigned early_prev = 0xffffffffu;
   // In a cluster the weighted value goes to role 0 first (DSMEM), the CTA's arrival at the cluster barrier follows, and the
   // global result rows leave AFTER it: an arrive.release waits for the thread's earlier stores, global ones included.
   constexpr int kPend = 6;
   float p_sum[kPend], p_step[kPend];
   int p_k[kPend], np = 0;
+  unsigned lb_mask = 0, lb_epoch = 0;   // the termination task's warp: done mask of the tile, epoch of the look-back ...
+  int lb_gt = -1;                       // ... and the tile's index (-1: not that warp)
   dispatch_bin<B, CF, 0, CF::BINS>((int)role * W + slot, sm, e,
       [&](auto, const Task& tk, const RlRewardTerm& rt, const RlObsTerm&, const bool, const EnvCtx& c) __attribute__((always_inline)) {
     if (tk.kind == TK_REWARD) {
@@ -619,6 +852,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
       }
     } else if (tk.kind == TK_DONES) {
       // TerminationManager.compute [IL]: bits | terminated << 8 | time_out << 9
+      const unsigned scan_epoch = ld_relaxed_u32(a.scan_ctl);   // in flight while the terms are evaluated
       const int eplen_now = __float_as_int(SMF(L.eplen, 0)) + 1;
       static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = eplen_now;
       uint32_t bits = 0, term = 0, trunc = 0;
@@ -629,7 +863,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
         } else if (t.type == RL_DONE_TERRAIN_OUT_OF_BOUNDS) {
           fired = (t.p[2] != 0.f) && ((fabsf(c.pos.x) > t.p[0]) || (fabsf(c.pos.y) > t.p[1]));
         } else if (t.type == RL_DONE_ILLEGAL_CONTACT) {
-          _Pragma("unroll 1")
+          RL_FEW_LOOP
           for (int b = 0; b < S.num_hist_bodies; ++b)
             if (((t.body_mask >> b) & 1ull) && (SMF(L.hnorm, b) > t.p[0])) fired = 1;
         }
@@ -639,12 +873,11 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
       if (a.k.out.done_bits) a.k.out.done_bits[env] = (uint8_t)bits;
       if (a.k.out.terminated) a.k.out.terminated[env] = (uint8_t)term;
       if (a.k.out.truncated) a.k.out.truncated[env] = (uint8_t)trunc;
-      // the tile's done mask and its ticket, long before the tail looks at the answer
-      const unsigned m = __ballot_sync(0xffffffffu, (term | trunc) != 0);
-      if (lane == 0) {
-        a.k.cta_mask[cluster_id * G + tile] = m;
-        early_prev = ticket_arrive_release(a.k.ticket);
-      }
+      // reset_buf.nonzero() [IL]: this tile's ids at its offset into the ascending list (decoupled look-back, no tail)
+      lb_mask = __ballot_sync(0xffffffffu, (term | trunc) != 0);
+      lb_gt = cluster_id * G + tile;
+      lb_epoch = scan_epoch;
+      lookback_publish(a.scan_state, scan_epoch, lb_gt, __popc(lb_mask), lane);   // resolved after the task barrier
     }
   }, [&]() __attribute__((always_inline)) {
     if (C > 1) cluster_arrive_release();   // this warp's term values are in role 0's record
@@ -654,11 +887,10 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
         static_cast<float*>(const_cast<void*>(f_sums.ptr))[(size_t)p_k[i] * f_sums.cs + env] = p_sum[i];
         if (f_stepr.ptr) static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)p_k[i] * f_stepr.cs + env] = p_step[i];
       }
-  });
+  }, V2_DBG_ROW);
   V2_STAMP(16 + warp);
-  if (lane == 0 && early_prev == (unsigned)(a.k.vgrid - 1)) s_last = 1;   // this tile's ticket was the last of the launch
   if (C > 1) { if (role != 0) return; cluster_wait_acquire(); }
-  __syncthreads();   // the term values of role 0's own warps, the termination flags, s_last
+  __syncthreads();   // the term values of role 0's own warps, the termination flags
   V2_STAMP_T0(5);
 
   // ---- final sum: one warp per tile adds the weighted values up in manager order (is_terminated is finished here) ----
@@ -688,12 +920,17 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
       for (uint64_t m = a.k.rw_zero; m != 0; m &= m - 1)
         static_cast<float*>(const_cast<void*>(f_stepr.ptr))[(size_t)(__ffsll((long long)m) - 1) * f_stepr.cs + env] = 0.f;
   }
-  V2_STAMP_T0(6); V2_GTIME(7);
-  if (s_last) {   // CTA-uniform: ordered compaction of the reset ids by the CTA that arrived last
-    __threadfence();
-    compact_reset_ids<NW>(a.k, a.k.vgrid, s_cnt, tid);
-    V2_GTIME(8);
+  // ---- reset_buf.nonzero() [IL]: the tile's ids at its offset into the ascending list (decoupled look-back, no tail) ----
+  if (lb_gt >= 0) {   // warp-uniform: the termination task's warp (not the final sum's when the tile has more than one warp)
+    const unsigned cnt = __popc(lb_mask);
+    const unsigned excl = lookback_resolve(a.scan_state, lb_epoch, lb_gt, cnt, lane);
+    if (((lb_mask >> lane) & 1u) && a.k.out.reset_ids) a.k.out.reset_ids[excl + __popc(lb_mask & ((1u << lane) - 1u))] = (int32_t)env;
+    if (lb_gt == a.k.vgrid - 1 && lane == 0) {   // the last tile: every tile has published (and read the epoch) by now
+      if (a.k.out.n_reset) *a.k.out.n_reset = (int32_t)(excl + cnt);
+      a.scan_ctl[0] = lb_epoch + 1u;
+    }
   }
+  V2_STAMP_T0(6); V2_GTIME(7);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -701,7 +938,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
 // ObservationManager.compute [IL] for all envs
 // ---------------------------------------------------------------------------------------------------
 template <class B, int C, int G, int NW>
-__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? 6 : 3))) v2_post_kernel(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? RL_V2_POST_MINB8 : RL_V2_POST_MINB16))) v2_post_kernel(const __grid_constant__ V2Args a) {
   using CF = Cfg2<B, RL_V2_POST, C, G, NW>;
   constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
@@ -709,7 +946,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms, A = S.n_actions;
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_last;
+  __shared__ __align__(8) uint64_t s_lbar;   // bulk copies of the logging reduction (log_stage_rows)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = warp / W, slot = warp - tile * W;
   const int e = tile * 32 + lane;
@@ -724,10 +961,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   if (C > 1) cluster_arrive_relaxed();
   if (a.k.use_pdl) pdl_launch_dependents();
   for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
-  if (tid == 0) {
-    s_last = 0;
-    arm_loads<CF>(a, role, &s_bar);
-  }
+  if (tid == 0) { mbar_init(&s_lbar, 1); init_load_barrier(&s_bar); }   // s_lbar: the logging reduction's bulk copies (before the same fence + CTA barrier)
   __syncthreads();
   if (a.k.use_pdl) pdl_wait();
   if (lane == 0) issue_loads<CF>(sm, a, role, env0, &s_bar, warp);
@@ -814,7 +1048,6 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   // episode sums / stored actions / episode length in global memory, the COMMAND task resamples their command before its
   // own update, the observation tasks see a reset env's stored action as 0 and its episode length as 0.
   const bool rme = u8_reset != 0;
-  unsigned early_prev = 0xffffffffu;
   const int n_tiles = a.k.N / 32;
   V2_STAMP_T0(4);
   const int eplen_now = rme ? 0 : __float_as_int(SMF(L.eplen, 0));
@@ -834,8 +1067,11 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
       const int part = tk.b, parts = tk.col0;
       const int fl = u8_bits;
       constexpr int NQ = K + RL_MAX_DONE_TERMS + 2;
+      constexpr int LROW = L.hist_pitch;   // floats of a partial row
+      const int vw = gt % kLogWarps, cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
+      float* const prow = a.k.log_partials + (size_t)(vw * cls_cap + gt / kLogWarps) * LROW;   // class-major (log_finish_*)
       if (__ballot_sync(0xffffffffu, rme) == 0u) {   // nothing to reset in this tile: the partials are zero
-        for (int q = part + lane * parts; q < NQ; q += 32 * parts) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;
+        for (int q = part + lane * parts; q < NQ; q += 32 * parts) prow[q] = 0.f;
       } else {
 #pragma unroll 4
         for (int q = part; q < NQ; q += parts) {   // independent reductions: their shuffle trees overlap
@@ -847,11 +1083,17 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
           }
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-          if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
+          if (lane == 0) prow[q] = x;
         }
       }
       __syncwarp();
-      if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);   // the tile's partials are written (the release covers only them)
+      // the tile's share of its partial row is written: arrive - for the launch when one staging area holds all rows
+      // (<= 128 tiles), else for the tile's class. acq_rel: the release covers only the row stores above, the acquire
+      // makes the other tiles' rows visible to the warp that turns out to be the last (no second round trip for that)
+      constexpr int kStageRows = kLogStageWords / LROW;
+      const bool one_level = (G == 1) && (kLogWarps * cls_cap <= kStageRows);
+      unsigned prev_c = 0;
+      if (lane == 0) prev_c = ticket_arrive_acq_rel(a.scan_ctl + (one_level ? 32 : 16 + vw));
       // ... and only now the zeroing of the reset envs' rows: the ticket's release does not have to wait for these stores
       if (rme) {
         float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
@@ -865,6 +1107,16 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
           gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
         }
         if (part == 0) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
+      }
+      // the last arrival of the class adds the class up (and, as the last of the classes, writes the means) - here, in
+      // this warp, while the rest of the CTA carries on: the launch has no tail
+      prev_c = __shfl_sync(0xffffffffu, prev_c, 0);
+      if (one_level) {
+        if constexpr (G == 1)
+          if (prev_c == (unsigned)(n_tiles * parts - 1)) log_finish_launch<CF>(a, sm, &s_lbar, n_tiles, lane);
+      } else {
+        const int class_tiles = (n_tiles - vw + kLogWarps - 1) / kLogWarps;
+        if (prev_c == (unsigned)(class_tiles * parts - 1)) log_finish_class<CF>(a, sm, &s_lbar, vw, n_tiles, lane);
       }
     } else if (tk.kind == TK_COMMAND) {
       // CommandTerm.reset [IL] of the reset envs (resample: V/mdp/commands.py:43-47), then CommandManager.compute and the
@@ -918,9 +1170,8 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
     }
   }, [&]() __attribute__((always_inline)) {
     if (C > 1 && !arrived) cluster_arrive_release();
-  });
+  }, V2_DBG_ROW);
   V2_STAMP(16 + warp);
-  if (lane == 0 && early_prev == (unsigned)(n_tiles * CF::log_parts - 1)) s_last = 1;   // the last ticket of the launch
   if (C > 1) cluster_wait_acquire();   // the command columns have reached their rows
   __syncthreads();
 
@@ -946,31 +1197,6 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
 
   if (C > 1) stream_height_scan();
   V2_STAMP_T0(6); V2_GTIME(7);
-  // ---- logging means of the reset (extras["log"] [IL]): the CTA whose ticket was the last of the launch -------------
-  if (s_last) {   // CTA-uniform (any role: the CTA whose LOG warp drew the last ticket)
-    __threadfence();
-    float* s_red = sm;   // the record is dead
-    __syncthreads();
-    for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32)
-      for (int vw = warp; vw < kLogWarps; vw += kWarps2) {   // 16 strided partial sums whatever the warp count of this CTA
-        float part = 0.f;
-        for (int g = vw; g < n_tiles; g += kLogWarps) part += __ldcg(a.k.log_partials + (size_t)g * RL_LOG_STRIDE + q);
-        s_red[vw * RL_LOG_STRIDE + q] = part;
-      }
-    __syncthreads();
-    if (tid < K + RL_MAX_DONE_TERMS + 2) {
-      float tot = 0.f;
-      for (int w = 0; w < kLogWarps; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
-      const RlResetLog& lg = a.k.out.reset_log;
-      const int n_reset_total = *a.k.out.n_reset;
-      const float cnt = (float)max(n_reset_total, 1);
-      if (n_reset_total == 0) tot = 0.f;
-      if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / cnt; }
-      else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
-      else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / cnt;
-    }
-    if (tid == 0) *a.k.ticket = 0u;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1010,6 +1236,11 @@ struct RlV2State {
   int n_tm[IF_COUNT];
   int next_tm[IF_COUNT];
   TmEntry tm[IF_COUNT][kTmCache];
+  // device scratch of the tail-free launch-wide results (V2Args::scan_state / scan_ctl / log_class)
+  unsigned long long* scan_state;
+  int scan_cap;
+  unsigned int* scan_ctl;
+  float* log_class;
 };
 
 namespace {
@@ -1063,10 +1294,14 @@ int launch_v2(RlCtx* ctx, const KArgs& k, cudaStream_t st) {
   for (int r = 0; r < C; ++r) {
     const uint32_t m = role_field_mask(s, CF::sched, KIND, r, CF::W) & staged;
     uint32_t bytes = 0;
+    int n = 0;
     for (int f = 0; f < IF_COUNT; ++f)
-      if ((m >> f) & 1u) bytes += (uint32_t)(in_field_ncomp(s, f) * CF::E * 4);
-    a.role_mask[r] = m; a.role_bytes[r] = bytes;
+      if ((m >> f) & 1u) { bytes += (uint32_t)(in_field_ncomp(s, f) * CF::E * 4); a.role_field[r][n++] = (uint8_t)f; }
+    // largest copies first: they are the last to land
+    std::stable_sort(a.role_field[r], a.role_field[r] + n, [&](uint8_t x, uint8_t y) { return in_field_ncomp(s, x) > in_field_ncomp(s, y); });
+    a.role_n[r] = (uint8_t)n; a.role_bytes[r] = bytes;
   }
+  a.scan_state = v->scan_state; a.scan_ctl = v->scan_ctl; a.log_class = v->log_class;
   if (KIND == RL_V2_PRE && s.num_rays > 0 && k.rays.ptr != nullptr && k.rays.cs == 1 && k.rays.es == s.num_rays &&
       ((size_t)CF::E * s.num_rays * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(k.rays.ptr) & 15u) == 0) {
     a.prefetch_rays = static_cast<const char*>(k.rays.ptr);
@@ -1160,14 +1395,40 @@ int rl_v2_create(RlCtx* ctx) {
   }
   // this translation unit's copy of the spec slots (the term functions read run-time indexed lists from it)
   CUDA_TRY(cudaMemcpyToSymbol(c_spec, &ctx->spec, sizeof(RlStepSpec), sizeof(RlStepSpec) * ctx->slot));
-  ctx->v2 = v;
+  ctx->v2 = v;   // from here on rl_v2_destroy frees what has been allocated
+  CUDA_TRY(cudaMalloc(&v->scan_ctl, sizeof(unsigned int) * 64));
+  CUDA_TRY(cudaMemset(v->scan_ctl, 0, sizeof(unsigned int) * 64));
+  const unsigned int first_epoch = 1u;   // zeroed status words are never valid
+  CUDA_TRY(cudaMemcpy(v->scan_ctl, &first_epoch, sizeof(first_epoch), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&v->log_class, sizeof(float) * kLogWarps * RL_LOG_STRIDE));
+  CUDA_TRY(cudaMemset(v->log_class, 0, sizeof(float) * kLogWarps * RL_LOG_STRIDE));
   return RL_OK;
 }
 
 void rl_v2_destroy(RlCtx* ctx) {
+  if (ctx->v2) {
+    if (ctx->v2->scan_state) cudaFree(ctx->v2->scan_state);
+    if (ctx->v2->scan_ctl) cudaFree(ctx->v2->scan_ctl);
+    if (ctx->v2->log_class) cudaFree(ctx->v2->log_class);
+  }
   delete ctx->v2;
   ctx->v2 = nullptr;
 }
+
+namespace {
+// status words of the look-back: zeroed once (epoch tags make the words of earlier launches invalid, never a stale word of
+// uninitialised memory); grows with the env count
+int ensure_scan_state(RlV2State* v, int n_tiles) {
+  if (n_tiles <= v->scan_cap) return RL_OK;
+  if (v->scan_state) CUDA_TRY(cudaFree(v->scan_state));
+  v->scan_state = nullptr; v->scan_cap = 0;
+  const int cap = n_tiles * 2 + 64;
+  CUDA_TRY(cudaMalloc(&v->scan_state, sizeof(unsigned long long) * (size_t)cap));
+  CUDA_TRY(cudaMemset(v->scan_state, 0, sizeof(unsigned long long) * (size_t)cap));
+  v->scan_cap = cap;
+  return RL_OK;
+}
+}  // namespace
 
 void rl_v2_config_for(const RlCtx* ctx, int64_t num_envs, int* cluster_size, int* tiles_per_cta, int* warps_per_cta, long long* launches) {
   *cluster_size = 0; *tiles_per_cta = 0; *warps_per_cta = 0; *launches = 0;
@@ -1196,7 +1457,6 @@ int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool
     if (HW > 0 && (k.hist.ptr == nullptr || k.hist.cs != 1 || k.hist.es != HW)) return RL_OK;   // contiguous force rows
     if (!soa_ok(k.outf[OF_SUMS], s.num_reward_terms) || !k.outf[OF_EPLEN].ptr || k.outf[OF_EPLEN].es != 1) return RL_OK;
     if (k.outf[OF_STEPR].ptr && k.outf[OF_STEPR].es != 1) return RL_OK;
-    if (!k.cta_mask || !k.ticket) return RL_OK;
   } else {
     if (!k.out.terminated || !k.out.truncated || !k.out.n_reset) return RL_OK;
     if (!k.is_heading.ptr || !k.is_standing.ptr || k.is_heading.es != 1 || k.is_standing.es != 1) return RL_OK;
@@ -1208,6 +1468,11 @@ int rl_v2_try_launch(RlCtx* ctx, const KArgs& k, int kind, cudaStream_t st, bool
       if (scan && (k.rays.ptr == nullptr || k.rays.cs != 1 || k.rays.es != s.num_rays || k.in[IF_RAYPOS].ptr == nullptr || k.in[IF_RAYPOS].es != 1))
         return RL_OK;
     }
+  }
+  if (k.N / 32 >= (1 << 24)) return RL_OK;   // the look-back's status word holds a 24-bit count
+  if (kind == RL_V2_PRE) {
+    const int rcs = ensure_scan_state(v, k.N / 32);
+    if (rcs != RL_OK) return rcs;
   }
   bool found = false;
   int rc = RL_OK, idx = 0;

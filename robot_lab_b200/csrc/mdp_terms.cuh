@@ -45,6 +45,15 @@ using DeviceGuard = RlDeviceGuard;
 #ifndef RL_TERM_LOOP
 #define RL_TERM_LOOP _Pragma("unroll 1")
 #endif
+// The SHORT loops - over the (four) feet, over the bodies of a contact mask. The kernels of mdp_step_v2.cu unroll these:
+// measured per task (tools/v2_timeline.py, profiles/r2_summary.md) the feet terms were the longest tasks of a tile - the
+// critical path of a 4096-env launch - because every iteration waited for a run-time indexed constant load, a call of the
+// division subroutine and the previous iteration's quaternion chain; unrolled against the baked spec the indices are
+// immediates, x / 2 and x / 4 are exact multiplications, and the feet's independent chains overlap. The order of every
+// sum is unchanged (bit-identical results).
+#ifndef RL_FEW_LOOP
+#define RL_FEW_LOOP _Pragma("unroll 1")
+#endif
 constexpr int kE = 32;  // envs per CTA = lanes per warp: in the compute phase lane e of every warp owns env e
 // (Round 1 cut the one long body sum - undesired_contacts over 15 bodies - into two parts that met through a lock-free
 // arrival counter in shared memory. Round 2 removed it: compute-sanitizer racecheck flags the protocol, the parts rounded
@@ -190,7 +199,7 @@ __host__ __device__ constexpr int out_field_word(const Layout& L, int f) {
 // ---------------------------------------------------------------------------------------------------
 // Work schedule. The compute phase is thread-per-env (lane e of every warp owns env e, so SIMT lanes never
 // duplicate per-env scalar work); the warps of a CTA differ in WHICH tasks they run: one task per reward term
-// (wide body-mask terms split in two halves) and one per observation term (the height scan in 64-column chunks),
+// and one per observation term (the height scan in column chunks),
 // balanced over the warps by a longest-processing-time greedy on rough instruction costs. constexpr, so a baked
 // spec gets its schedule at compile time and every warp's code is straight-line.
 // ---------------------------------------------------------------------------------------------------
@@ -204,7 +213,7 @@ struct Task {
 struct Schedule {
   int n;
   Task t[RL_MAX_TASKS];
-  uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (split terms, is_terminated)
+  uint8_t late[RL_MAX_REWARD_TERMS];    // term is finished in stage 2 (is_terminated)
 };
 
 __host__ __device__ constexpr int popc64(uint64_t m) { int n = 0; while (m) { m &= m - 1; ++n; } return n; }
@@ -397,7 +406,15 @@ __device__ __forceinline__ unsigned ticket_arrive_release(unsigned int* ticket) 
   asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket) : "memory");
   return prev;
 }
-
+// The ONE thread that drew the last ticket of a launch: an acquiring read of the ticket word synchronises with every
+// tile's release-arrival (they form one chain of read-modify-writes); the CTA barrier that follows extends that to the
+// CTA's other threads, whose tail loads go to L2 (ld.cg). No fence: a fence would also wait for this CTA's own
+// outstanding stores, with every other SM idle (profiles/r2_summary.md: 2 us of a 4096-env launch).
+__device__ __forceinline__ void ticket_acquire(const unsigned int* ticket) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ticket) : "memory");
+  (void)v;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Math (restates isaaclab.utils.math [IL]: quat_apply, quat_apply_inverse, yaw_quat, wrap_to_pi)
@@ -434,7 +451,23 @@ __device__ __forceinline__ float wrap_to_pi(float a) {
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 // torch.clamp semantics for NaN are irrelevant here; +-inf behave like fminf/fmaxf.
 // transcendental functions behind calls: one code copy each instead of ~100 inlined instructions per use
-__device__ __noinline__ float rl_div(float x, float y) { return x / y; }   // IEEE division, one code copy
+// IEEE division, one code copy. A zero numerator (a reward term that is 0 for the env: most contact / air-time terms on most
+// steps) sends the WHOLE warp through the ~30-instruction special-operand path of the division subroutine - 11 % of the
+// pre-reset launch's instructions at 65536 envs (profiles/r2_summary.md). (+-0) / y for a finite normal y is (+-0) * y
+// exactly (sign = xor of the signs), so those lanes divide 1 by y instead and take the product.
+__device__ __noinline__ float rl_div(float x, float y) {
+  const bool z = (x == 0.f) && (fabsf(y) >= 1.17549435e-38f) && (fabsf(y) <= 3.402823466e38f);
+  const float q = (z ? 1.f : x) / y;
+  return z ? x * y : q;
+}
+// x / (float)n for a small positive count n: halves and quarters are exact multiplications (the correctly rounded product
+// and the correctly rounded quotient of the same real number), everything else goes through the division subroutine
+__device__ __forceinline__ float div_count(float x, int n) {
+  if (n == 1) return x;
+  if (n == 2) return x * 0.5f;
+  if (n == 4) return x * 0.25f;
+  return rl_div(x, (float)n);
+}
 __device__ __noinline__ float rl_expf(float x) { return expf(x); }
 __device__ __noinline__ float rl_tanhf(float x) { return tanhf(x); }
 __device__ __noinline__ float rl_atan2f(float y, float x) { return atan2f(y, x); }
@@ -626,11 +659,13 @@ __device__ __noinline__ float hist_max_norm(const float* h, int T, int B, int b)
     const float ss = (f[0] * f[0] + f[1] * f[1]) + f[2] * f[2];
     m2 = (t == 0) ? ss : fmaxf(m2, ss);
   }
-  return (m2 == 0.f) ? 0.f : sqrtf(m2);
+  const bool z = (m2 == 0.f);   // a body without contact: keep the warp off sqrt's special-operand path
+  const float r = sqrtf(z ? 1.f : m2);
+  return z ? 0.f : r;
 }
 
 // One reward term for env e: raw value (no weight, no dt). [lo, hi) restricts body-mask terms to a body-index
-// range (the two halves of a split term add up).
+// range (callers pass 0, 64: the whole mask).
 // `t` may be a build-time constant (scalar members fold into immediates); `tc` is the same term in __constant__
 // memory and serves every run-time indexed list (a baked object indexed at run time would be a global-memory load).
 template <bool CN>
@@ -737,10 +772,10 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
         if (n < 2) continue;
         float m = 0.f;
         for (int i = 0; i < n; ++i) m += fabsf(SMF(L.act, tc.idx_a[start + i]));
-        m = m / (float)n;
+        m = div_count(m, n);
         float v = 0.f;
         for (int i = 0; i < n; ++i) { const float d = fabsf(SMF(L.act, tc.idx_a[start + i])) - m; v += d * d; }
-        r += v / (float)n;
+        r += div_count(v, n);
       }
       return (r * t.p[0]) * c.gate;
     }
@@ -752,7 +787,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_UNDESIRED_CONTACTS: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if (((t.body_mask >> b) & 1ull) && (HIST_MAX_NORM(h, b) > t.p[0])) s += 1.f;
       // one part of a split term (a restricted body range) returns its raw COUNT: the finisher adds the counts (exact)
@@ -762,7 +797,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_CONTACT_FORCES: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int b = lo; b < S.num_hist_bodies && b < hi; ++b)
         if ((t.body_mask >> b) & 1ull) s += fmaxf(HIST_MAX_NORM(h, b) - t.p[0], 0.f);
       return s;
@@ -791,7 +826,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_AIR_TIME: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = tc.idx_a[i];
         s += (SMF(L.lair, b) - t.p[0]) * (first_contact(sm, L, S, e, b) ? 1.f : 0.f);
@@ -801,11 +836,11 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_AIR_TIME_POSITIVE_BIPED: {
       int n_contact = 0;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) n_contact += (SMF(L.ccon, tc.idx_a[i]) > 0.f) ? 1 : 0;
       const bool single = (n_contact == 1);
       float r = INFINITY;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const int b = tc.idx_a[i];
         const float ct = SMF(L.ccon, b);
@@ -819,18 +854,18 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     case RL_REW_FEET_AIR_TIME_VARIANCE: {
       // torch.var (unbiased) is a Welford reduction on CPU; keep the same update order.
       float r = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int which = 0; which < 2; ++which) {
         const int off = which == 0 ? L.lair : L.lcon;
         float mean = 0.f, m2 = 0.f;
-        RL_TERM_LOOP
+        RL_FEW_LOOP
         for (int i = 0; i < t.n_idx; ++i) {
           const float x = fminf(SMF(off, tc.idx_a[i]), 0.5f);
           const float d = x - mean;
-          mean += d / (float)(i + 1);
+          mean += div_count(d, i + 1);
           m2 += d * (x - mean);
         }
-        r += m2 / (float)(t.n_idx - 1);
+        r += div_count(m2, t.n_idx - 1);
       }
       return r * c.gate;
     }
@@ -854,7 +889,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_CONTACT: {
       int n = 0;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = ((float)n != t.p[0]) ? 1.f : 0.f;
       r *= (c.cmd_norm > 0.1f) ? 1.f : 0.f;
@@ -862,7 +897,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_CONTACT_WITHOUT_CMD: {
       int n = 0;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) n += first_contact(sm, L, S, e, tc.idx_a[i]) ? 1 : 0;
       float r = (float)n;
       r *= (c.cmd_norm < 0.1f) ? 1.f : 0.f;
@@ -880,7 +915,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_SLIDE: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = lo; i < t.n_idx && i < hi; ++i) {   // [lo, hi): this part's slice of the feet list
         const V3 vw = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);
         const V3 vb = quat_apply_inverse(c.qw, c.q, V3{vw.x - c.vw.x, vw.y - c.vw.y, vw.z - c.vw.z});
@@ -891,7 +926,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_HEIGHT: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 p = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 v = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);
@@ -903,7 +938,7 @@ __device__ __forceinline__ float reward_term(const RlRewardTerm& t, const RlRewa
     }
     case RL_REW_FEET_HEIGHT_BODY: {
       float s = 0.f;
-      RL_TERM_LOOP
+      RL_FEW_LOOP
       for (int i = 0; i < t.n_idx; ++i) {
         const V3 pw = body_vec(sm, L, L.bpos, e, tc.idx_b[i]);
         const V3 vw = body_vec(sm, L, L.bvel, e, tc.idx_b[i]);

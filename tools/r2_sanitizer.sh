@@ -19,6 +19,9 @@ run() {   # tool, label, env assignments..., -- pytest selection
   local rc=$?
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error" gpurun_out/san_tmp.log | tail -n 6 >> "$out"
   grep -E "^========= (Error|Race|Barrier|Invalid|Warning)" gpurun_out/san_tmp.log | sort | uniq -c | head -n 12 >> "$out"
+  if [ $rc -ne 0 ]; then   # the full text of the first hazards (both accesses)
+    grep -A 8 -E "^========= (Error|Warning)" gpurun_out/san_tmp.log | head -n 40 >> "$out"
+  fi
   echo "rc=$rc" >> "$out"
 }
 for tool in memcheck racecheck synccheck; do

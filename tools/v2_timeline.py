@@ -66,7 +66,7 @@ for kind in ("pre", "post"):
     out = {}
     if kind == "pre":
         for name, a_, b_ in (("  entry -> mbarrier armed", 1, 9), ("  first CTA barrier", 9, 10), ("  this warp's copies issued", 10, 11),
-                             ("  joint constants -> smem", 11, 12), ("  zero slots + second barrier", 12, 2)):
+                             ("  norm prepass + joint constants", 11, 12), ("  zero slots + second barrier", 12, 2)):
             out[name] = med([float((d[:, b_] - d[:, a_]).float().median()) for d in rows])
     for name, a_, b_ in (("prologue + load issue", 1, 2), ("wait for the record", 2, 3), ("reset / prepass", 3, 4),
                          ("tasks + barrier", 4, 5), ("tail", 5, 6), ("entry -> tail done", 1, 6)):
@@ -82,6 +82,30 @@ for kind in ("pre", "post"):
         print(f"   {k:28s} {v:9.0f} cycles  {v / 1.9e3:6.2f} us")
     print("   per-warp task cycles:", " ".join(f"{int(x)}" for x in per_warp.tolist()))
     print(f"   globaltimer: first CTA entry -> last CTA tail {span / 1e3:.2f} us; entry spread over the grid {first_last_entry / 1e3:.2f} us")
+    # per-task cycles (stamps build: slot 32 + task index, in schedule order)
+    if kind == "pre":
+        names = ["DONES"] + [r.name for r in spec.rewards if r.weight != 0.0 and r.type_name != "is_terminated"]
+    else:
+        names = ["COMMAND"] + [f"LOG part {p}" for p in range(4)]
+        for g, grp in enumerate(spec.obs):
+            for t in grp.terms:
+                if t.name in ("velocity_commands", "height_scan") or t.type_name in ("generated_commands", "height_scan"):
+                    continue
+                for lo in range(0, t.dim, 32):
+                    names.append(f"OBS {grp.name}.{t.name}[{lo}:{min(lo + 32, t.dim)}]")
+    tcy = torch.stack([d[:, 32:64].float().median(dim=0).values for d in rows]).median(dim=0).values.tolist()
+    print("   per-task cycles (median over CTAs): " + ", ".join(f"{names[i] if i < len(names) else i}={int(c)}" for i, c in enumerate(tcy) if c > 0))
+    if kind == "post":   # the warp that finished the logging reduction of the launch (one-level form: stamps 56 - 58)
+        fin = [int(torch.argmax(d[:, 58])) for d in rows]
+        if all(int(d[c_, 58]) > 0 for d, c_ in zip(rows, fin)):
+            tl = lambda a_, b_: med([float(d[c_, b_] - d[c_, a_]) for d, c_ in zip(rows, fin)]) / 1e3
+            tl0 = lambda b_: med([float(d[c_, b_] - d[:, 0].min()) for d, c_ in zip(rows, fin)]) / 1e3
+            print(f"   logging finisher (globaltimer, us after the first entry): starts {tl0(56):.2f}, rows staged +{tl(56, 57):.2f}, "
+                  f"means written +{tl(57, 58):.2f}; its CTA ends {tl0(7):.2f}")
+    ends = [torch.sort(d[:, 7] - d[:, 0].min()).values.float() for d in rows]
+    q = lambda f: med([float(e_[int(f * (len(e_) - 1))]) for e_ in ends]) / 1e3
+    print(f"   CTA end times (us after the first entry; the launches have no launch-wide tail): 50 % {q(0.5):.2f}, 90 % {q(0.9):.2f}, "
+          f"99 % {q(0.99):.2f}, last {q(1.0):.2f}")
 
 
 # ---- launch-overhead probes (stamps build): the same launches, returning at entry / right after the record is resident ----
