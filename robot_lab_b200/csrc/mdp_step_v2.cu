@@ -123,11 +123,6 @@ __host__ __device__ constexpr bool v2_spec_ok(const RlStepSpec& s) {
   return true;
 }
 
-constexpr int kLogStageWords = 4096;   // 16 KB: 128 partial rows of 32 floats (64 rows of 64 floats when a spec logs more than 32 quantities)
-__host__ __device__ constexpr int log_row_floats(const RlStepSpec& s) {
-  return (s.num_reward_terms + RL_MAX_DONE_TERMS + 2) <= 32 ? 32 : RL_LOG_STRIDE;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Record layout of a CTA: 32 G envs; the term functions address it through the same Layout members as the general
 // kernel (SoA word w of env e at sm[w*E + e]).
@@ -171,11 +166,6 @@ __host__ __device__ constexpr Layout make_layout_v2(const RlStepSpec& s, const i
     L.obs_pitch0 = odd_pitch(env_cols_of(s.obs[0])); L.obs_pitch1 = odd_pitch(env_cols_of(s.obs[1]));
     L.obs0 = off; off = align_up(off + E * L.obs_pitch0, 32);
     L.obs1 = off; off = align_up(off + E * L.obs_pitch1, 32);
-    // staging area of the logging reduction (one tile per CTA): kLogStageWords words of partial rows, bulk-copied by the
-    // LOG warp that finishes the launch (or its class of tiles) WHILE the record is alive (hist = base, hist_pitch =
-    // floats of a row; both members are otherwise unused in this launch)
-    L.hist_pitch = log_row_floats(s);
-    if (E == 32) { L.hist = off; off = align_up(off + kLogStageWords, 32); }
   }
   L.total_words = off;
   return L;
@@ -400,10 +390,9 @@ struct alignas(64) V2Args {
   int32_t field_word[IF_COUNT];
   const char* prefetch_rays;   // PRE: the ray-hit rows the post-reset launch will stream (L2 prefetch), or NULL
   uint32_t prefetch_row_bytes;
-  // launch-wide results without a launch-wide tail (scratch owned by the context, see RlV2State):
+  // the pre-reset launch's ordered reset ids without a launch-wide tail (scratch owned by the context, see RlV2State):
   unsigned long long* scan_state;   // PRE: one status word per tile (epoch | flag | reset count or prefix): decoupled look-back
-  unsigned int* scan_ctl;           // [0] epoch of the look-back; [16 + c] ticket of logging class c; [32] ticket of the classes
-  float* log_class;                 // POST: [16][RL_LOG_STRIDE] partial sums of the 16 strided classes of tiles
+  unsigned int* scan_ctl;           // [0] epoch of the look-back
   alignas(64) CUtensorMap tm[IF_COUNT];
 };
 
@@ -604,157 +593,6 @@ __device__ __noinline__ unsigned lookback_resolve(unsigned long long* st, const 
   return excl;
 }
 
-// Logging means of the reset (extras["log"] [IL]) WITHOUT a launch-wide tail, in the general kernel's order of additions
-// (16 strided partial sums over the tiles - class c = tiles c, c + 16, ... - then their sum in class order: bit-identical).
-// A tile's partial row lives class-major: row (tile % 16) * ceil(tiles / 16) + tile / 16, so that the rows of a class are
-// one contiguous block. Every memory round trip at the end of a launch is expensive (0.6 us cold at 4096 envs, 2 - 3 us
-// while 65536 envs' result rows drain), so the reduction is built around ONE bulk copy:
-//   * up to 128 tiles (4096 envs): the LOG warp that makes the last arrival of the LAUNCH (an acq_rel atomic: no separate
-//     acquiring load) bulk-copies all rows into the staging area of its CTA - while the other warps of the CTA carry on
-//     with their tasks - adds the 16 chains from shared memory and writes the means;
-//   * beyond: the warp that makes the last arrival of its CLASS does the same for the class's rows, publishes the class
-//     sum and arrives for the class; the last of those 16 arrivals adds the class sums.
-// (First cuts of this round, profiles/r2_summary.md: one CTA after the last tile, one L2 round trip per 16 tiles - 2 us of
-// a 9.7 us launch at 4096 envs, 14 - 30 us of 62 at 65536; then class finishers with register-staged loads - 5 round trips.)
-__device__ __forceinline__ unsigned ticket_arrive_acq_rel(unsigned int* ticket) {
-  unsigned prev;
-  asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket) : "memory");
-  return prev;
-}
-// lanes = quantities; the means from the 16 class sums p[w] (register) - shared tail of both forms
-template <int K>
-__device__ __forceinline__ void log_write_means(const KArgs& k, const int q, float tot, const int n_reset_total) {
-  const RlResetLog& lg = k.out.reset_log;
-  const float cnt = (float)max(n_reset_total, 1);
-  if (n_reset_total == 0) tot = 0.f;
-  if (q < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[q] = tot / cnt; }
-  else if (q < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[q - K] = tot; }
-  else if (lg.metric_mean) lg.metric_mean[q - K - RL_MAX_DONE_TERMS] = tot / cnt;
-}
-// one warp: bulk copy of `rows` partial rows starting at row `row0` into the staging area, complete on return
-template <class CF>
-__device__ __forceinline__ void log_stage_rows(const V2Args& a, float* buf, uint64_t* bar, uint32_t& phase, const int row0, const int rows, const int lane) {
-  constexpr int ROW = CF::L.hist_pitch;
-  if (lane == 0) {
-    const uint32_t bytes = (uint32_t)(rows * ROW * 4);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the staging area before the copy overwrites it
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(buf, a.k.log_partials + (size_t)row0 * ROW, bytes, bar);
-  }
-  mbar_wait(bar, phase);
-  phase ^= 1u;
-}
-template <class CF>
-__device__ __noinline__ void log_finish_launch(const V2Args& a, float* sm, uint64_t* bar, const int n_tiles, const int lane) {
-  constexpr int K = CF::S.num_reward_terms, NQ = K + RL_MAX_DONE_TERMS + 2, QI = (NQ + 31) / 32, ROW = CF::L.hist_pitch;
-  float* buf = sm + CF::L.hist;
-  const int cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
-  const int n_reset_total = a.k.out.n_reset ? __ldcg(a.k.out.n_reset) : 0;   // written by the pre-reset launch
-  uint32_t phase = 0;
-  V2_GTIME_L(a.k, 56);
-  log_stage_rows<CF>(a, buf, bar, phase, 0, kLogWarps * cls_cap, lane);
-  V2_GTIME_L(a.k, 57);
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) {
-    const int q = lane + qi * 32;
-    if (q < NQ) {
-      float tot = 0.f;
-#pragma unroll 1
-      for (int w0 = 0; w0 < kLogWarps; w0 += 8) {   // 8 independent chains at a time, each in tile order
-        float part[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) part[w] = 0.f;
-#pragma unroll 1
-        for (int i = 0; i < cls_cap; ++i)
-#pragma unroll
-          for (int w = 0; w < 8; ++w)
-            if (w0 + w + kLogWarps * i < n_tiles) part[w] += buf[((w0 + w) * cls_cap + i) * ROW + q];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) tot += part[w];   // class order
-      }
-      log_write_means<K>(a.k, q, tot, n_reset_total);
-    }
-  }
-  if (lane == 0) a.scan_ctl[32] = 0u;   // every arrival of this launch has been made
-  V2_GTIME_L(a.k, 58);
-}
-template <class CF>
-__device__ __noinline__ void log_finish_class(const V2Args& a, float* sm, uint64_t* bar, const int vw, const int n_tiles, const int lane) {
-  constexpr int K = CF::S.num_reward_terms, NQ = K + RL_MAX_DONE_TERMS + 2, QI = (NQ + 31) / 32, ROW = CF::L.hist_pitch;
-  constexpr bool kStaged = (CF::E == 32);        // one tile per CTA: the staging area exists
-  constexpr int CHR = kLogStageWords / ROW;      // rows per bulk copy
-  float* buf = sm + CF::L.hist;
-  unsigned int* ctl = a.scan_ctl;
-  const int cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
-  const int class_tiles = (n_tiles - vw + kLogWarps - 1) / kLogWarps;
-  float part[QI];
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) part[qi] = 0.f;
-  if constexpr (kStaged) {
-    uint32_t phase = 0;
-#pragma unroll 1
-    for (int i0 = 0; i0 < class_tiles; i0 += CHR) {
-      const int rows = class_tiles - i0 < CHR ? class_tiles - i0 : CHR;
-      if (i0 > 0) __syncwarp();   // every lane is done with the previous chunk
-      log_stage_rows<CF>(a, buf, bar, phase, vw * cls_cap + i0, rows, lane);
-#pragma unroll
-      for (int qi = 0; qi < QI; ++qi) {
-        const int q = lane + qi * 32;
-        if (q < NQ)
-#pragma unroll 4
-          for (int i = 0; i < rows; ++i) part[qi] += buf[i * ROW + q];   // tile order
-      }
-    }
-  } else {   // several tiles per CTA (cluster configurations): rows through registers, 8 loads in flight per round
-#pragma unroll
-    for (int qi = 0; qi < QI; ++qi) {
-      const int q = lane + qi * 32;
-      if (q < NQ) {
-#pragma unroll 1
-        for (int i0 = 0; i0 < class_tiles; i0 += 8) {
-          float x[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (i0 + j < class_tiles) ? __ldcg(a.k.log_partials + (size_t)(vw * cls_cap + i0 + j) * ROW + q) : 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (i0 + j < class_tiles) part[qi] += x[j];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) {
-    const int q = lane + qi * 32;
-    if (q < NQ) a.log_class[vw * RL_LOG_STRIDE + q] = part[qi];
-  }
-  __syncwarp();
-  unsigned prev = 0;
-  if (lane == 0) prev = ticket_arrive_acq_rel(ctl + 32);
-  prev = __shfl_sync(0xffffffffu, prev, 0);
-  const int n_classes = n_tiles < kLogWarps ? n_tiles : kLogWarps;
-  if (prev != (unsigned)(n_classes - 1)) return;
-  const int n_reset_total = a.k.out.n_reset ? __ldcg(a.k.out.n_reset) : 0;   // written by the pre-reset launch
-#pragma unroll
-  for (int qi = 0; qi < QI; ++qi) {
-    const int q = lane + qi * 32;
-    if (q < NQ) {
-      float tot = 0.f;
-#pragma unroll 1
-      for (int w0 = 0; w0 < kLogWarps; w0 += 8) {
-        float p[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) p[w] = (w0 + w < n_classes) ? __ldcg(a.log_class + (w0 + w) * RL_LOG_STRIDE + q) : 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) tot += p[w];   // class order
-      }
-      log_write_means<K>(a.k, q, tot, n_reset_total);
-    }
-  }
-  // every arrival of this launch has been made: the tickets start the next launch at zero
-  if (lane < kLogWarps) ctl[16 + lane] = 0u;
-  if (lane == 0) ctl[32] = 0u;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // PRE: TerminationManager.compute + RewardManager.compute [IL] + reset_buf.nonzero()
 // ---------------------------------------------------------------------------------------------------
@@ -938,7 +776,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
 // ObservationManager.compute [IL] for all envs
 // ---------------------------------------------------------------------------------------------------
 template <class B, int C, int G, int NW>
-__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? RL_V2_POST_MINB8 : RL_V2_POST_MINB16))) v2_post_kernel(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ? 6 : 3))) v2_post_kernel(const __grid_constant__ V2Args a) {
   using CF = Cfg2<B, RL_V2_POST, C, G, NW>;
   constexpr int kWarps2 = NW, kThreads2 = NW * 32;
   constexpr Layout L = CF::L;
@@ -946,7 +784,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   constexpr int E = CF::E, W = CF::W, K = S.num_reward_terms, A = S.n_actions;
   extern __shared__ __align__(128) float sm[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(8) uint64_t s_lbar;   // bulk copies of the logging reduction (log_stage_rows)
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = warp / W, slot = warp - tile * W;
   const int e = tile * 32 + lane;
@@ -961,7 +799,10 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   if (C > 1) cluster_arrive_relaxed();
   if (a.k.use_pdl) pdl_launch_dependents();
   for (int i = tid; i < 5 * S.num_joints; i += kThreads2) sm[L.cj + i] = __ldg(a.k.cj + i);   // [5][J] table, one coalesced read
-  if (tid == 0) { mbar_init(&s_lbar, 1); init_load_barrier(&s_bar); }   // s_lbar: the logging reduction's bulk copies (before the same fence + CTA barrier)
+  if (tid == 0) {
+    s_last = 0;
+    init_load_barrier(&s_bar);
+  }
   __syncthreads();
   if (a.k.use_pdl) pdl_wait();
   if (lane == 0) issue_loads<CF>(sm, a, role, env0, &s_bar, warp);
@@ -1048,6 +889,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
   // episode sums / stored actions / episode length in global memory, the COMMAND task resamples their command before its
   // own update, the observation tasks see a reset env's stored action as 0 and its episode length as 0.
   const bool rme = u8_reset != 0;
+  unsigned early_prev = 0xffffffffu;
   const int n_tiles = a.k.N / 32;
   V2_STAMP_T0(4);
   const int eplen_now = rme ? 0 : __float_as_int(SMF(L.eplen, 0));
@@ -1067,11 +909,8 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
       const int part = tk.b, parts = tk.col0;
       const int fl = u8_bits;
       constexpr int NQ = K + RL_MAX_DONE_TERMS + 2;
-      constexpr int LROW = L.hist_pitch;   // floats of a partial row
-      const int vw = gt % kLogWarps, cls_cap = (n_tiles + kLogWarps - 1) / kLogWarps;
-      float* const prow = a.k.log_partials + (size_t)(vw * cls_cap + gt / kLogWarps) * LROW;   // class-major (log_finish_*)
       if (__ballot_sync(0xffffffffu, rme) == 0u) {   // nothing to reset in this tile: the partials are zero
-        for (int q = part + lane * parts; q < NQ; q += 32 * parts) prow[q] = 0.f;
+        for (int q = part + lane * parts; q < NQ; q += 32 * parts) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = 0.f;
       } else {
 #pragma unroll 4
         for (int q = part; q < NQ; q += parts) {   // independent reductions: their shuffle trees overlap
@@ -1083,17 +922,11 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
           }
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-          if (lane == 0) prow[q] = x;
+          if (lane == 0) a.k.log_partials[(size_t)gt * RL_LOG_STRIDE + q] = x;
         }
       }
       __syncwarp();
-      // the tile's share of its partial row is written: arrive - for the launch when one staging area holds all rows
-      // (<= 128 tiles), else for the tile's class. acq_rel: the release covers only the row stores above, the acquire
-      // makes the other tiles' rows visible to the warp that turns out to be the last (no second round trip for that)
-      constexpr int kStageRows = kLogStageWords / LROW;
-      const bool one_level = (G == 1) && (kLogWarps * cls_cap <= kStageRows);
-      unsigned prev_c = 0;
-      if (lane == 0) prev_c = ticket_arrive_acq_rel(a.scan_ctl + (one_level ? 32 : 16 + vw));
+      if (lane == 0) early_prev = ticket_arrive_release(a.k.ticket);   // the tile's partials are written (the release covers only them)
       // ... and only now the zeroing of the reset envs' rows: the ticket's release does not have to wait for these stores
       if (rme) {
         float* gs = static_cast<float*>(const_cast<void*>(a.k.outf[OF_SUMS].ptr));
@@ -1107,16 +940,6 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
           gp[(size_t)q * a.k.outf[OF_PACT].cs + env] = 0.f;
         }
         if (part == 0) static_cast<int*>(const_cast<void*>(a.k.outf[OF_EPLEN].ptr))[env] = 0;
-      }
-      // the last arrival of the class adds the class up (and, as the last of the classes, writes the means) - here, in
-      // this warp, while the rest of the CTA carries on: the launch has no tail
-      prev_c = __shfl_sync(0xffffffffu, prev_c, 0);
-      if (one_level) {
-        if constexpr (G == 1)
-          if (prev_c == (unsigned)(n_tiles * parts - 1)) log_finish_launch<CF>(a, sm, &s_lbar, n_tiles, lane);
-      } else {
-        const int class_tiles = (n_tiles - vw + kLogWarps - 1) / kLogWarps;
-        if (prev_c == (unsigned)(class_tiles * parts - 1)) log_finish_class<CF>(a, sm, &s_lbar, vw, n_tiles, lane);
       }
     } else if (tk.kind == TK_COMMAND) {
       // CommandTerm.reset [IL] of the reset envs (resample: V/mdp/commands.py:43-47), then CommandManager.compute and the
@@ -1172,6 +995,7 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
     if (C > 1 && !arrived) cluster_arrive_release();
   }, V2_DBG_ROW);
   V2_STAMP(16 + warp);
+  if (lane == 0 && early_prev == (unsigned)(n_tiles * CF::log_parts - 1)) { ticket_acquire(a.k.ticket); s_last = 1; }   // the last ticket of the launch
   if (C > 1) cluster_wait_acquire();   // the command columns have reached their rows
   __syncthreads();
 
@@ -1197,6 +1021,30 @@ __global__ void __launch_bounds__(NW * 32, G > 2 ? 1 : (NW <= 4 ? 8 : (NW <= 8 ?
 
   if (C > 1) stream_height_scan();
   V2_STAMP_T0(6); V2_GTIME(7);
+  // ---- logging means of the reset (extras["log"] [IL]): the CTA whose ticket was the last of the launch -------------
+  if (s_last) {   // CTA-uniform (any role: the CTA whose LOG warp drew the last ticket; its thread acquired the tiles' rows)
+    float* s_red = sm;   // the record is dead
+    __syncthreads();
+    for (int q = lane; q < K + RL_MAX_DONE_TERMS + 2; q += 32)
+      for (int vw = warp; vw < kLogWarps; vw += kWarps2) {   // 16 strided partial sums whatever the warp count of this CTA
+        float part = 0.f;
+        for (int g = vw; g < n_tiles; g += kLogWarps) part += __ldcg(a.k.log_partials + (size_t)g * RL_LOG_STRIDE + q);
+        s_red[vw * RL_LOG_STRIDE + q] = part;
+      }
+    __syncthreads();
+    if (tid < K + RL_MAX_DONE_TERMS + 2) {
+      float tot = 0.f;
+      for (int w = 0; w < kLogWarps; ++w) tot += s_red[w * RL_LOG_STRIDE + tid];
+      const RlResetLog& lg = a.k.out.reset_log;
+      const int n_reset_total = *a.k.out.n_reset;
+      const float cnt = (float)max(n_reset_total, 1);
+      if (n_reset_total == 0) tot = 0.f;
+      if (tid < K) { if (lg.episode_sum_mean) lg.episode_sum_mean[tid] = tot / cnt; }
+      else if (tid < K + RL_MAX_DONE_TERMS) { if (lg.done_term_count) lg.done_term_count[tid - K] = tot; }
+      else if (lg.metric_mean) lg.metric_mean[tid - K - RL_MAX_DONE_TERMS] = tot / cnt;
+    }
+    if (tid == 0) *a.k.ticket = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1236,11 +1084,10 @@ struct RlV2State {
   int n_tm[IF_COUNT];
   int next_tm[IF_COUNT];
   TmEntry tm[IF_COUNT][kTmCache];
-  // device scratch of the tail-free launch-wide results (V2Args::scan_state / scan_ctl / log_class)
+  // device scratch of the look-back (V2Args::scan_state / scan_ctl)
   unsigned long long* scan_state;
   int scan_cap;
   unsigned int* scan_ctl;
-  float* log_class;
 };
 
 namespace {
@@ -1301,7 +1148,7 @@ int launch_v2(RlCtx* ctx, const KArgs& k, cudaStream_t st) {
     std::stable_sort(a.role_field[r], a.role_field[r] + n, [&](uint8_t x, uint8_t y) { return in_field_ncomp(s, x) > in_field_ncomp(s, y); });
     a.role_n[r] = (uint8_t)n; a.role_bytes[r] = bytes;
   }
-  a.scan_state = v->scan_state; a.scan_ctl = v->scan_ctl; a.log_class = v->log_class;
+  a.scan_state = v->scan_state; a.scan_ctl = v->scan_ctl;
   if (KIND == RL_V2_PRE && s.num_rays > 0 && k.rays.ptr != nullptr && k.rays.cs == 1 && k.rays.es == s.num_rays &&
       ((size_t)CF::E * s.num_rays * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(k.rays.ptr) & 15u) == 0) {
     a.prefetch_rays = static_cast<const char*>(k.rays.ptr);
@@ -1400,8 +1247,6 @@ int rl_v2_create(RlCtx* ctx) {
   CUDA_TRY(cudaMemset(v->scan_ctl, 0, sizeof(unsigned int) * 64));
   const unsigned int first_epoch = 1u;   // zeroed status words are never valid
   CUDA_TRY(cudaMemcpy(v->scan_ctl, &first_epoch, sizeof(first_epoch), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&v->log_class, sizeof(float) * kLogWarps * RL_LOG_STRIDE));
-  CUDA_TRY(cudaMemset(v->log_class, 0, sizeof(float) * kLogWarps * RL_LOG_STRIDE));
   return RL_OK;
 }
 
@@ -1409,7 +1254,6 @@ void rl_v2_destroy(RlCtx* ctx) {
   if (ctx->v2) {
     if (ctx->v2->scan_state) cudaFree(ctx->v2->scan_state);
     if (ctx->v2->scan_ctl) cudaFree(ctx->v2->scan_ctl);
-    if (ctx->v2->log_class) cudaFree(ctx->v2->log_class);
   }
   delete ctx->v2;
   ctx->v2 = nullptr;

@@ -79,9 +79,7 @@ def test_cluster_kernels_use_cluster_barriers_and_dsmem(kernels):
 def test_new_kernels_are_smaller_than_the_general_kernel(kernels):
     """No load prologue, no store phase, no per-warp protocols: a new kernel is under half of the general kernel of the
     same task (5.3 - 5.6 k instructions in round 1). Code size is time here: every SM executes each instruction once."""
-    # (the post-reset kernels carry the finishers of the logging reduction - ~600 instructions that ONE warp per class of
-    # tiles executes, not every SM)
-    for kind, bound in (("pre", 5200), ("post", 5800)):
+    for kind, bound in (("pre", 5200), ("post", 5200)):
         for name, body in _cluster_kernels(kernels, kind).items():
             assert len(body) < bound, f"{name}: {len(body)} instructions"
 
@@ -102,16 +100,16 @@ def test_last_cta_tickets_are_release_atomics_not_sc_fences(kernels):
         assert len(re.findall(r"ATOM\.E\.ADD\.STRONG\.GPU", text)) >= 2, name          # early arrivals (pre- / post-reset)
         assert len(re.findall(r"MEMBAR\.ALL\.GPU", text)) >= 2, name                   # their release fences
         assert len(re.findall(r"MEMBAR\.SC\.GPU", text)) <= 2, name                    # only the two acquiring tails
-    # the new kernels have no launch-wide tail: the pre-reset kernel orders the reset ids by a decoupled look-back (plain
-    # relaxed loads / stores of one status word per tile, no atomic at all), the post-reset kernel's logging reduction is
-    # finished by the warps that make the last class arrivals (release atomics, acquiring loads, no SC fence)
+    # the pre-reset kernel orders the reset ids by a decoupled look-back (plain relaxed loads / stores of one status word per
+    # tile: no atomic, no fence, no launch-wide tail); the post-reset kernel's logging reduction keeps one release ticket per
+    # LOG part and an acquiring LOAD by the thread that drew the last one (no SC fence)
     for name, body in _cluster_kernels(kernels, "pre").items():
         text = "\n".join(body)
         assert "ATOM" not in text, name
         assert "MEMBAR.SC" not in text, name
     for name, body in _cluster_kernels(kernels, "post").items():
         text = "\n".join(body)
-        assert len(re.findall(r"ATOM\.E\.ADD\.STRONG\.GPU", text)) >= 2, name
+        assert len(re.findall(r"ATOM\.E\.ADD\.STRONG\.GPU", text)) >= 1, name
         assert "MEMBAR.SC" not in text, name
 
 

@@ -100,7 +100,7 @@ for kind in ("pre", "post"):
         if all(int(d[c_, 58]) > 0 for d, c_ in zip(rows, fin)):
             tl = lambda a_, b_: med([float(d[c_, b_] - d[c_, a_]) for d, c_ in zip(rows, fin)]) / 1e3
             tl0 = lambda b_: med([float(d[c_, b_] - d[:, 0].min()) for d, c_ in zip(rows, fin)]) / 1e3
-            print(f"   logging finisher (globaltimer, us after the first entry): starts {tl0(56):.2f}, rows staged +{tl(56, 57):.2f}, "
+            print(f"   logging finisher CTA (one-level form; globaltimer, us after the first entry): starts {tl0(56):.2f}, rows staged +{tl(56, 57):.2f}, "
                   f"means written +{tl(57, 58):.2f}; its CTA ends {tl0(7):.2f}")
     ends = [torch.sort(d[:, 7] - d[:, 0].min()).values.float() for d in rows]
     q = lambda f: med([float(e_[int(f * (len(e_) - 1))]) for e_ in ends]) / 1e3
