@@ -41,6 +41,8 @@ VARIANTS: dict[str, list[str]] = {
     "v2dev": ["-DRL_V2_DEV_ONE=1"],   # cluster kernels for Go2-rough only: seconds to compile while iterating on them
     "stamps": ["-DRL_V2_STAMPS=1"],     # clock stamps per CTA / warp into the debug buffer (tools/v2_timeline.py)
     "unrolled": ["-DRL_V2_UNROLL=1"],   # A/B: term loops of the new kernels fully unrolled against the baked spec
+    "few0": ["-DRL_V2_DEV_ONE=1", "-DRL_V2_FEW_UNROLL=0"],   # A/B: the short loops rolled (Go2-rough only)
+    "stamps_few0": ["-DRL_V2_DEV_ONE=1", "-DRL_V2_STAMPS=1", "-DRL_V2_FEW_UNROLL=0"],
     # A/B: register budget of the new kernels (Go2-rough only) - resident CTAs per SM at 8 / 16 warps per CTA
     "occ6": ["-DRL_V2_DEV_ONE=1", "-DRL_V2_PRE_MINB8=6", "-DRL_V2_PRE_MINB16=3"],
     "occ8": ["-DRL_V2_DEV_ONE=1", "-DRL_V2_PRE_MINB8=8", "-DRL_V2_PRE_MINB16=4", "-DRL_V2_POST_MINB8=8", "-DRL_V2_POST_MINB16=4"],
