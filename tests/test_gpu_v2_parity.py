@@ -164,3 +164,45 @@ def test_v2_two_launch_step_matches_oracle(native_lib, monkeypatch, key, v2_cfg)
     monkeypatch.setattr("robot_lab_b200.engine.MdpStepEngine.close", counting_close)
     T.test_two_launch_step_in_reference_order(native_lib, key, 2048)
     assert launches and launches[-1] == 2, "the cluster kernels did not run"
+
+
+@pytest.mark.parametrize("v2_cfg", ["1x1x16", "1x1x8", "4x4x16"])
+def test_reset_ids_by_lookback_under_graph_replay(native_lib, v2_cfg):
+    """The pre-reset kernel orders the reset ids by a decoupled look-back whose status words carry an epoch that lives in
+    device memory: a captured graph replays the SAME kernel arguments, so every replay has to see a fresh epoch; engines
+    are reused across env counts (stale status words of a larger launch), and one tile / many windows of tiles are the
+    edge cases of the look-back. reset_ids == nonzero(done) ascending, n_reset == count, every time."""
+    cfg, spec = H.make_spec("go2_rough")
+    eng = _engine(spec, v2_cfg)
+    gmul = int(v2_cfg.split("x")[1])
+    rng = dict(seed=3, use_random_inputs=False, use_step_counter=True)
+    for n in (32 * gmul * 40, 32 * gmul, 32 * gmul * 129, 32 * gmul * 3):   # big, one tile (cluster), > 4 windows, small again
+        bufs = []
+        for i in range(3):
+            b = eng.new_buffers(n)
+            st = make_state(spec, n, seed=50 + i)
+            b.load_logical(st)
+            b.cmd_uniforms, b.obs_uniforms = None, [None, None]
+            bufs.append(b)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for b in bufs:                                   # scratch allocation outside the capture
+                eng.step_pre_reset(b, **rng)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for b in bufs:
+                    eng.step_pre_reset(b, **rng)
+            for rep in range(3):
+                for b in bufs:                               # poison the outputs: a replay has to rewrite them
+                    b.reset_ids.fill_(-7)
+                    b.n_reset.fill_(-1)
+                g.replay()
+                stream.synchronize()
+                for i, b in enumerate(bufs):
+                    done = (b.terminated.bool() | b.truncated.bool()).nonzero().flatten()
+                    k = int(b.n_reset.item())
+                    assert k == done.numel(), f"N={n} cfg={v2_cfg} replay {rep} set {i}: n_reset {k} != {done.numel()}"
+                    assert torch.equal(b.reset_ids[:k].long(), done), f"N={n} cfg={v2_cfg} replay {rep} set {i}: ids differ"
+        assert eng.cluster_config(n)["launches"] > 0, "the cluster kernels did not run"
+    eng.close()
