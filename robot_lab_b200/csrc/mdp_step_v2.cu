@@ -8,21 +8,27 @@
 //   RL_V2_PRE   = DONES | REWARDS | COMPACT          (termination terms, reward terms, ordered reset ids)
 //   RL_V2_POST  = RESET (masked) | COMMAND | OBS     (manager reset of the done envs, command.compute, both obs groups)
 //
-//   * a cluster of C CTAs owns G tiles (32 G consecutive envs); CTA r of the cluster is ROLE r: it evaluates the r-th
-//     share of the term list for all G tiles. A CTA has 16 warps = G tiles x W task slots; warp (tile, slot) runs the
-//     tasks of bin role*W + slot for its tile, lane = env. An SM therefore executes 1/C of the term code and every
-//     instruction serves G warps; the code an SM sees is the same in every launch (role = cluster rank, placement is
-//     deterministic), so it stays in that SM's instruction cache across launches;
-//   * load: ONE thread issues a 2-D TMA tensor-map copy per SoA field ({32 G envs} x {components} box of the [C, N]
-//     tensor, SASS UTMALDG) and one 1-D bulk copy for the contact-force rows; nobody else touches the load path;
-//   * contact-force norms (max over the history of |F_b|) are computed once per env by a prepass of the role that holds
-//     their consumers and cached in the record (every consumer used to recompute them in its own serial chain);
+//   * a configuration is (C, G, NW): a cluster of C CTAs owns G tiles (32 G consecutive envs); CTA r of the cluster is
+//     ROLE r and evaluates the r-th share of the task list for all G tiles with NW warps = G tiles x W task slots; warp
+//     (tile, slot) runs the tasks of bin role*W + slot for its tile, lane = env. What production launches use is
+//     C = G = 1 - one tile per CTA, 16 warps up to 16384 envs, 8 beyond; the cluster forms (2 x 2, 4 x 4: an SM executes
+//     1/C of the term code, every instruction serves G warps) are compiled, tested and were measured: not faster
+//     (profiles/r2_summary.md);
+//   * load: one 2-D TMA tensor-map copy per SoA field ({32 G envs} x {components} box of the [C, N] tensor, SASS
+//     UTMALDG), issued by lane 0 of EVERY warp (one thread issuing all of them serialised the descriptors' first-touch
+//     misses); the contact-force rows are not staged at all;
+//   * contact-force norms (max over the history of |F_b|) are computed once per env by a prepass that streams the force
+//     rows from global memory while the copies are in flight, and cached in the record (every consumer used to recompute
+//     them in its own serial chain);
 //   * results leave from registers: lane = env makes every SoA result row a coalesced 128-byte store by the warp that
-//     produced it - there is no store phase; the weighted term values meet in role 0's shared memory through DSMEM
-//     (st.shared::cluster) and one cluster barrier, where one warp per tile adds them up in manager order - the same
-//     summation order as the general kernel and the reference (RewardManager.compute [IL]);
-//   * the height-scan observation (187 of the 235 critic columns) never enters shared memory: every warp of the cluster
-//     streams env rows global -> registers -> global with lanes = columns while the TMA loads are still in flight.
+//     produced it - there is no store phase; the weighted term values meet in role 0's shared memory (in a cluster:
+//     through DSMEM st.shared::cluster and one cluster barrier), where one warp per tile adds them up in manager order -
+//     the same summation order as the general kernel and the reference (RewardManager.compute [IL]);
+//   * the ordered reset-id list has no launch-wide tail: decoupled look-back over one status word per tile
+//     (lookback_publish / lookback_resolve); the logging means of the reset keep one (a release ticket per LOG task, an
+//     acquiring load by the thread that drew the last one);
+//   * the height-scan observation (187 of the 235 critic columns) never enters shared memory: every warp streams env
+//     rows global -> registers -> global with lanes = columns while the TMA loads are still in flight.
 //
 // Same term functions (csrc/mdp_terms.cuh), same operand order as the general kernel: all results are bit-identical to
 // it (tests/test_gpu_v2_parity.py). Launches that do not qualify (ragged env counts, env-id lists, strided IsaacLab
