@@ -1002,7 +1002,7 @@ __device__ __forceinline__ EnvCtx make_ctx(const float* sm, const Layout& L, int
   c.g = quat_apply_inverse(c.qw, c.q, V3{0.f, 0.f, -1.f});
   c.vb = quat_apply_inverse(c.qw, c.q, c.vw);
   c.wb = quat_apply_inverse(c.qw, c.q, c.ww);
-  c.gate = clampf(-c.g.z, 0.f, 0.7f) / 0.7f;
+  c.gate = rl_div(clampf(-c.g.z, 0.f, 0.7f), 0.7f);   // through rl_div: a robot that is upside down has a zero numerator (special-operand path)
   c.c0 = SMF(L.cmd, 0); c.c1 = SMF(L.cmd, 1); c.c2 = SMF(L.cmd, 2);
   c.cmd_norm = sqrtf((c.c0 * c.c0 + c.c1 * c.c1) + c.c2 * c.c2);
   c.vxy_norm = sqrtf(c.vb.x * c.vb.x + c.vb.y * c.vb.y);
