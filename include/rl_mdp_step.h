@@ -380,6 +380,10 @@ int64_t rl_struct_sizeof(const char* name);
  * (> ~4700 envs) that second resident CTA is worth 1.5 x (profiles/r1_summary.md section 5). -1: invalid spec. */
 int64_t rl_tile_record_bytes(const RlStepSpec* spec);
 
+/* A context owns device scratch that its launches share (tickets and per-tile partials of the launch-wide reductions,
+ * the status words and the epoch of the reset-id look-back): the launches of ONE context must be ordered - one stream, or
+ * streams ordered by events, or one captured graph - like the manager calls of the ManagerBasedRLEnv they replace. Use one
+ * context per concurrently stepping env. Copies of inputs / results may run on other streams. */
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
