@@ -218,3 +218,65 @@ def test_ideal_pd_torque_is_the_textbook_law():
     assert app.item() == pytest.approx(6.5)
     comp, app = port.actuator_step(tab, torch.tensor([[2.0]]), torch.tensor([[0.0]]), torch.tensor([[0.0]]))
     assert comp.item() == pytest.approx(50.0) and app.item() == pytest.approx(23.5)   # clipped to the effort limit
+
+
+def test_contact_timer_fsm_against_an_event_log():
+    """ContactSensor air / contact timers [IL], a second formulation that shares no code with the vectorised restatement:
+    per foot, keep the LOG of contact flags per sub-step and derive the four timers from it by definition - current_*_time
+    is dt x the length of the current run of (no) contact, last_air_time is dt x (length + 1) of the most recent COMPLETED
+    air run (it ended with a touch-down, whose sub-step IsaacLab books to the air time), last_contact_time the same for
+    contact runs. Random force sequences around the
+    1 N threshold, including exact zeros and exact threshold values."""
+    import helpers as H
+    cfg, spec = H.make_spec("go2_rough")
+    from robot_lab_b200.synthetic import make_state
+
+    n, steps, dt, thr = 64, 40, 0.005, 1.0
+    st = make_state(spec, n, seed=11)
+    for k in ("current_air_time", "last_air_time", "current_contact_time", "last_contact_time"):
+        st[k] = torch.zeros_like(st[k])
+    names_h = list(spec.layout.hist_body_names)
+    t2h = [names_h.index(nm) for nm in spec.layout.time_body_names]
+    g = torch.Generator().manual_seed(5)
+    log = []   # per sub-step: [n, feet] bool
+    for s_ in range(steps):
+        f = torch.randn(n, spec.B, 3, generator=g) * 1.2
+        f[torch.rand(n, spec.B, generator=g) < 0.35] = 0.0                  # swing phases: exactly zero force
+        f[0, t2h[0]] = torch.tensor([0.6, 0.8, 0.0])                         # |F| == threshold exactly: not a contact (strict >)
+        out = port.contact_sensor_update(spec, st, f, dt, thr)
+        st = {**st, **out}
+        log.append(torch.linalg.vector_norm(f[:, t2h, :], dim=-1) > thr)   # fp32 like the sensor (in double |(0.6f, 0.8f, 0)| > 1)
+        flags = torch.stack(log)                                             # [s, n, feet]
+        for e in (0, 1, 7, 33, 63):
+            for j in range(len(t2h)):
+                seq = flags[:, e, j].tolist()
+                run, last_air, last_con = 1, 0, 0
+                # walk the log: runs of equal flags
+                runs = []
+                for i in range(1, len(seq)):
+                    if seq[i] == seq[i - 1]:
+                        run += 1
+                    else:
+                        runs.append((seq[i - 1], run))
+                        run = 1
+                cur_flag, cur_run = seq[-1], run
+                for fl, ln in runs:                                           # completed runs, oldest first
+                    # IsaacLab books the sub-step of the transition to the run that ENDS there
+                    # (last_air_time = current_air_time + dt at first contact): a completed run of ln flags lasted ln + 1 steps
+                    if fl:
+                        last_con = ln + 1
+                    else:
+                        last_air = ln + 1
+                # a run that started at step 0 with the timers at zero: IsaacLab only counts "first contact / first
+                # detached" when the previous timer was > 0, which holds for every completed run of length >= 1
+                want = {
+                    "current_air_time": 0.0 if cur_flag else cur_run * dt,
+                    "current_contact_time": cur_run * dt if cur_flag else 0.0,
+                    "last_air_time": last_air * dt,
+                    "last_contact_time": last_con * dt,
+                }
+                for k, v in want.items():
+                    got = float(st[k][e, j])
+                    assert abs(got - v) < 1e-6, f"sub-step {s_} env {e} foot {j} {k}: {got} != {v}"
+    # the exact-threshold foot never touched down
+    assert float(st["current_contact_time"][0, 0]) == 0.0
