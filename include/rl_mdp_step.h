@@ -383,7 +383,9 @@ int64_t rl_tile_record_bytes(const RlStepSpec* spec);
 /* A context owns device scratch that its launches share (tickets and per-tile partials of the launch-wide reductions,
  * the status words and the epoch of the reset-id look-back): the launches of ONE context must be ordered - one stream, or
  * streams ordered by events, or one captured graph - like the manager calls of the ManagerBasedRLEnv they replace. Use one
- * context per concurrently stepping env. Copies of inputs / results may run on other streams. */
+ * context per concurrently stepping env. Copies of inputs / results may run on other streams. The scratch grows (is
+ * re-allocated) when a launch brings more envs than any launch of the context before: make the first launches of a context
+ * at its full env count before capturing graphs - a graph captured earlier holds the old scratch pointers. */
 int rl_ctx_create(const RlStepSpec* spec, int device, RlCtx** out);
 void rl_ctx_destroy(RlCtx* ctx);
 
