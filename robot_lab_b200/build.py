@@ -29,7 +29,9 @@ STEP_HEADERS = [CSRC / "mdp_terms.cuh", CSRC / "mdp_ctx.h"]   # shared by the tw
 OUT = PKG / "_lib" / "libmdpstep.so"
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--split-compile=0", "-lineinfo", "-fmad=false", "-std=c++17",
+    # no --split-compile: measured in round 2, it makes the generated code differ from build to build (the same source gave
+    # step kernels 5 - 7 % apart) for a compile-time gain of seconds; without it two builds are bit-identical
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", f"-I{ROOT / 'include'}", f"-I{CSRC}",
 ]
 
